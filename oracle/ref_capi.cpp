@@ -1,0 +1,354 @@
+/* oracle/ref_capi.cpp -- TEST INFRASTRUCTURE ONLY (never linked into the product library).
+ *
+ * A thin extern "C" accessor over the UNMODIFIED reference (x265 3.5+1) compiled from
+ * /root/reference by oracle/Makefile.  It lets tests/ and bench.py's cpu_baseline /
+ * `--impl reference` arm call the reference's own C primitive table
+ * (source/common/primitives.h:237 `struct EncoderPrimitives`, filled by
+ * x265_setup_primitives(), source/common/primitives.cpp:248) and the reference's own
+ * MotionEstimate class (source/encoder/motion.h:37, motion.cpp:739) through ctypes.
+ *
+ * This file is OUR code; it includes the reference headers where they lie and contains no
+ * reference source.  Built twice: X265_NS=x265 (8-bit) and X265_NS=x265_10bit.
+ */
+#include "common.h"
+#include "primitives.h"
+#include "constants.h"
+#include "motion.h"
+#include "bitcost.h"
+#include "lowres.h"
+#include "x265.h"
+
+#include <thread>
+#include <vector>
+#include <cstring>
+
+using namespace X265_NS;
+
+namespace {
+bool g_init = false;
+void ensure_init()
+{
+    if (g_init) return;
+    static x265_param param;
+    x265_param_default(&param);
+    param.logLevel = X265_LOG_NONE;
+    x265_setup_primitives(&param);   /* primitives.cpp:248: C table + aliases (ENABLE_ASSEMBLY=0) */
+    MotionEstimate::initScales();    /* motion.cpp:123 */
+    g_init = true;
+}
+
+/* run fn(i) for i in [0,n) on `threads` std::threads, disjoint contiguous ranges */
+template<class F> void parallel_for(int64_t n, int threads, F fn)
+{
+    if (threads <= 1 || n < 2) { for (int64_t i = 0; i < n; i++) fn(i, 0); return; }
+    std::vector<std::thread> pool;
+    int64_t chunk = (n + threads - 1) / threads;
+    for (int t = 0; t < threads; t++)
+    {
+        int64_t lo = t * chunk, hi = lo + chunk < n ? lo + chunk : n;
+        if (lo >= hi) break;
+        pool.emplace_back([=]() { for (int64_t i = lo; i < hi; i++) fn(i, t); });
+    }
+    for (auto& th : pool) th.join();
+}
+}
+
+extern "C" {
+
+int ref_depth(void) { return X265_DEPTH; }
+int ref_pixel_bytes(void) { return (int)sizeof(pixel); }
+int ref_sse_bytes(void) { return (int)sizeof(sse_t); }
+void ref_init(void) { ensure_init(); }
+
+/* partitionFromSizes() LUT, primitives.h:435 */
+int ref_partition_from_sizes(int w, int h) { ensure_init(); return partitionFromSizes(w, h); }
+
+/* ---- pixel compare family (primitives.h:133 pixelcmp_t) --------------------------------
+ * fam: 0 pu[idx].sad  1 pu[idx].satd  2 cu[idx].sa8d  3 cu[idx].psy_cost_pp
+ *      4 chroma[csp=1].pu[idx].satd   5 chroma[1].cu[idx].sa8d   6 chroma[2].cu[idx].sa8d */
+static pixelcmp_t get_cmp(int fam, int idx)
+{
+    switch (fam)
+    {
+    case 0: return primitives.pu[idx].sad;
+    case 1: return primitives.pu[idx].satd;
+    case 2: return primitives.cu[idx].sa8d;
+    case 3: return primitives.cu[idx].psy_cost_pp;
+    case 4: return primitives.chroma[X265_CSP_I420].pu[idx].satd;
+    case 5: return primitives.chroma[X265_CSP_I420].cu[idx].sa8d;
+    case 6: return primitives.chroma[X265_CSP_I422].cu[idx].sa8d;
+    }
+    return NULL;
+}
+
+int ref_pixelcmp(int fam, int idx, const void* a, intptr_t sa, const void* b, intptr_t sb)
+{
+    ensure_init();
+    pixelcmp_t f = get_cmp(fam, idx);
+    return f ? f((const pixel*)a, sa, (const pixel*)b, sb) : -1;
+}
+
+/* n independent block pairs: a = planeA + offA[i], b = planeB + offB[i] (element offsets) */
+int ref_pixelcmp_batch(int fam, int idx, const void* planeA, intptr_t sa, const void* planeB, intptr_t sb,
+                       const int64_t* offA, const int64_t* offB, int64_t n, int32_t* out, int threads)
+{
+    ensure_init();
+    pixelcmp_t f = get_cmp(fam, idx);
+    if (!f) return -1;
+    const pixel* A = (const pixel*)planeA; const pixel* B = (const pixel*)planeB;
+    parallel_for(n, threads, [=](int64_t i, int) { out[i] = f(A + offA[i], sa, B + offB[i], sb); });
+    return 0;
+}
+
+/* fam: 0 cu[idx].sse_pp (pixel,pixel)  1 cu[idx].sse_ss (int16,int16)  2 cu[idx].ssd_s (int16; b ignored) */
+uint64_t ref_sse(int fam, int idx, const void* a, intptr_t sa, const void* b, intptr_t sb)
+{
+    ensure_init();
+    switch (fam)
+    {
+    case 0: return primitives.cu[idx].sse_pp((const pixel*)a, sa, (const pixel*)b, sb);
+    case 1: return primitives.cu[idx].sse_ss((const int16_t*)a, sa, (const int16_t*)b, sb);
+    case 2: return primitives.cu[idx].ssd_s[NONALIGNED]((const int16_t*)a, sa);
+    }
+    return 0;
+}
+
+int ref_sse_batch(int fam, int idx, const void* planeA, intptr_t sa, const void* planeB, intptr_t sb,
+                  const int64_t* offA, const int64_t* offB, int64_t n, uint64_t* out, int threads)
+{
+    ensure_init();
+    parallel_for(n, threads, [=](int64_t i, int) {
+        if (fam == 0) out[i] = primitives.cu[idx].sse_pp((const pixel*)planeA + offA[i], sa, (const pixel*)planeB + offB[i], sb);
+        else if (fam == 1) out[i] = primitives.cu[idx].sse_ss((const int16_t*)planeA + offA[i], sa, (const int16_t*)planeB + offB[i], sb);
+        else out[i] = primitives.cu[idx].ssd_s[NONALIGNED]((const int16_t*)planeA + offA[i], sa);
+    });
+    return 0;
+}
+
+/* sad_x3 / sad_x4 (primitives.h:139-140): fenc has the hard-wired FENC_STRIDE (pixel.cpp:89,113) */
+void ref_sad_x3(int part, const void* fenc, const void* r0, const void* r1, const void* r2, intptr_t stride, int32_t* res)
+{
+    ensure_init();
+    primitives.pu[part].sad_x3((const pixel*)fenc, (const pixel*)r0, (const pixel*)r1, (const pixel*)r2, stride, res);
+}
+void ref_sad_x4(int part, const void* fenc, const void* r0, const void* r1, const void* r2, const void* r3, intptr_t stride, int32_t* res)
+{
+    ensure_init();
+    primitives.pu[part].sad_x4((const pixel*)fenc, (const pixel*)r0, (const pixel*)r1, (const pixel*)r2, (const pixel*)r3, stride, res);
+}
+
+/* ads (primitives.h:138) */
+int ref_ads(int part, int* encDC, uint32_t* sums, int delta, uint16_t* costMvX, int16_t* mvs, int width, int thresh)
+{
+    ensure_init();
+    return primitives.pu[part].ads(encDC, sums, delta, costMvX, mvs, width, thresh);
+}
+
+/* ---- transforms (primitives.h:153-162) -------------------------------------------------
+ * idx 0..3 = cu[BLOCK_4x4..32x32].dct / idct, idx 4 = dst4x4 / idst4x4 */
+void ref_dct(int idx, const int16_t* src, int16_t* dst, intptr_t srcStride)
+{
+    ensure_init();
+    (idx == 4 ? primitives.dst4x4 : primitives.cu[idx].dct)(src, dst, srcStride);
+}
+void ref_idct(int idx, const int16_t* src, int16_t* dst, intptr_t dstStride)
+{
+    ensure_init();
+    (idx == 4 ? primitives.idst4x4 : primitives.cu[idx].idct)(src, dst, dstStride);
+}
+/* n blocks, src block i at src + i*srcBlockStride (elements), contiguous dst blocks */
+void ref_dct_batch(int idx, const int16_t* src, int64_t srcBlockStride, intptr_t srcStride, int16_t* dst, int64_t n, int threads)
+{
+    ensure_init();
+    int sz = idx == 4 ? 4 : (4 << idx);
+    dct_t f = idx == 4 ? primitives.dst4x4 : primitives.cu[idx].dct;
+    parallel_for(n, threads, [=](int64_t i, int) { f(src + i * srcBlockStride, dst + i * sz * sz, srcStride); });
+}
+void ref_idct_batch(int idx, const int16_t* src, int16_t* dst, int64_t dstBlockStride, intptr_t dstStride, int64_t n, int threads)
+{
+    ensure_init();
+    int sz = idx == 4 ? 4 : (4 << idx);
+    idct_t f = idx == 4 ? primitives.idst4x4 : primitives.cu[idx].idct;
+    parallel_for(n, threads, [=](int64_t i, int) { f(src + i * sz * sz, dst + i * dstBlockStride, dstStride); });
+}
+uint32_t ref_quant(const int16_t* coef, const int32_t* quantCoeff, int32_t* deltaU, int16_t* qCoef, int qBits, int add, int numCoeff)
+{
+    ensure_init();
+    return primitives.quant(coef, quantCoeff, deltaU, qCoef, qBits, add, numCoeff);
+}
+uint32_t ref_nquant(const int16_t* coef, const int32_t* quantCoeff, int16_t* qCoef, int qBits, int add, int numCoeff)
+{
+    ensure_init();
+    return primitives.nquant(coef, quantCoeff, qCoef, qBits, add, numCoeff);
+}
+void ref_dequant_normal(const int16_t* quantCoef, int16_t* coef, int num, int scale, int shift)
+{
+    ensure_init();
+    primitives.dequant_normal(quantCoef, coef, num, scale, shift);
+}
+void ref_dequant_scaling(const int16_t* src, const int32_t* dequantCoef, int16_t* dst, int num, int mcqp_miper, int shift)
+{
+    ensure_init();
+    primitives.dequant_scaling(src, dequantCoef, dst, num, mcqp_miper, shift);
+}
+int ref_count_nonzero(int idx, const int16_t* q) { ensure_init(); return primitives.cu[idx].count_nonzero(q); }
+uint32_t ref_copy_cnt(int idx, int16_t* coeff, const int16_t* residual, intptr_t stride) { ensure_init(); return primitives.cu[idx].copy_cnt(coeff, residual, stride); }
+void ref_denoise_dct(int16_t* dctCoef, uint32_t* resSum, const uint16_t* offset, int numCoeff) { ensure_init(); primitives.denoiseDct(dctCoef, resSum, offset, numCoeff); }
+
+/* constant tables (constants.cpp:250-344) so tests can pin the product's generated tables */
+const int16_t* ref_dct_table(int idx)
+{
+    switch (idx) { case 0: return &g_t4[0][0]; case 1: return &g_t8[0][0]; case 2: return &g_t16[0][0]; case 3: return &g_t32[0][0]; }
+    return NULL;
+}
+const int16_t* ref_luma_filter(void) { return &g_lumaFilter[0][0]; }
+const int16_t* ref_chroma_filter(void) { return &g_chromaFilter[0][0]; }
+double ref_lambda(int qp) { return x265_lambda_tab[qp]; }
+double ref_lambda2(int qp) { return x265_lambda2_tab[qp]; }
+
+/* ---- interpolation (primitives.h:176-182) ----------------------------------------------
+ * csp < 0: luma pu[part].luma_*; csp >= 0: chroma[csp].pu[part].filter_*
+ * kind: 0 hpp 1 hps 2 vpp 3 vps 4 vsp 5 vss 6 hvpp(luma only) 7 p2s */
+void ref_interp(int kind, int csp, int part, const void* src, intptr_t srcStride, void* dst, intptr_t dstStride,
+                int coeffIdx, int arg2 /* isRowExt for hps, idxY for hvpp */)
+{
+    ensure_init();
+    if (csp < 0)
+    {
+        EncoderPrimitives::PU& p = primitives.pu[part];
+        switch (kind)
+        {
+        case 0: p.luma_hpp((const pixel*)src, srcStride, (pixel*)dst, dstStride, coeffIdx); break;
+        case 1: p.luma_hps((const pixel*)src, srcStride, (int16_t*)dst, dstStride, coeffIdx, arg2); break;
+        case 2: p.luma_vpp((const pixel*)src, srcStride, (pixel*)dst, dstStride, coeffIdx); break;
+        case 3: p.luma_vps((const pixel*)src, srcStride, (int16_t*)dst, dstStride, coeffIdx); break;
+        case 4: p.luma_vsp((const int16_t*)src, srcStride, (pixel*)dst, dstStride, coeffIdx); break;
+        case 5: p.luma_vss((const int16_t*)src, srcStride, (int16_t*)dst, dstStride, coeffIdx); break;
+        case 6: p.luma_hvpp((const pixel*)src, srcStride, (pixel*)dst, dstStride, coeffIdx, arg2); break;
+        case 7: p.convert_p2s[NONALIGNED]((const pixel*)src, srcStride, (int16_t*)dst, dstStride); break;
+        }
+    }
+    else
+    {
+        EncoderPrimitives::Chroma::PUChroma& p = primitives.chroma[csp].pu[part];
+        switch (kind)
+        {
+        case 0: p.filter_hpp((const pixel*)src, srcStride, (pixel*)dst, dstStride, coeffIdx); break;
+        case 1: p.filter_hps((const pixel*)src, srcStride, (int16_t*)dst, dstStride, coeffIdx, arg2); break;
+        case 2: p.filter_vpp((const pixel*)src, srcStride, (pixel*)dst, dstStride, coeffIdx); break;
+        case 3: p.filter_vps((const pixel*)src, srcStride, (int16_t*)dst, dstStride, coeffIdx); break;
+        case 4: p.filter_vsp((const int16_t*)src, srcStride, (pixel*)dst, dstStride, coeffIdx); break;
+        case 5: p.filter_vss((const int16_t*)src, srcStride, (int16_t*)dst, dstStride, coeffIdx); break;
+        case 7: p.p2s[NONALIGNED]((const pixel*)src, srcStride, (int16_t*)dst, dstStride); break;
+        }
+    }
+}
+int ref_interp_available(int kind, int csp, int part)
+{
+    ensure_init();
+    if (csp < 0) return 1;
+    EncoderPrimitives::Chroma::PUChroma& p = primitives.chroma[csp].pu[part];
+    switch (kind)
+    {
+    case 0: return p.filter_hpp != NULL; case 1: return p.filter_hps != NULL; case 2: return p.filter_vpp != NULL;
+    case 3: return p.filter_vps != NULL; case 4: return p.filter_vsp != NULL; case 5: return p.filter_vss != NULL;
+    case 7: return p.p2s[NONALIGNED] != NULL;
+    }
+    return 0;
+}
+
+/* ---- intra (primitives.h:143-145) ------------------------------------------------------ */
+void ref_intra_pred(int sizeIdx, int mode, void* dst, intptr_t dstStride, const void* srcPix, int bFilter)
+{
+    ensure_init();
+    primitives.cu[sizeIdx].intra_pred[mode]((pixel*)dst, dstStride, (const pixel*)srcPix, mode, bFilter);
+}
+void ref_intra_filter(int sizeIdx, const void* ref, void* filtered)
+{
+    ensure_init();
+    primitives.cu[sizeIdx].intra_filter((const pixel*)ref, (pixel*)filtered);
+}
+
+/* ---- glue ------------------------------------------------------------------------------- */
+void ref_pixelavg_pp(int part, void* dst, intptr_t ds, const void* s0, intptr_t ss0, const void* s1, intptr_t ss1)
+{
+    ensure_init();
+    primitives.pu[part].pixelavg_pp[NONALIGNED]((pixel*)dst, ds, (const pixel*)s0, ss0, (const pixel*)s1, ss1, 32);
+}
+void ref_sub_ps(int idx, int16_t* dst, intptr_t ds, const void* s0, const void* s1, intptr_t ss0, intptr_t ss1)
+{
+    ensure_init();
+    primitives.cu[idx].sub_ps(dst, ds, (const pixel*)s0, (const pixel*)s1, ss0, ss1);
+}
+void ref_add_ps(int idx, void* dst, intptr_t ds, const void* s0, const int16_t* s1, intptr_t ss0, intptr_t ss1)
+{
+    ensure_init();
+    primitives.cu[idx].add_ps[NONALIGNED]((pixel*)dst, ds, (const pixel*)s0, s1, ss0, ss1);
+}
+void ref_frame_init_lowres(const void* src0, void* dst0, void* dsth, void* dstv, void* dstc,
+                           intptr_t srcStride, intptr_t dstStride, int width, int height)
+{
+    ensure_init();
+    primitives.frameInitLowres((const pixel*)src0, (pixel*)dst0, (pixel*)dsth, (pixel*)dstv, (pixel*)dstc, srcStride, dstStride, width, height);
+}
+uint64_t ref_var(int idx, const void* pix, intptr_t stride) { ensure_init(); return primitives.cu[idx].var((const pixel*)pix, stride); }
+
+/* ---- BitCost table (bitcost.cpp:31-110): cost[i] for i in [-2*BC_MAX_MV, 2*BC_MAX_MV] --- */
+struct BitCostPeek : public BitCost { const uint16_t* table() const { return m_cost; } };
+void ref_bitcost_table(int qp, uint16_t* out /* 4*32768+1 entries, out[2*32768+i] = cost[i] */)
+{
+    ensure_init();
+    BitCostPeek bc; bc.setQP(qp);
+    memcpy(out, bc.table() - 2 * 32768, sizeof(uint16_t) * (4 * 32768 + 1));
+}
+
+/* ---- MotionEstimate::motionEstimate (motion.cpp:739) ------------------------------------
+ * One descriptor per PU search, luma only (the lookahead-style setSourcePU, motion.cpp:167,
+ * which leaves ctuAddr = -1 so no PicYuv is needed).  All MVs as {x,y} int32 pairs. */
+struct RefMEJob
+{
+    int32_t  puX, puY;        /* top-left of the PU in the fenc / ref planes (pixels)        */
+    int32_t  w, h;            /* PU size                                                      */
+    int32_t  mvminX, mvminY, mvmaxX, mvmaxY;   /* full-pel, inclusive (motion.cpp:740-741)   */
+    int32_t  mvpX, mvpY;      /* qpel predictor                                               */
+    int32_t  numCand;         /* <= 8                                                         */
+    int32_t  mvc[8][2];       /* qpel candidates                                              */
+    int32_t  outMvX, outMvY;  /* OUT: qpel                                                    */
+    int32_t  outCost;         /* OUT                                                          */
+};
+
+int ref_me_batch(const void* fencPlane, intptr_t fencStride, const void* refPlane, intptr_t refStride,
+                 RefMEJob* jobs, int64_t n, int searchMethod, int subpelRefine, int merange, int qp,
+                 int maxSlices, int threads)
+{
+    ensure_init();
+    { BitCost warm; warm.setQP(qp); }            /* build the shared cost table before threading */
+    int nt = threads < 1 ? 1 : threads;
+    std::vector<MotionEstimate*> mes(nt);
+    for (int t = 0; t < nt; t++)
+    {
+        mes[t] = new MotionEstimate;
+        mes[t]->init(X265_CSP_I400);             /* motion.cpp:118, luma-only fencPUYuv */
+        mes[t]->setQP(qp);
+    }
+    parallel_for(n, nt, [&](int64_t i, int t) {
+        RefMEJob& j = jobs[i];
+        MotionEstimate& me = *mes[t];
+        ReferencePlanes ref;
+        ref.fpelPlane[0] = (pixel*)refPlane;
+        ref.lumaStride = refStride;
+        ref.isLowres = false;
+        intptr_t off = j.puX + (intptr_t)j.puY * refStride;
+        /* fenc and ref planes must share one stride for this entry point (blockOffset is reused) */
+        me.setSourcePU((pixel*)fencPlane, fencStride, off, j.w, j.h, searchMethod, searchMethod, searchMethod, subpelRefine);
+        MV mvmin(j.mvminX, j.mvminY), mvmax(j.mvmaxX, j.mvmaxY), mvp(j.mvpX, j.mvpY), out(0, 0);
+        MV mvc[8];
+        for (int k = 0; k < j.numCand; k++) mvc[k] = MV(j.mvc[k][0], j.mvc[k][1]);
+        j.outCost = me.motionEstimate(&ref, mvmin, mvmax, mvp, j.numCand, mvc, merange, out, (uint32_t)maxSlices);
+        j.outMvX = out.x; j.outMvY = out.y;
+    });
+    for (int t = 0; t < nt; t++) delete mes[t];
+    return 0;
+}
+
+} /* extern "C" */

@@ -1,0 +1,32 @@
+/* oracle/x265_oracle.h -- TEST INFRASTRUCTURE ONLY.
+ *
+ * Plain-C restatement of the reference algorithms on the hot path (x265 3.5+1,
+ * msg7086/x265-Yuuki-Asuna).  Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may load this; the product library never does.
+ * Parity status: PINNED -- every function here is checked against the reference itself
+ * (oracle/_ref/libx265ref{8,10}.so compiled from /root/reference by oracle/Makefile) in
+ * tests/test_oracle_vs_ref.py and against the committed fixtures in tests/golden/.
+ *
+ * All functions take `depth` (8, 10 or 12).  depth == 8 -> pixel is uint8_t, else uint16_t
+ * (common/common.h:126-142).  Strides are in elements.
+ */
+#ifndef X265_ORACLE_H
+#define X265_ORACLE_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int      orc_sad(int depth, int w, int h, const void* a, intptr_t sa, const void* b, intptr_t sb);
+void     orc_sad_xn(int depth, int K, int w, int h, const void* fenc, const void* const* refs, intptr_t refStride, int32_t* res);
+int      orc_satd(int depth, int w, int h, const void* a, intptr_t sa, const void* b, intptr_t sb);
+/* per16 != 0: round once per 16x16 (sa8d_16x16 / sa8d16<>), else per 8x8 (sa8d_8x8 / sa8d8<>) */
+int      orc_sa8d(int depth, int w, int h, int per16, const void* a, intptr_t sa, const void* b, intptr_t sb);
+uint64_t orc_sse_pp(int depth, int w, int h, const void* a, intptr_t sa, const void* b, intptr_t sb);
+uint64_t orc_sse_ss(int depth, int w, int h, const int16_t* a, intptr_t sa, const int16_t* b, intptr_t sb);
+uint64_t orc_ssd_s(int depth, int size, const int16_t* a, intptr_t sa);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,131 @@
+"""GPU parity: block-compare kernels (through the C ABI) vs the oracle on TestBench-shaped
+fixtures -- all 25 PU sizes x {sad, satd}, all CU sizes x {sa8d, sse_pp, sse_ss, ssd_s}, 8- and
+10-bit, random / all-min / all-max buffers, unaligned offsets and strides.  Bit-exact."""
+import importlib
+
+import numpy as np
+import pytest
+
+from util import (CU_SIZES, LUMA_PU_SIZES, STRIDE, block_offsets, orc_cmp, pixel_buffers, ref_cmp, short_buffers)
+
+pkg = importlib.import_module("x265-yuuki-asuna_b200")
+pytestmark = pytest.mark.gpu
+
+KIND = {"sad": pkg.CMP_SAD, "satd": pkg.CMP_SATD, "sa8d": pkg.CMP_SA8D, "sa8d8": pkg.CMP_SA8D8,
+        "sse_pp": pkg.CMP_SSE_PP, "sse_ss": pkg.CMP_SSE_SS, "ssd_s": pkg.CMP_SSD_S}
+
+
+def _check(ctx, kind, depth, w, h, A, sa, B, sb, offA, offB):
+    got = ctx.pixelcmp_host(KIND[kind], depth, w, h, A, sa, B, sb, offA, offB)
+    exp = orc_cmp(kind, depth, w, h, A, sa, B, sb, offA, offB)
+    assert [int(v) for v in got] == exp, (kind, depth, w, h)
+    r = ref_cmp(kind, depth, w, h, A, sa, B, sb, offA, offB)
+    if r is not None:
+        assert [int(v) for v in got] == r, ("vs reference", kind, depth, w, h)
+
+
+@pytest.mark.parametrize("depth", [8, 10])
+@pytest.mark.parametrize("kind", ["sad", "satd"])
+def test_pu_compare_all_sizes(ctx, depth, kind):
+    bufs = pixel_buffers(depth)
+    offs = block_offsets()
+    for (w, h) in LUMA_PU_SIZES:
+        for ia, ib in [(0, 0), (0, 1), (0, 2), (1, 2)]:
+            _check(ctx, kind, depth, w, h, bufs[ia], STRIDE, bufs[ib], STRIDE, offs, offs[::-1].copy())
+
+
+@pytest.mark.parametrize("depth", [8, 10])
+def test_pu_compare_unaligned_ref(ctx, depth):
+    """reference block at odd offsets and stride 59 (pixelharness.cpp:150 uses FENC_STRIDE - 5)."""
+    bufs = pixel_buffers(depth, seed=99)
+    offa = block_offsets()
+    offb = offa + np.arange(len(offa)) % 7 + 1
+    for (w, h) in LUMA_PU_SIZES:
+        for kind in ("sad", "satd"):
+            _check(ctx, kind, depth, w, h, bufs[0], STRIDE, bufs[0][::-1].copy(), 59, offa, offb)
+
+
+@pytest.mark.parametrize("depth", [8, 10])
+@pytest.mark.parametrize("kind", ["sa8d", "sse_pp"])
+def test_cu_compare(ctx, depth, kind):
+    bufs = pixel_buffers(depth, seed=7)
+    offs = block_offsets()
+    for s in CU_SIZES:
+        for ia, ib in [(0, 0), (0, 1), (0, 2), (1, 2)]:
+            _check(ctx, kind, depth, s, s, bufs[ia], STRIDE, bufs[ib], STRIDE, offs, offs[::-1].copy() + 3)
+
+
+@pytest.mark.parametrize("depth", [8, 10])
+def test_sa8d8_chroma_aliases(ctx, depth):
+    bufs = pixel_buffers(depth, seed=8)
+    offs = block_offsets()
+    for (w, h) in [(8, 8), (8, 16), (16, 8), (32, 32)]:
+        _check(ctx, "sa8d8", depth, w, h, bufs[0], STRIDE, bufs[0], 61, offs, offs + 5)
+    for (w, h) in [(16, 32), (32, 64), (32, 16)]:       # sa8d16<16,32> etc. (pixel.cpp:1324-1325)
+        _check(ctx, "sa8d", depth, w, h, bufs[0], STRIDE, bufs[0], 61, offs, offs + 5)
+
+
+@pytest.mark.parametrize("depth", [8, 10])
+@pytest.mark.parametrize("kind", ["sse_ss", "ssd_s"])
+def test_short_compare(ctx, depth, kind):
+    for full in (False, True):
+        bufs = short_buffers(depth, full_range=full)
+        offs = block_offsets()
+        for s in CU_SIZES:
+            for ia, ib in [(0, 0), (0, 1), (1, 2)]:
+                _check(ctx, kind, depth, s, s, bufs[ia], STRIDE, bufs[ib], STRIDE, offs, offs[::-1].copy() + 1)
+
+
+@pytest.mark.parametrize("depth", [8, 10])
+def test_sad_x3_x4(ctx, depth):
+    """pu[].sad_x3 / sad_x4 (pixel.cpp:74-119): cached 64-stride fenc vs K refs at stride 59."""
+    import oracle
+    import ctypes
+    from util import vpo, ssz
+    bufs = pixel_buffers(depth, seed=21)
+    fenc_src, ref = bufs[0], bufs[0][::-1].copy()
+    n = 12
+    L = oracle.orc()
+    dRef = ctx.to_device(ref)
+    for (w, h) in LUMA_PU_SIZES:
+        for K in (3, 4):
+            fenc = np.zeros(n * 64 * 64, dtype=fenc_src.dtype)
+            for i in range(n):
+                blk = fenc_src[32 * i: 32 * i + 64 * 64]
+                fenc[i * 4096:(i + 1) * 4096] = blk
+            roff = (np.arange(n * K, dtype=np.int64) * 13 + 3) % 2000
+            dF, dO = ctx.to_device(fenc), ctx.to_device(roff)
+            dR = ctx.empty(n * K * 4)
+            ctx.sad_xn_dev(depth, K, w, h, dF, 4096, dRef, 59, dO, n, dR)
+            got = dR.download(np.int32).reshape(n, K)
+            for i in range(n):
+                ptrs = (ctypes.c_void_p * K)(*[vpo(ref, roff[i * K + k]).value for k in range(K)])
+                res = (ctypes.c_int32 * K)()
+                L.orc_sad_xn(depth, K, w, h, vpo(fenc, i * 4096), ptrs, ssz(59), res)
+                assert list(res) == list(got[i]), (w, h, K, i)
+            for b in (dF, dO, dR):
+                b.free()
+    dRef.free()
+
+
+def test_grid_mode_with_mv_field(ctx):
+    """grid mode = cost-at-predictor for every PU of a frame (motion.cpp:771-796 first step)."""
+    rng = np.random.default_rng(5)
+    W, H, S, pad = 256, 128, 320, 32
+    cur = rng.integers(0, 256, (H + 2 * pad) * S, dtype=np.int64).astype(np.uint8)
+    ref = rng.integers(0, 256, (H + 2 * pad) * S, dtype=np.int64).astype(np.uint8)
+    base = pad * S + pad
+    for (w, h) in [(8, 8), (16, 16), (32, 32), (64, 64), (32, 16)]:
+        cols, rows = W // w, H // h
+        n = cols * rows
+        mv = rng.integers(-16, 17, (n, 2), dtype=np.int64).astype(np.int16)
+        dC, dR, dMv, dOut = ctx.to_device(cur[base:]), ctx.to_device(ref), ctx.to_device(mv), ctx.empty(n * 4)
+        # A is passed pre-offset; B via a device pointer offset
+        ctx.pixelcmp_dev(pkg.CMP_SAD, 8, w, h, dC, S, dR.ptr + base, S, None, None, n, dOut, dMv=dMv, grid_cols=cols)
+        got = dOut.download(np.int32)
+        offA = np.array([base + (i // cols) * h * S + (i % cols) * w for i in range(n)], dtype=np.int64)
+        offB = offA + mv[:, 0].astype(np.int64) + mv[:, 1].astype(np.int64) * S
+        exp = orc_cmp("sad", 8, w, h, cur, S, ref, S, offA, offB)
+        assert list(map(int, got)) == exp, (w, h)
+        for b in (dC, dR, dMv, dOut):
+            b.free()

@@ -1,0 +1,193 @@
+// capi.cu -- the extern "C" shim of libx265b200.so (declared in include/x265b200.h).
+// Context/memory management plus the *_dev / *_host entry points that forward to the
+// kernel launchers in the other translation units.  No CPU fallback: every compute entry
+// point needs a live CUDA context and fails loudly otherwise.
+#include "common.cuh"
+#include "x265b200.h"
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+namespace x265b200 {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...)
+{
+    va_list ap; va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int check(cudaError_t e, const char* what)
+{
+    if (e == cudaSuccess) return 0;
+    set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+    return -1;
+}
+
+// scratch management for host-pointer entry points ------------------------------------------
+int scratch_dev(Ctx* ctx, int slot, size_t bytes, void** out)
+{
+    if (ctx->dScratchBytes[slot] < bytes)
+    {
+        if (ctx->dScratch[slot]) { X265B200_CHECK(cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->dScratch[slot]); ctx->dScratch[slot] = nullptr; ctx->dScratchBytes[slot] = 0; }
+        size_t cap = bytes + bytes / 4 + 256;
+        X265B200_CHECK(cudaMalloc(&ctx->dScratch[slot], cap));
+        ctx->dScratchBytes[slot] = cap;
+    }
+    *out = ctx->dScratch[slot];
+    return 0;
+}
+
+int scratch_pinned(Ctx* ctx, int slot, size_t bytes, void** out)
+{
+    if (ctx->hPinnedBytes[slot] < bytes)
+    {
+        if (ctx->hPinned[slot]) { X265B200_CHECK(cudaStreamSynchronize(ctx->stream)); cudaFreeHost(ctx->hPinned[slot]); ctx->hPinned[slot] = nullptr; ctx->hPinnedBytes[slot] = 0; }
+        size_t cap = bytes + bytes / 4 + 256;
+        X265B200_CHECK(cudaMallocHost(&ctx->hPinned[slot], cap));
+        ctx->hPinnedBytes[slot] = cap;
+    }
+    *out = ctx->hPinned[slot];
+    return 0;
+}
+
+// H2D of an arbitrary (possibly pageable) host buffer into scratch slot `slot`
+int stage_in(Ctx* ctx, int slot, const void* host, size_t bytes, void** dev)
+{
+    if (scratch_dev(ctx, slot, bytes ? bytes : 1, dev)) return -1;
+    if (bytes) X265B200_CHECK(cudaMemcpyAsync(*dev, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+// forward declarations of launchers -----------------------------------------------------------
+int pixelcmp_dev(Ctx*, int kind, int depth, int w, int h, const void* A, int64_t strideA, const void* B, int64_t strideB,
+                 const int64_t* offA, const int64_t* offB, const int16_t* mv, int gridCols, int64_t n, void* out);
+int sad_xn_dev(Ctx*, int depth, int K, int w, int h, const void* fenc, int64_t fencBlockStride,
+               const void* ref, int64_t refStride, const int64_t* refOff, int64_t n, int32_t* res);
+
+} // namespace x265b200
+
+using namespace x265b200;
+
+struct x265b200_ctx { Ctx c; };
+
+#define CTX(ctx) (&(ctx)->c)
+#define REQUIRE_CTX(ctx) do { if (!(ctx)) { set_error("null x265b200 context (CUDA backend not initialised; there is no CPU fallback)"); return -1; } \
+                              if (check(cudaSetDevice((ctx)->c.device), "cudaSetDevice")) return -1; } while (0)
+
+extern "C" {
+
+int x265b200_version(void) { return 100; }
+const char* x265b200_last_error(void) { return g_err; }
+
+int x265b200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int x265b200_create(int device, void* stream, x265b200_ctx** out)
+{
+    if (!out) { set_error("x265b200_create: out == NULL"); return -1; }
+    *out = nullptr;
+    int n = x265b200_device_count();
+    if (n <= 0) { set_error("x265b200_create: no CUDA device visible; this backend has no CPU fallback"); return -1; }
+    if (device < 0 || device >= n) { set_error("x265b200_create: device %d out of range [0,%d)", device, n); return -1; }
+    X265B200_CHECK(cudaSetDevice(device));
+    x265b200_ctx* ctx = new x265b200_ctx;
+    memset(&ctx->c, 0, sizeof(Ctx));
+    ctx->c.device = device;
+    if (stream) { ctx->c.stream = (cudaStream_t)stream; ctx->c.ownsStream = false; }
+    else
+    {
+        if (check(cudaStreamCreateWithFlags(&ctx->c.stream, cudaStreamNonBlocking), "cudaStreamCreate")) { delete ctx; return -1; }
+        ctx->c.ownsStream = true;
+    }
+    cudaDeviceProp prop;
+    if (check(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties")) { delete ctx; return -1; }
+    ctx->c.smCount = prop.multiProcessorCount;
+    *out = ctx;
+    return 0;
+}
+
+void x265b200_destroy(x265b200_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->c.device);
+    cudaStreamSynchronize(ctx->c.stream);
+    for (int i = 0; i < 8; i++)
+    {
+        if (ctx->c.dScratch[i]) cudaFree(ctx->c.dScratch[i]);
+        if (ctx->c.hPinned[i]) cudaFreeHost(ctx->c.hPinned[i]);
+    }
+    if (ctx->c.dMvCost) cudaFree(ctx->c.dMvCost);
+    if (ctx->c.ownsStream) cudaStreamDestroy(ctx->c.stream);
+    delete ctx;
+}
+
+int x265b200_sync(x265b200_ctx* ctx) { REQUIRE_CTX(ctx); X265B200_CHECK(cudaStreamSynchronize(ctx->c.stream)); return 0; }
+void* x265b200_stream(x265b200_ctx* ctx) { return ctx ? (void*)ctx->c.stream : nullptr; }
+uint64_t x265b200_launch_count(x265b200_ctx* ctx) { return ctx ? ctx->c.launches : 0; }
+
+int x265b200_malloc(x265b200_ctx* ctx, size_t bytes, void** p) { REQUIRE_CTX(ctx); X265B200_CHECK(cudaMalloc(p, bytes ? bytes : 1)); return 0; }
+int x265b200_free(x265b200_ctx* ctx, void* p) { REQUIRE_CTX(ctx); X265B200_CHECK(cudaStreamSynchronize(ctx->c.stream)); X265B200_CHECK(cudaFree(p)); return 0; }
+int x265b200_upload(x265b200_ctx* ctx, void* d, const void* h, size_t bytes)
+{
+    REQUIRE_CTX(ctx);
+    X265B200_CHECK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->c.stream));
+    return 0;
+}
+int x265b200_download(x265b200_ctx* ctx, void* h, const void* d, size_t bytes)
+{
+    REQUIRE_CTX(ctx);
+    X265B200_CHECK(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, ctx->c.stream));
+    X265B200_CHECK(cudaStreamSynchronize(ctx->c.stream));
+    return 0;
+}
+int x265b200_malloc_host(size_t bytes, void** p) { X265B200_CHECK(cudaMallocHost(p, bytes ? bytes : 1)); return 0; }
+int x265b200_free_host(void* p) { X265B200_CHECK(cudaFreeHost(p)); return 0; }
+
+// ---- block compare ----------------------------------------------------------------------------
+int x265b200_pixelcmp_dev(x265b200_ctx* ctx, int kind, int depth, int w, int h,
+                          const void* A, int64_t strideA, const void* B, int64_t strideB,
+                          const int64_t* offA, const int64_t* offB, const int16_t* mv, int gridCols,
+                          int64_t n, void* out)
+{
+    REQUIRE_CTX(ctx);
+    return pixelcmp_dev(CTX(ctx), kind, depth, w, h, A, strideA, B, strideB, offA, offB, mv, gridCols, n, out);
+}
+
+int x265b200_pixelcmp_host(x265b200_ctx* ctx, int kind, int depth, int w, int h,
+                           const void* A, size_t bytesA, int64_t strideA,
+                           const void* B, size_t bytesB, int64_t strideB,
+                           const int64_t* offA, const int64_t* offB, int64_t n, void* out)
+{
+    REQUIRE_CTX(ctx);
+    if (!offA) { set_error("pixelcmp_host: offA required"); return -1; }
+    Ctx* c = CTX(ctx);
+    void *dA, *dB = nullptr, *dOA, *dOB = nullptr, *dOut;
+    const bool wide = kind >= X265B200_CMP_SSE_PP;
+    size_t outBytes = (size_t)n * (wide ? 8 : 4);
+    if (stage_in(c, 0, A, bytesA, &dA)) return -1;
+    if (B && kind != X265B200_CMP_SSD_S) { if (stage_in(c, 1, B, bytesB, &dB)) return -1; } else dB = dA;
+    if (stage_in(c, 2, offA, (size_t)n * 8, &dOA)) return -1;
+    if (offB) { if (stage_in(c, 3, offB, (size_t)n * 8, &dOB)) return -1; }
+    if (scratch_dev(c, 4, outBytes ? outBytes : 1, &dOut)) return -1;
+    if (pixelcmp_dev(c, kind, depth, w, h, dA, strideA, dB, strideB, (const int64_t*)dOA, (const int64_t*)dOB, nullptr, 0, n, dOut)) return -1;
+    X265B200_CHECK(cudaMemcpyAsync(out, dOut, outBytes, cudaMemcpyDeviceToHost, c->stream));
+    X265B200_CHECK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int x265b200_sad_xn_dev(x265b200_ctx* ctx, int depth, int K, int w, int h, const void* fenc, int64_t fencBlockStride,
+                        const void* ref, int64_t refStride, const int64_t* refOff, int64_t n, int32_t* res)
+{
+    REQUIRE_CTX(ctx);
+    return sad_xn_dev(CTX(ctx), depth, K, w, h, fenc, fencBlockStride, ref, refStride, refOff, n, res);
+}
+
+} // extern "C"

@@ -1,0 +1,355 @@
+// pixel_kernels.cu -- block-compare primitives of the x265 EncoderPrimitives table as batched
+// sm_100a kernels: SAD / SATD / SA8D / SSE / ssd_s over N independent block pairs, and the
+// sad_x3 / sad_x4 multi-candidate forms.
+//
+// Reference semantics (bit-exact, integer):
+//   sad<lx,ly>            source/common/pixel.cpp:40-55
+//   sad_x3 / sad_x4       source/common/pixel.cpp:74-119   (fenc stride hard-wired to FENC_STRIDE=64)
+//   satd_4x4 / satd_8x4   source/common/pixel.cpp:210-297  (sum|H4 d H4^T| >> 1 per 4x4 / 8x4)
+//   _sa8d_8x8 / sa8d_*    source/common/pixel.cpp:299-377  ((s+2)>>2 per 8x8, or once per 16x16)
+//   sse<> / ssd_s         source/common/pixel.cpp:167-186, :379-391
+//
+// The SWAR tricks of the C reference (two 16-bit lanes per 32-bit word) cannot overflow for
+// legal pixel ranges (see DESIGN.md "exactness notes"), so the kernels compute the plain
+// mathematical Hadamard sums; the per-sub-block shifts and rounding granularity are kept.
+//
+// Roofline: every kernel here is HBM-bound: algorithmic bytes = N * (2*w*h*sizeof(pixel) + 4).
+// Work mapping: one lane per 4x4 cell (8x8 cell for SA8D); G = min(32, pow2ceil(cells)) lanes
+// cooperate on one block and finish with a segmented warp-shuffle reduction.
+#include "common.cuh"
+#include "x265b200.h"
+
+namespace x265b200 {
+
+// ---------------------------------------------------------------------------------------------
+// cells
+// ---------------------------------------------------------------------------------------------
+template<typename pixel>
+__device__ __forceinline__ int cell_sad(const pixel* a, int64_t sa, const pixel* b, int64_t sb)
+{
+    int s = 0;
+#pragma unroll
+    for (int r = 0; r < 4; r++) s += sad4<pixel>(a + r * sa, b + r * sb);
+    return s;
+}
+
+__device__ __forceinline__ void hadamard4(int& a, int& b, int& c, int& d)
+{
+    int t0 = a + b, t1 = a - b, t2 = c + d, t3 = c - d;
+    a = t0 + t2; c = t0 - t2; b = t1 + t3; d = t1 - t3;
+}
+
+// sum |H4 d H4^T| / 2 of one 4x4 (pixel.cpp:210-236; the /2 is exact: all 16 coefficients
+// share the parity of the block sum)
+template<typename pixel>
+__device__ __forceinline__ int cell_satd(const pixel* a, int64_t sa, const pixel* b, int64_t sb)
+{
+    int d[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+    {
+        int x[4], y[4];
+        ld4i<pixel>(a + r * sa, x);
+        ld4i<pixel>(b + r * sb, y);
+#pragma unroll
+        for (int c = 0; c < 4; c++) d[r][c] = x[c] - y[c];
+        hadamard4(d[r][0], d[r][1], d[r][2], d[r][3]);
+    }
+    int s = 0;
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+    {
+        hadamard4(d[0][c], d[1][c], d[2][c], d[3][c]);
+        s += abs(d[0][c]) + abs(d[1][c]) + abs(d[2][c]) + abs(d[3][c]);
+    }
+    return s >> 1;
+}
+
+__device__ __forceinline__ void hadamard8(int v[8])
+{
+    hadamard4(v[0], v[1], v[2], v[3]);
+    hadamard4(v[4], v[5], v[6], v[7]);
+#pragma unroll
+    for (int i = 0; i < 4; i++) { int p = v[i] + v[i + 4], m = v[i] - v[i + 4]; v[i] = p; v[i + 4] = m; }
+}
+
+// raw sum |H8 d H8^T| of one 8x8 (pixel.cpp:299-334 `_sa8d_8x8`, before rounding)
+template<typename pixel>
+__device__ __forceinline__ int cell_sa8d_raw(const pixel* a, int64_t sa, const pixel* b, int64_t sb)
+{
+    int d[8][8];
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+    {
+        int x[4], y[4];
+        ld4i<pixel>(a + r * sa, x); ld4i<pixel>(b + r * sb, y);
+#pragma unroll
+        for (int c = 0; c < 4; c++) d[r][c] = x[c] - y[c];
+        ld4i<pixel>(a + r * sa + 4, x); ld4i<pixel>(b + r * sb + 4, y);
+#pragma unroll
+        for (int c = 0; c < 4; c++) d[r][4 + c] = x[c] - y[c];
+        hadamard8(d[r]);
+    }
+    int s = 0;
+#pragma unroll
+    for (int c = 0; c < 8; c++)
+    {
+        int v[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) v[r] = d[r][c];
+        hadamard8(v);
+#pragma unroll
+        for (int r = 0; r < 8; r++) s += abs(v[r]);
+    }
+    return s;
+}
+
+template<typename pixel>
+__device__ __forceinline__ uint64_t cell_sse_pp(const pixel* a, int64_t sa, const pixel* b, int64_t sb)
+{
+    uint32_t s = 0;   // 16 * 4095^2 < 2^32
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+    {
+        int x[4], y[4];
+        ld4i<pixel>(a + r * sa, x); ld4i<pixel>(b + r * sb, y);
+#pragma unroll
+        for (int c = 0; c < 4; c++) { int t = x[c] - y[c]; s += (uint32_t)(t * t); }
+    }
+    return s;
+}
+
+// sse<int16,int16>: `tmp*tmp` is a wrapping int product, sign-extended when added to sse_t
+__device__ __forceinline__ uint64_t cell_sse_ss(const int16_t* a, int64_t sa, const int16_t* b, int64_t sb)
+{
+    uint64_t s = 0;
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+    {
+        int x[4], y[4];
+        ld4s(a + r * sa, x); ld4s(b + r * sb, y);
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+        {
+            int t = x[c] - y[c];
+            int p = (int)((uint32_t)t * (uint32_t)t);
+            s += (uint64_t)(int64_t)p;
+        }
+    }
+    return s;
+}
+
+__device__ __forceinline__ uint64_t cell_ssd_s(const int16_t* a, int64_t sa)
+{
+    uint64_t s = 0;
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+    {
+        int x[4];
+        ld4s(a + r * sa, x);
+#pragma unroll
+        for (int c = 0; c < 4; c++) s += (uint64_t)(int64_t)(x[c] * x[c]);
+    }
+    return s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// batched compare kernel
+// ---------------------------------------------------------------------------------------------
+struct CmpArgs
+{
+    const void* A; int64_t strideA;
+    const void* B; int64_t strideB;
+    const int64_t* offA;     // element offsets, or nullptr => grid mode
+    const int64_t* offB;
+    const int16_t* mv;       // grid mode: optional full-pel {x,y} per block applied to B
+    int   gridCols;          // grid mode: blocks per row
+    int64_t n;
+    int   w, h;
+    int   depth;
+    void* out;               // int32[n] (SAD/SATD/SA8D) or uint64[n] (SSE kinds)
+};
+
+template<typename pixel, int KIND>
+__global__ void __launch_bounds__(256)
+cmp_batch_kernel(CmpArgs p)
+{
+    constexpr bool is8 = (KIND == X265B200_CMP_SA8D || KIND == X265B200_CMP_SA8D8);
+    constexpr int CW = is8 ? 8 : 4;
+    const int cellsX = p.w / CW, cellsY = p.h / CW;
+    const int ncell = cellsX * cellsY;
+    int G = 1; while (G < ncell && G < 32) G <<= 1;
+    const int perWarp = 32 / G;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int g = lane / G, l = lane % G;
+    const int64_t blk = warp * perWarp + g;
+    const bool active = blk < p.n;
+
+    int64_t oa = 0, ob = 0;
+    if (active)
+    {
+        if (p.offA) { oa = p.offA[blk]; ob = p.offB ? p.offB[blk] : oa; }
+        else
+        {
+            int bx = (int)(blk % p.gridCols), by = (int)(blk / p.gridCols);
+            oa = (int64_t)by * p.h * p.strideA + (int64_t)bx * p.w;
+            ob = (int64_t)by * p.h * p.strideB + (int64_t)bx * p.w;
+            if (p.mv) ob += p.mv[2 * blk] + (int64_t)p.mv[2 * blk + 1] * p.strideB;
+        }
+    }
+
+    if (KIND == X265B200_CMP_SSE_PP || KIND == X265B200_CMP_SSE_SS || KIND == X265B200_CMP_SSD_S)
+    {
+        uint64_t acc = 0;
+        if (active)
+            for (int c = l; c < ncell; c += G)
+            {
+                int cx = c % cellsX, cy = c / cellsX;
+                if (KIND == X265B200_CMP_SSE_PP)
+                    acc += cell_sse_pp<pixel>((const pixel*)p.A + oa + (int64_t)cy * 4 * p.strideA + cx * 4, p.strideA,
+                                              (const pixel*)p.B + ob + (int64_t)cy * 4 * p.strideB + cx * 4, p.strideB);
+                else if (KIND == X265B200_CMP_SSE_SS)
+                    acc += cell_sse_ss((const int16_t*)p.A + oa + (int64_t)cy * 4 * p.strideA + cx * 4, p.strideA,
+                                       (const int16_t*)p.B + ob + (int64_t)cy * 4 * p.strideB + cx * 4, p.strideB);
+                else
+                    acc += cell_ssd_s((const int16_t*)p.A + oa + (int64_t)cy * 4 * p.strideA + cx * 4, p.strideA);
+            }
+        for (int o = G >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (active && l == 0)
+            ((uint64_t*)p.out)[blk] = p.depth < 10 ? (acc & 0xffffffffull) : acc;   // sse_t: common.h:144-148
+        return;
+    }
+
+    int acc = 0;
+    if (is8)
+    {
+        // cell order: 4 consecutive cells = the four 8x8 of one 16x16 (pixel.cpp:341-351 rounds once per 16x16)
+        const bool r16 = (KIND == X265B200_CMP_SA8D) && p.w >= 16 && p.h >= 16;
+        const int iters = (ncell + G - 1) / G;
+        for (int it = 0; it < iters; it++)
+        {
+            int c = it * G + l;
+            int v = 0;
+            if (active && c < ncell)
+            {
+                int cx, cy;
+                if (r16) { int q = c >> 2, s = c & 3; int qx = q % (cellsX >> 1), qy = q / (cellsX >> 1); cx = qx * 2 + (s & 1); cy = qy * 2 + (s >> 1); }
+                else { cx = c % cellsX; cy = c / cellsX; }
+                v = cell_sa8d_raw<pixel>((const pixel*)p.A + oa + (int64_t)cy * 8 * p.strideA + cx * 8, p.strideA,
+                                         (const pixel*)p.B + ob + (int64_t)cy * 8 * p.strideB + cx * 8, p.strideB);
+            }
+            if (r16)
+            {
+                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                if ((l & 3) == 0) acc += (v + 2) >> 2;
+            }
+            else
+                acc += (v + 2) >> 2;   // sa8d_8x8, pixel.cpp:336-339
+        }
+    }
+    else if (active)
+    {
+        for (int c = l; c < ncell; c += G)
+        {
+            int cx = c % cellsX, cy = c / cellsX;
+            const pixel* a = (const pixel*)p.A + oa + (int64_t)cy * 4 * p.strideA + cx * 4;
+            const pixel* b = (const pixel*)p.B + ob + (int64_t)cy * 4 * p.strideB + cx * 4;
+            acc += (KIND == X265B200_CMP_SAD) ? cell_sad<pixel>(a, p.strideA, b, p.strideB)
+                                              : cell_satd<pixel>(a, p.strideA, b, p.strideB);
+        }
+    }
+    for (int o = G >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (active && l == 0) ((int32_t*)p.out)[blk] = acc;
+}
+
+template<typename pixel>
+static int launch_cmp(Ctx* ctx, int kind, const CmpArgs& a)
+{
+    const bool is8 = (kind == X265B200_CMP_SA8D || kind == X265B200_CMP_SA8D8);
+    int cw = is8 ? 8 : 4;
+    int ncell = (a.w / cw) * (a.h / cw);
+    int G = 1; while (G < ncell && G < 32) G <<= 1;
+    int perWarp = 32 / G;
+    const int threads = 256;
+    int64_t warps = (a.n + perWarp - 1) / perWarp;
+    int64_t blocks = (warps * 32 + threads - 1) / threads;
+    if (blocks <= 0) return 0;
+    dim3 grid((unsigned)blocks), block(threads);
+    switch (kind)
+    {
+    case X265B200_CMP_SAD:    cmp_batch_kernel<pixel, X265B200_CMP_SAD><<<grid, block, 0, ctx->stream>>>(a); break;
+    case X265B200_CMP_SATD:   cmp_batch_kernel<pixel, X265B200_CMP_SATD><<<grid, block, 0, ctx->stream>>>(a); break;
+    case X265B200_CMP_SA8D:   cmp_batch_kernel<pixel, X265B200_CMP_SA8D><<<grid, block, 0, ctx->stream>>>(a); break;
+    case X265B200_CMP_SA8D8:  cmp_batch_kernel<pixel, X265B200_CMP_SA8D8><<<grid, block, 0, ctx->stream>>>(a); break;
+    case X265B200_CMP_SSE_PP: cmp_batch_kernel<pixel, X265B200_CMP_SSE_PP><<<grid, block, 0, ctx->stream>>>(a); break;
+    case X265B200_CMP_SSE_SS: cmp_batch_kernel<pixel, X265B200_CMP_SSE_SS><<<grid, block, 0, ctx->stream>>>(a); break;
+    case X265B200_CMP_SSD_S:  cmp_batch_kernel<pixel, X265B200_CMP_SSD_S><<<grid, block, 0, ctx->stream>>>(a); break;
+    default: set_error("pixelcmp: unknown kind %d", kind); return -1;
+    }
+    ctx->launches++;
+    return check(cudaGetLastError(), "cmp_batch_kernel launch");
+}
+
+int pixelcmp_dev(Ctx* ctx, int kind, int depth, int w, int h,
+                 const void* A, int64_t strideA, const void* B, int64_t strideB,
+                 const int64_t* offA, const int64_t* offB, const int16_t* mv, int gridCols,
+                 int64_t n, void* out)
+{
+    const bool is8 = (kind == X265B200_CMP_SA8D || kind == X265B200_CMP_SA8D8);
+    if (is8 && w == 4 && h == 4) kind = X265B200_CMP_SATD;          // cu[BLOCK_4x4].sa8d = satd_4x4 (pixel.cpp:1163)
+    else if (is8 && ((w | h) & 7)) { set_error("sa8d needs w,h multiples of 8 (got %dx%d)", w, h); return -1; }
+    if (w <= 0 || h <= 0 || ((w | h) & 3) || w > 64 || h > 64) { set_error("pixelcmp: unsupported block %dx%d", w, h); return -1; }
+    CmpArgs a; a.A = A; a.strideA = strideA; a.B = B; a.strideB = strideB; a.offA = offA; a.offB = offB; a.mv = mv;
+    a.gridCols = gridCols; a.n = n; a.w = w; a.h = h; a.depth = depth; a.out = out;
+    return depth > 8 ? launch_cmp<uint16_t>(ctx, kind, a) : launch_cmp<uint8_t>(ctx, kind, a);
+}
+
+// ---------------------------------------------------------------------------------------------
+// sad_x3 / sad_x4: one cached 64-stride fenc block against K reference blocks sharing a stride
+// (pixel.cpp:74-119).  One warp per item: lanes stride over the K*w*h/4 four-pixel groups.
+// ---------------------------------------------------------------------------------------------
+template<typename pixel>
+__global__ void __launch_bounds__(256)
+sad_xn_kernel(const pixel* __restrict__ fenc, int64_t fencBlockStride,   // item i's cached PU at fenc + i*fencBlockStride (row stride 64)
+              const pixel* __restrict__ ref, int64_t refStride,
+              const int64_t* __restrict__ refOff,                        // [n][K] element offsets into ref
+              int K, int w, int h, int64_t n, int32_t* __restrict__ res) // [n][K]
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t item = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (item >= n) return;
+    const pixel* f = fenc + item * fencBlockStride;
+    const int gw = w >> 2, ngroups = gw * h;
+    for (int k = 0; k < K; k++)
+    {
+        const pixel* r = ref + refOff[item * K + k];
+        int s = 0;
+        for (int u = lane; u < ngroups; u += 32)
+        {
+            int y = u / gw, x = (u - y * gw) << 2;
+            s += sad4<pixel>(f + y * 64 + x, r + (int64_t)y * refStride + x);
+        }
+        s = warp_sum(s);
+        if (lane == 0) res[item * K + k] = s;
+    }
+}
+
+int sad_xn_dev(Ctx* ctx, int depth, int K, int w, int h, const void* fenc, int64_t fencBlockStride,
+               const void* ref, int64_t refStride, const int64_t* refOff, int64_t n, int32_t* res)
+{
+    if (K < 1 || K > 4) { set_error("sad_xN: K=%d", K); return -1; }
+    if (w <= 0 || h <= 0 || (w & 3) || w > 64 || h > 64) { set_error("sad_xN: unsupported block %dx%d", w, h); return -1; }
+    const int threads = 256;
+    int64_t blocks = (n * 32 + threads - 1) / threads;
+    if (blocks <= 0) return 0;
+    if (depth > 8)
+        sad_xn_kernel<uint16_t><<<(unsigned)blocks, threads, 0, ctx->stream>>>((const uint16_t*)fenc, fencBlockStride, (const uint16_t*)ref, refStride, refOff, K, w, h, n, res);
+    else
+        sad_xn_kernel<uint8_t><<<(unsigned)blocks, threads, 0, ctx->stream>>>((const uint8_t*)fenc, fencBlockStride, (const uint8_t*)ref, refStride, refOff, K, w, h, n, res);
+    ctx->launches++;
+    return check(cudaGetLastError(), "sad_xn_kernel launch");
+}
+
+} // namespace x265b200
