@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 x265 hot-path backend (contract in the task brief).
+
+Workload ("step" = one 2160p 8-bit frame through the hot path, BASELINE.json configs[2] knobs:
+HEX search, subme 2, merange 57, 3 references, 2Nx2N PUs 64/32/16/8 of every CTU, mvp = 0):
+  1. sad_pred  : SAD at the predictor for every PU level x reference (grid-mode pixelcmp kernel; the
+                 streaming "ME SAD" kernel whose HBM GB/s is the second half of BASELINE's metric)
+  2. me_search : MotionEstimate::motionEstimate for every PU x reference (me_batch kernel)
+  3. residual  : fenc - ref0 -> DCT32 -> quant -> dequant -> IDCT32 over every 32x32 TU
+`value` = frames/s with inputs resident in HBM; `e2e` = the same through the C ABI with the new frame
+coming from pinned HOST memory and the per-PU {MV,cost} results copied back, every step.
+
+--impl reference times the reference's own C implementation (oracle/_ref, compiled from the
+unmodified x265 sources) of the same step on the host cores, on a bounded sample of the frame.
+"""
+import argparse
+import ctypes
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+W, H, CTU, PAD = 3840, 2160, 64, 128          # luma; PAD >= merange + 8 + halo, multiple of 64
+STRIDE = W + 2 * PAD
+ROWS = H + 2 * PAD + (64 - (H % 64)) % 64      # 34 CTU rows (2176) + margins
+CTU_COLS, CTU_ROWS = W // CTU, (H + CTU - 1) // CTU
+NREF, MERANGE, SUBME, QP = 3, 57, 2, 30
+LEVELS = [64, 32, 16, 8]
+METRIC = "2160p preset-medium fps at 1/2/4/8 B200; ME SAD achieved HBM GB/s vs peak"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+def synth_frames(nframes, seed=1234):
+    """band-limited noise + per-frame global translation + noise."""
+    rng = np.random.default_rng(seed)
+    big = rng.integers(0, 256, (ROWS + 96, STRIDE + 96), dtype=np.uint8).astype(np.float32)
+    k = np.ones(5, dtype=np.float32) / 5
+    for ax in (0, 1):
+        big = np.apply_along_axis(lambda r: np.convolve(r, k, mode="same"), ax, big)
+    big = (big - big.min()) / (big.max() - big.min()) * 255.0
+    mrng = np.random.default_rng(5678)
+    frames = []
+    x, y = 48, 48
+    for f in range(nframes):
+        dx, dy = mrng.integers(-6, 7, 2)
+        x = int(np.clip(x + dx, 0, 95)); y = int(np.clip(y + dy, 0, 95))
+        fr = big[y:y + ROWS, x:x + STRIDE] + rng.normal(0, 2.0, (ROWS, STRIDE)).astype(np.float32)
+        frames.append(np.clip(np.rint(fr), 0, 255).astype(np.uint8))
+    return frames
+
+
+def build_jobs(pkg, ctu_rows=None):
+    """one job per (ref, level, PU): mvp = 0, window = +-merange."""
+    rows = range(CTU_ROWS) if ctu_rows is None else ctu_rows
+    js = []
+    for r in range(NREF):
+        for s in LEVELS:
+            per = CTU // s
+            for cy in rows:
+                for cx in range(CTU_COLS):
+                    for py in range(per):
+                        y = cy * CTU + py * s
+                        if y + s > H + (64 - H % 64) % 64:
+                            continue
+                        for px in range(per):
+                            js.append((cx * CTU + px * s, y, s, r))
+    a = np.array(js, dtype=np.int32)
+    job = np.zeros(len(a), dtype=pkg.ME_JOB)
+    job["puX"], job["puY"], job["w"], job["h"], job["refIdx"] = a[:, 0], a[:, 1], a[:, 2], a[:, 2], a[:, 3]
+    job["mvminX"] = job["mvminY"] = -MERANGE
+    job["mvmaxX"] = job["mvmaxY"] = MERANGE
+    return job
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, idx):
+        super().__init__(daemon=True)
+        self.idx, self.samples, self.stop_flag = idx, [], False
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append([x.strip() for x in o])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if len(s) >= 6 and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) >= 6 and s[1].replace(".", "").isdigit()]
+        reasons = set()
+        for s in self.samples:
+            if len(s) >= 6:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons)}
+
+
+def run_reference(args, rank, world):
+    """The reference's own C path (oracle/_ref) on host cores, bounded sample: one CTU row."""
+    if rank != 0:
+        return
+    import oracle
+    from me_util import REF_ME_JOB
+    pkg = importlib.import_module("x265-yuuki-asuna_b200")
+    R = oracle.ref(8)
+    cores = os.cpu_count() or 1
+    if R is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libx265ref8.so not present"}))
+        return
+    frames = synth_frames(NREF + 1)
+    sample_rows = [CTU_ROWS // 2]
+    job = build_jobs(pkg, sample_rows)
+    frac = len(sample_rows) / CTU_ROWS
+    origin = PAD * STRIDE + PAD
+    cur = frames[NREF].ravel()
+
+    def step():
+        for r in range(NREF):
+            jr = job[job["refIdx"] == r]
+            rj = np.zeros(len(jr), dtype=REF_ME_JOB)
+            for f in ("puX", "puY", "w", "h", "mvminX", "mvminY", "mvmaxX", "mvmaxY", "mvpX", "mvpY", "numCand", "mvc"):
+                rj[f] = jr[f]
+            ref = frames[NREF - 1 - r].ravel()
+            R.ref_me_batch(ctypes.c_void_p(cur.ctypes.data + origin), ctypes.c_ssize_t(STRIDE),
+                           ctypes.c_void_p(ref.ctypes.data + origin), ctypes.c_ssize_t(STRIDE),
+                           ctypes.c_void_p(rj.ctypes.data), ctypes.c_int64(len(rj)), 1, SUBME, MERANGE, QP, 1, cores)
+        # residual pipeline on the sample row's 32x32 TUs
+        n32 = CTU_COLS * 2 * 2 * len(sample_rows)
+        resid = (cur[origin:origin + 64 * STRIDE].astype(np.int16) - frames[NREF - 1].ravel()[origin:origin + 64 * STRIDE].astype(np.int16))
+        blocks = np.ascontiguousarray(resid.reshape(64, STRIDE)[:, :W].reshape(2, 32, W // 32, 32).transpose(0, 2, 1, 3)).reshape(-1)
+        coef = np.empty_like(blocks); rec = np.empty_like(blocks)
+        R.ref_dct_batch(3, ctypes.c_void_p(blocks.ctypes.data), ctypes.c_int64(1024), ctypes.c_ssize_t(32), ctypes.c_void_p(coef.ctypes.data), ctypes.c_int64(n32), cores)
+        R.ref_idct_batch(3, ctypes.c_void_p(coef.ctypes.data), ctypes.c_void_p(rec.ctypes.data), ctypes.c_int64(1024), ctypes.c_ssize_t(32), ctypes.c_int64(n32), cores)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    fps = frac / dt
+    line = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic", "impl": "reference",
+            "config": {"workload": "2160p-8bit-medium-hotpath: HEX subme2 merange57 3refs 2Nx2N 64..8 + DCT32/IDCT32", "sample": "1 of %d CTU rows, scaled" % CTU_ROWS},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "reference",
+                             "sample": "%d PU searches (CTU row %d, 3 refs) + %d 32x32 DCT/IDCT, x%d to a frame; C table, no nasm asm" % (len(job), sample_rows[0], CTU_COLS * 4, CTU_ROWS)},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    pkg = importlib.import_module("x265-yuuki-asuna_b200")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    stream = torch.cuda.current_stream()
+    ctx = pkg.Ctx(local, stream=stream.cuda_stream)       # fails loudly without the CUDA library
+    dev = torch.device("cuda", local)
+    lam = pkg.lambda_for_qp(QP, 8)
+
+    # ---- resident data: a ring of frames (> L2), static PU descriptors ------------------------------
+    NF = 8
+    frames_h = synth_frames(NF, seed=1234 + rank)
+    pinned = [torch.from_numpy(f).pin_memory() for f in frames_h]
+    ring = [torch.empty((ROWS, STRIDE), dtype=torch.uint8, device=dev) for _ in range(NF)]
+    for d, h in zip(ring, pinned):
+        d.copy_(h)
+    job_h = build_jobs(pkg)
+    njobs = len(job_h)
+    jobs_d = torch.from_numpy(job_h.view(np.uint8).reshape(njobs, -1).copy()).to(dev)
+    origin = PAD * STRIDE + PAD
+    ref_ptr_table = torch.tensor([[ring[(t - 1 - r) % NF].data_ptr() + origin for r in range(NREF)] for t in range(NF)],
+                                 dtype=torch.int64).to(dev)
+    level_n = {s: (W // s) * ((CTU_ROWS * CTU) // s) for s in LEVELS}
+    sad_out = {s: torch.empty(NREF * level_n[s], dtype=torch.int32, device=dev) for s in LEVELS}
+    n32 = (W // 32) * (CTU_ROWS * 2)
+    resid = torch.empty((CTU_ROWS * CTU, W), dtype=torch.int16, device=dev)
+    coef = torch.empty(n32 * 1024, dtype=torch.int16, device=dev)
+    qcoef = torch.empty_like(coef); deq = torch.empty_like(coef)
+    recon = torch.empty((CTU_ROWS * CTU, W), dtype=torch.uint8, device=dev)
+    qtab = torch.full((1024,), 26214, dtype=torch.int32, device=dev)          # quantScales[qp%6=0] flat list
+    numsig = torch.empty(n32, dtype=torch.int32, device=dev)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    res_h = torch.empty((njobs, 3), dtype=torch.int32).pin_memory()
+    P = lambda t: t.data_ptr()
+
+    sad_events = []
+
+    def hot_path(t, time_sad=False):
+        cur = ring[t % NF]
+        refs = [ring[(t - 1 - r) % NF] for r in range(NREF)]
+        ref_ptrs = ref_ptr_table[t % NF]
+        cptr = P(cur) + origin
+        # 1. SAD at the predictor (mv = 0) for every PU level x ref: streaming, 2*W*H bytes per (level, ref)
+        if time_sad:
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True); e0.record()
+        for s in LEVELS:
+            for r in range(NREF):
+                ctx.pixelcmp_dev(pkg.CMP_SAD, 8, s, s, cptr, STRIDE, P(refs[r]) + origin, STRIDE, None, None, level_n[s],
+                                 P(sad_out[s]) + 4 * r * level_n[s], None, W // s)
+        if time_sad:
+            e1.record(); sad_events.append((e0, e1))
+        # 2. full motion search for every PU x ref
+        ctx.me_batch_dev(8, cptr, STRIDE, None, STRIDE, P(jobs_d), njobs, 64, 64, pkg.ME_HEX, SUBME, MERANGE, lam, 1, dRefPlanes=P(ref_ptrs))
+        # 3. residual -> DCT32 -> quant -> dequant -> IDCT32 -> recon (one launch each, whole plane)
+        HH = CTU_ROWS * CTU
+        ctx.sub_ps_plane_dev(8, cptr, STRIDE, P(refs[0]) + origin, STRIDE, P(resid), W, W, HH)
+        ctx.dct_plane_dev(3, 8, P(resid), W, W // 32, HH // 32, P(coef))
+        ctx.quant_dev(P(coef), P(qtab), None, P(qcoef), 14 + 5 + (15 - 8 - 5), 171 << (14 + 5 + 2 - 9), 1024, n32, P(numsig))
+        ctx.dequant_normal_dev(P(qcoef), P(deq), 1024, n32, 40 << 5, 9)
+        ctx.idct_plane_dev(3, 8, P(deq), P(resid), W, W // 32, HH // 32)
+        ctx.add_ps_plane_dev(8, P(recon), W, P(refs[0]) + origin, STRIDE, P(resid), W, W, HH)
+
+    def e2e_step(t):
+        ring[t % NF].copy_(pinned[t % NF], non_blocking=True)                   # H2D: the new frame
+        hot_path(t)
+        out = jobs_d.view(torch.int32).view(njobs, -1)[:, -3:]
+        res_h.copy_(out, non_blocking=True)                                   # D2H: {mvx, mvy, cost} per PU
+        stream.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- warm-up ---------------------------------------------------------------------------------------
+    for i in range(max(args.warmup, 3)):
+        hot_path(NREF + i)
+    barrier()
+    launches0 = ctx.launches
+
+    sampler = ClockSampler(local); sampler.start()
+    # ---- device-resident timing: per-step CUDA events, L2 flushed between steps -----------------------------
+    evs = []
+    barrier()
+    for i in range(args.steps):
+        flush.fill_(i & 255)                                                   # > L2 (126 MB): evicts frames and tables
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        hot_path(NREF + i, time_sad=True)
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    total_ms = float(sum(step_ms))
+    sad_ms = [a.elapsed_time(b) for a, b in sad_events]
+    launches = ctx.launches - launches0
+
+    # ---- end-to-end timing (host buffers in, results out) ---------------------------------------------------
+    for i in range(2):
+        e2e_step(NREF + i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        e2e_step(NREF + i)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    sampler.stop_flag = True; sampler.join(timeout=2)
+
+    tt = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total_ms, e2e_s = float(tt[0]), float(tt[1])
+
+    if rank == 0:
+        pk, pk_kind = peaks()
+        fps = world * args.steps / (total_ms / 1e3)
+        e2e_fps = world * args.steps / e2e_s
+        # roofline of the streaming ME-SAD kernel: algorithmic bytes = 2*W*H + nPU*4 per (level, ref) launch
+        sad_launches = len(LEVELS) * NREF
+        sad_bytes = sum(2 * W * (CTU_ROWS * CTU) + level_n[s] * 4 for s in LEVELS) * NREF
+        sad_t = float(np.mean(sad_ms)) / 1e3
+        achieved = sad_bytes / sad_t / 1e9
+        line = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u8", "data": "synthetic",
+                "config": {"workload": "2160p-8bit-medium-hotpath: sad_pred + HEX subme2 merange57 3refs 2Nx2N 64..8 (%d searches) + resid/DCT32/quant/dequant/IDCT32 (%d TUs)" % (njobs, n32),
+                           "l2": "512 MiB flush between timed steps", "parallelism": "frame-parallel x%d" % world},
+                "clocks": sampler.summary(), "gpu_launches": int(launches),
+                "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": ROWS * STRIDE, "d2h_bytes_per_step": njobs * 12},
+                "roofline": {"kernel": "cmp_batch_kernel<u8,SAD> (grid mode, ME SAD at predictor)", "bound": "hbm", "achieved": achieved,
+                             "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": None,
+                             "peak_kind": pk_kind, "launches_per_step": sad_launches, "ms_per_step": sad_t * 1e3}}
+        if world == 1:
+            line["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline():
+    """bounded sample of the same step on the host cores through the compiled reference (kind 'reference')."""
+    out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600)
+    try:
+        ref = json.loads(out.stdout.strip().splitlines()[-1])
+        return ref.get("cpu_baseline", {"unavailable": ref.get("unavailable")})
+    except Exception as e:      # noqa: BLE001
+        return {"unavailable": "reference arm failed: %s %s" % (e, out.stderr[-200:])}
+
+
+if __name__ == "__main__":
+    main()

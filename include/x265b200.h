@@ -77,6 +77,98 @@ int x265b200_sad_xn_dev(x265b200_ctx* ctx, int depth, int K, int w, int h,
                         const void* ref, int64_t refStride, const int64_t* refOff,
                         int64_t n, int32_t* res);
 
+/* ---- transforms: replaces cu[].dct / cu[].idct / dst4x4 / idst4x4 (primitives.h:153-154,
+ *      275-276,318-319; dct.cpp:442-610).  sizeIdx 0..3 = 4/8/16/32-point DCT, 4 = 4x4 DST.
+ * Forward: block i reads src + i*srcBlockStride with row pitch srcStride, writes N*N contiguous
+ * coefficients at dst + i*N*N.  Inverse: reads N*N contiguous at src + i*N*N, writes
+ * dst + i*dstBlockStride with row pitch dstStride.  8/16/32 run on the integer tensor cores. */
+int x265b200_dct_dev(x265b200_ctx* ctx, int sizeIdx, int depth, const int16_t* src, int64_t srcBlockStride,
+                     int64_t srcStride, int16_t* dst, int64_t n);
+int x265b200_idct_dev(x265b200_ctx* ctx, int sizeIdx, int depth, const int16_t* src, int16_t* dst,
+                      int64_t dstBlockStride, int64_t dstStride, int64_t n);
+/* Plane forms: the blocksX x blocksY grid of N x N TUs of an int16 plane (row pitch `stride`), TU
+ * (bx,by) <-> coefficient block by*blocksX+bx.  One launch per plane (the residual pipeline shape). */
+int x265b200_dct_plane_dev(x265b200_ctx* ctx, int sizeIdx, int depth, const int16_t* plane, int64_t stride,
+                           int blocksX, int blocksY, int16_t* coef);
+int x265b200_idct_plane_dev(x265b200_ctx* ctx, int sizeIdx, int depth, const int16_t* coef, int16_t* plane,
+                            int64_t stride, int blocksX, int blocksY);
+/* cu[].sub_ps / cu[].add_ps (primitives.h:189-190,282-283; pixel.cpp:814-840) over a whole w x h plane:
+ * dst = a - b (int16);  dst = clip(pred + resi). */
+int x265b200_sub_ps_plane_dev(x265b200_ctx* ctx, int depth, const void* a, int64_t strideA, const void* b, int64_t strideB,
+                              int16_t* dst, int64_t dstStride, int w, int h);
+int x265b200_add_ps_plane_dev(x265b200_ctx* ctx, int depth, void* dst, int64_t dstStride, const void* pred, int64_t predStride,
+                              const int16_t* resi, int64_t resiStride, int w, int h);
+/* quant / nquant (primitives.h:159-160,321-322; dct.cpp:664-713) over n TUs of numCoeff
+ * coefficients sharing one quantCoeff[numCoeff] table.  deltaU may be NULL; numSig: uint32[n]. */
+int x265b200_quant_dev(x265b200_ctx* ctx, const int16_t* coef, const int32_t* quantCoeff, int32_t* deltaU,
+                       int16_t* qCoef, int qBits, int add, int numCoeff, int64_t n, uint32_t* numSig);
+int x265b200_nquant_dev(x265b200_ctx* ctx, const int16_t* coef, const int32_t* quantCoeff, int16_t* qCoef,
+                        int qBits, int add, int numCoeff, int64_t n, uint32_t* numSig);
+/* dequant_normal / dequant_scaling (primitives.h:161-162,323-324; dct.cpp:612-662), n TUs of num coeffs */
+int x265b200_dequant_normal_dev(x265b200_ctx* ctx, const int16_t* quantCoef, int16_t* coef, int num, int64_t n,
+                                int scale, int shift);
+int x265b200_dequant_scaling_dev(x265b200_ctx* ctx, const int16_t* quantCoef, const int32_t* deQuantCoef,
+                                 int16_t* coef, int num, int64_t n, int mcqp_miper, int shift);
+/* cu[].count_nonzero (primitives.h:163; dct.cpp:714-726): out int32[n] */
+int x265b200_count_nonzero_dev(x265b200_ctx* ctx, const int16_t* quantCoeff, int numCoeff, int64_t n, int32_t* out);
+/* The N x N HEVC core-transform matrix the kernels use (host side, no GPU needed); N = 4,8,16,32. */
+int x265b200_dct_table(int N, int16_t* out);
+
+/* ---- interpolation: replaces pu[].luma_hpp/hps/vpp/vps/vsp/vss/hvpp/convert_p2s and
+ *      chroma[].pu[].filter_* / p2s (primitives.h:176-182,253-263,398-407; ipfilter.cpp:40-370).
+ * taps = 8 (luma) or 4 (chroma).  Job i filters the w x h block at src + srcOff into dst + dstOff
+ * with coeffIdx = idxX (idxY: vertical fraction of HVPP).  srcOff points at the block itself; the
+ * kernel applies the reference's -(N/2-1) tap offset (and the HPS isRowExt row offset) itself. */
+enum { X265B200_IP_HPP = 0, X265B200_IP_HPS = 1, X265B200_IP_VPP = 2, X265B200_IP_VPS = 3,
+       X265B200_IP_VSP = 4, X265B200_IP_VSS = 5, X265B200_IP_HVPP = 6, X265B200_IP_P2S = 7 };
+typedef struct { int64_t srcOff, dstOff; int32_t idxX, idxY; } x265b200_interp_job;
+int x265b200_interp_dev(x265b200_ctx* ctx, int kind, int taps, int depth, int w, int h,
+                        const void* src, int64_t srcStride, void* dst, int64_t dstStride,
+                        const x265b200_interp_job* jobs, int64_t n, int isRowExt);
+
+/* ---- intra prediction: replaces cu[].intra_pred[35] / intra_filter / intra_pred_allangs
+ *      (primitives.h:143-145,304-306; intrapred.cpp:31-234).  Neighbour arrays use the reference
+ *      layout [topLeft, top 2N, left 2N] (4N+1 pixels).  log2N = 2..5. */
+typedef struct { int64_t srcOff, dstOff; int32_t mode, bFilter; } x265b200_intra_job;
+int x265b200_intra_pred_dev(x265b200_ctx* ctx, int depth, int log2N, const void* neighbours,
+                            void* dst, int64_t dstStride, const x265b200_intra_job* jobs, int64_t n);
+/* n arrays of 4N+1 pixels, array i at i*(4N+1) in both src and dst */
+int x265b200_intra_filter_dev(x265b200_ctx* ctx, int depth, int log2N, const void* src, void* dst, int64_t n);
+/* block i: refPix/filtPix arrays at i*(4N+1), 33 predictions (modes 2..34) of N*N at dest + i*33*N*N */
+int x265b200_intra_allangs_dev(x265b200_ctx* ctx, int depth, int log2N, const void* refPix, const void* filtPix,
+                               void* dest, int bLuma, int64_t n);
+
+/* ---- motion estimation: replaces MotionEstimate::setSourcePU + MotionEstimate::motionEstimate
+ *      (encoder/motion.h:81-98; encoder/motion.cpp:167-191, :739-1569) for n independent PU
+ *      searches.  One job = one call of motionEstimate(); per-job semantics are identical:
+ *      mvmin/mvmax are full-pel inclusive bounds, mvp and mvc[] are quarter-pel, the result
+ *      (outMv, outCost) is `outQMv` and the return value.  searchMethod uses the X265_*_SEARCH
+ *      numbering of x265.h:492-497 (0 DIA, 1 HEX, 2 UMH, 3 STAR, 5 FULL; 4 SEA is a "next" row).
+ *      lambda = x265_lambda_tab[qp] of BitCost::setQP (bitcost.cpp:31-60).  Luma only
+ *      (bChromaSATD = false, i.e. subme <= 2 or the lookahead-style setSourcePU). */
+typedef struct {
+    int32_t puX, puY;                          /* PU position in the fenc/ref planes (pixels)   */
+    int32_t w, h;                              /* PU size (any of the 24 inter LumaPU shapes)   */
+    int32_t mvminX, mvminY, mvmaxX, mvmaxY;
+    int32_t mvpX, mvpY;
+    int32_t numCand;                           /* 0..8                                          */
+    int32_t mvc[8][2];
+    int32_t refIdx;                            /* index into refPlanes[] (0 when single plane)  */
+    int32_t outMvX, outMvY, outCost;           /* OUT                                           */
+} x265b200_me_job;
+/* refPlanes: optional device array of plane base pointers selected by job.refIdx; when NULL every
+ * job searches refPlane.  All planes share refStride; (puX,puY) addresses the same pixel in the
+ * fenc plane and in every reference plane.  maxW/maxH: largest PU in the batch (sizes smem). */
+int x265b200_me_batch_dev(x265b200_ctx* ctx, int depth, const void* fencPlane, int64_t fencStride,
+                          const void* refPlane, const void* const* refPlanes, int64_t refStride,
+                          x265b200_me_job* jobs, int64_t n, int maxW, int maxH,
+                          int searchMethod, int subpelRefine, int merange, double lambda, int maxSlices);
+/* The lambda-scaled MV cost table the kernels use (host side, no GPU needed):
+ * out[2*32768 + i] = cost of a quarter-pel MV difference i, i in [-65536, 65536]. */
+int x265b200_bitcost_table(double lambda, uint16_t* out);
+/* x265_lambda_tab[qp] for a bit depth (constants.cpp:34-150), regenerated as round(2^((qp-12)/6 + (depth-8)), 4 dp) */
+double x265b200_lambda(int qp, int depth);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,84 @@
+"""GPU parity: batched motion estimation vs the reference's own MotionEstimate::motionEstimate
+(oracle/_ref links the unmodified source/encoder/motion.cpp).  Every job must return the same
+quarter-pel MV and the same cost -- DIA/HEX/UMH/STAR/FULL, subme 0..7 (luma), all inter PU shapes,
+8- and 10-bit, candidates, tight ranges (border paths of the star/UMH code) and slice clamping."""
+import importlib
+
+import numpy as np
+import pytest
+
+from me_util import make_jobs, ref_me, synth_pair
+from util import LUMA_PU_SIZES
+
+pkg = importlib.import_module("x265-yuuki-asuna_b200")
+pytestmark = pytest.mark.gpu
+
+INTER_SIZES = [s for s in LUMA_PU_SIZES if s != (4, 4)]
+
+
+def _run(ctx, depth, method, subme, merange, qp, sizes, seed, n_per_size=10, maxSlices=1, mvp_span=24, motion=(5, -3), W=192, H=128):
+    pad = 64 + merange + 16
+    cur, ref, S, origin = synth_pair(W, H, pad, depth=depth, seed=seed, motion=motion)
+    rng = np.random.default_rng(seed + 1)
+    job = make_jobs(pkg, W, H, sizes, merange, rng, n_per_size=n_per_size, mvp_span=mvp_span)
+    if maxSlices > 1:
+        job["mvminY"] = np.maximum(job["mvminY"], -2)
+        job["mvmaxY"] = np.minimum(job["mvmaxY"], 3)
+    ex, ey, ec = ref_me(depth, cur, ref, S, origin, job, method, subme, merange, qp, maxSlices)
+    item = cur.itemsize
+    dC, dR, dJ = ctx.to_device(cur), ctx.to_device(ref), ctx.to_device(job)
+    lam = pkg.lambda_for_qp(qp, depth)
+    ctx.me_batch_dev(depth, dC.ptr + origin * item, S, dR.ptr + origin * item, S, dJ, len(job), 64, 64, method, subme, merange, lam, maxSlices)
+    out = dJ.download(pkg.ME_JOB)
+    bad = np.nonzero((out["outMvX"] != ex) | (out["outMvY"] != ey) | (out["outCost"] != ec))[0]
+    msg = ""
+    if len(bad):
+        i = bad[0]
+        msg = "job %d %s: got mv (%d,%d) cost %d, reference mv (%d,%d) cost %d; %d/%d differ" % (
+            i, job[i], out["outMvX"][i], out["outMvY"][i], out["outCost"][i], ex[i], ey[i], ec[i], len(bad), len(job))
+    for b in (dC, dR, dJ):
+        b.free()
+    assert not len(bad), msg
+
+
+@pytest.mark.parametrize("method", [pkg.ME_DIA, pkg.ME_HEX, pkg.ME_UMH, pkg.ME_STAR])
+@pytest.mark.parametrize("subme", [0, 1, 2])
+def test_me_all_shapes_8bit(ctx, method, subme):
+    _run(ctx, 8, method, subme, 57, 30, INTER_SIZES, seed=100 + method * 10 + subme, n_per_size=6)
+
+
+@pytest.mark.parametrize("method", [pkg.ME_HEX, pkg.ME_STAR])
+def test_me_10bit(ctx, method):
+    _run(ctx, 10, method, 2, 57, 32, INTER_SIZES, seed=300 + method, n_per_size=4)
+
+
+@pytest.mark.parametrize("subme", [3, 4, 5, 6, 7])
+def test_me_subme_levels_luma(ctx, subme):
+    _run(ctx, 8, pkg.ME_HEX, subme, 32, 27, [(8, 8), (16, 16), (32, 32), (64, 64), (16, 8), (32, 24)], seed=400 + subme, n_per_size=8)
+
+
+def test_me_large_motion_star_raster(ctx):
+    """large true motion forces the star search past distance 5 -> raster refinement (motion.cpp:1169-1203)."""
+    _run(ctx, 8, pkg.ME_STAR, 2, 48, 30, [(16, 16), (32, 32), (8, 8)], seed=500, n_per_size=10, motion=(23, -19), mvp_span=8)
+    _run(ctx, 8, pkg.ME_UMH, 2, 48, 30, [(16, 16), (32, 32), (64, 64)], seed=501, n_per_size=10, motion=(-21, 17), mvp_span=8)
+
+
+def test_me_tight_range_border_paths(ctx):
+    """tiny search windows exercise the per-point border checks of STAR / UMH / CROSS."""
+    for method in (pkg.ME_DIA, pkg.ME_HEX, pkg.ME_UMH, pkg.ME_STAR):
+        _run(ctx, 8, method, 2, 3, 30, [(8, 8), (16, 16), (32, 32)], seed=600 + method, n_per_size=12)
+        _run(ctx, 8, method, 1, 9, 22, [(16, 16), (64, 64)], seed=610 + method, n_per_size=8)
+
+
+def test_me_full_search(ctx):
+    _run(ctx, 8, pkg.ME_FULL, 2, 6, 30, [(8, 8), (16, 16), (32, 16)], seed=700, n_per_size=6)
+
+
+def test_me_slice_clamp(ctx):
+    _run(ctx, 8, pkg.ME_HEX, 2, 16, 30, [(16, 16), (32, 32)], seed=800, n_per_size=10, maxSlices=4)
+    _run(ctx, 8, pkg.ME_STAR, 3, 16, 30, [(16, 16)], seed=801, n_per_size=10, maxSlices=2)
+
+
+def test_me_qp_range(ctx):
+    for qp in (0, 12, 37, 51):
+        _run(ctx, 8, pkg.ME_HEX, 2, 24, qp, [(16, 16), (8, 8)], seed=900 + qp, n_per_size=8)

@@ -159,3 +159,131 @@ class Ctx:
         self._chk(self.L.x265b200_sad_xn_dev(
             self.h, depth, K, w, h, _vp(dFenc), ctypes.c_int64(fencBlockStride), _vp(dRef), ctypes.c_int64(refStride),
             _vp(dRefOff), ctypes.c_int64(n), _vp(dRes)))
+
+
+# ---- transforms / interpolation / intra (appended bindings) ---------------------------------------
+IP_HPP, IP_HPS, IP_VPP, IP_VPS, IP_VSP, IP_VSS, IP_HVPP, IP_P2S = range(8)
+
+INTERP_JOB = np.dtype([("srcOff", np.int64), ("dstOff", np.int64), ("idxX", np.int32), ("idxY", np.int32)])
+INTRA_JOB = np.dtype([("srcOff", np.int64), ("dstOff", np.int64), ("mode", np.int32), ("bFilter", np.int32)])
+
+
+def dct_table(N):
+    out = np.empty((N, N), dtype=np.int16)
+    if load().x265b200_dct_table(int(N), _vp(out)) != 0:
+        raise X265B200Error(load().x265b200_last_error().decode())
+    return out
+
+
+def _i64(v):
+    return ctypes.c_int64(int(v))
+
+
+def _ctx_dct_dev(self, sizeIdx, depth, dSrc, srcBlockStride, srcStride, dDst, n):
+    self._chk(self.L.x265b200_dct_dev(self.h, sizeIdx, depth, _vp(dSrc), _i64(srcBlockStride), _i64(srcStride), _vp(dDst), _i64(n)))
+
+
+def _ctx_idct_dev(self, sizeIdx, depth, dSrc, dDst, dstBlockStride, dstStride, n):
+    self._chk(self.L.x265b200_idct_dev(self.h, sizeIdx, depth, _vp(dSrc), _vp(dDst), _i64(dstBlockStride), _i64(dstStride), _i64(n)))
+
+
+def _ctx_quant_dev(self, dCoef, dQuantCoeff, dDeltaU, dQCoef, qBits, add, numCoeff, n, dNumSig, nquant=False):
+    if nquant:
+        self._chk(self.L.x265b200_nquant_dev(self.h, _vp(dCoef), _vp(dQuantCoeff), _vp(dQCoef), qBits, add, numCoeff, _i64(n), _vp(dNumSig)))
+    else:
+        self._chk(self.L.x265b200_quant_dev(self.h, _vp(dCoef), _vp(dQuantCoeff), _vp(dDeltaU), _vp(dQCoef), qBits, add, numCoeff, _i64(n), _vp(dNumSig)))
+
+
+def _ctx_dequant_normal_dev(self, dQ, dCoef, num, n, scale, shift):
+    self._chk(self.L.x265b200_dequant_normal_dev(self.h, _vp(dQ), _vp(dCoef), num, _i64(n), scale, shift))
+
+
+def _ctx_dequant_scaling_dev(self, dQ, dDeq, dCoef, num, n, per, shift):
+    self._chk(self.L.x265b200_dequant_scaling_dev(self.h, _vp(dQ), _vp(dDeq), _vp(dCoef), num, _i64(n), per, shift))
+
+
+def _ctx_count_nonzero_dev(self, dQ, numCoeff, n, dOut):
+    self._chk(self.L.x265b200_count_nonzero_dev(self.h, _vp(dQ), numCoeff, _i64(n), _vp(dOut)))
+
+
+def _ctx_interp_dev(self, kind, taps, depth, w, h, dSrc, srcStride, dDst, dstStride, dJobs, n, isRowExt=0):
+    self._chk(self.L.x265b200_interp_dev(self.h, kind, taps, depth, w, h, _vp(dSrc), _i64(srcStride), _vp(dDst), _i64(dstStride),
+                                         _vp(dJobs), _i64(n), int(isRowExt)))
+
+
+def _ctx_intra_pred_dev(self, depth, log2N, dNbr, dDst, dstStride, dJobs, n):
+    self._chk(self.L.x265b200_intra_pred_dev(self.h, depth, log2N, _vp(dNbr), _vp(dDst), _i64(dstStride), _vp(dJobs), _i64(n)))
+
+
+def _ctx_intra_filter_dev(self, depth, log2N, dSrc, dDst, n):
+    self._chk(self.L.x265b200_intra_filter_dev(self.h, depth, log2N, _vp(dSrc), _vp(dDst), _i64(n)))
+
+
+def _ctx_intra_allangs_dev(self, depth, log2N, dRef, dFilt, dDest, bLuma, n):
+    self._chk(self.L.x265b200_intra_allangs_dev(self.h, depth, log2N, _vp(dRef), _vp(dFilt), _vp(dDest), int(bLuma), _i64(n)))
+
+
+Ctx.dct_dev = _ctx_dct_dev
+Ctx.idct_dev = _ctx_idct_dev
+Ctx.quant_dev = _ctx_quant_dev
+Ctx.dequant_normal_dev = _ctx_dequant_normal_dev
+Ctx.dequant_scaling_dev = _ctx_dequant_scaling_dev
+Ctx.count_nonzero_dev = _ctx_count_nonzero_dev
+Ctx.interp_dev = _ctx_interp_dev
+Ctx.intra_pred_dev = _ctx_intra_pred_dev
+Ctx.intra_filter_dev = _ctx_intra_filter_dev
+Ctx.intra_allangs_dev = _ctx_intra_allangs_dev
+
+
+# ---- motion estimation -----------------------------------------------------------------------------
+ME_DIA, ME_HEX, ME_UMH, ME_STAR, ME_SEA, ME_FULL = range(6)
+ME_JOB = np.dtype([("puX", np.int32), ("puY", np.int32), ("w", np.int32), ("h", np.int32),
+                   ("mvminX", np.int32), ("mvminY", np.int32), ("mvmaxX", np.int32), ("mvmaxY", np.int32),
+                   ("mvpX", np.int32), ("mvpY", np.int32), ("numCand", np.int32), ("mvc", np.int32, (8, 2)),
+                   ("refIdx", np.int32), ("outMvX", np.int32), ("outMvY", np.int32), ("outCost", np.int32)])
+
+
+def lambda_for_qp(qp, depth=8):
+    f = load().x265b200_lambda
+    f.restype = ctypes.c_double
+    return float(f(int(qp), int(depth)))
+
+
+def bitcost_table(lam):
+    out = np.empty(4 * 32768 + 1, dtype=np.uint16)
+    if load().x265b200_bitcost_table(ctypes.c_double(lam), _vp(out)) != 0:
+        raise X265B200Error(load().x265b200_last_error().decode())
+    return out
+
+
+def _ctx_me_batch_dev(self, depth, dFenc, fencStride, dRef, refStride, dJobs, n, maxW, maxH, searchMethod, subpelRefine,
+                      merange, lam, maxSlices=1, dRefPlanes=None):
+    self._chk(self.L.x265b200_me_batch_dev(self.h, depth, _vp(dFenc), _i64(fencStride), _vp(dRef), _vp(dRefPlanes), _i64(refStride),
+                                           _vp(dJobs), _i64(n), int(maxW), int(maxH), int(searchMethod), int(subpelRefine),
+                                           int(merange), ctypes.c_double(lam), int(maxSlices)))
+
+
+Ctx.me_batch_dev = _ctx_me_batch_dev
+
+
+# ---- plane forms ---------------------------------------------------------------------------------
+def _ctx_dct_plane_dev(self, sizeIdx, depth, dPlane, stride, blocksX, blocksY, dCoef):
+    self._chk(self.L.x265b200_dct_plane_dev(self.h, sizeIdx, depth, _vp(dPlane), _i64(stride), int(blocksX), int(blocksY), _vp(dCoef)))
+
+
+def _ctx_idct_plane_dev(self, sizeIdx, depth, dCoef, dPlane, stride, blocksX, blocksY):
+    self._chk(self.L.x265b200_idct_plane_dev(self.h, sizeIdx, depth, _vp(dCoef), _vp(dPlane), _i64(stride), int(blocksX), int(blocksY)))
+
+
+def _ctx_sub_ps_plane_dev(self, depth, dA, strideA, dB, strideB, dDst, dstStride, w, h):
+    self._chk(self.L.x265b200_sub_ps_plane_dev(self.h, depth, _vp(dA), _i64(strideA), _vp(dB), _i64(strideB), _vp(dDst), _i64(dstStride), int(w), int(h)))
+
+
+def _ctx_add_ps_plane_dev(self, depth, dDst, dstStride, dPred, predStride, dResi, resiStride, w, h):
+    self._chk(self.L.x265b200_add_ps_plane_dev(self.h, depth, _vp(dDst), _i64(dstStride), _vp(dPred), _i64(predStride), _vp(dResi), _i64(resiStride), int(w), int(h)))
+
+
+Ctx.dct_plane_dev = _ctx_dct_plane_dev
+Ctx.idct_plane_dev = _ctx_idct_plane_dev
+Ctx.sub_ps_plane_dev = _ctx_sub_ps_plane_dev
+Ctx.add_ps_plane_dev = _ctx_add_ps_plane_dev

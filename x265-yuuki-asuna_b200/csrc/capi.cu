@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <cmath>
 
 namespace x265b200 {
 
@@ -67,6 +68,26 @@ int pixelcmp_dev(Ctx*, int kind, int depth, int w, int h, const void* A, int64_t
                  const int64_t* offA, const int64_t* offB, const int16_t* mv, int gridCols, int64_t n, void* out);
 int sad_xn_dev(Ctx*, int depth, int K, int w, int h, const void* fenc, int64_t fencBlockStride,
                const void* ref, int64_t refStride, const int64_t* refOff, int64_t n, int32_t* res);
+
+int transform_dev(Ctx*, int inverse, int sizeIdx, int depth, const int16_t* src, int64_t srcBlockStride, int64_t srcStride,
+                  int16_t* dst, int64_t dstBlockStride, int64_t dstStride, int64_t n, int64_t blocksPerRow, int64_t rowStride);
+int quant_dev(Ctx*, int isN, const int16_t* coef, const int32_t* quantCoeff, int32_t* deltaU, int16_t* qCoef,
+              int qBits, int add, int numCoeff, int64_t n, uint32_t* numSig);
+int dequant_dev(Ctx*, int scaling, const int16_t* q, const int32_t* deqCoef, int16_t* coef, int num, int64_t n, int scaleOrPer, int shift);
+int count_nonzero_dev(Ctx*, const int16_t* q, int numCoeff, int64_t n, int32_t* out);
+void host_dct_table(int N, int16_t* out);
+int interp_dev(Ctx*, int kind, int taps, int depth, int w, int h, const void* src, int64_t srcStride,
+               void* dst, int64_t dstStride, const x265b200_interp_job* jobs, int64_t n, int isRowExt);
+int intra_pred_dev(Ctx*, int depth, int log2N, const void* nbr, void* dst, int64_t dstStride, const x265b200_intra_job* jobs, int64_t n);
+int intra_filter_dev(Ctx*, int depth, int log2N, const void* src, void* dst, int64_t n);
+int intra_allangs_dev(Ctx*, int depth, int log2N, const void* refPix, const void* filtPix, void* dest, int bLuma, int64_t n);
+
+int me_batch_dev(Ctx*, int depth, const void* fencPlane, int64_t fencStride, const void* refPlane, const void* const* refPlanes,
+                 int64_t refStride, x265b200_me_job* jobs, int64_t n, int maxW, int maxH,
+                 int searchMethod, int subpelRefine, int merange, double lambda, int maxSlices);
+void host_bitcost_table(double lambda, uint16_t* out);
+int sub_ps_plane_dev(Ctx*, int depth, const void* a, int64_t strideA, const void* b, int64_t strideB, int16_t* dst, int64_t dstStride, int w, int h);
+int add_ps_plane_dev(Ctx*, int depth, void* dst, int64_t dstStride, const void* pred, int64_t predStride, const int16_t* resi, int64_t resiStride, int w, int h);
 
 } // namespace x265b200
 
@@ -188,6 +209,118 @@ int x265b200_sad_xn_dev(x265b200_ctx* ctx, int depth, int K, int w, int h, const
 {
     REQUIRE_CTX(ctx);
     return sad_xn_dev(CTX(ctx), depth, K, w, h, fenc, fencBlockStride, ref, refStride, refOff, n, res);
+}
+
+// ---- transforms ---------------------------------------------------------------------------------
+int x265b200_dct_dev(x265b200_ctx* ctx, int sizeIdx, int depth, const int16_t* src, int64_t srcBlockStride, int64_t srcStride, int16_t* dst, int64_t n)
+{
+    REQUIRE_CTX(ctx);
+    int N = sizeIdx == 4 ? 4 : (4 << sizeIdx);
+    return transform_dev(CTX(ctx), 0, sizeIdx, depth, src, srcBlockStride, srcStride, dst, (int64_t)N * N, N, n, 0, 0);
+}
+int x265b200_idct_dev(x265b200_ctx* ctx, int sizeIdx, int depth, const int16_t* src, int16_t* dst, int64_t dstBlockStride, int64_t dstStride, int64_t n)
+{
+    REQUIRE_CTX(ctx);
+    int N = sizeIdx == 4 ? 4 : (4 << sizeIdx);
+    return transform_dev(CTX(ctx), 1, sizeIdx, depth, src, (int64_t)N * N, N, dst, dstBlockStride, dstStride, n, 0, 0);
+}
+int x265b200_dct_plane_dev(x265b200_ctx* ctx, int sizeIdx, int depth, const int16_t* plane, int64_t stride, int blocksX, int blocksY, int16_t* coef)
+{
+    REQUIRE_CTX(ctx);
+    int N = sizeIdx == 4 ? 4 : (4 << sizeIdx);
+    return transform_dev(CTX(ctx), 0, sizeIdx, depth, plane, N, stride, coef, (int64_t)N * N, N, (int64_t)blocksX * blocksY, blocksX, (int64_t)N * stride);
+}
+int x265b200_idct_plane_dev(x265b200_ctx* ctx, int sizeIdx, int depth, const int16_t* coef, int16_t* plane, int64_t stride, int blocksX, int blocksY)
+{
+    REQUIRE_CTX(ctx);
+    int N = sizeIdx == 4 ? 4 : (4 << sizeIdx);
+    return transform_dev(CTX(ctx), 1, sizeIdx, depth, coef, (int64_t)N * N, N, plane, N, stride, (int64_t)blocksX * blocksY, blocksX, (int64_t)N * stride);
+}
+int x265b200_sub_ps_plane_dev(x265b200_ctx* ctx, int depth, const void* a, int64_t strideA, const void* b, int64_t strideB, int16_t* dst, int64_t dstStride, int w, int h)
+{
+    REQUIRE_CTX(ctx);
+    return sub_ps_plane_dev(CTX(ctx), depth, a, strideA, b, strideB, dst, dstStride, w, h);
+}
+int x265b200_add_ps_plane_dev(x265b200_ctx* ctx, int depth, void* dst, int64_t dstStride, const void* pred, int64_t predStride, const int16_t* resi, int64_t resiStride, int w, int h)
+{
+    REQUIRE_CTX(ctx);
+    return add_ps_plane_dev(CTX(ctx), depth, dst, dstStride, pred, predStride, resi, resiStride, w, h);
+}
+int x265b200_quant_dev(x265b200_ctx* ctx, const int16_t* coef, const int32_t* quantCoeff, int32_t* deltaU, int16_t* qCoef, int qBits, int add, int numCoeff, int64_t n, uint32_t* numSig)
+{
+    REQUIRE_CTX(ctx);
+    return quant_dev(CTX(ctx), 0, coef, quantCoeff, deltaU, qCoef, qBits, add, numCoeff, n, numSig);
+}
+int x265b200_nquant_dev(x265b200_ctx* ctx, const int16_t* coef, const int32_t* quantCoeff, int16_t* qCoef, int qBits, int add, int numCoeff, int64_t n, uint32_t* numSig)
+{
+    REQUIRE_CTX(ctx);
+    return quant_dev(CTX(ctx), 1, coef, quantCoeff, nullptr, qCoef, qBits, add, numCoeff, n, numSig);
+}
+int x265b200_dequant_normal_dev(x265b200_ctx* ctx, const int16_t* q, int16_t* coef, int num, int64_t n, int scale, int shift)
+{
+    REQUIRE_CTX(ctx);
+    return dequant_dev(CTX(ctx), 0, q, nullptr, coef, num, n, scale, shift);
+}
+int x265b200_dequant_scaling_dev(x265b200_ctx* ctx, const int16_t* q, const int32_t* deq, int16_t* coef, int num, int64_t n, int per, int shift)
+{
+    REQUIRE_CTX(ctx);
+    return dequant_dev(CTX(ctx), 1, q, deq, coef, num, n, per, shift);
+}
+int x265b200_count_nonzero_dev(x265b200_ctx* ctx, const int16_t* q, int numCoeff, int64_t n, int32_t* out)
+{
+    REQUIRE_CTX(ctx);
+    return count_nonzero_dev(CTX(ctx), q, numCoeff, n, out);
+}
+int x265b200_dct_table(int N, int16_t* out)
+{
+    if (N != 4 && N != 8 && N != 16 && N != 32) { set_error("dct_table: N=%d", N); return -1; }
+    host_dct_table(N, out);
+    return 0;
+}
+
+// ---- interpolation / intra ----------------------------------------------------------------------
+int x265b200_interp_dev(x265b200_ctx* ctx, int kind, int taps, int depth, int w, int h, const void* src, int64_t srcStride,
+                        void* dst, int64_t dstStride, const x265b200_interp_job* jobs, int64_t n, int isRowExt)
+{
+    REQUIRE_CTX(ctx);
+    return interp_dev(CTX(ctx), kind, taps, depth, w, h, src, srcStride, dst, dstStride, jobs, n, isRowExt);
+}
+int x265b200_intra_pred_dev(x265b200_ctx* ctx, int depth, int log2N, const void* nbr, void* dst, int64_t dstStride, const x265b200_intra_job* jobs, int64_t n)
+{
+    REQUIRE_CTX(ctx);
+    return intra_pred_dev(CTX(ctx), depth, log2N, nbr, dst, dstStride, jobs, n);
+}
+int x265b200_intra_filter_dev(x265b200_ctx* ctx, int depth, int log2N, const void* src, void* dst, int64_t n)
+{
+    REQUIRE_CTX(ctx);
+    return intra_filter_dev(CTX(ctx), depth, log2N, src, dst, n);
+}
+int x265b200_intra_allangs_dev(x265b200_ctx* ctx, int depth, int log2N, const void* refPix, const void* filtPix, void* dest, int bLuma, int64_t n)
+{
+    REQUIRE_CTX(ctx);
+    return intra_allangs_dev(CTX(ctx), depth, log2N, refPix, filtPix, dest, bLuma, n);
+}
+
+// ---- motion estimation ----------------------------------------------------------------------------
+int x265b200_me_batch_dev(x265b200_ctx* ctx, int depth, const void* fencPlane, int64_t fencStride,
+                          const void* refPlane, const void* const* refPlanes, int64_t refStride,
+                          x265b200_me_job* jobs, int64_t n, int maxW, int maxH,
+                          int searchMethod, int subpelRefine, int merange, double lambda, int maxSlices)
+{
+    REQUIRE_CTX(ctx);
+    return me_batch_dev(CTX(ctx), depth, fencPlane, fencStride, refPlane, refPlanes, refStride, jobs, n, maxW, maxH,
+                        searchMethod, subpelRefine, merange, lambda, maxSlices);
+}
+int x265b200_bitcost_table(double lambda, uint16_t* out)
+{
+    if (!out) { set_error("bitcost_table: out == NULL"); return -1; }
+    host_bitcost_table(lambda, out);
+    return 0;
+}
+double x265b200_lambda(int qp, int depth)
+{
+    double v = pow(2.0, (qp - 12) / 6.0 + (depth - 8));
+    return floor(v * 10000.0 + 0.5) / 10000.0;
 }
 
 } // extern "C"

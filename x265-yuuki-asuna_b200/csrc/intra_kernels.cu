@@ -1,0 +1,201 @@
+// intra_kernels.cu -- HEVC intra prediction (DC / planar / 33 angular modes, reference smoothing,
+// all-angles) as batched sm_100a kernels.  Every output pixel is a closed-form function of the
+// 4N+1 neighbour array, so one thread produces one pixel; the neighbour array is staged in smem.
+//
+// Reference semantics (bit-exact), source/common/intrapred.cpp:
+//   intraFilter<N>      :31-51    1:2:1 smoothing of [topLeft, top 2N, left 2N]
+//   intra_pred_dc_c     :69-85    dcVal = (N + sum)/(2N), optional edge filter :53-67
+//   planar_pred_c       :87-100
+//   intra_pred_ang_c    :102-204  horizontal modes = neighbour flip + transpose; angle==0 edge filter
+//   all_angs_pred_c     :206-234  33 NxN blocks, horizontal modes left un-transposed,
+//                                 filtered/unfiltered neighbours chosen by g_intraFilterFlags
+//                                 (constants.cpp:561) = |mode-26|,|mode-10| distance thresholds.
+// Roofline: HBM-bound, (4N+1) + N*N pixels per (block, mode).
+#include "common.cuh"
+#include "x265b200.h"
+
+namespace x265b200 {
+
+__constant__ int8_t  c_angle[17]   = { -32, -26, -21, -17, -13, -9, -5, -2, 0, 2, 5, 9, 13, 17, 21, 26, 32 };
+__constant__ int16_t c_invAngle[8] = { 4096, 1638, 910, 630, 482, 390, 315, 256 };
+
+// neighbours `s` are in the reference layout [0]=topLeft, [1..2N]=top, [2N+1..4N]=left.
+// Returns the UNFLIPPED angular prediction at (yy, xx) computed from flipped-or-not neighbours,
+// i.e. intra_pred_ang_c :126-189 with srcPix access redirected through nb().
+template<typename pixel>
+__device__ __forceinline__ int ang_pixel(const pixel* s, int N, int mode, int bFilter, int y, int x, int depth)
+{
+    const int N2 = N << 1;
+    const bool hor = mode < 18;
+    // flipped neighbour view (:111-120): nb(0)=s[0]; nb(1+i)=s[N2+1+i]; nb(N2+1+i)=s[1+i]
+    auto nb = [&](int i) -> int {
+        if (!hor || i == 0) return (int)s[i];
+        return i <= N2 ? (int)s[N2 + i] : (int)s[i - N2];
+    };
+    const int yy = hor ? x : y, xx = hor ? y : x;     // transpose back at the end (:192-203)
+    const int angleOffset = hor ? 10 - mode : mode - 26;
+    const int angle = c_angle[8 + angleOffset];
+    if (!angle)
+    {
+        if (bFilter && xx == 0)
+        {
+            int v = (int16_t)(nb(1) + ((nb(N2 + 1 + yy) - nb(0)) >> 1));
+            return clip3i(0, (1 << depth) - 1, v);
+        }
+        return nb(1 + xx);
+    }
+    const int angleSum = (yy + 1) * angle;
+    const int offset = angleSum >> 5, fraction = angleSum & 31;
+    // ref[idx] (:146-172)
+    auto ref = [&](int idx) -> int {
+        if (angle > 0 || idx >= -1) return nb(idx + 1);
+        int i = -2 - idx;
+        int invAngleSum = 128 + (i + 1) * c_invAngle[-angleOffset - 1];
+        return nb(N2 + (invAngleSum >> 8));
+    };
+    if (fraction)
+        return ((32 - fraction) * ref(offset + xx) + fraction * ref(offset + xx + 1) + 16) >> 5;
+    return ref(offset + xx);
+}
+
+template<typename pixel>
+__device__ __forceinline__ int intra_pixel(const pixel* s, int N, int log2N, int mode, int bFilter, int y, int x, int depth, int dcVal)
+{
+    const int N2 = N << 1;
+    if (mode == 0)        // planar :87-100
+    {
+        const pixel* above = s + 1; const pixel* left = s + N2 + 1;
+        return ((N - 1 - x) * left[y] + (N - 1 - y) * above[x] + (x + 1) * above[N] + (y + 1) * left[N] + N) >> (log2N + 1);
+    }
+    if (mode == 1)        // DC :69-85 (+ dcPredFilter :53-67)
+    {
+        if (!bFilter) return dcVal;
+        const pixel* above = s + 1; const pixel* left = s + N2 + 1;
+        if (x == 0 && y == 0) return (above[0] + left[0] + 2 * dcVal + 2) >> 2;
+        if (y == 0) return (above[x] + 3 * dcVal + 2) >> 2;
+        if (x == 0) return (left[y] + 3 * dcVal + 2) >> 2;
+        return dcVal;
+    }
+    return ang_pixel<pixel>(s, N, mode, bFilter, y, x, depth);
+}
+
+struct IntraArgs
+{
+    const void* nbr;          // neighbour arrays
+    void* dst; int64_t dstStride;
+    const x265b200_intra_job* jobs; int64_t n;
+    int log2N, depth;
+};
+
+template<typename pixel>
+__global__ void __launch_bounds__(256)
+intra_pred_kernel(IntraArgs p)
+{
+    __shared__ pixel s[132];
+    __shared__ int sDc;
+    const x265b200_intra_job job = p.jobs[blockIdx.x];
+    const int N = 1 << p.log2N;
+    const pixel* src = (const pixel*)p.nbr + job.srcOff;
+    for (int i = threadIdx.x; i < 4 * N + 1; i += blockDim.x) s[i] = src[i];
+    __syncthreads();
+    if (job.mode == 1)
+    {
+        if (threadIdx.x < 32)
+        {
+            int v = 0;
+            for (int i = threadIdx.x; i < N; i += 32) v += s[1 + i] + s[2 * N + 1 + i];
+            v = warp_sum(v);
+            if (threadIdx.x == 0) sDc = (N + v) / (N + N);
+        }
+        __syncthreads();
+    }
+    const int dc = job.mode == 1 ? sDc : 0;
+    pixel* d = (pixel*)p.dst + job.dstOff;
+    for (int e = threadIdx.x; e < N * N; e += blockDim.x)
+    {
+        int y = e >> p.log2N, x = e & (N - 1);
+        d[(int64_t)y * p.dstStride + x] = (pixel)intra_pixel<pixel>(s, N, p.log2N, job.mode, job.bFilter, y, x, p.depth, dc);
+    }
+}
+
+// intraFilter<N> :31-51, n neighbour arrays of 4N+1 pixels at srcOff/dstOff = i*(4N+1) unless jobs given
+template<typename pixel>
+__global__ void __launch_bounds__(128)
+intra_filter_kernel(const pixel* __restrict__ src, pixel* __restrict__ dst, int N, int64_t n)
+{
+    const int64_t b = blockIdx.x;
+    const int len = 4 * N + 1, N2 = 2 * N;
+    const pixel* s = src + b * len;
+    pixel* f = dst + b * len;
+    for (int i = threadIdx.x; i < len; i += blockDim.x)
+    {
+        int v;
+        if (i == 0) v = ((s[0] << 1) + s[1] + s[N2 + 1] + 2) >> 2;
+        else if (i == N2 || i == 2 * N2) v = s[i];
+        else if (i == N2 + 1) v = ((s[N2 + 1] << 1) + s[0] + s[N2 + 2] + 2) >> 2;
+        else v = ((s[i] << 1) + s[i - 1] + s[i + 1] + 2) >> 2;
+        f[i] = (pixel)v;
+    }
+}
+
+// all_angs_pred_c :206-234: block b -> dest[b][33][N*N]; refPix/filtPix are [n][4N+1]
+template<typename pixel>
+__global__ void __launch_bounds__(256)
+intra_allangs_kernel(const pixel* __restrict__ refPix, const pixel* __restrict__ filtPix, pixel* __restrict__ dest,
+                     int log2N, int bLuma, int depth, int64_t n)
+{
+    __shared__ pixel sr[132], sf[132];
+    const int N = 1 << log2N, len = 4 * N + 1;
+    const int64_t b = blockIdx.x;
+    for (int i = threadIdx.x; i < len; i += blockDim.x) { sr[i] = refPix[b * len + i]; sf[i] = filtPix[b * len + i]; }
+    __syncthreads();
+    pixel* out = dest + b * 33 * N * N;
+    // smoothing thresholds (constants.cpp:561): filtered when min(|m-26|,|m-10|) > {7,1,0} for N = 8,16,32; never for 4
+    const int thr = N == 8 ? 7 : (N == 16 ? 1 : (N == 32 ? 0 : 99));
+    for (int e = threadIdx.x; e < 33 * N * N; e += blockDim.x)
+    {
+        int m = e >> (2 * log2N), r = e & (N * N - 1);
+        int mode = m + 2;
+        int y = r >> log2N, x = r & (N - 1);
+        int dist = min(abs(mode - 26), abs(mode - 10));
+        const pixel* s = dist > thr ? sf : sr;
+        // horizontal modes are stored un-transposed (:217-232): out[y][x] = pred(x, y)
+        int v = mode < 18 ? ang_pixel<pixel>(s, N, mode, bLuma, x, y, depth) : ang_pixel<pixel>(s, N, mode, bLuma, y, x, depth);
+        out[e] = (pixel)v;
+    }
+}
+
+int intra_pred_dev(Ctx* ctx, int depth, int log2N, const void* nbr, void* dst, int64_t dstStride,
+                   const x265b200_intra_job* jobs, int64_t n)
+{
+    if (n <= 0) return 0;
+    if (log2N < 2 || log2N > 5) { set_error("intra: log2N %d", log2N); return -1; }
+    IntraArgs a; a.nbr = nbr; a.dst = dst; a.dstStride = dstStride; a.jobs = jobs; a.n = n; a.log2N = log2N; a.depth = depth;
+    int threads = (1 << (2 * log2N)) < 256 ? max(32, 1 << (2 * log2N)) : 256;
+    if (depth > 8) intra_pred_kernel<uint16_t><<<(unsigned)n, threads, 0, ctx->stream>>>(a);
+    else           intra_pred_kernel<uint8_t><<<(unsigned)n, threads, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    return check(cudaGetLastError(), "intra_pred kernel launch");
+}
+
+int intra_filter_dev(Ctx* ctx, int depth, int log2N, const void* src, void* dst, int64_t n)
+{
+    if (n <= 0) return 0;
+    if (log2N < 2 || log2N > 5) { set_error("intra_filter: log2N %d", log2N); return -1; }
+    if (depth > 8) intra_filter_kernel<uint16_t><<<(unsigned)n, 128, 0, ctx->stream>>>((const uint16_t*)src, (uint16_t*)dst, 1 << log2N, n);
+    else           intra_filter_kernel<uint8_t><<<(unsigned)n, 128, 0, ctx->stream>>>((const uint8_t*)src, (uint8_t*)dst, 1 << log2N, n);
+    ctx->launches++;
+    return check(cudaGetLastError(), "intra_filter kernel launch");
+}
+
+int intra_allangs_dev(Ctx* ctx, int depth, int log2N, const void* refPix, const void* filtPix, void* dest, int bLuma, int64_t n)
+{
+    if (n <= 0) return 0;
+    if (log2N < 2 || log2N > 5) { set_error("intra_allangs: log2N %d", log2N); return -1; }
+    if (depth > 8) intra_allangs_kernel<uint16_t><<<(unsigned)n, 256, 0, ctx->stream>>>((const uint16_t*)refPix, (const uint16_t*)filtPix, (uint16_t*)dest, log2N, bLuma, depth, n);
+    else           intra_allangs_kernel<uint8_t><<<(unsigned)n, 256, 0, ctx->stream>>>((const uint8_t*)refPix, (const uint8_t*)filtPix, (uint8_t*)dest, log2N, bLuma, depth, n);
+    ctx->launches++;
+    return check(cudaGetLastError(), "intra_allangs kernel launch");
+}
+
+} // namespace x265b200

@@ -1,0 +1,156 @@
+// me_kernels.cu -- batched full-resolution motion estimation: one warp per PU search, bit-exact
+// with MotionEstimate::motionEstimate (source/encoder/motion.cpp:739-1569) for
+// DIA / HEX / UMH / STAR / FULL integer search + hpel/qpel refinement (luma; chroma SATD of
+// subme > 2 is a "next" row).  The device algorithm lives in me_device.cuh.
+//
+// Also here: the BitCost lambda-scaled MV cost table (source/encoder/bitcost.cpp:31-110), built on
+// the HOST with the reference's own float/double expression order and uploaded once per lambda.
+//
+// Roofline: bytes = 2*W*H*sizeof(pixel) + nPU*8 per frame pair; the pattern search
+// itself is ALU/latency-bound (DESIGN.md "ME arithmetic"), the planes stay L2-resident.
+#include "me_device.cuh"
+#include "x265b200.h"
+#include <cmath>
+#include <vector>
+
+namespace x265b200 {
+
+// bitcost.cpp:95-110 CalculateLogs + :31-60 setQP.  `log` is the double overload applied to a float
+// argument, multiplied by the float 2/log(2) (double arithmetic), rounded to float on store.
+void host_bitcost_table(double lambda, uint16_t* out /* 4*32768+1, centred at out[2*32768] */)
+{
+    const int M = 32768;
+    static std::vector<float> bits;
+    if (bits.empty())
+    {
+        bits.resize(2 * M + 1);
+        bits[0] = 0.718f;
+        // NB: inside a .cu file `log(float)` would bind to CUDA's float overload; the reference (plain
+        // g++) calls the double `log`, so spell the promotions out.
+        float log2_2 = (float)((double)2.0f / log((double)2.0f));
+        for (int i = 1; i <= 2 * M; i++)
+            bits[i] = (float)(log((double)(float)(i + 1)) * (double)log2_2 + (double)1.718f);
+    }
+    uint16_t* c = out + 2 * M;
+    for (int i = 0; i <= 2 * M; i++)
+    {
+        double v = (double)bits[i] * lambda + (double)0.5f;
+        double lim = (1 << 15) - 1;
+        c[i] = c[-i] = (uint16_t)(v < lim ? v : lim);
+    }
+}
+
+int ensure_mvcost(Ctx* ctx, double lambda)
+{
+    if (ctx->mvCostValid && ctx->mvCostLambda == lambda) return 0;
+    const size_t n = 4 * 32768 + 1;
+    if (!ctx->dMvCost) X265B200_CHECK(cudaMalloc((void**)&ctx->dMvCost, (n + 3) * sizeof(uint16_t)));
+    std::vector<uint16_t> h(n);
+    host_bitcost_table(lambda, h.data());
+    X265B200_CHECK(cudaStreamSynchronize(ctx->stream));
+    X265B200_CHECK(cudaMemcpy(ctx->dMvCost, h.data(), n * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    ctx->mvCostLambda = lambda; ctx->mvCostValid = true;
+    return 0;
+}
+
+struct MEArgs
+{
+    const void* fencPlane; int64_t fencStride;
+    const void* const* refPlanes;     // device array of plane pointers (indexed by job.refIdx), or nullptr
+    const void* refPlane0; int64_t refStride;
+    x265b200_me_job* jobs; int64_t n;
+    const uint16_t* cost;
+    int searchMethod, subpelRefine, merange, maxSlices, depth;
+    int maxW, maxH;
+};
+
+constexpr int ME_WARPS = 4;
+
+template<typename pixel>
+__global__ void __launch_bounds__(ME_WARPS * 32)
+me_batch_kernel(MEArgs p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t fencBytes = (size_t)64 * p.maxH * sizeof(pixel);
+    const size_t predBytes = ((size_t)p.maxW * p.maxH * sizeof(pixel) + 15) & ~(size_t)15;
+    const size_t immedBytes = ((size_t)p.maxW * (p.maxH + 7) * sizeof(int16_t) + 15) & ~(size_t)15;
+    unsigned char* base = smem + warp * (fencBytes + predBytes + immedBytes);
+
+    const int64_t j = (int64_t)blockIdx.x * ME_WARPS + warp;
+    if (j >= p.n) return;
+    x265b200_me_job job = p.jobs[j];
+
+    MEState<pixel> s;
+    s.fenc = (pixel*)base;
+    s.pred = (pixel*)(base + fencBytes);
+    s.immed = (int16_t*)(base + fencBytes + predBytes);
+    s.stride = p.refStride;
+    const pixel* refPlane = (const pixel*)(p.refPlanes ? p.refPlanes[job.refIdx] : p.refPlane0);
+    s.fref = refPlane + job.puX + (int64_t)job.puY * p.refStride;
+    s.isLowres = false;
+    s.w = job.w; s.h = job.h; s.lane = lane; s.depth = p.depth;
+    s.partSizeScale = (job.h * job.h) >> 4;                      // motion.cpp:125-126 sizeScale
+    s.cost = p.cost + 2 * 32768;
+    s.mvpx = job.mvpX; s.mvpy = job.mvpY;
+
+    // setSourcePU: copy the PU into the 64-stride cache (motion.cpp:188-189)
+    const pixel* fp = (const pixel*)p.fencPlane + job.puX + (int64_t)job.puY * p.fencStride;
+    const int gw = job.w >> 2;
+    for (int u = lane; u < gw * job.h; u += 32)
+    {
+        int y = u / gw, x = (u - y * gw) << 2;
+        if (sizeof(pixel) == 1) *(uint32_t*)((uint8_t*)s.fenc + y * 64 + x) = ld_px4((const uint8_t*)fp + (int64_t)y * p.fencStride + x);
+        else
+        {
+            uint32_t* d = (uint32_t*)((uint16_t*)s.fenc + y * 64 + x);
+            const uint16_t* q = (const uint16_t*)fp + (int64_t)y * p.fencStride + x;
+            d[0] = ld_px2(q); d[1] = ld_px2(q + 2);
+        }
+    }
+    __syncwarp();
+
+    int ox, oy;
+    int cost = motion_estimate<pixel>(s, mv2(job.mvminX, job.mvminY), mv2(job.mvmaxX, job.mvmaxY), mv2(job.mvpX, job.mvpY),
+                                      job.numCand, &job.mvc[0][0], p.merange, p.searchMethod, p.subpelRefine, p.maxSlices,
+                                      (job.w == 64 && job.h == 64), ox, oy);
+    if (lane == 0)
+    {
+        p.jobs[j].outMvX = ox; p.jobs[j].outMvY = oy; p.jobs[j].outCost = cost;
+    }
+}
+
+int me_batch_dev(Ctx* ctx, int depth, const void* fencPlane, int64_t fencStride, const void* refPlane, const void* const* refPlanes,
+                 int64_t refStride, x265b200_me_job* jobs, int64_t n, int maxW, int maxH,
+                 int searchMethod, int subpelRefine, int merange, double lambda, int maxSlices)
+{
+    if (n <= 0) return 0;
+    if (searchMethod == ME_SEA) { set_error("me_batch: --me sea needs the SEA integral planes (next row, SURVEY.md 8f-3)"); return -1; }
+    if (searchMethod < 0 || searchMethod > ME_FULL) { set_error("me_batch: searchMethod %d", searchMethod); return -1; }
+    if (subpelRefine < 0 || subpelRefine > 7) { set_error("me_batch: subpelRefine %d", subpelRefine); return -1; }
+    if (maxW < 8 && maxH < 8) { set_error("me_batch: inter PUs are at least 8x4 / 4x8"); return -1; }
+    if (maxW > 64 || maxH > 64 || (maxW & 3) || (maxH & 3)) { set_error("me_batch: maxW/maxH %dx%d", maxW, maxH); return -1; }
+    if (ensure_mvcost(ctx, lambda)) return -1;
+    MEArgs a;
+    a.fencPlane = fencPlane; a.fencStride = fencStride; a.refPlanes = refPlanes; a.refPlane0 = refPlane; a.refStride = refStride;
+    a.jobs = jobs; a.n = n; a.cost = ctx->dMvCost; a.searchMethod = searchMethod; a.subpelRefine = subpelRefine;
+    a.merange = merange; a.maxSlices = maxSlices; a.depth = depth; a.maxW = maxW; a.maxH = maxH;
+    const size_t px = depth > 8 ? 2 : 1;
+    size_t perWarp = (size_t)64 * maxH * px + (((size_t)maxW * maxH * px + 15) & ~(size_t)15) + (((size_t)maxW * (maxH + 7) * 2 + 15) & ~(size_t)15);
+    size_t smem = perWarp * ME_WARPS;
+    unsigned blocks = (unsigned)((n + ME_WARPS - 1) / ME_WARPS);
+    if (depth > 8)
+    {
+        X265B200_CHECK(cudaFuncSetAttribute(me_batch_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        me_batch_kernel<uint16_t><<<blocks, ME_WARPS * 32, smem, ctx->stream>>>(a);
+    }
+    else
+    {
+        X265B200_CHECK(cudaFuncSetAttribute(me_batch_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        me_batch_kernel<uint8_t><<<blocks, ME_WARPS * 32, smem, ctx->stream>>>(a);
+    }
+    ctx->launches++;
+    return check(cudaGetLastError(), "me_batch kernel launch");
+}
+
+} // namespace x265b200

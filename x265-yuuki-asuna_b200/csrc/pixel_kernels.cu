@@ -352,4 +352,52 @@ int sad_xn_dev(Ctx* ctx, int depth, int K, int w, int h, const void* fenc, int64
     return check(cudaGetLastError(), "sad_xn_kernel launch");
 }
 
+// ---------------------------------------------------------------------------------------------
+// plane-wide sub_ps / add_ps (pixel.cpp:814-840): 4 pixels per thread
+// ---------------------------------------------------------------------------------------------
+template<typename pixel>
+__global__ void __launch_bounds__(256)
+sub_ps_plane_kernel(const pixel* __restrict__ a, int64_t sa, const pixel* __restrict__ b, int64_t sb, int16_t* __restrict__ d, int64_t sd, int w, int h)
+{
+    const int gw = (w + 3) >> 2;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)gw * h) return;
+    int y = (int)(i / gw), x = (int)(i - (int64_t)y * gw) << 2;
+    for (int k = 0; k < 4 && x + k < w; k++)
+        d[y * sd + x + k] = (int16_t)((int)a[y * sa + x + k] - (int)b[y * sb + x + k]);
+}
+template<typename pixel>
+__global__ void __launch_bounds__(256)
+add_ps_plane_kernel(pixel* __restrict__ d, int64_t sd, const pixel* __restrict__ p, int64_t sp, const int16_t* __restrict__ r, int64_t sr, int w, int h, int maxVal)
+{
+    const int gw = (w + 3) >> 2;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)gw * h) return;
+    int y = (int)(i / gw), x = (int)(i - (int64_t)y * gw) << 2;
+    for (int k = 0; k < 4 && x + k < w; k++)
+        d[y * sd + x + k] = (pixel)clip3i(0, maxVal, (int)p[y * sp + x + k] + (int)r[y * sr + x + k]);
+}
+
+int sub_ps_plane_dev(Ctx* ctx, int depth, const void* a, int64_t strideA, const void* b, int64_t strideB, int16_t* dst, int64_t dstStride, int w, int h)
+{
+    int64_t n = (int64_t)((w + 3) >> 2) * h;
+    if (n <= 0) return 0;
+    unsigned blocks = (unsigned)((n + 255) / 256);
+    if (depth > 8) sub_ps_plane_kernel<uint16_t><<<blocks, 256, 0, ctx->stream>>>((const uint16_t*)a, strideA, (const uint16_t*)b, strideB, dst, dstStride, w, h);
+    else           sub_ps_plane_kernel<uint8_t><<<blocks, 256, 0, ctx->stream>>>((const uint8_t*)a, strideA, (const uint8_t*)b, strideB, dst, dstStride, w, h);
+    ctx->launches++;
+    return check(cudaGetLastError(), "sub_ps_plane launch");
+}
+
+int add_ps_plane_dev(Ctx* ctx, int depth, void* dst, int64_t dstStride, const void* pred, int64_t predStride, const int16_t* resi, int64_t resiStride, int w, int h)
+{
+    int64_t n = (int64_t)((w + 3) >> 2) * h;
+    if (n <= 0) return 0;
+    unsigned blocks = (unsigned)((n + 255) / 256);
+    if (depth > 8) add_ps_plane_kernel<uint16_t><<<blocks, 256, 0, ctx->stream>>>((uint16_t*)dst, dstStride, (const uint16_t*)pred, predStride, resi, resiStride, w, h, (1 << depth) - 1);
+    else           add_ps_plane_kernel<uint8_t><<<blocks, 256, 0, ctx->stream>>>((uint8_t*)dst, dstStride, (const uint8_t*)pred, predStride, resi, resiStride, w, h, 255);
+    ctx->launches++;
+    return check(cudaGetLastError(), "add_ps_plane launch");
+}
+
 } // namespace x265b200

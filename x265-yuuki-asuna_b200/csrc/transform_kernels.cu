@@ -1,0 +1,493 @@
+// transform_kernels.cu -- HEVC core transforms and quantisation as batched sm_100a kernels.
+//
+// Reference semantics (bit-exact):
+//   dct4/8/16/32_c, dst4_c     source/common/dct.cpp:442-525 (butterflies :83-240, :418-440)
+//   idct4/8/16/32_c, idst4_c   source/common/dct.cpp:527-610 (inverse butterflies :242-416, :63-81)
+//   quant_c / nquant_c         source/common/dct.cpp:664-713
+//   dequant_normal/scaling_c   source/common/dct.cpp:612-662
+//   count_nonzero / copy_count / denoiseDct   source/common/dct.cpp:714-755
+//
+// The partial butterflies of the reference are an exact factorisation of the dense product
+//       pass(In)[k][j] = ( sum_n T[k][n] * In[j][n] + add ) >> shift
+// (all arithmetic is in the ring Z/2^32, so re-association cannot change a bit), forward DCT =
+// two such passes with T = g_tN, the result WRAPPED to int16 (dct.cpp:113); the inverse = two
+// passes with T^T, each SATURATED to int16 (dct.cpp:257).  For N = 8/16/32 the dense product runs
+// on the integer tensor cores (IMMA, mma.sync m16n8k32 / m16n8k16 s8): coefficients (|c| <= 90)
+// are s8, int16 samples are split x = 256*hi + lo with hi s8 and lo u8, so
+//       T*x = 256*(T*hi) + (T*lo)      exactly in s32.
+// 4x4 (DCT and DST) is scalar, one thread per block.
+//
+// Roofline: HBM-bound when streamed (4*N^2 bytes per block in+out vs 4*N^3 MACs);
+// DESIGN.md lists the per-size ridge points.
+#include "common.cuh"
+#include "tables.cuh"
+#include "x265b200.h"
+
+namespace x265b200 {
+
+__constant__ int c_dctMag[33];
+static bool g_tablesUploaded[16] = { false };
+
+static int upload_tables(Ctx* ctx)
+{
+    if (ctx->device < 16 && g_tablesUploaded[ctx->device]) return 0;
+    X265B200_CHECK(cudaMemcpyToSymbolAsync(c_dctMag, kDctMag, sizeof(kDctMag), 0, cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->device < 16) g_tablesUploaded[ctx->device] = true;
+    return 0;
+}
+
+__device__ __forceinline__ int dct_coef_dev(int N, int k, int n)
+{
+    int m = ((2 * n + 1) * k * (32 / N)) & 127;
+    if (m > 64) m = 128 - m;
+    return m > 32 ? -c_dctMag[64 - m] : c_dctMag[m];
+}
+
+// M[k][n]: forward uses T[k][n], inverse uses T[n][k]
+__device__ __forceinline__ int mcoef(int N, bool inverse, int k, int n)
+{
+    return inverse ? dct_coef_dev(N, n, k) : dct_coef_dev(N, k, n);
+}
+
+__device__ __forceinline__ uint32_t pack4(int b0, int b1, int b2, int b3)
+{
+    return (uint32_t)(b0 & 0xff) | ((uint32_t)(b1 & 0xff) << 8) | ((uint32_t)(b2 & 0xff) << 16) | ((uint32_t)(b3 & 0xff) << 24);
+}
+
+__device__ __forceinline__ void mma_k32_s8u8(int d[4], const uint32_t a[4], uint32_t b0, uint32_t b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mma_k32_s8s8(int d[4], const uint32_t a[4], uint32_t b0, uint32_t b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mma_k16_s8u8(int d[4], const uint32_t a[2], uint32_t b0)
+{
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};\n"
+                 : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(b0));
+}
+__device__ __forceinline__ void mma_k16_s8s8(int d[4], const uint32_t a[2], uint32_t b0)
+{
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};\n"
+                 : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(b0));
+}
+
+template<bool SAT> __device__ __forceinline__ int finish(int hi, int lo, int add, int shift)
+{
+    int v = (int)((uint32_t)hi * 256u + (uint32_t)lo);
+    v = (v + add) >> shift;
+    if (SAT) v = clip3i(-32768, 32767, v);
+    return v & 0xffff;     // int16 wrap (forward) / already in range (inverse)
+}
+
+// LD (row pitch in int16) of the per-warp smem tiles
+template<int N> struct Tile { static constexpr int LD = N + 8; static constexpr int ELEMS = N * (N + 8); };
+
+// One dense pass on a 32x32 tile held in smem: Out[k][j] = f(sum_n M[k][n] In[j][n])
+template<bool SAT>
+__device__ __forceinline__ void pass32(const uint32_t a[2][4], const int16_t* In, int16_t* Out, int add, int shift, int gid, int tig)
+{
+    constexpr int LD = Tile<32>::LD;
+#pragma unroll
+    for (int ni = 0; ni < 4; ni++)
+    {
+        const int16_t* p = In + (8 * ni + gid) * LD + 4 * tig;
+        uint2 w0 = *(const uint2*)p, w1 = *(const uint2*)(p + 16);
+        uint32_t b0lo = __byte_perm(w0.x, w0.y, 0x6420), b0hi = __byte_perm(w0.x, w0.y, 0x7531);
+        uint32_t b1lo = __byte_perm(w1.x, w1.y, 0x6420), b1hi = __byte_perm(w1.x, w1.y, 0x7531);
+#pragma unroll
+        for (int mi = 0; mi < 2; mi++)
+        {
+            int lo[4] = { 0, 0, 0, 0 }, hi[4] = { 0, 0, 0, 0 };
+            mma_k32_s8u8(lo, a[mi], b0lo, b1lo);
+            mma_k32_s8s8(hi, a[mi], b0hi, b1hi);
+            int r0 = finish<SAT>(hi[0], lo[0], add, shift), r1 = finish<SAT>(hi[1], lo[1], add, shift);
+            int r2 = finish<SAT>(hi[2], lo[2], add, shift), r3 = finish<SAT>(hi[3], lo[3], add, shift);
+            *(uint32_t*)(Out + (16 * mi + gid) * LD + 8 * ni + 2 * tig) = (uint32_t)r0 | ((uint32_t)r1 << 16);
+            *(uint32_t*)(Out + (16 * mi + gid + 8) * LD + 8 * ni + 2 * tig) = (uint32_t)r2 | ((uint32_t)r3 << 16);
+        }
+    }
+}
+
+template<bool SAT>
+__device__ __forceinline__ void pass16(const uint32_t a[2], const int16_t* In, int16_t* Out, int add, int shift, int gid, int tig)
+{
+    constexpr int LD = Tile<16>::LD;
+#pragma unroll
+    for (int ni = 0; ni < 2; ni++)
+    {
+        const int16_t* p = In + (8 * ni + gid) * LD + 4 * tig;
+        uint2 w0 = *(const uint2*)p;
+        uint32_t blo = __byte_perm(w0.x, w0.y, 0x6420), bhi = __byte_perm(w0.x, w0.y, 0x7531);
+        int lo[4] = { 0, 0, 0, 0 }, hi[4] = { 0, 0, 0, 0 };
+        mma_k16_s8u8(lo, a, blo);
+        mma_k16_s8s8(hi, a, bhi);
+        int r0 = finish<SAT>(hi[0], lo[0], add, shift), r1 = finish<SAT>(hi[1], lo[1], add, shift);
+        int r2 = finish<SAT>(hi[2], lo[2], add, shift), r3 = finish<SAT>(hi[3], lo[3], add, shift);
+        *(uint32_t*)(Out + gid * LD + 8 * ni + 2 * tig) = (uint32_t)r0 | ((uint32_t)r1 << 16);
+        *(uint32_t*)(Out + (gid + 8) * LD + 8 * ni + 2 * tig) = (uint32_t)r2 | ((uint32_t)r3 << 16);
+    }
+}
+
+// Two 8x8 blocks per mma through a block-diagonal A: rows 0-7 x k 0-7 = M8 (block 0),
+// rows 8-15 x k 8-15 = M8 (block 1).  In/Out hold the two blocks back to back ([2][8][LD]).
+template<bool SAT>
+__device__ __forceinline__ void pass8(const uint32_t a[2], const int16_t* In, int16_t* Out, int add, int shift, int gid, int tig)
+{
+    constexpr int LD = Tile<8>::LD;
+    const int blk = tig >> 1;                                   // k 0..7 -> block 0, k 8..15 -> block 1
+    const int16_t* p = In + blk * 8 * LD + gid * LD + 4 * (tig & 1);
+    uint2 w0 = *(const uint2*)p;
+    uint32_t blo = __byte_perm(w0.x, w0.y, 0x6420), bhi = __byte_perm(w0.x, w0.y, 0x7531);
+    int lo[4] = { 0, 0, 0, 0 }, hi[4] = { 0, 0, 0, 0 };
+    mma_k16_s8u8(lo, a, blo);
+    mma_k16_s8s8(hi, a, bhi);
+    int r0 = finish<SAT>(hi[0], lo[0], add, shift), r1 = finish<SAT>(hi[1], lo[1], add, shift);
+    int r2 = finish<SAT>(hi[2], lo[2], add, shift), r3 = finish<SAT>(hi[3], lo[3], add, shift);
+    *(uint32_t*)(Out + gid * LD + 2 * tig) = (uint32_t)r0 | ((uint32_t)r1 << 16);                 // block 0: R[k=gid][j]
+    *(uint32_t*)(Out + 8 * LD + gid * LD + 2 * tig) = (uint32_t)r2 | ((uint32_t)r3 << 16);        // block 1
+}
+
+struct XformArgs
+{
+    const int16_t* src; int64_t srcBlockStride; int64_t srcStride;   // forward: strided src, contiguous dst
+    int16_t* dst;       int64_t dstBlockStride; int64_t dstStride;   // inverse: contiguous src, strided dst
+    int64_t n;
+    int64_t bpr;          // blocks per row of a 2-D block grid (>= n: plain linear list)
+    int64_t srcRowStride, dstRowStride;   // element offset between block rows of the grid
+    int shift1, shift2;
+};
+
+__device__ __forceinline__ int64_t xf_src_off(const XformArgs& p, int64_t b) { return (b / p.bpr) * p.srcRowStride + (b % p.bpr) * p.srcBlockStride; }
+__device__ __forceinline__ int64_t xf_dst_off(const XformArgs& p, int64_t b) { return (b / p.bpr) * p.dstRowStride + (b % p.bpr) * p.dstBlockStride; }
+
+constexpr int XF_WARPS = 8;
+
+// N = 32 or 16: one block per warp-iteration.  N = 8: two blocks per warp-iteration.
+template<int N, bool INVERSE>
+__global__ void __launch_bounds__(XF_WARPS * 32)
+xform_mma_kernel(XformArgs p)
+{
+    constexpr int LD = Tile<N>::LD;
+    constexpr int PER = (N == 8) ? 2 : 1;
+    constexpr int TILE = PER * N * LD;
+    __shared__ __align__(16) int16_t smem[XF_WARPS][2][TILE];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
+    int16_t* bufA = smem[warp][0];
+    int16_t* bufB = smem[warp][1];
+
+    // A fragments (coefficient matrix) live in registers for the whole kernel
+    uint32_t a32[2][4]; uint32_t a16[2];
+    if (N == 32)
+    {
+#pragma unroll
+        for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+            {
+                int row = 16 * mi + gid + ((r & 1) ? 8 : 0), k0 = 4 * tig + ((r & 2) ? 16 : 0);
+                a32[mi][r] = pack4(mcoef(32, INVERSE, row, k0), mcoef(32, INVERSE, row, k0 + 1), mcoef(32, INVERSE, row, k0 + 2), mcoef(32, INVERSE, row, k0 + 3));
+            }
+    }
+    else if (N == 16)
+    {
+#pragma unroll
+        for (int r = 0; r < 2; r++)
+        {
+            int row = gid + 8 * r, k0 = 4 * tig;
+            a16[r] = pack4(mcoef(16, INVERSE, row, k0), mcoef(16, INVERSE, row, k0 + 1), mcoef(16, INVERSE, row, k0 + 2), mcoef(16, INVERSE, row, k0 + 3));
+        }
+    }
+    else
+    {
+        int k0 = 4 * (tig & 1);
+        uint32_t v = pack4(mcoef(8, INVERSE, gid, k0), mcoef(8, INVERSE, gid, k0 + 1), mcoef(8, INVERSE, gid, k0 + 2), mcoef(8, INVERSE, gid, k0 + 3));
+        a16[0] = (tig < 2) ? v : 0u;      // rows 0-7 see k 0-7
+        a16[1] = (tig >= 2) ? v : 0u;     // rows 8-15 see k 8-15
+    }
+
+    const int add1 = 1 << (p.shift1 - 1), add2 = 1 << (p.shift2 - 1);
+    const int64_t units = (p.n + PER - 1) / PER;
+    for (int64_t u = (int64_t)blockIdx.x * XF_WARPS + warp; u < units; u += (int64_t)gridDim.x * XF_WARPS)
+    {
+        // ---- load: In[j][n] = src[j][n] (forward) or src[n][j] (inverse, contiguous NxN) ----
+#pragma unroll
+        for (int s = 0; s < PER; s++)
+        {
+            int64_t b = u * PER + s;
+            int16_t* tile = bufA + s * N * LD;
+            if (b < p.n)
+            {
+                const int16_t* sp = p.src + xf_src_off(p, b);
+                for (int e = lane; e < N * N / 2; e += 32)
+                {
+                    int row = (2 * e) / N, col = (2 * e) % N;
+                    uint32_t w = ld_px2((const uint16_t*)(sp + (INVERSE ? (int64_t)row * N : (int64_t)row * p.srcStride) + col));
+                    if (!INVERSE) *(uint32_t*)(tile + row * LD + col) = w;
+                    else { tile[col * LD + row] = (int16_t)(w & 0xffff); tile[(col + 1) * LD + row] = (int16_t)(w >> 16); }
+                }
+            }
+            else
+                for (int e = lane; e < N * LD / 2; e += 32) ((uint32_t*)tile)[e] = 0;
+        }
+        __syncwarp();
+        if (N == 32)      { pass32<INVERSE>(a32, bufA, bufB, add1, p.shift1, gid, tig); __syncwarp(); pass32<INVERSE>(a32, bufB, bufA, add2, p.shift2, gid, tig); }
+        else if (N == 16) { pass16<INVERSE>(a16, bufA, bufB, add1, p.shift1, gid, tig); __syncwarp(); pass16<INVERSE>(a16, bufB, bufA, add2, p.shift2, gid, tig); }
+        else              { pass8<INVERSE>(a16, bufA, bufB, add1, p.shift1, gid, tig);  __syncwarp(); pass8<INVERSE>(a16, bufB, bufA, add2, p.shift2, gid, tig); }
+        __syncwarp();
+        // ---- store: forward dst[k*N + j] = R[k][j]; inverse dst[j*dstStride + k] = R[k][j] ----
+#pragma unroll
+        for (int s = 0; s < PER; s++)
+        {
+            int64_t b = u * PER + s;
+            if (b >= p.n) continue;
+            const int16_t* tile = bufA + s * N * LD;
+            int16_t* dp = p.dst + xf_dst_off(p, b);
+            if (!INVERSE)
+                for (int e = lane; e < N * N / 2; e += 32)
+                {
+                    int row = (2 * e) / N, col = (2 * e) % N;
+                    *(uint32_t*)(dp + row * N + col) = *(const uint32_t*)(tile + row * LD + col);
+                }
+            else
+                for (int e = lane; e < N * N; e += 32)
+                {
+                    int j = e / N, k = e % N;
+                    dp[(int64_t)j * p.dstStride + k] = tile[k * LD + j];
+                }
+        }
+        __syncwarp();
+    }
+}
+
+// ---- 4x4: DCT (kind 0) / DST (kind 1), one thread per block ----------------------------------
+__device__ __forceinline__ int16_t wrap16(int v) { return (int16_t)v; }
+__device__ __forceinline__ int16_t sat16(int v) { return (int16_t)clip3i(-32768, 32767, v); }
+
+// dct.cpp:418-440 partialButterfly4 / :43-61 fastForwardDst : out[k*4 + j] from in[j*4 + n]
+__device__ __forceinline__ void fwd4_pass(const int in[16], int out[16], int shift, bool dst)
+{
+    const int add = 1 << (shift - 1);
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+    {
+        const int s0 = in[4 * j], s1 = in[4 * j + 1], s2 = in[4 * j + 2], s3 = in[4 * j + 3];
+        if (!dst)
+        {
+            int E0 = s0 + s3, O0 = s0 - s3, E1 = s1 + s2, O1 = s1 - s2;
+            out[j]      = wrap16((64 * E0 + 64 * E1 + add) >> shift);
+            out[8 + j]  = wrap16((64 * E0 - 64 * E1 + add) >> shift);
+            out[4 + j]  = wrap16((83 * O0 + 36 * O1 + add) >> shift);
+            out[12 + j] = wrap16((36 * O0 - 83 * O1 + add) >> shift);
+        }
+        else
+        {
+            int c0 = s0 + s3, c1 = s1 + s3, c2 = s0 - s1, c3 = 74 * s2;
+            out[j]      = wrap16((29 * c0 + 55 * c1 + c3 + add) >> shift);
+            out[4 + j]  = wrap16((74 * (s0 + s1 - s3) + add) >> shift);
+            out[8 + j]  = wrap16((29 * c2 + 55 * c0 - c3 + add) >> shift);
+            out[12 + j] = wrap16((55 * c2 - 29 * c1 + c3 + add) >> shift);
+        }
+    }
+}
+
+// dct.cpp:242-265 partialButterflyInverse4 / :63-81 inversedst : out[j*4 + k] from in[n*4 + j]
+__device__ __forceinline__ void inv4_pass(const int in[16], int out[16], int shift, bool dst)
+{
+    const int add = 1 << (shift - 1);
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+    {
+        const int t0 = in[j], t1 = in[4 + j], t2 = in[8 + j], t3 = in[12 + j];
+        if (!dst)
+        {
+            int O0 = 83 * t1 + 36 * t3, O1 = 36 * t1 - 83 * t3, E0 = 64 * t0 + 64 * t2, E1 = 64 * t0 - 64 * t2;
+            out[4 * j]     = sat16((E0 + O0 + add) >> shift);
+            out[4 * j + 1] = sat16((E1 + O1 + add) >> shift);
+            out[4 * j + 2] = sat16((E1 - O1 + add) >> shift);
+            out[4 * j + 3] = sat16((E0 - O0 + add) >> shift);
+        }
+        else
+        {
+            int c0 = t0 + t2, c1 = t2 + t3, c2 = t0 - t3, c3 = 74 * t1;
+            out[4 * j]     = sat16((29 * c0 + 55 * c1 + c3 + add) >> shift);
+            out[4 * j + 1] = sat16((55 * c2 - 29 * c1 + c3 + add) >> shift);
+            out[4 * j + 2] = sat16((74 * (t0 - t2 + t3) + add) >> shift);
+            out[4 * j + 3] = sat16((55 * c0 + 29 * c2 - c3 + add) >> shift);
+        }
+    }
+}
+
+template<bool INVERSE>
+__global__ void __launch_bounds__(128)
+xform4_kernel(XformArgs p, int isDst)
+{
+    int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.n) return;
+    int in[16], tmp[16], out[16];
+    const int16_t* sp = p.src + xf_src_off(p, b);
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+    {
+        int v[4];
+        ld4s(sp + (INVERSE ? r * 4 : (int64_t)r * p.srcStride), v);
+#pragma unroll
+        for (int c = 0; c < 4; c++) in[4 * r + c] = v[c];
+    }
+    if (!INVERSE) { fwd4_pass(in, tmp, p.shift1, isDst); fwd4_pass(tmp, out, p.shift2, isDst); }
+    else          { inv4_pass(in, tmp, p.shift1, isDst); inv4_pass(tmp, out, p.shift2, isDst); }
+    int16_t* dp = p.dst + xf_dst_off(p, b);
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+            dp[(INVERSE ? (int64_t)r * p.dstStride : r * 4) + c] = (int16_t)out[4 * r + c];
+}
+
+// sizeIdx: 0..3 = 4/8/16/32 DCT, 4 = 4x4 DST (same numbering as the reference TestBench harness)
+int transform_dev(Ctx* ctx, int inverse, int sizeIdx, int depth, const int16_t* src, int64_t srcBlockStride, int64_t srcStride,
+                  int16_t* dst, int64_t dstBlockStride, int64_t dstStride, int64_t n, int64_t blocksPerRow, int64_t rowStride)
+{
+    if (sizeIdx < 0 || sizeIdx > 4) { set_error("transform: sizeIdx %d", sizeIdx); return -1; }
+    if (n <= 0) return 0;
+    if (upload_tables(ctx)) return -1;
+    const int N = sizeIdx == 4 ? 4 : (4 << sizeIdx);
+    const int log2N = sizeIdx == 4 ? 2 : sizeIdx + 2;
+    XformArgs a;
+    a.src = src; a.srcBlockStride = srcBlockStride; a.srcStride = srcStride;
+    a.dst = dst; a.dstBlockStride = dstBlockStride; a.dstStride = dstStride; a.n = n;
+    a.bpr = blocksPerRow > 0 ? blocksPerRow : (n > 0 ? n : 1);
+    // forward: the strided side is src, dst is a linear list; inverse: the other way round
+    a.srcRowStride = inverse ? a.bpr * a.srcBlockStride : rowStride;
+    a.dstRowStride = inverse ? rowStride : a.bpr * a.dstBlockStride;
+    if (blocksPerRow <= 0) { a.srcRowStride = a.bpr * a.srcBlockStride; a.dstRowStride = a.bpr * a.dstBlockStride; }
+    if (!inverse) { a.shift1 = log2N - 1 + (depth - 8); a.shift2 = log2N + 6; }      // dct.cpp:444-445, 478-479, ...
+    else          { a.shift1 = 7; a.shift2 = 12 - (depth - 8); }                     // dct.cpp:529-530
+    if (N == 4)
+    {
+        unsigned blocks = (unsigned)((n + 127) / 128);
+        if (!inverse) xform4_kernel<false><<<blocks, 128, 0, ctx->stream>>>(a, sizeIdx == 4);
+        else          xform4_kernel<true><<<blocks, 128, 0, ctx->stream>>>(a, sizeIdx == 4);
+    }
+    else
+    {
+        int64_t units = N == 8 ? (n + 1) / 2 : n;
+        int64_t want = (units + XF_WARPS - 1) / XF_WARPS;
+        int64_t cap = (int64_t)ctx->smCount * 8;
+        unsigned blocks = (unsigned)(want < cap ? want : cap);
+        dim3 block(XF_WARPS * 32);
+        if (N == 32) { if (!inverse) xform_mma_kernel<32, false><<<blocks, block, 0, ctx->stream>>>(a); else xform_mma_kernel<32, true><<<blocks, block, 0, ctx->stream>>>(a); }
+        if (N == 16) { if (!inverse) xform_mma_kernel<16, false><<<blocks, block, 0, ctx->stream>>>(a); else xform_mma_kernel<16, true><<<blocks, block, 0, ctx->stream>>>(a); }
+        if (N == 8)  { if (!inverse) xform_mma_kernel<8, false><<<blocks, block, 0, ctx->stream>>>(a);  else xform_mma_kernel<8, true><<<blocks, block, 0, ctx->stream>>>(a); }
+    }
+    ctx->launches++;
+    return check(cudaGetLastError(), "transform kernel launch");
+}
+
+// ---------------------------------------------------------------------------------------------
+// quant / nquant / dequant / count_nonzero / denoise : one warp per TU block
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+quant_kernel(const int16_t* __restrict__ coef, const int32_t* __restrict__ quantCoeff, int32_t* __restrict__ deltaU,
+             int16_t* __restrict__ qCoef, int qBits, int add, int numCoeff, int64_t n, uint32_t* __restrict__ numSig, int isN)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (b >= n) return;
+    const int16_t* c = coef + b * numCoeff;
+    int cnt = 0;
+    for (int i = lane; i < numCoeff; i += 32)
+    {
+        int level = c[i];
+        int sign = level < 0 ? -1 : 1;
+        int tmplevel = (int)((uint32_t)abs(level) * (uint32_t)quantCoeff[i]);
+        level = (tmplevel + add) >> qBits;
+        if (!isN && deltaU) deltaU[b * numCoeff + i] = (tmplevel - (level << qBits)) >> (qBits - 8);
+        if (level) cnt++;
+        level *= sign;
+        int q = clip3i(-32768, 32767, level);
+        qCoef[b * numCoeff + i] = (int16_t)(isN ? abs(q) : q);      // dct.cpp:682 / :709
+    }
+    cnt = warp_sum(cnt);
+    if (lane == 0 && numSig) numSig[b] = (uint32_t)cnt;
+}
+
+int quant_dev(Ctx* ctx, int isN, const int16_t* coef, const int32_t* quantCoeff, int32_t* deltaU, int16_t* qCoef,
+              int qBits, int add, int numCoeff, int64_t n, uint32_t* numSig)
+{
+    if (n <= 0) return 0;
+    unsigned blocks = (unsigned)((n * 32 + 255) / 256);
+    quant_kernel<<<blocks, 256, 0, ctx->stream>>>(coef, quantCoeff, deltaU, qCoef, qBits, add, numCoeff, n, numSig, isN);
+    ctx->launches++;
+    return check(cudaGetLastError(), "quant kernel launch");
+}
+
+__global__ void __launch_bounds__(256)
+dequant_kernel(const int16_t* __restrict__ q, const int32_t* __restrict__ deqCoef, int16_t* __restrict__ coef,
+               int num, int64_t total, int scaleOrPer, int shift, int scaling)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int v = q[i];
+    int r;
+    if (!scaling)
+    {
+        int add = 1 << (shift - 1);
+        r = clip3i(-32768, 32767, (v * scaleOrPer + add) >> shift);                  // dct.cpp:631-632
+    }
+    else
+    {
+        int per = scaleOrPer, sh = shift + 4, d = deqCoef[i % num];
+        if (sh > per) { int add = 1 << (sh - per - 1); r = clip3i(-32768, 32767, (v * d + add) >> (sh - per)); }       // :646-652
+        else          { int c = clip3i(-32768, 32767, v * d); r = clip3i(-32768, 32767, (int)((uint32_t)c << (per - sh))); } // :656-660
+    }
+    coef[i] = (int16_t)r;
+}
+
+int dequant_dev(Ctx* ctx, int scaling, const int16_t* q, const int32_t* deqCoef, int16_t* coef, int num, int64_t n,
+                int scaleOrPer, int shift)
+{
+    int64_t total = n * num;
+    if (total <= 0) return 0;
+    unsigned blocks = (unsigned)((total + 255) / 256);
+    dequant_kernel<<<blocks, 256, 0, ctx->stream>>>(q, deqCoef, coef, num, total, scaleOrPer, shift, scaling);
+    ctx->launches++;
+    return check(cudaGetLastError(), "dequant kernel launch");
+}
+
+// count_nonzero (dct.cpp:714-726) over n contiguous blocks of numCoeff
+__global__ void __launch_bounds__(256)
+count_nonzero_kernel(const int16_t* __restrict__ q, int numCoeff, int64_t n, int32_t* __restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (b >= n) return;
+    int cnt = 0;
+    for (int i = lane; i < numCoeff; i += 32) cnt += q[b * numCoeff + i] != 0;
+    cnt = warp_sum(cnt);
+    if (lane == 0) out[b] = cnt;
+}
+
+int count_nonzero_dev(Ctx* ctx, const int16_t* q, int numCoeff, int64_t n, int32_t* out)
+{
+    if (n <= 0) return 0;
+    unsigned blocks = (unsigned)((n * 32 + 255) / 256);
+    count_nonzero_kernel<<<blocks, 256, 0, ctx->stream>>>(q, numCoeff, n, out);
+    ctx->launches++;
+    return check(cudaGetLastError(), "count_nonzero kernel launch");
+}
+
+void host_dct_table(int N, int16_t* out)
+{
+    for (int k = 0; k < N; k++)
+        for (int n = 0; n < N; n++) out[k * N + n] = (int16_t)dct_coef(N, k, n);
+}
+
+} // namespace x265b200
