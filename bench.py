@@ -186,8 +186,10 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=local)               # a real (non-NULL) stream shared by torch and the C ABI
+    torch.cuda.set_stream(stream)
     ctx = pkg.Ctx(local, stream=stream.cuda_stream)       # fails loudly without the CUDA library
+    assert stream.cuda_stream != 0 and ctx.stream == stream.cuda_stream
     dev = torch.device("cuda", local)
     lam = pkg.lambda_for_qp(QP, 8)
 

@@ -169,6 +169,31 @@ int x265b200_bitcost_table(double lambda, uint16_t* out);
 /* x265_lambda_tab[qp] for a bit depth (constants.cpp:34-150), regenerated as round(2^((qp-12)/6 + (depth-8)), 4 dp) */
 double x265b200_lambda(int qp, int depth);
 
+/* ---- lookahead (lowres pre-analysis) ----------------------------------------------------------
+ * x265b200_lowres_init_dev: replaces primitives.frameInitLowres + extendPicBorder x4 as used by
+ *   Lowres::init (common/lowres.cpp:294-302; pixel.cpp:604-628, :1027-1041).  planes[4] are the
+ *   ORIGINS (pixel 0,0) of the four hpel planes; margins are filled by edge replication.
+ * x265b200_la_intra_dev: replaces LookaheadTLD::lowresIntraEstimate (slicetype.cpp:696-805) for one
+ *   frame.  intraPenalty = 5 * (int)x265_lambda_tab[X265_LOOKAHEAD_QP].  sums[2] = costEst, costEstAq.
+ * x265b200_la_estimate_dev: replaces CostEstimateGroup::estimateFrameCost / estimateCUCost
+ *   (slicetype.cpp:3115-3388; non-cooperative path, weightp off, HME off) for a batch of frame
+ *   triples.  `planes` = device array [numFrames][4] of plane origins; MVs and MV costs of list i live
+ *   in slot mvSlot[i] of mvPool ([slot][ncu][2] int32) / mvCostPool ([slot][ncu] int32) -- the
+ *   reference's lowresMvs[i][dist] / lowresMvCosts[i][dist] cache; doSearch[i] = 0 reuses the slot.
+ *   Outputs per triple t: lowresCosts[t][ncu] (uint16), rowSatds[t][heightInCU], sums[t][4] =
+ *   {costEst (raw sum, before the b-frame 100/130 scaling of :3203-3204), costEstAq, intraMbs, 0}. */
+typedef struct { int32_t b, p0, p1; int32_t doSearch[2]; int32_t mvSlot[2]; } x265b200_la_triple;
+int x265b200_lowres_init_dev(x265b200_ctx* ctx, int depth, const void* src, int64_t srcStride,
+                             void* const planes[4], int64_t dstStride, int width, int height, int marginX, int marginY);
+int x265b200_la_intra_dev(x265b200_ctx* ctx, int depth, const void* plane0, int64_t stride, int widthInCU, int heightInCU,
+                          const int32_t* invQscale, int intraPenalty, int32_t* intraCost, uint8_t* intraMode,
+                          uint16_t* lowresCosts, int32_t* rowSatds, int32_t* sums);
+int x265b200_la_estimate_dev(x265b200_ctx* ctx, int depth, const void* const* planes, int64_t stride,
+                             int widthInCU, int heightInCU, const x265b200_la_triple* triplesHost, int numTriples,
+                             int32_t* mvPool, int32_t* mvCostPool, const int32_t* const* intraCost,
+                             const int32_t* const* invQscale, uint16_t* lowresCosts, int32_t* rowSatds, int32_t* sums,
+                             double lambda, int maxSlices);
+
 #ifdef __cplusplus
 }
 #endif

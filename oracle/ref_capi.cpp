@@ -352,3 +352,114 @@ int ref_me_batch(const void* fencPlane, intptr_t fencStride, const void* refPlan
 }
 
 } /* extern "C" */
+
+/* ---- lookahead: Lowres::init, LookaheadTLD::lowresIntraEstimate, CostEstimateGroup::singleCost ----
+ * Built on the reference's own Lookahead / Lowres / PicYuv objects (no pool => non-cooperative path,
+ * slicetype.cpp:3175-3199).  weightp, HME and cutree are off; AQ factors can be injected. */
+#include "slicetype.h"
+#include "picyuv.h"
+#include "frame.h"
+
+namespace {
+struct RefLA
+{
+    x265_param* param;
+    Lookahead*  la;
+    std::vector<PicYuv*> pics;
+    std::vector<Lowres*> lowres;
+    std::vector<Lowres*> framePtrs;
+};
+}
+
+extern "C" {
+
+void* ref_la_create(int width, int height, int bframes, int aq)
+{
+    ensure_init();
+    RefLA* h = new RefLA;
+    h->param = x265_param_alloc();
+    x265_param_default_preset(h->param, "medium", NULL);
+    h->param->sourceWidth = width; h->param->sourceHeight = height;
+    h->param->internalCsp = X265_CSP_I400;
+    h->param->internalBitDepth = X265_DEPTH;
+    h->param->bframes = bframes;
+    h->param->bEnableWeightedPred = 0; h->param->bEnableWeightedBiPred = 0;
+    h->param->lookaheadSlices = 0;
+    h->param->bEnableHME = 0;
+    h->param->rc.aqMode = aq ? X265_AQ_VARIANCE : X265_AQ_NONE;
+    h->param->rc.cuTree = 0;
+    h->param->logLevel = X265_LOG_NONE;
+    h->param->maxSlices = 1;
+    h->param->bCopyPicToFrame = 1;
+    h->la = new Lookahead(h->param, NULL);
+    h->la->create();
+    return h;
+}
+
+int ref_la_add_frame(void* hv, const void* luma, intptr_t strideElems)
+{
+    RefLA* h = (RefLA*)hv;
+    PicYuv* pic = new PicYuv;
+    pic->create(h->param, true);
+    x265_picture in;
+    x265_picture_init(h->param, &in);
+    in.planes[0] = (void*)luma; in.stride[0] = (int)(strideElems * sizeof(pixel));
+    in.bitDepth = X265_DEPTH; in.colorSpace = X265_CSP_I400;
+    pic->copyFromPicture(in, *h->param, 0, 0);
+    Lowres* lr = new Lowres;
+    memset((void*)lr, 0, sizeof(Lowres));
+    lr->create(h->param, pic, h->param->rc.qgSize);
+    lr->init(pic, (int)h->lowres.size());
+    h->pics.push_back(pic); h->lowres.push_back(lr); h->framePtrs.push_back(lr);
+    return (int)h->lowres.size() - 1;
+}
+
+/* geometry: out[0]=lowres width, [1]=lines, [2]=lumaStride, [3]=marginX, [4]=marginY, [5]=widthInCU, [6]=heightInCU,
+ * [7]=fullres stride, [8]=fullres marginX, [9]=fullres marginY, [10]=fullres buffer rows */
+void ref_la_geometry(void* hv, int64_t* out)
+{
+    RefLA* h = (RefLA*)hv;
+    Lowres* lr = h->lowres[0]; PicYuv* p = h->pics[0];
+    out[0] = lr->width; out[1] = lr->lines; out[2] = lr->lumaStride; out[3] = p->m_lumaMarginX; out[4] = p->m_lumaMarginY;
+    out[5] = lr->maxBlocksInRow; out[6] = lr->maxBlocksInCol; out[7] = p->m_stride; out[8] = p->m_lumaMarginX; out[9] = p->m_lumaMarginY;
+    uint32_t numCuInHeight = (p->m_picHeight + h->param->maxCUSize - 1) / h->param->maxCUSize;
+    out[10] = numCuInHeight * h->param->maxCUSize + 2 * p->m_lumaMarginY;
+}
+/* full padded buffers (start of allocation) */
+const void* ref_la_fullres_buffer(void* hv, int idx) { RefLA* h = (RefLA*)hv; return h->pics[idx]->m_picBuf[0]; }
+const void* ref_la_lowres_buffer(void* hv, int idx, int k) { RefLA* h = (RefLA*)hv; return h->lowres[idx]->buffer[k]; }
+int32_t* ref_la_inv_qscale(void* hv, int idx) { RefLA* h = (RefLA*)hv; return h->lowres[idx]->invQscaleFactor; }
+
+void ref_la_intra(void* hv, int idx)
+{
+    RefLA* h = (RefLA*)hv;
+    h->la->m_tld[0].lowresIntraEstimate(*h->lowres[idx], h->param->rc.qgSize);
+}
+const int32_t* ref_la_intra_cost(void* hv, int idx) { return ((RefLA*)hv)->lowres[idx]->intraCost; }
+const uint8_t* ref_la_intra_mode(void* hv, int idx) { return ((RefLA*)hv)->lowres[idx]->intraMode; }
+
+int64_t ref_la_frame_cost(void* hv, int p0, int p1, int b, int intraPenalty)
+{
+    RefLA* h = (RefLA*)hv;
+    CostEstimateGroup est(*h->la, h->framePtrs.data());
+    return est.singleCost(p0, p1, b, !!intraPenalty);
+}
+/* outputs cached on frame b (common/lowres.h) */
+const int32_t* ref_la_mvs(void* hv, int b, int list, int dist) { return (const int32_t*)((RefLA*)hv)->lowres[b]->lowresMvs[list][dist]; }
+const int32_t* ref_la_mvcosts(void* hv, int b, int list, int dist) { return ((RefLA*)hv)->lowres[b]->lowresMvCosts[list][dist]; }
+const uint16_t* ref_la_lowres_costs(void* hv, int b, int d0, int d1) { return ((RefLA*)hv)->lowres[b]->lowresCosts[d0][d1]; }
+const int32_t* ref_la_row_satds(void* hv, int b, int d0, int d1) { return ((RefLA*)hv)->lowres[b]->rowSatds[d0][d1]; }
+int64_t ref_la_cost_est(void* hv, int b, int d0, int d1, int aq) { Lowres* l = ((RefLA*)hv)->lowres[b]; return aq ? l->costEstAq[d0][d1] : l->costEst[d0][d1]; }
+int ref_la_intra_mbs(void* hv, int b, int d0) { return ((RefLA*)hv)->lowres[b]->intraMbs[d0]; }
+
+void ref_la_destroy(void* hv)
+{
+    RefLA* h = (RefLA*)hv;
+    for (auto l : h->lowres) { l->destroy(); delete l; }
+    for (auto p : h->pics) { p->destroy(); delete p; }
+    h->la->destroy(); delete h->la;
+    x265_param_free(h->param);
+    delete h;
+}
+
+} /* extern "C" */

@@ -1,0 +1,166 @@
+"""GPU parity: the lookahead path -- Lowres::init (frameInitLowres + border extension),
+lowresIntraEstimate and estimateFrameCost/estimateCUCost -- against the reference's own Lookahead /
+Lowres / CostEstimateGroup objects (oracle/_ref links the unmodified slicetype.cpp, lowres.cpp).
+Compared bit-exactly: the 4 hpel planes incl. margins, intraCost/intraMode, per-CU MVs and MV costs of
+both lists, lowresCosts (cost | listused<<14), rowSatds, costEst, costEstAq, intraMbs."""
+import ctypes
+import importlib
+
+import numpy as np
+import pytest
+
+import oracle
+from util import pdtype
+
+pkg = importlib.import_module("x265-yuuki-asuna_b200")
+pytestmark = pytest.mark.gpu
+
+
+def _bind(R):
+    R.ref_la_create.restype = ctypes.c_void_p
+    R.ref_la_frame_cost.restype = ctypes.c_int64
+    R.ref_la_cost_est.restype = ctypes.c_int64
+    for f in ("ref_la_mvs", "ref_la_mvcosts", "ref_la_lowres_costs", "ref_la_row_satds", "ref_la_intra_cost", "ref_la_intra_mode",
+              "ref_la_fullres_buffer", "ref_la_lowres_buffer", "ref_la_inv_qscale"):
+        getattr(R, f).restype = ctypes.c_void_p
+    return R
+
+
+def _arr(ptr, ctype, shape):
+    return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctype)), shape=shape).copy()
+
+
+def _frames(W, H, n, depth, seed):
+    rng = np.random.default_rng(seed)
+    base = rng.integers(0, 256, (H + 96, W + 96)).astype(np.float32)
+    k = np.ones(5) / 5
+    for ax in (0, 1):
+        base = np.apply_along_axis(lambda r: np.convolve(r, k, mode="same"), ax, base)
+    base = (base - base.min()) / (base.max() - base.min()) * 255
+    out = []
+    x = y = 40
+    for i in range(n):
+        x += int(rng.integers(-5, 6)); y += int(rng.integers(-4, 5))
+        fr = base[y:y + H, x:x + W] + rng.normal(0, 2.5, (H, W))
+        if i == n - 1:
+            fr[H // 3: H // 3 + 40, W // 4: W // 4 + 60] = rng.integers(0, 256, (40, 60))   # an occlusion: intra-coded CUs
+        out.append(np.ascontiguousarray(np.clip(np.rint(fr * (1 << (depth - 8))), 0, (1 << depth) - 1).astype(pdtype(depth))))
+    return out
+
+
+@pytest.mark.parametrize("depth,W,H,aq", [(8, 320, 192, 0), (8, 416, 240, 1), (10, 320, 192, 1)])
+def test_lookahead_matches_reference(ctx, depth, W, H, aq):
+    R = oracle.ref(depth)
+    assert R is not None, "oracle/_ref missing"
+    _bind(R)
+    NF, BF = 5, 3
+    h = ctypes.c_void_p(R.ref_la_create(W, H, BF, aq))
+    frames = _frames(W, H, NF, depth, seed=W + depth)
+    for f in frames:
+        R.ref_la_add_frame(h, ctypes.c_void_p(f.ctypes.data), ctypes.c_ssize_t(W))
+    g = (ctypes.c_int64 * 11)()
+    R.ref_la_geometry(h, g)
+    lw, ll, ls, mx, my, wcu, hcu, fs, fmx, fmy, frows = [int(v) for v in g]
+    ncu = wcu * hcu
+    dt = pdtype(depth)
+    px = np.dtype(dt).itemsize
+    ct = ctypes.c_uint8 if depth == 8 else ctypes.c_uint16
+    planesize = ls * (ll + 2 * my)
+    padoff = ls * my + mx
+    rng = np.random.default_rng(99)
+
+    # ---- Lowres::init ---------------------------------------------------------------------------
+    dPlanes = []          # device buffers [frame][4]
+    plane_ptrs = np.zeros((NF, 4), dtype=np.int64)
+    for i in range(NF):
+        full = _arr(R.ref_la_fullres_buffer(h, i), ct, (fs * frows,))
+        dFull = ctx.to_device(full)
+        bufs = [ctx.to_device(np.zeros(planesize, dtype=dt)) for _ in range(4)]
+        ctx.lowres_init_dev(depth, dFull.ptr + (fmy * fs + fmx) * px, fs, [b.ptr + padoff * px for b in bufs], ls, lw, ll, mx, my)
+        for k in range(4):
+            exp = _arr(R.ref_la_lowres_buffer(h, i, k), ct, (planesize,))
+            got = bufs[k].download(dt)
+            assert np.array_equal(got, exp), ("lowres plane", i, k)
+            plane_ptrs[i, k] = bufs[k].ptr + padoff * px
+        dPlanes.append(bufs)
+        dFull.free()
+    dPlanePtrs = ctx.to_device(plane_ptrs)
+
+    # ---- AQ factors (injected on both sides) and lowresIntraEstimate ----------------------------------
+    invq_ptrs = np.zeros(NF, dtype=np.int64)
+    dInvQ = []
+    for i in range(NF):
+        if aq:
+            q = rng.integers(128, 512, ncu).astype(np.int32)
+            ctypes.memmove(R.ref_la_inv_qscale(h, i), q.ctypes.data, q.nbytes)
+            dInvQ.append(ctx.to_device(q)); invq_ptrs[i] = dInvQ[-1].ptr
+    dInvQPtrs = ctx.to_device(invq_ptrs)
+    lam = pkg.lambda_for_qp(12 + 6 * (depth - 8), depth)
+    intraPenalty = 5 * int(lam)
+    dIntraCost, intra_ptrs = [], np.zeros(NF, dtype=np.int64)
+    for i in range(NF):
+        R.ref_la_intra(h, i)
+        dIC, dIM, dLC, dRS, dSm = ctx.empty(ncu * 4), ctx.empty(ncu), ctx.empty(ncu * 2), ctx.empty(hcu * 4), ctx.empty(8)
+        ctx.la_intra_dev(depth, plane_ptrs[i, 0], ls, wcu, hcu, invq_ptrs[i] if aq else None, intraPenalty, dIC, dIM, dLC, dRS, dSm)
+        assert np.array_equal(dIC.download(np.int32), _arr(R.ref_la_intra_cost(h, i), ctypes.c_int32, (ncu,))), ("intraCost", i)
+        assert np.array_equal(dIM.download(np.uint8), _arr(R.ref_la_intra_mode(h, i), ctypes.c_uint8, (ncu,))), ("intraMode", i)
+        assert np.array_equal(dLC.download(np.uint16), _arr(R.ref_la_lowres_costs(h, i, 0, 0), ctypes.c_uint16, (ncu,)))
+        assert np.array_equal(dRS.download(np.int32), _arr(R.ref_la_row_satds(h, i, 0, 0), ctypes.c_int32, (hcu,)))
+        sums = dSm.download(np.int32)
+        assert int(sums[0]) == R.ref_la_cost_est(h, i, 0, 0, 0)
+        if aq:
+            assert int(sums[1]) == R.ref_la_cost_est(h, i, 0, 0, 1)
+        dIntraCost.append(dIC); intra_ptrs[i] = dIC.ptr
+        for b in (dIM, dLC, dRS, dSm):
+            b.free()
+    dIntraPtrs = ctx.to_device(intra_ptrs)
+
+    # ---- estimateFrameCost: waves of triples; MV slots model the lowresMvs[list][dist] cache ---------------
+    def slot(b, lst, dist):
+        return (b * 2 + lst) * (BF + 2) + dist
+    nslots = NF * 2 * (BF + 2)
+    dMv, dMvC = ctx.to_device(np.zeros(nslots * ncu * 2, dtype=np.int32)), ctx.to_device(np.zeros(nslots * ncu, dtype=np.int32))
+    searched = set()
+    waves = [[(0, 4, 2), (0, 4, 1), (0, 4, 3), (0, 4, 4)],      # B, B, B, P(b == p1)
+             [(0, 2, 2), (2, 4, 3), (0, 1, 1), (1, 4, 2)]]      # reuse of cached lists mixed with new searches
+    for wave in waves:
+        tr = np.zeros(len(wave), dtype=pkg.LA_TRIPLE)
+        for t, (p0, p1, b) in enumerate(wave):
+            tr[t]["b"], tr[t]["p0"], tr[t]["p1"] = b, p0, p1
+            for lst, dist in ((0, b - p0), (1, p1 - b)):
+                key = (b, lst, dist)
+                tr[t]["mvSlot"][lst] = slot(*key)
+                need = key not in searched and (lst == 0 or p1 > b)
+                tr[t]["doSearch"][lst] = int(need)
+                if need:
+                    searched.add(key)
+            R.ref_la_frame_cost(h, p0, p1, b, 0)
+        dLC, dRS, dSm = ctx.empty(len(wave) * ncu * 2), ctx.empty(len(wave) * hcu * 4), ctx.empty(len(wave) * 16)
+        ctx.la_estimate_dev(depth, dPlanePtrs, ls, wcu, hcu, tr, dMv, dMvC, dIntraPtrs, dInvQPtrs if aq else None, dLC, dRS, dSm, lam)
+        lc = dLC.download(np.uint16).reshape(len(wave), ncu)
+        rs = dRS.download(np.int32).reshape(len(wave), hcu)
+        sm = dSm.download(np.int32).reshape(len(wave), 4)
+        mv = dMv.download(np.int32).reshape(nslots, ncu, 2)
+        mvc = dMvC.download(np.int32).reshape(nslots, ncu)
+        for t, (p0, p1, b) in enumerate(wave):
+            for lst, dist in ((0, b - p0), (1, p1 - b)):
+                if lst == 1 and p1 == b:
+                    continue
+                emv = _arr(R.ref_la_mvs(h, b, lst, dist), ctypes.c_int32, (ncu, 2))
+                emc = _arr(R.ref_la_mvcosts(h, b, lst, dist), ctypes.c_int32, (ncu,))
+                bad = np.nonzero((mv[slot(b, lst, dist)] != emv).any(axis=1) | (mvc[slot(b, lst, dist)] != emc))[0]
+                assert not len(bad), ("MV/cost", (p0, p1, b), lst, int(bad[0]), mv[slot(b, lst, dist)][bad[0]].tolist(), emv[bad[0]].tolist(),
+                                      int(mvc[slot(b, lst, dist)][bad[0]]), int(emc[bad[0]]), len(bad))
+            assert np.array_equal(lc[t], _arr(R.ref_la_lowres_costs(h, b, b - p0, p1 - b), ctypes.c_uint16, (ncu,))), ("lowresCosts", wave[t])
+            assert np.array_equal(rs[t], _arr(R.ref_la_row_satds(h, b, b - p0, p1 - b), ctypes.c_int32, (hcu,))), ("rowSatds", wave[t])
+            score = int(sm[t][0])
+            if b != p1:
+                score = score * 100 // 130                      # slicetype.cpp:3203-3204, bFrameBias = 0
+            assert score == R.ref_la_cost_est(h, b, b - p0, p1 - b, 0), ("costEst", wave[t])
+            if aq:
+                assert int(sm[t][1]) == R.ref_la_cost_est(h, b, b - p0, p1 - b, 1), ("costEstAq", wave[t])
+            if b == p1:
+                assert int(sm[t][2]) == R.ref_la_intra_mbs(h, b, b - p0), ("intraMbs", wave[t])
+        for bb in (dLC, dRS, dSm):
+            bb.free()
+    R.ref_la_destroy(h)

@@ -287,3 +287,30 @@ Ctx.dct_plane_dev = _ctx_dct_plane_dev
 Ctx.idct_plane_dev = _ctx_idct_plane_dev
 Ctx.sub_ps_plane_dev = _ctx_sub_ps_plane_dev
 Ctx.add_ps_plane_dev = _ctx_add_ps_plane_dev
+
+
+# ---- lookahead -------------------------------------------------------------------------------------
+LA_TRIPLE = np.dtype([("b", np.int32), ("p0", np.int32), ("p1", np.int32), ("doSearch", np.int32, (2,)), ("mvSlot", np.int32, (2,))])
+
+
+def _ctx_lowres_init_dev(self, depth, dSrc, srcStride, planePtrs, dstStride, width, height, marginX, marginY):
+    arr = (ctypes.c_void_p * 4)(*[int(p) for p in planePtrs])
+    self._chk(self.L.x265b200_lowres_init_dev(self.h, depth, _vp(dSrc), _i64(srcStride), arr, _i64(dstStride), int(width), int(height), int(marginX), int(marginY)))
+
+
+def _ctx_la_intra_dev(self, depth, dPlane0, stride, wcu, hcu, dInvQ, intraPenalty, dIntraCost, dIntraMode, dLowresCosts, dRowSatds, dSums):
+    self._chk(self.L.x265b200_la_intra_dev(self.h, depth, _vp(dPlane0), _i64(stride), int(wcu), int(hcu), _vp(dInvQ), int(intraPenalty),
+                                           _vp(dIntraCost), _vp(dIntraMode), _vp(dLowresCosts), _vp(dRowSatds), _vp(dSums)))
+
+
+def _ctx_la_estimate_dev(self, depth, dPlanes, stride, wcu, hcu, triples, dMvPool, dMvCostPool, dIntraCostPtrs, dInvQPtrs,
+                         dLowresCosts, dRowSatds, dSums, lam, maxSlices=1):
+    triples = np.ascontiguousarray(triples, dtype=LA_TRIPLE)
+    self._chk(self.L.x265b200_la_estimate_dev(self.h, depth, _vp(dPlanes), _i64(stride), int(wcu), int(hcu), _vp(triples), len(triples),
+                                              _vp(dMvPool), _vp(dMvCostPool), _vp(dIntraCostPtrs), _vp(dInvQPtrs), _vp(dLowresCosts),
+                                              _vp(dRowSatds), _vp(dSums), ctypes.c_double(lam), int(maxSlices)))
+
+
+Ctx.lowres_init_dev = _ctx_lowres_init_dev
+Ctx.la_intra_dev = _ctx_la_intra_dev
+Ctx.la_estimate_dev = _ctx_la_estimate_dev

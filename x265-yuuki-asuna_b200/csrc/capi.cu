@@ -86,6 +86,13 @@ int me_batch_dev(Ctx*, int depth, const void* fencPlane, int64_t fencStride, con
                  int64_t refStride, x265b200_me_job* jobs, int64_t n, int maxW, int maxH,
                  int searchMethod, int subpelRefine, int merange, double lambda, int maxSlices);
 void host_bitcost_table(double lambda, uint16_t* out);
+int lowres_init_dev(Ctx*, int depth, const void* src, int64_t srcStride, void* const planes[4], int64_t dstStride, int width, int height, int marginX, int marginY);
+int la_intra_dev(Ctx*, int depth, const void* plane0, int64_t stride, int widthInCU, int heightInCU, const int32_t* invQscale,
+                 int intraPenalty, int32_t* intraCost, uint8_t* intraMode, uint16_t* lowresCosts, int32_t* rowSatds, int32_t* sums);
+int la_estimate_dev(Ctx*, int depth, const void* const* planes, int64_t stride, int widthInCU, int heightInCU,
+                    const x265b200_la_triple* triplesHost, int numTriples, int32_t* mvPool, int32_t* mvCostPool,
+                    const int32_t* const* intraCost, const int32_t* const* invQscale, uint16_t* lowresCosts, int32_t* rowSatds, int32_t* sums,
+                    double lambda, int maxSlices);
 int sub_ps_plane_dev(Ctx*, int depth, const void* a, int64_t strideA, const void* b, int64_t strideB, int16_t* dst, int64_t dstStride, int w, int h);
 int add_ps_plane_dev(Ctx*, int depth, void* dst, int64_t dstStride, const void* pred, int64_t predStride, const int16_t* resi, int64_t resiStride, int w, int h);
 
@@ -321,6 +328,30 @@ double x265b200_lambda(int qp, int depth)
 {
     double v = pow(2.0, (qp - 12) / 6.0 + (depth - 8));
     return floor(v * 10000.0 + 0.5) / 10000.0;
+}
+
+// ---- lookahead -------------------------------------------------------------------------------------
+int x265b200_lowres_init_dev(x265b200_ctx* ctx, int depth, const void* src, int64_t srcStride, void* const planes[4], int64_t dstStride,
+                             int width, int height, int marginX, int marginY)
+{
+    REQUIRE_CTX(ctx);
+    return lowres_init_dev(CTX(ctx), depth, src, srcStride, planes, dstStride, width, height, marginX, marginY);
+}
+int x265b200_la_intra_dev(x265b200_ctx* ctx, int depth, const void* plane0, int64_t stride, int widthInCU, int heightInCU,
+                          const int32_t* invQscale, int intraPenalty, int32_t* intraCost, uint8_t* intraMode,
+                          uint16_t* lowresCosts, int32_t* rowSatds, int32_t* sums)
+{
+    REQUIRE_CTX(ctx);
+    return la_intra_dev(CTX(ctx), depth, plane0, stride, widthInCU, heightInCU, invQscale, intraPenalty, intraCost, intraMode, lowresCosts, rowSatds, sums);
+}
+int x265b200_la_estimate_dev(x265b200_ctx* ctx, int depth, const void* const* planes, int64_t stride, int widthInCU, int heightInCU,
+                             const x265b200_la_triple* triplesHost, int numTriples, int32_t* mvPool, int32_t* mvCostPool,
+                             const int32_t* const* intraCost, const int32_t* const* invQscale, uint16_t* lowresCosts,
+                             int32_t* rowSatds, int32_t* sums, double lambda, int maxSlices)
+{
+    REQUIRE_CTX(ctx);
+    return la_estimate_dev(CTX(ctx), depth, planes, stride, widthInCU, heightInCU, triplesHost, numTriples, mvPool, mvCostPool,
+                           intraCost, invQscale, lowresCosts, rowSatds, sums, lambda, maxSlices);
 }
 
 } // extern "C"

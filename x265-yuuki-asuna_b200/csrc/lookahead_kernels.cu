@@ -1,0 +1,524 @@
+// lookahead_kernels.cu -- the lookahead's lowres pre-analysis on the device:
+//   * frame_init_lowres_core   source/common/pixel.cpp:604-628   (+ extendPicBorder :1027-1041)
+//   * lowresIntraEstimate      source/encoder/slicetype.cpp:696-805
+//   * estimateFrameCost / estimateCUCost   source/encoder/slicetype.cpp:3115-3388
+//     (non-cooperative path: --lookahead-slices 0 / batch mode; weightp off)
+//
+// estimateCUCost predicts each 8x8 CU's MV from its right / below neighbours in reverse raster
+// order (slicetype.cpp:3269-3280), so CUs of one (frame-triple, list) form a wavefront.  Phase 1 runs
+// one warp per CU ROW; rows are claimed bottom-up from an atomic work counter and a row waits (spin
+// on a per-row progress word in global memory) until the row below is two CUs ahead.  Many
+// (triple, list) chains are in flight at once -- that is where the parallelism comes from.
+// Phase 2 (bidir / intra compare / accumulation) is embarrassingly parallel, one thread per CU.
+#include "me_device.cuh"
+#include "x265b200.h"
+#include <vector>
+
+namespace x265b200 {
+
+int scratch_dev(Ctx* ctx, int slot, size_t bytes, void** out);
+int ensure_mvcost(Ctx* ctx, double lambda);
+
+// ---------------------------------------------------------------------------------------------
+// lowres init: 2x downscale into 4 hpel planes (pixel.cpp:604-628), one thread per output pixel
+// ---------------------------------------------------------------------------------------------
+template<typename pixel>
+__global__ void __launch_bounds__(256)
+lowres_init_kernel(const pixel* __restrict__ src, int64_t srcStride, pixel* __restrict__ d0, pixel* __restrict__ dh,
+                   pixel* __restrict__ dv, pixel* __restrict__ dc, int64_t dstStride, int width, int height)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= width || y >= height) return;
+    const pixel* s0 = src + (int64_t)2 * y * srcStride + 2 * x;
+    const pixel* s1 = s0 + srcStride;
+    const pixel* s2 = s1 + srcStride;
+#define LR_FILTER(a, b, c, d) ((((a + b + 1) >> 1) + ((c + d + 1) >> 1) + 1) >> 1)
+    int a0 = s0[0], a1 = s0[1], a2 = s0[2], b0 = s1[0], b1 = s1[1], b2 = s1[2], c0 = s2[0], c1 = s2[1], c2 = s2[2];
+    int64_t o = (int64_t)y * dstStride + x;
+    d0[o] = (pixel)LR_FILTER(a0, b0, a1, b1);
+    dh[o] = (pixel)LR_FILTER(a1, b1, a2, b2);
+    dv[o] = (pixel)LR_FILTER(b0, c0, b1, c1);
+    dc[o] = (pixel)LR_FILTER(b1, c1, b2, c2);
+#undef LR_FILTER
+}
+
+// extendPicBorder (pixel.cpp:1027-1041): replicate edges into the margins; one thread per margin pixel row/col
+template<typename pixel>
+__global__ void __launch_bounds__(256)
+extend_border_kernel(pixel* __restrict__ pic, int64_t stride, int width, int height, int marginX, int marginY)
+{
+    const int fullW = width + 2 * marginX, fullH = height + 2 * marginY;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)fullW * fullH) return;
+    int yy = (int)(i / fullW) - marginY, xx = (int)(i % fullW) - marginX;
+    if (xx >= 0 && xx < width && yy >= 0 && yy < height) return;
+    int sx = min(max(xx, 0), width - 1), sy = min(max(yy, 0), height - 1);
+    pic[(int64_t)yy * stride + xx] = pic[(int64_t)sy * stride + sx];
+}
+
+int lowres_init_dev(Ctx* ctx, int depth, const void* src, int64_t srcStride, void* const planes[4], int64_t dstStride,
+                    int width, int height, int marginX, int marginY)
+{
+    dim3 grid((width + 255) / 256, height), block(256);
+    if (depth > 8)
+        lowres_init_kernel<uint16_t><<<grid, block, 0, ctx->stream>>>((const uint16_t*)src, srcStride, (uint16_t*)planes[0], (uint16_t*)planes[1], (uint16_t*)planes[2], (uint16_t*)planes[3], dstStride, width, height);
+    else
+        lowres_init_kernel<uint8_t><<<grid, block, 0, ctx->stream>>>((const uint8_t*)src, srcStride, (uint8_t*)planes[0], (uint8_t*)planes[1], (uint8_t*)planes[2], (uint8_t*)planes[3], dstStride, width, height);
+    ctx->launches++;
+    if (check(cudaGetLastError(), "lowres_init launch")) return -1;
+    if (marginX > 0 || marginY > 0)
+    {
+        int64_t total = (int64_t)(width + 2 * marginX) * (height + 2 * marginY);
+        unsigned blocks = (unsigned)((total + 255) / 256);
+        for (int k = 0; k < 4; k++)
+        {
+            if (depth > 8) extend_border_kernel<uint16_t><<<blocks, 256, 0, ctx->stream>>>((uint16_t*)planes[k], dstStride, width, height, marginX, marginY);
+            else           extend_border_kernel<uint8_t><<<blocks, 256, 0, ctx->stream>>>((uint8_t*)planes[k], dstStride, width, height, marginX, marginY);
+            ctx->launches++;
+        }
+        if (check(cudaGetLastError(), "extend_border launch")) return -1;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// small per-thread 8x8 helpers (phase 2 and intra estimate)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int satd8x8_arr(const int* a /* [64] fenc */, const int* b /* [64] pred */)
+{
+    int total = 0;
+#pragma unroll
+    for (int cy = 0; cy < 2; cy++)
+#pragma unroll
+        for (int cx = 0; cx < 2; cx++)
+        {
+            int d[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+            {
+#pragma unroll
+                for (int k = 0; k < 4; k++) d[i][k] = a[(cy * 4 + i) * 8 + cx * 4 + k] - b[(cy * 4 + i) * 8 + cx * 4 + k];
+                me_hadamard4(d[i][0], d[i][1], d[i][2], d[i][3]);
+            }
+            int t = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+            {
+                me_hadamard4(d[0][k], d[1][k], d[2][k], d[3][k]);
+                t += abs(d[0][k]) + abs(d[1][k]) + abs(d[2][k]) + abs(d[3][k]);
+            }
+            total += t >> 1;
+        }
+    return total;
+}
+
+// ReferencePlanes::lowresMC (lowres.h:67-92) into an int[64] array (stride 8)
+template<typename pixel>
+__device__ __forceinline__ void lowres_mc_arr(const pixel* const planes[4], int64_t pelOffset, int64_t stride, int qx, int qy, int* out)
+{
+    if ((qx | qy) & 1)
+    {
+        int hpelA = (qy & 2) | ((qx & 2) >> 1);
+        const pixel* fa = planes[hpelA] + pelOffset + (qx >> 2) + (int64_t)(qy >> 2) * stride;
+        int qmvx = qx + (qx & 1), qmvy = qy + (qy & 1);
+        int hpelB = (qmvy & 2) | ((qmvx & 2) >> 1);
+        const pixel* fb = planes[hpelB] + pelOffset + (qmvx >> 2) + (int64_t)(qmvy >> 2) * stride;
+        for (int y = 0; y < 8; y++)
+            for (int x = 0; x < 8; x++)
+                out[y * 8 + x] = ((int)fa[y * stride + x] + (int)fb[y * stride + x] + 1) >> 1;
+    }
+    else
+    {
+        int hpel = (qy & 2) | ((qx & 2) >> 1);
+        const pixel* f = planes[hpel] + pelOffset + (qx >> 2) + (int64_t)(qy >> 2) * stride;
+        for (int y = 0; y < 8; y++)
+            for (int x = 0; x < 8; x++)
+                out[y * 8 + x] = f[y * stride + x];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// lowresIntraEstimate (slicetype.cpp:696-805), one thread per 8x8 CU
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int la_intra_pixel(const int* s /* 33 neighbours */, int mode, int bFilter, int y, int x, int dcVal, int depth)
+{
+    // N = 8 specialisation of intrapred.cpp:69-204 (see intra_kernels.cu for the general form)
+    const int N = 8, N2 = 16;
+    if (mode == 0)
+        return ((N - 1 - x) * s[N2 + 1 + y] + (N - 1 - y) * s[1 + x] + (x + 1) * s[1 + N] + (y + 1) * s[N2 + 1 + N] + N) >> 4;
+    if (mode == 1)
+    {
+        if (!bFilter) return dcVal;
+        if (x == 0 && y == 0) return (s[1] + s[N2 + 1] + 2 * dcVal + 2) >> 2;
+        if (y == 0) return (s[1 + x] + 3 * dcVal + 2) >> 2;
+        if (x == 0) return (s[N2 + 1 + y] + 3 * dcVal + 2) >> 2;
+        return dcVal;
+    }
+    const int8_t angleTable[17] = { -32, -26, -21, -17, -13, -9, -5, -2, 0, 2, 5, 9, 13, 17, 21, 26, 32 };
+    const int16_t invAngleTable[8] = { 4096, 1638, 910, 630, 482, 390, 315, 256 };
+    const bool hor = mode < 18;
+    auto nb = [&](int i) -> int { if (!hor || i == 0) return s[i]; return i <= N2 ? s[N2 + i] : s[i - N2]; };
+    const int yy = hor ? x : y, xx = hor ? y : x;
+    const int angleOffset = hor ? 10 - mode : mode - 26;
+    const int angle = angleTable[8 + angleOffset];
+    if (!angle)
+    {
+        if (bFilter && xx == 0)
+        {
+            int v = (int16_t)(nb(1) + ((nb(N2 + 1 + yy) - nb(0)) >> 1));
+            return clip3i(0, (1 << depth) - 1, v);
+        }
+        return nb(1 + xx);
+    }
+    const int angleSum = (yy + 1) * angle, offset = angleSum >> 5, fraction = angleSum & 31;
+    auto ref = [&](int idx) -> int {
+        if (angle > 0 || idx >= -1) return nb(idx + 1);
+        int i = -2 - idx;
+        int invAngleSum = 128 + (i + 1) * invAngleTable[-angleOffset - 1];
+        return nb(N2 + (invAngleSum >> 8));
+    };
+    if (fraction) return ((32 - fraction) * ref(offset + xx) + fraction * ref(offset + xx + 1) + 16) >> 5;
+    return ref(offset + xx);
+}
+
+struct LAIntraArgs
+{
+    const void* plane0; int64_t stride;         // lowresPlane[0] origin
+    const int32_t* invQscale;                   // may be null
+    int widthInCU, heightInCU, depth, intraPenalty;
+    int32_t* intraCost; uint8_t* intraMode; uint16_t* lowresCosts; int32_t* rowSatds; int32_t* sums /* [2]: costEst, costEstAq */;
+};
+
+template<typename pixel>
+__global__ void __launch_bounds__(64)
+la_intra_kernel(LAIntraArgs p)
+{
+    const int cuXY = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cuXY >= p.widthInCU * p.heightInCU) return;
+    const int cuX = cuXY % p.widthInCU, cuY = cuXY / p.widthInCU;
+    const pixel* pixCur = (const pixel*)p.plane0 + 8 * cuX + (int64_t)8 * cuY * p.stride;
+    int fenc[64];
+    for (int y = 0; y < 8; y++)
+        for (int x = 0; x < 8; x++) fenc[y * 8 + x] = pixCur[y * p.stride + x];
+    // neighbours (slicetype.cpp:731-735) and their 1:2:1 filtered version (intrapred.cpp:31-51)
+    int smp[33], flt[33];
+    const pixel* tl = pixCur - p.stride - 1;
+    for (int i = 0; i <= 16; i++) smp[i] = tl[i];
+    for (int i = 1; i <= 16; i++) smp[16 + i] = tl[(int64_t)i * p.stride];
+    flt[0] = ((smp[0] << 1) + smp[1] + smp[17] + 2) >> 2;
+    for (int i = 1; i < 16; i++) flt[i] = ((smp[i] << 1) + smp[i - 1] + smp[i + 1] + 2) >> 2;
+    flt[16] = smp[16];
+    flt[17] = ((smp[17] << 1) + smp[0] + smp[18] + 2) >> 2;
+    for (int i = 18; i < 32; i++) flt[i] = ((smp[i] << 1) + smp[i - 1] + smp[i + 1] + 2) >> 2;
+    flt[32] = smp[32];
+
+    int pred[64];
+    int icost = ME_COST_MAX, ilowmode = 0;
+    // DC (unfiltered neighbours, edge filter on since cuSize <= 16)
+    {
+        int dc = 8;
+        for (int i = 0; i < 8; i++) dc += smp[1 + i] + smp[17 + i];
+        dc = dc / 16;
+        for (int e = 0; e < 64; e++) pred[e] = la_intra_pixel(smp, 1, 1, e >> 3, e & 7, dc, p.depth);
+        int cost = satd8x8_arr(fenc, pred);
+        if (cost < icost) { icost = cost; ilowmode = 1; }
+    }
+    // planar uses the FILTERED neighbours (planar = !!(cuSize >= 8), slicetype.cpp:712,751)
+    {
+        for (int e = 0; e < 64; e++) pred[e] = la_intra_pixel(flt, 0, 0, e >> 3, e & 7, 0, p.depth);
+        int cost = satd8x8_arr(fenc, pred);
+        if (cost < icost) { icost = cost; ilowmode = 0; }
+    }
+    auto angCost = [&](int mode) -> int {
+        int dist = min(abs(mode - 26), abs(mode - 10));
+        const int* nbp = dist > 7 ? flt : smp;            // g_intraFilterFlags[mode] & 8
+        for (int e = 0; e < 64; e++) pred[e] = la_intra_pixel(nbp, mode, 1, e >> 3, e & 7, 0, p.depth);
+        return satd8x8_arr(fenc, pred);
+    };
+    int acost = ME_COST_MAX, alowmode = 4;
+    for (int mode = 5; mode < 35; mode += 5)
+    {
+        int cost = angCost(mode);
+        if (cost < acost) { acost = cost; alowmode = mode; }
+    }
+    for (int dist = 2; dist >= 1; dist--)
+    {
+        int minusmode = alowmode - dist, plusmode = alowmode + dist;
+        int cost = angCost(minusmode);
+        if (cost < acost) { acost = cost; alowmode = minusmode; }
+        cost = angCost(plusmode);
+        if (cost < acost) { acost = cost; alowmode = plusmode; }
+    }
+    if (acost < icost) { icost = acost; ilowmode = alowmode; }
+    icost += p.intraPenalty + 4;
+
+    p.lowresCosts[cuXY] = (uint16_t)min(icost, (1 << 14) - 1);
+    p.intraCost[cuXY] = icost;
+    p.intraMode[cuXY] = (uint8_t)ilowmode;
+    const bool bFrameScoreCU = (cuX > 0 && cuX < p.widthInCU - 1 && cuY > 0 && cuY < p.heightInCU - 1) || p.widthInCU <= 2 || p.heightInCU <= 2;
+    int icostAq = (bFrameScoreCU && p.invQscale) ? ((icost * p.invQscale[cuXY] + 128) >> 8) : icost;
+    if (bFrameScoreCU) { atomicAdd(&p.sums[0], icost); atomicAdd(&p.sums[1], icostAq); }
+    atomicAdd(&p.rowSatds[cuY], icostAq);
+}
+
+int la_intra_dev(Ctx* ctx, int depth, const void* plane0, int64_t stride, int widthInCU, int heightInCU, const int32_t* invQscale,
+                 int intraPenalty, int32_t* intraCost, uint8_t* intraMode, uint16_t* lowresCosts, int32_t* rowSatds, int32_t* sums)
+{
+    LAIntraArgs a; a.plane0 = plane0; a.stride = stride; a.invQscale = invQscale; a.widthInCU = widthInCU; a.heightInCU = heightInCU;
+    a.depth = depth; a.intraPenalty = intraPenalty; a.intraCost = intraCost; a.intraMode = intraMode; a.lowresCosts = lowresCosts;
+    a.rowSatds = rowSatds; a.sums = sums;
+    X265B200_CHECK(cudaMemsetAsync(rowSatds, 0, sizeof(int32_t) * heightInCU, ctx->stream));
+    X265B200_CHECK(cudaMemsetAsync(sums, 0, sizeof(int32_t) * 2, ctx->stream));
+    int n = widthInCU * heightInCU;
+    if (depth > 8) la_intra_kernel<uint16_t><<<(n + 63) / 64, 64, 0, ctx->stream>>>(a);
+    else           la_intra_kernel<uint8_t><<<(n + 63) / 64, 64, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    return check(cudaGetLastError(), "la_intra launch");
+}
+
+// ---------------------------------------------------------------------------------------------
+// estimateCUCost phase 1: per (triple, list) MV search chains, one warp per CU row
+// ---------------------------------------------------------------------------------------------
+struct LAChain { int32_t b, ref, bBidir, mvSlot; };   // frame indices; MV/cost pool slot
+
+struct LASearchArgs
+{
+    const void* const* planes;     // [numFrames][4] plane origins
+    int64_t stride;
+    const LAChain* chains; int numChains;
+    int widthInCU, heightInCU, depth, merange, maxSlices;
+    int32_t* mvPool;               // [slot][ncu][2]
+    int32_t* mvCostPool;           // [slot][ncu]
+    int* progress;                 // [numChains][heightInCU], zeroed
+    int* workCounter;              // zeroed
+    const uint16_t* cost;
+};
+
+constexpr int LA_WARPS = 4;
+
+template<typename pixel>
+__global__ void __launch_bounds__(LA_WARPS * 32)
+la_search_kernel(LASearchArgs p)
+{
+    __shared__ __align__(16) pixel sFenc[LA_WARPS][8 * 64];
+    __shared__ __align__(16) pixel sPred[LA_WARPS][64];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int W = p.widthInCU, Hc = p.heightInCU, ncu = W * Hc;
+
+    for (;;)
+    {
+        int id = 0;
+        if (lane == 0) id = atomicAdd(p.workCounter, 1);
+        id = __shfl_sync(0xffffffffu, id, 0);
+        if (id >= p.numChains * Hc) return;
+        const int chain = id / Hc, cuY = Hc - 1 - (id % Hc);
+        const LAChain ch = p.chains[chain];
+        const bool lastRow = (cuY == Hc - 1);
+        volatile int* below = p.progress + chain * Hc + cuY + 1;
+        int* mine = p.progress + chain * Hc + cuY;
+        int32_t* mvs = p.mvPool + (int64_t)ch.mvSlot * ncu * 2;
+        int32_t* mvcosts = p.mvCostPool + (int64_t)ch.mvSlot * ncu;
+        const pixel* const* fencPlanes = (const pixel* const*)p.planes + ch.b * 4;
+        const pixel* const* refPlanes = (const pixel* const*)p.planes + ch.ref * 4;
+
+        MEState<pixel> s;
+        s.fenc = sFenc[warp]; s.pred = sPred[warp]; s.immed = nullptr;
+        s.stride = p.stride; s.isLowres = true; s.w = 8; s.h = 8; s.lane = lane; s.depth = p.depth;
+        s.partSizeScale = 4; s.cost = p.cost + 2 * 32768;
+
+        int rightX = 0, rightY = 0;       // fencMV[1] of the previous iteration
+        for (int cuX = W - 1; cuX >= 0; cuX--)
+        {
+            const int cuXY = cuX + cuY * W;
+            const int64_t pelOffset = 8 * cuX + (int64_t)8 * cuY * p.stride;
+            if (!lastRow)
+            {
+                const int need = min(W, W - cuX + 1);
+                if (lane == 0) { while (*below < need) __nanosleep(64); }
+                __syncwarp();
+                __threadfence();
+            }
+            // setSourcePU: cache the 8x8 source block (motion.cpp:188-189)
+            __syncwarp();
+            if (lane < 16)
+            {
+                int y = lane >> 1, x = (lane & 1) * 4;
+                const pixel* fp = fencPlanes[0] + pelOffset + (int64_t)y * p.stride + x;
+                if (sizeof(pixel) == 1) *(uint32_t*)((uint8_t*)s.fenc + y * 64 + x) = ld_px4((const uint8_t*)fp);
+                else { uint32_t* d = (uint32_t*)((uint16_t*)s.fenc + y * 64 + x); d[0] = ld_px2((const uint16_t*)fp); d[1] = ld_px2((const uint16_t*)fp + 2); }
+            }
+            __syncwarp();
+            for (int k = 0; k < 4; k++) s.lowres[k] = refPlanes[k] + pelOffset;
+            s.fref = s.lowres[0];
+
+            // reverse-order MV prediction candidates (slicetype.cpp:3269-3280)
+            int mvc[4][2], numc = 0;
+            if (cuX < W - 1) { mvc[numc][0] = rightX; mvc[numc][1] = rightY; numc++; }
+            if (!lastRow)
+            {
+                const volatile int32_t* row = mvs + (int64_t)(cuXY + W) * 2;
+                mvc[numc][0] = row[0]; mvc[numc][1] = row[1]; numc++;
+                if (cuX > 0) { mvc[numc][0] = row[-2]; mvc[numc][1] = row[-1]; numc++; }
+                if (cuX < W - 1) { mvc[numc][0] = row[2]; mvc[numc][1] = row[3]; numc++; }
+            }
+            int mvpx = 0, mvpy = 0, skipCost = 0x7fffffff;
+            if (numc)
+            {
+                int mvpcost = ME_COST_MAX;
+                for (int idx = 0; idx < numc; idx++)
+                {
+                    int cost = lowres_qpel_cost<pixel>(s, mvc[idx][0], mvc[idx][1], true);     // lowresMC + bufSATD
+                    if (cost < mvpcost) { mvpcost = cost; mvpx = mvc[idx][0]; mvpy = mvc[idx][1]; }
+                    if (!(mvpx | mvpy) && ch.bBidir) skipCost = cost;                          // :3304-3305 (as written)
+                }
+            }
+            s.mvpx = mvpx; s.mvpy = mvpy;
+            MV2 mvmin = mv2(-cuX * 8 - 8, -cuY * 8 - 8), mvmax = mv2((W - cuX - 1) * 8 + 8, (Hc - cuY - 1) * 8 + 8);
+            int ox, oy;
+            int fencCost = motion_estimate<pixel>(s, mvmin, mvmax, mv2(mvpx, mvpy), 0, nullptr, p.merange, ME_HEX, 1, p.maxSlices, 0, ox, oy);
+            if (skipCost < 64 && skipCost < fencCost && ch.bBidir) { fencCost = skipCost; ox = 0; oy = 0; }
+            rightX = ox; rightY = oy;
+            if (lane == 0)
+            {
+                mvs[cuXY * 2] = ox; mvs[cuXY * 2 + 1] = oy; mvcosts[cuXY] = fencCost;
+                __threadfence();
+                *(volatile int*)mine = W - cuX;
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// estimateCUCost phase 2 (slicetype.cpp:3253-3262 list costs, :3326-3387): one thread per CU
+// ---------------------------------------------------------------------------------------------
+struct LAFinishArgs
+{
+    const void* const* planes; int64_t stride;
+    const x265b200_la_triple* triples; int numTriples;
+    int widthInCU, heightInCU, depth;
+    const int32_t* mvPool; const int32_t* mvCostPool;
+    const int32_t* const* intraCost;      // [numFrames] per-frame intra cost arrays
+    const int32_t* const* invQscale;      // [numFrames] or null entries
+    uint16_t* lowresCosts;                // [numTriples][ncu]
+    int32_t* rowSatds;                    // [numTriples][heightInCU]
+    int32_t* sums;                        // [numTriples][4]: costEst, costEstAq, intraMbs
+};
+
+template<typename pixel>
+__global__ void __launch_bounds__(64)
+la_finish_kernel(LAFinishArgs p)
+{
+    const int ncu = p.widthInCU * p.heightInCU;
+    const int t = blockIdx.y;
+    const int cuXY = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cuXY >= ncu) return;
+    const x265b200_la_triple tr = p.triples[t];
+    const int cuX = cuXY % p.widthInCU, cuY = cuXY / p.widthInCU;
+    const int bBidir = tr.b < tr.p1;
+    const int64_t pelOffset = 8 * cuX + (int64_t)8 * cuY * p.stride;
+    int bcost = ME_COST_MAX, listused = 0;
+    for (int i = 0; i < 1 + bBidir; i++)
+    {
+        int fencCost = p.mvCostPool[(int64_t)tr.mvSlot[i] * ncu + cuXY];
+        if (fencCost < bcost) { bcost = fencCost; listused = i + 1; }
+    }
+    if (bBidir)
+    {
+        const pixel* const* f0 = (const pixel* const*)p.planes + tr.p0 * 4;
+        const pixel* const* f1 = (const pixel* const*)p.planes + tr.p1 * 4;
+        const pixel* fb = ((const pixel* const*)p.planes)[tr.b * 4] + pelOffset;
+        int fenc[64], a[64], b2[64];
+        for (int y = 0; y < 8; y++) for (int x = 0; x < 8; x++) fenc[y * 8 + x] = fb[y * p.stride + x];
+        const int32_t* mv0 = p.mvPool + ((int64_t)tr.mvSlot[0] * ncu + cuXY) * 2;
+        const int32_t* mv1 = p.mvPool + ((int64_t)tr.mvSlot[1] * ncu + cuXY) * 2;
+        lowres_mc_arr<pixel>(f0, pelOffset, p.stride, mv0[0], mv0[1], a);
+        lowres_mc_arr<pixel>(f1, pelOffset, p.stride, mv1[0], mv1[1], b2);
+        for (int e = 0; e < 64; e++) a[e] = (a[e] + b2[e] + 1) >> 1;
+        int bicost = satd8x8_arr(fenc, a);
+        if (bicost < bcost) { bcost = bicost; listused = 3; }
+        const pixel* s0 = f0[0] + pelOffset; const pixel* s1 = f1[0] + pelOffset;       // coloc candidate
+        for (int y = 0; y < 8; y++) for (int x = 0; x < 8; x++) a[y * 8 + x] = ((int)s0[y * p.stride + x] + (int)s1[y * p.stride + x] + 1) >> 1;
+        bicost = satd8x8_arr(fenc, a);
+        if (bicost < bcost) { bcost = bicost; listused = 3; }
+        bcost += 4;
+    }
+    else
+    {
+        bcost += 4;
+        int ic = p.intraCost[tr.b][cuXY];
+        if (ic < bcost) { bcost = ic; listused = 0; }
+    }
+    const bool bFrameScoreCU = (cuX > 0 && cuX < p.widthInCU - 1 && cuY > 0 && cuY < p.heightInCU - 1) || p.widthInCU <= 2 || p.heightInCU <= 2;
+    const int32_t* iq = p.invQscale ? p.invQscale[tr.b] : nullptr;
+    int bcostAq = (bFrameScoreCU && iq) ? ((bcost * iq[cuXY] + 128) >> 8) : bcost;
+    if (bFrameScoreCU)
+    {
+        atomicAdd(&p.sums[t * 4 + 0], bcost);
+        atomicAdd(&p.sums[t * 4 + 1], bcostAq);
+        if (!listused && !bBidir) atomicAdd(&p.sums[t * 4 + 2], 1);
+    }
+    atomicAdd(&p.rowSatds[t * p.heightInCU + cuY], bcostAq);
+    p.lowresCosts[(int64_t)t * ncu + cuXY] = (uint16_t)(min(bcost, (1 << 14) - 1) | (listused << 14));
+}
+
+int la_estimate_dev(Ctx* ctx, int depth, const void* const* planes, int64_t stride, int widthInCU, int heightInCU,
+                    const x265b200_la_triple* triplesHost, int numTriples,
+                    int32_t* mvPool, int32_t* mvCostPool, const int32_t* const* intraCost, const int32_t* const* invQscale,
+                    uint16_t* lowresCosts, int32_t* rowSatds, int32_t* sums, double lambda, int maxSlices)
+{
+    if (numTriples <= 0) return 0;
+    if (maxSlices > 1) { set_error("la_estimate: maxSlices > 1 is not supported on the lowres path"); return -1; }
+    if (ensure_mvcost(ctx, lambda)) return -1;
+    void* dTriplesV = nullptr;
+    if (scratch_dev(ctx, 6, sizeof(x265b200_la_triple) * numTriples, &dTriplesV)) return -1;
+    X265B200_CHECK(cudaMemcpyAsync(dTriplesV, triplesHost, sizeof(x265b200_la_triple) * numTriples, cudaMemcpyHostToDevice, ctx->stream));
+    const x265b200_la_triple* triples = (const x265b200_la_triple*)dTriplesV;
+    // build the chain list (host) and upload it with the sync words
+    std::vector<LAChain> chains;
+    for (int t = 0; t < numTriples; t++)
+    {
+        const x265b200_la_triple& tr = triplesHost[t];
+        int bBidir = tr.b < tr.p1;
+        if (tr.doSearch[0]) { LAChain c; c.b = tr.b; c.ref = tr.p0; c.bBidir = bBidir; c.mvSlot = tr.mvSlot[0]; chains.push_back(c); }
+        if (bBidir && tr.doSearch[1]) { LAChain c; c.b = tr.b; c.ref = tr.p1; c.bBidir = bBidir; c.mvSlot = tr.mvSlot[1]; chains.push_back(c); }
+    }
+    const int numChains = (int)chains.size();
+    void* scratch = nullptr;
+    size_t chainBytes = ((sizeof(LAChain) * (numChains ? numChains : 1) + 255) / 256) * 256;
+    size_t progBytes = sizeof(int) * ((size_t)numChains * heightInCU + 64);
+    if (scratch_dev(ctx, 7, chainBytes + progBytes, &scratch)) return -1;
+    LAChain* dChains = (LAChain*)scratch;
+    int* dProg = (int*)((char*)scratch + chainBytes);
+    if (numChains)
+    {
+        X265B200_CHECK(cudaMemcpyAsync(dChains, chains.data(), sizeof(LAChain) * numChains, cudaMemcpyHostToDevice, ctx->stream));
+        X265B200_CHECK(cudaMemsetAsync(dProg, 0, progBytes, ctx->stream));
+        LASearchArgs a; a.planes = planes; a.stride = stride; a.chains = dChains; a.numChains = numChains;
+        a.widthInCU = widthInCU; a.heightInCU = heightInCU; a.depth = depth; a.merange = 16; a.maxSlices = maxSlices;   // s_merange, slicetype.h:259
+        a.mvPool = mvPool; a.mvCostPool = mvCostPool; a.progress = dProg; a.workCounter = dProg + (size_t)numChains * heightInCU; a.cost = ctx->dMvCost;
+        // every claimed row must be able to make progress: rows are claimed bottom-up, so any grid size is deadlock-free
+        int64_t rows = (int64_t)numChains * heightInCU;
+        int64_t blocksWanted = (rows + LA_WARPS - 1) / LA_WARPS;
+        int64_t cap = (int64_t)ctx->smCount * 8;
+        unsigned blocks = (unsigned)(blocksWanted < cap ? blocksWanted : cap);
+        // the host must not free `chains` before the async copy is consumed
+        X265B200_CHECK(cudaStreamSynchronize(ctx->stream));
+        if (depth > 8) la_search_kernel<uint16_t><<<blocks, LA_WARPS * 32, 0, ctx->stream>>>(a);
+        else           la_search_kernel<uint8_t><<<blocks, LA_WARPS * 32, 0, ctx->stream>>>(a);
+        ctx->launches++;
+        if (check(cudaGetLastError(), "la_search launch")) return -1;
+    }
+    X265B200_CHECK(cudaMemsetAsync(rowSatds, 0, sizeof(int32_t) * (size_t)numTriples * heightInCU, ctx->stream));
+    X265B200_CHECK(cudaMemsetAsync(sums, 0, sizeof(int32_t) * (size_t)numTriples * 4, ctx->stream));
+    LAFinishArgs f; f.planes = planes; f.stride = stride; f.triples = triples; f.numTriples = numTriples; f.widthInCU = widthInCU; f.heightInCU = heightInCU;
+    f.depth = depth; f.mvPool = mvPool; f.mvCostPool = mvCostPool; f.intraCost = intraCost; f.invQscale = invQscale;
+    f.lowresCosts = lowresCosts; f.rowSatds = rowSatds; f.sums = sums;
+    dim3 grid((widthInCU * heightInCU + 63) / 64, numTriples);
+    if (depth > 8) la_finish_kernel<uint16_t><<<grid, 64, 0, ctx->stream>>>(f);
+    else           la_finish_kernel<uint8_t><<<grid, 64, 0, ctx->stream>>>(f);
+    ctx->launches++;
+    return check(cudaGetLastError(), "la_finish launch");
+}
+
+} // namespace x265b200
