@@ -201,7 +201,13 @@ def main():
     for d, h in zip(ring, pinned):
         d.copy_(h)
     job_h = build_jobs(pkg)
+    job_h = job_h[np.argsort(-job_h["w"], kind="stable")]          # group by PU size (64, 32, 16, 8)
     njobs = len(job_h)
+    job_bytes = job_h.dtype.itemsize
+    level_ranges = {}
+    for s in LEVELS:
+        idx = np.nonzero(job_h["w"] == s)[0]
+        level_ranges[s] = (int(idx[0]), int(len(idx)))
     jobs_d = torch.from_numpy(job_h.view(np.uint8).reshape(njobs, -1).copy()).to(dev)
     origin = PAD * STRIDE + PAD
     ref_ptr_table = torch.tensor([[ring[(t - 1 - r) % NF].data_ptr() + origin for r in range(NREF)] for t in range(NF)],
@@ -220,23 +226,30 @@ def main():
     P = lambda t: t.data_ptr()
 
     sad_events = []
+    me_events = []
 
     def hot_path(t, time_sad=False):
         cur = ring[t % NF]
         refs = [ring[(t - 1 - r) % NF] for r in range(NREF)]
         ref_ptrs = ref_ptr_table[t % NF]
         cptr = P(cur) + origin
-        # 1. SAD at the predictor (mv = 0) for every PU level x ref: streaming, 2*W*H bytes per (level, ref)
+        # 1. SAD at the predictor for every PU level x ref: ONE streaming pass per reference (SAD pyramid)
         if time_sad:
             e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True); e0.record()
-        for s in LEVELS:
-            for r in range(NREF):
-                ctx.pixelcmp_dev(pkg.CMP_SAD, 8, s, s, cptr, STRIDE, P(refs[r]) + origin, STRIDE, None, None, level_n[s],
-                                 P(sad_out[s]) + 4 * r * level_n[s], None, W // s)
+        for r in range(NREF):
+            ctx.sad_pyramid_dev(8, cptr, STRIDE, P(refs[r]) + origin, STRIDE, CTU_COLS, CTU_ROWS, None,
+                                P(sad_out[8]) + 4 * r * level_n[8], P(sad_out[16]) + 4 * r * level_n[16],
+                                P(sad_out[32]) + 4 * r * level_n[32], P(sad_out[64]) + 4 * r * level_n[64])
         if time_sad:
             e1.record(); sad_events.append((e0, e1))
         # 2. full motion search for every PU x ref
-        ctx.me_batch_dev(8, cptr, STRIDE, None, STRIDE, P(jobs_d), njobs, 64, 64, pkg.ME_HEX, SUBME, MERANGE, lam, 1, dRefPlanes=P(ref_ptrs))
+        # one launch per PU size class so each launch carves only the shared memory its PUs need
+        if time_sad:
+            m0 = torch.cuda.Event(enable_timing=True); m1 = torch.cuda.Event(enable_timing=True); m0.record()
+        for s, (j0, jn) in level_ranges.items():
+            ctx.me_batch_dev(8, cptr, STRIDE, None, STRIDE, P(jobs_d) + j0 * job_bytes, jn, s, s, pkg.ME_HEX, SUBME, MERANGE, lam, 1, dRefPlanes=P(ref_ptrs))
+        if time_sad:
+            m1.record(); me_events.append((m0, m1))
         # 3. residual -> DCT32 -> quant -> dequant -> IDCT32 -> recon (one launch each, whole plane)
         HH = CTU_ROWS * CTU
         ctx.sub_ps_plane_dev(8, cptr, STRIDE, P(refs[0]) + origin, STRIDE, P(resid), W, W, HH)
@@ -246,9 +259,23 @@ def main():
         ctx.idct_plane_dev(3, 8, P(deq), P(resid), W, W // 32, HH // 32)
         ctx.add_ps_plane_dev(8, P(recon), W, P(refs[0]) + origin, STRIDE, P(resid), W, W, HH)
 
+    # ---- N > 1: the path's one real exchange: every rank needs the reference pixels the others
+    # produced, and rank 0 collects the per-PU {mv,cost}.  One all_gather of the new luma plane + one gather.
+    if world > 1:
+        gathered = torch.empty((world * ROWS, STRIDE), dtype=torch.uint8, device=dev)   # concatenated form
+        res_all = [torch.empty((njobs, 3), dtype=torch.int32, device=dev) for _ in range(world)] if rank == 0 else None
+
+    def exchange(t):
+        if world == 1:
+            return
+        dist.all_gather_into_tensor(gathered, ring[t % NF])
+        out = jobs_d.view(torch.int32).view(njobs, -1)[:, -3:].contiguous()
+        dist.gather(out, res_all, dst=0)
+
     def e2e_step(t):
         ring[t % NF].copy_(pinned[t % NF], non_blocking=True)                   # H2D: the new frame
         hot_path(t)
+        exchange(t)
         out = jobs_d.view(torch.int32).view(njobs, -1)[:, -3:]
         res_h.copy_(out, non_blocking=True)                                   # D2H: {mvx, mvy, cost} per PU
         stream.synchronize()
@@ -262,6 +289,7 @@ def main():
     # ---- warm-up ---------------------------------------------------------------------------------------
     for i in range(max(args.warmup, 3)):
         hot_path(NREF + i)
+        exchange(NREF + i)
     barrier()
     launches0 = ctx.launches
 
@@ -274,12 +302,14 @@ def main():
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
         hot_path(NREF + i, time_sad=True)
+        exchange(NREF + i)
         e1.record()
         evs.append((e0, e1))
     barrier()
     step_ms = [a.elapsed_time(b) for a, b in evs]
     total_ms = float(sum(step_ms))
     sad_ms = [a.elapsed_time(b) for a, b in sad_events]
+    me_ms = [a.elapsed_time(b) for a, b in me_events]
     launches = ctx.launches - launches0
 
     # ---- end-to-end timing (host buffers in, results out) ---------------------------------------------------
@@ -303,8 +333,8 @@ def main():
         fps = world * args.steps / (total_ms / 1e3)
         e2e_fps = world * args.steps / e2e_s
         # roofline of the streaming ME-SAD kernel: algorithmic bytes = 2*W*H + nPU*4 per (level, ref) launch
-        sad_launches = len(LEVELS) * NREF
-        sad_bytes = sum(2 * W * (CTU_ROWS * CTU) + level_n[s] * 4 for s in LEVELS) * NREF
+        sad_launches = NREF
+        sad_bytes = (2 * W * (CTU_ROWS * CTU) + sum(level_n[s] * 4 for s in LEVELS)) * NREF
         sad_t = float(np.mean(sad_ms)) / 1e3
         achieved = sad_bytes / sad_t / 1e9
         line = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -314,9 +344,14 @@ def main():
                            "l2": "512 MiB flush between timed steps", "parallelism": "frame-parallel x%d" % world},
                 "clocks": sampler.summary(), "gpu_launches": int(launches),
                 "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": ROWS * STRIDE, "d2h_bytes_per_step": njobs * 12},
-                "roofline": {"kernel": "cmp_batch_kernel<u8,SAD> (grid mode, ME SAD at predictor)", "bound": "hbm", "achieved": achieved,
+                "roofline": {"kernel": "sad_pyramid_kernel (streaming ME SAD at the predictor, all 4 PU levels in one pass per reference)", "bound": "hbm", "achieved": achieved,
                              "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": None,
                              "peak_kind": pk_kind, "launches_per_step": sad_launches, "ms_per_step": sad_t * 1e3}}
+        me_bytes = NREF * (2 * W * (CTU_ROWS * CTU)) + njobs * 8
+        me_t = float(np.mean(me_ms)) / 1e3
+        line["roofline_me_search"] = {"kernel": "me_batch_kernel (HEX + subme 2, %d searches)" % njobs, "bound": "hbm", "achieved": me_bytes / me_t / 1e9,
+                                      "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": me_bytes / me_t / 1e9 / pk["hbm_gbs"], "ms_per_step": me_t * 1e3,
+                                      "note": "ALU/latency-bound pattern search over L2-resident planes (DESIGN.md 5)"}
         if world == 1:
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line))

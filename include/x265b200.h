@@ -40,6 +40,9 @@ int         x265b200_malloc(x265b200_ctx* ctx, size_t bytes, void** devPtr);
 int         x265b200_free(x265b200_ctx* ctx, void* devPtr);
 int         x265b200_upload(x265b200_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
 int         x265b200_download(x265b200_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+/* 2-D strided copies (pitches and width in BYTES), e.g. a w x h block out of / into a strided host plane */
+int         x265b200_upload2d(x265b200_ctx* ctx, void* dst_dev, size_t dpitch, const void* src_host, size_t spitch, size_t widthBytes, size_t height);
+int         x265b200_download2d(x265b200_ctx* ctx, void* dst_host, size_t dpitch, const void* src_dev, size_t spitch, size_t widthBytes, size_t height);
 int         x265b200_malloc_host(size_t bytes, void** hostPtr);  /* pinned */
 int         x265b200_free_host(void* hostPtr);
 
@@ -68,6 +71,14 @@ int x265b200_pixelcmp_host(x265b200_ctx* ctx, int kind, int depth, int w, int h,
                            const void* A, size_t bytesA, int64_t strideA,
                            const void* B, size_t bytesB, int64_t strideB,
                            const int64_t* offA, const int64_t* offB, int64_t n, void* out);
+
+/* SAD pyramid: one streaming pass over a frame pair -> sad<8,8>, sad<16,16>, sad<32,32>, sad<64,64>
+ * (pixel.cpp:40-55) of every 2Nx2N PU of every 64x64 CTU, i.e. the cost-at-predictor step of
+ * motionEstimate (motion.cpp:771-784) for all PU levels at once.  mvCtu: optional full-pel {x,y} per CTU
+ * applied to the reference.  outN is the raster grid of NxN blocks (ctuCols*64/N per row).  8-bit. */
+int x265b200_sad_pyramid_dev(x265b200_ctx* ctx, int depth, const void* cur, int64_t strideCur, const void* ref, int64_t strideRef,
+                             int ctuCols, int ctuRows, const int16_t* mvCtu,
+                             int32_t* out8, int32_t* out16, int32_t* out32, int32_t* out64);
 
 /* sad_x3 / sad_x4: replaces pu[].sad_x3 / pu[].sad_x4 (primitives.h:139-140,248-249;
  * pixel.cpp:74-119).  Item i compares the cached 64-stride PU at fenc + i*fencBlockStride with

@@ -1,0 +1,345 @@
+// x265_b200_primitives.cpp -- the drop-in adapter: provides
+//
+//     namespace X265_NS { void setupAssemblyPrimitives(EncoderPrimitives& p, int cpuMask); }
+//
+// exactly as declared by the reference (source/common/primitives.h:470) and called from
+// x265_setup_primitives() (source/common/primitives.cpp:264) and TestBench (source/test/testbench.cpp:211).
+// It is compiled AGAINST THE REFERENCE'S OWN HEADERS (-I<x265>/source/common) once per bit depth
+// (X265_DEPTH / HIGH_BIT_DEPTH / X265_NS as in the x265 build) and linked with libx265b200.so, which
+// is all a maintainer has to add to an x265 build configured with ENABLE_ASSEMBLY.
+//
+// Phase A of SURVEY.md 7 / 8b: every installed slot is a pointer-compatible, synchronous HOST-pointer
+// thunk -- stage the operands (H2D), run the same sm_100a kernel the batched API uses, copy the result
+// back -- so the unmodified encoder and the unmodified TestBench link it.  These thunks exist for parity
+// (a ~30 us round trip per call can never be fast); throughput comes from the batched C ABI.
+// There is no CPU fallback: if the CUDA backend cannot start, setupAssemblyPrimitives aborts loudly.
+#include "common.h"
+#include "primitives.h"
+#include "x265b200.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+using namespace X265_NS;
+
+namespace {
+
+struct ThreadCtx
+{
+    x265b200_ctx* ctx;
+    void* buf[8]; size_t cap[8];
+    ~ThreadCtx() { if (ctx) x265b200_destroy(ctx); }
+};
+thread_local ThreadCtx tl = { nullptr, { 0 }, { 0 } };
+
+[[noreturn]] void die(const char* what)
+{
+    fprintf(stderr, "x265 [error]: B200 primitive backend: %s: %s\n", what, x265b200_last_error());
+    abort();            // encoder-level convention: log + abort (encoder.cpp:332-454); never a silent CPU fallback
+}
+#define CK(e) do { if ((e) != 0) die(#e); } while (0)
+
+x265b200_ctx* C()
+{
+    if (!tl.ctx)
+    {
+        const char* d = getenv("X265B200_DEVICE");
+        CK(x265b200_create(d ? atoi(d) : 0, nullptr, &tl.ctx));
+    }
+    return tl.ctx;
+}
+
+void* dev(int slot, size_t bytes)
+{
+    if (tl.cap[slot] < bytes)
+    {
+        if (tl.buf[slot]) CK(x265b200_free(C(), tl.buf[slot]));
+        size_t cap = bytes * 2 + 256;
+        CK(x265b200_malloc(C(), cap, &tl.buf[slot]));
+        tl.cap[slot] = cap;
+    }
+    return tl.buf[slot];
+}
+
+// stage a w x h region (elements of `es` bytes) with row stride `stride` into slot -> compact pitch w
+void* up2d(int slot, const void* src, intptr_t stride, int w, int h, int es)
+{
+    void* d = dev(slot, (size_t)w * h * es);
+    CK(x265b200_upload2d(C(), d, (size_t)w * es, src, (size_t)stride * es, (size_t)w * es, h));
+    return d;
+}
+void* up1d(int slot, const void* src, size_t bytes)
+{
+    void* d = dev(slot, bytes);
+    CK(x265b200_upload(C(), d, src, bytes));
+    return d;
+}
+void down2d(void* dst, intptr_t stride, const void* d, int w, int h, int es)
+{
+    CK(x265b200_download2d(C(), dst, (size_t)stride * es, d, (size_t)w * es, (size_t)w * es, h));
+}
+
+const int PX = (int)sizeof(pixel);
+
+// ---- block compare ------------------------------------------------------------------------------
+template<int W, int H, int KIND>
+int cmp_thunk(const pixel* a, intptr_t sa, const pixel* b, intptr_t sb)
+{
+    void* dA = up2d(0, a, sa, W, H, PX);
+    void* dB = up2d(1, b, sb, W, H, PX);
+    void* dO = dev(2, 8);
+    CK(x265b200_pixelcmp_dev(C(), KIND, X265_DEPTH, W, H, dA, W, dB, W, nullptr, nullptr, nullptr, 1, 1, dO));
+    int32_t r; CK(x265b200_download(C(), &r, dO, 4));
+    return r;
+}
+template<int W, int H>
+sse_t sse_pp_thunk(const pixel* a, intptr_t sa, const pixel* b, intptr_t sb)
+{
+    void* dA = up2d(0, a, sa, W, H, PX);
+    void* dB = up2d(1, b, sb, W, H, PX);
+    void* dO = dev(2, 8);
+    CK(x265b200_pixelcmp_dev(C(), X265B200_CMP_SSE_PP, X265_DEPTH, W, H, dA, W, dB, W, nullptr, nullptr, nullptr, 1, 1, dO));
+    uint64_t r; CK(x265b200_download(C(), &r, dO, 8));
+    return (sse_t)r;
+}
+template<int W, int H>
+sse_t sse_ss_thunk(const int16_t* a, intptr_t sa, const int16_t* b, intptr_t sb)
+{
+    void* dA = up2d(0, a, sa, W, H, 2);
+    void* dB = up2d(1, b, sb, W, H, 2);
+    void* dO = dev(2, 8);
+    CK(x265b200_pixelcmp_dev(C(), X265B200_CMP_SSE_SS, X265_DEPTH, W, H, dA, W, dB, W, nullptr, nullptr, nullptr, 1, 1, dO));
+    uint64_t r; CK(x265b200_download(C(), &r, dO, 8));
+    return (sse_t)r;
+}
+template<int N>
+sse_t ssd_s_thunk(const int16_t* a, intptr_t sa)
+{
+    void* dA = up2d(0, a, sa, N, N, 2);
+    void* dO = dev(2, 8);
+    CK(x265b200_pixelcmp_dev(C(), X265B200_CMP_SSD_S, X265_DEPTH, N, N, dA, N, dA, N, nullptr, nullptr, nullptr, 1, 1, dO));
+    uint64_t r; CK(x265b200_download(C(), &r, dO, 8));
+    return (sse_t)r;
+}
+template<int W, int H, int K>
+void sad_xn(const pixel* fenc, const pixel* const refs[K], intptr_t stride, int32_t* res)
+{
+    void* dF = up2d(0, fenc, FENC_STRIDE, FENC_STRIDE, H, PX);                 // keep the 64-pixel pitch (pixel.cpp:89)
+    char* dR = (char*)dev(1, (size_t)K * W * H * PX);
+    int64_t off[4];
+    for (int k = 0; k < K; k++)
+    {
+        CK(x265b200_upload2d(C(), dR + (size_t)k * W * H * PX, (size_t)W * PX, refs[k], (size_t)stride * PX, (size_t)W * PX, H));
+        off[k] = (int64_t)k * W * H;
+    }
+    void* dOff = up1d(2, off, sizeof(int64_t) * K);
+    void* dO = dev(3, 16);
+    CK(x265b200_sad_xn_dev(C(), X265_DEPTH, K, W, H, dF, 0, dR, W, (const int64_t*)dOff, 1, (int32_t*)dO));
+    CK(x265b200_download(C(), res, dO, 4 * K));
+}
+template<int W, int H>
+void sad_x3_thunk(const pixel* fenc, const pixel* r0, const pixel* r1, const pixel* r2, intptr_t stride, int32_t* res)
+{
+    const pixel* refs[3] = { r0, r1, r2 };
+    sad_xn<W, H, 3>(fenc, refs, stride, res);
+}
+template<int W, int H>
+void sad_x4_thunk(const pixel* fenc, const pixel* r0, const pixel* r1, const pixel* r2, const pixel* r3, intptr_t stride, int32_t* res)
+{
+    const pixel* refs[4] = { r0, r1, r2, r3 };
+    sad_xn<W, H, 4>(fenc, refs, stride, res);
+}
+
+// ---- transforms ---------------------------------------------------------------------------------
+template<int IDX, int N>
+void dct_thunk(const int16_t* src, int16_t* dst, intptr_t srcStride)
+{
+    void* dS = up2d(0, src, srcStride, N, N, 2);
+    void* dD = dev(1, N * N * 2);
+    CK(x265b200_dct_dev(C(), IDX, X265_DEPTH, (const int16_t*)dS, N * N, N, (int16_t*)dD, 1));
+    CK(x265b200_download(C(), dst, dD, N * N * 2));
+}
+template<int IDX, int N>
+void idct_thunk(const int16_t* src, int16_t* dst, intptr_t dstStride)
+{
+    void* dS = up1d(0, src, N * N * 2);
+    void* dD = dev(1, N * N * 2);
+    CK(x265b200_idct_dev(C(), IDX, X265_DEPTH, (const int16_t*)dS, (int16_t*)dD, N * N, N, 1));
+    down2d(dst, dstStride, dD, N, N, 2);
+}
+uint32_t quant_thunk(const int16_t* coef, const int32_t* quantCoeff, int32_t* deltaU, int16_t* qCoef, int qBits, int add, int numCoeff)
+{
+    void* dC = up1d(0, coef, numCoeff * 2); void* dQ = up1d(1, quantCoeff, numCoeff * 4);
+    void* dU = dev(2, numCoeff * 4); void* dO = dev(3, numCoeff * 2); void* dN = dev(4, 4);
+    CK(x265b200_quant_dev(C(), (const int16_t*)dC, (const int32_t*)dQ, (int32_t*)dU, (int16_t*)dO, qBits, add, numCoeff, 1, (uint32_t*)dN));
+    CK(x265b200_download(C(), deltaU, dU, numCoeff * 4)); CK(x265b200_download(C(), qCoef, dO, numCoeff * 2));
+    uint32_t n; CK(x265b200_download(C(), &n, dN, 4));
+    return n;
+}
+uint32_t nquant_thunk(const int16_t* coef, const int32_t* quantCoeff, int16_t* qCoef, int qBits, int add, int numCoeff)
+{
+    void* dC = up1d(0, coef, numCoeff * 2); void* dQ = up1d(1, quantCoeff, numCoeff * 4);
+    void* dO = dev(3, numCoeff * 2); void* dN = dev(4, 4);
+    CK(x265b200_nquant_dev(C(), (const int16_t*)dC, (const int32_t*)dQ, (int16_t*)dO, qBits, add, numCoeff, 1, (uint32_t*)dN));
+    CK(x265b200_download(C(), qCoef, dO, numCoeff * 2));
+    uint32_t n; CK(x265b200_download(C(), &n, dN, 4));
+    return n;
+}
+void dequant_normal_thunk(const int16_t* q, int16_t* coef, int num, int scale, int shift)
+{
+    void* dQ = up1d(0, q, num * 2); void* dO = dev(1, num * 2);
+    CK(x265b200_dequant_normal_dev(C(), (const int16_t*)dQ, (int16_t*)dO, num, 1, scale, shift));
+    CK(x265b200_download(C(), coef, dO, num * 2));
+}
+void dequant_scaling_thunk(const int16_t* q, const int32_t* deq, int16_t* coef, int num, int per, int shift)
+{
+    void* dQ = up1d(0, q, num * 2); void* dD = up1d(2, deq, num * 4); void* dO = dev(1, num * 2);
+    CK(x265b200_dequant_scaling_dev(C(), (const int16_t*)dQ, (const int32_t*)dD, (int16_t*)dO, num, 1, per, shift));
+    CK(x265b200_download(C(), coef, dO, num * 2));
+}
+template<int N>
+int count_nonzero_thunk(const int16_t* q)
+{
+    void* dQ = up1d(0, q, N * N * 2); void* dO = dev(1, 4);
+    CK(x265b200_count_nonzero_dev(C(), (const int16_t*)dQ, N * N, 1, (int32_t*)dO));
+    int32_t n; CK(x265b200_download(C(), &n, dO, 4));
+    return n;
+}
+
+// ---- interpolation -----------------------------------------------------------------------------
+// stages exactly the footprint the reference function reads (SURVEY.md 8a "interpolation read footprint")
+template<int TAPS, int W, int H, int KIND>
+void interp_run(const void* src, intptr_t srcStride, void* dst, intptr_t dstStride, int idxX, int idxY, int isRowExt)
+{
+    const bool srcShort = (KIND == X265B200_IP_VSP || KIND == X265B200_IP_VSS);
+    const bool dstShort = (KIND == X265B200_IP_HPS || KIND == X265B200_IP_VPS || KIND == X265B200_IP_VSS || KIND == X265B200_IP_P2S);
+    const bool horiz = (KIND == X265B200_IP_HPP || KIND == X265B200_IP_HPS || KIND == X265B200_IP_HVPP);
+    const bool vert = (KIND == X265B200_IP_VPP || KIND == X265B200_IP_VPS || KIND == X265B200_IP_VSP || KIND == X265B200_IP_VSS || KIND == X265B200_IP_HVPP ||
+                       (KIND == X265B200_IP_HPS && isRowExt));
+    const int half = TAPS / 2 - 1;
+    const int left = horiz ? half : 0, top = vert ? half : 0;
+    const int rw = W + (horiz ? TAPS - 1 : 0), rh = H + (vert ? TAPS - 1 : 0);
+    const int ses = srcShort ? 2 : PX, des = dstShort ? 2 : PX;
+    const char* origin = (const char*)src - ((intptr_t)top * srcStride + left) * ses;
+    void* dS = up2d(0, origin, srcStride, rw, rh, ses);
+    const int outRows = H + ((KIND == X265B200_IP_HPS && isRowExt) ? TAPS - 1 : 0);
+    void* dD = dev(1, (size_t)W * outRows * des);
+    x265b200_interp_job job; job.srcOff = (int64_t)top * rw + left; job.dstOff = 0; job.idxX = idxX; job.idxY = idxY;
+    void* dJ = up1d(2, &job, sizeof(job));
+    CK(x265b200_interp_dev(C(), KIND, TAPS, X265_DEPTH, W, H, dS, rw, dD, W, (const x265b200_interp_job*)dJ, 1, isRowExt));
+    down2d(dst, dstStride, dD, W, outRows, des);
+}
+template<int T, int W, int H, int K> void ip_pp(const pixel* s, intptr_t ss, pixel* d, intptr_t ds, int c) { interp_run<T, W, H, K>(s, ss, d, ds, c, 0, 0); }
+template<int T, int W, int H> void ip_hps(const pixel* s, intptr_t ss, int16_t* d, intptr_t ds, int c, int ext) { interp_run<T, W, H, X265B200_IP_HPS>(s, ss, d, ds, c, 0, ext); }
+template<int T, int W, int H> void ip_vps(const pixel* s, intptr_t ss, int16_t* d, intptr_t ds, int c) { interp_run<T, W, H, X265B200_IP_VPS>(s, ss, d, ds, c, 0, 0); }
+template<int T, int W, int H> void ip_vsp(const int16_t* s, intptr_t ss, pixel* d, intptr_t ds, int c) { interp_run<T, W, H, X265B200_IP_VSP>(s, ss, d, ds, c, 0, 0); }
+template<int T, int W, int H> void ip_vss(const int16_t* s, intptr_t ss, int16_t* d, intptr_t ds, int c) { interp_run<T, W, H, X265B200_IP_VSS>(s, ss, d, ds, c, 0, 0); }
+template<int W, int H> void ip_hvpp(const pixel* s, intptr_t ss, pixel* d, intptr_t ds, int cx, int cy) { interp_run<8, W, H, X265B200_IP_HVPP>(s, ss, d, ds, cx, cy, 0); }
+template<int W, int H> void ip_p2s(const pixel* s, intptr_t ss, int16_t* d, intptr_t ds) { interp_run<8, W, H, X265B200_IP_P2S>(s, ss, d, ds, 0, 0, 0); }
+
+// ---- intra ---------------------------------------------------------------------------------------
+template<int LOG2>
+void intra_pred_thunk(pixel* dst, intptr_t dstStride, const pixel* srcPix, int dirMode, int bFilter)
+{
+    const int N = 1 << LOG2;
+    void* dS = up1d(0, srcPix, (4 * N + 1) * PX);
+    void* dD = dev(1, N * N * PX);
+    x265b200_intra_job job; job.srcOff = 0; job.dstOff = 0; job.mode = dirMode; job.bFilter = bFilter;
+    void* dJ = up1d(2, &job, sizeof(job));
+    CK(x265b200_intra_pred_dev(C(), X265_DEPTH, LOG2, dS, dD, N, (const x265b200_intra_job*)dJ, 1));
+    down2d(dst, dstStride, dD, N, N, PX);
+}
+template<int LOG2>
+void intra_filter_thunk(const pixel* ref, pixel* filtered)
+{
+    const int N = 1 << LOG2;
+    void* dS = up1d(0, ref, (4 * N + 1) * PX); void* dD = dev(1, (4 * N + 1) * PX);
+    CK(x265b200_intra_filter_dev(C(), X265_DEPTH, LOG2, dS, dD, 1));
+    CK(x265b200_download(C(), filtered, dD, (4 * N + 1) * PX));
+}
+template<int LOG2>
+void intra_allangs_thunk(pixel* dest, pixel* refPix, pixel* filtPix, int bLuma)
+{
+    const int N = 1 << LOG2;
+    void* dR = up1d(0, refPix, (4 * N + 1) * PX); void* dF = up1d(2, filtPix, (4 * N + 1) * PX);
+    void* dD = dev(1, 33 * N * N * PX);
+    CK(x265b200_intra_allangs_dev(C(), X265_DEPTH, LOG2, dR, dF, dD, bLuma, 1));
+    CK(x265b200_download(C(), dest, dD, 33 * N * N * PX));
+}
+
+} // namespace
+
+namespace X265_NS {
+
+void setupAssemblyPrimitives(EncoderPrimitives& p, int /*cpuMask: SIMD flags are meaningless for this backend*/)
+{
+    if (x265b200_device_count() <= 0)
+    {
+        fprintf(stderr, "x265 [error]: B200 primitive backend linked but no CUDA device is visible (no CPU fallback)\n");
+        abort();
+    }
+    C();
+
+#define PU(W, H) \
+    p.pu[LUMA_ ## W ## x ## H].sad      = cmp_thunk<W, H, X265B200_CMP_SAD>; \
+    p.pu[LUMA_ ## W ## x ## H].satd     = cmp_thunk<W, H, X265B200_CMP_SATD>; \
+    p.pu[LUMA_ ## W ## x ## H].sad_x3   = sad_x3_thunk<W, H>; \
+    p.pu[LUMA_ ## W ## x ## H].sad_x4   = sad_x4_thunk<W, H>; \
+    p.pu[LUMA_ ## W ## x ## H].luma_hpp = ip_pp<8, W, H, X265B200_IP_HPP>; \
+    p.pu[LUMA_ ## W ## x ## H].luma_vpp = ip_pp<8, W, H, X265B200_IP_VPP>; \
+    p.pu[LUMA_ ## W ## x ## H].luma_hps = ip_hps<8, W, H>; \
+    p.pu[LUMA_ ## W ## x ## H].luma_vps = ip_vps<8, W, H>; \
+    p.pu[LUMA_ ## W ## x ## H].luma_vsp = ip_vsp<8, W, H>; \
+    p.pu[LUMA_ ## W ## x ## H].luma_vss = ip_vss<8, W, H>; \
+    p.pu[LUMA_ ## W ## x ## H].luma_hvpp = ip_hvpp<W, H>; \
+    p.pu[LUMA_ ## W ## x ## H].convert_p2s[NONALIGNED] = ip_p2s<W, H>; \
+    p.pu[LUMA_ ## W ## x ## H].convert_p2s[ALIGNED] = ip_p2s<W, H>;
+    PU(4, 4) PU(8, 8) PU(16, 16) PU(32, 32) PU(64, 64)
+    PU(8, 4) PU(4, 8) PU(16, 8) PU(8, 16) PU(32, 16) PU(16, 32) PU(64, 32) PU(32, 64)
+    PU(16, 12) PU(12, 16) PU(16, 4) PU(4, 16) PU(32, 24) PU(24, 32) PU(32, 8) PU(8, 32)
+    PU(64, 48) PU(48, 64) PU(64, 16) PU(16, 64)
+#undef PU
+
+    // chroma 4:2:0 4-tap filters (ipfilter.cpp:375-383); satd/sa8d/sse chroma slots are aliases of the
+    // luma pointers installed by setupAliasPrimitives (primitives.cpp:139-208)
+#define CH420(LW, LH, W, H) \
+    p.chroma[X265_CSP_I420].pu[LUMA_ ## LW ## x ## LH].filter_hpp = ip_pp<4, W, H, X265B200_IP_HPP>; \
+    p.chroma[X265_CSP_I420].pu[LUMA_ ## LW ## x ## LH].filter_vpp = ip_pp<4, W, H, X265B200_IP_VPP>; \
+    p.chroma[X265_CSP_I420].pu[LUMA_ ## LW ## x ## LH].filter_hps = ip_hps<4, W, H>; \
+    p.chroma[X265_CSP_I420].pu[LUMA_ ## LW ## x ## LH].filter_vps = ip_vps<4, W, H>; \
+    p.chroma[X265_CSP_I420].pu[LUMA_ ## LW ## x ## LH].filter_vsp = ip_vsp<4, W, H>; \
+    p.chroma[X265_CSP_I420].pu[LUMA_ ## LW ## x ## LH].filter_vss = ip_vss<4, W, H>;
+    CH420(8, 8, 4, 4) CH420(16, 16, 8, 8) CH420(32, 32, 16, 16) CH420(64, 64, 32, 32)
+    CH420(16, 8, 8, 4) CH420(8, 16, 4, 8) CH420(32, 16, 16, 8) CH420(16, 32, 8, 16) CH420(64, 32, 32, 16) CH420(32, 64, 16, 32)
+    CH420(32, 24, 16, 12) CH420(24, 32, 12, 16) CH420(32, 8, 16, 4) CH420(8, 32, 4, 16)
+    CH420(64, 48, 32, 24) CH420(48, 64, 24, 32) CH420(64, 16, 32, 8) CH420(16, 64, 8, 32)
+#undef CH420
+
+#define CU(IDX, N, LOG2) \
+    p.cu[IDX].sa8d   = cmp_thunk<N, N, X265B200_CMP_SA8D>; \
+    p.cu[IDX].sse_pp = sse_pp_thunk<N, N>; \
+    p.cu[IDX].sse_ss = sse_ss_thunk<N, N>; \
+    p.cu[IDX].ssd_s[NONALIGNED] = ssd_s_thunk<N>; \
+    p.cu[IDX].ssd_s[ALIGNED] = ssd_s_thunk<N>;
+    CU(BLOCK_4x4, 4, 2) CU(BLOCK_8x8, 8, 3) CU(BLOCK_16x16, 16, 4) CU(BLOCK_32x32, 32, 5) CU(BLOCK_64x64, 64, 6)
+#undef CU
+
+#define TU(IDX, N, LOG2) \
+    p.cu[IDX].dct = dct_thunk<IDX, N>; p.cu[IDX].standard_dct = dct_thunk<IDX, N>; \
+    p.cu[IDX].idct = idct_thunk<IDX, N>; \
+    p.cu[IDX].count_nonzero = count_nonzero_thunk<N>; \
+    p.cu[IDX].intra_filter = intra_filter_thunk<LOG2>; \
+    p.cu[IDX].intra_pred_allangs = intra_allangs_thunk<LOG2>; \
+    for (int m = 0; m < NUM_INTRA_MODE; m++) p.cu[IDX].intra_pred[m] = intra_pred_thunk<LOG2>;
+    TU(BLOCK_4x4, 4, 2) TU(BLOCK_8x8, 8, 3) TU(BLOCK_16x16, 16, 4) TU(BLOCK_32x32, 32, 5)
+#undef TU
+    p.dst4x4 = dct_thunk<4, 4>;
+    p.idst4x4 = idct_thunk<4, 4>;
+    p.quant = quant_thunk;
+    p.nquant = nquant_thunk;
+    p.dequant_normal = dequant_normal_thunk;
+    p.dequant_scaling = dequant_scaling_thunk;
+}
+
+} // namespace X265_NS

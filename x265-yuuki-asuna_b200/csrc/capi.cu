@@ -66,6 +66,8 @@ int stage_in(Ctx* ctx, int slot, const void* host, size_t bytes, void** dev)
 // forward declarations of launchers -----------------------------------------------------------
 int pixelcmp_dev(Ctx*, int kind, int depth, int w, int h, const void* A, int64_t strideA, const void* B, int64_t strideB,
                  const int64_t* offA, const int64_t* offB, const int16_t* mv, int gridCols, int64_t n, void* out);
+int sad_pyramid_dev(Ctx*, int depth, const void* cur, int64_t strideC, const void* ref, int64_t strideR, int ctuCols, int ctuRows,
+                    const int16_t* mvCtu, int32_t* out8, int32_t* out16, int32_t* out32, int32_t* out64);
 int sad_xn_dev(Ctx*, int depth, int K, int w, int h, const void* fenc, int64_t fencBlockStride,
                const void* ref, int64_t refStride, const int64_t* refOff, int64_t n, int32_t* res);
 
@@ -176,6 +178,20 @@ int x265b200_download(x265b200_ctx* ctx, void* h, const void* d, size_t bytes)
     X265B200_CHECK(cudaStreamSynchronize(ctx->c.stream));
     return 0;
 }
+int x265b200_upload2d(x265b200_ctx* ctx, void* d, size_t dpitch, const void* h, size_t spitch, size_t wbytes, size_t height)
+{
+    REQUIRE_CTX(ctx);
+    if (!wbytes || !height) return 0;
+    X265B200_CHECK(cudaMemcpy2DAsync(d, dpitch, h, spitch, wbytes, height, cudaMemcpyHostToDevice, ctx->c.stream));
+    return 0;
+}
+int x265b200_download2d(x265b200_ctx* ctx, void* h, size_t dpitch, const void* d, size_t spitch, size_t wbytes, size_t height)
+{
+    REQUIRE_CTX(ctx);
+    if (wbytes && height) X265B200_CHECK(cudaMemcpy2DAsync(h, dpitch, d, spitch, wbytes, height, cudaMemcpyDeviceToHost, ctx->c.stream));
+    X265B200_CHECK(cudaStreamSynchronize(ctx->c.stream));
+    return 0;
+}
 int x265b200_malloc_host(size_t bytes, void** p) { X265B200_CHECK(cudaMallocHost(p, bytes ? bytes : 1)); return 0; }
 int x265b200_free_host(void* p) { X265B200_CHECK(cudaFreeHost(p)); return 0; }
 
@@ -209,6 +225,13 @@ int x265b200_pixelcmp_host(x265b200_ctx* ctx, int kind, int depth, int w, int h,
     X265B200_CHECK(cudaMemcpyAsync(out, dOut, outBytes, cudaMemcpyDeviceToHost, c->stream));
     X265B200_CHECK(cudaStreamSynchronize(c->stream));
     return 0;
+}
+
+int x265b200_sad_pyramid_dev(x265b200_ctx* ctx, int depth, const void* cur, int64_t strideCur, const void* ref, int64_t strideRef,
+                             int ctuCols, int ctuRows, const int16_t* mvCtu, int32_t* out8, int32_t* out16, int32_t* out32, int32_t* out64)
+{
+    REQUIRE_CTX(ctx);
+    return sad_pyramid_dev(CTX(ctx), depth, cur, strideCur, ref, strideRef, ctuCols, ctuRows, mvCtu, out8, out16, out32, out64);
 }
 
 int x265b200_sad_xn_dev(x265b200_ctx* ctx, int depth, int K, int w, int h, const void* fenc, int64_t fencBlockStride,

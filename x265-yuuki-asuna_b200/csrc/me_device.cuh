@@ -59,54 +59,104 @@ __device__ __forceinline__ int mvcost(const MEState<pixel>& s, int qx, int qy)
 {
     int ix = clip3i(-kMvTableHalf, kMvTableHalf, qx - s.mvpx);
     int iy = clip3i(-kMvTableHalf, kMvTableHalf, qy - s.mvpy);
-    return ((int)__ldg(s.cost + ix) + (int)__ldg(s.cost + iy)) & 0xffff;      // bitcost.h:45 returns uint16_t
+    return ((int)s.cost[ix] + (int)s.cost[iy]) & 0xffff;      // bitcost.h:45 returns uint16_t
 }
 
-// ---- block compares (warp cooperative) ---------------------------------------------------------
-template<typename pixel> __device__ __forceinline__ int sad4_sg(const pixel* fs, const pixel* rg);
-template<> __device__ __forceinline__ int sad4_sg<uint8_t>(const uint8_t* fs, const uint8_t* rg)
+// ---- row loaders ---------------------------------------------------------------------------------
+// NW consecutive 32-bit words of pixels starting at ANY pixel address (generic pointer: global plane or
+// shared-memory window).  Loads NW+1 aligned words and funnel-shifts.
+template<typename pixel, int NW>
+__device__ __forceinline__ void ld_words(const pixel* p, uint32_t out[NW])
 {
-    return (int)__vsadu4(*(const uint32_t*)fs, ld_px4(rg));
-}
-template<> __device__ __forceinline__ int sad4_sg<uint16_t>(const uint16_t* fs, const uint16_t* rg)
-{
-    const uint32_t* f = (const uint32_t*)fs;
-    return (int)(__vsadu2(f[0], ld_px2(rg)) + __vsadu2(f[1], ld_px2(rg + 2)));
-}
-template<typename pixel> __device__ __forceinline__ int sad4_ss(const pixel* fs, const pixel* ps);
-template<> __device__ __forceinline__ int sad4_ss<uint8_t>(const uint8_t* fs, const uint8_t* ps)
-{
-    return (int)__vsadu4(*(const uint32_t*)fs, *(const uint32_t*)ps);
-}
-template<> __device__ __forceinline__ int sad4_ss<uint16_t>(const uint16_t* fs, const uint16_t* ps)
-{
-    const uint32_t* f = (const uint32_t*)fs; const uint32_t* p = (const uint32_t*)ps;
-    return (int)(__vsadu2(f[0], p[0]) + __vsadu2(f[1], p[1]));
-}
-
-// SAD of the cached PU against a GLOBAL block (any alignment)
-template<typename pixel>
-__device__ __forceinline__ int warp_sad_g(const MEState<pixel>& s, const pixel* r, int64_t rs)
-{
-    const int gw = s.w >> 2, ng = gw * s.h;
-    int acc = 0;
-    for (int u = s.lane; u < ng; u += 32)
+    uintptr_t a = (uintptr_t)p;
+    const uint32_t* w = (const uint32_t*)(a & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)(a & 3) * 8;
+    uint32_t t[NW + 1];
+#pragma unroll
+    for (int i = 0; i < NW; i++) t[i] = w[i];
+    if (sh)
     {
-        int y = u / gw, x = (u - y * gw) << 2;
-        acc += sad4_sg<pixel>(s.fenc + y * 64 + x, r + (int64_t)y * rs + x);
+        t[NW] = w[NW];
+#pragma unroll
+        for (int i = 0; i < NW; i++) out[i] = __funnelshift_r(t[i], t[i + 1], sh);
     }
-    return warp_sum(acc);
+    else
+    {
+#pragma unroll
+        for (int i = 0; i < NW; i++) out[i] = t[i];
+    }
 }
-// SAD of the cached PU against a SHARED block with row stride ps (4-pixel aligned)
+
+template<typename pixel> __device__ __forceinline__ uint32_t sad_word(uint32_t a, uint32_t b);
+template<> __device__ __forceinline__ uint32_t sad_word<uint8_t>(uint32_t a, uint32_t b) { return __vsadu4(a, b); }
+template<> __device__ __forceinline__ uint32_t sad_word<uint16_t>(uint32_t a, uint32_t b) { return __vsadu2(a, b); }
+
+// SAD of one SEG-pixel row segment: fenc in smem (aligned), ref anywhere
+template<typename pixel, int SEG>
+__device__ __forceinline__ int sad_seg(const pixel* f, const pixel* r)
+{
+    constexpr int NW = SEG * (int)sizeof(pixel) / 4;
+    uint32_t rw[NW];
+    ld_words<pixel, NW>(r, rw);
+    const uint32_t* fw = (const uint32_t*)f;
+    uint32_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < NW; i++) acc += sad_word<pixel>(fw[i], rw[i]);
+    return (int)acc;
+}
+
+// K (1..4) candidate SADs of the cached PU at full-pel offsets (ox[k], oy[k]) from s.fref, all at once:
+// lanes are spread over candidates x rows x SEG-pixel segments, per-lane partial sums are combined with a
+// 10-shuffle transpose-reduce and every lane receives all K totals.
+template<typename pixel, int SEG>
+__device__ __forceinline__ void sad_k_impl(const MEState<pixel>& s, int K, const int ox[4], const int oy[4], int costs[4])
+{
+    const int segs = s.w / SEG, upc = s.h * segs, total = K * upc;
+    int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    int cand = 0, rem = s.lane;
+    while (rem >= upc) { rem -= upc; cand++; }
+    for (int u = s.lane; u < total; u += 32)
+    {
+        const int y = rem / segs, x = (rem - y * segs) * SEG;
+        const pixel* r = s.fref + (ox[cand & 3] + x) + (int64_t)(oy[cand & 3] + y) * s.stride;
+        const int v = sad_seg<pixel, SEG>(s.fenc + y * 64 + x, r);
+        a0 += cand == 0 ? v : 0; a1 += cand == 1 ? v : 0; a2 += cand == 2 ? v : 0; a3 += cand == 3 ? v : 0;
+        rem += 32;
+        while (rem >= upc) { rem -= upc; cand++; }
+    }
+    if (K == 1) { costs[0] = warp_sum(a0); return; }
+    const bool b4 = s.lane & 16, b3 = s.lane & 8;
+    int b0 = b4 ? a2 : a0, s0 = b4 ? a0 : a2; b0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+    int b1 = b4 ? a3 : a1, s1 = b4 ? a1 : a3; b1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+    int c = b3 ? b1 : b0, t = b3 ? b0 : b1; c += __shfl_xor_sync(0xffffffffu, t, 8);
+    c += __shfl_xor_sync(0xffffffffu, c, 4);
+    c += __shfl_xor_sync(0xffffffffu, c, 2);
+    c += __shfl_xor_sync(0xffffffffu, c, 1);
+    // lanes 0-7 hold cand 0, 8-15 cand 1, 16-23 cand 2, 24-31 cand 3
+    costs[0] = __shfl_sync(0xffffffffu, c, 0);
+    costs[1] = __shfl_sync(0xffffffffu, c, 8);
+    costs[2] = __shfl_sync(0xffffffffu, c, 16);
+    costs[3] = __shfl_sync(0xffffffffu, c, 24);
+}
+
 template<typename pixel>
-__device__ __forceinline__ int warp_sad_s(const MEState<pixel>& s, const pixel* p, int ps)
+__device__ __noinline__ void warp_sad_k(const MEState<pixel>& s, int K, const int ox[4], const int oy[4], int costs[4])
+{
+    if (!(s.w & 15))     sad_k_impl<pixel, 16>(s, K, ox, oy, costs);
+    else if (!(s.w & 7)) sad_k_impl<pixel, 8>(s, K, ox, oy, costs);
+    else                 sad_k_impl<pixel, 4>(s, K, ox, oy, costs);
+}
+
+// SAD of the cached PU against an arbitrary block (global or shared) with row stride rs
+template<typename pixel>
+__device__ __noinline__ int warp_sad_block(const MEState<pixel>& s, const pixel* r, int64_t rs)
 {
     const int gw = s.w >> 2, ng = gw * s.h;
     int acc = 0;
     for (int u = s.lane; u < ng; u += 32)
     {
         int y = u / gw, x = (u - y * gw) << 2;
-        acc += sad4_ss<pixel>(s.fenc + y * 64 + x, p + y * ps + x);
+        acc += sad_seg<pixel, 4>(s.fenc + y * 64 + x, r + (int64_t)y * rs + x);
     }
     return warp_sum(acc);
 }
@@ -117,22 +167,21 @@ __device__ __forceinline__ void me_hadamard4(int& a, int& b, int& c, int& d)
     a = t0 + t2; c = t0 - t2; b = t1 + t3; d = t1 - t3;
 }
 
-template<typename pixel> __device__ __forceinline__ void px4_s(const pixel* p, int v[4]);
-template<> __device__ __forceinline__ void px4_s<uint8_t>(const uint8_t* p, int v[4])
+template<typename pixel> __device__ __forceinline__ void unpack4(const uint32_t* w, int v[4]);
+template<> __device__ __forceinline__ void unpack4<uint8_t>(const uint32_t* w, int v[4])
 {
-    uint32_t x = *(const uint32_t*)p;
-    v[0] = x & 0xff; v[1] = (x >> 8) & 0xff; v[2] = (x >> 16) & 0xff; v[3] = x >> 24;
+    v[0] = w[0] & 0xff; v[1] = (w[0] >> 8) & 0xff; v[2] = (w[0] >> 16) & 0xff; v[3] = w[0] >> 24;
 }
-template<> __device__ __forceinline__ void px4_s<uint16_t>(const uint16_t* p, int v[4])
+template<> __device__ __forceinline__ void unpack4<uint16_t>(const uint32_t* w, int v[4])
 {
-    const uint32_t* q = (const uint32_t*)p;
-    v[0] = q[0] & 0xffff; v[1] = q[0] >> 16; v[2] = q[1] & 0xffff; v[3] = q[1] >> 16;
+    v[0] = w[0] & 0xffff; v[1] = w[0] >> 16; v[2] = w[1] & 0xffff; v[3] = w[1] >> 16;
 }
 
-// SATD (pixel.cpp:210-297): sum over 4x4 cells of (sum|H d H^T| >> 1); REFG: ref in global memory
-template<typename pixel, bool REFG>
-__device__ __forceinline__ int warp_satd(const MEState<pixel>& s, const pixel* r, int64_t rs)
+// SATD (pixel.cpp:210-297): sum over 4x4 cells of (sum|H d H^T| >> 1); ref anywhere (generic pointer)
+template<typename pixel>
+__device__ __noinline__ int warp_satd(const MEState<pixel>& s, const pixel* r, int64_t rs)
 {
+    constexpr int NW = 4 * (int)sizeof(pixel) / 4;
     const int cw = s.w >> 2, nc = cw * (s.h >> 2);
     int acc = 0;
     for (int c = s.lane; c < nc; c += 32)
@@ -145,8 +194,10 @@ __device__ __forceinline__ int warp_satd(const MEState<pixel>& s, const pixel* r
         for (int i = 0; i < 4; i++)
         {
             int a[4], b[4];
-            px4_s<pixel>(f + i * 64, a);
-            if (REFG) ld4i<pixel>(q + i * rs, b); else px4_s<pixel>(q + i * rs, b);
+            uint32_t rw[NW];
+            unpack4<pixel>((const uint32_t*)(f + i * 64), a);
+            ld_words<pixel, NW>(q + i * rs, rw);
+            unpack4<pixel>(rw, b);
 #pragma unroll
             for (int k = 0; k < 4; k++) d[i][k] = a[k] - b[k];
             me_hadamard4(d[i][0], d[i][1], d[i][2], d[i][3]);
@@ -164,60 +215,136 @@ __device__ __forceinline__ int warp_satd(const MEState<pixel>& s, const pixel* r
 }
 
 // ---- subpel (motion.cpp:1571-1599, luma only) ---------------------------------------------------
-// interpolates the PU at fractional (xFrac,yFrac) of the block starting at `src` into s.pred
-template<typename pixel>
-__device__ __forceinline__ void warp_interp_luma(const MEState<pixel>& s, const pixel* src, int xFrac, int yFrac)
+template<typename pixel> __device__ __forceinline__ void unpack_row12(const uint32_t* w, int v[12]);
+template<> __device__ __forceinline__ void unpack_row12<uint8_t>(const uint32_t* w, int v[12])
 {
+#pragma unroll
+    for (int i = 0; i < 3; i++) { v[4 * i] = w[i] & 0xff; v[4 * i + 1] = (w[i] >> 8) & 0xff; v[4 * i + 2] = (w[i] >> 16) & 0xff; v[4 * i + 3] = w[i] >> 24; }
+}
+template<> __device__ __forceinline__ void unpack_row12<uint16_t>(const uint32_t* w, int v[12])
+{
+#pragma unroll
+    for (int i = 0; i < 6; i++) { v[2 * i] = w[i] & 0xffff; v[2 * i + 1] = w[i] >> 16; }
+}
+template<typename pixel> __device__ __forceinline__ void store_px4(pixel* p, const int v[4]);
+template<> __device__ __forceinline__ void store_px4<uint8_t>(uint8_t* p, const int v[4])
+{
+    *(uint32_t*)p = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
+}
+template<> __device__ __forceinline__ void store_px4<uint16_t>(uint16_t* p, const int v[4])
+{
+    uint32_t* q = (uint32_t*)p;
+    q[0] = (uint32_t)v[0] | ((uint32_t)v[1] << 16); q[1] = (uint32_t)v[2] | ((uint32_t)v[3] << 16);
+}
+
+// interpolates the PU at fractional (xFrac,yFrac) of the block starting at `src` into s.pred (stride w).
+// Each lane produces groups of 4 horizontally adjacent pixels from word loads (3 words per row for the
+// horizontal taps, one word per tap row for the vertical ones).
+template<typename pixel>
+__device__ __noinline__ void warp_interp_luma(const MEState<pixel>& s, const pixel* src, int xFrac, int yFrac)
+{
+    constexpr int NW12 = 12 * (int)sizeof(pixel) / 4, NW4 = 4 * (int)sizeof(pixel) / 4;
     const int w = s.w, h = s.h, maxVal = (1 << s.depth) - 1, headRoom = 14 - s.depth;
-    if (!yFrac || !xFrac)
+    const int gw = w >> 2;
+    int c[8];
+    if (!yFrac)
     {
-        // luma_hpp / luma_vpp : ipfilter.cpp:79-118, :164-203
-        const int idx = yFrac ? yFrac : xFrac;
-        const int64_t step = yFrac ? s.stride : 1;
-        int c[8];
+        // luma_hpp : ipfilter.cpp:79-118
 #pragma unroll
-        for (int t = 0; t < 8; t++) c[t] = c_meLumaFilter[idx][t];
-        const pixel* base = src - 3 * step;
-        for (int e = s.lane; e < w * h; e += 32)
+        for (int t = 0; t < 8; t++) c[t] = c_meLumaFilter[xFrac][t];
+        for (int u = s.lane; u < gw * h; u += 32)
         {
-            int y = e / w, x = e - y * w;
-            const pixel* q = base + (int64_t)y * s.stride + x;
-            int sum = 0;
+            int y = u / gw, x = (u - y * gw) << 2;
+            uint32_t rw[NW12]; int v[12], o[4];
+            ld_words<pixel, NW12>(src + (int64_t)y * s.stride + x - 3, rw);
+            unpack_row12<pixel>(rw, v);
 #pragma unroll
-            for (int t = 0; t < 8; t++) sum += (int)__ldg(q + t * step) * c[t];
-            int val = (int16_t)((sum + 32) >> 6);
-            s.pred[e] = (pixel)(val < 0 ? 0 : (val > maxVal ? maxVal : val));
+            for (int k = 0; k < 4; k++)
+            {
+                int sum = 0;
+#pragma unroll
+                for (int t = 0; t < 8; t++) sum += v[k + t] * c[t];
+                int val = (int16_t)((sum + 32) >> 6);
+                o[k] = val < 0 ? 0 : (val > maxVal ? maxVal : val);
+            }
+            store_px4<pixel>(s.pred + y * w + x, o);
+        }
+    }
+    else if (!xFrac)
+    {
+        // luma_vpp : ipfilter.cpp:164-203
+#pragma unroll
+        for (int t = 0; t < 8; t++) c[t] = c_meLumaFilter[yFrac][t];
+        for (int u = s.lane; u < gw * h; u += 32)
+        {
+            int y = u / gw, x = (u - y * gw) << 2;
+            int sum[4] = { 0, 0, 0, 0 }, o[4];
+#pragma unroll
+            for (int t = 0; t < 8; t++)
+            {
+                uint32_t rw[NW4]; int v[4];
+                ld_words<pixel, NW4>(src + (int64_t)(y + t - 3) * s.stride + x, rw);
+                unpack4<pixel>(rw, v);
+#pragma unroll
+                for (int k = 0; k < 4; k++) sum[k] += v[k] * c[t];
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+            {
+                int val = (int16_t)((sum[k] + 32) >> 6);
+                o[k] = val < 0 ? 0 : (val > maxVal ? maxVal : val);
+            }
+            store_px4<pixel>(s.pred + y * w + x, o);
         }
     }
     else
     {
         // luma_hvpp = hps(isRowExt) + vsp : ipfilter.cpp:362-369
-        int c[8];
 #pragma unroll
         for (int t = 0; t < 8; t++) c[t] = c_meLumaFilter[xFrac][t];
         const int shift = 6 - headRoom, offset = (int)((unsigned)-8192 << shift);
-        const pixel* base = src - 3 - 3 * s.stride;
-        for (int e = s.lane; e < w * (h + 7); e += 32)
+        for (int u = s.lane; u < gw * (h + 7); u += 32)
         {
-            int y = e / w, x = e - y * w;
-            const pixel* q = base + (int64_t)y * s.stride + x;
-            int sum = 0;
+            int y = u / gw, x = (u - y * gw) << 2;
+            uint32_t rw[NW12]; int v[12];
+            ld_words<pixel, NW12>(src + (int64_t)(y - 3) * s.stride + x - 3, rw);
+            unpack_row12<pixel>(rw, v);
+            int o[4];
 #pragma unroll
-            for (int t = 0; t < 8; t++) sum += (int)__ldg(q + t) * c[t];
-            s.immed[e] = (int16_t)((sum + offset) >> shift);
+            for (int k = 0; k < 4; k++)
+            {
+                int sum = 0;
+#pragma unroll
+                for (int t = 0; t < 8; t++) sum += v[k + t] * c[t];
+                o[k] = (int16_t)((sum + offset) >> shift);
+            }
+            uint32_t* d = (uint32_t*)(s.immed + y * w + x);
+            d[0] = (uint32_t)(o[0] & 0xffff) | ((uint32_t)o[1] << 16);
+            d[1] = (uint32_t)(o[2] & 0xffff) | ((uint32_t)o[3] << 16);
         }
         __syncwarp();
 #pragma unroll
         for (int t = 0; t < 8; t++) c[t] = c_meLumaFilter[yFrac][t];
         const int shift2 = 6 + headRoom, offset2 = (1 << (shift2 - 1)) + (8192 << 6);
-        for (int e = s.lane; e < w * h; e += 32)
+        for (int u = s.lane; u < gw * h; u += 32)
         {
-            int y = e / w, x = e - y * w;
-            int sum = 0;
+            int y = u / gw, x = (u - y * gw) << 2;
+            int sum[4] = { 0, 0, 0, 0 }, o[4];
 #pragma unroll
-            for (int t = 0; t < 8; t++) sum += (int)s.immed[(y + t) * w + x] * c[t];
-            int val = (int16_t)((sum + offset2) >> shift2);
-            s.pred[e] = (pixel)(val < 0 ? 0 : (val > maxVal ? maxVal : val));
+            for (int t = 0; t < 8; t++)
+            {
+                const uint32_t* q = (const uint32_t*)(s.immed + (y + t) * w + x);
+                uint32_t w0 = q[0], w1 = q[1];
+                sum[0] += (int)(int16_t)(w0 & 0xffff) * c[t]; sum[1] += ((int)w0 >> 16) * c[t];
+                sum[2] += (int)(int16_t)(w1 & 0xffff) * c[t]; sum[3] += ((int)w1 >> 16) * c[t];
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+            {
+                int val = (int16_t)((sum[k] + offset2) >> shift2);
+                o[k] = val < 0 ? 0 : (val > maxVal ? maxVal : val);
+            }
+            store_px4<pixel>(s.pred + y * w + x, o);
         }
     }
     __syncwarp();
@@ -225,22 +352,22 @@ __device__ __forceinline__ void warp_interp_luma(const MEState<pixel>& s, const 
 
 // MotionEstimate::subpelCompare (motion.cpp:1571-1599); useSatd selects cmp
 template<typename pixel>
-__device__ __forceinline__ int subpel_compare(const MEState<pixel>& s, int qx, int qy, bool useSatd)
+__device__ __noinline__ int subpel_compare(const MEState<pixel>& s, int qx, int qy, bool useSatd)
 {
     const pixel* fref = s.fref + (qx >> 2) + (int64_t)(qy >> 2) * s.stride;
     const int xFrac = qx & 3, yFrac = qy & 3;
     if (!(xFrac | yFrac))
-        return useSatd ? warp_satd<pixel, true>(s, fref, s.stride) : warp_sad_g<pixel>(s, fref, s.stride);
+        return useSatd ? warp_satd<pixel>(s, fref, s.stride) : warp_sad_block<pixel>(s, fref, s.stride);
     __syncwarp();
     warp_interp_luma<pixel>(s, fref, xFrac, yFrac);
-    int c = useSatd ? warp_satd<pixel, false>(s, s.pred, s.w) : warp_sad_s<pixel>(s, s.pred, s.w);
+    int c = useSatd ? warp_satd<pixel>(s, s.pred, s.w) : warp_sad_block<pixel>(s, s.pred, s.w);
     __syncwarp();
     return c;
 }
 
 // ReferencePlanes::lowresQPelCost (common/lowres.h:94-120), 8x8 lowres blocks, hme = false
 template<typename pixel>
-__device__ __forceinline__ int lowres_qpel_cost(const MEState<pixel>& s, int qx, int qy, bool useSatd)
+__device__ __noinline__ int lowres_qpel_cost(const MEState<pixel>& s, int qx, int qy, bool useSatd)
 {
     if ((qx | qy) & 1)
     {
@@ -253,16 +380,16 @@ __device__ __forceinline__ int lowres_qpel_cost(const MEState<pixel>& s, int qx,
         for (int e = s.lane; e < s.w * s.h; e += 32)          // pixelavg_pp, pixel.cpp:545-557
         {
             int y = e / s.w, x = e - y * s.w;
-            s.pred[e] = (pixel)(((int)__ldg(frefA + (int64_t)y * s.stride + x) + (int)__ldg(frefB + (int64_t)y * s.stride + x) + 1) >> 1);
+            s.pred[e] = (pixel)(((int)frefA[(int64_t)y * s.stride + x] + (int)frefB[(int64_t)y * s.stride + x] + 1) >> 1);
         }
         __syncwarp();
-        int c = useSatd ? warp_satd<pixel, false>(s, s.pred, s.w) : warp_sad_s<pixel>(s, s.pred, s.w);
+        int c = useSatd ? warp_satd<pixel>(s, s.pred, s.w) : warp_sad_block<pixel>(s, s.pred, s.w);
         __syncwarp();
         return c;
     }
     int hpel = (qy & 2) | ((qx & 2) >> 1);
     const pixel* fref = s.lowres[hpel] + (qx >> 2) + (int64_t)(qy >> 2) * s.stride;
-    return useSatd ? warp_satd<pixel, true>(s, fref, s.stride) : warp_sad_g<pixel>(s, fref, s.stride);
+    return useSatd ? warp_satd<pixel>(s, fref, s.stride) : warp_sad_block<pixel>(s, fref, s.stride);
 }
 
 // ---- the search ------------------------------------------------------------------------------------
@@ -275,24 +402,32 @@ struct MESearch
 
     __device__ __forceinline__ MESearch(const MEState<pixel>& st) : s(st) {}
 
-    __device__ __forceinline__ int sadAt(int mx, int my) const { return warp_sad_g<pixel>(s, s.fref + mx + (int64_t)my * s.stride, s.stride); }
+    __device__ __forceinline__ int sadAt(int mx, int my) const
+    {
+        int ox[4] = { mx, 0, 0, 0 }, oy[4] = { my, 0, 0, 0 }, c[4];
+        warp_sad_k<pixel>(s, 1, ox, oy, c);
+        return c[0];
+    }
     __device__ __forceinline__ int fcost(int mx, int my) const { return mvcost(s, mx << 2, my << 2); }
     __device__ __forceinline__ bool inRange(int x, int y) const { return x >= mvmin.x && x <= mvmax.x && y >= mvmin.y && y <= mvmax.y; }
     __device__ __forceinline__ bool yOk(int y) const { return (y >= mvmin.y) & (y <= mvmax.y); }
 
     // COST_MV (motion.cpp:238-244)
-    __device__ __forceinline__ void costMv(int mx, int my)
+    __device__ __noinline__ void costMv(int mx, int my)
     {
         int cost = sadAt(mx, my) + fcost(mx, my);
         if (cost < bcost) { bcost = cost; bmv = mv2(mx, my); }
     }
     // COST_MV_X4 (motion.cpp:277-298): only the y range is checked (quirk)
-    __device__ __forceinline__ void costMvX4(MV2 omv, int x0, int y0, int x1, int y1, int x2, int y2, int x3, int y3)
+    __device__ __noinline__ void costMvX4(MV2 omv, int x0, int y0, int x1, int y1, int x2, int y2, int x3, int y3)
     {
         const int dx[4] = { x0, x1, x2, x3 }, dy[4] = { y0, y1, y2, y3 };
-        int costs[4];
+        int costs[4], ox[4], oy[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) costs[k] = sadAt(omv.x + dx[k], omv.y + dy[k]) + fcost(omv.x + dx[k], omv.y + dy[k]);
+        for (int k = 0; k < 4; k++) { ox[k] = omv.x + dx[k]; oy[k] = omv.y + dy[k]; }
+        warp_sad_k<pixel>(s, 4, ox, oy, costs);
+#pragma unroll
+        for (int k = 0; k < 4; k++) costs[k] += fcost(ox[k], oy[k]);
 #pragma unroll
         for (int k = 0; k < 4; k++)
             if (yOk(omv.y + dy[k]) && costs[k] < bcost) { bcost = costs[k]; bmv = mv2(omv.x + dx[k], omv.y + dy[k]); }
@@ -300,10 +435,13 @@ struct MESearch
     // COST_MV_X4_DIR / COST_MV_X3_DIR (motion.cpp:246-257, :315-328): costs relative to bmv, no update
     __device__ __forceinline__ void dirCosts(int n, const int dx[], const int dy[], int costs[]) const
     {
-        for (int k = 0; k < n; k++) costs[k] = sadAt(bmv.x + dx[k], bmv.y + dy[k]) + fcost(bmv.x + dx[k], bmv.y + dy[k]);
+        int ox[4] = { 0, 0, 0, 0 }, oy[4] = { 0, 0, 0, 0 };
+        for (int k = 0; k < n; k++) { ox[k] = bmv.x + dx[k]; oy[k] = bmv.y + dy[k]; }
+        warp_sad_k<pixel>(s, n, ox, oy, costs);
+        for (int k = 0; k < n; k++) costs[k] += fcost(ox[k], oy[k]);
     }
     // CROSS (motion.cpp:336-360)
-    __device__ __forceinline__ void cross(MV2 omv, int start, int x_max, int y_max)
+    __device__ __noinline__ void cross(MV2 omv, int start, int x_max, int y_max)
     {
         int i = start;
         if (x_max <= min(mvmax.x - omv.x, omv.x - mvmin.x))
@@ -324,14 +462,14 @@ struct MESearch
     }
 
     // COST_MV_PT_DIST (motion.cpp:224-236)
-    __device__ __forceinline__ void ptDist(int mx, int my, int point, int dist, int& bPointNr, int& bDistance)
+    __device__ __noinline__ void ptDist(int mx, int my, int point, int dist, int& bPointNr, int& bDistance)
     {
         int cost = sadAt(mx, my) + fcost(mx, my);
         if (cost < bcost) { bcost = cost; bmv = mv2(mx, my); bPointNr = point; bDistance = dist; }
     }
 
     // StarPatternSearch (motion.cpp:362-604)
-    __device__ void starPattern(int& bPointNr, int& bDistance, int earlyExitIters, int merange)
+    __device__ __noinline__ void starPattern(int& bPointNr, int& bDistance, int earlyExitIters, int merange)
     {
         const MV2 omv = bmv;
         int saved = bcost, rounds = 0;
@@ -431,7 +569,7 @@ struct MESearch
     }
 
     // square refine shared by HEX (motion.cpp:924-942)
-    __device__ __forceinline__ void squareRefine()
+    __device__ __noinline__ void squareRefine()
     {
         int costs[4];
         int dir = 0;
@@ -449,7 +587,7 @@ struct MESearch
     }
 
     // me_hex2 (motion.cpp:845-944)
-    __device__ void hexSearch(int merange)
+    __device__ __noinline__ void hexSearch(int merange)
     {
         int costs[4];
         { const int dx[3] = { -2, -1, 1 }, dy[3] = { 0, 2, 2 }; dirCosts(3, dx, dy, costs); }
@@ -693,7 +831,9 @@ __device__ int motion_estimate(const MEState<pixel>& s, MV2 mvmin, MV2 mvmax, MV
                 {
                     if (tx + RasterDistance * 3 <= mvmax.x)
                     {
-                        int c0 = S.sadAt(tx, ty), c1 = S.sadAt(tx + 5, ty), c2 = S.sadAt(tx + 10, ty), c3 = S.sadAt(tx + 15, ty);
+                        int rx[4] = { tx, tx + 5, tx + 10, tx + 15 }, ry[4] = { ty, ty, ty, ty }, rc[4];
+                        warp_sad_k<pixel>(s, 4, rx, ry, rc);
+                        int c0 = rc[0], c1 = rc[1], c2 = rc[2], c3 = rc[3];
                         c0 += S.fcost(tx, ty);
                         if (c0 < S.bcost) { S.bcost = c0; S.bmv = mv2(tx, ty); }
                         tx += RasterDistance;

@@ -400,4 +400,92 @@ int add_ps_plane_dev(Ctx* ctx, int depth, void* dst, int64_t dstStride, const vo
     return check(cudaGetLastError(), "add_ps_plane launch");
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// SAD pyramid: ONE streaming pass over a frame pair produces the SADs of every 8x8, 16x16, 32x32 and
+// 64x64 2Nx2N PU of every CTU (the "cost at the predictor" step of motionEstimate, motion.cpp:771-784,
+// for all PU levels at once; sad<lx,ly> of pixel.cpp:40-55 is additive over sub-blocks).  Each plane
+// byte is fetched exactly once with 128-bit loads; per-CTU full-pel displacement optional.
+// Mapping: one warp = 64 rows x 128 px (two CTUs); lane = rsub*8 + col owns a 16x16 block
+// (col: 16-px column, rsub: 16-row band); 32x32 / 64x64 sums are warp-shuffle reductions.
+// Algorithmic bytes per launch: 2*W*H + 4*(n8 + n16 + n32 + n64).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ld16_any(const uint8_t* p)
+{
+    uintptr_t a = (uintptr_t)p;
+    if ((a & 15) == 0) return __ldg((const uint4*)p);
+    const uint32_t* w = (const uint32_t*)(a & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)(a & 3) * 8;
+    uint32_t t0 = __ldg(w), t1 = __ldg(w + 1), t2 = __ldg(w + 2), t3 = __ldg(w + 3);
+    if (!sh) return make_uint4(t0, t1, t2, t3);
+    uint32_t t4 = __ldg(w + 4);
+    return make_uint4(__funnelshift_r(t0, t1, sh), __funnelshift_r(t1, t2, sh), __funnelshift_r(t2, t3, sh), __funnelshift_r(t3, t4, sh));
+}
+
+__global__ void __launch_bounds__(256)
+sad_pyramid_kernel(const uint8_t* __restrict__ cur, int64_t strideC, const uint8_t* __restrict__ ref, int64_t strideR,
+                   int ctuCols, int ctuRows, const int16_t* __restrict__ mvCtu,
+                   int32_t* __restrict__ out8, int32_t* __restrict__ out16, int32_t* __restrict__ out32, int32_t* __restrict__ out64)
+{
+    const int lane = threadIdx.x & 31;
+    const int pairsPerRow = (ctuCols + 1) >> 1;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (warp >= (int64_t)pairsPerRow * ctuRows) return;
+    const int ctuY = (int)(warp / pairsPerRow), pair = (int)(warp % pairsPerRow);
+    const int col = lane & 7, rsub = lane >> 3;
+    const int ctuX = pair * 2 + (col >> 2);
+    const bool valid = ctuX < ctuCols;
+    const int x0 = pair * 128 + col * 16, y0 = ctuY * 64 + rsub * 16;
+    int mvx = 0, mvy = 0;
+    if (mvCtu && valid) { mvx = mvCtu[2 * (ctuY * ctuCols + ctuX)]; mvy = mvCtu[2 * (ctuY * ctuCols + ctuX) + 1]; }
+    const uint8_t* c = cur + (int64_t)y0 * strideC + x0;
+    const uint8_t* r = ref + (int64_t)(y0 + mvy) * strideR + x0 + mvx;
+    uint32_t s8[4] = { 0, 0, 0, 0 };        // [row group 0/1][left/right 8x8]
+    if (valid)
+    {
+#pragma unroll
+        for (int g = 0; g < 2; g++)
+        {
+            uint4 a[8], b[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) { a[i] = __ldg((const uint4*)(c + (int64_t)(g * 8 + i) * strideC)); b[i] = ld16_any(r + (int64_t)(g * 8 + i) * strideR); }
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+            {
+                s8[g * 2 + 0] += __vsadu4(a[i].x, b[i].x) + __vsadu4(a[i].y, b[i].y);
+                s8[g * 2 + 1] += __vsadu4(a[i].z, b[i].z) + __vsadu4(a[i].w, b[i].w);
+            }
+        }
+    }
+    const int n8x = ctuCols * 8, n16x = ctuCols * 4, n32x = ctuCols * 2;
+    if (valid)
+    {
+        const int bx = x0 >> 3, by = y0 >> 3;
+        *(int2*)(out8 + (int64_t)by * n8x + bx) = make_int2((int)s8[0], (int)s8[1]);
+        *(int2*)(out8 + (int64_t)(by + 1) * n8x + bx) = make_int2((int)s8[2], (int)s8[3]);
+    }
+    int s16 = (int)(s8[0] + s8[1] + s8[2] + s8[3]);
+    if (valid) out16[(int64_t)(y0 >> 4) * n16x + (x0 >> 4)] = s16;
+    int s32 = s16 + __shfl_xor_sync(0xffffffffu, s16, 1);
+    s32 += __shfl_xor_sync(0xffffffffu, s32, 8);
+    if (valid && !(lane & 1) && !(lane & 8)) out32[(int64_t)(y0 >> 5) * n32x + (x0 >> 5)] = s32;
+    int s64 = s32 + __shfl_xor_sync(0xffffffffu, s32, 2);
+    s64 += __shfl_xor_sync(0xffffffffu, s64, 16);
+    if (valid && !(lane & 3) && !(lane & 24)) out64[(int64_t)ctuY * ctuCols + ctuX] = s64;
+}
+
+int sad_pyramid_dev(Ctx* ctx, int depth, const void* cur, int64_t strideC, const void* ref, int64_t strideR, int ctuCols, int ctuRows,
+                    const int16_t* mvCtu, int32_t* out8, int32_t* out16, int32_t* out32, int32_t* out64)
+{
+    if (depth != 8) { set_error("sad_pyramid: 8-bit planes only (use pixelcmp grid mode for high bit depth)"); return -1; }
+    if (((uintptr_t)cur & 15) || (strideC & 15)) { set_error("sad_pyramid: cur plane and stride must be 16-byte aligned"); return -1; }
+    if (((uintptr_t)out8 & 7)) { set_error("sad_pyramid: out8 must be 8-byte aligned"); return -1; }
+    int64_t warps = (int64_t)((ctuCols + 1) / 2) * ctuRows;
+    if (warps <= 0) return 0;
+    unsigned blocks = (unsigned)((warps * 32 + 255) / 256);
+    sad_pyramid_kernel<<<blocks, 256, 0, ctx->stream>>>((const uint8_t*)cur, strideC, (const uint8_t*)ref, strideR, ctuCols, ctuRows, mvCtu, out8, out16, out32, out64);
+    ctx->launches++;
+    return check(cudaGetLastError(), "sad_pyramid launch");
+}
+
 } // namespace x265b200
