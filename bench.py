@@ -222,6 +222,7 @@ def main():
     qtab = torch.full((1024,), 26214, dtype=torch.int32, device=dev)          # quantScales[qp%6=0] flat list
     numsig = torch.empty(n32, dtype=torch.int32, device=dev)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    me_out = torch.empty((njobs, 3), dtype=torch.int32, device=dev)
     res_h = torch.empty((njobs, 3), dtype=torch.int32).pin_memory()
     P = lambda t: t.data_ptr()
 
@@ -242,12 +243,11 @@ def main():
                                 P(sad_out[32]) + 4 * r * level_n[32], P(sad_out[64]) + 4 * r * level_n[64])
         if time_sad:
             e1.record(); sad_events.append((e0, e1))
-        # 2. full motion search for every PU x ref
-        # one launch per PU size class so each launch carves only the shared memory its PUs need
+        # 2. full motion search for every PU x ref: TMA-staged windows, one CTA per (CTU, ref)
         if time_sad:
             m0 = torch.cuda.Event(enable_timing=True); m1 = torch.cuda.Event(enable_timing=True); m0.record()
-        for s, (j0, jn) in level_ranges.items():
-            ctx.me_batch_dev(8, cptr, STRIDE, None, STRIDE, P(jobs_d) + j0 * job_bytes, jn, s, s, pkg.ME_HEX, SUBME, MERANGE, lam, 1, dRefPlanes=P(ref_ptrs))
+        ctx.me_frame_dev(8, cptr, STRIDE, [P(r) + origin for r in refs], STRIDE, PAD, PAD, ROWS, CTU_COLS, CTU_ROWS, 15, None,
+                         pkg.ME_HEX, SUBME, MERANGE, lam, P(me_out))
         if time_sad:
             m1.record(); me_events.append((m0, m1))
         # 3. residual -> DCT32 -> quant -> dequant -> IDCT32 -> recon (one launch each, whole plane)
@@ -269,15 +269,13 @@ def main():
         if world == 1:
             return
         dist.all_gather_into_tensor(gathered, ring[t % NF])
-        out = jobs_d.view(torch.int32).view(njobs, -1)[:, -3:].contiguous()
-        dist.gather(out, res_all, dst=0)
+        dist.gather(me_out, res_all, dst=0)
 
     def e2e_step(t):
         ring[t % NF].copy_(pinned[t % NF], non_blocking=True)                   # H2D: the new frame
         hot_path(t)
         exchange(t)
-        out = jobs_d.view(torch.int32).view(njobs, -1)[:, -3:]
-        res_h.copy_(out, non_blocking=True)                                   # D2H: {mvx, mvy, cost} per PU
+        res_h.copy_(me_out, non_blocking=True)                                   # D2H: {mvx, mvy, cost} per PU
         stream.synchronize()
 
     def barrier():
@@ -349,7 +347,7 @@ def main():
                              "peak_kind": pk_kind, "launches_per_step": sad_launches, "ms_per_step": sad_t * 1e3}}
         me_bytes = NREF * (2 * W * (CTU_ROWS * CTU)) + njobs * 8
         me_t = float(np.mean(me_ms)) / 1e3
-        line["roofline_me_search"] = {"kernel": "me_batch_kernel (HEX + subme 2, %d searches)" % njobs, "bound": "hbm", "achieved": me_bytes / me_t / 1e9,
+        line["roofline_me_search"] = {"kernel": "me_frame_kernel (TMA-staged windows; HEX + subme 2, %d searches)" % njobs, "bound": "hbm", "achieved": me_bytes / me_t / 1e9,
                                       "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": me_bytes / me_t / 1e9 / pk["hbm_gbs"], "ms_per_step": me_t * 1e3,
                                       "note": "ALU/latency-bound pattern search over L2-resident planes (DESIGN.md 5)"}
         if world == 1:

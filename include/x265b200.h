@@ -174,6 +174,18 @@ int x265b200_me_batch_dev(x265b200_ctx* ctx, int depth, const void* fencPlane, i
                           const void* refPlane, const void* const* refPlanes, int64_t refStride,
                           x265b200_me_job* jobs, int64_t n, int maxW, int maxH,
                           int searchMethod, int subpelRefine, int merange, double lambda, int maxSlices);
+/* Frame form of the same search: every 2Nx2N PU (levels selected by puMask: bit0 64x64, bit1 32x32, bit2 16x16,
+ * bit3 8x8) of every 64x64 CTU against numRefs reference planes.  One CTA per (CTU, reference) stages the
+ * source CTU and the search window in shared memory with TMA, then runs the PU searches from there.
+ * Per-PU semantics = motionEstimate(mvmin = (mvp>>2) - merange, mvmax = (mvp>>2) + merange, qmvp = mvp, no mvc)
+ * with the CTU's mvp (mvpCtu[ref][ctu][2], quarter-pel, NULL = 0).  Planes are given by their ORIGIN (pixel 0,0);
+ * marginX/marginY pixels around the picture and rowsTotal rows of `stride` pixels must be allocated (the
+ * reference's PicYuv layout).  refOriginsHost is a HOST array of device pointers.
+ * out: int32 {mvx, mvy, cost} per PU, ordered [ref][level 64,32,16,8 (only those in puMask)][raster grid of PUs]. */
+int x265b200_me_frame_dev(x265b200_ctx* ctx, int depth, const void* curOrigin, int64_t curStride,
+                          const void* const* refOriginsHost, int numRefs, int64_t refStride,
+                          int marginX, int marginY, int rowsTotal, int ctuCols, int ctuRows, int puMask,
+                          const int32_t* mvpCtu, int searchMethod, int subpelRefine, int merange, double lambda, int32_t* out);
 /* The lambda-scaled MV cost table the kernels use (host side, no GPU needed):
  * out[2*32768 + i] = cost of a quarter-pel MV difference i, i in [-65536, 65536]. */
 int x265b200_bitcost_table(double lambda, uint16_t* out);

@@ -82,3 +82,53 @@ def test_me_slice_clamp(ctx):
 def test_me_qp_range(ctx):
     for qp in (0, 12, 37, 51):
         _run(ctx, 8, pkg.ME_HEX, 2, 24, qp, [(16, 16), (8, 8)], seed=900 + qp, n_per_size=8)
+
+
+@pytest.mark.parametrize("depth,method,subme,merange", [(8, pkg.ME_HEX, 2, 57), (8, pkg.ME_STAR, 3, 24), (8, pkg.ME_DIA, 0, 57),
+                                                        (8, pkg.ME_UMH, 2, 32), (10, pkg.ME_HEX, 2, 40)])
+def test_me_frame_tma_window(ctx, depth, method, subme, merange):
+    """frame form (TMA-staged search windows, one CTA per CTU x reference) == the reference's motionEstimate
+    for every 2Nx2N PU of every CTU, two references, per-CTU predictors."""
+    ctuCols, ctuRows, NREF = 3, 2, 2
+    W, H = ctuCols * 64, ctuRows * 64
+    mx, my = 144, 128                      # plane margins (>= merange + 16)
+    pad = mx
+    cur, ref0, S, origin = synth_pair(W, H, pad, depth=depth, seed=42 + depth, motion=(7, -4))
+    _, ref1, _, _ = synth_pair(W, H, pad, depth=depth, seed=43 + depth, motion=(-9, 6))
+    refs = [ref0, ref1]
+    rowsTotal = H + 2 * pad
+    rng = np.random.default_rng(5)
+    mvp = rng.integers(-40, 41, (NREF, ctuCols * ctuRows, 2)).astype(np.int32)
+    mvp[0, 0] = 0
+    lam = pkg.lambda_for_qp(30, depth)
+    item = cur.itemsize
+    dC = ctx.to_device(cur)
+    dR = [ctx.to_device(r) for r in refs]
+    dMvp = ctx.to_device(mvp)
+    per_level = [ctuCols * ctuRows * (1 << l) ** 2 for l in range(4)]
+    nPU = sum(per_level)
+    dOut = ctx.empty(NREF * nPU * 12)
+    ctx.me_frame_dev(depth, dC.ptr + origin * item, S, [d.ptr + origin * item for d in dR], S, pad, pad, rowsTotal, ctuCols, ctuRows, 15,
+                     dMvp, method, subme, merange, lam, dOut)
+    got = dOut.download(np.int32).reshape(NREF, nPU, 3)
+    for r in range(NREF):
+        jobs = []
+        for level in range(4):
+            s = 64 >> level
+            per = 1 << level
+            for gy in range(ctuRows * per):
+                for gx in range(ctuCols * per):
+                    ctu = (gy // per) * ctuCols + (gx // per)
+                    px, py = int(mvp[r, ctu, 0]), int(mvp[r, ctu, 1])
+                    jobs.append((gx * s, gy * s, s, px, py))
+        job = np.zeros(len(jobs), dtype=pkg.ME_JOB)
+        for i, (x, y, s, px, py) in enumerate(jobs):
+            job[i]["puX"], job[i]["puY"], job[i]["w"], job[i]["h"] = x, y, s, s
+            job[i]["mvpX"], job[i]["mvpY"] = px, py
+            job[i]["mvminX"], job[i]["mvminY"] = (px >> 2) - merange, (py >> 2) - merange
+            job[i]["mvmaxX"], job[i]["mvmaxY"] = (px >> 2) + merange, (py >> 2) + merange
+        ex, ey, ec = ref_me(depth, cur, refs[r], S, origin, job, method, subme, merange, 30)
+        bad = np.nonzero((got[r, :, 0] != ex) | (got[r, :, 1] != ey) | (got[r, :, 2] != ec))[0]
+        assert not len(bad), (r, int(bad[0]), jobs[bad[0]], got[r, bad[0]].tolist(), int(ex[bad[0]]), int(ey[bad[0]]), int(ec[bad[0]]), len(bad))
+    for b in [dC, dMvp, dOut] + dR:
+        b.free()

@@ -62,11 +62,14 @@ void* dev(int slot, size_t bytes)
     return tl.buf[slot];
 }
 
-// stage a w x h region (elements of `es` bytes) with row stride `stride` into slot -> compact pitch w
-void* up2d(int slot, const void* src, intptr_t stride, int w, int h, int es)
+// stage a w x h region (elements of `es` bytes, row stride `stride` elements) as ONE contiguous span of
+// (h-1)*stride + w elements; the device copy keeps the caller's stride (TestBench uses strides smaller than
+// the block width, e.g. FENC_STRIDE-5 for sad_x3/x4, so a pitched 2-D copy is not generally possible).
+void* up_span(int slot, const void* src, intptr_t stride, int w, int h, int es)
 {
-    void* d = dev(slot, (size_t)w * h * es);
-    CK(x265b200_upload2d(C(), d, (size_t)w * es, src, (size_t)stride * es, (size_t)w * es, h));
+    size_t bytes = ((size_t)(h - 1) * stride + w) * es;
+    void* d = dev(slot, bytes);
+    CK(x265b200_upload(C(), d, src, bytes));
     return d;
 }
 void* up1d(int slot, const void* src, size_t bytes)
@@ -77,7 +80,9 @@ void* up1d(int slot, const void* src, size_t bytes)
 }
 void down2d(void* dst, intptr_t stride, const void* d, int w, int h, int es)
 {
-    CK(x265b200_download2d(C(), dst, (size_t)stride * es, d, (size_t)w * es, (size_t)w * es, h));
+    if (stride >= w) { CK(x265b200_download2d(C(), dst, (size_t)stride * es, d, (size_t)w * es, (size_t)w * es, h)); return; }
+    for (int y = 0; y < h; y++)      // overlapping destination rows: copy in the order the C code writes them
+        CK(x265b200_download(C(), (char*)dst + (size_t)y * stride * es, (const char*)d + (size_t)y * w * es, (size_t)w * es));
 }
 
 const int PX = (int)sizeof(pixel);
@@ -86,56 +91,57 @@ const int PX = (int)sizeof(pixel);
 template<int W, int H, int KIND>
 int cmp_thunk(const pixel* a, intptr_t sa, const pixel* b, intptr_t sb)
 {
-    void* dA = up2d(0, a, sa, W, H, PX);
-    void* dB = up2d(1, b, sb, W, H, PX);
+    void* dA = up_span(0, a, sa, W, H, PX);
+    void* dB = up_span(1, b, sb, W, H, PX);
     void* dO = dev(2, 8);
-    CK(x265b200_pixelcmp_dev(C(), KIND, X265_DEPTH, W, H, dA, W, dB, W, nullptr, nullptr, nullptr, 1, 1, dO));
+    CK(x265b200_pixelcmp_dev(C(), KIND, X265_DEPTH, W, H, dA, sa, dB, sb, nullptr, nullptr, nullptr, 1, 1, dO));
     int32_t r; CK(x265b200_download(C(), &r, dO, 4));
     return r;
 }
 template<int W, int H>
 sse_t sse_pp_thunk(const pixel* a, intptr_t sa, const pixel* b, intptr_t sb)
 {
-    void* dA = up2d(0, a, sa, W, H, PX);
-    void* dB = up2d(1, b, sb, W, H, PX);
+    void* dA = up_span(0, a, sa, W, H, PX);
+    void* dB = up_span(1, b, sb, W, H, PX);
     void* dO = dev(2, 8);
-    CK(x265b200_pixelcmp_dev(C(), X265B200_CMP_SSE_PP, X265_DEPTH, W, H, dA, W, dB, W, nullptr, nullptr, nullptr, 1, 1, dO));
+    CK(x265b200_pixelcmp_dev(C(), X265B200_CMP_SSE_PP, X265_DEPTH, W, H, dA, sa, dB, sb, nullptr, nullptr, nullptr, 1, 1, dO));
     uint64_t r; CK(x265b200_download(C(), &r, dO, 8));
     return (sse_t)r;
 }
 template<int W, int H>
 sse_t sse_ss_thunk(const int16_t* a, intptr_t sa, const int16_t* b, intptr_t sb)
 {
-    void* dA = up2d(0, a, sa, W, H, 2);
-    void* dB = up2d(1, b, sb, W, H, 2);
+    void* dA = up_span(0, a, sa, W, H, 2);
+    void* dB = up_span(1, b, sb, W, H, 2);
     void* dO = dev(2, 8);
-    CK(x265b200_pixelcmp_dev(C(), X265B200_CMP_SSE_SS, X265_DEPTH, W, H, dA, W, dB, W, nullptr, nullptr, nullptr, 1, 1, dO));
+    CK(x265b200_pixelcmp_dev(C(), X265B200_CMP_SSE_SS, X265_DEPTH, W, H, dA, sa, dB, sb, nullptr, nullptr, nullptr, 1, 1, dO));
     uint64_t r; CK(x265b200_download(C(), &r, dO, 8));
     return (sse_t)r;
 }
 template<int N>
 sse_t ssd_s_thunk(const int16_t* a, intptr_t sa)
 {
-    void* dA = up2d(0, a, sa, N, N, 2);
+    void* dA = up_span(0, a, sa, N, N, 2);
     void* dO = dev(2, 8);
-    CK(x265b200_pixelcmp_dev(C(), X265B200_CMP_SSD_S, X265_DEPTH, N, N, dA, N, dA, N, nullptr, nullptr, nullptr, 1, 1, dO));
+    CK(x265b200_pixelcmp_dev(C(), X265B200_CMP_SSD_S, X265_DEPTH, N, N, dA, sa, dA, sa, nullptr, nullptr, nullptr, 1, 1, dO));
     uint64_t r; CK(x265b200_download(C(), &r, dO, 8));
     return (sse_t)r;
 }
 template<int W, int H, int K>
 void sad_xn(const pixel* fenc, const pixel* const refs[K], intptr_t stride, int32_t* res)
 {
-    void* dF = up2d(0, fenc, FENC_STRIDE, FENC_STRIDE, H, PX);                 // keep the 64-pixel pitch (pixel.cpp:89)
-    char* dR = (char*)dev(1, (size_t)K * W * H * PX);
+    void* dF = up_span(0, fenc, FENC_STRIDE, W, H, PX);                         // 64-pixel pitch kept (pixel.cpp:89)
+    const size_t span = (size_t)(H - 1) * stride + W;                           // elements per reference block
+    char* dR = (char*)dev(1, (size_t)K * span * PX);
     int64_t off[4];
     for (int k = 0; k < K; k++)
     {
-        CK(x265b200_upload2d(C(), dR + (size_t)k * W * H * PX, (size_t)W * PX, refs[k], (size_t)stride * PX, (size_t)W * PX, H));
-        off[k] = (int64_t)k * W * H;
+        CK(x265b200_upload(C(), dR + (size_t)k * span * PX, refs[k], span * PX));
+        off[k] = (int64_t)k * span;
     }
     void* dOff = up1d(2, off, sizeof(int64_t) * K);
     void* dO = dev(3, 16);
-    CK(x265b200_sad_xn_dev(C(), X265_DEPTH, K, W, H, dF, 0, dR, W, (const int64_t*)dOff, 1, (int32_t*)dO));
+    CK(x265b200_sad_xn_dev(C(), X265_DEPTH, K, W, H, dF, 0, dR, stride, (const int64_t*)dOff, 1, (int32_t*)dO));
     CK(x265b200_download(C(), res, dO, 4 * K));
 }
 template<int W, int H>
@@ -155,9 +161,9 @@ void sad_x4_thunk(const pixel* fenc, const pixel* r0, const pixel* r1, const pix
 template<int IDX, int N>
 void dct_thunk(const int16_t* src, int16_t* dst, intptr_t srcStride)
 {
-    void* dS = up2d(0, src, srcStride, N, N, 2);
+    void* dS = up_span(0, src, srcStride, N, N, 2);
     void* dD = dev(1, N * N * 2);
-    CK(x265b200_dct_dev(C(), IDX, X265_DEPTH, (const int16_t*)dS, N * N, N, (int16_t*)dD, 1));
+    CK(x265b200_dct_dev(C(), IDX, X265_DEPTH, (const int16_t*)dS, 0, srcStride, (int16_t*)dD, 1));
     CK(x265b200_download(C(), dst, dD, N * N * 2));
 }
 template<int IDX, int N>
@@ -222,12 +228,12 @@ void interp_run(const void* src, intptr_t srcStride, void* dst, intptr_t dstStri
     const int rw = W + (horiz ? TAPS - 1 : 0), rh = H + (vert ? TAPS - 1 : 0);
     const int ses = srcShort ? 2 : PX, des = dstShort ? 2 : PX;
     const char* origin = (const char*)src - ((intptr_t)top * srcStride + left) * ses;
-    void* dS = up2d(0, origin, srcStride, rw, rh, ses);
+    void* dS = up_span(0, origin, srcStride, rw, rh, ses);
     const int outRows = H + ((KIND == X265B200_IP_HPS && isRowExt) ? TAPS - 1 : 0);
     void* dD = dev(1, (size_t)W * outRows * des);
-    x265b200_interp_job job; job.srcOff = (int64_t)top * rw + left; job.dstOff = 0; job.idxX = idxX; job.idxY = idxY;
+    x265b200_interp_job job; job.srcOff = (int64_t)top * srcStride + left; job.dstOff = 0; job.idxX = idxX; job.idxY = idxY;
     void* dJ = up1d(2, &job, sizeof(job));
-    CK(x265b200_interp_dev(C(), KIND, TAPS, X265_DEPTH, W, H, dS, rw, dD, W, (const x265b200_interp_job*)dJ, 1, isRowExt));
+    CK(x265b200_interp_dev(C(), KIND, TAPS, X265_DEPTH, W, H, dS, srcStride, dD, W, (const x265b200_interp_job*)dJ, 1, isRowExt));
     down2d(dst, dstStride, dD, W, outRows, des);
 }
 template<int T, int W, int H, int K> void ip_pp(const pixel* s, intptr_t ss, pixel* d, intptr_t ds, int c) { interp_run<T, W, H, K>(s, ss, d, ds, c, 0, 0); }

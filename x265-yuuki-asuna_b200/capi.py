@@ -322,3 +322,14 @@ def _ctx_sad_pyramid_dev(self, depth, dCur, strideCur, dRef, strideRef, ctuCols,
 
 
 Ctx.sad_pyramid_dev = _ctx_sad_pyramid_dev
+
+
+def _ctx_me_frame_dev(self, depth, dCur, curStride, refOrigins, refStride, marginX, marginY, rowsTotal, ctuCols, ctuRows, puMask,
+                      dMvpCtu, searchMethod, subpelRefine, merange, lam, dOut):
+    arr = (ctypes.c_void_p * len(refOrigins))(*[int(p) for p in refOrigins])
+    self._chk(self.L.x265b200_me_frame_dev(self.h, depth, _vp(dCur), _i64(curStride), arr, len(refOrigins), _i64(refStride), int(marginX), int(marginY),
+                                           int(rowsTotal), int(ctuCols), int(ctuRows), int(puMask), _vp(dMvpCtu), int(searchMethod), int(subpelRefine),
+                                           int(merange), ctypes.c_double(lam), _vp(dOut)))
+
+
+Ctx.me_frame_dev = _ctx_me_frame_dev

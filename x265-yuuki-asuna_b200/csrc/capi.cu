@@ -88,6 +88,9 @@ int me_batch_dev(Ctx*, int depth, const void* fencPlane, int64_t fencStride, con
                  int64_t refStride, x265b200_me_job* jobs, int64_t n, int maxW, int maxH,
                  int searchMethod, int subpelRefine, int merange, double lambda, int maxSlices);
 void host_bitcost_table(double lambda, uint16_t* out);
+int me_frame_dev(Ctx*, int depth, const void* curOrigin, int64_t curStride, const void* const* refOriginsHost, int numRefs, int64_t refStride,
+                 int marginX, int marginY, int rowsTotal, int ctuCols, int ctuRows, int puMask, const int32_t* mvpCtu,
+                 int searchMethod, int subpelRefine, int merange, double lambda, int32_t* out);
 int lowres_init_dev(Ctx*, int depth, const void* src, int64_t srcStride, void* const planes[4], int64_t dstStride, int width, int height, int marginX, int marginY);
 int la_intra_dev(Ctx*, int depth, const void* plane0, int64_t stride, int widthInCU, int heightInCU, const int32_t* invQscale,
                  int intraPenalty, int32_t* intraCost, uint8_t* intraMode, uint16_t* lowresCosts, int32_t* rowSatds, int32_t* sums);
@@ -340,6 +343,14 @@ int x265b200_me_batch_dev(x265b200_ctx* ctx, int depth, const void* fencPlane, i
     REQUIRE_CTX(ctx);
     return me_batch_dev(CTX(ctx), depth, fencPlane, fencStride, refPlane, refPlanes, refStride, jobs, n, maxW, maxH,
                         searchMethod, subpelRefine, merange, lambda, maxSlices);
+}
+int x265b200_me_frame_dev(x265b200_ctx* ctx, int depth, const void* curOrigin, int64_t curStride, const void* const* refOriginsHost, int numRefs,
+                          int64_t refStride, int marginX, int marginY, int rowsTotal, int ctuCols, int ctuRows, int puMask,
+                          const int32_t* mvpCtu, int searchMethod, int subpelRefine, int merange, double lambda, int32_t* out)
+{
+    REQUIRE_CTX(ctx);
+    return me_frame_dev(CTX(ctx), depth, curOrigin, curStride, refOriginsHost, numRefs, refStride, marginX, marginY, rowsTotal,
+                        ctuCols, ctuRows, puMask, mvpCtu, searchMethod, subpelRefine, merange, lambda, out);
 }
 int x265b200_bitcost_table(double lambda, uint16_t* out)
 {

@@ -323,7 +323,7 @@ la_search_kernel(LASearchArgs p)
 
         MEState<pixel> s;
         s.fenc = sFenc[warp]; s.pred = sPred[warp]; s.immed = nullptr;
-        s.stride = p.stride; s.isLowres = true; s.w = 8; s.h = 8; s.lane = lane; s.depth = p.depth;
+        s.stride = p.stride; s.isLowres = true; s.perThread = false; s.w = 8; s.h = 8; s.lane = lane; s.depth = p.depth;
         s.partSizeScale = 4; s.cost = p.cost + 2 * 32768;
 
         int rightX = 0, rightY = 0;       // fencMV[1] of the previous iteration
@@ -349,7 +349,7 @@ la_search_kernel(LASearchArgs p)
             }
             __syncwarp();
             for (int k = 0; k < 4; k++) s.lowres[k] = refPlanes[k] + pelOffset;
-            s.fref = s.lowres[0];
+            s.fref = s.lowres[0]; s.gfref = s.lowres[0]; s.gstride = p.stride;
 
             // reverse-order MV prediction candidates (slicetype.cpp:3269-3280)
             int mvc[4][2], numc = 0;

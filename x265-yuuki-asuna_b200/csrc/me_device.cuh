@@ -43,10 +43,13 @@ struct MEState
     pixel*   pred;       // subpel prediction, row stride = w (motion.cpp:1581 subpelbuf)
     int16_t* immed;      // hvpp intermediate, w * (h + 7)
     // reference
-    const pixel* fref;   // fpelPlane[0] + blockOffset
+    const pixel* fref;   // fpelPlane[0] + blockOffset (global plane, or the TMA-staged shared-memory window)
     int64_t  stride;
+    const pixel* gfref;  // the same block in the GLOBAL plane (for the zero-MV candidate, which may lie outside a window)
+    int64_t  gstride;
     const pixel* lowres[4];   // lowres hpel planes + blockOffset (isLowres path), else unused
     bool     isLowres;
+    bool     perThread;   // true: ONE THREAD runs the whole search (small PUs); false: one warp (lanes cooperate)
     int      w, h, lane, depth, partSizeScale;
     const uint16_t* cost;     // centred lambda-scaled MV cost table (bitcost.cpp:31-60)
     int      mvpx, mvpy;      // setMVP(qmvp), bitcost.h:41
@@ -139,27 +142,6 @@ __device__ __forceinline__ void sad_k_impl(const MEState<pixel>& s, int K, const
     costs[3] = __shfl_sync(0xffffffffu, c, 24);
 }
 
-template<typename pixel>
-__device__ __noinline__ void warp_sad_k(const MEState<pixel>& s, int K, const int ox[4], const int oy[4], int costs[4])
-{
-    if (!(s.w & 15))     sad_k_impl<pixel, 16>(s, K, ox, oy, costs);
-    else if (!(s.w & 7)) sad_k_impl<pixel, 8>(s, K, ox, oy, costs);
-    else                 sad_k_impl<pixel, 4>(s, K, ox, oy, costs);
-}
-
-// SAD of the cached PU against an arbitrary block (global or shared) with row stride rs
-template<typename pixel>
-__device__ __noinline__ int warp_sad_block(const MEState<pixel>& s, const pixel* r, int64_t rs)
-{
-    const int gw = s.w >> 2, ng = gw * s.h;
-    int acc = 0;
-    for (int u = s.lane; u < ng; u += 32)
-    {
-        int y = u / gw, x = (u - y * gw) << 2;
-        acc += sad_seg<pixel, 4>(s.fenc + y * 64 + x, r + (int64_t)y * rs + x);
-    }
-    return warp_sum(acc);
-}
 
 __device__ __forceinline__ void me_hadamard4(int& a, int& b, int& c, int& d)
 {
@@ -177,10 +159,91 @@ template<> __device__ __forceinline__ void unpack4<uint16_t>(const uint32_t* w, 
     v[0] = w[0] & 0xffff; v[1] = w[0] >> 16; v[2] = w[1] & 0xffff; v[3] = w[1] >> 16;
 }
 
+
+// ---- per-thread primitives (perThread mode: no shuffles, no __syncwarp; used for 8x8 / 16x16 PUs) -----------
+template<typename pixel, int SEG>
+__device__ __forceinline__ int thread_sad_one(const MEState<pixel>& s, const pixel* r, int64_t rs)
+{
+    int acc = 0;
+    for (int y = 0; y < s.h; y++)
+        for (int x = 0; x < s.w; x += SEG)
+            acc += sad_seg<pixel, SEG>(s.fenc + y * 64 + x, r + (int64_t)y * rs + x);
+    return acc;
+}
+template<typename pixel>
+__device__ __forceinline__ int thread_sad_any(const MEState<pixel>& s, const pixel* r, int64_t rs)
+{
+    if (!(s.w & 15)) return thread_sad_one<pixel, 16>(s, r, rs);
+    if (!(s.w & 7))  return thread_sad_one<pixel, 8>(s, r, rs);
+    return thread_sad_one<pixel, 4>(s, r, rs);
+}
+template<typename pixel>
+__device__ __forceinline__ int thread_satd(const MEState<pixel>& s, const pixel* r, int64_t rs)
+{
+    constexpr int NW = 4 * (int)sizeof(pixel) / 4;
+    int acc = 0;
+    for (int cy = 0; cy < s.h; cy += 4)
+        for (int cx = 0; cx < s.w; cx += 4)
+        {
+            int d[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+            {
+                int a[4], b[4];
+                uint32_t rw[NW];
+                unpack4<pixel>((const uint32_t*)(s.fenc + (cy + i) * 64 + cx), a);
+                ld_words<pixel, NW>(r + (int64_t)(cy + i) * rs + cx, rw);
+                unpack4<pixel>(rw, b);
+#pragma unroll
+                for (int k = 0; k < 4; k++) d[i][k] = a[k] - b[k];
+                me_hadamard4(d[i][0], d[i][1], d[i][2], d[i][3]);
+            }
+            int t = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+            {
+                me_hadamard4(d[0][k], d[1][k], d[2][k], d[3][k]);
+                t += abs(d[0][k]) + abs(d[1][k]) + abs(d[2][k]) + abs(d[3][k]);
+            }
+            acc += t >> 1;
+        }
+    return acc;
+}
+
+template<typename pixel>
+__device__ __noinline__ void warp_sad_k(const MEState<pixel>& s, int K, const int ox[4], const int oy[4], int costs[4])
+{
+    if (s.perThread)
+    {
+        for (int k = 0; k < K; k++)
+            costs[k] = thread_sad_any<pixel>(s, s.fref + ox[k] + (int64_t)oy[k] * s.stride, s.stride);
+        return;
+    }
+    if (!(s.w & 15))     sad_k_impl<pixel, 16>(s, K, ox, oy, costs);
+    else if (!(s.w & 7)) sad_k_impl<pixel, 8>(s, K, ox, oy, costs);
+    else                 sad_k_impl<pixel, 4>(s, K, ox, oy, costs);
+}
+
+// SAD of the cached PU against an arbitrary block (global or shared) with row stride rs
+template<typename pixel>
+__device__ __noinline__ int warp_sad_block(const MEState<pixel>& s, const pixel* r, int64_t rs)
+{
+    if (s.perThread) return thread_sad_any<pixel>(s, r, rs);
+    const int gw = s.w >> 2, ng = gw * s.h;
+    int acc = 0;
+    for (int u = s.lane; u < ng; u += 32)
+    {
+        int y = u / gw, x = (u - y * gw) << 2;
+        acc += sad_seg<pixel, 4>(s.fenc + y * 64 + x, r + (int64_t)y * rs + x);
+    }
+    return warp_sum(acc);
+}
+
 // SATD (pixel.cpp:210-297): sum over 4x4 cells of (sum|H d H^T| >> 1); ref anywhere (generic pointer)
 template<typename pixel>
 __device__ __noinline__ int warp_satd(const MEState<pixel>& s, const pixel* r, int64_t rs)
 {
+    if (s.perThread) return thread_satd<pixel>(s, r, rs);
     constexpr int NW = 4 * (int)sizeof(pixel) / 4;
     const int cw = s.w >> 2, nc = cw * (s.h >> 2);
     int acc = 0;
@@ -246,13 +309,14 @@ __device__ __noinline__ void warp_interp_luma(const MEState<pixel>& s, const pix
     constexpr int NW12 = 12 * (int)sizeof(pixel) / 4, NW4 = 4 * (int)sizeof(pixel) / 4;
     const int w = s.w, h = s.h, maxVal = (1 << s.depth) - 1, headRoom = 14 - s.depth;
     const int gw = w >> 2;
+    const int u0 = s.perThread ? 0 : s.lane, du = s.perThread ? 1 : 32;
     int c[8];
     if (!yFrac)
     {
         // luma_hpp : ipfilter.cpp:79-118
 #pragma unroll
         for (int t = 0; t < 8; t++) c[t] = c_meLumaFilter[xFrac][t];
-        for (int u = s.lane; u < gw * h; u += 32)
+        for (int u = u0; u < gw * h; u += du)
         {
             int y = u / gw, x = (u - y * gw) << 2;
             uint32_t rw[NW12]; int v[12], o[4];
@@ -275,7 +339,7 @@ __device__ __noinline__ void warp_interp_luma(const MEState<pixel>& s, const pix
         // luma_vpp : ipfilter.cpp:164-203
 #pragma unroll
         for (int t = 0; t < 8; t++) c[t] = c_meLumaFilter[yFrac][t];
-        for (int u = s.lane; u < gw * h; u += 32)
+        for (int u = u0; u < gw * h; u += du)
         {
             int y = u / gw, x = (u - y * gw) << 2;
             int sum[4] = { 0, 0, 0, 0 }, o[4];
@@ -303,7 +367,7 @@ __device__ __noinline__ void warp_interp_luma(const MEState<pixel>& s, const pix
 #pragma unroll
         for (int t = 0; t < 8; t++) c[t] = c_meLumaFilter[xFrac][t];
         const int shift = 6 - headRoom, offset = (int)((unsigned)-8192 << shift);
-        for (int u = s.lane; u < gw * (h + 7); u += 32)
+        for (int u = u0; u < gw * (h + 7); u += du)
         {
             int y = u / gw, x = (u - y * gw) << 2;
             uint32_t rw[NW12]; int v[12];
@@ -322,11 +386,11 @@ __device__ __noinline__ void warp_interp_luma(const MEState<pixel>& s, const pix
             d[0] = (uint32_t)(o[0] & 0xffff) | ((uint32_t)o[1] << 16);
             d[1] = (uint32_t)(o[2] & 0xffff) | ((uint32_t)o[3] << 16);
         }
-        __syncwarp();
+        if (!s.perThread) __syncwarp();
 #pragma unroll
         for (int t = 0; t < 8; t++) c[t] = c_meLumaFilter[yFrac][t];
         const int shift2 = 6 + headRoom, offset2 = (1 << (shift2 - 1)) + (8192 << 6);
-        for (int u = s.lane; u < gw * h; u += 32)
+        for (int u = u0; u < gw * h; u += du)
         {
             int y = u / gw, x = (u - y * gw) << 2;
             int sum[4] = { 0, 0, 0, 0 }, o[4];
@@ -347,7 +411,7 @@ __device__ __noinline__ void warp_interp_luma(const MEState<pixel>& s, const pix
             store_px4<pixel>(s.pred + y * w + x, o);
         }
     }
-    __syncwarp();
+    if (!s.perThread) __syncwarp();
 }
 
 // MotionEstimate::subpelCompare (motion.cpp:1571-1599); useSatd selects cmp
@@ -358,10 +422,10 @@ __device__ __noinline__ int subpel_compare(const MEState<pixel>& s, int qx, int 
     const int xFrac = qx & 3, yFrac = qy & 3;
     if (!(xFrac | yFrac))
         return useSatd ? warp_satd<pixel>(s, fref, s.stride) : warp_sad_block<pixel>(s, fref, s.stride);
-    __syncwarp();
+    if (!s.perThread) __syncwarp();
     warp_interp_luma<pixel>(s, fref, xFrac, yFrac);
     int c = useSatd ? warp_satd<pixel>(s, s.pred, s.w) : warp_sad_block<pixel>(s, s.pred, s.w);
-    __syncwarp();
+    if (!s.perThread) __syncwarp();
     return c;
 }
 
@@ -665,7 +729,7 @@ __device__ int motion_estimate(const MEState<pixel>& s, MV2 mvmin, MV2 mvmax, MV
     // measure SAD cost at MV(0) if MVP is not zero (:786-796)
     if (pmv.x | pmv.y)
     {
-        int cost = S.sadAt(0, 0) + mvcost(s, 0, 0);
+        int cost = warp_sad_block<pixel>(s, s.gfref, s.gstride) + mvcost(s, 0, 0);
         if (cost < S.bcost)
         {
             S.bcost = cost;

@@ -1,0 +1,252 @@
+// me_frame_kernels.cu -- frame-shaped motion estimation with TMA-staged search windows.
+//
+// One CTA = one (CTU, reference) pair.  The 64x64 source CTU and the reference search window
+// (64 + 2*(merange+8) pixels square, enough for every integer candidate, the hex/square overshoot and the
+// 8-tap sub-pel footprint) are brought into shared memory by two TMA tile loads
+// (cp.async.bulk.tensor.2d, SASS UTMALDG) signalled on an mbarrier; all 85 2Nx2N PU searches of the CTU
+// (64x64, 4x 32x32, 16x 16x16, 64x 8x8) then run out of shared memory, one warp per PU search, with the
+// same warp-cooperative bit-exact device algorithm as me_batch_kernel (me_device.cuh =
+// MotionEstimate::motionEstimate, motion.cpp:739-1569).  The window pitch is 16*k bytes chosen so that 8
+// consecutive rows fall in distinct banks.  PUs are handed out largest-first from shared-memory queues.
+//
+// Per-PU semantics: motionEstimate(ref, mvmin = (mvp>>2) - merange, mvmax = (mvp>>2) + merange, qmvp = mvp,
+// numCandidates = 0, merange, ...) with the CTU's predictor mvp shared by all its PUs (Search::setSearchRange
+// shape, search.cpp:2724-2769, before picture-boundary clipping).
+#include "me_device.cuh"
+#include "x265b200.h"
+#include <cuda.h>
+#include <vector>
+
+namespace x265b200 {
+
+int scratch_dev(Ctx* ctx, int slot, size_t bytes, void** out);
+int ensure_mvcost(Ctx* ctx, double lambda);
+
+struct MEFrameArgs
+{
+    const CUtensorMap* maps;          // [0] = current plane (box 64x64), [1 + r] = reference r (box winW x winH)
+    const void* const* refOrigins;    // device array of plane origins (zero-MV candidate outside the window)
+    int64_t refStride;
+    int ctuCols, ctuRows, numRefs, marginX, marginY;
+    const int32_t* mvpCtu;            // [ref][ctu][2] quarter-pel, or null (= 0)
+    int32_t* out;                     // [ref][level grid][3]
+    int64_t levelOff[4];              // element offset (in PUs) of level 64/32/16/8 inside one reference's block
+    int64_t perRef;                   // PUs per reference
+    int puMask;
+    const uint16_t* cost;
+    int searchMethod, subpelRefine, merange, depth, R, winW, winH;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+constexpr int MF_WARPS = 8;
+
+// scratch (pred + immed) bytes for one search of PUs up to `s` pixels square
+__host__ __device__ inline size_t mf_scratch_bytes(int s, int px)
+{
+    size_t pred = ((size_t)s * s * px + 15) & ~(size_t)15;
+    size_t immed = ((size_t)s * (s + 7) * 2 + 15) & ~(size_t)15;
+    return pred + immed;
+}
+// CTA roles (8 warps): warp 0 = the 64x64 PU (warp-cooperative); warps 1-4 = one 32x32 PU each
+// (warp-cooperative); warp 5 lanes 0-15 = the sixteen 16x16 PUs, ONE THREAD per search; warps 6-7 = the
+// sixty-four 8x8 PUs, one thread per search.  Small PUs have too few pixels to feed 32 lanes, so running the
+// whole bit-exact search per thread removes every shuffle/broadcast and keeps all lanes busy.
+__host__ __device__ inline size_t mf_total_scratch(int px)
+{
+    return mf_scratch_bytes(64, px) + 4 * mf_scratch_bytes(32, px) + 16 * mf_scratch_bytes(16, px) + 64 * mf_scratch_bytes(8, px);
+}
+
+template<typename pixel>
+__global__ void __launch_bounds__(MF_WARPS * 32)
+me_frame_kernel(MEFrameArgs p)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int px = (int)sizeof(pixel);
+    const size_t winBytes = ((size_t)p.winW * p.winH * px + 127) & ~(size_t)127;
+    pixel* window = (pixel*)smem;
+    pixel* fencCtu = (pixel*)(smem + winBytes);
+    unsigned char* scratch = smem + winBytes + 64 * 64 * px;
+    uint64_t* bar = (uint64_t*)(scratch + mf_total_scratch(px));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    const int ctu = blockIdx.x, ref = blockIdx.y;
+    const int ctuX = ctu % p.ctuCols, ctuY = ctu / p.ctuCols;
+    int mvpx = 0, mvpy = 0;
+    if (p.mvpCtu) { const int32_t* m = p.mvpCtu + ((int64_t)ref * p.ctuCols * p.ctuRows + ctu) * 2; mvpx = m[0]; mvpy = m[1]; }
+    const int cx = mvpx >> 2, cy = mvpy >> 2;
+    const int wx0 = ctuX * 64 + cx - p.R, wy0 = ctuY * 64 + cy - p.R;        // picture coordinates of window pixel (0,0)
+
+    if (threadIdx.x == 0)
+    {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        mbar_expect_tx(bar, (uint32_t)((size_t)p.winW * p.winH * px + 64 * 64 * px));
+        tma_load_2d(window, p.maps + 1 + ref, bar, wx0 + p.marginX, wy0 + p.marginY);
+        tma_load_2d(fencCtu, p.maps, bar, ctuX * 64 + p.marginX, ctuY * 64 + p.marginY);
+    }
+    mbar_wait(bar, 0);
+
+    // ---- role ------------------------------------------------------------------------------------------
+    int level, idx; bool perThread; size_t soff;
+    if (warp == 0)      { level = 0; idx = 0; perThread = false; soff = 0; }
+    else if (warp <= 4) { level = 1; idx = warp - 1; perThread = false; soff = mf_scratch_bytes(64, px) + (size_t)(warp - 1) * mf_scratch_bytes(32, px); }
+    else if (warp == 5)
+    {
+        level = 2; idx = lane; perThread = true;
+        soff = mf_scratch_bytes(64, px) + 4 * mf_scratch_bytes(32, px) + (size_t)lane * mf_scratch_bytes(16, px);
+        if (lane >= 16) return;
+    }
+    else
+    {
+        level = 3; idx = (warp - 6) * 32 + lane; perThread = true;
+        soff = mf_scratch_bytes(64, px) + 4 * mf_scratch_bytes(32, px) + 16 * mf_scratch_bytes(16, px) + (size_t)idx * mf_scratch_bytes(8, px);
+    }
+    if (!(p.puMask & (1 << level))) return;
+    const int sz = 64 >> level, per = 1 << level;
+    const int puy = (idx / per) * sz, pux = (idx % per) * sz;
+
+    MEState<pixel> s;
+    s.pred = (pixel*)(scratch + soff);
+    s.immed = (int16_t*)(scratch + soff + (((size_t)sz * sz * px + 15) & ~(size_t)15));
+    s.stride = p.winW; s.isLowres = false; s.perThread = perThread; s.lane = perThread ? 0 : lane; s.depth = p.depth;
+    s.cost = p.cost + 2 * 32768; s.mvpx = mvpx; s.mvpy = mvpy;
+    s.w = sz; s.h = sz; s.partSizeScale = (sz * sz) >> 4;
+    s.fenc = fencCtu + puy * 64 + pux;
+    s.fref = window + (int64_t)(puy - cy + p.R) * p.winW + (pux - cx + p.R);
+    s.gfref = (const pixel*)p.refOrigins[ref] + (ctuX * 64 + pux) + (int64_t)(ctuY * 64 + puy) * p.refStride;
+    s.gstride = p.refStride;
+    int ox, oy;
+    int cost = motion_estimate<pixel>(s, mv2(cx - p.merange, cy - p.merange), mv2(cx + p.merange, cy + p.merange), mv2(mvpx, mvpy),
+                                      0, nullptr, p.merange, p.searchMethod, p.subpelRefine, 1, sz == 64, ox, oy);
+    if (perThread || lane == 0)
+    {
+        const int gx = ctuX * per + pux / sz, gy = ctuY * per + puy / sz;
+        int32_t* o = p.out + ((int64_t)ref * p.perRef + p.levelOff[level] + (int64_t)gy * (p.ctuCols * per) + gx) * 3;
+        o[0] = ox; o[1] = oy; o[2] = cost;
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn)
+    {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+static int encode_plane(CUtensorMap* m, int depth, const void* origin, int64_t stride, int marginX, int marginY, int rowsTotal, int boxW, int boxH)
+{
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("me_frame: cuTensorMapEncodeTiled not available from the driver"); return -1; }
+    const int px = depth > 8 ? 2 : 1;
+    const char* base = (const char*)origin - ((int64_t)marginY * stride + marginX) * px;
+    if (((uintptr_t)base & 15) || ((stride * px) & 15)) { set_error("me_frame: plane base / stride must be 16-byte aligned for TMA"); return -1; }
+    cuuint64_t gdim[2] = { (cuuint64_t)stride, (cuuint64_t)rowsTotal };
+    cuuint64_t gstr[1] = { (cuuint64_t)stride * px };
+    cuuint32_t box[2] = { (cuuint32_t)boxW, (cuuint32_t)boxH };
+    cuuint32_t estr[2] = { 1, 1 };
+    CUresult r = enc(m, depth > 8 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)base, gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("me_frame: cuTensorMapEncodeTiled failed (%d)", (int)r); return -1; }
+    return 0;
+}
+
+int me_frame_dev(Ctx* ctx, int depth, const void* curOrigin, int64_t curStride, const void* const* refOriginsHost, int numRefs, int64_t refStride,
+                 int marginX, int marginY, int rowsTotal, int ctuCols, int ctuRows, int puMask, const int32_t* mvpCtu,
+                 int searchMethod, int subpelRefine, int merange, double lambda, int32_t* out)
+{
+    if (numRefs <= 0 || ctuCols <= 0 || ctuRows <= 0) return 0;
+    if (searchMethod == ME_SEA || searchMethod < 0 || searchMethod > ME_FULL) { set_error("me_frame: searchMethod %d unsupported", searchMethod); return -1; }
+    if (subpelRefine < 0 || subpelRefine > 7) { set_error("me_frame: subpelRefine %d", subpelRefine); return -1; }
+    const int px = depth > 8 ? 2 : 1;
+    const int R = merange + 8;
+    int winW = 64 + 2 * R;
+    // pitch: a multiple of 16 bytes whose word count is 4 mod 8 -> 8 consecutive rows hit distinct bank groups
+    int pitchBytes = ((winW * px + 15) / 16) * 16;
+    while (((pitchBytes / 4) % 8) != 4) pitchBytes += 16;
+    winW = pitchBytes / px;
+    const int winH = 64 + 2 * R;
+    if (winW > 256 || winH > 256) { set_error("me_frame: merange %d needs a %dx%d window, above the 256-element TMA box limit; use x265b200_me_batch_dev", merange, winW, winH); return -1; }
+    if (marginX < R + 8 || marginY < R) { set_error("me_frame: plane margins (%d,%d) smaller than the search window reach %d", marginX, marginY, R); return -1; }
+    if (ensure_mvcost(ctx, lambda)) return -1;
+
+    std::vector<CUtensorMap> maps(numRefs + 1);
+    if (encode_plane(&maps[0], depth, curOrigin, curStride, marginX, marginY, rowsTotal, 64, 64)) return -1;
+    for (int r = 0; r < numRefs; r++)
+        if (encode_plane(&maps[1 + r], depth, refOriginsHost[r], refStride, marginX, marginY, rowsTotal, winW, winH)) return -1;
+    void* dScr = nullptr;
+    size_t mapBytes = sizeof(CUtensorMap) * maps.size(), ptrBytes = sizeof(void*) * numRefs;
+    if (scratch_dev(ctx, 5, mapBytes + ptrBytes + 64, &dScr)) return -1;
+    X265B200_CHECK(cudaMemcpyAsync(dScr, maps.data(), mapBytes, cudaMemcpyHostToDevice, ctx->stream));
+    X265B200_CHECK(cudaMemcpyAsync((char*)dScr + mapBytes, refOriginsHost, ptrBytes, cudaMemcpyHostToDevice, ctx->stream));
+    X265B200_CHECK(cudaStreamSynchronize(ctx->stream));      // `maps` is a host temporary
+
+    MEFrameArgs a;
+    a.maps = (const CUtensorMap*)dScr; a.refOrigins = (const void* const*)((char*)dScr + mapBytes); a.refStride = refStride;
+    a.ctuCols = ctuCols; a.ctuRows = ctuRows; a.numRefs = numRefs; a.marginX = marginX; a.marginY = marginY;
+    a.mvpCtu = mvpCtu; a.out = out; a.puMask = puMask; a.cost = ctx->dMvCost;
+    a.searchMethod = searchMethod; a.subpelRefine = subpelRefine; a.merange = merange; a.depth = depth; a.R = R; a.winW = winW; a.winH = winH;
+    int64_t off = 0;
+    for (int l = 0; l < 4; l++)
+    {
+        a.levelOff[l] = off;
+        if (puMask & (1 << l)) off += (int64_t)ctuCols * ctuRows * (1 << l) * (1 << l);
+    }
+    a.perRef = off;
+    size_t smem = (((size_t)winW * winH * px + 127) & ~(size_t)127) + (size_t)64 * 64 * px + mf_total_scratch(px) + 16;
+    dim3 grid(ctuCols * ctuRows, numRefs);
+    if (depth > 8)
+    {
+        X265B200_CHECK(cudaFuncSetAttribute(me_frame_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        me_frame_kernel<uint16_t><<<grid, MF_WARPS * 32, smem, ctx->stream>>>(a);
+    }
+    else
+    {
+        X265B200_CHECK(cudaFuncSetAttribute(me_frame_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        me_frame_kernel<uint8_t><<<grid, MF_WARPS * 32, smem, ctx->stream>>>(a);
+    }
+    ctx->launches++;
+    return check(cudaGetLastError(), "me_frame kernel launch");
+}
+
+} // namespace x265b200

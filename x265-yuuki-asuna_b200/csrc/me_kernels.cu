@@ -88,7 +88,8 @@ me_batch_kernel(MEArgs p)
     s.stride = p.refStride;
     const pixel* refPlane = (const pixel*)(p.refPlanes ? p.refPlanes[job.refIdx] : p.refPlane0);
     s.fref = refPlane + job.puX + (int64_t)job.puY * p.refStride;
-    s.isLowres = false;
+    s.gfref = s.fref; s.gstride = p.refStride;
+    s.isLowres = false; s.perThread = false;
     s.w = job.w; s.h = job.h; s.lane = lane; s.depth = p.depth;
     s.partSizeScale = (job.h * job.h) >> 4;                      // motion.cpp:125-126 sizeScale
     s.cost = p.cost + 2 * 32768;
