@@ -139,22 +139,26 @@ def test_sad_pyramid_matches_per_level_sad(ctx, with_mv):
     W, H = ctuCols * 64, ctuRows * 64
     S = W + 2 * pad + 16 - (W + 2 * pad) % 16
     cur = rng.integers(0, 256, (H + 2 * pad) * S, dtype=np.int64).astype(np.uint8)
-    ref = rng.integers(0, 256, (H + 2 * pad) * S, dtype=np.int64).astype(np.uint8)
+    NREF = 2
+    refs = [rng.integers(0, 256, (H + 2 * pad) * S, dtype=np.int64).astype(np.uint8) for _ in range(NREF)]
     base = pad * S + 48
-    mv = rng.integers(-20, 21, (ctuRows * ctuCols, 2), dtype=np.int64).astype(np.int16) if with_mv else None
-    dC, dR = ctx.to_device(cur), ctx.to_device(ref)
+    mv = rng.integers(-20, 21, (NREF, ctuRows * ctuCols, 2), dtype=np.int64).astype(np.int16) if with_mv else None
+    dC = ctx.to_device(cur)
+    dR = [ctx.to_device(r) for r in refs]
+    dPtrs = ctx.to_device(np.array([d.ptr + base for d in dR], dtype=np.int64))
     dMv = ctx.to_device(mv) if with_mv else None
-    outs = {s: ctx.empty((W // s) * (H // s) * 4) for s in (8, 16, 32, 64)}
-    ctx.sad_pyramid_dev(8, dC.ptr + base, S, dR.ptr + base, S, ctuCols, ctuRows, dMv, outs[8], outs[16], outs[32], outs[64])
+    outs = {s: ctx.empty(NREF * (W // s) * (H // s) * 4) for s in (8, 16, 32, 64)}
+    ctx.sad_pyramid_dev(8, dC.ptr + base, S, dPtrs, NREF, S, ctuCols, ctuRows, dMv, outs[8], outs[16], outs[32], outs[64])
     for s in (8, 16, 32, 64):
-        got = outs[s].download(np.int32)
+        got = outs[s].download(np.int32).reshape(NREF, -1)
         cols = W // s
-        offA, offB = [], []
-        for i in range(cols * (H // s)):
-            bx, by = i % cols, i // cols
-            ctu = (by * s // 64) * ctuCols + (bx * s // 64)
-            mx, my = (int(mv[ctu][0]), int(mv[ctu][1])) if with_mv else (0, 0)
-            offA.append(base + by * s * S + bx * s)
-            offB.append(base + (by * s + my) * S + bx * s + mx)
-        exp = orc_cmp("sad", 8, s, s, cur, S, ref, S, np.array(offA), np.array(offB))
-        assert list(map(int, got)) == exp, (s, with_mv)
+        for r in range(NREF):
+            offA, offB = [], []
+            for i in range(cols * (H // s)):
+                bx, by = i % cols, i // cols
+                ctu = (by * s // 64) * ctuCols + (bx * s // 64)
+                mx, my = (int(mv[r][ctu][0]), int(mv[r][ctu][1])) if with_mv else (0, 0)
+                offA.append(base + by * s * S + bx * s)
+                offB.append(base + (by * s + my) * S + bx * s + mx)
+            exp = orc_cmp("sad", 8, s, s, cur, S, refs[r], S, np.array(offA), np.array(offB))
+            assert list(map(int, got[r])) == exp, (s, with_mv, r)

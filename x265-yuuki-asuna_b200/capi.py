@@ -316,8 +316,8 @@ Ctx.la_intra_dev = _ctx_la_intra_dev
 Ctx.la_estimate_dev = _ctx_la_estimate_dev
 
 
-def _ctx_sad_pyramid_dev(self, depth, dCur, strideCur, dRef, strideRef, ctuCols, ctuRows, dMvCtu, dOut8, dOut16, dOut32, dOut64):
-    self._chk(self.L.x265b200_sad_pyramid_dev(self.h, depth, _vp(dCur), _i64(strideCur), _vp(dRef), _i64(strideRef), int(ctuCols), int(ctuRows),
+def _ctx_sad_pyramid_dev(self, depth, dCur, strideCur, dRefPtrs, numRefs, strideRef, ctuCols, ctuRows, dMvCtu, dOut8, dOut16, dOut32, dOut64):
+    self._chk(self.L.x265b200_sad_pyramid_dev(self.h, depth, _vp(dCur), _i64(strideCur), _vp(dRefPtrs), int(numRefs), _i64(strideRef), int(ctuCols), int(ctuRows),
                                               _vp(dMvCtu), _vp(dOut8), _vp(dOut16), _vp(dOut32), _vp(dOut64)))
 
 

@@ -66,7 +66,7 @@ int stage_in(Ctx* ctx, int slot, const void* host, size_t bytes, void** dev)
 // forward declarations of launchers -----------------------------------------------------------
 int pixelcmp_dev(Ctx*, int kind, int depth, int w, int h, const void* A, int64_t strideA, const void* B, int64_t strideB,
                  const int64_t* offA, const int64_t* offB, const int16_t* mv, int gridCols, int64_t n, void* out);
-int sad_pyramid_dev(Ctx*, int depth, const void* cur, int64_t strideC, const void* ref, int64_t strideR, int ctuCols, int ctuRows,
+int sad_pyramid_dev(Ctx*, int depth, const void* cur, int64_t strideC, const void* const* refs, int numRefs, int64_t strideR, int ctuCols, int ctuRows,
                     const int16_t* mvCtu, int32_t* out8, int32_t* out16, int32_t* out32, int32_t* out64);
 int sad_xn_dev(Ctx*, int depth, int K, int w, int h, const void* fenc, int64_t fencBlockStride,
                const void* ref, int64_t refStride, const int64_t* refOff, int64_t n, int32_t* res);
@@ -230,11 +230,11 @@ int x265b200_pixelcmp_host(x265b200_ctx* ctx, int kind, int depth, int w, int h,
     return 0;
 }
 
-int x265b200_sad_pyramid_dev(x265b200_ctx* ctx, int depth, const void* cur, int64_t strideCur, const void* ref, int64_t strideRef,
+int x265b200_sad_pyramid_dev(x265b200_ctx* ctx, int depth, const void* cur, int64_t strideCur, const void* const* refsDev, int numRefs, int64_t strideRef,
                              int ctuCols, int ctuRows, const int16_t* mvCtu, int32_t* out8, int32_t* out16, int32_t* out32, int32_t* out64)
 {
     REQUIRE_CTX(ctx);
-    return sad_pyramid_dev(CTX(ctx), depth, cur, strideCur, ref, strideRef, ctuCols, ctuRows, mvCtu, out8, out16, out32, out64);
+    return sad_pyramid_dev(CTX(ctx), depth, cur, strideCur, refsDev, numRefs, strideRef, ctuCols, ctuRows, mvCtu, out8, out16, out32, out64);
 }
 
 int x265b200_sad_xn_dev(x265b200_ctx* ctx, int depth, int K, int w, int h, const void* fenc, int64_t fencBlockStride,

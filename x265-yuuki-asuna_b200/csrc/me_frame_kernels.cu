@@ -16,15 +16,23 @@
 #include "x265b200.h"
 #include <cuda.h>
 #include <vector>
+#include <cstring>
 
 namespace x265b200 {
 
 int scratch_dev(Ctx* ctx, int slot, size_t bytes, void** out);
 int ensure_mvcost(Ctx* ctx, double lambda);
 
+constexpr int MF_MAX_REFS = 6;
+// TMA descriptors travel as a __grid_constant__ kernel parameter (the canonical, fence-free way)
+struct alignas(64) MEFrameMaps
+{
+    CUtensorMap cur;                  // current plane, box 64x64
+    CUtensorMap ref[MF_MAX_REFS];     // reference planes, box winW x winH
+};
+
 struct MEFrameArgs
 {
-    const CUtensorMap* maps;          // [0] = current plane (box 64x64), [1 + r] = reference r (box winW x winH)
     const void* const* refOrigins;    // device array of plane origins (zero-MV candidate outside the window)
     int64_t refStride;
     int ctuCols, ctuRows, numRefs, marginX, marginY;
@@ -85,7 +93,7 @@ __host__ __device__ inline size_t mf_total_scratch(int px)
 
 template<typename pixel>
 __global__ void __launch_bounds__(MF_WARPS * 32)
-me_frame_kernel(MEFrameArgs p)
+me_frame_kernel(const __grid_constant__ MEFrameMaps maps, MEFrameArgs p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const int px = (int)sizeof(pixel);
@@ -112,8 +120,8 @@ me_frame_kernel(MEFrameArgs p)
     if (threadIdx.x == 0)
     {
         mbar_expect_tx(bar, (uint32_t)((size_t)p.winW * p.winH * px + 64 * 64 * px));
-        tma_load_2d(window, p.maps + 1 + ref, bar, wx0 + p.marginX, wy0 + p.marginY);
-        tma_load_2d(fencCtu, p.maps, bar, ctuX * 64 + p.marginX, ctuY * 64 + p.marginY);
+        tma_load_2d(window, &maps.ref[ref], bar, wx0 + p.marginX, wy0 + p.marginY);
+        tma_load_2d(fencCtu, &maps.cur, bar, ctuX * 64 + p.marginX, ctuY * 64 + p.marginY);
     }
     mbar_wait(bar, 0);
 
@@ -210,19 +218,19 @@ int me_frame_dev(Ctx* ctx, int depth, const void* curOrigin, int64_t curStride, 
     if (marginX < R + 8 || marginY < R) { set_error("me_frame: plane margins (%d,%d) smaller than the search window reach %d", marginX, marginY, R); return -1; }
     if (ensure_mvcost(ctx, lambda)) return -1;
 
-    std::vector<CUtensorMap> maps(numRefs + 1);
-    if (encode_plane(&maps[0], depth, curOrigin, curStride, marginX, marginY, rowsTotal, 64, 64)) return -1;
+    if (numRefs > MF_MAX_REFS) { set_error("me_frame: at most %d references per call", MF_MAX_REFS); return -1; }
+    MEFrameMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    if (encode_plane(&maps.cur, depth, curOrigin, curStride, marginX, marginY, rowsTotal, 64, 64)) return -1;
     for (int r = 0; r < numRefs; r++)
-        if (encode_plane(&maps[1 + r], depth, refOriginsHost[r], refStride, marginX, marginY, rowsTotal, winW, winH)) return -1;
+        if (encode_plane(&maps.ref[r], depth, refOriginsHost[r], refStride, marginX, marginY, rowsTotal, winW, winH)) return -1;
     void* dScr = nullptr;
-    size_t mapBytes = sizeof(CUtensorMap) * maps.size(), ptrBytes = sizeof(void*) * numRefs;
-    if (scratch_dev(ctx, 5, mapBytes + ptrBytes + 64, &dScr)) return -1;
-    X265B200_CHECK(cudaMemcpyAsync(dScr, maps.data(), mapBytes, cudaMemcpyHostToDevice, ctx->stream));
-    X265B200_CHECK(cudaMemcpyAsync((char*)dScr + mapBytes, refOriginsHost, ptrBytes, cudaMemcpyHostToDevice, ctx->stream));
-    X265B200_CHECK(cudaStreamSynchronize(ctx->stream));      // `maps` is a host temporary
+    size_t ptrBytes = sizeof(void*) * numRefs;
+    if (scratch_dev(ctx, 5, ptrBytes + 64, &dScr)) return -1;
+    X265B200_CHECK(cudaMemcpyAsync(dScr, refOriginsHost, ptrBytes, cudaMemcpyHostToDevice, ctx->stream));
 
     MEFrameArgs a;
-    a.maps = (const CUtensorMap*)dScr; a.refOrigins = (const void* const*)((char*)dScr + mapBytes); a.refStride = refStride;
+    a.refOrigins = (const void* const*)dScr; a.refStride = refStride;
     a.ctuCols = ctuCols; a.ctuRows = ctuRows; a.numRefs = numRefs; a.marginX = marginX; a.marginY = marginY;
     a.mvpCtu = mvpCtu; a.out = out; a.puMask = puMask; a.cost = ctx->dMvCost;
     a.searchMethod = searchMethod; a.subpelRefine = subpelRefine; a.merange = merange; a.depth = depth; a.R = R; a.winW = winW; a.winH = winH;
@@ -238,12 +246,12 @@ int me_frame_dev(Ctx* ctx, int depth, const void* curOrigin, int64_t curStride, 
     if (depth > 8)
     {
         X265B200_CHECK(cudaFuncSetAttribute(me_frame_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        me_frame_kernel<uint16_t><<<grid, MF_WARPS * 32, smem, ctx->stream>>>(a);
+        me_frame_kernel<uint16_t><<<grid, MF_WARPS * 32, smem, ctx->stream>>>(maps, a);
     }
     else
     {
         X265B200_CHECK(cudaFuncSetAttribute(me_frame_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        me_frame_kernel<uint8_t><<<grid, MF_WARPS * 32, smem, ctx->stream>>>(a);
+        me_frame_kernel<uint8_t><<<grid, MF_WARPS * 32, smem, ctx->stream>>>(maps, a);
     }
     ctx->launches++;
     return check(cudaGetLastError(), "me_frame kernel launch");

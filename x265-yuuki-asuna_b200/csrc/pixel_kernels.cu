@@ -405,7 +405,8 @@ int add_ps_plane_dev(Ctx* ctx, int depth, void* dst, int64_t dstStride, const vo
 // SAD pyramid: ONE streaming pass over a frame pair produces the SADs of every 8x8, 16x16, 32x32 and
 // 64x64 2Nx2N PU of every CTU (the "cost at the predictor" step of motionEstimate, motion.cpp:771-784,
 // for all PU levels at once; sad<lx,ly> of pixel.cpp:40-55 is additive over sub-blocks).  Each plane
-// byte is fetched exactly once with 128-bit loads; per-CTU full-pel displacement optional.
+// byte is fetched exactly once with 128-bit loads; per-CTU full-pel displacement optional; all references of a
+// frame are processed by one launch (grid.y = reference).
 // Mapping: one warp = 64 rows x 128 px (two CTUs); lane = rsub*8 + col owns a 16x16 block
 // (col: 16-px column, rsub: 16-row band); 32x32 / 64x64 sums are warp-shuffle reductions.
 // Algorithmic bytes per launch: 2*W*H + 4*(n8 + n16 + n32 + n64).
@@ -423,10 +424,17 @@ __device__ __forceinline__ uint4 ld16_any(const uint8_t* p)
 }
 
 __global__ void __launch_bounds__(256)
-sad_pyramid_kernel(const uint8_t* __restrict__ cur, int64_t strideC, const uint8_t* __restrict__ ref, int64_t strideR,
+sad_pyramid_kernel(const uint8_t* __restrict__ cur, int64_t strideC, const uint8_t* const* __restrict__ refs, int64_t strideR,
                    int ctuCols, int ctuRows, const int16_t* __restrict__ mvCtu,
                    int32_t* __restrict__ out8, int32_t* __restrict__ out16, int32_t* __restrict__ out32, int32_t* __restrict__ out64)
 {
+    // blockIdx.y = reference index: all references of a frame in ONE launch (the source CTU rows are shared in L2)
+    const uint8_t* __restrict__ ref = refs[blockIdx.y];
+    {
+        const int64_t nctu = (int64_t)ctuCols * ctuRows;
+        out8 += blockIdx.y * nctu * 64; out16 += blockIdx.y * nctu * 16; out32 += blockIdx.y * nctu * 4; out64 += blockIdx.y * nctu;
+        if (mvCtu) mvCtu += blockIdx.y * nctu * 2;
+    }
     const int lane = threadIdx.x & 31;
     const int pairsPerRow = (ctuCols + 1) >> 1;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -474,16 +482,16 @@ sad_pyramid_kernel(const uint8_t* __restrict__ cur, int64_t strideC, const uint8
     if (valid && !(lane & 3) && !(lane & 24)) out64[(int64_t)ctuY * ctuCols + ctuX] = s64;
 }
 
-int sad_pyramid_dev(Ctx* ctx, int depth, const void* cur, int64_t strideC, const void* ref, int64_t strideR, int ctuCols, int ctuRows,
+int sad_pyramid_dev(Ctx* ctx, int depth, const void* cur, int64_t strideC, const void* const* refs, int numRefs, int64_t strideR, int ctuCols, int ctuRows,
                     const int16_t* mvCtu, int32_t* out8, int32_t* out16, int32_t* out32, int32_t* out64)
 {
     if (depth != 8) { set_error("sad_pyramid: 8-bit planes only (use pixelcmp grid mode for high bit depth)"); return -1; }
     if (((uintptr_t)cur & 15) || (strideC & 15)) { set_error("sad_pyramid: cur plane and stride must be 16-byte aligned"); return -1; }
     if (((uintptr_t)out8 & 7)) { set_error("sad_pyramid: out8 must be 8-byte aligned"); return -1; }
     int64_t warps = (int64_t)((ctuCols + 1) / 2) * ctuRows;
-    if (warps <= 0) return 0;
-    unsigned blocks = (unsigned)((warps * 32 + 255) / 256);
-    sad_pyramid_kernel<<<blocks, 256, 0, ctx->stream>>>((const uint8_t*)cur, strideC, (const uint8_t*)ref, strideR, ctuCols, ctuRows, mvCtu, out8, out16, out32, out64);
+    if (warps <= 0 || numRefs <= 0) return 0;
+    dim3 grid((unsigned)((warps * 32 + 255) / 256), (unsigned)numRefs);
+    sad_pyramid_kernel<<<grid, 256, 0, ctx->stream>>>((const uint8_t*)cur, strideC, (const uint8_t* const*)refs, strideR, ctuCols, ctuRows, mvCtu, out8, out16, out32, out64);
     ctx->launches++;
     return check(cudaGetLastError(), "sad_pyramid launch");
 }

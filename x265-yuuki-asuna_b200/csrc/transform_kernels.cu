@@ -26,12 +26,39 @@
 namespace x265b200 {
 
 __constant__ int c_dctMag[33];
+// per-lane mma A fragments: [forward/inverse][N = 32, 16, 8][lane][8 regs]
+__device__ uint32_t g_xfFrag[2][3][32][8];
 static bool g_tablesUploaded[16] = { false };
 
 static int upload_tables(Ctx* ctx)
 {
     if (ctx->device < 16 && g_tablesUploaded[ctx->device]) return 0;
     X265B200_CHECK(cudaMemcpyToSymbolAsync(c_dctMag, kDctMag, sizeof(kDctMag), 0, cudaMemcpyHostToDevice, ctx->stream));
+    static uint32_t frag[2][3][32][8];
+    auto pk = [](int a, int b, int c, int d) { return (uint32_t)(a & 0xff) | ((uint32_t)(b & 0xff) << 8) | ((uint32_t)(c & 0xff) << 16) | ((uint32_t)(d & 0xff) << 24); };
+    for (int inv = 0; inv < 2; inv++)
+        for (int lane = 0; lane < 32; lane++)
+        {
+            const int gid = lane >> 2, tig = lane & 3;
+            auto M = [&](int N, int k, int n) { return inv ? dct_coef(N, n, k) : dct_coef(N, k, n); };
+            for (int mi = 0; mi < 2; mi++)
+                for (int r = 0; r < 4; r++)
+                {
+                    int row = 16 * mi + gid + ((r & 1) ? 8 : 0), k0 = 4 * tig + ((r & 2) ? 16 : 0);
+                    frag[inv][0][lane][mi * 4 + r] = pk(M(32, row, k0), M(32, row, k0 + 1), M(32, row, k0 + 2), M(32, row, k0 + 3));
+                }
+            for (int r = 0; r < 2; r++)
+            {
+                int row = gid + 8 * r, k0 = 4 * tig;
+                frag[inv][1][lane][r] = pk(M(16, row, k0), M(16, row, k0 + 1), M(16, row, k0 + 2), M(16, row, k0 + 3));
+            }
+            int k0 = 4 * (tig & 1);
+            uint32_t v = pk(M(8, gid, k0), M(8, gid, k0 + 1), M(8, gid, k0 + 2), M(8, gid, k0 + 3));
+            frag[inv][2][lane][0] = tig < 2 ? v : 0u;        // rows 0-7 see k 0-7
+            frag[inv][2][lane][1] = tig >= 2 ? v : 0u;       // rows 8-15 see k 8-15
+            for (int r = 2; r < 8; r++) { frag[inv][1][lane][r] = 0; frag[inv][2][lane][r] = 0; }
+        }
+    X265B200_CHECK(cudaMemcpyToSymbolAsync(g_xfFrag, frag, sizeof(frag), 0, cudaMemcpyHostToDevice, ctx->stream));
     if (ctx->device < 16) g_tablesUploaded[ctx->device] = true;
     return 0;
 }
@@ -183,34 +210,20 @@ xform_mma_kernel(XformArgs p)
     int16_t* bufA = smem[warp][0];
     int16_t* bufB = smem[warp][1];
 
-    // A fragments (coefficient matrix) live in registers for the whole kernel
+    // A fragments (coefficient matrix) live in registers for the whole kernel; they come from a per-lane table
+    // built once on the host (g_xfFrag) -- computing them in-kernel from __constant__ memory with divergent
+    // indices saturated the constant-cache address unit (ncu: ADU 87%).
     uint32_t a32[2][4]; uint32_t a16[2];
-    if (N == 32)
     {
-#pragma unroll
-        for (int mi = 0; mi < 2; mi++)
-#pragma unroll
-            for (int r = 0; r < 4; r++)
-            {
-                int row = 16 * mi + gid + ((r & 1) ? 8 : 0), k0 = 4 * tig + ((r & 2) ? 16 : 0);
-                a32[mi][r] = pack4(mcoef(32, INVERSE, row, k0), mcoef(32, INVERSE, row, k0 + 1), mcoef(32, INVERSE, row, k0 + 2), mcoef(32, INVERSE, row, k0 + 3));
-            }
-    }
-    else if (N == 16)
-    {
-#pragma unroll
-        for (int r = 0; r < 2; r++)
+        const uint32_t* f = g_xfFrag[INVERSE ? 1 : 0][N == 32 ? 0 : (N == 16 ? 1 : 2)][lane];
+        if (N == 32)
         {
-            int row = gid + 8 * r, k0 = 4 * tig;
-            a16[r] = pack4(mcoef(16, INVERSE, row, k0), mcoef(16, INVERSE, row, k0 + 1), mcoef(16, INVERSE, row, k0 + 2), mcoef(16, INVERSE, row, k0 + 3));
+#pragma unroll
+            for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+                for (int r = 0; r < 4; r++) a32[mi][r] = f[mi * 4 + r];
         }
-    }
-    else
-    {
-        int k0 = 4 * (tig & 1);
-        uint32_t v = pack4(mcoef(8, INVERSE, gid, k0), mcoef(8, INVERSE, gid, k0 + 1), mcoef(8, INVERSE, gid, k0 + 2), mcoef(8, INVERSE, gid, k0 + 3));
-        a16[0] = (tig < 2) ? v : 0u;      // rows 0-7 see k 0-7
-        a16[1] = (tig >= 2) ? v : 0u;     // rows 8-15 see k 8-15
+        else { a16[0] = f[0]; a16[1] = f[1]; }
     }
 
     const int add1 = 1 << (p.shift1 - 1), add2 = 1 << (p.shift2 - 1);
@@ -226,6 +239,17 @@ xform_mma_kernel(XformArgs p)
             if (b < p.n)
             {
                 const int16_t* sp = p.src + xf_src_off(p, b);
+                if (!INVERSE && N >= 16 && !(((uintptr_t)sp | (uintptr_t)(p.srcStride * 2)) & 15))
+                {
+                    // 128-bit coalesced rows: N/8 lanes per row
+                    constexpr int LPR = N / 8;
+                    for (int e = lane; e < N * LPR; e += 32)
+                    {
+                        int row = e / LPR, c8 = (e % LPR) * 8;
+                        *(uint4*)(tile + row * LD + c8) = __ldg((const uint4*)(sp + (int64_t)row * p.srcStride + c8));
+                    }
+                }
+                else
                 for (int e = lane; e < N * N / 2; e += 32)
                 {
                     int row = (2 * e) / N, col = (2 * e) % N;
@@ -250,11 +274,21 @@ xform_mma_kernel(XformArgs p)
             if (b >= p.n) continue;
             const int16_t* tile = bufA + s * N * LD;
             int16_t* dp = p.dst + xf_dst_off(p, b);
-            if (!INVERSE)
+            if (!INVERSE && N >= 16 && !((uintptr_t)dp & 15))
+            {
+                constexpr int LPR = N / 8;
+                for (int e = lane; e < N * LPR; e += 32)
+                {
+                    int row = e / LPR, c8 = (e % LPR) * 8;
+                    *(uint4*)(dp + row * N + c8) = *(const uint4*)(tile + row * LD + c8);
+                }
+            }
+            else if (!INVERSE)
                 for (int e = lane; e < N * N / 2; e += 32)
                 {
                     int row = (2 * e) / N, col = (2 * e) % N;
-                    *(uint32_t*)(dp + row * N + col) = *(const uint32_t*)(tile + row * LD + col);
+                    if ((uintptr_t)dp & 3) { dp[row * N + col] = tile[row * LD + col]; dp[row * N + col + 1] = tile[row * LD + col + 1]; }
+                    else *(uint32_t*)(dp + row * N + col) = *(const uint32_t*)(tile + row * LD + col);
                 }
             else
                 for (int e = lane; e < N * N; e += 32)
