@@ -192,3 +192,276 @@ uint64_t orc_ssd_s(int depth, int size, const int16_t* a, intptr_t sa)
             sum += (uint64_t)(int64_t)(a[y * sa + x] * a[y * sa + x]);
     return depth < 10 ? (sum & 0xffffffffull) : sum;
 }
+
+/* =====================================================================================================
+ * Transforms.  common/dct.cpp:83-240,418-440 (partialButterfly*) compute, for each input row j,
+ *   dst[k*line + j] = (sum_n g_tN[k][n] * src[j*N + n] + add) >> shift
+ * through an even/odd factorisation; the factorisation is exact, so the dense sum below is the same
+ * integer.  Forward results are truncated to int16 (dct.cpp:113), inverse results saturate (dct.cpp:257).
+ * The matrices g_t4..g_t32 (common/constants.cpp:270-344) are regenerated from the 33 HEVC cosine
+ * magnitudes; tests/test_tables_cpu.py pins them against the reference's tables.
+ * ===================================================================================================== */
+static const int dct_mag[33] = { 64, 90, 90, 90, 89, 88, 87, 85, 83, 82, 80, 78, 75, 73, 70, 67, 64,
+                                 61, 57, 54, 50, 46, 43, 38, 36, 31, 25, 22, 18, 13, 9, 4, 0 };
+static int dct_coef(int N, int k, int n)
+{
+    int m = ((2 * n + 1) * k * (32 / N)) % 128;
+    if (m > 64) m = 128 - m;
+    return m > 32 ? -dct_mag[64 - m] : dct_mag[m];
+}
+static const int dst4_mat[4][4] = { { 29, 55, 74, 84 }, { 74, 74, 0, -74 }, { 84, -29, -74, 55 }, { 55, -84, 74, -29 } };   /* dct.cpp:43-61 expanded */
+
+static int clip16(int v) { return v < -32768 ? -32768 : (v > 32767 ? 32767 : v); }
+
+/* one forward pass: out[k*N + j] = (int16)((sum_n M[k][n] * in[j*N + n] + add) >> shift) */
+static void fwd_pass(int N, int isDst, const int16_t* in, int16_t* out, int shift)
+{
+    int add = 1 << (shift - 1);
+    for (int j = 0; j < N; j++)
+        for (int k = 0; k < N; k++)
+        {
+            int sum = 0;
+            for (int n = 0; n < N; n++)
+                sum += (isDst ? dst4_mat[k][n] : dct_coef(N, k, n)) * in[j * N + n];
+            out[k * N + j] = (int16_t)((sum + add) >> shift);
+        }
+}
+/* one inverse pass (dct.cpp:242-416, :63-81): out[j*N + k] = clip16((sum_n M[n][k] * in[n*N + j] + add) >> shift) */
+static void inv_pass(int N, int isDst, const int16_t* in, int16_t* out, int shift)
+{
+    int add = 1 << (shift - 1);
+    for (int j = 0; j < N; j++)
+        for (int k = 0; k < N; k++)
+        {
+            int sum = 0;
+            for (int n = 0; n < N; n++)
+                sum += (isDst ? dst4_mat[n][k] : dct_coef(N, n, k)) * in[n * N + j];
+            out[j * N + k] = (int16_t)clip16((sum + add) >> shift);
+        }
+}
+
+void orc_dct(int depth, int idx, const int16_t* src, int16_t* dst, intptr_t srcStride)
+{
+    int N = idx == 4 ? 4 : (4 << idx), log2N = idx == 4 ? 2 : idx + 2;
+    int16_t block[32 * 32], coef[32 * 32];
+    for (int i = 0; i < N; i++) memcpy(block + i * N, src + i * srcStride, N * sizeof(int16_t));
+    fwd_pass(N, idx == 4, block, coef, log2N - 1 + (depth - 8));      /* dct.cpp:444,461,478,495,512 shift_1st */
+    fwd_pass(N, idx == 4, coef, dst, log2N + 6);                      /* shift_2nd */
+}
+
+void orc_idct(int depth, int idx, const int16_t* src, int16_t* dst, intptr_t dstStride)
+{
+    int N = idx == 4 ? 4 : (4 << idx);
+    int16_t coef[32 * 32], block[32 * 32];
+    inv_pass(N, idx == 4, src, coef, 7);                              /* dct.cpp:529-530 */
+    inv_pass(N, idx == 4, coef, block, 12 - (depth - 8));
+    for (int i = 0; i < N; i++) memcpy(dst + i * dstStride, block + i * N, N * sizeof(int16_t));
+}
+
+/* dct.cpp:664-686 */
+uint32_t orc_quant(const int16_t* coef, const int32_t* quantCoeff, int32_t* deltaU, int16_t* qCoef, int qBits, int add, int numCoeff)
+{
+    uint32_t numSig = 0;
+    for (int i = 0; i < numCoeff; i++)
+    {
+        int level = coef[i], sign = level < 0 ? -1 : 1;
+        int tmplevel = (int)((uint32_t)abs(level) * (uint32_t)quantCoeff[i]);
+        level = (tmplevel + add) >> qBits;
+        deltaU[i] = (tmplevel - (level << qBits)) >> (qBits - 8);
+        if (level) numSig++;
+        level *= sign;
+        qCoef[i] = (int16_t)clip16(level);
+    }
+    return numSig;
+}
+/* dct.cpp:688-713 */
+uint32_t orc_nquant(const int16_t* coef, const int32_t* quantCoeff, int16_t* qCoef, int qBits, int add, int numCoeff)
+{
+    uint32_t numSig = 0;
+    for (int i = 0; i < numCoeff; i++)
+    {
+        int level = coef[i], sign = level < 0 ? -1 : 1;
+        int tmplevel = (int)((uint32_t)abs(level) * (uint32_t)quantCoeff[i]);
+        level = (tmplevel + add) >> qBits;
+        if (level) numSig++;
+        level *= sign;
+        qCoef[i] = (int16_t)abs(clip16(level));
+    }
+    return numSig;
+}
+/* dct.cpp:612-634 */
+void orc_dequant_normal(const int16_t* q, int16_t* coef, int num, int scale, int shift)
+{
+    int add = 1 << (shift - 1);
+    for (int n = 0; n < num; n++) coef[n] = (int16_t)clip16((q[n] * scale + add) >> shift);
+}
+/* dct.cpp:636-662 */
+void orc_dequant_scaling(const int16_t* q, const int32_t* deq, int16_t* coef, int num, int per, int shift)
+{
+    shift += 4;
+    if (shift > per)
+    {
+        int add = 1 << (shift - per - 1);
+        for (int n = 0; n < num; n++) coef[n] = (int16_t)clip16((q[n] * deq[n] + add) >> (shift - per));
+    }
+    else
+        for (int n = 0; n < num; n++) coef[n] = (int16_t)clip16((int)((uint32_t)clip16(q[n] * deq[n]) << (per - shift)));
+}
+
+/* =====================================================================================================
+ * Interpolation (common/ipfilter.cpp:40-370).  Taps: common/constants.cpp:250-268 (HEVC standard values).
+ * ===================================================================================================== */
+static const int luma_filter[4][8] = { { 0, 0, 0, 64, 0, 0, 0, 0 }, { -1, 4, -10, 58, 17, -5, 1, 0 },
+                                       { -1, 4, -11, 40, 40, -11, 4, -1 }, { 0, 1, -5, 17, 58, -10, 4, -1 } };
+static const int chroma_filter[8][4] = { { 0, 64, 0, 0 }, { -2, 58, 10, -2 }, { -4, 54, 16, -2 }, { -6, 46, 28, -4 },
+                                         { -4, 36, 36, -4 }, { -4, 28, 46, -6 }, { -2, 16, 54, -4 }, { -2, 10, 58, -2 } };
+static int tap(int taps, int idx, int t) { return taps == 8 ? luma_filter[idx][t] : chroma_filter[idx][t]; }
+static void put_px(void* p, int depth, intptr_t i, int v) { if (depth == 8) ((uint8_t*)p)[i] = (uint8_t)v; else ((uint16_t*)p)[i] = (uint16_t)v; }
+
+/* generic N-tap pass.  srcShort/dstShort select int16 operands; `step` = 1 (horizontal) or srcStride (vertical) */
+static void fir_pass(int depth, int taps, int idx, int w, int rows, const void* src, int srcShort, intptr_t srcStride, intptr_t step,
+                     void* dst, int dstShort, intptr_t dstStride, int shift, int offset)
+{
+    int maxVal = (1 << depth) - 1;
+    for (int y = 0; y < rows; y++)
+        for (int x = 0; x < w; x++)
+        {
+            int sum = 0;
+            for (int t = 0; t < taps; t++)
+            {
+                intptr_t o = y * srcStride + x + t * step;
+                sum += (srcShort ? ((const int16_t*)src)[o] : px(src, depth, o)) * tap(taps, idx, t);
+            }
+            int val = (int16_t)((sum + offset) >> shift);
+            if (dstShort) ((int16_t*)dst)[y * dstStride + x] = (int16_t)val;
+            else put_px(dst, depth, y * dstStride + x, val < 0 ? 0 : (val > maxVal ? maxVal : val));
+        }
+}
+
+void orc_interp(int depth, int kind, int taps, int w, int h, const void* src, intptr_t srcStride, void* dst, intptr_t dstStride,
+                int idxX, int idxY, int isRowExt)
+{
+    int headRoom = 14 - depth, half = taps / 2 - 1;
+    const void* sh = padd(src, depth, -half);                               /* src - (N/2-1)            */
+    const void* sv = padd(src, depth, -half * srcStride);                   /* src - (N/2-1)*srcStride  */
+    switch (kind)
+    {
+    case 0: fir_pass(depth, taps, idxX, w, h, sh, 0, srcStride, 1, dst, 0, dstStride, 6, 32); break;                               /* :79-118  */
+    case 1:                                                                                                                          /* :120-162 */
+    {
+        int shift = 6 - headRoom, offset = (int)((unsigned)-8192 << shift), rows = h;
+        if (isRowExt) { sh = padd(sh, depth, -half * srcStride); rows += taps - 1; }
+        fir_pass(depth, taps, idxX, w, rows, sh, 0, srcStride, 1, dst, 1, dstStride, shift, offset);
+        break;
+    }
+    case 2: fir_pass(depth, taps, idxX, w, h, sv, 0, srcStride, srcStride, dst, 0, dstStride, 6, 32); break;                       /* :164-203 */
+    case 3: { int shift = 6 - headRoom; fir_pass(depth, taps, idxX, w, h, sv, 0, srcStride, srcStride, dst, 1, dstStride, shift, (int)((unsigned)-8192 << shift)); break; } /* :205-239 */
+    case 4: { int shift = 6 + headRoom; fir_pass(depth, taps, idxX, w, h, (const int16_t*)src - half * srcStride, 1, srcStride, srcStride, dst, 0, dstStride, shift, (1 << (shift - 1)) + (8192 << 6)); break; } /* :241-282 */
+    case 5: fir_pass(depth, taps, idxX, w, h, (const int16_t*)src - half * srcStride, 1, srcStride, srcStride, dst, 1, dstStride, 6, 0); break;  /* :284-317 */
+    case 6:                                                                                                                          /* :362-369 */
+    {
+        int16_t immed[64 * (64 + 7)];
+        int shift = 6 - headRoom, shift2 = 6 + headRoom;
+        fir_pass(depth, taps, idxX, w, h + taps - 1, padd(sh, depth, -half * srcStride), 0, srcStride, 1, immed, 1, w, shift, (int)((unsigned)-8192 << shift));
+        fir_pass(depth, taps, idxY, w, h, immed, 1, w, w, dst, 0, dstStride, shift2, (1 << (shift2 - 1)) + (8192 << 6));
+        break;
+    }
+    case 7:                                                                                                                          /* :40-57 */
+        for (int y = 0; y < h; y++)
+            for (int x = 0; x < w; x++)
+            {
+                int16_t val = (int16_t)(px(src, depth, y * srcStride + x) << headRoom);
+                ((int16_t*)dst)[y * dstStride + x] = (int16_t)(val - (int16_t)8192);
+            }
+        break;
+    }
+}
+
+/* =====================================================================================================
+ * Intra prediction (common/intrapred.cpp:31-204)
+ * ===================================================================================================== */
+void orc_intra_filter(int depth, int log2N, const void* s, void* f)         /* :31-51 */
+{
+    int N = 1 << log2N, N2 = 2 * N;
+    put_px(f, depth, 0, ((px(s, depth, 0) << 1) + px(s, depth, 1) + px(s, depth, N2 + 1) + 2) >> 2);
+    for (int i = 1; i < N2; i++) put_px(f, depth, i, ((px(s, depth, i) << 1) + px(s, depth, i - 1) + px(s, depth, i + 1) + 2) >> 2);
+    put_px(f, depth, N2, px(s, depth, N2));
+    put_px(f, depth, N2 + 1, ((px(s, depth, N2 + 1) << 1) + px(s, depth, 0) + px(s, depth, N2 + 2) + 2) >> 2);
+    for (int i = N2 + 2; i < 2 * N2; i++) put_px(f, depth, i, ((px(s, depth, i) << 1) + px(s, depth, i - 1) + px(s, depth, i + 1) + 2) >> 2);
+    put_px(f, depth, 2 * N2, px(s, depth, 2 * N2));
+}
+
+void orc_intra_pred(int depth, int log2N, int mode, int bFilter, const void* srcPix, void* dst, intptr_t ds)
+{
+    static const int angleTable[17] = { -32, -26, -21, -17, -13, -9, -5, -2, 0, 2, 5, 9, 13, 17, 21, 26, 32 };
+    static const int invAngleTable[8] = { 4096, 1638, 910, 630, 482, 390, 315, 256 };
+    int N = 1 << log2N, N2 = 2 * N, maxVal = (1 << depth) - 1;
+    int s[129];
+    for (int i = 0; i < 4 * N + 1; i++) s[i] = px(srcPix, depth, i);
+    if (mode == 0)                                                            /* planar :87-100 */
+    {
+        for (int y = 0; y < N; y++)
+            for (int x = 0; x < N; x++)
+                put_px(dst, depth, y * ds + x, ((N - 1 - x) * s[N2 + 1 + y] + (N - 1 - y) * s[1 + x] + (x + 1) * s[1 + N] + (y + 1) * s[N2 + 1 + N] + N) >> (log2N + 1));
+        return;
+    }
+    if (mode == 1)                                                            /* DC :53-85 */
+    {
+        int dc = N;
+        for (int i = 0; i < N; i++) dc += s[1 + i] + s[N2 + 1 + i];
+        dc /= 2 * N;
+        for (int y = 0; y < N; y++) for (int x = 0; x < N; x++) put_px(dst, depth, y * ds + x, dc);
+        if (bFilter)
+        {
+            put_px(dst, depth, 0, (s[1] + s[N2 + 1] + 2 * dc + 2) >> 2);
+            for (int x = 1; x < N; x++) put_px(dst, depth, x, (s[1 + x] + 3 * dc + 2) >> 2);
+            for (int y = 1; y < N; y++) put_px(dst, depth, y * ds, (s[N2 + 1 + y] + 3 * dc + 2) >> 2);
+        }
+        return;
+    }
+    /* angular :102-204 */
+    int hor = mode < 18, nbuf[129];
+    if (hor)
+    {
+        nbuf[0] = s[0];
+        for (int i = 0; i < N2; i++) { nbuf[1 + i] = s[N2 + 1 + i]; nbuf[N2 + 1 + i] = s[1 + i]; }
+    }
+    else memcpy(nbuf, s, sizeof(int) * (4 * N + 1));
+    int angleOffset = hor ? 10 - mode : mode - 26, angle = angleTable[8 + angleOffset];
+    int pred[32][32];
+    if (!angle)
+    {
+        for (int y = 0; y < N; y++) for (int x = 0; x < N; x++) pred[y][x] = nbuf[1 + x];
+        if (bFilter)
+            for (int y = 0; y < N; y++)
+            {
+                int v = (int16_t)(nbuf[1] + ((nbuf[N2 + 1 + y] - nbuf[0]) >> 1));
+                pred[y][0] = v < 0 ? 0 : (v > maxVal ? maxVal : v);
+            }
+    }
+    else
+    {
+        int refBuf[64 + 1], *ref;
+        if (angle < 0)
+        {
+            int nbProjected = -((N * angle) >> 5) - 1;
+            int* ref_pix = refBuf + nbProjected + 1;
+            int invAngle = invAngleTable[-angleOffset - 1], invAngleSum = 128;
+            for (int i = 0; i < nbProjected; i++) { invAngleSum += invAngle; ref_pix[-2 - i] = nbuf[N2 + (invAngleSum >> 8)]; }
+            for (int i = 0; i < N + 1; i++) ref_pix[-1 + i] = nbuf[i];
+            ref = ref_pix;
+        }
+        else ref = nbuf + 1;
+        int angleSum = 0;
+        for (int y = 0; y < N; y++)
+        {
+            angleSum += angle;
+            int offset = angleSum >> 5, fraction = angleSum & 31;
+            for (int x = 0; x < N; x++)
+                pred[y][x] = fraction ? ((32 - fraction) * ref[offset + x] + fraction * ref[offset + x + 1] + 16) >> 5 : ref[offset + x];
+        }
+    }
+    for (int y = 0; y < N; y++)
+        for (int x = 0; x < N; x++)
+            put_px(dst, depth, y * ds + x, hor ? pred[x][y] : pred[y][x]);
+}

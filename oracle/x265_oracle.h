@@ -30,3 +30,24 @@ uint64_t orc_ssd_s(int depth, int size, const int16_t* a, intptr_t sa);
 }
 #endif
 #endif
+
+/* ---- transforms (restatement of common/dct.cpp) ---- */
+#ifdef __cplusplus
+extern "C" {
+#endif
+/* idx 0..3 = 4/8/16/32-point DCT, 4 = 4x4 DST.  Forward: strided src -> N*N contiguous; inverse: N*N contiguous -> strided dst */
+void     orc_dct(int depth, int idx, const int16_t* src, int16_t* dst, intptr_t srcStride);
+void     orc_idct(int depth, int idx, const int16_t* src, int16_t* dst, intptr_t dstStride);
+uint32_t orc_quant(const int16_t* coef, const int32_t* quantCoeff, int32_t* deltaU, int16_t* qCoef, int qBits, int add, int numCoeff);
+uint32_t orc_nquant(const int16_t* coef, const int32_t* quantCoeff, int16_t* qCoef, int qBits, int add, int numCoeff);
+void     orc_dequant_normal(const int16_t* quantCoef, int16_t* coef, int num, int scale, int shift);
+void     orc_dequant_scaling(const int16_t* quantCoef, const int32_t* deQuantCoef, int16_t* coef, int num, int per, int shift);
+/* interpolation: kind 0 hpp 1 hps 2 vpp 3 vps 4 vsp 5 vss 6 hvpp 7 p2s; taps 8 (luma) / 4 (chroma) */
+void     orc_interp(int depth, int kind, int taps, int w, int h, const void* src, intptr_t srcStride, void* dst, intptr_t dstStride,
+                    int idxX, int idxY, int isRowExt);
+/* intra: neighbours [topLeft, top 2N, left 2N]; mode 0 planar, 1 DC, 2..34 angular */
+void     orc_intra_pred(int depth, int log2N, int mode, int bFilter, const void* srcPix, void* dst, intptr_t dstStride);
+void     orc_intra_filter(int depth, int log2N, const void* src, void* dst);
+#ifdef __cplusplus
+}
+#endif

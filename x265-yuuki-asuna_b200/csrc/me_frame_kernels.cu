@@ -7,7 +7,7 @@
 // (64x64, 4x 32x32, 16x 16x16, 64x 8x8) then run out of shared memory, one warp per PU search, with the
 // same warp-cooperative bit-exact device algorithm as me_batch_kernel (me_device.cuh =
 // MotionEstimate::motionEstimate, motion.cpp:739-1569).  The window pitch is 16*k bytes chosen so that 8
-// consecutive rows fall in distinct banks.  PUs are handed out largest-first from shared-memory queues.
+// consecutive rows fall in distinct banks; the box start is aligned down to 16 bytes as TMA requires.
 //
 // Per-PU semantics: motionEstimate(ref, mvmin = (mvp>>2) - merange, mvmax = (mvp>>2) + merange, qmvp = mvp,
 // numCandidates = 0, merange, ...) with the CTU's predictor mvp shared by all its PUs (Search::setSearchRange
@@ -109,7 +109,10 @@ me_frame_kernel(const __grid_constant__ MEFrameMaps maps, MEFrameArgs p)
     int mvpx = 0, mvpy = 0;
     if (p.mvpCtu) { const int32_t* m = p.mvpCtu + ((int64_t)ref * p.ctuCols * p.ctuRows + ctu) * 2; mvpx = m[0]; mvpy = m[1]; }
     const int cx = mvpx >> 2, cy = mvpy >> 2;
-    const int wx0 = ctuX * 64 + cx - p.R, wy0 = ctuY * 64 + cy - p.R;        // picture coordinates of window pixel (0,0)
+    const int wx0 = ctuX * 64 + cx - p.R, wy0 = ctuY * 64 + cy - p.R;        // picture coordinates of the search window
+    // TMA needs the box's inner start coordinate 16-byte aligned (measured on this B200: an unaligned x raises
+    // "illegal instruction"), so the box starts at the aligned-down column and `ex` pixels are skipped.
+    const int tx = wx0 + p.marginX, ax = tx & ~(16 / px - 1), ex = tx - ax;
 
     if (threadIdx.x == 0)
     {
@@ -120,7 +123,7 @@ me_frame_kernel(const __grid_constant__ MEFrameMaps maps, MEFrameArgs p)
     if (threadIdx.x == 0)
     {
         mbar_expect_tx(bar, (uint32_t)((size_t)p.winW * p.winH * px + 64 * 64 * px));
-        tma_load_2d(window, &maps.ref[ref], bar, wx0 + p.marginX, wy0 + p.marginY);
+        tma_load_2d(window, &maps.ref[ref], bar, ax, wy0 + p.marginY);
         tma_load_2d(fencCtu, &maps.cur, bar, ctuX * 64 + p.marginX, ctuY * 64 + p.marginY);
     }
     mbar_wait(bar, 0);
@@ -151,7 +154,7 @@ me_frame_kernel(const __grid_constant__ MEFrameMaps maps, MEFrameArgs p)
     s.cost = p.cost + 2 * 32768; s.mvpx = mvpx; s.mvpy = mvpy;
     s.w = sz; s.h = sz; s.partSizeScale = (sz * sz) >> 4;
     s.fenc = fencCtu + puy * 64 + pux;
-    s.fref = window + (int64_t)(puy - cy + p.R) * p.winW + (pux - cx + p.R);
+    s.fref = window + (int64_t)(puy - cy + p.R) * p.winW + (pux - cx + p.R + ex);
     s.gfref = (const pixel*)p.refOrigins[ref] + (ctuX * 64 + pux) + (int64_t)(ctuY * 64 + puy) * p.refStride;
     s.gstride = p.refStride;
     int ox, oy;
@@ -208,13 +211,14 @@ int me_frame_dev(Ctx* ctx, int depth, const void* curOrigin, int64_t curStride, 
     if (subpelRefine < 0 || subpelRefine > 7) { set_error("me_frame: subpelRefine %d", subpelRefine); return -1; }
     const int px = depth > 8 ? 2 : 1;
     const int R = merange + 8;
-    int winW = 64 + 2 * R;
+    int winW = 64 + 2 * R + (16 / px - 1);            // + slack for the 16-byte alignment of the TMA box start
     // pitch: a multiple of 16 bytes whose word count is 4 mod 8 -> 8 consecutive rows hit distinct bank groups
     int pitchBytes = ((winW * px + 15) / 16) * 16;
     while (((pitchBytes / 4) % 8) != 4) pitchBytes += 16;
     winW = pitchBytes / px;
     const int winH = 64 + 2 * R;
     if (winW > 256 || winH > 256) { set_error("me_frame: merange %d needs a %dx%d window, above the 256-element TMA box limit; use x265b200_me_batch_dev", merange, winW, winH); return -1; }
+    if ((marginX * px) & 15) { set_error("me_frame: marginX*sizeof(pixel) must be a multiple of 16 bytes (TMA box alignment)"); return -1; }
     if (marginX < R + 8 || marginY < R) { set_error("me_frame: plane margins (%d,%d) smaller than the search window reach %d", marginX, marginY, R); return -1; }
     if (ensure_mvcost(ctx, lambda)) return -1;
 
