@@ -245,10 +245,13 @@ template<int W, int H> void ip_hvpp(const pixel* s, intptr_t ss, pixel* d, intpt
 template<int W, int H> void ip_p2s(const pixel* s, intptr_t ss, int16_t* d, intptr_t ds) { interp_run<8, W, H, X265B200_IP_P2S>(s, ss, d, ds, 0, 0, 0); }
 
 // ---- intra ---------------------------------------------------------------------------------------
-template<int LOG2>
+// SLOT: 0 = intra_pred[PLANAR_IDX], 1 = intra_pred[DC_IDX] (both ignore dirMode, intrapred.cpp:69-100 -- TestBench
+// calls them with dirMode = 0), 2 = the angular slots (mode = dirMode)
+template<int LOG2, int SLOT>
 void intra_pred_thunk(pixel* dst, intptr_t dstStride, const pixel* srcPix, int dirMode, int bFilter)
 {
     const int N = 1 << LOG2;
+    if (SLOT < 2) dirMode = SLOT;
     void* dS = up1d(0, srcPix, (4 * N + 1) * PX);
     void* dD = dev(1, N * N * PX);
     x265b200_intra_job job; job.srcOff = 0; job.dstOff = 0; job.mode = dirMode; job.bFilter = bFilter;
@@ -337,7 +340,8 @@ void setupAssemblyPrimitives(EncoderPrimitives& p, int /*cpuMask: SIMD flags are
     p.cu[IDX].count_nonzero = count_nonzero_thunk<N>; \
     p.cu[IDX].intra_filter = intra_filter_thunk<LOG2>; \
     p.cu[IDX].intra_pred_allangs = intra_allangs_thunk<LOG2>; \
-    for (int m = 0; m < NUM_INTRA_MODE; m++) p.cu[IDX].intra_pred[m] = intra_pred_thunk<LOG2>;
+    p.cu[IDX].intra_pred[PLANAR_IDX] = intra_pred_thunk<LOG2, 0>; p.cu[IDX].intra_pred[DC_IDX] = intra_pred_thunk<LOG2, 1>; \
+    for (int m = 2; m < NUM_INTRA_MODE; m++) p.cu[IDX].intra_pred[m] = intra_pred_thunk<LOG2, 2>;
     TU(BLOCK_4x4, 4, 2) TU(BLOCK_8x8, 8, 3) TU(BLOCK_16x16, 16, 4) TU(BLOCK_32x32, 32, 5)
 #undef TU
     p.dst4x4 = dct_thunk<4, 4>;

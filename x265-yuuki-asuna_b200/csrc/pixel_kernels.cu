@@ -423,7 +423,7 @@ __device__ __forceinline__ uint4 ld16_any(const uint8_t* p)
     return make_uint4(__funnelshift_r(t0, t1, sh), __funnelshift_r(t1, t2, sh), __funnelshift_r(t2, t3, sh), __funnelshift_r(t3, t4, sh));
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128, 8)
 sad_pyramid_kernel(const uint8_t* __restrict__ cur, int64_t strideC, const uint8_t* const* __restrict__ refs, int64_t strideR,
                    int ctuCols, int ctuRows, const int16_t* __restrict__ mvCtu,
                    int32_t* __restrict__ out8, int32_t* __restrict__ out16, int32_t* __restrict__ out32, int32_t* __restrict__ out64)
@@ -451,17 +451,18 @@ sad_pyramid_kernel(const uint8_t* __restrict__ cur, int64_t strideC, const uint8
     uint32_t s8[4] = { 0, 0, 0, 0 };        // [row group 0/1][left/right 8x8]
     if (valid)
     {
+        // 4 batches of 4 rows: 8 independent 128-bit loads in flight per lane, modest register footprint
 #pragma unroll
-        for (int g = 0; g < 2; g++)
+        for (int g = 0; g < 4; g++)
         {
-            uint4 a[8], b[8];
+            uint4 a[4], b[4];
 #pragma unroll
-            for (int i = 0; i < 8; i++) { a[i] = __ldg((const uint4*)(c + (int64_t)(g * 8 + i) * strideC)); b[i] = ld16_any(r + (int64_t)(g * 8 + i) * strideR); }
+            for (int i = 0; i < 4; i++) { a[i] = __ldg((const uint4*)(c + (int64_t)(g * 4 + i) * strideC)); b[i] = ld16_any(r + (int64_t)(g * 4 + i) * strideR); }
 #pragma unroll
-            for (int i = 0; i < 8; i++)
+            for (int i = 0; i < 4; i++)
             {
-                s8[g * 2 + 0] += __vsadu4(a[i].x, b[i].x) + __vsadu4(a[i].y, b[i].y);
-                s8[g * 2 + 1] += __vsadu4(a[i].z, b[i].z) + __vsadu4(a[i].w, b[i].w);
+                s8[(g >> 1) * 2 + 0] += __vsadu4(a[i].x, b[i].x) + __vsadu4(a[i].y, b[i].y);
+                s8[(g >> 1) * 2 + 1] += __vsadu4(a[i].z, b[i].z) + __vsadu4(a[i].w, b[i].w);
             }
         }
     }
@@ -490,8 +491,8 @@ int sad_pyramid_dev(Ctx* ctx, int depth, const void* cur, int64_t strideC, const
     if (((uintptr_t)out8 & 7)) { set_error("sad_pyramid: out8 must be 8-byte aligned"); return -1; }
     int64_t warps = (int64_t)((ctuCols + 1) / 2) * ctuRows;
     if (warps <= 0 || numRefs <= 0) return 0;
-    dim3 grid((unsigned)((warps * 32 + 255) / 256), (unsigned)numRefs);
-    sad_pyramid_kernel<<<grid, 256, 0, ctx->stream>>>((const uint8_t*)cur, strideC, (const uint8_t* const*)refs, strideR, ctuCols, ctuRows, mvCtu, out8, out16, out32, out64);
+    dim3 grid((unsigned)((warps * 32 + 127) / 128), (unsigned)numRefs);
+    sad_pyramid_kernel<<<grid, 128, 0, ctx->stream>>>((const uint8_t*)cur, strideC, (const uint8_t* const*)refs, strideR, ctuCols, ctuRows, mvCtu, out8, out16, out32, out64);
     ctx->launches++;
     return check(cudaGetLastError(), "sad_pyramid launch");
 }
