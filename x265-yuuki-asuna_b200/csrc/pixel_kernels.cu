@@ -407,8 +407,7 @@ int add_ps_plane_dev(Ctx* ctx, int depth, void* dst, int64_t dstStride, const vo
 // for all PU levels at once; sad<lx,ly> of pixel.cpp:40-55 is additive over sub-blocks).  Each plane
 // byte is fetched exactly once with 128-bit loads; per-CTU full-pel displacement optional; all references of a
 // frame are processed by one launch (grid.y = reference).
-// Mapping: one warp = 64 rows x 128 px (two CTUs); lane = rsub*8 + col owns a 16x16 block
-// (col: 16-px column, rsub: 16-row band); 32x32 / 64x64 sums are warp-shuffle reductions.
+// Mapping: see the kernel comment (CTA = 64 rows x 512 px, lane = 16x16 block).
 // Algorithmic bytes per launch: 2*W*H + 4*(n8 + n16 + n32 + n64).
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint4 ld16_any(const uint8_t* p)
@@ -423,11 +422,15 @@ __device__ __forceinline__ uint4 ld16_any(const uint8_t* p)
     return make_uint4(__funnelshift_r(t0, t1, sh), __funnelshift_r(t1, t2, sh), __funnelshift_r(t2, t3, sh), __funnelshift_r(t3, t4, sh));
 }
 
+// CTA = 4 warps = one CTU row (64 rows) x 512 px (8 CTUs): warp w owns the 16-row band w, lane l the 16-px column l, so
+// every row is read as one contiguous 512-byte run per warp (DRAM-friendly); 32x32 / 64x64 sums combine lanes by
+// shuffle and the 4 row bands through shared memory.
 __global__ void __launch_bounds__(128, 8)
 sad_pyramid_kernel(const uint8_t* __restrict__ cur, int64_t strideC, const uint8_t* const* __restrict__ refs, int64_t strideR,
                    int ctuCols, int ctuRows, const int16_t* __restrict__ mvCtu,
                    int32_t* __restrict__ out8, int32_t* __restrict__ out16, int32_t* __restrict__ out32, int32_t* __restrict__ out64)
 {
+    __shared__ int sBand[4][32];
     // blockIdx.y = reference index: all references of a frame in ONE launch (the source CTU rows are shared in L2)
     const uint8_t* __restrict__ ref = refs[blockIdx.y];
     {
@@ -435,15 +438,12 @@ sad_pyramid_kernel(const uint8_t* __restrict__ cur, int64_t strideC, const uint8
         out8 += blockIdx.y * nctu * 64; out16 += blockIdx.y * nctu * 16; out32 += blockIdx.y * nctu * 4; out64 += blockIdx.y * nctu;
         if (mvCtu) mvCtu += blockIdx.y * nctu * 2;
     }
-    const int lane = threadIdx.x & 31;
-    const int pairsPerRow = (ctuCols + 1) >> 1;
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (warp >= (int64_t)pairsPerRow * ctuRows) return;
-    const int ctuY = (int)(warp / pairsPerRow), pair = (int)(warp % pairsPerRow);
-    const int col = lane & 7, rsub = lane >> 3;
-    const int ctuX = pair * 2 + (col >> 2);
+    const int lane = threadIdx.x & 31, rsub = threadIdx.x >> 5;
+    const int chunksPerRow = (ctuCols + 7) >> 3;
+    const int ctuY = blockIdx.x / chunksPerRow, chunk = blockIdx.x % chunksPerRow;
+    const int ctuX = chunk * 8 + (lane >> 2);
     const bool valid = ctuX < ctuCols;
-    const int x0 = pair * 128 + col * 16, y0 = ctuY * 64 + rsub * 16;
+    const int x0 = chunk * 512 + lane * 16, y0 = ctuY * 64 + rsub * 16;
     int mvx = 0, mvy = 0;
     if (mvCtu && valid) { mvx = mvCtu[2 * (ctuY * ctuCols + ctuX)]; mvy = mvCtu[2 * (ctuY * ctuCols + ctuX) + 1]; }
     const uint8_t* c = cur + (int64_t)y0 * strideC + x0;
@@ -451,7 +451,7 @@ sad_pyramid_kernel(const uint8_t* __restrict__ cur, int64_t strideC, const uint8
     uint32_t s8[4] = { 0, 0, 0, 0 };        // [row group 0/1][left/right 8x8]
     if (valid)
     {
-        // 4 batches of 4 rows: 8 independent 128-bit loads in flight per lane, modest register footprint
+        // 4 batches of 4 rows: 8 independent 128-bit loads in flight per lane
 #pragma unroll
         for (int g = 0; g < 4; g++)
         {
@@ -473,14 +473,20 @@ sad_pyramid_kernel(const uint8_t* __restrict__ cur, int64_t strideC, const uint8
         *(int2*)(out8 + (int64_t)by * n8x + bx) = make_int2((int)s8[0], (int)s8[1]);
         *(int2*)(out8 + (int64_t)(by + 1) * n8x + bx) = make_int2((int)s8[2], (int)s8[3]);
     }
-    int s16 = (int)(s8[0] + s8[1] + s8[2] + s8[3]);
+    const int s16 = (int)(s8[0] + s8[1] + s8[2] + s8[3]);
     if (valid) out16[(int64_t)(y0 >> 4) * n16x + (x0 >> 4)] = s16;
-    int s32 = s16 + __shfl_xor_sync(0xffffffffu, s16, 1);
-    s32 += __shfl_xor_sync(0xffffffffu, s32, 8);
-    if (valid && !(lane & 1) && !(lane & 8)) out32[(int64_t)(y0 >> 5) * n32x + (x0 >> 5)] = s32;
-    int s64 = s32 + __shfl_xor_sync(0xffffffffu, s32, 2);
-    s64 += __shfl_xor_sync(0xffffffffu, s64, 16);
-    if (valid && !(lane & 3) && !(lane & 24)) out64[(int64_t)ctuY * ctuCols + ctuX] = s64;
+    const int h32 = s16 + __shfl_xor_sync(0xffffffffu, s16, 1);            // 32 px wide, 16 rows
+    sBand[rsub][lane] = h32;
+    __syncthreads();
+    if (valid && !(lane & 1) && !(rsub & 1))
+        out32[(int64_t)(y0 >> 5) * n32x + (x0 >> 5)] = sBand[rsub][lane] + sBand[rsub + 1][lane];
+    if (valid && !(lane & 3) && rsub == 0)
+    {
+        int s64 = 0;
+#pragma unroll
+        for (int w = 0; w < 4; w++) s64 += sBand[w][lane] + sBand[w][lane + 2];
+        out64[(int64_t)ctuY * ctuCols + ctuX] = s64;
+    }
 }
 
 int sad_pyramid_dev(Ctx* ctx, int depth, const void* cur, int64_t strideC, const void* const* refs, int numRefs, int64_t strideR, int ctuCols, int ctuRows,
@@ -489,9 +495,9 @@ int sad_pyramid_dev(Ctx* ctx, int depth, const void* cur, int64_t strideC, const
     if (depth != 8) { set_error("sad_pyramid: 8-bit planes only (use pixelcmp grid mode for high bit depth)"); return -1; }
     if (((uintptr_t)cur & 15) || (strideC & 15)) { set_error("sad_pyramid: cur plane and stride must be 16-byte aligned"); return -1; }
     if (((uintptr_t)out8 & 7)) { set_error("sad_pyramid: out8 must be 8-byte aligned"); return -1; }
-    int64_t warps = (int64_t)((ctuCols + 1) / 2) * ctuRows;
-    if (warps <= 0 || numRefs <= 0) return 0;
-    dim3 grid((unsigned)((warps * 32 + 127) / 128), (unsigned)numRefs);
+    int64_t ctas = (int64_t)((ctuCols + 7) / 8) * ctuRows;
+    if (ctas <= 0 || numRefs <= 0) return 0;
+    dim3 grid((unsigned)ctas, (unsigned)numRefs);
     sad_pyramid_kernel<<<grid, 128, 0, ctx->stream>>>((const uint8_t*)cur, strideC, (const uint8_t* const*)refs, strideR, ctuCols, ctuRows, mvCtu, out8, out16, out32, out64);
     ctx->launches++;
     return check(cudaGetLastError(), "sad_pyramid launch");

@@ -228,9 +228,64 @@ xform_mma_kernel(XformArgs p)
 
     const int add1 = 1 << (p.shift1 - 1), add2 = 1 << (p.shift2 - 1);
     const int64_t units = (p.n + PER - 1) / PER;
-    for (int64_t u = (int64_t)blockIdx.x * XF_WARPS + warp; u < units; u += (int64_t)gridDim.x * XF_WARPS)
-    {
-        // ---- load: In[j][n] = src[j][n] (forward) or src[n][j] (inverse, contiguous NxN) ----
+    constexpr int CPB = N * N / 8;                 // 16-byte chunks per block
+    constexpr int CH = PER * CPB;                  // chunks per unit
+    constexpr int CNT = (CH + 31) / 32;            // chunks per lane
+    constexpr int LPR = N / 8;                     // chunks per row
+
+    // 128-bit path: whole unit addressable with aligned uint4 loads?
+    auto vec_ok = [&](int64_t u) -> bool {
+        bool ok = true;
+#pragma unroll
+        for (int s = 0; s < PER; s++)
+        {
+            int64_t b = u * PER + s;
+            if (b >= p.n) continue;
+            uintptr_t a = (uintptr_t)(p.src + xf_src_off(p, b));
+            if (!INVERSE) a |= (uintptr_t)(p.srcStride * 2);
+            ok = ok && !(a & 15);
+        }
+        return ok;
+    };
+    auto fetch = [&](int64_t u, uint4 regs[CNT]) {
+#pragma unroll
+        for (int i = 0; i < CNT; i++)
+        {
+            const int c = lane + 32 * i;
+            regs[i] = make_uint4(0, 0, 0, 0);
+            if (c < CH)
+            {
+                const int s = c / CPB, cc = c % CPB, row = cc / LPR, c8 = (cc % LPR) * 8;
+                const int64_t b = u * PER + s;
+                if (b < p.n)
+                    regs[i] = __ldg((const uint4*)(p.src + xf_src_off(p, b) + (INVERSE ? (int64_t)row * N : (int64_t)row * p.srcStride) + c8));
+            }
+        }
+    };
+    auto commit = [&](const uint4 regs[CNT]) {
+#pragma unroll
+        for (int i = 0; i < CNT; i++)
+        {
+            const int c = lane + 32 * i;
+            if (c < CH)
+            {
+                const int s = c / CPB, cc = c % CPB, row = cc / LPR, c8 = (cc % LPR) * 8;
+                int16_t* tile = bufA + s * N * LD;
+                if (!INVERSE) *(uint4*)(tile + row * LD + c8) = regs[i];
+                else
+                {
+                    const uint32_t w[4] = { regs[i].x, regs[i].y, regs[i].z, regs[i].w };
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                    {
+                        tile[(c8 + 2 * k) * LD + row] = (int16_t)(w[k] & 0xffff);
+                        tile[(c8 + 2 * k + 1) * LD + row] = (int16_t)(w[k] >> 16);
+                    }
+                }
+            }
+        }
+    };
+    auto scalar_load = [&](int64_t u) {
 #pragma unroll
         for (int s = 0; s < PER; s++)
         {
@@ -239,17 +294,6 @@ xform_mma_kernel(XformArgs p)
             if (b < p.n)
             {
                 const int16_t* sp = p.src + xf_src_off(p, b);
-                if (!INVERSE && N >= 16 && !(((uintptr_t)sp | (uintptr_t)(p.srcStride * 2)) & 15))
-                {
-                    // 128-bit coalesced rows: N/8 lanes per row
-                    constexpr int LPR = N / 8;
-                    for (int e = lane; e < N * LPR; e += 32)
-                    {
-                        int row = e / LPR, c8 = (e % LPR) * 8;
-                        *(uint4*)(tile + row * LD + c8) = __ldg((const uint4*)(sp + (int64_t)row * p.srcStride + c8));
-                    }
-                }
-                else
                 for (int e = lane; e < N * N / 2; e += 32)
                 {
                     int row = (2 * e) / N, col = (2 * e) % N;
@@ -261,6 +305,21 @@ xform_mma_kernel(XformArgs p)
             else
                 for (int e = lane; e < N * LD / 2; e += 32) ((uint32_t*)tile)[e] = 0;
         }
+    };
+
+    const int64_t ustride = (int64_t)gridDim.x * XF_WARPS;
+    int64_t u = (int64_t)blockIdx.x * XF_WARPS + warp;
+    uint4 pre[CNT];
+    bool pv = false;
+    if (u < units) { pv = vec_ok(u); if (pv) fetch(u, pre); }
+    for (; u < units; u += ustride)
+    {
+        // ---- load: In[j][n] = src[j][n] (forward) or src[n][j] (inverse, contiguous NxN) ----
+        if (pv) commit(pre); else scalar_load(u);
+        // software pipeline: the next unit's global loads are in flight during this unit's tensor-core passes
+        const int64_t nu = u + ustride;
+        bool nv = false;
+        if (nu < units) { nv = vec_ok(nu); if (nv) fetch(nu, pre); }
         __syncwarp();
         if (N == 32)      { pass32<INVERSE>(a32, bufA, bufB, add1, p.shift1, gid, tig); __syncwarp(); pass32<INVERSE>(a32, bufB, bufA, add2, p.shift2, gid, tig); }
         else if (N == 16) { pass16<INVERSE>(a16, bufA, bufB, add1, p.shift1, gid, tig); __syncwarp(); pass16<INVERSE>(a16, bufB, bufA, add2, p.shift2, gid, tig); }
@@ -274,10 +333,9 @@ xform_mma_kernel(XformArgs p)
             if (b >= p.n) continue;
             const int16_t* tile = bufA + s * N * LD;
             int16_t* dp = p.dst + xf_dst_off(p, b);
-            if (!INVERSE && N >= 16 && !((uintptr_t)dp & 15))
+            if (!INVERSE && !((uintptr_t)dp & 15))
             {
-                constexpr int LPR = N / 8;
-                for (int e = lane; e < N * LPR; e += 32)
+                for (int e = lane; e < CPB; e += 32)
                 {
                     int row = e / LPR, c8 = (e % LPR) * 8;
                     *(uint4*)(dp + row * N + c8) = *(const uint4*)(tile + row * LD + c8);
@@ -290,6 +348,16 @@ xform_mma_kernel(XformArgs p)
                     if ((uintptr_t)dp & 3) { dp[row * N + col] = tile[row * LD + col]; dp[row * N + col + 1] = tile[row * LD + col + 1]; }
                     else *(uint32_t*)(dp + row * N + col) = *(const uint32_t*)(tile + row * LD + col);
                 }
+            else if (!(((uintptr_t)dp | (uintptr_t)(p.dstStride * 2)) & 15))
+                for (int e = lane; e < CPB; e += 32)
+                {
+                    int j = e / LPR, c8 = (e % LPR) * 8;           // output row j, columns c8..c8+7 = R[c8+k][j]
+                    uint32_t w[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        w[k] = (uint32_t)(uint16_t)tile[(c8 + 2 * k) * LD + j] | ((uint32_t)(uint16_t)tile[(c8 + 2 * k + 1) * LD + j] << 16);
+                    *(uint4*)(dp + (int64_t)j * p.dstStride + c8) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
             else
                 for (int e = lane; e < N * N; e += 32)
                 {
@@ -298,6 +366,7 @@ xform_mma_kernel(XformArgs p)
                 }
         }
         __syncwarp();
+        pv = nv;
     }
 }
 
@@ -414,7 +483,7 @@ int transform_dev(Ctx* ctx, int inverse, int sizeIdx, int depth, const int16_t* 
     {
         int64_t units = N == 8 ? (n + 1) / 2 : n;
         int64_t want = (units + XF_WARPS - 1) / XF_WARPS;
-        int64_t cap = (int64_t)ctx->smCount * 8;
+        int64_t cap = (int64_t)ctx->smCount * 3;      // ~2-3 units per warp so the load prefetch has something to overlap
         unsigned blocks = (unsigned)(want < cap ? want : cap);
         dim3 block(XF_WARPS * 32);
         if (N == 32) { if (!inverse) xform_mma_kernel<32, false><<<blocks, block, 0, ctx->stream>>>(a); else xform_mma_kernel<32, true><<<blocks, block, 0, ctx->stream>>>(a); }
