@@ -300,6 +300,26 @@ template<> __device__ __forceinline__ void store_px4<uint16_t>(uint16_t* p, cons
     q[0] = (uint32_t)v[0] | ((uint32_t)v[1] << 16); q[1] = (uint32_t)v[2] | ((uint32_t)v[3] << 16);
 }
 
+// 8-tap horizontal FIR of 4 adjacent 8-bit outputs from 3 packed words (12 pixels) with two u8 x s8 dot products
+// per output (DP4A): out[k] = sum_t px[k+t]*c[t], taps packed 4 per word (|c| <= 58 fits s8).
+__device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c)
+{
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ void hfir4_u8(const uint32_t w[3], uint32_t clo, uint32_t chi, int out[4])
+{
+    out[0] = dp4a_us(w[1], chi, dp4a_us(w[0], clo, 0));
+#pragma unroll
+    for (int k = 1; k < 4; k++)
+        out[k] = dp4a_us(__funnelshift_r(w[1], w[2], 8 * k), chi, dp4a_us(__funnelshift_r(w[0], w[1], 8 * k), clo, 0));
+}
+__device__ __forceinline__ uint32_t pack_taps(const int c[8], int o)
+{
+    return (uint32_t)(c[o] & 0xff) | ((uint32_t)(c[o + 1] & 0xff) << 8) | ((uint32_t)(c[o + 2] & 0xff) << 16) | ((uint32_t)(c[o + 3] & 0xff) << 24);
+}
+
 // interpolates the PU at fractional (xFrac,yFrac) of the block starting at `src` into s.pred (stride w).
 // Each lane produces groups of 4 horizontally adjacent pixels from word loads (3 words per row for the
 // horizontal taps, one word per tap row for the vertical ones).
@@ -319,16 +339,24 @@ __device__ __noinline__ void warp_interp_luma(const MEState<pixel>& s, const pix
         for (int u = u0; u < gw * h; u += du)
         {
             int y = u / gw, x = (u - y * gw) << 2;
-            uint32_t rw[NW12]; int v[12], o[4];
+            uint32_t rw[NW12]; int v[12], o[4], sums[4];
             ld_words<pixel, NW12>(src + (int64_t)y * s.stride + x - 3, rw);
-            unpack_row12<pixel>(rw, v);
+            if (sizeof(pixel) == 1) hfir4_u8(rw, pack_taps(c, 0), pack_taps(c, 4), sums);
+            else
+            {
+                unpack_row12<pixel>(rw, v);
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                {
+                    sums[k] = 0;
+#pragma unroll
+                    for (int t = 0; t < 8; t++) sums[k] += v[k + t] * c[t];
+                }
+            }
 #pragma unroll
             for (int k = 0; k < 4; k++)
             {
-                int sum = 0;
-#pragma unroll
-                for (int t = 0; t < 8; t++) sum += v[k + t] * c[t];
-                int val = (int16_t)((sum + 32) >> 6);
+                int val = (int16_t)((sums[k] + 32) >> 6);
                 o[k] = val < 0 ? 0 : (val > maxVal ? maxVal : val);
             }
             store_px4<pixel>(s.pred + y * w + x, o);
@@ -370,18 +398,23 @@ __device__ __noinline__ void warp_interp_luma(const MEState<pixel>& s, const pix
         for (int u = u0; u < gw * (h + 7); u += du)
         {
             int y = u / gw, x = (u - y * gw) << 2;
-            uint32_t rw[NW12]; int v[12];
+            uint32_t rw[NW12]; int v[12], sums[4];
             ld_words<pixel, NW12>(src + (int64_t)(y - 3) * s.stride + x - 3, rw);
-            unpack_row12<pixel>(rw, v);
+            if (sizeof(pixel) == 1) hfir4_u8(rw, pack_taps(c, 0), pack_taps(c, 4), sums);
+            else
+            {
+                unpack_row12<pixel>(rw, v);
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                {
+                    sums[k] = 0;
+#pragma unroll
+                    for (int t = 0; t < 8; t++) sums[k] += v[k + t] * c[t];
+                }
+            }
             int o[4];
 #pragma unroll
-            for (int k = 0; k < 4; k++)
-            {
-                int sum = 0;
-#pragma unroll
-                for (int t = 0; t < 8; t++) sum += v[k + t] * c[t];
-                o[k] = (int16_t)((sum + offset) >> shift);
-            }
+            for (int k = 0; k < 4; k++) o[k] = (int16_t)((sums[k] + offset) >> shift);
             uint32_t* d = (uint32_t*)(s.immed + y * w + x);
             d[0] = (uint32_t)(o[0] & 0xffff) | ((uint32_t)o[1] << 16);
             d[1] = (uint32_t)(o[2] & 0xffff) | ((uint32_t)o[3] << 16);

@@ -86,9 +86,11 @@ __host__ __device__ inline size_t mf_scratch_bytes(int s, int px)
 // (warp-cooperative); warp 5 lanes 0-15 = the sixteen 16x16 PUs, ONE THREAD per search; warps 6-7 = the
 // sixty-four 8x8 PUs, one thread per search.  Small PUs have too few pixels to feed 32 lanes, so running the
 // whole bit-exact search per thread removes every shuffle/broadcast and keeps all lanes busy.
+// shared-memory scratch: only the warp-cooperative roles; per-thread searches keep pred/immed in their own
+// (L1-cached) local memory, which keeps the CTA at ~73 KB so three CTAs fit an SM.
 __host__ __device__ inline size_t mf_total_scratch(int px)
 {
-    return mf_scratch_bytes(64, px) + 4 * mf_scratch_bytes(32, px) + 16 * mf_scratch_bytes(16, px) + 64 * mf_scratch_bytes(8, px);
+    return mf_scratch_bytes(64, px) + 4 * mf_scratch_bytes(32, px);
 }
 
 template<typename pixel>
@@ -129,27 +131,27 @@ me_frame_kernel(const __grid_constant__ MEFrameMaps maps, MEFrameArgs p)
     mbar_wait(bar, 0);
 
     // ---- role ------------------------------------------------------------------------------------------
+    __align__(16) unsigned char tscratch[16 * 16 * sizeof(pixel) + 16 * 23 * 2];     // per-thread pred + immed (16x16 max)
     int level, idx; bool perThread; size_t soff;
     if (warp == 0)      { level = 0; idx = 0; perThread = false; soff = 0; }
     else if (warp <= 4) { level = 1; idx = warp - 1; perThread = false; soff = mf_scratch_bytes(64, px) + (size_t)(warp - 1) * mf_scratch_bytes(32, px); }
     else if (warp == 5)
     {
-        level = 2; idx = lane; perThread = true;
-        soff = mf_scratch_bytes(64, px) + 4 * mf_scratch_bytes(32, px) + (size_t)lane * mf_scratch_bytes(16, px);
+        level = 2; idx = lane; perThread = true; soff = 0;
         if (lane >= 16) return;
     }
     else
     {
-        level = 3; idx = (warp - 6) * 32 + lane; perThread = true;
-        soff = mf_scratch_bytes(64, px) + 4 * mf_scratch_bytes(32, px) + 16 * mf_scratch_bytes(16, px) + (size_t)idx * mf_scratch_bytes(8, px);
+        level = 3; idx = (warp - 6) * 32 + lane; perThread = true; soff = 0;
     }
     if (!(p.puMask & (1 << level))) return;
     const int sz = 64 >> level, per = 1 << level;
     const int puy = (idx / per) * sz, pux = (idx % per) * sz;
 
     MEState<pixel> s;
-    s.pred = (pixel*)(scratch + soff);
-    s.immed = (int16_t*)(scratch + soff + (((size_t)sz * sz * px + 15) & ~(size_t)15));
+    unsigned char* myScratch = perThread ? tscratch : scratch + soff;
+    s.pred = (pixel*)myScratch;
+    s.immed = (int16_t*)(myScratch + (((size_t)sz * sz * px + 15) & ~(size_t)15));
     s.stride = p.winW; s.isLowres = false; s.perThread = perThread; s.lane = perThread ? 0 : lane; s.depth = p.depth;
     s.cost = p.cost + 2 * 32768; s.mvpx = mvpx; s.mvpy = mvpy;
     s.w = sz; s.h = sz; s.partSizeScale = (sz * sz) >> 4;
