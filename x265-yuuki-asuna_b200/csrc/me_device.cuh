@@ -364,29 +364,36 @@ __device__ __noinline__ void warp_interp_luma(const MEState<pixel>& s, const pix
     }
     else if (!xFrac)
     {
-        // luma_vpp : ipfilter.cpp:164-203
+        // luma_vpp : ipfilter.cpp:164-203.  Unit = 4 columns x 4 rows: the 11 source rows are loaded and unpacked once
+        // and reused by the 4 output rows (sliding window) instead of 8 loads per output row.
 #pragma unroll
         for (int t = 0; t < 8; t++) c[t] = c_meLumaFilter[yFrac][t];
-        for (int u = u0; u < gw * h; u += du)
+        for (int u = u0; u < gw * (h >> 2); u += du)
         {
-            int y = u / gw, x = (u - y * gw) << 2;
-            int sum[4] = { 0, 0, 0, 0 }, o[4];
+            const int rb = u / gw, x = (u - rb * gw) << 2, y0 = rb << 2;
+            int win[11][4];
 #pragma unroll
-            for (int t = 0; t < 8; t++)
+            for (int r = 0; r < 11; r++)
             {
-                uint32_t rw[NW4]; int v[4];
-                ld_words<pixel, NW4>(src + (int64_t)(y + t - 3) * s.stride + x, rw);
-                unpack4<pixel>(rw, v);
-#pragma unroll
-                for (int k = 0; k < 4; k++) sum[k] += v[k] * c[t];
+                uint32_t rw[NW4];
+                ld_words<pixel, NW4>(src + (int64_t)(y0 + r - 3) * s.stride + x, rw);
+                unpack4<pixel>(rw, win[r]);
             }
 #pragma unroll
-            for (int k = 0; k < 4; k++)
+            for (int r = 0; r < 4; r++)
             {
-                int val = (int16_t)((sum[k] + 32) >> 6);
-                o[k] = val < 0 ? 0 : (val > maxVal ? maxVal : val);
+                int o[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                {
+                    int sum = 0;
+#pragma unroll
+                    for (int t = 0; t < 8; t++) sum += win[r + t][k] * c[t];
+                    int val = (int16_t)((sum + 32) >> 6);
+                    o[k] = val < 0 ? 0 : (val > maxVal ? maxVal : val);
+                }
+                store_px4<pixel>(s.pred + (y0 + r) * w + x, o);
             }
-            store_px4<pixel>(s.pred + y * w + x, o);
         }
     }
     else
@@ -423,25 +430,33 @@ __device__ __noinline__ void warp_interp_luma(const MEState<pixel>& s, const pix
 #pragma unroll
         for (int t = 0; t < 8; t++) c[t] = c_meLumaFilter[yFrac][t];
         const int shift2 = 6 + headRoom, offset2 = (1 << (shift2 - 1)) + (8192 << 6);
-        for (int u = u0; u < gw * h; u += du)
+        for (int u = u0; u < gw * (h >> 2); u += du)
         {
-            int y = u / gw, x = (u - y * gw) << 2;
-            int sum[4] = { 0, 0, 0, 0 }, o[4];
+            const int rb = u / gw, x = (u - rb * gw) << 2, y0 = rb << 2;
+            int win[11][4];
 #pragma unroll
-            for (int t = 0; t < 8; t++)
+            for (int r = 0; r < 11; r++)
             {
-                const uint32_t* q = (const uint32_t*)(s.immed + (y + t) * w + x);
-                uint32_t w0 = q[0], w1 = q[1];
-                sum[0] += (int)(int16_t)(w0 & 0xffff) * c[t]; sum[1] += ((int)w0 >> 16) * c[t];
-                sum[2] += (int)(int16_t)(w1 & 0xffff) * c[t]; sum[3] += ((int)w1 >> 16) * c[t];
+                const uint32_t* q = (const uint32_t*)(s.immed + (y0 + r) * w + x);
+                const uint32_t w0 = q[0], w1 = q[1];
+                win[r][0] = (int)(int16_t)(w0 & 0xffff); win[r][1] = (int)w0 >> 16;
+                win[r][2] = (int)(int16_t)(w1 & 0xffff); win[r][3] = (int)w1 >> 16;
             }
 #pragma unroll
-            for (int k = 0; k < 4; k++)
+            for (int r = 0; r < 4; r++)
             {
-                int val = (int16_t)((sum[k] + offset2) >> shift2);
-                o[k] = val < 0 ? 0 : (val > maxVal ? maxVal : val);
+                int o[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                {
+                    int sum = 0;
+#pragma unroll
+                    for (int t = 0; t < 8; t++) sum += win[r + t][k] * c[t];
+                    int val = (int16_t)((sum + offset2) >> shift2);
+                    o[k] = val < 0 ? 0 : (val > maxVal ? maxVal : val);
+                }
+                store_px4<pixel>(s.pred + (y0 + r) * w + x, o);
             }
-            store_px4<pixel>(s.pred + y * w + x, o);
         }
     }
     if (!s.perThread) __syncwarp();
