@@ -756,7 +756,7 @@ struct MESearch
 
 // Full MotionEstimate::motionEstimate.  Returns the cost; (outx,outy) = outQMv.
 template<typename pixel>
-__device__ __noinline__ int motion_estimate(const MEState<pixel>& s, MV2 mvmin, MV2 mvmax, MV2 qmvp, int numCand, const int* mvc /* [numCand][2] */,
+__device__ int motion_estimate(const MEState<pixel>& s, MV2 mvmin, MV2 mvmax, MV2 qmvp, int numCand, const int* mvc /* [numCand][2] */,
                                int merange, int searchMethod, int subpelRefine, int maxSlices, int partEnumIs64, int& outx, int& outy)
 {
     MESearch<pixel> S(s);

@@ -90,11 +90,11 @@ __host__ __device__ inline size_t mf_scratch_bytes(int s, int px)
 // (L1-cached) local memory, which keeps the CTA at ~73 KB so three CTAs fit an SM.
 __host__ __device__ inline size_t mf_total_scratch(int px)
 {
-    return mf_scratch_bytes(64, px) + 4 * mf_scratch_bytes(32, px) + mf_scratch_bytes(16, px);
+    return mf_scratch_bytes(64, px) + 4 * mf_scratch_bytes(32, px);
 }
 
 template<typename pixel>
-__global__ void __launch_bounds__(MF_WARPS * 32, 3)
+__global__ void __launch_bounds__(MF_WARPS * 32)
 me_frame_kernel(const __grid_constant__ MEFrameMaps maps, MEFrameArgs p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -104,7 +104,6 @@ me_frame_kernel(const __grid_constant__ MEFrameMaps maps, MEFrameArgs p)
     pixel* fencCtu = (pixel*)(smem + winBytes);
     unsigned char* scratch = smem + winBytes + 64 * 64 * px;
     uint64_t* bar = (uint64_t*)(scratch + mf_total_scratch(px));
-    int* q16 = (int*)(bar + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     const int ctu = blockIdx.x, ref = blockIdx.y;
@@ -120,7 +119,6 @@ me_frame_kernel(const __grid_constant__ MEFrameMaps maps, MEFrameArgs p)
     if (threadIdx.x == 0)
     {
         mbar_init(bar, 1);
-        *q16 = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -132,60 +130,44 @@ me_frame_kernel(const __grid_constant__ MEFrameMaps maps, MEFrameArgs p)
     }
     mbar_wait(bar, 0);
 
-    // ---- roles ------------------------------------------------------------------------------------------
-    // warp 0: the 64x64 PU; warps 1-4: one 32x32 PU each; warp 5 and every warp that finishes its big PU: the
-    // sixteen 16x16 PUs from a shared queue (all warp-cooperative); warps 6-7: the sixty-four 8x8 PUs, one THREAD
-    // per search (too few pixels to feed 32 lanes; per-thread removes every shuffle/broadcast).
-    __align__(16) unsigned char tscratch[8 * 8 * sizeof(pixel) + 8 * 15 * 2];     // per-thread pred + immed (8x8)
-    const bool perThread = warp >= 6;
-    size_t soff;
-    if (warp == 0)      soff = 0;
-    else if (warp <= 4) soff = mf_scratch_bytes(64, px) + (size_t)(warp - 1) * mf_scratch_bytes(32, px);
-    else                soff = mf_scratch_bytes(64, px) + 4 * mf_scratch_bytes(32, px);          // warp 5: 16x16 scratch
+    // ---- role ------------------------------------------------------------------------------------------
+    __align__(16) unsigned char tscratch[16 * 16 * sizeof(pixel) + 16 * 23 * 2];     // per-thread pred + immed (16x16 max)
+    int level, idx; bool perThread; size_t soff;
+    if (warp == 0)      { level = 0; idx = 0; perThread = false; soff = 0; }
+    else if (warp <= 4) { level = 1; idx = warp - 1; perThread = false; soff = mf_scratch_bytes(64, px) + (size_t)(warp - 1) * mf_scratch_bytes(32, px); }
+    else if (warp == 5)
+    {
+        level = 2; idx = lane; perThread = true; soff = 0;
+        if (lane >= 16) return;
+    }
+    else
+    {
+        level = 3; idx = (warp - 6) * 32 + lane; perThread = true; soff = 0;
+    }
+    if (!(p.puMask & (1 << level))) return;
+    const int sz = 64 >> level, per = 1 << level;
+    const int puy = (idx / per) * sz, pux = (idx % per) * sz;
 
     MEState<pixel> s;
-    s.stride = p.winW; s.isLowres = false; s.perThread = perThread; s.lane = perThread ? 0 : lane; s.depth = p.depth;
-    s.cost = p.cost + 2 * 32768; s.mvpx = mvpx; s.mvpy = mvpy; s.gstride = p.refStride;
     unsigned char* myScratch = perThread ? tscratch : scratch + soff;
-
-    auto run_pu = [&](int level, int idx) {
-        const int sz = 64 >> level, per = 1 << level;
-        const int puy = (idx / per) * sz, pux = (idx % per) * sz;
-        s.pred = (pixel*)myScratch;
-        s.immed = (int16_t*)(myScratch + (((size_t)sz * sz * px + 15) & ~(size_t)15));
-        s.w = sz; s.h = sz; s.partSizeScale = (sz * sz) >> 4;
-        s.fenc = fencCtu + puy * 64 + pux;
-        s.fref = window + (int64_t)(puy - cy + p.R) * p.winW + (pux - cx + p.R + ex);
-        s.gfref = (const pixel*)p.refOrigins[ref] + (ctuX * 64 + pux) + (int64_t)(ctuY * 64 + puy) * p.refStride;
-        int ox, oy;
-        int cost = motion_estimate<pixel>(s, mv2(cx - p.merange, cy - p.merange), mv2(cx + p.merange, cy + p.merange), mv2(mvpx, mvpy),
-                                          0, nullptr, p.merange, p.searchMethod, p.subpelRefine, 1, sz == 64, ox, oy);
-        if (perThread || lane == 0)
-        {
-            const int gx = ctuX * per + pux / sz, gy = ctuY * per + puy / sz;
-            int32_t* o = p.out + ((int64_t)ref * p.perRef + p.levelOff[level] + (int64_t)gy * (p.ctuCols * per) + gx) * 3;
-            o[0] = ox; o[1] = oy; o[2] = cost;
-        }
-    };
-
-    if (perThread)
+    s.pred = (pixel*)myScratch;
+    s.immed = (int16_t*)(myScratch + (((size_t)sz * sz * px + 15) & ~(size_t)15));
+    s.stride = p.winW; s.isLowres = false; s.perThread = perThread; s.lane = perThread ? 0 : lane; s.depth = p.depth;
+    s.cost = p.cost + 2 * 32768; s.mvpx = mvpx; s.mvpy = mvpy;
+    s.w = sz; s.h = sz; s.partSizeScale = (sz * sz) >> 4;
+    s.fenc = fencCtu + puy * 64 + pux;
+    s.fref = window + (int64_t)(puy - cy + p.R) * p.winW + (pux - cx + p.R + ex);
+    s.gfref = (const pixel*)p.refOrigins[ref] + (ctuX * 64 + pux) + (int64_t)(ctuY * 64 + puy) * p.refStride;
+    s.gstride = p.refStride;
+    int ox, oy;
+    int cost = motion_estimate<pixel>(s, mv2(cx - p.merange, cy - p.merange), mv2(cx + p.merange, cy + p.merange), mv2(mvpx, mvpy),
+                                      0, nullptr, p.merange, p.searchMethod, p.subpelRefine, 1, sz == 64, ox, oy);
+    if (perThread || lane == 0)
     {
-        if (p.puMask & 8) run_pu(3, (warp - 6) * 32 + lane);
-        return;
+        const int gx = ctuX * per + pux / sz, gy = ctuY * per + puy / sz;
+        int32_t* o = p.out + ((int64_t)ref * p.perRef + p.levelOff[level] + (int64_t)gy * (p.ctuCols * per) + gx) * 3;
+        o[0] = ox; o[1] = oy; o[2] = cost;
     }
-    if (warp == 0 && (p.puMask & 1)) run_pu(0, 0);
-    if (warp >= 1 && warp <= 4 && (p.puMask & 2)) run_pu(1, warp - 1);
-    if (p.puMask & 4)
-        for (;;)
-        {
-            int idx = 0;
-            if (lane == 0) idx = atomicAdd(q16, 1);
-            idx = __shfl_sync(0xffffffffu, idx, 0);
-            if (idx >= 16) break;
-            __syncwarp();
-            run_pu(2, idx);
-            __syncwarp();
-        }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
