@@ -187,6 +187,8 @@ int x265b200_me_frame_dev(x265b200_ctx* ctx, int depth, const void* curOrigin, i
                           const void* const* refOriginsHost, int numRefs, int64_t refStride,
                           int marginX, int marginY, int rowsTotal, int ctuCols, int ctuRows, int puMask,
                           const int32_t* mvpCtu, int searchMethod, int subpelRefine, int merange, double lambda, int32_t* out);
+/* profiling aid: cumulative busy cycles of the 8 warp roles of me_frame CTAs (out9[8] = number of CTAs) */
+int x265b200_debug_me_frame_cycles(x265b200_ctx* ctx, uint64_t* out9);
 /* The lambda-scaled MV cost table the kernels use (host side, no GPU needed):
  * out[2*32768 + i] = cost of a quarter-pel MV difference i, i in [-65536, 65536]. */
 int x265b200_bitcost_table(double lambda, uint16_t* out);

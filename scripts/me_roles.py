@@ -1,0 +1,20 @@
+"""per-role busy cycles of the me_frame kernel on a 2160p frame (profiling aid)."""
+import ctypes, importlib, os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench
+pkg = importlib.import_module("x265-yuuki-asuna_b200")
+ctx = pkg.Ctx(0)
+frames = bench.synth_frames(4)
+d = [ctx.to_device(f) for f in frames]
+origin = bench.PAD * bench.STRIDE + bench.PAD
+n = sum(bench.CTU_COLS * bench.CTU_ROWS * (1 << l) ** 2 for l in range(4))
+dOut = ctx.empty(3 * n * 12)
+for it in range(2):
+    ctx.me_frame_dev(8, d[3].ptr + origin, bench.STRIDE, [d[i].ptr + origin for i in range(3)], bench.STRIDE, bench.PAD, bench.PAD, bench.ROWS,
+                     bench.CTU_COLS, bench.CTU_ROWS, 15, None, pkg.ME_HEX, 2, 57, pkg.lambda_for_qp(30, 8), dOut)
+out = (ctypes.c_uint64 * 9)()
+ctx.L.x265b200_debug_me_frame_cycles(ctx.h, out)
+c = list(out)
+print("CTAs", c[8], "avg kcycles per role:", [round(v / max(c[8], 1) / 1e3, 1) for v in c[:8]])

@@ -88,6 +88,7 @@ int me_batch_dev(Ctx*, int depth, const void* fencPlane, int64_t fencStride, con
                  int64_t refStride, x265b200_me_job* jobs, int64_t n, int maxW, int maxH,
                  int searchMethod, int subpelRefine, int merange, double lambda, int maxSlices);
 void host_bitcost_table(double lambda, uint16_t* out);
+int debug_me_frame_cycles(unsigned long long* out);
 int me_frame_dev(Ctx*, int depth, const void* curOrigin, int64_t curStride, const void* const* refOriginsHost, int numRefs, int64_t refStride,
                  int marginX, int marginY, int rowsTotal, int ctuCols, int ctuRows, int puMask, const int32_t* mvpCtu,
                  int searchMethod, int subpelRefine, int merange, double lambda, int32_t* out);
@@ -351,6 +352,12 @@ int x265b200_me_frame_dev(x265b200_ctx* ctx, int depth, const void* curOrigin, i
     REQUIRE_CTX(ctx);
     return me_frame_dev(CTX(ctx), depth, curOrigin, curStride, refOriginsHost, numRefs, refStride, marginX, marginY, rowsTotal,
                         ctuCols, ctuRows, puMask, mvpCtu, searchMethod, subpelRefine, merange, lambda, out);
+}
+int x265b200_debug_me_frame_cycles(x265b200_ctx* ctx, uint64_t* out9)
+{
+    REQUIRE_CTX(ctx);
+    X265B200_CHECK(cudaStreamSynchronize(ctx->c.stream));
+    return debug_me_frame_cycles((unsigned long long*)out9);
 }
 int x265b200_bitcost_table(double lambda, uint16_t* out)
 {

@@ -74,6 +74,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 }
 
 constexpr int MF_WARPS = 8;
+// per-role busy cycles, accumulated by every CTA (profiling aid, read with x265b200_debug_me_frame_cycles)
+__device__ unsigned long long g_mfCycles[MF_WARPS + 1];
 
 // scratch (pred + immed) bytes for one search of PUs up to `s` pixels square
 __host__ __device__ inline size_t mf_scratch_bytes(int s, int px)
@@ -129,6 +131,7 @@ me_frame_kernel(const __grid_constant__ MEFrameMaps maps, MEFrameArgs p)
         tma_load_2d(fencCtu, &maps.cur, bar, ctuX * 64 + p.marginX, ctuY * 64 + p.marginY);
     }
     mbar_wait(bar, 0);
+    const long long tStart = clock64();
 
     // ---- role ------------------------------------------------------------------------------------------
     __align__(16) unsigned char tscratch[16 * 16 * sizeof(pixel) + 16 * 23 * 2];     // per-thread pred + immed (16x16 max)
@@ -168,6 +171,7 @@ me_frame_kernel(const __grid_constant__ MEFrameMaps maps, MEFrameArgs p)
         int32_t* o = p.out + ((int64_t)ref * p.perRef + p.levelOff[level] + (int64_t)gy * (p.ctuCols * per) + gx) * 3;
         o[0] = ox; o[1] = oy; o[2] = cost;
     }
+    if (lane == 0) { atomicAdd(&g_mfCycles[warp], (unsigned long long)(clock64() - tStart)); if (warp == 0) atomicAdd(&g_mfCycles[MF_WARPS], 1ull); }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -216,7 +220,15 @@ int me_frame_dev(Ctx* ctx, int depth, const void* curOrigin, int64_t curStride, 
     int winW = 64 + 2 * R + (16 / px - 1);            // + slack for the 16-byte alignment of the TMA box start
     // pitch: a multiple of 16 bytes whose word count is 4 mod 8 -> 8 consecutive rows hit distinct bank groups
     int pitchBytes = ((winW * px + 15) / 16) * 16;
-    while (((pitchBytes / 4) % 8) != 4) pitchBytes += 16;
+    // prefer a pitch whose word count is 4 mod 8 (8 consecutive rows in distinct bank groups) unless that would push
+    // the CTA past a third of the SM's shared memory (3 resident CTAs matter more than 2-way conflicts)
+    {
+        int alt = pitchBytes;
+        while (((alt / 4) % 8) != 4) alt += 16;
+        size_t fixedBytes = (size_t)64 * 64 * px + mf_total_scratch(px) + 16 + 1024;
+        if ((((size_t)alt * (64 + 2 * R) + 127) & ~(size_t)127) + fixedBytes <= 233472 / 3) pitchBytes = alt;
+        else if (((pitchBytes / 4) % 32) == 0) pitchBytes += 16;
+    }
     winW = pitchBytes / px;
     const int winH = 64 + 2 * R;
     if (winW > 256 || winH > 256) { set_error("me_frame: merange %d needs a %dx%d window, above the 256-element TMA box limit; use x265b200_me_batch_dev", merange, winW, winH); return -1; }
@@ -261,6 +273,12 @@ int me_frame_dev(Ctx* ctx, int depth, const void* curOrigin, int64_t curStride, 
     }
     ctx->launches++;
     return check(cudaGetLastError(), "me_frame kernel launch");
+}
+
+int debug_me_frame_cycles(unsigned long long* out)
+{
+    X265B200_CHECK(cudaMemcpyFromSymbol(out, g_mfCycles, sizeof(unsigned long long) * (MF_WARPS + 1)));
+    return 0;
 }
 
 } // namespace x265b200
