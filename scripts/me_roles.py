@@ -14,7 +14,8 @@ dOut = ctx.empty(3 * n * 12)
 for it in range(2):
     ctx.me_frame_dev(8, d[3].ptr + origin, bench.STRIDE, [d[i].ptr + origin for i in range(3)], bench.STRIDE, bench.PAD, bench.PAD, bench.ROWS,
                      bench.CTU_COLS, bench.CTU_ROWS, 15, None, pkg.ME_HEX, 2, 57, pkg.lambda_for_qp(30, 8), dOut)
-out = (ctypes.c_uint64 * 9)()
+NW = 7   # MF_WARPS in csrc/me_frame_kernels.cu
+out = (ctypes.c_uint64 * (NW + 1))()
 ctx.L.x265b200_debug_me_frame_cycles(ctx.h, out)
 c = list(out)
-print("CTAs", c[8], "avg kcycles per role:", [round(v / max(c[8], 1) / 1e3, 1) for v in c[:8]])
+print("CTAs", c[NW], "avg kcycles per role:", [round(v / max(c[NW], 1) / 1e3, 1) for v in c[:NW]])

@@ -49,7 +49,9 @@ struct MEState
     int64_t  gstride;
     const pixel* lowres[4];   // lowres hpel planes + blockOffset (isLowres path), else unused
     bool     isLowres;
-    bool     perThread;   // true: ONE THREAD runs the whole search (small PUs); false: one warp (lanes cooperate)
+    bool     perThread;   // true: ONE THREAD runs the whole search on its (sub-)block; false: one warp (lanes cooperate)
+    int      groupSize;   // perThread only: 1, or 2/4 lanes that each own a sub-block of the PU and sum their costs
+    unsigned groupMask;   // lanes of this group (shuffle mask)
     int      w, h, lane, depth, partSizeScale;
     const uint16_t* cost;     // centred lambda-scaled MV cost table (bitcost.cpp:31-60)
     int      mvpx, mvpy;      // setMVP(qmvp), bitcost.h:41
@@ -160,7 +162,16 @@ template<> __device__ __forceinline__ void unpack4<uint16_t>(const uint32_t* w, 
 }
 
 
-// ---- per-thread primitives (perThread mode: no shuffles, no __syncwarp; used for 8x8 / 16x16 PUs) -----------
+// ---- per-thread primitives (perThread mode: no full-warp shuffles, no __syncwarp; used for 8x8 / 16x16 PUs) ----
+// A PU may be split over groupSize = 2 or 4 adjacent lanes, each owning a sub-block (SAD and SATD are additive over
+// sub-blocks of 4x4 cells): the lanes of a group compute identical totals, so they follow the same control flow.
+template<typename pixel>
+__device__ __forceinline__ int group_sum(const MEState<pixel>& s, int v)
+{
+    for (int o = 1; o < s.groupSize; o <<= 1) v += __shfl_xor_sync(s.groupMask, v, o);
+    return v;
+}
+
 template<typename pixel, int SEG>
 __device__ __forceinline__ int thread_sad_one(const MEState<pixel>& s, const pixel* r, int64_t rs)
 {
@@ -216,7 +227,7 @@ __device__ __noinline__ void warp_sad_k(const MEState<pixel>& s, int K, const in
     if (s.perThread)
     {
         for (int k = 0; k < K; k++)
-            costs[k] = thread_sad_any<pixel>(s, s.fref + ox[k] + (int64_t)oy[k] * s.stride, s.stride);
+            costs[k] = group_sum<pixel>(s, thread_sad_any<pixel>(s, s.fref + ox[k] + (int64_t)oy[k] * s.stride, s.stride));
         return;
     }
     if (!(s.w & 15))     sad_k_impl<pixel, 16>(s, K, ox, oy, costs);
@@ -228,7 +239,7 @@ __device__ __noinline__ void warp_sad_k(const MEState<pixel>& s, int K, const in
 template<typename pixel>
 __device__ __noinline__ int warp_sad_block(const MEState<pixel>& s, const pixel* r, int64_t rs)
 {
-    if (s.perThread) return thread_sad_any<pixel>(s, r, rs);
+    if (s.perThread) return group_sum<pixel>(s, thread_sad_any<pixel>(s, r, rs));
     const int gw = s.w >> 2, ng = gw * s.h;
     int acc = 0;
     for (int u = s.lane; u < ng; u += 32)
@@ -243,7 +254,7 @@ __device__ __noinline__ int warp_sad_block(const MEState<pixel>& s, const pixel*
 template<typename pixel>
 __device__ __noinline__ int warp_satd(const MEState<pixel>& s, const pixel* r, int64_t rs)
 {
-    if (s.perThread) return thread_satd<pixel>(s, r, rs);
+    if (s.perThread) return group_sum<pixel>(s, thread_satd<pixel>(s, r, rs));
     constexpr int NW = 4 * (int)sizeof(pixel) / 4;
     const int cw = s.w >> 2, nc = cw * (s.h >> 2);
     int acc = 0;

@@ -73,7 +73,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
         "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
-constexpr int MF_WARPS = 8;
+constexpr int MF_WARPS = 7;
 // per-role busy cycles, accumulated by every CTA (profiling aid, read with x265b200_debug_me_frame_cycles)
 __device__ unsigned long long g_mfCycles[MF_WARPS + 1];
 
@@ -84,19 +84,20 @@ __host__ __device__ inline size_t mf_scratch_bytes(int s, int px)
     size_t immed = ((size_t)s * (s + 7) * 2 + 15) & ~(size_t)15;
     return pred + immed;
 }
-// CTA roles (8 warps): warp 0 = the 64x64 PU (warp-cooperative); warps 1-4 = one 32x32 PU each
-// (warp-cooperative); warp 5 lanes 0-15 = the sixteen 16x16 PUs, ONE THREAD per search; warps 6-7 = the
-// sixty-four 8x8 PUs, one thread per search.  Small PUs have too few pixels to feed 32 lanes, so running the
-// whole bit-exact search per thread removes every shuffle/broadcast and keeps all lanes busy.
+// CTA roles (7 warps, balanced to ~0.6 M busy cycles each on 2160p): warp 0 = the 64x64 PU (warp-cooperative);
+// warps 1-2 = two 32x32 PUs each (warp-cooperative); warps 3-4 = the sixteen 16x16 PUs, FOUR lanes per PU (each
+// lane runs the whole bit-exact search on its 8x8 quadrant, SAD/SATD summed over the quad with 2 shuffles);
+// warps 5-6 = the sixty-four 8x8 PUs, one lane per search.  Small PUs have too few pixels to feed 32 lanes, so
+// running the search per thread removes the warp-wide shuffles/broadcasts and keeps all lanes busy.
 // shared-memory scratch: only the warp-cooperative roles; per-thread searches keep pred/immed in their own
 // (L1-cached) local memory, which keeps the CTA at ~73 KB so three CTAs fit an SM.
 __host__ __device__ inline size_t mf_total_scratch(int px)
 {
-    return mf_scratch_bytes(64, px) + 4 * mf_scratch_bytes(32, px);
+    return mf_scratch_bytes(64, px) + 2 * mf_scratch_bytes(32, px);
 }
 
 template<typename pixel>
-__global__ void __launch_bounds__(MF_WARPS * 32)
+__global__ void __launch_bounds__(MF_WARPS * 32, 3)
 me_frame_kernel(const __grid_constant__ MEFrameMaps maps, MEFrameArgs p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -133,44 +134,59 @@ me_frame_kernel(const __grid_constant__ MEFrameMaps maps, MEFrameArgs p)
     mbar_wait(bar, 0);
     const long long tStart = clock64();
 
-    // ---- role ------------------------------------------------------------------------------------------
-    __align__(16) unsigned char tscratch[16 * 16 * sizeof(pixel) + 16 * 23 * 2];     // per-thread pred + immed (16x16 max)
-    int level, idx; bool perThread; size_t soff;
-    if (warp == 0)      { level = 0; idx = 0; perThread = false; soff = 0; }
-    else if (warp <= 4) { level = 1; idx = warp - 1; perThread = false; soff = mf_scratch_bytes(64, px) + (size_t)(warp - 1) * mf_scratch_bytes(32, px); }
-    else if (warp == 5)
-    {
-        level = 2; idx = lane; perThread = true; soff = 0;
-        if (lane >= 16) return;
-    }
-    else
-    {
-        level = 3; idx = (warp - 6) * 32 + lane; perThread = true; soff = 0;
-    }
-    if (!(p.puMask & (1 << level))) return;
-    const int sz = 64 >> level, per = 1 << level;
-    const int puy = (idx / per) * sz, pux = (idx % per) * sz;
-
+    // ---- roles (7 warps, each ~0.5 M cycles of work; measured with g_mfCycles) -------------------------------------
+    //  warp 0      : the 64x64 PU, warp-cooperative
+    //  warps 1-2   : two 32x32 PUs each, warp-cooperative
+    //  warps 3-4   : the sixteen 16x16 PUs, FOUR lanes per PU (each lane runs the search on its 8x8 quadrant, costs
+    //                summed over the quad with shuffles)
+    //  warps 5-6   : the sixty-four 8x8 PUs, one lane per PU
+    __align__(16) unsigned char tscratch[8 * 8 * sizeof(pixel) + 8 * 15 * 2];     // per-lane pred + immed (8x8 sub-block)
+    const bool perThread = warp >= 3;
     MEState<pixel> s;
-    unsigned char* myScratch = perThread ? tscratch : scratch + soff;
-    s.pred = (pixel*)myScratch;
-    s.immed = (int16_t*)(myScratch + (((size_t)sz * sz * px + 15) & ~(size_t)15));
     s.stride = p.winW; s.isLowres = false; s.perThread = perThread; s.lane = perThread ? 0 : lane; s.depth = p.depth;
-    s.cost = p.cost + 2 * 32768; s.mvpx = mvpx; s.mvpy = mvpy;
-    s.w = sz; s.h = sz; s.partSizeScale = (sz * sz) >> 4;
-    s.fenc = fencCtu + puy * 64 + pux;
-    s.fref = window + (int64_t)(puy - cy + p.R) * p.winW + (pux - cx + p.R + ex);
-    s.gfref = (const pixel*)p.refOrigins[ref] + (ctuX * 64 + pux) + (int64_t)(ctuY * 64 + puy) * p.refStride;
-    s.gstride = p.refStride;
-    int ox, oy;
-    int cost = motion_estimate<pixel>(s, mv2(cx - p.merange, cy - p.merange), mv2(cx + p.merange, cy + p.merange), mv2(mvpx, mvpy),
-                                      0, nullptr, p.merange, p.searchMethod, p.subpelRefine, 1, sz == 64, ox, oy);
-    if (perThread || lane == 0)
+    s.cost = p.cost + 2 * 32768; s.mvpx = mvpx; s.mvpy = mvpy; s.gstride = p.refStride;
+    s.groupSize = 1; s.groupMask = 0xffffffffu;
+    const size_t soff = warp == 0 ? 0 : mf_scratch_bytes(64, px) + (size_t)(warp - 1) * mf_scratch_bytes(32, px);
+    unsigned char* myScratch = perThread ? tscratch : scratch + soff;
+
+    // sub: search block size handled by this lane/warp; (sx, sy): its offset inside the PU; writer: lane that stores the result
+    auto run_pu = [&](int level, int idx, int sub, int sx, int sy, bool writer) {
+        const int sz = 64 >> level, per = 1 << level;
+        const int puy = (idx / per) * sz, pux = (idx % per) * sz;
+        s.pred = (pixel*)myScratch;
+        s.immed = (int16_t*)(myScratch + (((size_t)sub * sub * px + 15) & ~(size_t)15));
+        s.w = sub; s.h = sub; s.partSizeScale = (sz * sz) >> 4;
+        s.fenc = fencCtu + (puy + sy) * 64 + pux + sx;
+        s.fref = window + (int64_t)(puy + sy - cy + p.R) * p.winW + (pux + sx - cx + p.R + ex);
+        s.gfref = (const pixel*)p.refOrigins[ref] + (ctuX * 64 + pux + sx) + (int64_t)(ctuY * 64 + puy + sy) * p.refStride;
+        int ox, oy;
+        int cost = motion_estimate<pixel>(s, mv2(cx - p.merange, cy - p.merange), mv2(cx + p.merange, cy + p.merange), mv2(mvpx, mvpy),
+                                          0, nullptr, p.merange, p.searchMethod, p.subpelRefine, 1, sz == 64, ox, oy);
+        if (writer)
+        {
+            const int gx = ctuX * per + pux / sz, gy = ctuY * per + puy / sz;
+            int32_t* o = p.out + ((int64_t)ref * p.perRef + p.levelOff[level] + (int64_t)gy * (p.ctuCols * per) + gx) * 3;
+            o[0] = ox; o[1] = oy; o[2] = cost;
+        }
+    };
+
+    // one call site (motion_estimate is large; several inlined copies cost registers)
+    int level, idx, n = 1, sub, sx = 0, sy = 0; bool writer = lane == 0;
+    if (warp == 0)      { level = 0; idx = 0; sub = 64; }
+    else if (warp <= 2) { level = 1; idx = (warp - 1) * 2; n = 2; sub = 32; }
+    else if (warp <= 4)
     {
-        const int gx = ctuX * per + pux / sz, gy = ctuY * per + puy / sz;
-        int32_t* o = p.out + ((int64_t)ref * p.perRef + p.levelOff[level] + (int64_t)gy * (p.ctuCols * per) + gx) * 3;
-        o[0] = ox; o[1] = oy; o[2] = cost;
+        const int q = lane & 3;
+        level = 2; idx = (warp - 3) * 8 + (lane >> 2); sub = 8; sx = (q & 1) * 8; sy = (q >> 1) * 8; writer = q == 0;
+        s.groupSize = 4; s.groupMask = 0xfu << (lane & ~3);
     }
+    else                { level = 3; idx = (warp - 5) * 32 + lane; sub = 8; writer = true; }
+    if ((p.puMask >> level) & 1)
+        for (int i = 0; i < n; i++)
+        {
+            run_pu(level, idx + i, sub, sx, sy, writer);
+            if (!perThread) __syncwarp();
+        }
     if (lane == 0) { atomicAdd(&g_mfCycles[warp], (unsigned long long)(clock64() - tStart)); if (warp == 0) atomicAdd(&g_mfCycles[MF_WARPS], 1ull); }
 }
 

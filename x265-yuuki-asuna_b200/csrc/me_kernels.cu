@@ -89,7 +89,7 @@ me_batch_kernel(MEArgs p)
     const pixel* refPlane = (const pixel*)(p.refPlanes ? p.refPlanes[job.refIdx] : p.refPlane0);
     s.fref = refPlane + job.puX + (int64_t)job.puY * p.refStride;
     s.gfref = s.fref; s.gstride = p.refStride;
-    s.isLowres = false; s.perThread = false;
+    s.isLowres = false; s.perThread = false; s.groupSize = 1; s.groupMask = 0xffffffffu;
     s.w = job.w; s.h = job.h; s.lane = lane; s.depth = p.depth;
     s.partSizeScale = (job.h * job.h) >> 4;                      // motion.cpp:125-126 sizeScale
     s.cost = p.cost + 2 * 32768;
