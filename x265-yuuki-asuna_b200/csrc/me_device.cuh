@@ -9,7 +9,19 @@
 #include "common.cuh"
 #include "tables.cuh"
 
+// A translation unit whose searches ALL run in per-thread mode defines ME_FORCE_THREAD before including this header:
+// the warp-cooperative bodies are then compiled out (smaller kernel, see me_frame_kernels.cu).  The variant lives in
+// its own inline namespace so the differently-compiled templates never share a symbol.
+#ifdef ME_FORCE_THREAD
+#define ME_IS_THREAD(s) true
+#define ME_VARIANT me_thread_only
+#else
+#define ME_IS_THREAD(s) ((s).perThread)
+#define ME_VARIANT me_generic
+#endif
+
 namespace x265b200 {
+inline namespace ME_VARIANT {
 
 enum { ME_DIA = 0, ME_HEX = 1, ME_UMH = 2, ME_STAR = 3, ME_SEA = 4, ME_FULL = 5 };   // x265.h:492-497
 #define ME_COST_MAX (1 << 28)                                                       // motion.h:65
@@ -79,17 +91,9 @@ __device__ __forceinline__ void ld_words(const pixel* p, uint32_t out[NW])
     uint32_t t[NW + 1];
 #pragma unroll
     for (int i = 0; i < NW; i++) t[i] = w[i];
-    if (sh)
-    {
-        t[NW] = w[NW];
+    t[NW] = sh ? w[NW] : 0u;             // predicated: never touches the word after an aligned run
 #pragma unroll
-        for (int i = 0; i < NW; i++) out[i] = __funnelshift_r(t[i], t[i + 1], sh);
-    }
-    else
-    {
-#pragma unroll
-        for (int i = 0; i < NW; i++) out[i] = t[i];
-    }
+    for (int i = 0; i < NW; i++) out[i] = __funnelshift_r(t[i], t[i + 1], sh);
 }
 
 template<typename pixel> __device__ __forceinline__ uint32_t sad_word(uint32_t a, uint32_t b);
@@ -193,7 +197,9 @@ __device__ __forceinline__ int thread_satd(const MEState<pixel>& s, const pixel*
 {
     constexpr int NW = 4 * (int)sizeof(pixel) / 4;
     int acc = 0;
+#pragma unroll 1
     for (int cy = 0; cy < s.h; cy += 4)
+#pragma unroll 1
         for (int cx = 0; cx < s.w; cx += 4)
         {
             int d[4][4];
@@ -224,7 +230,7 @@ __device__ __forceinline__ int thread_satd(const MEState<pixel>& s, const pixel*
 template<typename pixel>
 __device__ __noinline__ void warp_sad_k(const MEState<pixel>& s, int K, const int ox[4], const int oy[4], int costs[4])
 {
-    if (s.perThread)
+    if (ME_IS_THREAD(s))
     {
         for (int k = 0; k < K; k++)
             costs[k] = group_sum<pixel>(s, thread_sad_any<pixel>(s, s.fref + ox[k] + (int64_t)oy[k] * s.stride, s.stride));
@@ -239,7 +245,7 @@ __device__ __noinline__ void warp_sad_k(const MEState<pixel>& s, int K, const in
 template<typename pixel>
 __device__ __noinline__ int warp_sad_block(const MEState<pixel>& s, const pixel* r, int64_t rs)
 {
-    if (s.perThread) return group_sum<pixel>(s, thread_sad_any<pixel>(s, r, rs));
+    if (ME_IS_THREAD(s)) return group_sum<pixel>(s, thread_sad_any<pixel>(s, r, rs));
     const int gw = s.w >> 2, ng = gw * s.h;
     int acc = 0;
     for (int u = s.lane; u < ng; u += 32)
@@ -254,10 +260,11 @@ __device__ __noinline__ int warp_sad_block(const MEState<pixel>& s, const pixel*
 template<typename pixel>
 __device__ __noinline__ int warp_satd(const MEState<pixel>& s, const pixel* r, int64_t rs)
 {
-    if (s.perThread) return group_sum<pixel>(s, thread_satd<pixel>(s, r, rs));
+    if (ME_IS_THREAD(s)) return group_sum<pixel>(s, thread_satd<pixel>(s, r, rs));
     constexpr int NW = 4 * (int)sizeof(pixel) / 4;
     const int cw = s.w >> 2, nc = cw * (s.h >> 2);
     int acc = 0;
+#pragma unroll 1
     for (int c = s.lane; c < nc; c += 32)
     {
         int cy = c / cw, cx = c - cy * cw;
@@ -340,13 +347,14 @@ __device__ __noinline__ void warp_interp_luma(const MEState<pixel>& s, const pix
     constexpr int NW12 = 12 * (int)sizeof(pixel) / 4, NW4 = 4 * (int)sizeof(pixel) / 4;
     const int w = s.w, h = s.h, maxVal = (1 << s.depth) - 1, headRoom = 14 - s.depth;
     const int gw = w >> 2;
-    const int u0 = s.perThread ? 0 : s.lane, du = s.perThread ? 1 : 32;
+    const int u0 = ME_IS_THREAD(s) ? 0 : s.lane, du = ME_IS_THREAD(s) ? 1 : 32;
     int c[8];
     if (!yFrac)
     {
         // luma_hpp : ipfilter.cpp:79-118
 #pragma unroll
         for (int t = 0; t < 8; t++) c[t] = c_meLumaFilter[xFrac][t];
+#pragma unroll 1
         for (int u = u0; u < gw * h; u += du)
         {
             int y = u / gw, x = (u - y * gw) << 2;
@@ -379,6 +387,7 @@ __device__ __noinline__ void warp_interp_luma(const MEState<pixel>& s, const pix
         // and reused by the 4 output rows (sliding window) instead of 8 loads per output row.
 #pragma unroll
         for (int t = 0; t < 8; t++) c[t] = c_meLumaFilter[yFrac][t];
+#pragma unroll 1
         for (int u = u0; u < gw * (h >> 2); u += du)
         {
             const int rb = u / gw, x = (u - rb * gw) << 2, y0 = rb << 2;
@@ -413,6 +422,7 @@ __device__ __noinline__ void warp_interp_luma(const MEState<pixel>& s, const pix
 #pragma unroll
         for (int t = 0; t < 8; t++) c[t] = c_meLumaFilter[xFrac][t];
         const int shift = 6 - headRoom, offset = (int)((unsigned)-8192 << shift);
+#pragma unroll 1
         for (int u = u0; u < gw * (h + 7); u += du)
         {
             int y = u / gw, x = (u - y * gw) << 2;
@@ -437,10 +447,11 @@ __device__ __noinline__ void warp_interp_luma(const MEState<pixel>& s, const pix
             d[0] = (uint32_t)(o[0] & 0xffff) | ((uint32_t)o[1] << 16);
             d[1] = (uint32_t)(o[2] & 0xffff) | ((uint32_t)o[3] << 16);
         }
-        if (!s.perThread) __syncwarp();
+        if (!ME_IS_THREAD(s)) __syncwarp();
 #pragma unroll
         for (int t = 0; t < 8; t++) c[t] = c_meLumaFilter[yFrac][t];
         const int shift2 = 6 + headRoom, offset2 = (1 << (shift2 - 1)) + (8192 << 6);
+#pragma unroll 1
         for (int u = u0; u < gw * (h >> 2); u += du)
         {
             const int rb = u / gw, x = (u - rb * gw) << 2, y0 = rb << 2;
@@ -470,7 +481,7 @@ __device__ __noinline__ void warp_interp_luma(const MEState<pixel>& s, const pix
             }
         }
     }
-    if (!s.perThread) __syncwarp();
+    if (!ME_IS_THREAD(s)) __syncwarp();
 }
 
 // MotionEstimate::subpelCompare (motion.cpp:1571-1599); useSatd selects cmp
@@ -481,10 +492,10 @@ __device__ __noinline__ int subpel_compare(const MEState<pixel>& s, int qx, int 
     const int xFrac = qx & 3, yFrac = qy & 3;
     if (!(xFrac | yFrac))
         return useSatd ? warp_satd<pixel>(s, fref, s.stride) : warp_sad_block<pixel>(s, fref, s.stride);
-    if (!s.perThread) __syncwarp();
+    if (!ME_IS_THREAD(s)) __syncwarp();
     warp_interp_luma<pixel>(s, fref, xFrac, yFrac);
     int c = useSatd ? warp_satd<pixel>(s, s.pred, s.w) : warp_sad_block<pixel>(s, s.pred, s.w);
-    if (!s.perThread) __syncwarp();
+    if (!ME_IS_THREAD(s)) __syncwarp();
     return c;
 }
 
@@ -1073,4 +1084,5 @@ __device__ int motion_estimate(const MEState<pixel>& s, MV2 mvmin, MV2 mvmax, MV
     return bcost;
 }
 
+} // inline namespace ME_VARIANT
 } // namespace x265b200

@@ -12,6 +12,7 @@
 // Per-PU semantics: motionEstimate(ref, mvmin = (mvp>>2) - merange, mvmax = (mvp>>2) + merange, qmvp = mvp,
 // numCandidates = 0, merange, ...) with the CTU's predictor mvp shared by all its PUs (Search::setSearchRange
 // shape, search.cpp:2724-2769, before picture-boundary clipping).
+#define ME_FORCE_THREAD 1
 #include "me_device.cuh"
 #include "x265b200.h"
 #include <cuda.h>
@@ -73,31 +74,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
         "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
-constexpr int MF_WARPS = 7;
+constexpr int MF_WARPS = 4;
 // per-role busy cycles, accumulated by every CTA (profiling aid, read with x265b200_debug_me_frame_cycles)
 __device__ unsigned long long g_mfCycles[MF_WARPS + 1];
 
-// scratch (pred + immed) bytes for one search of PUs up to `s` pixels square
-__host__ __device__ inline size_t mf_scratch_bytes(int s, int px)
-{
-    size_t pred = ((size_t)s * s * px + 15) & ~(size_t)15;
-    size_t immed = ((size_t)s * (s + 7) * 2 + 15) & ~(size_t)15;
-    return pred + immed;
-}
-// CTA roles (7 warps, balanced to ~0.6 M busy cycles each on 2160p): warp 0 = the 64x64 PU (warp-cooperative);
-// warps 1-2 = two 32x32 PUs each (warp-cooperative); warps 3-4 = the sixteen 16x16 PUs, FOUR lanes per PU (each
-// lane runs the whole bit-exact search on its 8x8 quadrant, SAD/SATD summed over the quad with 2 shuffles);
-// warps 5-6 = the sixty-four 8x8 PUs, one lane per search.  Small PUs have too few pixels to feed 32 lanes, so
-// running the search per thread removes the warp-wide shuffles/broadcasts and keeps all lanes busy.
-// shared-memory scratch: only the warp-cooperative roles; per-thread searches keep pred/immed in their own
-// (L1-cached) local memory, which keeps the CTA at ~73 KB so three CTAs fit an SM.
-__host__ __device__ inline size_t mf_total_scratch(int px)
-{
-    return mf_scratch_bytes(64, px) + 2 * mf_scratch_bytes(32, px);
-}
-
+// CTA roles (4 warps).  EVERY search runs in per-thread mode: a lane owns an 8-pixel-wide sub-block of the PU, runs the
+// whole bit-exact search on it and the lanes of one PU sum their SAD/SATD partials with shuffles (they then hold
+// identical costs and follow identical control flow).  One code path for all PU sizes keeps the hot code inside the
+// instruction cache: with warp-cooperative 64x64/32x32 roles next to per-thread 16x16/8x8 roles the profile showed
+// 42% of warp time in stall_no_instruction (profiles/r01_me_frame_roles.txt), each role alone < 3%.
+//   warp 0 : the 64x64 PU, 32 lanes x (8 wide x 16 tall)
+//   warp 1 : the four 32x32 PUs, two at a time, 16 lanes x 8x8 each
+//   warp 2 : the sixteen 16x16 PUs, eight at a time, 4 lanes x 8x8 each
+//   warp 3 : the sixty-four 8x8 PUs, thirty-two at a time, one lane each
+// No shared-memory scratch: pred/immed of a sub-block live in the lane's local memory.
+constexpr int MF_SUBH_MAX = 16;
 template<typename pixel>
-__global__ void __launch_bounds__(MF_WARPS * 32, 3)
+__global__ void __launch_bounds__(MF_WARPS * 32, 4)
 me_frame_kernel(const __grid_constant__ MEFrameMaps maps, MEFrameArgs p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -105,8 +98,7 @@ me_frame_kernel(const __grid_constant__ MEFrameMaps maps, MEFrameArgs p)
     const size_t winBytes = ((size_t)p.winW * p.winH * px + 127) & ~(size_t)127;
     pixel* window = (pixel*)smem;
     pixel* fencCtu = (pixel*)(smem + winBytes);
-    unsigned char* scratch = smem + winBytes + 64 * 64 * px;
-    uint64_t* bar = (uint64_t*)(scratch + mf_total_scratch(px));
+    uint64_t* bar = (uint64_t*)(smem + winBytes + 64 * 64 * px);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     const int ctu = blockIdx.x, ref = blockIdx.y;
@@ -134,59 +126,48 @@ me_frame_kernel(const __grid_constant__ MEFrameMaps maps, MEFrameArgs p)
     mbar_wait(bar, 0);
     const long long tStart = clock64();
 
-    // ---- roles (7 warps, each ~0.5 M cycles of work; measured with g_mfCycles) -------------------------------------
-    //  warp 0      : the 64x64 PU, warp-cooperative
-    //  warps 1-2   : two 32x32 PUs each, warp-cooperative
-    //  warps 3-4   : the sixteen 16x16 PUs, FOUR lanes per PU (each lane runs the search on its 8x8 quadrant, costs
-    //                summed over the quad with shuffles)
-    //  warps 5-6   : the sixty-four 8x8 PUs, one lane per PU
-    __align__(16) unsigned char tscratch[8 * 8 * sizeof(pixel) + 8 * 15 * 2];     // per-lane pred + immed (8x8 sub-block)
-    const bool perThread = warp >= 3;
+    // ---- roles ---------------------------------------------------------------------------------------------------
+    __align__(16) unsigned char tscratch[8 * MF_SUBH_MAX * sizeof(pixel) + 8 * (MF_SUBH_MAX + 7) * 2];   // per-lane pred + immed
     MEState<pixel> s;
-    s.stride = p.winW; s.isLowres = false; s.perThread = perThread; s.lane = perThread ? 0 : lane; s.depth = p.depth;
+    s.stride = p.winW; s.isLowres = false; s.perThread = true; s.lane = 0; s.depth = p.depth;
     s.cost = p.cost + 2 * 32768; s.mvpx = mvpx; s.mvpy = mvpy; s.gstride = p.refStride;
-    s.groupSize = 1; s.groupMask = 0xffffffffu;
-    const size_t soff = warp == 0 ? 0 : mf_scratch_bytes(64, px) + (size_t)(warp - 1) * mf_scratch_bytes(32, px);
-    unsigned char* myScratch = perThread ? tscratch : scratch + soff;
 
-    // sub: search block size handled by this lane/warp; (sx, sy): its offset inside the PU; writer: lane that stores the result
-    auto run_pu = [&](int level, int idx, int sub, int sx, int sy, bool writer) {
-        const int sz = 64 >> level, per = 1 << level;
-        const int puy = (idx / per) * sz, pux = (idx % per) * sz;
-        s.pred = (pixel*)myScratch;
-        s.immed = (int16_t*)(myScratch + (((size_t)sub * sub * px + 15) & ~(size_t)15));
-        s.w = sub; s.h = sub; s.partSizeScale = (sz * sz) >> 4;
-        s.fenc = fencCtu + (puy + sy) * 64 + pux + sx;
-        s.fref = window + (int64_t)(puy + sy - cy + p.R) * p.winW + (pux + sx - cx + p.R + ex);
-        s.gfref = (const pixel*)p.refOrigins[ref] + (ctuX * 64 + pux + sx) + (int64_t)(ctuY * 64 + puy + sy) * p.refStride;
-        int ox, oy;
-        int cost = motion_estimate<pixel>(s, mv2(cx - p.merange, cy - p.merange), mv2(cx + p.merange, cy + p.merange), mv2(mvpx, mvpy),
-                                          0, nullptr, p.merange, p.searchMethod, p.subpelRefine, 1, sz == 64, ox, oy);
-        if (writer)
-        {
-            const int gx = ctuX * per + pux / sz, gy = ctuY * per + puy / sz;
-            int32_t* o = p.out + ((int64_t)ref * p.perRef + p.levelOff[level] + (int64_t)gy * (p.ctuCols * per) + gx) * 3;
-            o[0] = ox; o[1] = oy; o[2] = cost;
-        }
-    };
+    // level = log2(64 / PU size); per round a warp searches 32 / lanesPerPu PUs; lane q of a PU owns sub-block (sx, sy)
+    const int level = warp, rounds = warp == 0 ? 1 : 2;
+    const int lanesLog2 = warp == 0 ? 5 : 6 - 2 * warp;                   // 32, 16, 4, 1 lanes per PU
+    const int q = lane & ((1 << lanesLog2) - 1), pusPerRound = 32 >> lanesLog2;
+    const int subH = warp == 0 ? 16 : 8;
+    const int subCols = warp == 0 ? 8 : (8 >> warp);                       // sub-blocks per PU row: 8, 4, 2, 1
+    const int sx = (q % subCols) * 8, sy = (q / subCols) * subH;
+    s.groupSize = 1 << lanesLog2;
+    s.groupMask = lanesLog2 == 5 ? 0xffffffffu : (((1u << (1 << lanesLog2)) - 1u) << (lane & ~((1 << lanesLog2) - 1)));
+    s.pred = (pixel*)tscratch;
+    s.immed = (int16_t*)(tscratch + 8 * MF_SUBH_MAX * sizeof(pixel));
+    s.w = 8; s.h = subH;
 
-    // one call site (motion_estimate is large; several inlined copies cost registers)
-    int level, idx, n = 1, sub, sx = 0, sy = 0; bool writer = lane == 0;
-    if (warp == 0)      { level = 0; idx = 0; sub = 64; }
-    else if (warp <= 2) { level = 1; idx = (warp - 1) * 2; n = 2; sub = 32; }
-    else if (warp <= 4)
-    {
-        const int q = lane & 3;
-        level = 2; idx = (warp - 3) * 8 + (lane >> 2); sub = 8; sx = (q & 1) * 8; sy = (q >> 1) * 8; writer = q == 0;
-        s.groupSize = 4; s.groupMask = 0xfu << (lane & ~3);
-    }
-    else                { level = 3; idx = (warp - 5) * 32 + lane; sub = 8; writer = true; }
     if ((p.puMask >> level) & 1)
-        for (int i = 0; i < n; i++)
+    {
+        const int sz = 64 >> level, per = 1 << level;
+        s.partSizeScale = (sz * sz) >> 4;
+#pragma unroll 1
+        for (int i = 0; i < rounds; i++)
         {
-            run_pu(level, idx + i, sub, sx, sy, writer);
-            if (!perThread) __syncwarp();
+            const int idx = i * pusPerRound + (lane >> lanesLog2);
+            const int puy = (idx / per) * sz, pux = (idx % per) * sz;
+            s.fenc = fencCtu + (puy + sy) * 64 + pux + sx;
+            s.fref = window + (int64_t)(puy + sy - cy + p.R) * p.winW + (pux + sx - cx + p.R + ex);
+            s.gfref = (const pixel*)p.refOrigins[ref] + (ctuX * 64 + pux + sx) + (int64_t)(ctuY * 64 + puy + sy) * p.refStride;
+            int ox, oy;
+            int cost = motion_estimate<pixel>(s, mv2(cx - p.merange, cy - p.merange), mv2(cx + p.merange, cy + p.merange), mv2(mvpx, mvpy),
+                                              0, nullptr, p.merange, p.searchMethod, p.subpelRefine, 1, sz == 64, ox, oy);
+            if (q == 0)
+            {
+                const int gx = ctuX * per + pux / sz, gy = ctuY * per + puy / sz;
+                int32_t* o = p.out + ((int64_t)ref * p.perRef + p.levelOff[level] + (int64_t)gy * (p.ctuCols * per) + gx) * 3;
+                o[0] = ox; o[1] = oy; o[2] = cost;
+            }
         }
+    }
     if (lane == 0) { atomicAdd(&g_mfCycles[warp], (unsigned long long)(clock64() - tStart)); if (warp == 0) atomicAdd(&g_mfCycles[MF_WARPS], 1ull); }
 }
 
@@ -237,12 +218,12 @@ int me_frame_dev(Ctx* ctx, int depth, const void* curOrigin, int64_t curStride, 
     // pitch: a multiple of 16 bytes whose word count is 4 mod 8 -> 8 consecutive rows hit distinct bank groups
     int pitchBytes = ((winW * px + 15) / 16) * 16;
     // prefer a pitch whose word count is 4 mod 8 (8 consecutive rows in distinct bank groups) unless that would push
-    // the CTA past a third of the SM's shared memory (3 resident CTAs matter more than 2-way conflicts)
+    // the CTA past a quarter of the SM's shared memory (4 resident CTAs matter more than 2-way conflicts)
     {
         int alt = pitchBytes;
         while (((alt / 4) % 8) != 4) alt += 16;
-        size_t fixedBytes = (size_t)64 * 64 * px + mf_total_scratch(px) + 16 + 1024;
-        if ((((size_t)alt * (64 + 2 * R) + 127) & ~(size_t)127) + fixedBytes <= 233472 / 3) pitchBytes = alt;
+        size_t fixedBytes = (size_t)64 * 64 * px + 16 + 1024;
+        if ((((size_t)alt * (64 + 2 * R) + 127) & ~(size_t)127) + fixedBytes <= 233472 / 4) pitchBytes = alt;
         else if (((pitchBytes / 4) % 32) == 0) pitchBytes += 16;
     }
     winW = pitchBytes / px;
@@ -275,7 +256,7 @@ int me_frame_dev(Ctx* ctx, int depth, const void* curOrigin, int64_t curStride, 
         if (puMask & (1 << l)) off += (int64_t)ctuCols * ctuRows * (1 << l) * (1 << l);
     }
     a.perRef = off;
-    size_t smem = (((size_t)winW * winH * px + 127) & ~(size_t)127) + (size_t)64 * 64 * px + mf_total_scratch(px) + 16;
+    size_t smem = (((size_t)winW * winH * px + 127) & ~(size_t)127) + (size_t)64 * 64 * px + 16;
     dim3 grid(ctuCols * ctuRows, numRefs);
     if (depth > 8)
     {
