@@ -8,15 +8,18 @@
 #pragma once
 #include "common.cuh"
 #include "tables.cuh"
+#include <type_traits>
 
 // A translation unit whose searches ALL run in per-thread mode defines ME_FORCE_THREAD before including this header:
 // the warp-cooperative bodies are then compiled out (smaller kernel, see me_frame_kernels.cu).  The variant lives in
 // its own inline namespace so the differently-compiled templates never share a symbol.
 #ifdef ME_FORCE_THREAD
 #define ME_IS_THREAD(s) true
+#define ME_PU_W(s) 8                      /* every lane searches an 8-pixel-wide sub-block */
 #define ME_VARIANT me_thread_only
 #else
 #define ME_IS_THREAD(s) ((s).perThread)
+#define ME_PU_W(s) ((s).w)
 #define ME_VARIANT me_generic
 #endif
 
@@ -120,7 +123,7 @@ __device__ __forceinline__ int sad_seg(const pixel* f, const pixel* r)
 template<typename pixel, int SEG>
 __device__ __forceinline__ void sad_k_impl(const MEState<pixel>& s, int K, const int ox[4], const int oy[4], int costs[4])
 {
-    const int segs = s.w / SEG, upc = s.h * segs, total = K * upc;
+    const int segs = ME_PU_W(s) / SEG, upc = s.h * segs, total = K * upc;
     int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
     int cand = 0, rem = s.lane;
     while (rem >= upc) { rem -= upc; cand++; }
@@ -181,15 +184,45 @@ __device__ __forceinline__ int thread_sad_one(const MEState<pixel>& s, const pix
 {
     int acc = 0;
     for (int y = 0; y < s.h; y++)
-        for (int x = 0; x < s.w; x += SEG)
+        for (int x = 0; x < ME_PU_W(s); x += SEG)
             acc += sad_seg<pixel, SEG>(s.fenc + y * 64 + x, r + (int64_t)y * rs + x);
     return acc;
+}
+// 8-pixel-wide sub-block (the me_frame layout): 8 rows at a time with every load issued before the first use, so one
+// candidate costs one load latency per 8 rows instead of one per row; fenc rows are 8-pixel aligned (one vector load).
+template<typename pixel>
+__device__ __forceinline__ int thread_sad_w8(const MEState<pixel>& s, const pixel* r, int64_t rs)
+{
+    constexpr int NW = 8 * (int)sizeof(pixel) / 4;
+    typedef typename std::conditional<sizeof(pixel) == 1, uint2, uint4>::type fvec;
+    uint32_t acc = 0;
+#pragma unroll 1
+    for (int y0 = 0; y0 < s.h; y0 += 8)
+    {
+        uint32_t rw[8][NW];
+        fvec f[8];
+#pragma unroll
+        for (int y = 0; y < 8; y++)
+        {
+            ld_words<pixel, NW>(r + (int64_t)(y0 + y) * rs, rw[y]);
+            f[y] = *(const fvec*)(s.fenc + (y0 + y) * 64);
+        }
+#pragma unroll
+        for (int y = 0; y < 8; y++)
+        {
+            const uint32_t* fw = (const uint32_t*)&f[y];
+#pragma unroll
+            for (int i = 0; i < NW; i++) acc += sad_word<pixel>(fw[i], rw[y][i]);
+        }
+    }
+    return (int)acc;
 }
 template<typename pixel>
 __device__ __forceinline__ int thread_sad_any(const MEState<pixel>& s, const pixel* r, int64_t rs)
 {
-    if (!(s.w & 15)) return thread_sad_one<pixel, 16>(s, r, rs);
-    if (!(s.w & 7))  return thread_sad_one<pixel, 8>(s, r, rs);
+    if (ME_PU_W(s) == 8 && !(s.h & 7)) return thread_sad_w8<pixel>(s, r, rs);
+    if (!(ME_PU_W(s) & 15)) return thread_sad_one<pixel, 16>(s, r, rs);
+    if (!(ME_PU_W(s) & 7))  return thread_sad_one<pixel, 8>(s, r, rs);
     return thread_sad_one<pixel, 4>(s, r, rs);
 }
 template<typename pixel>
@@ -200,7 +233,7 @@ __device__ __forceinline__ int thread_satd(const MEState<pixel>& s, const pixel*
 #pragma unroll 1
     for (int cy = 0; cy < s.h; cy += 4)
 #pragma unroll 1
-        for (int cx = 0; cx < s.w; cx += 4)
+        for (int cx = 0; cx < ME_PU_W(s); cx += 4)
         {
             int d[4][4];
 #pragma unroll
@@ -236,9 +269,11 @@ __device__ __noinline__ void warp_sad_k(const MEState<pixel>& s, int K, const in
             costs[k] = group_sum<pixel>(s, thread_sad_any<pixel>(s, s.fref + ox[k] + (int64_t)oy[k] * s.stride, s.stride));
         return;
     }
-    if (!(s.w & 15))     sad_k_impl<pixel, 16>(s, K, ox, oy, costs);
-    else if (!(s.w & 7)) sad_k_impl<pixel, 8>(s, K, ox, oy, costs);
+#ifndef ME_FORCE_THREAD
+    if (!(ME_PU_W(s) & 15))     sad_k_impl<pixel, 16>(s, K, ox, oy, costs);
+    else if (!(ME_PU_W(s) & 7)) sad_k_impl<pixel, 8>(s, K, ox, oy, costs);
     else                 sad_k_impl<pixel, 4>(s, K, ox, oy, costs);
+#endif
 }
 
 // SAD of the cached PU against an arbitrary block (global or shared) with row stride rs
@@ -246,7 +281,7 @@ template<typename pixel>
 __device__ __noinline__ int warp_sad_block(const MEState<pixel>& s, const pixel* r, int64_t rs)
 {
     if (ME_IS_THREAD(s)) return group_sum<pixel>(s, thread_sad_any<pixel>(s, r, rs));
-    const int gw = s.w >> 2, ng = gw * s.h;
+    const int gw = ME_PU_W(s) >> 2, ng = gw * s.h;
     int acc = 0;
     for (int u = s.lane; u < ng; u += 32)
     {
@@ -262,7 +297,7 @@ __device__ __noinline__ int warp_satd(const MEState<pixel>& s, const pixel* r, i
 {
     if (ME_IS_THREAD(s)) return group_sum<pixel>(s, thread_satd<pixel>(s, r, rs));
     constexpr int NW = 4 * (int)sizeof(pixel) / 4;
-    const int cw = s.w >> 2, nc = cw * (s.h >> 2);
+    const int cw = ME_PU_W(s) >> 2, nc = cw * (s.h >> 2);
     int acc = 0;
 #pragma unroll 1
     for (int c = s.lane; c < nc; c += 32)
@@ -345,7 +380,7 @@ template<typename pixel>
 __device__ __noinline__ void warp_interp_luma(const MEState<pixel>& s, const pixel* src, int xFrac, int yFrac)
 {
     constexpr int NW12 = 12 * (int)sizeof(pixel) / 4, NW4 = 4 * (int)sizeof(pixel) / 4;
-    const int w = s.w, h = s.h, maxVal = (1 << s.depth) - 1, headRoom = 14 - s.depth;
+    const int w = ME_PU_W(s), h = s.h, maxVal = (1 << s.depth) - 1, headRoom = 14 - s.depth;
     const int gw = w >> 2;
     const int u0 = ME_IS_THREAD(s) ? 0 : s.lane, du = ME_IS_THREAD(s) ? 1 : 32;
     int c[8];
@@ -494,7 +529,7 @@ __device__ __noinline__ int subpel_compare(const MEState<pixel>& s, int qx, int 
         return useSatd ? warp_satd<pixel>(s, fref, s.stride) : warp_sad_block<pixel>(s, fref, s.stride);
     if (!ME_IS_THREAD(s)) __syncwarp();
     warp_interp_luma<pixel>(s, fref, xFrac, yFrac);
-    int c = useSatd ? warp_satd<pixel>(s, s.pred, s.w) : warp_sad_block<pixel>(s, s.pred, s.w);
+    int c = useSatd ? warp_satd<pixel>(s, s.pred, ME_PU_W(s)) : warp_sad_block<pixel>(s, s.pred, ME_PU_W(s));
     if (!ME_IS_THREAD(s)) __syncwarp();
     return c;
 }
@@ -511,13 +546,13 @@ __device__ __noinline__ int lowres_qpel_cost(const MEState<pixel>& s, int qx, in
         int hpelB = (qmvy & 2) | ((qmvx & 2) >> 1);
         const pixel* frefB = s.lowres[hpelB] + (qmvx >> 2) + (int64_t)(qmvy >> 2) * s.stride;
         __syncwarp();
-        for (int e = s.lane; e < s.w * s.h; e += 32)          // pixelavg_pp, pixel.cpp:545-557
+        for (int e = s.lane; e < ME_PU_W(s) * s.h; e += 32)          // pixelavg_pp, pixel.cpp:545-557
         {
-            int y = e / s.w, x = e - y * s.w;
+            int y = e / ME_PU_W(s), x = e - y * ME_PU_W(s);
             s.pred[e] = (pixel)(((int)frefA[(int64_t)y * s.stride + x] + (int)frefB[(int64_t)y * s.stride + x] + 1) >> 1);
         }
         __syncwarp();
-        int c = useSatd ? warp_satd<pixel>(s, s.pred, s.w) : warp_sad_block<pixel>(s, s.pred, s.w);
+        int c = useSatd ? warp_satd<pixel>(s, s.pred, ME_PU_W(s)) : warp_sad_block<pixel>(s, s.pred, ME_PU_W(s));
         __syncwarp();
         return c;
     }
