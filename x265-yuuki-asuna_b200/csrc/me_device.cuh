@@ -519,6 +519,175 @@ __device__ __noinline__ void warp_interp_luma(const MEState<pixel>& s, const pix
     if (!ME_IS_THREAD(s)) __syncwarp();
 }
 
+// ---- fused sub-pel cost, per-thread mode ------------------------------------------------------------------------
+// The prediction of a sub-block is never stored: it is produced one 4x4 cell at a time in registers (the same
+// luma_hpp / luma_vpp / luma_hvpp arithmetic as warp_interp_luma above, ipfilter.cpp:79-118,164-203,362-369) and
+// the cell's SAD or SATD against fenc is accumulated on the spot.  Vertical taps slide down a 4-column strip: the
+// 11-row window keeps its last 7 rows between cells, so every source (or first-stage) row is produced once.
+template<typename pixel>
+__device__ __forceinline__ void pack4(const int v[4], uint32_t* out);
+template<> __device__ __forceinline__ void pack4<uint8_t>(const int v[4], uint32_t* out)
+{
+    out[0] = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
+}
+template<> __device__ __forceinline__ void pack4<uint16_t>(const int v[4], uint32_t* out)
+{
+    out[0] = (uint32_t)v[0] | ((uint32_t)v[1] << 16); out[1] = (uint32_t)v[2] | ((uint32_t)v[3] << 16);
+}
+
+template<typename pixel>
+__device__ __forceinline__ int cell_cost(const pixel* f, const int o[4][4], bool useSatd)
+{
+    constexpr int NW = 4 * (int)sizeof(pixel) / 4;
+    if (useSatd)
+    {
+        int d[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+        {
+            int a[4];
+            unpack4<pixel>((const uint32_t*)(f + i * 64), a);
+#pragma unroll
+            for (int k = 0; k < 4; k++) d[i][k] = a[k] - o[i][k];
+            me_hadamard4(d[i][0], d[i][1], d[i][2], d[i][3]);
+        }
+        int t = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+        {
+            me_hadamard4(d[0][k], d[1][k], d[2][k], d[3][k]);
+            t += abs(d[0][k]) + abs(d[1][k]) + abs(d[2][k]) + abs(d[3][k]);
+        }
+        return t >> 1;
+    }
+    uint32_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+    {
+        uint32_t pw[NW];
+        pack4<pixel>(o[i], pw);
+        const uint32_t* fw = (const uint32_t*)(f + i * 64);
+#pragma unroll
+        for (int j = 0; j < NW; j++) acc += sad_word<pixel>(fw[j], pw[j]);
+    }
+    return (int)acc;
+}
+
+template<typename pixel>
+__device__ __noinline__ int thread_subpel_cost(const MEState<pixel>& s, const pixel* src, int xFrac, int yFrac, bool useSatd)
+{
+    constexpr int NW12 = 12 * (int)sizeof(pixel) / 4, NW4 = 4 * (int)sizeof(pixel) / 4;
+    const int maxVal = (1 << s.depth) - 1, headRoom = 14 - s.depth;
+    const int W = ME_PU_W(s), H = s.h;
+    int ch[8];
+#pragma unroll
+    for (int t = 0; t < 8; t++) ch[t] = c_meLumaFilter[xFrac][t];
+    const uint32_t clo = pack_taps(ch, 0), chi = pack_taps(ch, 4);
+    // horizontal 8-tap sums of 4 adjacent outputs whose first tap sits at p
+    auto hsums = [&](const pixel* p, int sums[4]) {
+        uint32_t rw[NW12];
+        ld_words<pixel, NW12>(p, rw);
+        if (sizeof(pixel) == 1) hfir4_u8(rw, clo, chi, sums);
+        else
+        {
+            int v[12];
+            unpack_row12<pixel>(rw, v);
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+            {
+                sums[k] = 0;
+#pragma unroll
+                for (int t = 0; t < 8; t++) sums[k] += v[k + t] * ch[t];
+            }
+        }
+    };
+    int acc = 0;
+    if (!yFrac)
+    {
+        // luma_hpp
+#pragma unroll 1
+        for (int y0 = 0; y0 < H; y0 += 4)
+#pragma unroll 1
+            for (int x = 0; x < W; x += 4)
+            {
+                int o[4][4];
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+                {
+                    int sums[4];
+                    hsums(src + (int64_t)(y0 + r) * s.stride + x - 3, sums);
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                    {
+                        int val = (int16_t)((sums[k] + 32) >> 6);
+                        o[r][k] = val < 0 ? 0 : (val > maxVal ? maxVal : val);
+                    }
+                }
+                acc += cell_cost<pixel>(s.fenc + y0 * 64 + x, o, useSatd);
+            }
+        return acc;
+    }
+    // luma_vpp (xFrac == 0) or luma_hvpp = hps(isRowExt) + vsp
+    int cv[8];
+#pragma unroll
+    for (int t = 0; t < 8; t++) cv[t] = c_meLumaFilter[yFrac][t];
+    const int sh1 = 6 - headRoom, off1 = (int)((unsigned)-8192 << sh1);
+    const int sh2 = xFrac ? 6 + headRoom : 6, off2 = xFrac ? (1 << (sh2 - 1)) + (8192 << 6) : 32;
+#pragma unroll 1
+    for (int x = 0; x < W; x += 4)
+    {
+        int win[11][4];                      // win[r] = (first-stage) row y0 + r - 3 of this strip
+#pragma unroll
+        for (int r = 0; r < 11; r++)
+#pragma unroll
+            for (int k = 0; k < 4; k++) win[r][k] = 0;
+        // two lead-in steps (y0 = -8, -4) fill rows -3..3; each later step adds 4 rows and emits one cell
+#pragma unroll 1
+        for (int y0 = -8; y0 < H; y0 += 4)
+        {
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+            {
+                const pixel* p = src + (int64_t)(y0 + 4 + r) * s.stride + x;
+                if (xFrac)
+                {
+                    int sums[4];
+                    hsums(p - 3, sums);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) win[7 + r][k] = (int16_t)((sums[k] + off1) >> sh1);
+                }
+                else
+                {
+                    uint32_t rw[NW4];
+                    ld_words<pixel, NW4>(p, rw);
+                    unpack4<pixel>(rw, win[7 + r]);
+                }
+            }
+            if (y0 >= 0)
+            {
+                int o[4][4];
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                    {
+                        int sum = 0;
+#pragma unroll
+                        for (int t = 0; t < 8; t++) sum += win[r + t][k] * cv[t];
+                        int val = (int16_t)((sum + off2) >> sh2);
+                        o[r][k] = val < 0 ? 0 : (val > maxVal ? maxVal : val);
+                    }
+                acc += cell_cost<pixel>(s.fenc + y0 * 64 + x, o, useSatd);
+            }
+#pragma unroll
+            for (int r = 0; r < 7; r++)
+#pragma unroll
+                for (int k = 0; k < 4; k++) win[r][k] = win[r + 4][k];
+        }
+    }
+    return acc;
+}
+
 // MotionEstimate::subpelCompare (motion.cpp:1571-1599); useSatd selects cmp
 template<typename pixel>
 __device__ __noinline__ int subpel_compare(const MEState<pixel>& s, int qx, int qy, bool useSatd)
@@ -527,7 +696,8 @@ __device__ __noinline__ int subpel_compare(const MEState<pixel>& s, int qx, int 
     const int xFrac = qx & 3, yFrac = qy & 3;
     if (!(xFrac | yFrac))
         return useSatd ? warp_satd<pixel>(s, fref, s.stride) : warp_sad_block<pixel>(s, fref, s.stride);
-    if (!ME_IS_THREAD(s)) __syncwarp();
+    if (ME_IS_THREAD(s)) return group_sum<pixel>(s, thread_subpel_cost<pixel>(s, fref, xFrac, yFrac, useSatd));
+    __syncwarp();
     warp_interp_luma<pixel>(s, fref, xFrac, yFrac);
     int c = useSatd ? warp_satd<pixel>(s, s.pred, ME_PU_W(s)) : warp_sad_block<pixel>(s, s.pred, ME_PU_W(s));
     if (!ME_IS_THREAD(s)) __syncwarp();

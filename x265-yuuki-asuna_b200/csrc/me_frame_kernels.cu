@@ -87,8 +87,7 @@ __device__ unsigned long long g_mfCycles[MF_WARPS + 1];
 //   warp 1 : the four 32x32 PUs, two at a time, 16 lanes x 8x8 each
 //   warp 2 : the sixteen 16x16 PUs, eight at a time, 4 lanes x 8x8 each
 //   warp 3 : the sixty-four 8x8 PUs, thirty-two at a time, one lane each
-// No shared-memory scratch: pred/immed of a sub-block live in the lane's local memory.
-constexpr int MF_SUBH_MAX = 16;
+// No scratch at all: sub-pel predictions are produced and costed cell by cell in registers (thread_subpel_cost).
 template<typename pixel>
 __global__ void __launch_bounds__(MF_WARPS * 32, 4)
 me_frame_kernel(const __grid_constant__ MEFrameMaps maps, MEFrameArgs p)
@@ -127,7 +126,6 @@ me_frame_kernel(const __grid_constant__ MEFrameMaps maps, MEFrameArgs p)
     const long long tStart = clock64();
 
     // ---- roles ---------------------------------------------------------------------------------------------------
-    __align__(16) unsigned char tscratch[8 * MF_SUBH_MAX * sizeof(pixel) + 8 * (MF_SUBH_MAX + 7) * 2];   // per-lane pred + immed
     MEState<pixel> s;
     s.stride = p.winW; s.isLowres = false; s.perThread = true; s.lane = 0; s.depth = p.depth;
     s.cost = p.cost + 2 * 32768; s.mvpx = mvpx; s.mvpy = mvpy; s.gstride = p.refStride;
@@ -141,8 +139,7 @@ me_frame_kernel(const __grid_constant__ MEFrameMaps maps, MEFrameArgs p)
     const int sx = (q % subCols) * 8, sy = (q / subCols) * subH;
     s.groupSize = 1 << lanesLog2;
     s.groupMask = lanesLog2 == 5 ? 0xffffffffu : (((1u << (1 << lanesLog2)) - 1u) << (lane & ~((1 << lanesLog2) - 1)));
-    s.pred = (pixel*)tscratch;
-    s.immed = (int16_t*)(tscratch + 8 * MF_SUBH_MAX * sizeof(pixel));
+    s.pred = nullptr; s.immed = nullptr;       // per-thread searches never store a prediction (thread_subpel_cost)
     s.w = 8; s.h = subH;
 
     if ((p.puMask >> level) & 1)
