@@ -35,6 +35,8 @@ ROWS = H + 2 * PAD + (64 - (H % 64)) % 64      # 34 CTU rows (2176) + margins
 CTU_COLS, CTU_ROWS = W // CTU, (H + CTU - 1) // CTU
 NREF, MERANGE, SUBME, QP = 3, 57, 2, 30
 LEVELS = [64, 32, 16, 8]
+# DRAM bytes one sad_pyramid launch (3 references, 2160p 8-bit) moved under `ncu --set full` (profiles/r01_pyramid_dct_v3.txt)
+SAD_PYRAMID_DRAM_BYTES = 33437696
 METRIC = "2160p preset-medium fps at 1/2/4/8 B200; ME SAD achieved HBM GB/s vs peak"
 
 
@@ -383,7 +385,8 @@ def main():
                 "clocks": sampler.summary(), "gpu_launches": int(launches),
                 "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": ROWS * STRIDE, "d2h_bytes_per_step": njobs * 12},
                 "roofline": {"kernel": "sad_pyramid_kernel (streaming ME SAD at the predictor, all 4 PU levels in one pass per reference)", "bound": "hbm", "achieved": achieved,
-                             "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": None,
+                             "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": SAD_PYRAMID_DRAM_BYTES,
+                             "traffic_src": "profiles/r01_pyramid_dct_v3.txt (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum per launch; the current frame is fetched from DRAM once and re-read by the 2 other references through L2, outputs stay in L2)",
                              "peak_kind": pk_kind, "launches_per_step": sad_launches, "us_per_launch": sad_t * 1e6,
                              "how": "%d back-to-back launches (one CUDA graph) on disjoint frame sets after an L2 flush, CUDA events; in-step (single launch between events): %.1f us" % (groups, float(np.mean(sad_ms)) * 1e3)}}
         dct_bytes = n32 * 1024 * 2 * 2
@@ -394,7 +397,7 @@ def main():
         me_t = float(np.mean(me_ms)) / 1e3
         line["roofline_me_search"] = {"kernel": "me_frame_kernel (TMA-staged windows; HEX + subme 2, %d searches)" % njobs, "bound": "hbm", "achieved": me_bytes / me_t / 1e9,
                                       "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": me_bytes / me_t / 1e9 / pk["hbm_gbs"], "ms_per_step": me_t * 1e3,
-                                      "note": "ALU/latency-bound pattern search over L2-resident planes (DESIGN.md 5)"}
+                                      "note": "instruction-issue/fetch-bound pattern search over smem-staged windows (DESIGN.md 5, profiles/r01_me_frame_v5.txt); HBM figure shown for scale only"}
         if world == 1:
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line))
