@@ -156,8 +156,9 @@ int x265b200_intra_allangs_dev(x265b200_ctx* ctx, int depth, int log2N, const vo
  *      mvmin/mvmax are full-pel inclusive bounds, mvp and mvc[] are quarter-pel, the result
  *      (outMv, outCost) is `outQMv` and the return value.  searchMethod uses the X265_*_SEARCH
  *      numbering of x265.h:492-497 (0 DIA, 1 HEX, 2 UMH, 3 STAR, 5 FULL; 4 SEA is a "next" row).
- *      lambda = x265_lambda_tab[qp] of BitCost::setQP (bitcost.cpp:31-60).  Luma only
- *      (bChromaSATD = false, i.e. subme <= 2 or the lookahead-style setSourcePU). */
+ *      lambda = x265_lambda_tab[qp] of BitCost::setQP (bitcost.cpp:31-60).  x265b200_me_batch_dev is the luma-only
+ *      form (bChromaSATD = false: subme <= 2, or the lookahead-style setSourcePU of motion.cpp:167);
+ *      x265b200_me_batch_chroma_dev below is the encode-style form with the chroma residual term. */
 typedef struct {
     int32_t puX, puY;                          /* PU position in the fenc/ref planes (pixels)   */
     int32_t w, h;                              /* PU size (any of the 24 inter LumaPU shapes)   */
@@ -175,6 +176,23 @@ int x265b200_me_batch_dev(x265b200_ctx* ctx, int depth, const void* fencPlane, i
                           const void* refPlane, const void* const* refPlanes, int64_t refStride,
                           x265b200_me_job* jobs, int64_t n, int maxW, int maxH,
                           int searchMethod, int subpelRefine, int merange, double lambda, int maxSlices);
+/* Encode-style form: the Yuv-based MotionEstimate::setSourcePU (motion.cpp:193-222) used by Search::predInterSearch.
+ * With subpelRefine > 2, csp != 4:0:0 and a chroma block that is a multiple of 4x4 (i.e. chroma[csp].pu[part].satd
+ * exists, pixel.cpp:1200-1290) bChromaSATD is set and EVERY subpelCompare adds the SATD of the interpolated Cb and Cr
+ * blocks (4-tap filters at eighth-pel fractions, motion.cpp:1601-1661).  csp uses x265.h:588-592 (1 = 4:2:0,
+ * 2 = 4:2:2, 3 = 4:4:4).  Chroma planes are addressed like the luma ones: pixel (puX >> hshift, puY >> vshift);
+ * ref{Cb,Cr}Planes are optional device arrays indexed by job.refIdx (else refCb / refCr). */
+typedef struct {
+    int32_t csp;
+    const void* fencCb; const void* fencCr; int64_t fencStrideC;
+    const void* refCb; const void* refCr;
+    const void* const* refCbPlanes; const void* const* refCrPlanes;
+    int64_t refStrideC;
+} x265b200_me_chroma;
+int x265b200_me_batch_chroma_dev(x265b200_ctx* ctx, int depth, const void* fencPlane, int64_t fencStride,
+                                 const void* refPlane, const void* const* refPlanes, int64_t refStride,
+                                 const x265b200_me_chroma* chroma, x265b200_me_job* jobs, int64_t n, int maxW, int maxH,
+                                 int searchMethod, int subpelRefine, int merange, double lambda, int maxSlices);
 /* Frame form of the same search: every 2Nx2N PU (levels selected by puMask: bit0 64x64, bit1 32x32, bit2 16x16,
  * bit3 8x8) of every 64x64 CTU against numRefs reference planes.  One CTA per (CTU, reference) stages the
  * source CTU and the search window in shared memory with TMA, then runs the PU searches from there.

@@ -463,3 +463,64 @@ void ref_la_destroy(void* hv)
 }
 
 } /* extern "C" */
+
+/* ---- MotionEstimate with the chroma residual term --------------------------------------------------
+ * The encode-style setSourcePU (motion.cpp:193-222, the one Search::predInterSearch uses): bChromaSATD is
+ * decided by the reference itself (subpelRefine > 2 && chroma satd exists).  The CU Yuv holds the PU at
+ * partition 0; the reference picture is a PicYuv shell whose offset tables are {0}, so
+ * getCbAddr(0, 0) = fpelPlane[1] = the chroma block under the PU. */
+#include "yuv.h"
+extern "C" int ref_me_batch_chroma(const void* fencY, const void* fencCb, const void* fencCr, intptr_t fencStrideY, intptr_t fencStrideC,
+                                   const void* refY, const void* refCb, const void* refCr, intptr_t refStrideY, intptr_t refStrideC,
+                                   int csp, RefMEJob* jobs, int64_t n, int searchMethod, int subpelRefine, int merange, int qp,
+                                   int maxSlices, int threads)
+{
+    ensure_init();
+    { BitCost warm; warm.setQP(qp); }
+    const int hs = csp != X265_CSP_I444, vs = csp == X265_CSP_I420;
+    int nt = threads < 1 ? 1 : threads;
+    std::vector<MotionEstimate*> mes(nt);
+    std::vector<Yuv*> cus(nt);
+    for (int t = 0; t < nt; t++)
+    {
+        mes[t] = new MotionEstimate;
+        mes[t]->init(csp);
+        mes[t]->setQP(qp);
+        cus[t] = new Yuv;
+        if (!cus[t]->create(64, csp)) return -1;
+    }
+    parallel_for(n, nt, [&](int64_t i, int t) {
+        RefMEJob& j = jobs[i];
+        MotionEstimate& me = *mes[t];
+        Yuv& cu = *cus[t];
+        const pixel* fy = (const pixel*)fencY + j.puX + (intptr_t)j.puY * fencStrideY;
+        for (int y = 0; y < j.h; y++) memcpy(cu.m_buf[0] + y * cu.m_size, fy + y * fencStrideY, j.w * sizeof(pixel));
+        const pixel* fc[2] = { (const pixel*)fencCb, (const pixel*)fencCr };
+        for (int c = 0; c < 2; c++)
+        {
+            const pixel* p = fc[c] + (j.puX >> hs) + (intptr_t)(j.puY >> vs) * fencStrideC;
+            for (int y = 0; y < (j.h >> vs); y++) memcpy(cu.m_buf[1 + c] + y * cu.m_csize, p + y * fencStrideC, (j.w >> hs) * sizeof(pixel));
+        }
+        me.setSourcePU(cu, 0, 0, 0, j.w, j.h, searchMethod, subpelRefine, true);
+
+        intptr_t zero = 0;
+        PicYuv pic;
+        pic.m_cuOffsetY = pic.m_cuOffsetC = pic.m_buOffsetY = pic.m_buOffsetC = &zero;
+        pic.m_stride = refStrideY; pic.m_strideC = refStrideC;
+        ReferencePlanes ref;
+        ref.reconPic = &pic;
+        ref.fpelPlane[0] = (pixel*)refY + j.puX + (intptr_t)j.puY * refStrideY;
+        ref.fpelPlane[1] = (pixel*)refCb + (j.puX >> hs) + (intptr_t)(j.puY >> vs) * refStrideC;
+        ref.fpelPlane[2] = (pixel*)refCr + (j.puX >> hs) + (intptr_t)(j.puY >> vs) * refStrideC;
+        ref.lumaStride = refStrideY; ref.chromaStride = refStrideC;
+        ref.isLowres = false;
+        MV mvmin(j.mvminX, j.mvminY), mvmax(j.mvmaxX, j.mvmaxY), mvp(j.mvpX, j.mvpY), out(0, 0);
+        MV mvc[8];
+        for (int k = 0; k < j.numCand; k++) mvc[k] = MV(j.mvc[k][0], j.mvc[k][1]);
+        j.outCost = me.motionEstimate(&ref, mvmin, mvmax, mvp, j.numCand, mvc, merange, out, (uint32_t)maxSlices);
+        j.outMvX = out.x; j.outMvY = out.y;
+        pic.m_cuOffsetY = pic.m_cuOffsetC = pic.m_buOffsetY = pic.m_buOffsetC = NULL;
+    });
+    for (int t = 0; t < nt; t++) { delete mes[t]; cus[t]->destroy(); delete cus[t]; }
+    return 0;
+}

@@ -69,3 +69,31 @@ def ref_me(depth, cur, ref, stride, origin, job, method, subme, merange, qp, max
                    ctypes.c_void_p(ref.ctypes.data + origin * item), ctypes.c_ssize_t(stride),
                    vp(rj), ctypes.c_int64(len(rj)), int(method), int(subme), int(merange), int(qp), int(maxSlices), int(threads))
     return rj["outMvX"].copy(), rj["outMvY"].copy(), rj["outCost"].copy()
+
+
+def synth_chroma_pair(W, H, pad, csp, depth=8, seed=77, motion=(5, -3), noise=2.0):
+    """Cb/Cr plane pairs for a (cur, ref) picture pair: chroma-resolution band-limited noise moved by the luma motion
+    scaled to the chroma grid.  Returns (curCb, curCr, refCb, refCr, strideC, originC, padC)."""
+    hs, vs = int(csp != 3), int(csp == 1)
+    Wc, Hc, pc = W >> hs, H >> vs, pad
+    out = []
+    for k in range(2):
+        c, r, Sc, oc = synth_pair(Wc, Hc, pc, depth=depth, seed=seed + 13 * k, motion=(motion[0] >> hs, motion[1] >> vs), noise=noise)
+        out.append((c, r))
+    return out[0][0], out[1][0], out[0][1], out[1][1], Sc, oc
+
+
+def ref_me_chroma(depth, csp, cur, ref, stride, origin, curC, refC, strideC, originC, job, method, subme, merange, qp, maxSlices=1, threads=4):
+    """The reference's encode-style setSourcePU + motionEstimate (bChromaSATD decided by the reference)."""
+    R = oracle.ref(depth)
+    assert R is not None, "oracle/_ref missing"
+    rj = np.zeros(len(job), dtype=REF_ME_JOB)
+    for f in ("puX", "puY", "w", "h", "mvminX", "mvminY", "mvmaxX", "mvmaxY", "mvpX", "mvpY", "numCand", "mvc"):
+        rj[f] = job[f]
+    item = cur.itemsize
+    P = lambda a, o: ctypes.c_void_p(a.ctypes.data + o * item)
+    rc = R.ref_me_batch_chroma(P(cur, origin), P(curC[0], originC), P(curC[1], originC), ctypes.c_ssize_t(stride), ctypes.c_ssize_t(strideC),
+                               P(ref, origin), P(refC[0], originC), P(refC[1], originC), ctypes.c_ssize_t(stride), ctypes.c_ssize_t(strideC),
+                               int(csp), vp(rj), ctypes.c_int64(len(rj)), int(method), int(subme), int(merange), int(qp), int(maxSlices), int(threads))
+    assert rc == 0
+    return rj["outMvX"].copy(), rj["outMvY"].copy(), rj["outCost"].copy()

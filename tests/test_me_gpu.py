@@ -7,7 +7,7 @@ import importlib
 import numpy as np
 import pytest
 
-from me_util import make_jobs, ref_me, synth_pair
+from me_util import make_jobs, ref_me, ref_me_chroma, synth_chroma_pair, synth_pair
 from util import LUMA_PU_SIZES
 
 pkg = importlib.import_module("x265-yuuki-asuna_b200")
@@ -55,6 +55,53 @@ def test_me_10bit(ctx, method):
 @pytest.mark.parametrize("subme", [3, 4, 5, 6, 7])
 def test_me_subme_levels_luma(ctx, subme):
     _run(ctx, 8, pkg.ME_HEX, subme, 32, 27, [(8, 8), (16, 16), (32, 32), (64, 64), (16, 8), (32, 24)], seed=400 + subme, n_per_size=8)
+
+
+def _run_chroma(ctx, depth, csp, method, subme, merange, qp, sizes, seed, n_per_size=6):
+    W, H = 192, 128
+    pad = 64 + merange + 16
+    cur, ref, S, origin = synth_pair(W, H, pad, depth=depth, seed=seed)
+    cCb, cCr, rCb, rCr, Sc, oc = synth_chroma_pair(W, H, pad, csp, depth=depth, seed=seed + 5)
+    rng = np.random.default_rng(seed + 1)
+    job = make_jobs(pkg, W, H, sizes, merange, rng, n_per_size=n_per_size)
+    ex, ey, ec = ref_me_chroma(depth, csp, cur, ref, S, origin, (cCb, cCr), (rCb, rCr), Sc, oc, job, method, subme, merange, qp)
+    item = cur.itemsize
+    bufs = [ctx.to_device(a) for a in (cur, ref, cCb, cCr, rCb, rCr, job)]
+    dC, dR, dCb, dCr, dRb, dRr, dJ = bufs
+    lam = pkg.lambda_for_qp(qp, depth)
+    ctx.me_batch_chroma_dev(depth, dC.ptr + origin * item, S, dR.ptr + origin * item, S, csp, dCb.ptr + oc * item, dCr.ptr + oc * item, Sc,
+                            dRb.ptr + oc * item, dRr.ptr + oc * item, Sc, dJ, len(job), 64, 64, method, subme, merange, lam)
+    out = dJ.download(pkg.ME_JOB)
+    bad = np.nonzero((out["outMvX"] != ex) | (out["outMvY"] != ey) | (out["outCost"] != ec))[0]
+    msg = ""
+    if len(bad):
+        i = bad[0]
+        msg = "job %d %s: got mv (%d,%d) cost %d, reference mv (%d,%d) cost %d; %d/%d differ" % (
+            i, job[i], out["outMvX"][i], out["outMvY"][i], out["outCost"][i], ex[i], ey[i], ec[i], len(bad), len(job))
+    for b in bufs:
+        b.free()
+    assert not len(bad), msg
+    return ec
+
+
+@pytest.mark.parametrize("subme", [3, 4, 5, 7])
+def test_me_chroma_satd_420(ctx, subme):
+    """encode-style setSourcePU: subme > 2 adds the Cb/Cr SATD to every subpelCompare (motion.cpp:212,1601-1661);
+    shapes whose chroma block is not a multiple of 4x4 (16x12, 12x16, 8x4, 16x4 ...) stay luma-only in the reference too."""
+    _run_chroma(ctx, 8, 1, pkg.ME_HEX if subme != 5 else pkg.ME_STAR, subme, 32, 28, INTER_SIZES, seed=900 + subme)
+
+
+def test_me_chroma_satd_below_subme3_is_luma_only(ctx):
+    _run_chroma(ctx, 8, 1, pkg.ME_HEX, 2, 32, 28, [(16, 16), (32, 32)], seed=950)
+
+
+@pytest.mark.parametrize("csp", [2, 3])
+def test_me_chroma_satd_422_444(ctx, csp):
+    _run_chroma(ctx, 8, csp, pkg.ME_UMH, 3, 24, 30, [(8, 8), (16, 16), (32, 16), (16, 32), (64, 64), (24, 32), (12, 16)], seed=960 + csp)
+
+
+def test_me_chroma_satd_10bit(ctx):
+    _run_chroma(ctx, 10, 1, pkg.ME_STAR, 3, 32, 32, [(8, 8), (16, 16), (32, 32), (64, 64), (32, 8), (8, 32)], seed=980)
 
 
 def test_me_large_motion_star_raster(ctx):

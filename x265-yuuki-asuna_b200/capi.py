@@ -266,6 +266,24 @@ def _ctx_me_batch_dev(self, depth, dFenc, fencStride, dRef, refStride, dJobs, n,
 Ctx.me_batch_dev = _ctx_me_batch_dev
 
 
+class ME_CHROMA(ctypes.Structure):
+    """x265b200_me_chroma (include/x265b200.h)"""
+    _fields_ = [("csp", ctypes.c_int32), ("fencCb", ctypes.c_void_p), ("fencCr", ctypes.c_void_p), ("fencStrideC", ctypes.c_int64),
+                ("refCb", ctypes.c_void_p), ("refCr", ctypes.c_void_p), ("refCbPlanes", ctypes.c_void_p), ("refCrPlanes", ctypes.c_void_p),
+                ("refStrideC", ctypes.c_int64)]
+
+
+def _ctx_me_batch_chroma_dev(self, depth, dFenc, fencStride, dRef, refStride, csp, dFencCb, dFencCr, fencStrideC, dRefCb, dRefCr, refStrideC,
+                             dJobs, n, maxW, maxH, searchMethod, subpelRefine, merange, lam, maxSlices=1):
+    ch = ME_CHROMA(int(csp), _vp(dFencCb), _vp(dFencCr), int(fencStrideC), _vp(dRefCb), _vp(dRefCr), None, None, int(refStrideC))
+    self._chk(self.L.x265b200_me_batch_chroma_dev(self.h, depth, _vp(dFenc), _i64(fencStride), _vp(dRef), None, _i64(refStride),
+                                                  ctypes.byref(ch), _vp(dJobs), _i64(n), int(maxW), int(maxH), int(searchMethod),
+                                                  int(subpelRefine), int(merange), ctypes.c_double(lam), int(maxSlices)))
+
+
+Ctx.me_batch_chroma_dev = _ctx_me_batch_chroma_dev
+
+
 # ---- plane forms ---------------------------------------------------------------------------------
 def _ctx_dct_plane_dev(self, sizeIdx, depth, dPlane, stride, blocksX, blocksY, dCoef):
     self._chk(self.L.x265b200_dct_plane_dev(self.h, sizeIdx, depth, _vp(dPlane), _i64(stride), int(blocksX), int(blocksY), _vp(dCoef)))

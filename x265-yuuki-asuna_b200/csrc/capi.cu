@@ -85,7 +85,7 @@ int intra_filter_dev(Ctx*, int depth, int log2N, const void* src, void* dst, int
 int intra_allangs_dev(Ctx*, int depth, int log2N, const void* refPix, const void* filtPix, void* dest, int bLuma, int64_t n);
 
 int me_batch_dev(Ctx*, int depth, const void* fencPlane, int64_t fencStride, const void* refPlane, const void* const* refPlanes,
-                 int64_t refStride, x265b200_me_job* jobs, int64_t n, int maxW, int maxH,
+                 int64_t refStride, const x265b200_me_chroma* chroma, x265b200_me_job* jobs, int64_t n, int maxW, int maxH,
                  int searchMethod, int subpelRefine, int merange, double lambda, int maxSlices);
 void host_bitcost_table(double lambda, uint16_t* out);
 int debug_me_frame_cycles(unsigned long long* out);
@@ -342,7 +342,17 @@ int x265b200_me_batch_dev(x265b200_ctx* ctx, int depth, const void* fencPlane, i
                           int searchMethod, int subpelRefine, int merange, double lambda, int maxSlices)
 {
     REQUIRE_CTX(ctx);
-    return me_batch_dev(CTX(ctx), depth, fencPlane, fencStride, refPlane, refPlanes, refStride, jobs, n, maxW, maxH,
+    return me_batch_dev(CTX(ctx), depth, fencPlane, fencStride, refPlane, refPlanes, refStride, nullptr, jobs, n, maxW, maxH,
+                        searchMethod, subpelRefine, merange, lambda, maxSlices);
+}
+int x265b200_me_batch_chroma_dev(x265b200_ctx* ctx, int depth, const void* fencPlane, int64_t fencStride,
+                                 const void* refPlane, const void* const* refPlanes, int64_t refStride,
+                                 const x265b200_me_chroma* chroma, x265b200_me_job* jobs, int64_t n, int maxW, int maxH,
+                                 int searchMethod, int subpelRefine, int merange, double lambda, int maxSlices)
+{
+    REQUIRE_CTX(ctx);
+    if (!chroma) { set_error("me_batch_chroma: chroma descriptor is NULL"); return -1; }
+    return me_batch_dev(CTX(ctx), depth, fencPlane, fencStride, refPlane, refPlanes, refStride, chroma, jobs, n, maxW, maxH,
                         searchMethod, subpelRefine, merange, lambda, maxSlices);
 }
 int x265b200_me_frame_dev(x265b200_ctx* ctx, int depth, const void* curOrigin, int64_t curStride, const void* const* refOriginsHost, int numRefs,

@@ -323,7 +323,7 @@ la_search_kernel(LASearchArgs p)
 
         MEState<pixel> s;
         s.fenc = sFenc[warp]; s.pred = sPred[warp]; s.immed = nullptr;
-        s.stride = p.stride; s.isLowres = true; s.perThread = false; s.groupSize = 1; s.groupMask = 0xffffffffu; s.w = 8; s.h = 8; s.lane = lane; s.depth = p.depth;
+        s.stride = p.stride; s.isLowres = true; s.perThread = false; s.chromaSatd = false; s.groupSize = 1; s.groupMask = 0xffffffffu; s.w = 8; s.h = 8; s.lane = lane; s.depth = p.depth;
         s.partSizeScale = 4; s.cost = p.cost + 2 * 32768;
 
         int rightX = 0, rightY = 0;       // fencMV[1] of the previous iteration

@@ -68,6 +68,12 @@ struct MEState
     int      groupSize;   // perThread only: 1, or 2/4 lanes that each own a sub-block of the PU and sum their costs
     unsigned groupMask;   // lanes of this group (shuffle mask)
     int      w, h, lane, depth, partSizeScale;
+    // chroma residual cost of subpelCompare (bChromaSATD, motion.cpp:212,1601-1661); warp-cooperative searches only
+    bool     chromaSatd;
+    const pixel* fencC[2];    // cached Cb / Cr PU, row stride csize (= 64 >> hshift, Yuv::m_csize)
+    const pixel* frefC[2];    // Cb / Cr reference planes at the PU position (ReferencePlanes::getCbAddr/getCrAddr)
+    int64_t  strideC;
+    int      csize, hshift, vshift;
     const uint16_t* cost;     // centred lambda-scaled MV cost table (bitcost.cpp:31-60)
     int      mvpx, mvpy;      // setMVP(qmvp), bitcost.h:41
 };
@@ -688,20 +694,151 @@ __device__ __noinline__ int thread_subpel_cost(const MEState<pixel>& s, const pi
     return acc;
 }
 
+#ifndef ME_FORCE_THREAD
+// ---- chroma term of subpelCompare (motion.cpp:1601-1661), warp-cooperative ---------------------------------------
+__constant__ int16_t c_meChromaFilter[8][4] = {
+    { 0, 64, 0, 0 }, { -2, 58, 10, -2 }, { -4, 54, 16, -2 }, { -6, 46, 28, -4 },
+    { -4, 36, 36, -4 }, { -4, 28, 46, -6 }, { -2, 16, 54, -4 }, { -2, 10, 58, -2 } };   // == g_chromaFilter, constants.cpp:258-268
+
+// SATD of a w x h block (multiples of 4) f (stride fs, 4-pixel aligned) vs r (any alignment)
+template<typename pixel>
+__device__ __noinline__ int warp_satd_blk(const pixel* f, int fs, const pixel* r, int64_t rs, int w, int h, int lane)
+{
+    constexpr int NW = 4 * (int)sizeof(pixel) / 4;
+    const int cw = w >> 2, nc = cw * (h >> 2);
+    int acc = 0;
+#pragma unroll 1
+    for (int c = lane; c < nc; c += 32)
+    {
+        int cy = c / cw, cx = c - cy * cw;
+        const pixel* ff = f + cy * 4 * fs + cx * 4;
+        const pixel* q = r + (int64_t)cy * 4 * rs + cx * 4;
+        int d[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+        {
+            int a[4], b[4];
+            uint32_t rw[NW];
+            unpack4<pixel>((const uint32_t*)(ff + i * fs), a);
+            ld_words<pixel, NW>(q + i * rs, rw);
+            unpack4<pixel>(rw, b);
+#pragma unroll
+            for (int k = 0; k < 4; k++) d[i][k] = a[k] - b[k];
+            me_hadamard4(d[i][0], d[i][1], d[i][2], d[i][3]);
+        }
+        int t = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+        {
+            me_hadamard4(d[0][k], d[1][k], d[2][k], d[3][k]);
+            t += abs(d[0][k]) + abs(d[1][k]) + abs(d[2][k]) + abs(d[3][k]);
+        }
+        acc += t >> 1;
+    }
+    return warp_sum(acc);
+}
+
+// chroma[csp].pu[].filter_hpp / filter_vpp / filter_hps(isRowExt) + filter_vsp (ipfilter.cpp:79-118,120-162,164-203,
+// 241-282 with N = 4) of a wC x hC block at eighth-pel fractions into s.pred (stride wC)
+template<typename pixel>
+__device__ __noinline__ void warp_interp_chroma(const MEState<pixel>& s, const pixel* src, int xFrac, int yFrac, int wC, int hC)
+{
+    const int maxVal = (1 << s.depth) - 1, headRoom = 14 - s.depth;
+    const int64_t st = s.strideC;
+    if (!yFrac || !xFrac)
+    {
+        const int frac = yFrac ? yFrac : xFrac;
+        const int64_t step = yFrac ? st : 1;
+        const int c0 = c_meChromaFilter[frac][0], c1 = c_meChromaFilter[frac][1], c2 = c_meChromaFilter[frac][2], c3 = c_meChromaFilter[frac][3];
+        for (int e = s.lane; e < wC * hC; e += 32)
+        {
+            const int y = e / wC, x = e - y * wC;
+            const pixel* q = src + (int64_t)y * st + x - step;
+            const int sum = (int)q[0] * c0 + (int)q[step] * c1 + (int)q[2 * step] * c2 + (int)q[3 * step] * c3;
+            const int val = (int16_t)((sum + 32) >> 6);
+            s.pred[e] = (pixel)(val < 0 ? 0 : (val > maxVal ? maxVal : val));
+        }
+    }
+    else
+    {
+        {
+            const int c0 = c_meChromaFilter[xFrac][0], c1 = c_meChromaFilter[xFrac][1], c2 = c_meChromaFilter[xFrac][2], c3 = c_meChromaFilter[xFrac][3];
+            const int shift = 6 - headRoom, offset = (int)((unsigned)-8192 << shift);
+            for (int e = s.lane; e < wC * (hC + 3); e += 32)       // rows -1 .. hC+1
+            {
+                const int y = e / wC, x = e - y * wC;
+                const pixel* q = src + (int64_t)(y - 1) * st + x - 1;
+                const int sum = (int)q[0] * c0 + (int)q[1] * c1 + (int)q[2] * c2 + (int)q[3] * c3;
+                s.immed[e] = (int16_t)((sum + offset) >> shift);
+            }
+        }
+        __syncwarp();
+        const int c0 = c_meChromaFilter[yFrac][0], c1 = c_meChromaFilter[yFrac][1], c2 = c_meChromaFilter[yFrac][2], c3 = c_meChromaFilter[yFrac][3];
+        const int shift = 6 + headRoom, offset = (1 << (shift - 1)) + (8192 << 6);
+        for (int e = s.lane; e < wC * hC; e += 32)
+        {
+            const int16_t* q = s.immed + e;
+            const int sum = (int)q[0] * c0 + (int)q[wC] * c1 + (int)q[2 * wC] * c2 + (int)q[3 * wC] * c3;
+            const int val = (int16_t)((sum + offset) >> shift);
+            s.pred[e] = (pixel)(val < 0 ? 0 : (val > maxVal ? maxVal : val));
+        }
+    }
+    __syncwarp();
+}
+
+template<typename pixel>
+__device__ __noinline__ int warp_chroma_cost(const MEState<pixel>& s, int qx, int qy)
+{
+    const int mvx = qx << (1 - s.hshift), mvy = qy << (1 - s.vshift);
+    const int64_t off = (mvx >> 3) + (int64_t)(mvy >> 3) * s.strideC;
+    const int xFrac = mvx & 7, yFrac = mvy & 7;
+    const int wC = s.w >> s.hshift, hC = s.h >> s.vshift;
+    int cost = 0;
+    for (int c = 0; c < 2; c++)
+    {
+        const pixel* r = s.frefC[c] + off;
+        if (!(xFrac | yFrac))
+            cost += warp_satd_blk<pixel>(s.fencC[c], s.csize, r, s.strideC, wC, hC, s.lane);
+        else
+        {
+            __syncwarp();
+            warp_interp_chroma<pixel>(s, r, xFrac, yFrac, wC, hC);
+            cost += warp_satd_blk<pixel>(s.fencC[c], s.csize, s.pred, wC, wC, hC, s.lane);
+            __syncwarp();
+        }
+    }
+    return cost;
+}
+#endif
+
 // MotionEstimate::subpelCompare (motion.cpp:1571-1599); useSatd selects cmp
 template<typename pixel>
 __device__ __noinline__ int subpel_compare(const MEState<pixel>& s, int qx, int qy, bool useSatd)
 {
     const pixel* fref = s.fref + (qx >> 2) + (int64_t)(qy >> 2) * s.stride;
     const int xFrac = qx & 3, yFrac = qy & 3;
+    if (ME_IS_THREAD(s))
+    {
+        if (!(xFrac | yFrac))
+            return useSatd ? warp_satd<pixel>(s, fref, s.stride) : warp_sad_block<pixel>(s, fref, s.stride);
+        return group_sum<pixel>(s, thread_subpel_cost<pixel>(s, fref, xFrac, yFrac, useSatd));
+    }
+#ifndef ME_FORCE_THREAD
+    int c;
     if (!(xFrac | yFrac))
-        return useSatd ? warp_satd<pixel>(s, fref, s.stride) : warp_sad_block<pixel>(s, fref, s.stride);
-    if (ME_IS_THREAD(s)) return group_sum<pixel>(s, thread_subpel_cost<pixel>(s, fref, xFrac, yFrac, useSatd));
-    __syncwarp();
-    warp_interp_luma<pixel>(s, fref, xFrac, yFrac);
-    int c = useSatd ? warp_satd<pixel>(s, s.pred, ME_PU_W(s)) : warp_sad_block<pixel>(s, s.pred, ME_PU_W(s));
-    if (!ME_IS_THREAD(s)) __syncwarp();
+        c = useSatd ? warp_satd<pixel>(s, fref, s.stride) : warp_sad_block<pixel>(s, fref, s.stride);
+    else
+    {
+        __syncwarp();
+        warp_interp_luma<pixel>(s, fref, xFrac, yFrac);
+        c = useSatd ? warp_satd<pixel>(s, s.pred, ME_PU_W(s)) : warp_sad_block<pixel>(s, s.pred, ME_PU_W(s));
+        __syncwarp();
+    }
+    if (s.chromaSatd) c += warp_chroma_cost<pixel>(s, qx, qy);      // motion.cpp:1601
     return c;
+#else
+    return 0;
+#endif
 }
 
 // ReferencePlanes::lowresQPelCost (common/lowres.h:94-120), 8x8 lowres blocks, hme = false

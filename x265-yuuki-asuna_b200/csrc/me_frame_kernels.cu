@@ -127,7 +127,7 @@ me_frame_kernel(const __grid_constant__ MEFrameMaps maps, MEFrameArgs p)
 
     // ---- roles ---------------------------------------------------------------------------------------------------
     MEState<pixel> s;
-    s.stride = p.winW; s.isLowres = false; s.perThread = true; s.lane = 0; s.depth = p.depth;
+    s.stride = p.winW; s.isLowres = false; s.perThread = true; s.chromaSatd = false; s.lane = 0; s.depth = p.depth;
     s.cost = p.cost + 2 * 32768; s.mvpx = mvpx; s.mvpy = mvpy; s.gstride = p.refStride;
 
     // level = log2(64 / PU size); per round a warp searches 32 / lanesPerPu PUs; lane q of a PU owns sub-block (sx, sy)

@@ -62,6 +62,10 @@ struct MEArgs
     const uint16_t* cost;
     int searchMethod, subpelRefine, merange, maxSlices, depth;
     int maxW, maxH;
+    // encode-style setSourcePU (motion.cpp:193-222): Cb/Cr planes for the bChromaSATD term; csp 0 = luma only
+    const void* fencC[2]; int64_t fencStrideC;
+    const void* refC0[2]; const void* const* refCPlanes[2]; int64_t refStrideC;
+    int csp, hshift, vshift;
 };
 
 constexpr int ME_WARPS = 4;
@@ -75,7 +79,9 @@ me_batch_kernel(MEArgs p)
     const size_t fencBytes = (size_t)64 * p.maxH * sizeof(pixel);
     const size_t predBytes = ((size_t)p.maxW * p.maxH * sizeof(pixel) + 15) & ~(size_t)15;
     const size_t immedBytes = ((size_t)p.maxW * (p.maxH + 7) * sizeof(int16_t) + 15) & ~(size_t)15;
-    unsigned char* base = smem + warp * (fencBytes + predBytes + immedBytes);
+    const int csize = 64 >> p.hshift, maxHC = p.maxH >> p.vshift;
+    const size_t fencCBytes = p.csp ? (((size_t)csize * maxHC * sizeof(pixel) + 15) & ~(size_t)15) : 0;
+    unsigned char* base = smem + warp * (fencBytes + predBytes + immedBytes + 2 * fencCBytes);
 
     const int64_t j = (int64_t)blockIdx.x * ME_WARPS + warp;
     if (j >= p.n) return;
@@ -90,6 +96,12 @@ me_batch_kernel(MEArgs p)
     s.fref = refPlane + job.puX + (int64_t)job.puY * p.refStride;
     s.gfref = s.fref; s.gstride = p.refStride;
     s.isLowres = false; s.perThread = false; s.groupSize = 1; s.groupMask = 0xffffffffu;
+    // bChromaSATD = subpelRefine > 2 && chromaSatd != NULL && csp != I400 (motion.cpp:212); chroma[csp].pu[].satd exists
+    // exactly when the chroma block is a multiple of 4x4 (pixel.cpp:1200-1226, :1262-1290; 4:4:4 aliases the luma satd)
+    const int wC = job.w >> p.hshift, hC = job.h >> p.vshift;
+    s.chromaSatd = p.csp != 0 && p.subpelRefine > 2 && !(wC & 3) && !(hC & 3);
+    s.csize = csize; s.hshift = p.hshift; s.vshift = p.vshift; s.strideC = p.refStrideC;
+    s.fencC[0] = s.fencC[1] = nullptr; s.frefC[0] = s.frefC[1] = nullptr;
     s.w = job.w; s.h = job.h; s.lane = lane; s.depth = p.depth;
     s.partSizeScale = (job.h * job.h) >> 4;                      // motion.cpp:125-126 sizeScale
     s.cost = p.cost + 2 * 32768;
@@ -109,6 +121,25 @@ me_batch_kernel(MEArgs p)
             d[0] = ld_px2(q); d[1] = ld_px2(q + 2);
         }
     }
+    if (s.chromaSatd)
+    {
+        // Yuv::copyPUFromYuv with bChroma (yuv.cpp:126-140): Cb, Cr PU into the m_csize-stride cache
+        const int64_t coff = (job.puX >> p.hshift) + (int64_t)(job.puY >> p.vshift);
+        for (int c = 0; c < 2; c++)
+        {
+            pixel* dst = (pixel*)(base + fencBytes + predBytes + immedBytes + c * fencCBytes);
+            const pixel* fc = (const pixel*)p.fencC[c] + (job.puX >> p.hshift) + (int64_t)(job.puY >> p.vshift) * p.fencStrideC;
+            for (int e = lane; e < wC * hC; e += 32)
+            {
+                const int y = e / wC, x = e - y * wC;
+                dst[y * csize + x] = fc[(int64_t)y * p.fencStrideC + x];
+            }
+            s.fencC[c] = dst;
+            const pixel* rc = (const pixel*)(p.refCPlanes[c] ? p.refCPlanes[c][job.refIdx] : p.refC0[c]);
+            s.frefC[c] = rc + (job.puX >> p.hshift) + (int64_t)(job.puY >> p.vshift) * p.refStrideC;
+        }
+        (void)coff;
+    }
     __syncwarp();
 
     int ox, oy;
@@ -122,7 +153,7 @@ me_batch_kernel(MEArgs p)
 }
 
 int me_batch_dev(Ctx* ctx, int depth, const void* fencPlane, int64_t fencStride, const void* refPlane, const void* const* refPlanes,
-                 int64_t refStride, x265b200_me_job* jobs, int64_t n, int maxW, int maxH,
+                 int64_t refStride, const x265b200_me_chroma* chroma, x265b200_me_job* jobs, int64_t n, int maxW, int maxH,
                  int searchMethod, int subpelRefine, int merange, double lambda, int maxSlices)
 {
     if (n <= 0) return 0;
@@ -136,8 +167,20 @@ int me_batch_dev(Ctx* ctx, int depth, const void* fencPlane, int64_t fencStride,
     a.fencPlane = fencPlane; a.fencStride = fencStride; a.refPlanes = refPlanes; a.refPlane0 = refPlane; a.refStride = refStride;
     a.jobs = jobs; a.n = n; a.cost = ctx->dMvCost; a.searchMethod = searchMethod; a.subpelRefine = subpelRefine;
     a.merange = merange; a.maxSlices = maxSlices; a.depth = depth; a.maxW = maxW; a.maxH = maxH;
+    a.csp = 0; a.hshift = a.vshift = 0; a.fencStrideC = a.refStrideC = 0;
+    a.fencC[0] = a.fencC[1] = a.refC0[0] = a.refC0[1] = nullptr; a.refCPlanes[0] = a.refCPlanes[1] = nullptr;
+    if (chroma && chroma->csp)
+    {
+        if (chroma->csp < 1 || chroma->csp > 3) { set_error("me_batch: csp %d (1 = 4:2:0, 2 = 4:2:2, 3 = 4:4:4)", chroma->csp); return -1; }
+        a.csp = chroma->csp; a.hshift = chroma->csp != 3; a.vshift = chroma->csp == 1;      // x265.h:588-592, Yuv::create
+        a.fencC[0] = chroma->fencCb; a.fencC[1] = chroma->fencCr; a.fencStrideC = chroma->fencStrideC;
+        a.refC0[0] = chroma->refCb; a.refC0[1] = chroma->refCr; a.refStrideC = chroma->refStrideC;
+        a.refCPlanes[0] = chroma->refCbPlanes; a.refCPlanes[1] = chroma->refCrPlanes;
+        if (!a.fencC[0] || !a.fencC[1] || (!a.refC0[0] && !a.refCPlanes[0]) || (!a.refC0[1] && !a.refCPlanes[1])) { set_error("me_batch: chroma planes missing"); return -1; }
+    }
     const size_t px = depth > 8 ? 2 : 1;
     size_t perWarp = (size_t)64 * maxH * px + (((size_t)maxW * maxH * px + 15) & ~(size_t)15) + (((size_t)maxW * (maxH + 7) * 2 + 15) & ~(size_t)15);
+    if (a.csp) perWarp += 2 * ((((size_t)(64 >> a.hshift) * (maxH >> a.vshift) * px) + 15) & ~(size_t)15);
     size_t smem = perWarp * ME_WARPS;
     unsigned blocks = (unsigned)((n + ME_WARPS - 1) / ME_WARPS);
     if (depth > 8)
