@@ -126,6 +126,41 @@ int x265b200_count_nonzero_dev(x265b200_ctx* ctx, const int16_t* quantCoeff, int
 /* The N x N HEVC core-transform matrix the kernels use (host side, no GPU needed); N = 4,8,16,32. */
 int x265b200_dct_table(int N, int16_t* out);
 
+/* ---- glue: the element-wise entries of the table (pixel.cpp:393-557, :759-862).
+ * Job i works on the w x h block at dst + dstOff / src0 + src0Off / src1 + src1Off (offsets and strides in elements of
+ * the operand's own type: pixel or int16).  Operand types per op (P = pixel, S = int16):
+ *   COPY_PP P<-P  COPY_SS S<-S  COPY_SP P<-S  COPY_PS S<-P   cu[]/pu[].copy_* (blockcopy_*_c)
+ *   FILL_S  S<-p0                                             cu[].blockfill_s
+ *   CPY2DTO1D_SHL/SHR  S<-S, dst contiguous (dstStride = w), p0 = shift      cu[].cpy2Dto1D_shl/shr
+ *   CPY1DTO2D_SHL/SHR  S<-S, src contiguous (src0Stride = w), p0 = shift     cu[].cpy1Dto2D_shl/shr
+ *   SUB_PS  S<-P-P (also calcresidual)   ADD_PS P<-clip(P+S)                 cu[].sub_ps / add_ps / calcresidual
+ *   ADDAVG  P<-clip((S+S+offset)>>shift)  PIXELAVG_PP P<-(P+P+1)>>1          pu[].addAvg / pixelavg_pp
+ *   TRANSPOSE P<-P, dst contiguous w x w                                     cu[].transpose
+ *   WEIGHT_PP P<-P, WEIGHT_SP P<-S: p0 = w0, p1 = round, p2 = shift, p3 = offset   weight_pp / weight_sp */
+enum { X265B200_GL_COPY_PP = 0, X265B200_GL_COPY_SS, X265B200_GL_COPY_SP, X265B200_GL_COPY_PS, X265B200_GL_FILL_S,
+       X265B200_GL_CPY2DTO1D_SHL, X265B200_GL_CPY2DTO1D_SHR, X265B200_GL_CPY1DTO2D_SHL, X265B200_GL_CPY1DTO2D_SHR,
+       X265B200_GL_SUB_PS, X265B200_GL_ADD_PS, X265B200_GL_ADDAVG, X265B200_GL_PIXELAVG_PP, X265B200_GL_TRANSPOSE,
+       X265B200_GL_WEIGHT_PP, X265B200_GL_WEIGHT_SP };
+typedef struct { int64_t dstOff, src0Off, src1Off; } x265b200_glue_job;
+int x265b200_glue_dev(x265b200_ctx* ctx, int op, int depth, int w, int h, void* dst, int64_t dstStride,
+                      const void* src0, int64_t src0Stride, const void* src1, int64_t src1Stride,
+                      const x265b200_glue_job* jobs, int64_t n, int p0, int p1, int p2, int p3);
+/* cu[].var (pixel_var, pixel.cpp:703-720): out[i] = sum | (uint64)sqr << 32 of the size x size block at src + off[i] */
+int x265b200_var_dev(x265b200_ctx* ctx, int depth, int size, const void* src, int64_t stride, const int64_t* off, int64_t n, uint64_t* out);
+/* cu[].psy_cost_pp (psyCost_pp, pixel.cpp:726-757), size = 4, 8, 16, 32 or 64 */
+int x265b200_psy_cost_dev(x265b200_ctx* ctx, int depth, int size, const void* source, int64_t sstride, const void* recon, int64_t rstride,
+                          const int64_t* offS, const int64_t* offR, int64_t n, int32_t* out);
+/* cu[].copy_cnt (copy_count, dct.cpp:728-743): coeff + i*size*size (contiguous) <- residual + off[i]; numSig[i] = non-zeros */
+int x265b200_copy_cnt_dev(x265b200_ctx* ctx, int size, int16_t* coeff, const int16_t* residual, int64_t resiStride,
+                          const int64_t* off, int64_t n, uint32_t* numSig);
+/* denoiseDct (dct.cpp:745-755) over n TUs of numCoeff coefficients (contiguous) that share resSum[numCoeff] (accumulated
+ * into, as NoiseReduction does per TU size/type) and offset[numCoeff] */
+int x265b200_denoise_dct_dev(x265b200_ctx* ctx, int16_t* dctCoef, uint32_t* resSum, const uint16_t* offset, int numCoeff, int64_t n);
+/* cu[].lowpass_dct (lowPassDct8/16/32_c, lowpassdct.cpp:33-111), sizeIdx 1..3 = 8/16/32: 2x2 average -> half-size
+ * standard DCT -> zero-padded N x N with the DC replaced by the scaled block sum.  Same addressing as x265b200_dct_dev. */
+int x265b200_lowpass_dct_dev(x265b200_ctx* ctx, int sizeIdx, int depth, const int16_t* src, int64_t srcBlockStride,
+                             int64_t srcStride, int16_t* dst, int64_t n);
+
 /* ---- interpolation: replaces pu[].luma_hpp/hps/vpp/vps/vsp/vss/hvpp/convert_p2s and
  *      chroma[].pu[].filter_* / p2s (primitives.h:176-182,253-263,398-407; ipfilter.cpp:40-370).
  * taps = 8 (luma) or 4 (chroma).  Job i filters the w x h block at src + srcOff into dst + dstOff
@@ -155,10 +190,14 @@ int x265b200_intra_allangs_dev(x265b200_ctx* ctx, int depth, int log2N, const vo
  *      searches.  One job = one call of motionEstimate(); per-job semantics are identical:
  *      mvmin/mvmax are full-pel inclusive bounds, mvp and mvc[] are quarter-pel, the result
  *      (outMv, outCost) is `outQMv` and the return value.  searchMethod uses the X265_*_SEARCH
- *      numbering of x265.h:492-497 (0 DIA, 1 HEX, 2 UMH, 3 STAR, 5 FULL; 4 SEA is a "next" row).
+ *      numbering of x265.h:492-497 (0 DIA, 1 HEX, 2 UMH, 3 STAR, 5 FULL; 4 SEA is a "next" row);
+ *      searchMethod 6 (X265B200_ME_REFINE) runs MotionEstimate::refineMV instead (motion.cpp:606-737:
+ *      predictor, one square refine, sub-pel with the fixed workload[5]; mvc/merange/subpelRefine/maxSlices unused;
+ *      the reference returns only the MV, outCost is the final SATD + mvcost).
  *      lambda = x265_lambda_tab[qp] of BitCost::setQP (bitcost.cpp:31-60).  x265b200_me_batch_dev is the luma-only
  *      form (bChromaSATD = false: subme <= 2, or the lookahead-style setSourcePU of motion.cpp:167);
  *      x265b200_me_batch_chroma_dev below is the encode-style form with the chroma residual term. */
+#define X265B200_ME_REFINE 6
 typedef struct {
     int32_t puX, puY;                          /* PU position in the fenc/ref planes (pixels)   */
     int32_t w, h;                              /* PU size (any of the 24 inter LumaPU shapes)   */

@@ -291,6 +291,23 @@ void ref_frame_init_lowres(const void* src0, void* dst0, void* dsth, void* dstv,
     ensure_init();
     primitives.frameInitLowres((const pixel*)src0, (pixel*)dst0, (pixel*)dsth, (pixel*)dstv, (pixel*)dstc, srcStride, dstStride, width, height);
 }
+/* glue slots used by tests/test_glue_gpu.py (the rest is pinned by the reference's own TestBench) */
+void ref_lowpass_dct(int idx, const int16_t* src, int16_t* dst, intptr_t srcStride)
+{
+    ensure_init();
+    /* lowPassDct*_c call through cu[].standard_dct, which only enableLowpassDCTPrimitives (primitives.cpp:75-86,
+     * --lowpass-dct) fills in; do that half of it here without rerouting cu[].dct */
+    for (int i = BLOCK_4x4; i <= BLOCK_32x32; i++)
+        if (!primitives.cu[i].standard_dct) primitives.cu[i].standard_dct = primitives.cu[i].dct;
+    primitives.cu[idx].lowpass_dct(src, dst, srcStride);
+}
+void ref_weight_pp(const void* src, void* dst, intptr_t stride, int w, int h, int w0, int round, int shift, int offset)
+{ ensure_init(); primitives.weight_pp((const pixel*)src, (pixel*)dst, stride, w, h, w0, round, shift, offset); }
+void ref_weight_sp(const int16_t* src, void* dst, intptr_t ss, intptr_t ds, int w, int h, int w0, int round, int shift, int offset)
+{ ensure_init(); primitives.weight_sp(src, (pixel*)dst, ss, ds, w, h, w0, round, shift, offset); }
+int ref_psy_cost(int idx, const void* s, intptr_t ss, const void* r, intptr_t rs) { ensure_init(); return primitives.cu[idx].psy_cost_pp((const pixel*)s, ss, (const pixel*)r, rs); }
+void ref_addavg(int part, const int16_t* a, const int16_t* b, void* dst, intptr_t sa, intptr_t sb, intptr_t ds)
+{ ensure_init(); primitives.pu[part].addAvg[NONALIGNED](a, b, (pixel*)dst, sa, sb, ds); }
 uint64_t ref_var(int idx, const void* pix, intptr_t stride) { ensure_init(); return primitives.cu[idx].var((const pixel*)pix, stride); }
 
 /* ---- BitCost table (bitcost.cpp:31-110): cost[i] for i in [-2*BC_MAX_MV, 2*BC_MAX_MV] --- */
@@ -340,11 +357,18 @@ int ref_me_batch(const void* fencPlane, intptr_t fencStride, const void* refPlan
         ref.isLowres = false;
         intptr_t off = j.puX + (intptr_t)j.puY * refStride;
         /* fenc and ref planes must share one stride for this entry point (blockOffset is reused) */
-        me.setSourcePU((pixel*)fencPlane, fencStride, off, j.w, j.h, searchMethod, searchMethod, searchMethod, subpelRefine);
+        const int sm = searchMethod == 6 ? X265_HEX_SEARCH : searchMethod;
+        me.setSourcePU((pixel*)fencPlane, fencStride, off, j.w, j.h, sm, sm, sm, subpelRefine);
         MV mvmin(j.mvminX, j.mvminY), mvmax(j.mvmaxX, j.mvmaxY), mvp(j.mvpX, j.mvpY), out(0, 0);
         MV mvc[8];
         for (int k = 0; k < j.numCand; k++) mvc[k] = MV(j.mvc[k][0], j.mvc[k][1]);
-        j.outCost = me.motionEstimate(&ref, mvmin, mvmax, mvp, j.numCand, mvc, merange, out, (uint32_t)maxSlices);
+        if (searchMethod == 6)      /* MotionEstimate::refineMV (motion.cpp:606-737): returns only the MV */
+        {
+            me.refineMV(&ref, mvmin, mvmax, mvp, out);
+            j.outCost = 0;
+        }
+        else
+            j.outCost = me.motionEstimate(&ref, mvmin, mvmax, mvp, j.numCand, mvc, merange, out, (uint32_t)maxSlices);
         j.outMvX = out.x; j.outMvY = out.y;
     });
     for (int t = 0; t < nt; t++) delete mes[t];
@@ -501,7 +525,7 @@ extern "C" int ref_me_batch_chroma(const void* fencY, const void* fencCb, const 
             const pixel* p = fc[c] + (j.puX >> hs) + (intptr_t)(j.puY >> vs) * fencStrideC;
             for (int y = 0; y < (j.h >> vs); y++) memcpy(cu.m_buf[1 + c] + y * cu.m_csize, p + y * fencStrideC, (j.w >> hs) * sizeof(pixel));
         }
-        me.setSourcePU(cu, 0, 0, 0, j.w, j.h, searchMethod, subpelRefine, true);
+        me.setSourcePU(cu, 0, 0, 0, j.w, j.h, searchMethod == 6 ? X265_HEX_SEARCH : searchMethod, subpelRefine, true);
 
         intptr_t zero = 0;
         PicYuv pic;
@@ -517,7 +541,13 @@ extern "C" int ref_me_batch_chroma(const void* fencY, const void* fencCb, const 
         MV mvmin(j.mvminX, j.mvminY), mvmax(j.mvmaxX, j.mvmaxY), mvp(j.mvpX, j.mvpY), out(0, 0);
         MV mvc[8];
         for (int k = 0; k < j.numCand; k++) mvc[k] = MV(j.mvc[k][0], j.mvc[k][1]);
-        j.outCost = me.motionEstimate(&ref, mvmin, mvmax, mvp, j.numCand, mvc, merange, out, (uint32_t)maxSlices);
+        if (searchMethod == 6)
+        {
+            me.refineMV(&ref, mvmin, mvmax, mvp, out);
+            j.outCost = 0;
+        }
+        else
+            j.outCost = me.motionEstimate(&ref, mvmin, mvmax, mvp, j.numCand, mvc, merange, out, (uint32_t)maxSlices);
         j.outMvX = out.x; j.outMvY = out.y;
         pic.m_cuOffsetY = pic.m_cuOffsetC = pic.m_buOffsetY = pic.m_buOffsetC = NULL;
     });

@@ -57,7 +57,7 @@ def test_me_subme_levels_luma(ctx, subme):
     _run(ctx, 8, pkg.ME_HEX, subme, 32, 27, [(8, 8), (16, 16), (32, 32), (64, 64), (16, 8), (32, 24)], seed=400 + subme, n_per_size=8)
 
 
-def _run_chroma(ctx, depth, csp, method, subme, merange, qp, sizes, seed, n_per_size=6):
+def _run_chroma(ctx, depth, csp, method, subme, merange, qp, sizes, seed, n_per_size=6, mv_only=False):
     W, H = 192, 128
     pad = 64 + merange + 16
     cur, ref, S, origin = synth_pair(W, H, pad, depth=depth, seed=seed)
@@ -72,6 +72,8 @@ def _run_chroma(ctx, depth, csp, method, subme, merange, qp, sizes, seed, n_per_
     ctx.me_batch_chroma_dev(depth, dC.ptr + origin * item, S, dR.ptr + origin * item, S, csp, dCb.ptr + oc * item, dCr.ptr + oc * item, Sc,
                             dRb.ptr + oc * item, dRr.ptr + oc * item, Sc, dJ, len(job), 64, 64, method, subme, merange, lam)
     out = dJ.download(pkg.ME_JOB)
+    if mv_only:
+        ec = out["outCost"]
     bad = np.nonzero((out["outMvX"] != ex) | (out["outMvY"] != ey) | (out["outCost"] != ec))[0]
     msg = ""
     if len(bad):
@@ -102,6 +104,28 @@ def test_me_chroma_satd_422_444(ctx, csp):
 
 def test_me_chroma_satd_10bit(ctx):
     _run_chroma(ctx, 10, 1, pkg.ME_STAR, 3, 32, 32, [(8, 8), (16, 16), (32, 32), (64, 64), (32, 8), (8, 32)], seed=980)
+
+
+def test_me_refine_mv(ctx):
+    """MotionEstimate::refineMV (motion.cpp:606-737): only the MV is returned by the reference."""
+    W, H, merange, depth, qp = 192, 128, 16, 8, 30
+    pad = 64 + merange + 16
+    cur, ref, S, origin = synth_pair(W, H, pad, depth=depth, seed=4242)
+    job = make_jobs(pkg, W, H, INTER_SIZES, merange, np.random.default_rng(4243), n_per_size=6, with_cands=False)
+    ex, ey, _ = ref_me(depth, cur, ref, S, origin, job, pkg.ME_REFINE, 2, merange, qp)
+    dC, dR, dJ = ctx.to_device(cur), ctx.to_device(ref), ctx.to_device(job)
+    ctx.me_batch_dev(depth, dC.ptr + origin, S, dR.ptr + origin, S, dJ, len(job), 64, 64, pkg.ME_REFINE, 2, merange, pkg.lambda_for_qp(qp, depth))
+    out = dJ.download(pkg.ME_JOB)
+    for b in (dC, dR, dJ):
+        b.free()
+    bad = np.nonzero((out["outMvX"] != ex) | (out["outMvY"] != ey))[0]
+    assert not len(bad), "refineMV: %d/%d MVs differ, first job %s got (%d,%d) want (%d,%d)" % (
+        len(bad), len(job), job[bad[0]], out["outMvX"][bad[0]], out["outMvY"][bad[0]], ex[bad[0]], ey[bad[0]])
+    assert len(set(zip(ex.tolist(), ey.tolist()))) > 8        # the fixture moves the MVs
+
+
+def test_me_refine_mv_chroma(ctx):
+    ec = _run_chroma(ctx, 8, 1, pkg.ME_REFINE, 3, 16, 30, [(8, 8), (16, 16), (32, 32), (64, 64), (32, 16)], seed=4300, mv_only=True)
 
 
 def test_me_large_motion_star_raster(ctx):

@@ -277,6 +277,83 @@ void intra_allangs_thunk(pixel* dest, pixel* refPix, pixel* filtPix, int bLuma)
     CK(x265b200_download(C(), dest, dD, 33 * N * N * PX));
 }
 
+// ---- glue (class G of SURVEY.md 8a-bis): one-job launches of the generic element-wise kernel ---------------------
+// e0/e1/ed: element sizes of src0 / src1 / dst
+void glue_run(int op, int w, int h, void* dst, intptr_t dstStride, int ed, const void* s0, intptr_t s0Stride, int e0,
+              const void* s1, intptr_t s1Stride, int e1, int p0 = 0, int p1 = 0, int p2 = 0, int p3 = 0, int dw = -1, int dh = -1)
+{
+    if (dw < 0) { dw = w; dh = h; }
+    void* d0 = s0 ? up_span(0, s0, s0Stride, op == X265B200_GL_TRANSPOSE ? h : w, op == X265B200_GL_TRANSPOSE ? w : h, e0) : nullptr;
+    void* d1 = s1 ? up_span(1, s1, s1Stride, w, h, e1) : nullptr;
+    void* dD = dev(2, (size_t)dw * dh * ed);
+    x265b200_glue_job job = { 0, 0, 0 };
+    void* dJ = up1d(3, &job, sizeof(job));
+    CK(x265b200_glue_dev(C(), op, X265_DEPTH, w, h, dD, dw, d0, s0Stride, d1, s1Stride, (const x265b200_glue_job*)dJ, 1, p0, p1, p2, p3));
+    down2d(dst, dstStride, dD, dw, dh, ed);
+}
+template<int W, int H> void copy_pp_thunk(pixel* d, intptr_t ds, const pixel* s, intptr_t ss) { glue_run(X265B200_GL_COPY_PP, W, H, d, ds, PX, s, ss, PX, nullptr, 0, 0); }
+template<int W, int H> void copy_sp_thunk(pixel* d, intptr_t ds, const int16_t* s, intptr_t ss) { glue_run(X265B200_GL_COPY_SP, W, H, d, ds, PX, s, ss, 2, nullptr, 0, 0); }
+template<int W, int H> void copy_ps_thunk(int16_t* d, intptr_t ds, const pixel* s, intptr_t ss) { glue_run(X265B200_GL_COPY_PS, W, H, d, ds, 2, s, ss, PX, nullptr, 0, 0); }
+template<int W, int H> void copy_ss_thunk(int16_t* d, intptr_t ds, const int16_t* s, intptr_t ss) { glue_run(X265B200_GL_COPY_SS, W, H, d, ds, 2, s, ss, 2, nullptr, 0, 0); }
+template<int N> void blockfill_s_thunk(int16_t* d, intptr_t ds, int16_t val) { glue_run(X265B200_GL_FILL_S, N, N, d, ds, 2, nullptr, 0, 0, nullptr, 0, 0, val); }
+template<int N> void cpy2Dto1D_shl_thunk(int16_t* d, const int16_t* s, intptr_t ss, int shift) { glue_run(X265B200_GL_CPY2DTO1D_SHL, N, N, d, N, 2, s, ss, 2, nullptr, 0, 0, shift); }
+template<int N> void cpy2Dto1D_shr_thunk(int16_t* d, const int16_t* s, intptr_t ss, int shift) { glue_run(X265B200_GL_CPY2DTO1D_SHR, N, N, d, N, 2, s, ss, 2, nullptr, 0, 0, shift); }
+template<int N> void cpy1Dto2D_shl_thunk(int16_t* d, const int16_t* s, intptr_t ds, int shift) { glue_run(X265B200_GL_CPY1DTO2D_SHL, N, N, d, ds, 2, s, N, 2, nullptr, 0, 0, shift); }
+template<int N> void cpy1Dto2D_shr_thunk(int16_t* d, const int16_t* s, intptr_t ds, int shift) { glue_run(X265B200_GL_CPY1DTO2D_SHR, N, N, d, ds, 2, s, N, 2, nullptr, 0, 0, shift); }
+template<int N> void calcresidual_thunk(const pixel* fenc, const pixel* pred, int16_t* resi, intptr_t stride) { glue_run(X265B200_GL_SUB_PS, N, N, resi, stride, 2, fenc, stride, PX, pred, stride, PX); }
+template<int W, int H> void sub_ps_thunk(int16_t* d, intptr_t ds, const pixel* a, const pixel* b, intptr_t sa, intptr_t sb) { glue_run(X265B200_GL_SUB_PS, W, H, d, ds, 2, a, sa, PX, b, sb, PX); }
+template<int W, int H> void add_ps_thunk(pixel* d, intptr_t ds, const pixel* a, const int16_t* b, intptr_t sa, intptr_t sb) { glue_run(X265B200_GL_ADD_PS, W, H, d, ds, PX, a, sa, PX, b, sb, 2); }
+template<int W, int H> void pixelavg_pp_thunk(pixel* d, intptr_t ds, const pixel* a, intptr_t sa, const pixel* b, intptr_t sb, int) { glue_run(X265B200_GL_PIXELAVG_PP, W, H, d, ds, PX, a, sa, PX, b, sb, PX); }
+template<int W, int H> void addAvg_thunk(const int16_t* a, const int16_t* b, pixel* d, intptr_t sa, intptr_t sb, intptr_t ds) { glue_run(X265B200_GL_ADDAVG, W, H, d, ds, PX, a, sa, 2, b, sb, 2); }
+template<int N> void transpose_thunk(pixel* d, const pixel* s, intptr_t stride) { glue_run(X265B200_GL_TRANSPOSE, N, N, d, N, PX, s, stride, PX, nullptr, 0, 0); }
+void weight_pp_thunk(const pixel* s, pixel* d, intptr_t stride, int w, int h, int w0, int round, int shift, int offset)
+{
+    glue_run(X265B200_GL_WEIGHT_PP, w, h, d, stride, PX, s, stride, PX, nullptr, 0, 0, w0, round, shift, offset);
+}
+void weight_sp_thunk(const int16_t* s, pixel* d, intptr_t ss, intptr_t ds, int w, int h, int w0, int round, int shift, int offset)
+{
+    glue_run(X265B200_GL_WEIGHT_SP, w, h, d, ds, PX, s, ss, 2, nullptr, 0, 0, w0, round, shift, offset);
+}
+template<int N> uint64_t var_thunk(const pixel* pix, intptr_t stride)
+{
+    void* dS = up_span(0, pix, stride, N, N, PX);
+    int64_t zero = 0; void* dOff = up1d(1, &zero, 8); void* dO = dev(2, 8);
+    CK(x265b200_var_dev(C(), X265_DEPTH, N, dS, stride, (const int64_t*)dOff, 1, (uint64_t*)dO));
+    uint64_t r; CK(x265b200_download(C(), &r, dO, 8));
+    return r;
+}
+template<int N> int psy_cost_pp_thunk(const pixel* src, intptr_t ss, const pixel* rec, intptr_t rs)
+{
+    void* dS = up_span(0, src, ss, N, N, PX); void* dR = up_span(1, rec, rs, N, N, PX);
+    int64_t zero = 0; void* dOff = up1d(3, &zero, 8); void* dO = dev(2, 8);
+    CK(x265b200_psy_cost_dev(C(), X265_DEPTH, N, dS, ss, dR, rs, (const int64_t*)dOff, (const int64_t*)dOff, 1, (int32_t*)dO));
+    int32_t r; CK(x265b200_download(C(), &r, dO, 4));
+    return r;
+}
+template<int N> uint32_t copy_cnt_thunk(int16_t* coeff, const int16_t* resi, intptr_t stride)
+{
+    void* dS = up_span(0, resi, stride, N, N, 2);
+    int64_t zero = 0; void* dOff = up1d(3, &zero, 8); void* dC = dev(1, N * N * 2); void* dO = dev(2, 8);
+    CK(x265b200_copy_cnt_dev(C(), N, (int16_t*)dC, (const int16_t*)dS, stride, (const int64_t*)dOff, 1, (uint32_t*)dO));
+    CK(x265b200_download(C(), coeff, dC, N * N * 2));
+    uint32_t r; CK(x265b200_download(C(), &r, dO, 4));
+    return r;
+}
+void denoise_dct_thunk(int16_t* coef, uint32_t* resSum, const uint16_t* offset, int numCoeff)
+{
+    void* dC = up1d(0, coef, numCoeff * 2); void* dR = up1d(1, resSum, numCoeff * 4); void* dF = up1d(2, offset, numCoeff * 2);
+    CK(x265b200_denoise_dct_dev(C(), (int16_t*)dC, (uint32_t*)dR, (const uint16_t*)dF, numCoeff, 1));
+    CK(x265b200_download(C(), coef, dC, numCoeff * 2)); CK(x265b200_download(C(), resSum, dR, numCoeff * 4));
+}
+template<int IDX, int N>
+void lowpass_dct_thunk(const int16_t* src, int16_t* dst, intptr_t srcStride)
+{
+    void* dS = up_span(0, src, srcStride, N, N, 2);
+    void* dD = dev(1, N * N * 2);
+    CK(x265b200_lowpass_dct_dev(C(), IDX, X265_DEPTH, (const int16_t*)dS, 0, srcStride, (int16_t*)dD, 1));
+    CK(x265b200_download(C(), dst, dD, N * N * 2));
+}
+
 } // namespace
 
 namespace X265_NS {
@@ -303,7 +380,12 @@ void setupAssemblyPrimitives(EncoderPrimitives& p, int /*cpuMask: SIMD flags are
     p.pu[LUMA_ ## W ## x ## H].luma_vss = ip_vss<8, W, H>; \
     p.pu[LUMA_ ## W ## x ## H].luma_hvpp = ip_hvpp<W, H>; \
     p.pu[LUMA_ ## W ## x ## H].convert_p2s[NONALIGNED] = ip_p2s<W, H>; \
-    p.pu[LUMA_ ## W ## x ## H].convert_p2s[ALIGNED] = ip_p2s<W, H>;
+    p.pu[LUMA_ ## W ## x ## H].convert_p2s[ALIGNED] = ip_p2s<W, H>; \
+    p.pu[LUMA_ ## W ## x ## H].copy_pp = copy_pp_thunk<W, H>; \
+    p.pu[LUMA_ ## W ## x ## H].pixelavg_pp[NONALIGNED] = pixelavg_pp_thunk<W, H>; \
+    p.pu[LUMA_ ## W ## x ## H].pixelavg_pp[ALIGNED] = pixelavg_pp_thunk<W, H>; \
+    p.pu[LUMA_ ## W ## x ## H].addAvg[NONALIGNED] = addAvg_thunk<W, H>; \
+    p.pu[LUMA_ ## W ## x ## H].addAvg[ALIGNED] = addAvg_thunk<W, H>;
     PU(4, 4) PU(8, 8) PU(16, 16) PU(32, 32) PU(64, 64)
     PU(8, 4) PU(4, 8) PU(16, 8) PU(8, 16) PU(32, 16) PU(16, 32) PU(64, 32) PU(32, 64)
     PU(16, 12) PU(12, 16) PU(16, 4) PU(4, 16) PU(32, 24) PU(24, 32) PU(32, 8) PU(8, 32)
@@ -330,7 +412,14 @@ void setupAssemblyPrimitives(EncoderPrimitives& p, int /*cpuMask: SIMD flags are
     p.cu[IDX].sse_pp = sse_pp_thunk<N, N>; \
     p.cu[IDX].sse_ss = sse_ss_thunk<N, N>; \
     p.cu[IDX].ssd_s[NONALIGNED] = ssd_s_thunk<N>; \
-    p.cu[IDX].ssd_s[ALIGNED] = ssd_s_thunk<N>;
+    p.cu[IDX].ssd_s[ALIGNED] = ssd_s_thunk<N>; \
+    p.cu[IDX].copy_pp = copy_pp_thunk<N, N>; p.cu[IDX].copy_sp = copy_sp_thunk<N, N>; \
+    p.cu[IDX].copy_ps = copy_ps_thunk<N, N>; p.cu[IDX].copy_ss = copy_ss_thunk<N, N>; \
+    p.cu[IDX].sub_ps = sub_ps_thunk<N, N>; \
+    p.cu[IDX].add_ps[NONALIGNED] = add_ps_thunk<N, N>; p.cu[IDX].add_ps[ALIGNED] = add_ps_thunk<N, N>; \
+    p.cu[IDX].blockfill_s[NONALIGNED] = blockfill_s_thunk<N>; p.cu[IDX].blockfill_s[ALIGNED] = blockfill_s_thunk<N>; \
+    p.cu[IDX].var = var_thunk<N>; \
+    p.cu[IDX].psy_cost_pp = psy_cost_pp_thunk<N>;
     CU(BLOCK_4x4, 4, 2) CU(BLOCK_8x8, 8, 3) CU(BLOCK_16x16, 16, 4) CU(BLOCK_32x32, 32, 5) CU(BLOCK_64x64, 64, 6)
 #undef CU
 
@@ -338,6 +427,12 @@ void setupAssemblyPrimitives(EncoderPrimitives& p, int /*cpuMask: SIMD flags are
     p.cu[IDX].dct = dct_thunk<IDX, N>; p.cu[IDX].standard_dct = dct_thunk<IDX, N>; \
     p.cu[IDX].idct = idct_thunk<IDX, N>; \
     p.cu[IDX].count_nonzero = count_nonzero_thunk<N>; \
+    p.cu[IDX].copy_cnt = copy_cnt_thunk<N>; \
+    p.cu[IDX].calcresidual[NONALIGNED] = calcresidual_thunk<N>; p.cu[IDX].calcresidual[ALIGNED] = calcresidual_thunk<N>; \
+    p.cu[IDX].transpose = transpose_thunk<N>; \
+    p.cu[IDX].cpy2Dto1D_shl = cpy2Dto1D_shl_thunk<N>; p.cu[IDX].cpy2Dto1D_shr = cpy2Dto1D_shr_thunk<N>; \
+    p.cu[IDX].cpy1Dto2D_shl[NONALIGNED] = cpy1Dto2D_shl_thunk<N>; p.cu[IDX].cpy1Dto2D_shl[ALIGNED] = cpy1Dto2D_shl_thunk<N>; \
+    p.cu[IDX].cpy1Dto2D_shr = cpy1Dto2D_shr_thunk<N>; \
     p.cu[IDX].intra_filter = intra_filter_thunk<LOG2>; \
     p.cu[IDX].intra_pred_allangs = intra_allangs_thunk<LOG2>; \
     p.cu[IDX].intra_pred[PLANAR_IDX] = intra_pred_thunk<LOG2, 0>; p.cu[IDX].intra_pred[DC_IDX] = intra_pred_thunk<LOG2, 1>; \
@@ -350,6 +445,14 @@ void setupAssemblyPrimitives(EncoderPrimitives& p, int /*cpuMask: SIMD flags are
     p.nquant = nquant_thunk;
     p.dequant_normal = dequant_normal_thunk;
     p.dequant_scaling = dequant_scaling_thunk;
+    p.cu[BLOCK_64x64].transpose = transpose_thunk<64>;
+    p.weight_pp = weight_pp_thunk;
+    p.weight_sp = weight_sp_thunk;
+    p.denoiseDct = denoise_dct_thunk;
+    // installed unconditionally; x265_setup_primitives only routes cu[].dct through it with --lowpass-dct (primitives.cpp:75-86)
+    p.cu[BLOCK_8x8].lowpass_dct = lowpass_dct_thunk<1, 8>;
+    p.cu[BLOCK_16x16].lowpass_dct = lowpass_dct_thunk<2, 16>;
+    p.cu[BLOCK_32x32].lowpass_dct = lowpass_dct_thunk<3, 32>;
 }
 
 } // namespace X265_NS

@@ -235,8 +235,49 @@ Ctx.intra_filter_dev = _ctx_intra_filter_dev
 Ctx.intra_allangs_dev = _ctx_intra_allangs_dev
 
 
+# ---- glue ----------------------------------------------------------------------------------------
+(GL_COPY_PP, GL_COPY_SS, GL_COPY_SP, GL_COPY_PS, GL_FILL_S, GL_CPY2DTO1D_SHL, GL_CPY2DTO1D_SHR, GL_CPY1DTO2D_SHL, GL_CPY1DTO2D_SHR,
+ GL_SUB_PS, GL_ADD_PS, GL_ADDAVG, GL_PIXELAVG_PP, GL_TRANSPOSE, GL_WEIGHT_PP, GL_WEIGHT_SP) = range(16)
+GLUE_JOB = np.dtype([("dstOff", np.int64), ("src0Off", np.int64), ("src1Off", np.int64)])
+
+
+def _ctx_glue_dev(self, op, depth, w, h, dDst, dstStride, dSrc0, src0Stride, dSrc1, src1Stride, dJobs, n, p0=0, p1=0, p2=0, p3=0):
+    self._chk(self.L.x265b200_glue_dev(self.h, int(op), int(depth), int(w), int(h), _vp(dDst), _i64(dstStride), _vp(dSrc0), _i64(src0Stride),
+                                       _vp(dSrc1), _i64(src1Stride), _vp(dJobs), _i64(n), int(p0), int(p1), int(p2), int(p3)))
+
+
+def _ctx_var_dev(self, depth, size, dSrc, stride, dOff, n, dOut):
+    self._chk(self.L.x265b200_var_dev(self.h, int(depth), int(size), _vp(dSrc), _i64(stride), _vp(dOff), _i64(n), _vp(dOut)))
+
+
+def _ctx_psy_cost_dev(self, depth, size, dSrc, sstride, dRec, rstride, dOffS, dOffR, n, dOut):
+    self._chk(self.L.x265b200_psy_cost_dev(self.h, int(depth), int(size), _vp(dSrc), _i64(sstride), _vp(dRec), _i64(rstride),
+                                           _vp(dOffS), _vp(dOffR), _i64(n), _vp(dOut)))
+
+
+def _ctx_copy_cnt_dev(self, size, dCoeff, dResi, stride, dOff, n, dNumSig):
+    self._chk(self.L.x265b200_copy_cnt_dev(self.h, int(size), _vp(dCoeff), _vp(dResi), _i64(stride), _vp(dOff), _i64(n), _vp(dNumSig)))
+
+
+def _ctx_denoise_dct_dev(self, dCoef, dResSum, dOffset, numCoeff, n):
+    self._chk(self.L.x265b200_denoise_dct_dev(self.h, _vp(dCoef), _vp(dResSum), _vp(dOffset), int(numCoeff), _i64(n)))
+
+
+def _ctx_lowpass_dct_dev(self, sizeIdx, depth, dSrc, srcBlockStride, srcStride, dDst, n):
+    self._chk(self.L.x265b200_lowpass_dct_dev(self.h, int(sizeIdx), int(depth), _vp(dSrc), _i64(srcBlockStride), _i64(srcStride), _vp(dDst), _i64(n)))
+
+
+Ctx.glue_dev = _ctx_glue_dev
+Ctx.var_dev = _ctx_var_dev
+Ctx.psy_cost_dev = _ctx_psy_cost_dev
+Ctx.copy_cnt_dev = _ctx_copy_cnt_dev
+Ctx.denoise_dct_dev = _ctx_denoise_dct_dev
+Ctx.lowpass_dct_dev = _ctx_lowpass_dct_dev
+
+
 # ---- motion estimation -----------------------------------------------------------------------------
 ME_DIA, ME_HEX, ME_UMH, ME_STAR, ME_SEA, ME_FULL = range(6)
+ME_REFINE = 6      # MotionEstimate::refineMV (motion.cpp:606-737) through the me_batch entry points
 ME_JOB = np.dtype([("puX", np.int32), ("puY", np.int32), ("w", np.int32), ("h", np.int32),
                    ("mvminX", np.int32), ("mvminY", np.int32), ("mvmaxX", np.int32), ("mvmaxY", np.int32),
                    ("mvpX", np.int32), ("mvpY", np.int32), ("numCand", np.int32), ("mvc", np.int32, (8, 2)),

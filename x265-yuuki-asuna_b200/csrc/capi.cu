@@ -88,6 +88,15 @@ int me_batch_dev(Ctx*, int depth, const void* fencPlane, int64_t fencStride, con
                  int64_t refStride, const x265b200_me_chroma* chroma, x265b200_me_job* jobs, int64_t n, int maxW, int maxH,
                  int searchMethod, int subpelRefine, int merange, double lambda, int maxSlices);
 void host_bitcost_table(double lambda, uint16_t* out);
+int glue_dev(Ctx*, int op, int depth, int w, int h, void* dst, int64_t dstStride, const void* src0, int64_t src0Stride,
+             const void* src1, int64_t src1Stride, const x265b200_glue_job* jobs, int64_t n, int p0, int p1, int p2, int p3);
+int var_dev(Ctx*, int depth, int size, const void* src, int64_t stride, const int64_t* off, int64_t n, uint64_t* out);
+int psycost_dev(Ctx*, int depth, int dim, const void* src, int64_t sstride, const void* rec, int64_t rstride,
+                const int64_t* offS, const int64_t* offR, int64_t n, int32_t* out);
+int copy_cnt_dev(Ctx*, int size, int16_t* coeff, const int16_t* resi, int64_t stride, const int64_t* off, int64_t n, uint32_t* numSig);
+int denoise_dct_dev(Ctx*, int16_t* coef, uint32_t* resSum, const uint16_t* offset, int numCoeff, int64_t n);
+int lowpass_front_dev(Ctx*, const int16_t* src, int64_t srcBlockStride, int64_t srcStride, int64_t n, int N, int16_t* avg, int32_t* total);
+int lowpass_back_dev(Ctx*, const int16_t* coefHalf, const int32_t* total, int64_t n, int N, int16_t* dst);
 int debug_me_frame_cycles(unsigned long long* out);
 int me_frame_dev(Ctx*, int depth, const void* curOrigin, int64_t curStride, const void* const* refOriginsHost, int numRefs, int64_t refStride,
                  int marginX, int marginY, int rowsTotal, int ctuCols, int ctuRows, int puMask, const int32_t* mvpCtu,
@@ -333,6 +342,52 @@ int x265b200_intra_allangs_dev(x265b200_ctx* ctx, int depth, int log2N, const vo
 {
     REQUIRE_CTX(ctx);
     return intra_allangs_dev(CTX(ctx), depth, log2N, refPix, filtPix, dest, bLuma, n);
+}
+
+// ---- glue ---------------------------------------------------------------------------------------
+int x265b200_glue_dev(x265b200_ctx* ctx, int op, int depth, int w, int h, void* dst, int64_t dstStride,
+                      const void* src0, int64_t src0Stride, const void* src1, int64_t src1Stride,
+                      const x265b200_glue_job* jobs, int64_t n, int p0, int p1, int p2, int p3)
+{
+    REQUIRE_CTX(ctx);
+    return glue_dev(CTX(ctx), op, depth, w, h, dst, dstStride, src0, src0Stride, src1, src1Stride, jobs, n, p0, p1, p2, p3);
+}
+int x265b200_var_dev(x265b200_ctx* ctx, int depth, int size, const void* src, int64_t stride, const int64_t* off, int64_t n, uint64_t* out)
+{
+    REQUIRE_CTX(ctx);
+    return var_dev(CTX(ctx), depth, size, src, stride, off, n, out);
+}
+int x265b200_psy_cost_dev(x265b200_ctx* ctx, int depth, int size, const void* source, int64_t sstride, const void* recon, int64_t rstride,
+                          const int64_t* offS, const int64_t* offR, int64_t n, int32_t* out)
+{
+    REQUIRE_CTX(ctx);
+    return psycost_dev(CTX(ctx), depth, size, source, sstride, recon, rstride, offS, offR, n, out);
+}
+int x265b200_copy_cnt_dev(x265b200_ctx* ctx, int size, int16_t* coeff, const int16_t* residual, int64_t resiStride,
+                          const int64_t* off, int64_t n, uint32_t* numSig)
+{
+    REQUIRE_CTX(ctx);
+    return copy_cnt_dev(CTX(ctx), size, coeff, residual, resiStride, off, n, numSig);
+}
+int x265b200_denoise_dct_dev(x265b200_ctx* ctx, int16_t* dctCoef, uint32_t* resSum, const uint16_t* offset, int numCoeff, int64_t n)
+{
+    REQUIRE_CTX(ctx);
+    return denoise_dct_dev(CTX(ctx), dctCoef, resSum, offset, numCoeff, n);
+}
+int x265b200_lowpass_dct_dev(x265b200_ctx* ctx, int sizeIdx, int depth, const int16_t* src, int64_t srcBlockStride,
+                             int64_t srcStride, int16_t* dst, int64_t n)
+{
+    REQUIRE_CTX(ctx);
+    if (sizeIdx < 1 || sizeIdx > 3) { set_error("lowpass_dct: sizeIdx %d (1..3 = 8/16/32)", sizeIdx); return -1; }
+    if (n <= 0) return 0;
+    const int N = 4 << sizeIdx, half = N >> 1;
+    void *dAvg = nullptr, *dCoef = nullptr, *dTot = nullptr;
+    if (scratch_dev(CTX(ctx), 0, (size_t)n * half * half * 2, &dAvg) || scratch_dev(CTX(ctx), 1, (size_t)n * half * half * 2, &dCoef) ||
+        scratch_dev(CTX(ctx), 2, (size_t)n * 4, &dTot)) return -1;
+    if (lowpass_front_dev(CTX(ctx), src, srcBlockStride, srcStride, n, N, (int16_t*)dAvg, (int32_t*)dTot)) return -1;
+    // the half-size transform is the table's own standard_dct (lowpassdct.cpp:117-119)
+    if (x265b200_dct_dev(ctx, sizeIdx - 1, depth, (const int16_t*)dAvg, (int64_t)half * half, half, (int16_t*)dCoef, n)) return -1;
+    return lowpass_back_dev(CTX(ctx), (const int16_t*)dCoef, (const int32_t*)dTot, n, N, dst);
 }
 
 // ---- motion estimation ----------------------------------------------------------------------------

@@ -26,7 +26,8 @@
 namespace x265b200 {
 inline namespace ME_VARIANT {
 
-enum { ME_DIA = 0, ME_HEX = 1, ME_UMH = 2, ME_STAR = 3, ME_SEA = 4, ME_FULL = 5 };   // x265.h:492-497
+enum { ME_DIA = 0, ME_HEX = 1, ME_UMH = 2, ME_STAR = 3, ME_SEA = 4, ME_FULL = 5,   // x265.h:492-497
+       ME_REFINE = 6 };   // not a search method of the reference: selects MotionEstimate::refineMV (motion.cpp:606-737)
 #define ME_COST_MAX (1 << 28)                                                       // motion.h:65
 
 struct MV2 { int x, y; };
@@ -1138,8 +1139,12 @@ __device__ int motion_estimate(const MEState<pixel>& s, MV2 mvmin, MV2 mvmax, MV
     if ((pmv.x | pmv.y) & 3)
         S.bcost = S.sadAt(S.bmv.x, S.bmv.y) + S.fcost(S.bmv.x, S.bmv.y);
 
+    // refineMV (:606-737) measures neither the zero MV nor candidates: predictor, square refine, workload[5] subpel
+    const bool refineOnly = searchMethod == ME_REFINE;
+    if (refineOnly) numCand = 0;
+
     // measure SAD cost at MV(0) if MVP is not zero (:786-796)
-    if (pmv.x | pmv.y)
+    if ((pmv.x | pmv.y) && !refineOnly)
     {
         int cost = warp_sad_block<pixel>(s, s.gfref, s.gstride) + mvcost(s, 0, 0);
         if (cost < S.bcost)
@@ -1190,6 +1195,9 @@ __device__ int motion_estimate(const MEState<pixel>& s, MV2 mvmin, MV2 mvmax, MV
     }
     case ME_HEX:
         S.hexSearch(merange);
+        break;
+    case ME_REFINE:       // motion.cpp:644-663
+        S.squareRefine();
         break;
     case ME_UMH:      // motion.cpp:946-1130
     {
@@ -1355,17 +1363,17 @@ __device__ int motion_estimate(const MEState<pixel>& s, MV2 mvmin, MV2 mvmax, MV
     if (bprecost < S.bcost) { bmv = bestpre; bcost = bprecost; }
     else { bmv = mv2(S.bmv.x << 2, S.bmv.y << 2); bcost = S.bcost; }
 
-    const SubpelWL wl = c_workload[subpelRefine];
+    const SubpelWL wl = c_workload[refineOnly ? 5 : subpelRefine];          // refineMV: fixed workload[5] (:673)
 
     // slice bound clamp (:1458-1463)
-    if ((maxSlices > 1) & ((bmv.y < qmvmin.y) | (bmv.y > qmvmax.y)))
+    if ((maxSlices > 1) & !refineOnly & ((bmv.y < qmvmin.y) | (bmv.y > qmvmax.y)))
     {
         bmv.y = min(max(bmv.y, qmvmin.y), qmvmax.y);
         bcost = subpel_compare<pixel>(s, bmv.x, bmv.y, true) + mvcost(s, bmv.x, bmv.y);
     }
 
-    if (!bcost)
-        bcost = mvcost(s, bmv.x, bmv.y);                                  // :1465-1470
+    if (!bcost && !refineOnly)
+        bcost = mvcost(s, bmv.x, bmv.y);                                  // :1465-1470 (refineMV has no such exit)
     else if (s.isLowres)                                                  // :1471-1503
     {
         int bdir = 0;

@@ -158,7 +158,7 @@ int me_batch_dev(Ctx* ctx, int depth, const void* fencPlane, int64_t fencStride,
 {
     if (n <= 0) return 0;
     if (searchMethod == ME_SEA) { set_error("me_batch: --me sea needs the SEA integral planes (next row, SURVEY.md 8f-3)"); return -1; }
-    if (searchMethod < 0 || searchMethod > ME_FULL) { set_error("me_batch: searchMethod %d", searchMethod); return -1; }
+    if (searchMethod < 0 || searchMethod > ME_REFINE) { set_error("me_batch: searchMethod %d", searchMethod); return -1; }
     if (subpelRefine < 0 || subpelRefine > 7) { set_error("me_batch: subpelRefine %d", subpelRefine); return -1; }
     if (maxW < 8 && maxH < 8) { set_error("me_batch: inter PUs are at least 8x4 / 4x8"); return -1; }
     if (maxW > 64 || maxH > 64 || (maxW & 3) || (maxH & 3)) { set_error("me_batch: maxW/maxH %dx%d", maxW, maxH); return -1; }
