@@ -400,10 +400,64 @@ def main():
                                       "note": "instruction-issue/fetch-bound pattern search over smem-staged windows (DESIGN.md 5, profiles/r01_me_frame_v5.txt); HBM figure shown for scale only"}
         if world == 1:
             line["cpu_baseline"] = cpu_baseline()
+            try:
+                line["lookahead"] = lookahead_leg(pkg, ctx, ring, origin)
+            except Exception as e:      # noqa: BLE001  (extra measurement; never lose the main line to it)
+                line["lookahead"] = {"unavailable": str(e)[:200]}
         print(json.dumps(line))
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def lookahead_leg(pkg, ctx, ring, origin, nframes=8, bframes=4):
+    """The lookahead half of the path (NOT part of `value`): Lowres::init + lowresIntraEstimate per frame and the
+    estimateFrameCost list searches `nframes` frames trigger at preset medium (bframes 4: 2 x 5 per frame), batched
+    into ONE launch the way the encoder's lookahead queue allows.  Timed with host clocks around stream syncs."""
+    Wc, Hc = W, CTU_ROWS * CTU
+    mx, my = PAD, 80
+    wcu, hcu = (Wc // 2 + 7) // 8, (Hc // 2 + 7) // 8
+    lw, ll = wcu * 8, hcu * 8
+    ls = (Wc // 2 + 2 * mx + 31) & ~31
+    planesize, padoff, ncu = ls * (ll + 2 * my), ls * my + mx, wcu * hcu
+    NF = nframes + 2 * (bframes + 1)
+    planes = [[ctx.to_device(np.zeros(planesize, dtype=np.uint8)) for _ in range(4)] for _ in range(NF)]
+    ptrs = np.array([[b.ptr + padoff for b in fr] for fr in planes], dtype=np.int64)
+    lam = pkg.lambda_for_qp(12, 8)
+    dIC = [ctx.empty(ncu * 4) for _ in range(NF)]
+    dIM, dLC0, dRS0, dSm0 = ctx.empty(ncu), ctx.empty(ncu * 2), ctx.empty(hcu * 4), ctx.empty(8)
+
+    def init_and_intra():
+        for i in range(NF):
+            ctx.lowres_init_dev(8, ring[i].data_ptr() + origin, STRIDE, ptrs[i], ls, lw, ll, mx, my)
+            ctx.la_intra_dev(8, ptrs[i, 0], ls, wcu, hcu, None, 5 * int(lam), dIC[i], dIM, dLC0, dRS0, dSm0)
+    init_and_intra(); ctx.sync()
+    t0 = time.perf_counter(); init_and_intra(); ctx.sync()
+    pre_ms = (time.perf_counter() - t0) * 1e3 / NF
+    dPlanePtrs = ctx.to_device(ptrs)
+    dIntraPtrs = ctx.to_device(np.array([b.ptr for b in dIC], dtype=np.int64))
+    nslots = NF * 2 * (bframes + 2)
+    dMv, dMvC = ctx.to_device(np.zeros(nslots * ncu * 2, dtype=np.int32)), ctx.to_device(np.zeros(nslots * ncu, dtype=np.int32))
+    wave = [(b - dd, b + dd, b) for b in range(bframes + 1, bframes + 1 + nframes) for dd in range(1, bframes + 2)]
+    tr = np.zeros(len(wave), dtype=pkg.LA_TRIPLE)
+    for t, (p0, p1, b) in enumerate(wave):
+        tr[t]["b"], tr[t]["p0"], tr[t]["p1"] = b, p0, p1
+        for lst, dist in ((0, b - p0), (1, p1 - b)):
+            tr[t]["mvSlot"][lst] = (b * 2 + lst) * (bframes + 2) + dist
+            tr[t]["doSearch"][lst] = 1
+    dLC, dRS, dSm = ctx.empty(len(wave) * ncu * 2), ctx.empty(len(wave) * hcu * 4), ctx.empty(len(wave) * 16)
+    run = lambda: ctx.la_estimate_dev(8, dPlanePtrs, ls, wcu, hcu, tr, dMv, dMvC, dIntraPtrs, None, dLC, dRS, dSm, lam)
+    run(); ctx.sync()
+    t0 = time.perf_counter(); run(); ctx.sync()
+    est_ms = (time.perf_counter() - t0) * 1e3
+    for b in [x for fr in planes for x in fr] + dIC + [dIM, dLC0, dRS0, dSm0, dPlanePtrs, dIntraPtrs, dMv, dMvC, dLC, dRS, dSm]:
+        b.free()
+    per_frame = pre_ms + est_ms / nframes
+    return {"included_in_value": False, "lowres": "%dx%d (%dx%d CUs)" % (lw, ll, wcu, hcu), "frames_batched": nframes,
+            "list_searches": 2 * len(wave), "lowres_init_plus_intra_ms_per_frame": pre_ms, "estimate_launch_ms": est_ms,
+            "ms_per_frame": per_frame, "frames_per_s": 1e3 / per_frame,
+            "note": "estimateFrameCost is a dependent wavefront (~560 CU steps of ~30 us per (frame, list) field): one launch costs ~17-25 ms "
+                    "whatever the batch, so throughput comes from batching the fields of several queued frames (DESIGN.md 5b, profiles/r01_lookahead.txt)"}
 
 
 def cpu_baseline():

@@ -1,0 +1,141 @@
+// la_search_thread.cu -- estimateCUCost phase 1 (slicetype.cpp:3216-3325: MV candidates, mvp choice, motionEstimate
+// HEX / subme 1 / merange 16 on one 8x8 lowres CU) with ONE LANE PER CU.
+//
+// estimateCUCost walks the CUs of a (frame, list) field in reverse raster order and predicts each CU from its right
+// neighbour and the three neighbours in the row below (slicetype.cpp:3269-3280), so a CU can start once the row below is
+// two CUs ahead.  Here a warp owns a BAND of 32 consecutive CU rows: lane r searches row (bandBottom - r) and runs two
+// columns behind lane r-1, one __syncwarp per step keeps the stagger (and publishes the MVs lane r-1 just wrote).  Only
+// lane 0 waits on another warp (the top row of the band below, through a progress word in global memory); bands are
+// claimed bottom-up from an atomic counter, so a band's producer is always resident.  Every lane runs the whole
+// bit-exact search in per-thread mode (me_device.cuh, thread-only build: 8x8 block, SAD rows batched, the lowres
+// quarter-pel average built and costed per 4x4 cell in registers) -- a 64-pixel CU cannot feed 32 lanes (the
+// one-warp-per-CU kernel in lookahead_kernels.cu tops out at 0.85 ms per 32 640-CU field; profiles/r01_lookahead.txt).
+#define ME_FORCE_THREAD 1
+#include "me_device.cuh"
+#include "lookahead_args.cuh"
+
+namespace x265b200 {
+
+constexpr int LAT_WARPS = 2;
+
+template<typename pixel>
+__global__ void __launch_bounds__(LAT_WARPS * 32)
+la_search_thread_kernel(LASearchArgs p)
+{
+    // 8 lanes share one 8-row x 64-pixel tile: lane L's cached source CU sits at column (L & 7) * 8, row stride 64
+    __shared__ __align__(16) pixel sFenc[LAT_WARPS][4][8 * 64];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int W = p.widthInCU, Hc = p.heightInCU, ncu = W * Hc;
+    const int bands = (Hc + 31) >> 5;
+
+    for (;;)
+    {
+        int id = 0;
+        if (lane == 0) id = atomicAdd(p.workCounter, 1);
+        id = __shfl_sync(0xffffffffu, id, 0);
+        if (id >= p.numChains * bands) return;
+        const int chain = id / bands, band = id - chain * bands;
+        const LAChain ch = p.chains[chain];
+        const int cuY = Hc - 1 - band * 32 - lane;                  // this lane's row (bottom-up inside the band)
+        const bool rowValid = cuY >= 0;
+        const bool lastRow = cuY == Hc - 1;
+        volatile int* below = p.progress + chain * Hc + cuY + 1;
+        int32_t* mvs = p.mvPool + (int64_t)ch.mvSlot * ncu * 2;
+        int32_t* mvcosts = p.mvCostPool + (int64_t)ch.mvSlot * ncu;
+        const pixel* const* fencPlanes = (const pixel* const*)p.planes + ch.b * 4;
+        const pixel* const* refPlanes = (const pixel* const*)p.planes + ch.ref * 4;
+        // the row above this lane belongs to another warp when this is the band's top lane (or the band's last valid row)
+        const bool publishes = rowValid && cuY > 0 && (lane == 31);
+
+        MEState<pixel> s;
+        s.fenc = &sFenc[warp][lane >> 3][(lane & 7) * 8];
+        s.pred = nullptr; s.immed = nullptr;
+        s.stride = p.stride; s.isLowres = true; s.perThread = true; s.chromaSatd = false; s.groupSize = 1; s.groupMask = 1u << lane;
+        s.w = 8; s.h = 8; s.lane = 0; s.depth = p.depth; s.partSizeScale = 4; s.cost = p.cost + 2 * 32768;
+
+        int rightX = 0, rightY = 0;                                  // fencMV of the CU to the right (previous step of this lane)
+        const int steps = W + 2 * 31;
+#pragma unroll 1
+        for (int t = 0; t < steps; t++)
+        {
+            const int cuX = W - 1 - (t - 2 * lane);
+            if (rowValid && cuX >= 0 && cuX < W)
+            {
+                const int cuXY = cuX + cuY * W;
+                const int64_t pelOffset = 8 * cuX + (int64_t)8 * cuY * p.stride;
+                if (lane == 0 && !lastRow)
+                {
+                    const int need = min(W, W - cuX + 1);
+                    while (*below < need) __nanosleep(64);
+                    __threadfence();
+                }
+                // setSourcePU: cache the 8x8 source block (motion.cpp:188-189)
+                {
+                    constexpr int NW = 8 * (int)sizeof(pixel) / 4;
+                    const pixel* fp = fencPlanes[0] + pelOffset;
+#pragma unroll
+                    for (int y = 0; y < 8; y++)
+                    {
+                        uint32_t wv[NW];
+                        ld_words<pixel, NW>(fp + (int64_t)y * p.stride, wv);
+                        uint32_t* d = (uint32_t*)(const_cast<pixel*>(s.fenc) + y * 64);
+#pragma unroll
+                        for (int i = 0; i < NW; i++) d[i] = wv[i];
+                    }
+                }
+                for (int k = 0; k < 4; k++) s.lowres[k] = refPlanes[k] + pelOffset;
+                s.fref = s.lowres[0]; s.gfref = s.lowres[0]; s.gstride = p.stride;
+
+                // reverse-order MV prediction candidates (slicetype.cpp:3269-3280)
+                int mvc[4][2], numc = 0;
+                if (cuX < W - 1) { mvc[numc][0] = rightX; mvc[numc][1] = rightY; numc++; }
+                if (!lastRow)
+                {
+                    const volatile int32_t* row = mvs + (int64_t)(cuXY + W) * 2;
+                    mvc[numc][0] = row[0]; mvc[numc][1] = row[1]; numc++;
+                    if (cuX > 0) { mvc[numc][0] = row[-2]; mvc[numc][1] = row[-1]; numc++; }
+                    if (cuX < W - 1) { mvc[numc][0] = row[2]; mvc[numc][1] = row[3]; numc++; }
+                }
+                int mvpx = 0, mvpy = 0, skipCost = 0x7fffffff;
+                if (numc)
+                {
+                    int mvpcost = ME_COST_MAX;
+                    for (int idx = 0; idx < numc; idx++)
+                    {
+                        int cost = lowres_qpel_cost<pixel>(s, mvc[idx][0], mvc[idx][1], true);     // lowresMC + bufSATD (:3292-3303)
+                        if (cost < mvpcost) { mvpcost = cost; mvpx = mvc[idx][0]; mvpy = mvc[idx][1]; }
+                        if (!(mvpx | mvpy) && ch.bBidir) skipCost = cost;                          // :3304-3305 (as written)
+                    }
+                }
+                s.mvpx = mvpx; s.mvpy = mvpy;
+                const MV2 mvmin = mv2(-cuX * 8 - 8, -cuY * 8 - 8), mvmax = mv2((W - cuX - 1) * 8 + 8, (Hc - cuY - 1) * 8 + 8);
+                int ox, oy;
+                int fencCost = motion_estimate<pixel>(s, mvmin, mvmax, mv2(mvpx, mvpy), 0, nullptr, p.merange, ME_HEX, 1, p.maxSlices, 0, ox, oy);
+                if (skipCost < 64 && skipCost < fencCost && ch.bBidir) { fencCost = skipCost; ox = 0; oy = 0; }
+                rightX = ox; rightY = oy;
+                mvs[cuXY * 2] = ox; mvs[cuXY * 2 + 1] = oy; mvcosts[cuXY] = fencCost;
+                if (publishes)
+                {
+                    __threadfence();
+                    *(volatile int*)(p.progress + chain * Hc + cuY) = W - cuX;
+                }
+            }
+            __syncwarp();          // keeps the two-column stagger and orders lane r-1's MV stores before lane r's loads
+        }
+    }
+}
+
+int la_search_thread_launch(Ctx* ctx, int depth, const LASearchArgs& a)
+{
+    const int bands = (a.heightInCU + 31) >> 5;
+    const int64_t items = (int64_t)a.numChains * bands;
+    int64_t blocksWanted = (items + LAT_WARPS - 1) / LAT_WARPS;
+    int64_t cap = (int64_t)ctx->smCount * 8;
+    unsigned blocks = (unsigned)(blocksWanted < cap ? blocksWanted : cap);
+    if (depth > 8) la_search_thread_kernel<uint16_t><<<blocks, LAT_WARPS * 32, 0, ctx->stream>>>(a);
+    else           la_search_thread_kernel<uint8_t><<<blocks, LAT_WARPS * 32, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    return check(cudaGetLastError(), "la_search (per-thread) launch");
+}
+
+} // namespace x265b200

@@ -1,0 +1,25 @@
+// lookahead_args.cuh -- argument blocks shared by the two implementations of estimateCUCost phase 1
+// (lookahead_kernels.cu: one warp per CU; la_search_thread.cu: one lane per CU)
+#pragma once
+#include "common.cuh"
+
+namespace x265b200 {
+
+struct LAChain { int32_t b, ref, bBidir, mvSlot; };   // frame indices; MV/cost pool slot
+
+struct LASearchArgs
+{
+    const void* const* planes;     // [numFrames][4] plane origins
+    int64_t stride;
+    const LAChain* chains; int numChains;
+    int widthInCU, heightInCU, depth, merange, maxSlices;
+    int32_t* mvPool;               // [slot][ncu][2]
+    int32_t* mvCostPool;           // [slot][ncu]
+    int* progress;                 // [numChains][heightInCU], zeroed
+    int* workCounter;              // zeroed
+    const uint16_t* cost;
+};
+
+int la_search_thread_launch(Ctx* ctx, int depth, const LASearchArgs& a);
+
+} // namespace x265b200

@@ -11,8 +11,10 @@
 // (triple, list) chains are in flight at once -- that is where the parallelism comes from.
 // Phase 2 (bidir / intra compare / accumulation) is embarrassingly parallel, one thread per CU.
 #include "me_device.cuh"
+#include "lookahead_args.cuh"
 #include "x265b200.h"
 #include <vector>
+#include <cstdlib>
 
 namespace x265b200 {
 
@@ -279,21 +281,6 @@ int la_intra_dev(Ctx* ctx, int depth, const void* plane0, int64_t stride, int wi
 // ---------------------------------------------------------------------------------------------
 // estimateCUCost phase 1: per (triple, list) MV search chains, one warp per CU row
 // ---------------------------------------------------------------------------------------------
-struct LAChain { int32_t b, ref, bBidir, mvSlot; };   // frame indices; MV/cost pool slot
-
-struct LASearchArgs
-{
-    const void* const* planes;     // [numFrames][4] plane origins
-    int64_t stride;
-    const LAChain* chains; int numChains;
-    int widthInCU, heightInCU, depth, merange, maxSlices;
-    int32_t* mvPool;               // [slot][ncu][2]
-    int32_t* mvCostPool;           // [slot][ncu]
-    int* progress;                 // [numChains][heightInCU], zeroed
-    int* workCounter;              // zeroed
-    const uint16_t* cost;
-};
-
 constexpr int LA_WARPS = 4;
 
 template<typename pixel>
@@ -504,10 +491,20 @@ int la_estimate_dev(Ctx* ctx, int depth, const void* const* planes, int64_t stri
         unsigned blocks = (unsigned)(blocksWanted < cap ? blocksWanted : cap);
         // the host must not free `chains` before the async copy is consumed
         X265B200_CHECK(cudaStreamSynchronize(ctx->stream));
-        if (depth > 8) la_search_kernel<uint16_t><<<blocks, LA_WARPS * 32, 0, ctx->stream>>>(a);
-        else           la_search_kernel<uint8_t><<<blocks, LA_WARPS * 32, 0, ctx->stream>>>(a);
-        ctx->launches++;
-        if (check(cudaGetLastError(), "la_search launch")) return -1;
+        // default: one lane per CU, 32 staggered rows per warp (la_search_thread.cu); X265B200_LA_WARP=1 selects the
+        // older one-warp-per-CU kernel (kept for A/B measurements, same results)
+        static const bool useWarpKernel = getenv("X265B200_LA_WARP") && atoi(getenv("X265B200_LA_WARP")) != 0;
+        if (!useWarpKernel)
+        {
+            if (la_search_thread_launch(ctx, depth, a)) return -1;
+        }
+        else
+        {
+            if (depth > 8) la_search_kernel<uint16_t><<<blocks, LA_WARPS * 32, 0, ctx->stream>>>(a);
+            else           la_search_kernel<uint8_t><<<blocks, LA_WARPS * 32, 0, ctx->stream>>>(a);
+            ctx->launches++;
+            if (check(cudaGetLastError(), "la_search launch")) return -1;
+        }
     }
     X265B200_CHECK(cudaMemsetAsync(rowSatds, 0, sizeof(int32_t) * (size_t)numTriples * heightInCU, ctx->stream));
     X265B200_CHECK(cudaMemsetAsync(sums, 0, sizeof(int32_t) * (size_t)numTriples * 4, ctx->stream));

@@ -232,11 +232,26 @@ __device__ __forceinline__ int thread_sad_any(const MEState<pixel>& s, const pix
     if (!(ME_PU_W(s) & 7))  return thread_sad_one<pixel, 8>(s, r, rs);
     return thread_sad_one<pixel, 4>(s, r, rs);
 }
+// 4x4 Hadamard cost of d[i][k] = a - b rows already differenced: sum |H d H^T| >> 1
+__device__ __forceinline__ int satd_cell(int d[4][4])
+{
+#pragma unroll
+    for (int i = 0; i < 4; i++) me_hadamard4(d[i][0], d[i][1], d[i][2], d[i][3]);
+    int t = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+    {
+        me_hadamard4(d[0][k], d[1][k], d[2][k], d[3][k]);
+        t += abs(d[0][k]) + abs(d[1][k]) + abs(d[2][k]) + abs(d[3][k]);
+    }
+    return t >> 1;
+}
+
 template<typename pixel>
 __device__ __forceinline__ int thread_satd(const MEState<pixel>& s, const pixel* r, int64_t rs)
 {
-    constexpr int NW = 4 * (int)sizeof(pixel) / 4;
     int acc = 0;
+    constexpr int NW = 4 * (int)sizeof(pixel) / 4;
 #pragma unroll 1
     for (int cy = 0; cy < s.h; cy += 4)
 #pragma unroll 1
@@ -253,16 +268,8 @@ __device__ __forceinline__ int thread_satd(const MEState<pixel>& s, const pixel*
                 unpack4<pixel>(rw, b);
 #pragma unroll
                 for (int k = 0; k < 4; k++) d[i][k] = a[k] - b[k];
-                me_hadamard4(d[i][0], d[i][1], d[i][2], d[i][3]);
             }
-            int t = 0;
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-            {
-                me_hadamard4(d[0][k], d[1][k], d[2][k], d[3][k]);
-                t += abs(d[0][k]) + abs(d[1][k]) + abs(d[2][k]) + abs(d[3][k]);
-            }
-            acc += t >> 1;
+            acc += satd_cell(d);
         }
     return acc;
 }
@@ -843,9 +850,62 @@ __device__ __noinline__ int subpel_compare(const MEState<pixel>& s, int qx, int 
 }
 
 // ReferencePlanes::lowresQPelCost (common/lowres.h:94-120), 8x8 lowres blocks, hme = false
+// per-thread form: the pixelavg_pp of the two hpel planes (pixel.cpp:545-557) is built 4x4 cell by cell in registers
+// (the byte-wise rounded average is exactly (a + b + 1) >> 1) and costed on the spot
+template<typename pixel> __device__ __forceinline__ uint32_t avg_word(uint32_t a, uint32_t b);
+template<> __device__ __forceinline__ uint32_t avg_word<uint8_t>(uint32_t a, uint32_t b) { return __vavgu4(a, b); }
+template<> __device__ __forceinline__ uint32_t avg_word<uint16_t>(uint32_t a, uint32_t b) { return __vavgu2(a, b); }
+
+template<typename pixel>
+__device__ __forceinline__ int thread_lowres_avg_cost(const MEState<pixel>& s, const pixel* A, const pixel* B, bool useSatd)
+{
+    // lowres CUs are 8 pixels wide: both 4x4 cells of a row group come from one batch of (A, B) row loads
+    constexpr int NW8 = 8 * (int)sizeof(pixel) / 4, NW4 = NW8 / 2;
+    int acc = 0;
+#pragma unroll 1
+    for (int y0 = 0; y0 < s.h; y0 += 4)
+    {
+        uint32_t wv[4][NW8];
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+        {
+            uint32_t wa[NW8], wb[NW8];
+            ld_words<pixel, NW8>(A + (int64_t)(y0 + r) * s.stride, wa);
+            ld_words<pixel, NW8>(B + (int64_t)(y0 + r) * s.stride, wb);
+#pragma unroll
+            for (int i = 0; i < NW8; i++) wv[r][i] = avg_word<pixel>(wa[i], wb[i]);
+        }
+#pragma unroll
+        for (int c = 0; c < 2; c++)
+        {
+            int o[4][4];
+#pragma unroll
+            for (int r = 0; r < 4; r++) unpack4<pixel>(wv[r] + c * NW4, o[r]);
+            acc += cell_cost<pixel>(s.fenc + y0 * 64 + c * 4, o, useSatd);
+        }
+    }
+    return acc;
+}
+
 template<typename pixel>
 __device__ __noinline__ int lowres_qpel_cost(const MEState<pixel>& s, int qx, int qy, bool useSatd)
 {
+    if (ME_IS_THREAD(s))
+    {
+        if ((qx | qy) & 1)
+        {
+            const int hpelA = (qy & 2) | ((qx & 2) >> 1);
+            const pixel* frefA = s.lowres[hpelA] + (qx >> 2) + (int64_t)(qy >> 2) * s.stride;
+            const int qmvx = qx + (qx & 1), qmvy = qy + (qy & 1);
+            const int hpelB = (qmvy & 2) | ((qmvx & 2) >> 1);
+            const pixel* frefB = s.lowres[hpelB] + (qmvx >> 2) + (int64_t)(qmvy >> 2) * s.stride;
+            return group_sum<pixel>(s, thread_lowres_avg_cost<pixel>(s, frefA, frefB, useSatd));
+        }
+        const int hpel = (qy & 2) | ((qx & 2) >> 1);
+        const pixel* fref = s.lowres[hpel] + (qx >> 2) + (int64_t)(qy >> 2) * s.stride;
+        return useSatd ? warp_satd<pixel>(s, fref, s.stride) : warp_sad_block<pixel>(s, fref, s.stride);
+    }
+#ifndef ME_FORCE_THREAD
     if ((qx | qy) & 1)
     {
         int hpelA = (qy & 2) | ((qx & 2) >> 1);
@@ -867,6 +927,9 @@ __device__ __noinline__ int lowres_qpel_cost(const MEState<pixel>& s, int qx, in
     int hpel = (qy & 2) | ((qx & 2) >> 1);
     const pixel* fref = s.lowres[hpel] + (qx >> 2) + (int64_t)(qy >> 2) * s.stride;
     return useSatd ? warp_satd<pixel>(s, fref, s.stride) : warp_sad_block<pixel>(s, fref, s.stride);
+#else
+    return 0;
+#endif
 }
 
 // ---- the search ------------------------------------------------------------------------------------
