@@ -37,6 +37,9 @@ NREF, MERANGE, SUBME, QP = 3, 57, 2, 30
 LEVELS = [64, 32, 16, 8]
 # DRAM bytes one sad_pyramid launch (3 references, 2160p 8-bit) moved under `ncu --set full` (profiles/r01_pyramid_dct_v3.txt)
 SAD_PYRAMID_DRAM_BYTES = 33437696
+WORKLOAD = ("2160p-8bit-medium primitive mix (SURVEY.md 8d config 3): SAD at the predictor + HEX subme2 merange57 search of every 2Nx2N PU 64..8 x 3 refs; "
+            "one 8-tap MC interpolation per PU and level (all 15 fractions); residual -> DCT/quant/dequant/IDCT on every 32/16/8/4 TU -> recon; "
+            "intra filter + all 35 modes on every 8/16/32 block")
 METRIC = "2160p preset-medium fps at 1/2/4/8 B200; ME SAD achieved HBM GB/s vs peak"
 
 
@@ -87,6 +90,61 @@ def build_jobs(pkg, ctu_rows=None):
     job["mvminX"] = job["mvminY"] = -MERANGE
     job["mvmaxX"] = job["mvmaxY"] = MERANGE
     return job
+
+
+TU_SIZES = [(3, 32), (2, 16), (1, 8), (0, 4)]      # (sizeIdx, N): every TU size of the residual plane
+INTRA_SIZES = [(1, 8, 3), (2, 16, 4), (3, 32, 5)]   # (sizeIdx, N, log2N): all 35 modes on every block
+IP_HPP, IP_VPP, IP_HVPP = 0, 2, 6                   # X265B200_IP_* / ref_interp_batch kinds
+
+
+def interp_jobs(pkg, s, rows=None):
+    """one luma interpolation per PU of level s: block at its own position in reference 0, fraction cycling through
+    the 15 non-zero quarter-pel positions.  Returns {kind: job array}; srcOff is relative to
+    the plane origin (STRIDE pitch), dstOff addresses a W-pitch prediction plane."""
+    per_row = W // s
+    out = {IP_HPP: [], IP_VPP: [], IP_HVPP: []}
+    ys = range(0, CTU_ROWS * CTU, s) if rows is None else [cy * CTU + py * s for cy in rows for py in range(CTU // s)]
+    for y in ys:
+        for bx in range(per_row):
+            k = ((y // s) * per_row + bx) % 15 + 1
+            fx, fy = k & 3, k >> 2
+            x = bx * s
+            src, dst = y * STRIDE + x, y * W + x
+            if fy == 0:
+                out[IP_HPP].append((src, dst, fx, 0))
+            elif fx == 0:
+                out[IP_VPP].append((src, dst, fy, 0))
+            else:
+                out[IP_HVPP].append((src, dst, fx, fy))
+    res = {}
+    for kind, lst in out.items():
+        a = np.zeros(len(lst), dtype=pkg.INTERP_JOB)
+        if lst:
+            t = np.array(lst, dtype=np.int64)
+            a["srcOff"], a["dstOff"], a["idxX"], a["idxY"] = t[:, 0], t[:, 1], t[:, 2], t[:, 3]
+        res[kind] = a
+    return res
+
+
+def neighbour_arrays(frame, N, rows=None):
+    """[topLeft, top 2N, left 2N] (intrapred.cpp:36-50 layout) of every N x N block, taken from the padded frame."""
+    f = frame.reshape(ROWS, STRIDE)
+    ys = np.arange(0, CTU_ROWS * CTU, N) if rows is None else np.array([cy * CTU + k * N for cy in rows for k in range(CTU // N)])
+    xs = np.arange(0, W, N)
+    Y, X = np.meshgrid(ys + PAD, xs + PAD, indexing="ij")
+    Y, X = Y.ravel(), X.ravel()
+    out = np.empty((len(Y), 4 * N + 1), dtype=np.uint8)
+    out[:, 0] = f[Y - 1, X - 1]
+    k = np.arange(2 * N)
+    out[:, 1:2 * N + 1] = f[(Y - 1)[:, None], X[:, None] + k[None, :]]
+    out[:, 2 * N + 1:] = f[Y[:, None] + k[None, :], (X - 1)[:, None]]
+    return out
+
+
+def quant_params(N):
+    log2 = int(np.log2(N))
+    qbits = 14 + 5 + (15 - 8 - log2)                # QUANT_SHIFT + per(qp 30) + transformShift (quant.cpp:397-480)
+    return qbits, 171 << (qbits - 9)
 
 
 class ClockSampler(threading.Thread):
@@ -146,13 +204,39 @@ def run_reference(args, rank, world):
             R.ref_me_batch(ctypes.c_void_p(cur.ctypes.data + origin), ctypes.c_ssize_t(STRIDE),
                            ctypes.c_void_p(ref.ctypes.data + origin), ctypes.c_ssize_t(STRIDE),
                            ctypes.c_void_p(rj.ctypes.data), ctypes.c_int64(len(rj)), 1, SUBME, MERANGE, QP, 1, cores)
-        # residual pipeline on the sample row's 32x32 TUs
-        n32 = CTU_COLS * 2 * 2 * len(sample_rows)
-        resid = (cur[origin:origin + 64 * STRIDE].astype(np.int16) - frames[NREF - 1].ravel()[origin:origin + 64 * STRIDE].astype(np.int16))
-        blocks = np.ascontiguousarray(resid.reshape(64, STRIDE)[:, :W].reshape(2, 32, W // 32, 32).transpose(0, 2, 1, 3)).reshape(-1)
-        coef = np.empty_like(blocks); rec = np.empty_like(blocks)
-        R.ref_dct_batch(3, ctypes.c_void_p(blocks.ctypes.data), ctypes.c_int64(1024), ctypes.c_ssize_t(32), ctypes.c_void_p(coef.ctypes.data), ctypes.c_int64(n32), cores)
-        R.ref_idct_batch(3, ctypes.c_void_p(coef.ctypes.data), ctypes.c_void_p(rec.ctypes.data), ctypes.c_int64(1024), ctypes.c_ssize_t(32), ctypes.c_int64(n32), cores)
+        # MC: one luma interpolation per PU of the sample row, all 15 fractions
+        ref0 = frames[NREF - 1].ravel()
+        for sz in LEVELS:
+            part = R.ref_partition_from_sizes(sz, sz)
+            for kind, ja in ip_jobs[sz].items():
+                if len(ja):
+                    R.ref_interp_batch(kind, part, ctypes.c_void_p(ref0.ctypes.data + origin), ctypes.c_ssize_t(STRIDE),
+                                       ctypes.c_void_p(pred[sz].ctypes.data), ctypes.c_ssize_t(W), ctypes.c_void_p(ja.ctypes.data), ctypes.c_int64(len(ja)), cores)
+        # residual of the sample row against the 16x16-level prediction, every TU size: DCT, quant, dequant, IDCT
+        y0 = sample_rows[0] * CTU
+        curv = cur.reshape(ROWS, STRIDE)[PAD + y0:PAD + y0 + CTU, PAD:PAD + W].astype(np.int16)
+        resid = curv - pred[16].reshape(-1, W)[y0:y0 + CTU].astype(np.int16)
+        for idx, N in TU_SIZES:
+            nb = (W // N) * (CTU // N)
+            blocks = np.ascontiguousarray(resid.reshape(CTU // N, N, W // N, N).transpose(0, 2, 1, 3)).reshape(-1)
+            coef = np.empty_like(blocks); q = np.empty_like(blocks); dq = np.empty_like(blocks); rec = np.empty_like(blocks)
+            qbits, add = quant_params(N)
+            R.ref_dct_batch(idx, ctypes.c_void_p(blocks.ctypes.data), ctypes.c_int64(N * N), ctypes.c_ssize_t(N), ctypes.c_void_p(coef.ctypes.data), ctypes.c_int64(nb), cores)
+            R.ref_quant_dequant_batch(ctypes.c_void_p(coef.ctypes.data), ctypes.c_void_p(qtab.ctypes.data), ctypes.c_void_p(q.ctypes.data), ctypes.c_void_p(dq.ctypes.data),
+                                      ctypes.c_void_p(deltaU.ctypes.data), qbits, add, N * N, ctypes.c_int64(nb), 40 << 5, 9, cores)
+            R.ref_idct_batch(idx, ctypes.c_void_p(dq.ctypes.data), ctypes.c_void_p(rec.ctypes.data), ctypes.c_int64(N * N), ctypes.c_ssize_t(N), ctypes.c_int64(nb), cores)
+        # intra: filter + all 35 modes on every 8/16/32 block of the sample row
+        for idx, N, _ in INTRA_SIZES:
+            nb = len(nbr[N])
+            R.ref_intra_batch(idx, ctypes.c_void_p(nbr[N].ctypes.data), ctypes.c_void_p(filt[N].ctypes.data), ctypes.c_void_p(intra_out[N].ctypes.data), ctypes.c_int64(nb), cores)
+
+    ip_jobs = {sz: interp_jobs(pkg, sz, sample_rows) for sz in LEVELS}
+    pred = {sz: np.zeros(CTU_ROWS * CTU * W, dtype=np.uint8) for sz in LEVELS}
+    qtab = np.full(1024, 26214, dtype=np.int32)
+    deltaU = np.zeros(cores * 1024, dtype=np.int32)
+    nbr = {N: neighbour_arrays(cur, N, sample_rows) for _, N, _ in INTRA_SIZES}
+    filt = {N: np.empty_like(nbr[N]) for N in nbr}
+    intra_out = {N: np.empty(len(nbr[N]) * 35 * N * N, dtype=np.uint8) for N in nbr}
 
     for _ in range(args.warmup):
         step()
@@ -164,9 +248,9 @@ def run_reference(args, rank, world):
     line = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic", "impl": "reference",
-            "config": {"workload": "2160p-8bit-medium-hotpath: HEX subme2 merange57 3refs 2Nx2N 64..8 + DCT32/IDCT32", "sample": "1 of %d CTU rows, scaled" % CTU_ROWS},
+            "config": {"workload": WORKLOAD, "sample": "1 of %d CTU rows, scaled" % CTU_ROWS},
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "reference",
-                             "sample": "%d PU searches (CTU row %d, 3 refs) + %d 32x32 DCT/IDCT, x%d to a frame; C table, no nasm asm" % (len(job), sample_rows[0], CTU_COLS * 4, CTU_ROWS)},
+                             "sample": "CTU row %d of %d (x%d to a frame): %d PU searches (3 refs), %d MC interpolations, DCT/quant/dequant/IDCT of its 32/16/8/4 TUs, 35 intra modes on its 8/16/32 blocks; C table, no nasm asm" % (sample_rows[0], CTU_ROWS, CTU_ROWS, len(job), sum(len(a) for d in ip_jobs.values() for a in d.values()))},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -222,7 +306,25 @@ def main():
     qcoef = torch.empty_like(coef); deq = torch.empty_like(coef)
     recon = torch.empty((CTU_ROWS * CTU, W), dtype=torch.uint8, device=dev)
     qtab = torch.full((1024,), 26214, dtype=torch.int32, device=dev)          # quantScales[qp%6=0] flat list
-    numsig = torch.empty(n32, dtype=torch.int32, device=dev)
+    numsig = torch.empty((W // 4) * (CTU_ROWS * CTU // 4), dtype=torch.int32, device=dev)
+    resid2 = torch.empty((CTU_ROWS * CTU, W), dtype=torch.int16, device=dev)
+    # MC jobs (static), prediction planes, intra neighbour arrays (taken once from frame 0: static inputs) and outputs
+    ip_jobs_h = {sz: interp_jobs(pkg, sz) for sz in LEVELS}
+    ip_jobs_d = {sz: {k: torch.from_numpy(a.view(np.uint8).copy()).to(dev) for k, a in ip_jobs_h[sz].items() if len(a)} for sz in LEVELS}
+    n_interp = sum(len(a) for d in ip_jobs_h.values() for a in d.values())
+    pred = {sz: torch.zeros((CTU_ROWS * CTU, W), dtype=torch.uint8, device=dev) for sz in LEVELS}
+    nbr_d, filt_d, pd_jobs_d, n_intra = {}, {}, {}, 0
+    for _, N, _ in INTRA_SIZES:
+        a = neighbour_arrays(frames_h[0].ravel(), N)
+        nbr_d[N] = torch.from_numpy(a).to(dev); filt_d[N] = torch.empty_like(nbr_d[N])
+        pj = np.zeros(2 * len(a), dtype=pkg.INTRA_JOB)
+        idx = np.arange(len(a), dtype=np.int64)
+        pj["srcOff"] = np.repeat(idx * (4 * N + 1), 2); pj["dstOff"] = np.arange(2 * len(a), dtype=np.int64) * N * N
+        pj["mode"] = np.tile([0, 1], len(a)); pj["bFilter"] = int(N <= 16)
+        pd_jobs_d[N] = torch.from_numpy(pj.view(np.uint8).copy()).to(dev)
+        n_intra += len(a)
+    allangs_out = torch.empty(33 * W * CTU_ROWS * CTU, dtype=torch.uint8, device=dev)       # 33 modes x every pixel, reused per size
+    pd_out = torch.empty(2 * W * CTU_ROWS * CTU, dtype=torch.uint8, device=dev)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
     me_out = torch.empty((njobs, 3), dtype=torch.int32, device=dev)
     res_h = torch.empty((njobs, 3), dtype=torch.int32).pin_memory()
@@ -250,14 +352,28 @@ def main():
                          pkg.ME_HEX, SUBME, MERANGE, lam, P(me_out))
         if time_sad:
             m1.record(); me_events.append((m0, m1))
-        # 3. residual -> DCT32 -> quant -> dequant -> IDCT32 -> recon (one launch each, whole plane)
+        # 3. MC: one 8-tap interpolation per PU and level from reference 0 (HPP / VPP / HVPP by fraction)
         HH = CTU_ROWS * CTU
-        ctx.sub_ps_plane_dev(8, cptr, STRIDE, P(refs[0]) + origin, STRIDE, P(resid), W, W, HH)
-        ctx.dct_plane_dev(3, 8, P(resid), W, W // 32, HH // 32, P(coef))
-        ctx.quant_dev(P(coef), P(qtab), None, P(qcoef), 14 + 5 + (15 - 8 - 5), 171 << (14 + 5 + 2 - 9), 1024, n32, P(numsig))
-        ctx.dequant_normal_dev(P(qcoef), P(deq), 1024, n32, 40 << 5, 9)
-        ctx.idct_plane_dev(3, 8, P(deq), P(resid), W, W // 32, HH // 32)
-        ctx.add_ps_plane_dev(8, P(recon), W, P(refs[0]) + origin, STRIDE, P(resid), W, W, HH)
+        r0 = P(refs[0]) + origin
+        for sz in LEVELS:
+            for kind, jd in ip_jobs_d[sz].items():
+                ctx.interp_dev(kind, 8, 8, sz, sz, r0, STRIDE, P(pred[sz]), W, P(jd), len(ip_jobs_h[sz][kind]), 0)
+        # 4. residual against the 16x16-level prediction -> DCT -> quant -> dequant -> IDCT on every TU size -> recon
+        ctx.sub_ps_plane_dev(8, cptr, STRIDE, P(pred[16]), W, P(resid), W, W, HH)
+        for idx, N in TU_SIZES:
+            nb = (W // N) * (HH // N)
+            qbits, add = quant_params(N)
+            ctx.dct_plane_dev(idx, 8, P(resid), W, W // N, HH // N, P(coef))
+            ctx.quant_dev(P(coef), P(qtab), None, P(qcoef), qbits, add, N * N, nb, P(numsig))
+            ctx.dequant_normal_dev(P(qcoef), P(deq), N * N, nb, 40 << 5, 9)
+            ctx.idct_plane_dev(idx, 8, P(deq), P(resid2), W, W // N, HH // N)
+        ctx.add_ps_plane_dev(8, P(recon), W, P(pred[16]), W, P(resid2), W, W, HH)
+        # 5. intra: neighbour filter + 33 angular modes + planar + DC on every 8/16/32 block
+        for _, N, log2N in INTRA_SIZES:
+            nb = nbr_d[N].shape[0]
+            ctx.intra_filter_dev(8, log2N, P(nbr_d[N]), P(filt_d[N]), nb)
+            ctx.intra_allangs_dev(8, log2N, P(nbr_d[N]), P(filt_d[N]), P(allangs_out), 1, nb)
+            ctx.intra_pred_dev(8, log2N, P(nbr_d[N]), P(pd_out), N, P(pd_jobs_d[N]), 2 * nb)
 
     # ---- N > 1: the path's one real exchange: every rank needs the reference pixels the others
     # produced, and rank 0 collects the per-PU {mv,cost}.  One all_gather of the new luma plane + one gather.
@@ -380,7 +496,7 @@ def main():
         line = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u8", "data": "synthetic",
-                "config": {"workload": "2160p-8bit-medium-hotpath: sad_pred + HEX subme2 merange57 3refs 2Nx2N 64..8 (%d searches) + resid/DCT32/quant/dequant/IDCT32 (%d TUs)" % (njobs, n32),
+                "config": {"workload": WORKLOAD, "units_per_step": {"pu_searches": njobs, "mc_interpolations": n_interp, "tu_per_size": {str(N): (W // N) * (CTU_ROWS * CTU // N) for _, N in TU_SIZES}, "intra_blocks_x35_modes": n_intra},
                            "l2": "512 MiB flush between timed steps", "parallelism": "frame-parallel x%d" % world},
                 "clocks": sampler.summary(), "gpu_launches": int(launches),
                 "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": ROWS * STRIDE, "d2h_bytes_per_step": njobs * 12},

@@ -554,3 +554,48 @@ extern "C" int ref_me_batch_chroma(const void* fencY, const void* fencCb, const 
     for (int t = 0; t < nt; t++) { delete mes[t]; cus[t]->destroy(); delete cus[t]; }
     return 0;
 }
+
+/* ---- batched table calls for bench.py's CPU arm (the reference's own C primitives over job lists, threaded) ---- */
+extern "C" {
+struct RefInterpJob { int64_t srcOff, dstOff; int32_t idxX, idxY; };      /* same layout as x265b200_interp_job */
+/* luma 8-tap: kind 0 = luma_hpp, 2 = luma_vpp, 6 = luma_hvpp */
+void ref_interp_batch(int kind, int part, const void* src, intptr_t srcStride, void* dst, intptr_t dstStride,
+                      const RefInterpJob* jobs, int64_t n, int threads)
+{
+    ensure_init();
+    EncoderPrimitives::PU& p = primitives.pu[part];
+    parallel_for(n, threads, [&](int64_t i, int) {
+        const pixel* s = (const pixel*)src + jobs[i].srcOff; pixel* d = (pixel*)dst + jobs[i].dstOff;
+        if (kind == 0) p.luma_hpp(s, srcStride, d, dstStride, jobs[i].idxX);
+        else if (kind == 2) p.luma_vpp(s, srcStride, d, dstStride, jobs[i].idxX);
+        else p.luma_hvpp(s, srcStride, d, dstStride, jobs[i].idxX, jobs[i].idxY);
+    });
+}
+/* per block: intra_filter, the 33 angular modes (the C table has no intra_pred_allangs, primitives.cpp:257, so the
+ * encoder loops over intra_pred[mode], search.cpp:1385-1400), planar and DC.  neigh/filt: n arrays of 4N+1 pixels;
+ * dest: n x 35 x N*N pixels (modes 0..34) */
+void ref_intra_batch(int sizeIdx, const void* neigh, void* filt, void* dest, int64_t n, int threads)
+{
+    ensure_init();
+    const int N = 4 << sizeIdx, A = 4 * N + 1;
+    parallel_for(n, threads, [&](int64_t i, int) {
+        const pixel* ref = (const pixel*)neigh + i * A; pixel* f = (pixel*)filt + i * A;
+        pixel* out = (pixel*)dest + i * 35 * N * N;
+        primitives.cu[sizeIdx].intra_filter(ref, f);
+        for (int mode = 0; mode < 35; mode++)
+        {
+            const pixel* srcPix = (g_intraFilterFlags[mode] & N) ? f : ref;
+            primitives.cu[sizeIdx].intra_pred[mode](out + mode * N * N, N, srcPix, mode, N <= 16);
+        }
+    });
+}
+void ref_quant_dequant_batch(const int16_t* coef, const int32_t* quantCoeff, int16_t* qCoef, int16_t* deq, int32_t* deltaU,
+                             int qBits, int add, int numCoeff, int64_t n, int scale, int shift, int threads)
+{
+    ensure_init();
+    parallel_for(n, threads, [&](int64_t i, int t) {
+        primitives.quant(coef + i * numCoeff, quantCoeff, deltaU + (int64_t)t * numCoeff, qCoef + i * numCoeff, qBits, add, numCoeff);
+        primitives.dequant_normal(qCoef + i * numCoeff, deq + i * numCoeff, numCoeff, scale, shift);
+    });
+}
+}

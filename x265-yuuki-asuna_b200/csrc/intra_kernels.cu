@@ -138,30 +138,79 @@ intra_filter_kernel(const pixel* __restrict__ src, pixel* __restrict__ dst, int 
     }
 }
 
-// all_angs_pred_c :206-234: block b -> dest[b][33][N*N]; refPix/filtPix are [n][4N+1]
+// all_angs_pred_c :206-234: block b -> dest[b][33][N*N]; refPix/filtPix are [n][4N+1].
+// One CTA per block.  Phase 1 builds, for each of the 33 modes, the projected reference line ref[-N .. 2N] of
+// intra_pred_ang_c (:146-172: flipped neighbours for horizontal modes, inverse-angle projection of the side samples for
+// negative angles) in shared memory; phase 2 is then a 2-tap interpolation of CONSECUTIVE line entries, so a thread
+// produces 4 horizontally adjacent pixels from 5 line bytes and issues one 32-bit (64-bit for 16-bit pixels) store.
+// (The first version computed one pixel per thread through ang_pixel: 620 us per 274 MB size at 2160p, 15x off the
+// write roofline; profiles/r01_launches_v5.csv.)
 template<typename pixel>
 __global__ void __launch_bounds__(256)
 intra_allangs_kernel(const pixel* __restrict__ refPix, const pixel* __restrict__ filtPix, pixel* __restrict__ dest,
                      int log2N, int bLuma, int depth, int64_t n)
 {
     __shared__ pixel sr[132], sf[132];
-    const int N = 1 << log2N, len = 4 * N + 1;
+    __shared__ __align__(8) pixel line[33][104];          // entry L <-> ref[L - N], L in [0, 3N + 1]
+    const int N = 1 << log2N, N2 = N << 1, len = 4 * N + 1, LW = 3 * N + 2;
     const int64_t b = blockIdx.x;
     for (int i = threadIdx.x; i < len; i += blockDim.x) { sr[i] = refPix[b * len + i]; sf[i] = filtPix[b * len + i]; }
     __syncthreads();
-    pixel* out = dest + b * 33 * N * N;
     // smoothing thresholds (constants.cpp:561): filtered when min(|m-26|,|m-10|) > {7,1,0} for N = 8,16,32; never for 4
     const int thr = N == 8 ? 7 : (N == 16 ? 1 : (N == 32 ? 0 : 99));
-    for (int e = threadIdx.x; e < 33 * N * N; e += blockDim.x)
+    for (int e = threadIdx.x; e < 33 * LW; e += blockDim.x)
     {
-        int m = e >> (2 * log2N), r = e & (N * N - 1);
-        int mode = m + 2;
-        int y = r >> log2N, x = r & (N - 1);
-        int dist = min(abs(mode - 26), abs(mode - 10));
-        const pixel* s = dist > thr ? sf : sr;
-        // horizontal modes are stored un-transposed (:217-232): out[y][x] = pred(x, y)
-        int v = mode < 18 ? ang_pixel<pixel>(s, N, mode, bLuma, x, y, depth) : ang_pixel<pixel>(s, N, mode, bLuma, y, x, depth);
-        out[e] = (pixel)v;
+        const int m = e / LW, L = e - m * LW, idx = L - N, mode = m + 2;
+        const bool hor = mode < 18;
+        const int angleOffset = hor ? 10 - mode : mode - 26;
+        const int angle = c_angle[8 + angleOffset];
+        const pixel* s = min(abs(mode - 26), abs(mode - 10)) > thr ? sf : sr;
+        int i;                                             // index into the (flipped) neighbour view
+        if (angle >= 0 || idx >= -1) i = idx + 1;
+        else i = N2 + ((128 + (-1 - idx) * c_invAngle[-angleOffset - 1]) >> 8);
+        i = max(0, min(i, 4 * N));                         // entries outside a mode's reach are never read back
+        const int j = (!hor || i == 0) ? i : (i <= N2 ? N2 + i : i - N2);
+        line[m][L] = s[j];
+    }
+    __syncthreads();
+    pixel* out = dest + b * 33 * N * N;
+    const int maxVal = (1 << depth) - 1;
+    for (int q = threadIdx.x; q < 33 * N * N / 4; q += blockDim.x)
+    {
+        const int e = q * 4;
+        const int m = e >> (2 * log2N), r = e & (N * N - 1), mode = m + 2;
+        const int y = r >> log2N, x = r & (N - 1);
+        const bool hor = mode < 18;
+        const int angle = c_angle[8 + (hor ? 10 - mode : mode - 26)];
+        int o[4];
+        if (!angle)
+        {
+            // pure horizontal / vertical: copy of ref[1 + x], first column edge-filtered for luma (:176-189)
+            const pixel* a = &line[m][N + x];
+#pragma unroll
+            for (int k = 0; k < 4; k++) o[k] = a[k];
+            if (bLuma && x == 0)
+            {
+                const pixel* s = min(abs(mode - 26), abs(mode - 10)) > thr ? sf : sr;
+                auto nb = [&](int i) -> int { return (!hor || i == 0) ? (int)s[i] : (i <= N2 ? (int)s[N2 + i] : (int)s[i - N2]); };
+                const int v = (int16_t)(nb(1) + ((nb(N2 + 1 + y) - nb(0)) >> 1));
+                o[0] = v < 0 ? 0 : (v > maxVal ? maxVal : v);
+            }
+        }
+        else
+        {
+            const int angleSum = (y + 1) * angle, offset = angleSum >> 5, fraction = angleSum & 31;
+            const pixel* a = &line[m][offset + x + N];
+            int pv[5];
+#pragma unroll
+            for (int k = 0; k < 5; k++) pv[k] = a[k];
+#pragma unroll
+            for (int k = 0; k < 4; k++) o[k] = fraction ? ((32 - fraction) * pv[k] + fraction * pv[k + 1] + 16) >> 5 : pv[k];
+        }
+        if (sizeof(pixel) == 1)
+            *(uint32_t*)(out + e) = (uint32_t)o[0] | ((uint32_t)o[1] << 8) | ((uint32_t)o[2] << 16) | ((uint32_t)o[3] << 24);
+        else
+            *(uint2*)(out + e) = make_uint2((uint32_t)o[0] | ((uint32_t)o[1] << 16), (uint32_t)o[2] | ((uint32_t)o[3] << 16));
     }
 }
 
