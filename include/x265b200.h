@@ -136,11 +136,14 @@ int x265b200_dct_table(int N, int16_t* out);
  *   SUB_PS  S<-P-P (also calcresidual)   ADD_PS P<-clip(P+S)                 cu[].sub_ps / add_ps / calcresidual
  *   ADDAVG  P<-clip((S+S+offset)>>shift)  PIXELAVG_PP P<-(P+P+1)>>1          pu[].addAvg / pixelavg_pp
  *   TRANSPOSE P<-P, dst contiguous w x w                                     cu[].transpose
- *   WEIGHT_PP P<-P, WEIGHT_SP P<-S: p0 = w0, p1 = round, p2 = shift, p3 = offset   weight_pp / weight_sp */
+ *   WEIGHT_PP P<-P, WEIGHT_SP P<-S: p0 = w0, p1 = round, p2 = shift, p3 = offset   weight_pp / weight_sp
+ *   SCALE1D_128TO64 P<-P: two 128-pixel lines at src0 (+0, +128) -> two 64-pixel lines at dst (+0, +64)  scale1D_128to64 (pixel.cpp:559)
+ *   SCALE2D_64TO32  P<-P: 64x64 block (src0Stride) -> contiguous 32x32                                   scale2D_64to32 (pixel.cpp:585)
+ *   (w, h are ignored for the two scale ops) */
 enum { X265B200_GL_COPY_PP = 0, X265B200_GL_COPY_SS, X265B200_GL_COPY_SP, X265B200_GL_COPY_PS, X265B200_GL_FILL_S,
        X265B200_GL_CPY2DTO1D_SHL, X265B200_GL_CPY2DTO1D_SHR, X265B200_GL_CPY1DTO2D_SHL, X265B200_GL_CPY1DTO2D_SHR,
        X265B200_GL_SUB_PS, X265B200_GL_ADD_PS, X265B200_GL_ADDAVG, X265B200_GL_PIXELAVG_PP, X265B200_GL_TRANSPOSE,
-       X265B200_GL_WEIGHT_PP, X265B200_GL_WEIGHT_SP };
+       X265B200_GL_WEIGHT_PP, X265B200_GL_WEIGHT_SP, X265B200_GL_SCALE1D_128TO64, X265B200_GL_SCALE2D_64TO32 };
 typedef struct { int64_t dstOff, src0Off, src1Off; } x265b200_glue_job;
 int x265b200_glue_dev(x265b200_ctx* ctx, int op, int depth, int w, int h, void* dst, int64_t dstStride,
                       const void* src0, int64_t src0Stride, const void* src1, int64_t src1Stride,
@@ -190,7 +193,7 @@ int x265b200_intra_allangs_dev(x265b200_ctx* ctx, int depth, int log2N, const vo
  *      searches.  One job = one call of motionEstimate(); per-job semantics are identical:
  *      mvmin/mvmax are full-pel inclusive bounds, mvp and mvc[] are quarter-pel, the result
  *      (outMv, outCost) is `outQMv` and the return value.  searchMethod uses the X265_*_SEARCH
- *      numbering of x265.h:492-497 (0 DIA, 1 HEX, 2 UMH, 3 STAR, 5 FULL; 4 SEA is a "next" row);
+ *      numbering of x265.h:492-497 (0 DIA, 1 HEX, 2 UMH, 3 STAR, 5 FULL; 4 SEA goes through x265b200_me_batch_sea_dev);
  *      searchMethod 6 (X265B200_ME_REFINE) runs MotionEstimate::refineMV instead (motion.cpp:606-737:
  *      predictor, one square refine, sub-pel with the fixed workload[5]; mvc/merange/subpelRefine/maxSlices unused;
  *      the reference returns only the MV, outCost is the final SATD + mvcost).
@@ -232,6 +235,34 @@ int x265b200_me_batch_chroma_dev(x265b200_ctx* ctx, int depth, const void* fencP
                                  const void* refPlane, const void* const* refPlanes, int64_t refStride,
                                  const x265b200_me_chroma* chroma, x265b200_me_job* jobs, int64_t n, int maxW, int maxH,
                                  int searchMethod, int subpelRefine, int merange, double lambda, int maxSlices);
+/* --me sea (X265_SEA, motion.cpp:1242-1395): the same entry with MotionEstimate::integral[] supplied.
+ * integralPlanes: DEVICE array [numRefs][12] (numRefs = 1 when refPlanes is NULL) of uint32 plane pointers in the order of
+ * FrameData::m_meIntegral (framedata.h:171: 32x32, 32x24, 32x8, 24x32, 16x16, 16x12, 16x4, 12x16, 8x32, 8x8, 4x16, 4x4);
+ * plane element (puX + puY*refStride) holds the box sum whose top-left pixel is (puX, puY) of the matching reference
+ * plane (search.cpp:2264).  Where the reference's ads/sad_x4 read fencPUYuv pixels outside the PU (8x4, 4x8, 32x8, 8x32:
+ * stale data of an earlier PU), this backend reads 0. */
+int x265b200_me_batch_sea_dev(x265b200_ctx* ctx, int depth, const void* fencPlane, int64_t fencStride,
+                              const void* refPlane, const void* const* refPlanes, int64_t refStride,
+                              const uint32_t* const* integralPlanes, x265b200_me_job* jobs, int64_t n, int maxW, int maxH,
+                              int subpelRefine, int merange, double lambda, int maxSlices);
+/* FrameFilter::computeMEIntegral (framefilter.cpp:722-825) for a whole reconstructed frame: the 12 integral planes of a
+ * PicYuv luma plane (origin pointer, `stride`, margins padX = maxCU+32 / padY = maxCU+16, maxHeight = numCuInHeight*maxCU).
+ * planes[k] = ORIGIN (element matching pixel 0,0) of plane k, same geometry as the pixel plane.  Elements the reference
+ * finalises -- box origins in columns [-padX, stride-padX-w) and rows [1-padY, maxHeight+padY-1-h] -- hold the w x h box
+ * sum; the first row and the trailing rows/columns (running sums / never written in the reference) are written as 0. */
+int x265b200_sea_integral_dev(x265b200_ctx* ctx, int depth, const void* reconOrigin, int64_t stride, int padX, int padY, int maxHeight,
+                              uint32_t* const planes[12]);
+/* integral_inith[INTEGRAL_w] / integral_initv[INTEGRAL_h] (primitives.h:368-369; framefilter.cpp:39-140), one row:
+ * inith: sum[x] = pix[x] + .. + pix[x+width-1] + sum[x - stride] for x < stride - width;
+ * initv: sum[x] = sum[x + height*stride] - sum[x] for x < stride.  width/height in {4, 8, 12, 16, 24, 32}. */
+int x265b200_integral_inith_dev(x265b200_ctx* ctx, int depth, int width, uint32_t* sum, const void* pix, int64_t stride);
+int x265b200_integral_initv_dev(x265b200_ctx* ctx, int height, uint32_t* sum, int64_t stride);
+/* pu[].ads = ads_x1 / ads_x2 / ads_x4<lx,ly> (primitives.h:138,250; pixel.cpp:121-165) for n rows: job i tests `width`
+ * consecutive x offsets of sums + sumsOff against encDC / thresh (kind = 1, 2 or 4; lxHalf = lx >> 1; costMvX[width] is
+ * shared) and writes the surviving offsets, in order, to mvs + i*width and their number to counts[i]. */
+typedef struct { int64_t sumsOff; int32_t thresh; int32_t encDC[4]; } x265b200_ads_job;
+int x265b200_ads_dev(x265b200_ctx* ctx, int kind, int lxHalf, const uint32_t* sums, int64_t delta, const uint16_t* costMvX, int width,
+                     const x265b200_ads_job* jobs, int64_t n, int16_t* mvs, int32_t* counts);
 /* Frame form of the same search: every 2Nx2N PU (levels selected by puMask: bit0 64x64, bit1 32x32, bit2 16x16,
  * bit3 8x8) of every 64x64 CTU against numRefs reference planes.  One CTA per (CTU, reference) stages the
  * source CTU and the search window in shared memory with TMA, then runs the PU searches from there.
@@ -268,6 +299,10 @@ double x265b200_lambda(int qp, int depth);
 typedef struct { int32_t b, p0, p1; int32_t doSearch[2]; int32_t mvSlot[2]; } x265b200_la_triple;
 int x265b200_lowres_init_dev(x265b200_ctx* ctx, int depth, const void* src, int64_t srcStride,
                              void* const planes[4], int64_t dstStride, int width, int height, int marginX, int marginY);
+/* extendPicBorder (pixel.cpp:1027-1041: PicYuv / Lowres margins) and, with marginY = 0, primitives.extendRowBorder =
+ * extendCURowColBorder (primitives.h:340; ipfilter.cpp:59-77): replicate the edge pixels of the width x height picture
+ * at `origin` into marginX columns left/right and marginY rows above/below. */
+int x265b200_extend_border_dev(x265b200_ctx* ctx, int depth, void* origin, int64_t stride, int width, int height, int marginX, int marginY);
 int x265b200_la_intra_dev(x265b200_ctx* ctx, int depth, const void* plane0, int64_t stride, int widthInCU, int heightInCU,
                           const int32_t* invQscale, int intraPenalty, int32_t* intraCost, uint8_t* intraMode,
                           uint16_t* lowresCosts, int32_t* rowSatds, int32_t* sums);

@@ -599,3 +599,81 @@ void ref_quant_dequant_batch(const int16_t* coef, const int32_t* quantCoeff, int
     });
 }
 }
+
+/* ---- --me sea: the integral planes exactly as FrameFilter::computeMEIntegral drives the table
+ * (framefilter.cpp:722-825: integral_inith per pixel row, integral_initv h rows later), and the reference's own
+ * MotionEstimate running X265_SEA against them.  planes[k]: ORIGIN (element of pixel 0,0) of plane k. */
+extern "C" {
+void ref_sea_integrals(const void* reconOrigin, intptr_t stride, int padX, int padY, int maxHeight, uint32_t* const planes[12])
+{
+    ensure_init();
+    static const int W[12] = { 32, 32, 32, 24, 16, 16, 16, 12, 8, 8, 4, 4 };
+    static const int H[12] = { 32, 24, 8, 32, 16, 12, 4, 16, 32, 8, 16, 4 };
+    static const int idx[33] = { 0, 0, 0, 0, INTEGRAL_4, 0, 0, 0, INTEGRAL_8, 0, 0, 0, INTEGRAL_12, 0, 0, 0, INTEGRAL_16,
+                                 0, 0, 0, 0, 0, 0, 0, INTEGRAL_24, 0, 0, 0, 0, 0, 0, 0, INTEGRAL_32 };
+    for (int k = 0; k < 12; k++)
+        memset(planes[k] - padY * stride - padX, 0, stride * sizeof(uint32_t));
+    const int height = maxHeight + padY - 1;
+    for (int y = -padY; y < height; y++)
+    {
+        pixel* pix = (pixel*)reconOrigin + y * stride - padX;
+        for (int k = 0; k < 12; k++)
+        {
+            uint32_t* sum = planes[k] + (y + 1) * stride - padX;
+            primitives.integral_inith[idx[W[k]]](sum, pix, stride);
+            if (y >= H[k] - padY)
+                primitives.integral_initv[idx[H[k]]](sum - H[k] * stride, stride);
+        }
+    }
+}
+
+/* integralPlanes[12]: pointers addressed like refPlane (element 0 <-> refPlane[0]) */
+int ref_me_batch_sea(const void* fencPlane, intptr_t fencStride, const void* refPlane, intptr_t refStride,
+                     uint32_t* const integralPlanes[12], RefMEJob* jobs, int64_t n, int subpelRefine, int merange, int qp,
+                     int maxSlices, int threads)
+{
+    ensure_init();
+    { BitCost warm; warm.setQP(qp); }
+    int nt = threads < 1 ? 1 : threads;
+    std::vector<MotionEstimate*> mes(nt);
+    for (int t = 0; t < nt; t++)
+    {
+        mes[t] = new MotionEstimate;
+        mes[t]->init(X265_CSP_I400);
+        mes[t]->setQP(qp);
+    }
+    parallel_for(n, nt, [&](int64_t i, int t) {
+        RefMEJob& j = jobs[i];
+        MotionEstimate& me = *mes[t];
+        ReferencePlanes ref;
+        ref.fpelPlane[0] = (pixel*)refPlane;
+        ref.lumaStride = refStride;
+        ref.isLowres = false;
+        intptr_t off = j.puX + (intptr_t)j.puY * refStride;
+        /* pixels of fencPUYuv outside the PU are stale in the encoder; the backend defines them as 0 */
+        memset(me.fencPUYuv.m_buf[0], 0, sizeof(pixel) * FENC_STRIDE * FENC_STRIDE);
+        me.setSourcePU((pixel*)fencPlane, fencStride, off, j.w, j.h, X265_SEA, X265_SEA, X265_SEA, subpelRefine);
+        for (int k = 0; k < INTEGRAL_PLANE_NUM; k++) me.integral[k] = integralPlanes[k] + off;      /* search.cpp:2264 */
+        MV mvmin(j.mvminX, j.mvminY), mvmax(j.mvmaxX, j.mvmaxY), mvp(j.mvpX, j.mvpY), out(0, 0);
+        MV mvc[8];
+        for (int k = 0; k < j.numCand; k++) mvc[k] = MV(j.mvc[k][0], j.mvc[k][1]);
+        j.outCost = me.motionEstimate(&ref, mvmin, mvmax, mvp, j.numCand, mvc, merange, out, (uint32_t)maxSlices);
+        j.outMvX = out.x; j.outMvY = out.y;
+    });
+    for (int t = 0; t < nt; t++) delete mes[t];
+    return 0;
+}
+
+void ref_integral_inith(int w, uint32_t* sum, const void* pix, intptr_t stride)
+{
+    ensure_init();
+    const int k = w == 4 ? INTEGRAL_4 : w == 8 ? INTEGRAL_8 : w == 12 ? INTEGRAL_12 : w == 16 ? INTEGRAL_16 : w == 24 ? INTEGRAL_24 : INTEGRAL_32;
+    primitives.integral_inith[k](sum, (pixel*)pix, stride);
+}
+void ref_integral_initv(int h, uint32_t* sum, intptr_t stride)
+{
+    ensure_init();
+    const int k = h == 4 ? INTEGRAL_4 : h == 8 ? INTEGRAL_8 : h == 12 ? INTEGRAL_12 : h == 16 ? INTEGRAL_16 : h == 24 ? INTEGRAL_24 : INTEGRAL_32;
+    primitives.integral_initv[k](sum, stride);
+}
+} /* extern "C" */

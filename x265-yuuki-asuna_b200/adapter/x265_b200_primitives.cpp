@@ -354,6 +354,84 @@ void lowpass_dct_thunk(const int16_t* src, int16_t* dst, intptr_t srcStride)
     CK(x265b200_download(C(), dst, dD, N * N * 2));
 }
 
+// ---- --me sea support (pixel.cpp:121-165, framefilter.cpp:39-140) ---------------------------------------------------
+template<int KIND, int LXH>
+int ads_thunk(int encDC[], uint32_t* sums, int delta, uint16_t* costMvX, int16_t* mvs, int width, int thresh)
+{
+    if (width <= 0) return 0;
+    const size_t seg = (size_t)width + LXH;                 // elements read from each of the (up to) two plane rows
+    uint32_t* dS = (uint32_t*)dev(0, 2 * seg * 4);
+    CK(x265b200_upload(C(), dS, sums, seg * 4));
+    if (KIND != 1) CK(x265b200_upload(C(), dS + seg, sums + delta, seg * 4));
+    void* dC = up1d(1, costMvX, (size_t)width * 2);
+    x265b200_ads_job job; job.sumsOff = 0; job.thresh = thresh;
+    for (int k = 0; k < 4; k++) job.encDC[k] = k < KIND ? encDC[k] : 0;
+    void* dJ = up1d(2, &job, sizeof(job));
+    void* dM = dev(3, (size_t)width * 2); void* dN = dev(4, 4);
+    CK(x265b200_ads_dev(C(), KIND, LXH, dS, (int64_t)seg, (const uint16_t*)dC, width, (const x265b200_ads_job*)dJ, 1, (int16_t*)dM, (int32_t*)dN));
+    int32_t n; CK(x265b200_download(C(), &n, dN, 4));
+    if (n > 0) CK(x265b200_download(C(), mvs, dM, (size_t)n * 2));
+    return n;
+}
+template<int W>
+void integral_inith_thunk(uint32_t* sum, pixel* pix, intptr_t stride)
+{
+    if (stride <= W) return;
+    uint32_t* dS = (uint32_t*)dev(0, (size_t)2 * stride * 4);
+    CK(x265b200_upload(C(), dS, sum - stride, (size_t)stride * 4));
+    void* dP = up1d(1, pix, (size_t)stride * PX);
+    CK(x265b200_integral_inith_dev(C(), X265_DEPTH, W, dS + stride, dP, stride));
+    CK(x265b200_download(C(), sum, dS + stride, (size_t)(stride - W) * 4));
+}
+template<int H>
+void integral_initv_thunk(uint32_t* sum, intptr_t stride)
+{
+    if (stride <= 0) return;
+    uint32_t* dS = (uint32_t*)dev(0, (size_t)(H + 1) * stride * 4);
+    CK(x265b200_upload(C(), dS, sum, (size_t)stride * 4));
+    CK(x265b200_upload(C(), dS + (size_t)H * stride, sum + (size_t)H * stride, (size_t)stride * 4));
+    CK(x265b200_integral_initv_dev(C(), H, dS, stride));
+    CK(x265b200_download(C(), sum, dS, (size_t)stride * 4));
+}
+
+// ---- lowres / borders / pre-scale (pixel.cpp:559-628, ipfilter.cpp:59-77) ------------------------------------------------
+void frame_init_lowres_thunk(const pixel* src0, pixel* dst0, pixel* dsth, pixel* dstv, pixel* dstc, intptr_t srcStride, intptr_t dstStride,
+                             int width, int height)
+{
+    if (width <= 0 || height <= 0) return;
+    void* dS = up_span(0, src0, srcStride, 2 * width + 1, 2 * height + 1, PX);       // the C loop reads src0[2x+2] and the row 2y+2
+    void* planes[4];
+    for (int k = 0; k < 4; k++) planes[k] = dev(1 + k, (size_t)width * height * PX);
+    CK(x265b200_lowres_init_dev(C(), X265_DEPTH, dS, srcStride, planes, width, width, height, 0, 0));
+    pixel* dst[4] = { dst0, dsth, dstv, dstc };
+    for (int k = 0; k < 4; k++) down2d(dst[k], dstStride, planes[k], width, height, PX);
+}
+void extend_row_border_thunk(pixel* txt, intptr_t stride, int width, int height, int marginX)
+{
+    if (height <= 0 || marginX <= 0) return;
+    const size_t span = (size_t)(height - 1) * stride + width + 2 * (size_t)marginX;
+    char* d = (char*)dev(0, span * PX);
+    CK(x265b200_upload(C(), d, txt - marginX, span * PX));
+    CK(x265b200_extend_border_dev(C(), X265_DEPTH, d + (size_t)marginX * PX, stride, width, height, marginX, 0));
+    CK(x265b200_download(C(), txt - marginX, d, span * PX));
+}
+void scale1D_thunk(pixel* dst, const pixel* src)
+{
+    void* dS = up1d(0, src, 256 * PX); void* dD = dev(1, 128 * PX);
+    x265b200_glue_job job = { 0, 0, 0 };
+    void* dJ = up1d(3, &job, sizeof(job));
+    CK(x265b200_glue_dev(C(), X265B200_GL_SCALE1D_128TO64, X265_DEPTH, 128, 1, dD, 128, dS, 256, nullptr, 0, (const x265b200_glue_job*)dJ, 1, 0, 0, 0, 0));
+    CK(x265b200_download(C(), dst, dD, 128 * PX));
+}
+void scale2D_thunk(pixel* dst, const pixel* src, intptr_t stride)
+{
+    void* dS = up_span(0, src, stride, 64, 64, PX); void* dD = dev(1, 32 * 32 * PX);
+    x265b200_glue_job job = { 0, 0, 0 };
+    void* dJ = up1d(3, &job, sizeof(job));
+    CK(x265b200_glue_dev(C(), X265B200_GL_SCALE2D_64TO32, X265_DEPTH, 32, 32, dD, 32, dS, stride, nullptr, 0, (const x265b200_glue_job*)dJ, 1, 0, 0, 0, 0));
+    CK(x265b200_download(C(), dst, dD, 32 * 32 * PX));
+}
+
 } // namespace
 
 namespace X265_NS {
@@ -392,20 +470,63 @@ void setupAssemblyPrimitives(EncoderPrimitives& p, int /*cpuMask: SIMD flags are
     PU(64, 48) PU(48, 64) PU(64, 16) PU(16, 64)
 #undef PU
 
-    // chroma 4:2:0 4-tap filters (ipfilter.cpp:375-383); satd/sa8d/sse chroma slots are aliases of the
-    // luma pointers installed by setupAliasPrimitives (primitives.cpp:139-208)
-#define CH420(LW, LH, W, H) \
-    p.chroma[X265_CSP_I420].pu[LUMA_ ## LW ## x ## LH].filter_hpp = ip_pp<4, W, H, X265B200_IP_HPP>; \
-    p.chroma[X265_CSP_I420].pu[LUMA_ ## LW ## x ## LH].filter_vpp = ip_pp<4, W, H, X265B200_IP_VPP>; \
-    p.chroma[X265_CSP_I420].pu[LUMA_ ## LW ## x ## LH].filter_hps = ip_hps<4, W, H>; \
-    p.chroma[X265_CSP_I420].pu[LUMA_ ## LW ## x ## LH].filter_vps = ip_vps<4, W, H>; \
-    p.chroma[X265_CSP_I420].pu[LUMA_ ## LW ## x ## LH].filter_vsp = ip_vsp<4, W, H>; \
-    p.chroma[X265_CSP_I420].pu[LUMA_ ## LW ## x ## LH].filter_vss = ip_vss<4, W, H>;
-    CH420(8, 8, 4, 4) CH420(16, 16, 8, 8) CH420(32, 32, 16, 16) CH420(64, 64, 32, 32)
-    CH420(16, 8, 8, 4) CH420(8, 16, 4, 8) CH420(32, 16, 16, 8) CH420(16, 32, 8, 16) CH420(64, 32, 32, 16) CH420(32, 64, 16, 32)
-    CH420(32, 24, 16, 12) CH420(24, 32, 12, 16) CH420(32, 8, 16, 4) CH420(8, 32, 4, 16)
-    CH420(64, 48, 32, 24) CH420(48, 64, 24, 32) CH420(64, 16, 32, 8) CH420(16, 64, 8, 32)
+    // chroma tables (ipfilter.cpp:375-403, pixel.cpp:1168-1320): 4-tap filters + p2s for every chroma PU shape of 4:2:0 / 4:2:2 /
+    // 4:4:4, addAvg / copy_pp for 4:2:0 / 4:2:2 (the 4:4:4 ones, and all chroma satd, are aliases of the luma pointers installed by
+    // setupAliasPrimitives, primitives.cpp:139-208)
+#define CH_FILT(CSP, PART, W, H) \
+    p.chroma[CSP].pu[PART].filter_hpp = ip_pp<4, W, H, X265B200_IP_HPP>; \
+    p.chroma[CSP].pu[PART].filter_vpp = ip_pp<4, W, H, X265B200_IP_VPP>; \
+    p.chroma[CSP].pu[PART].filter_hps = ip_hps<4, W, H>; \
+    p.chroma[CSP].pu[PART].filter_vps = ip_vps<4, W, H>; \
+    p.chroma[CSP].pu[PART].filter_vsp = ip_vsp<4, W, H>; \
+    p.chroma[CSP].pu[PART].filter_vss = ip_vss<4, W, H>; \
+    p.chroma[CSP].pu[PART].p2s[NONALIGNED] = ip_p2s<W, H>; \
+    p.chroma[CSP].pu[PART].p2s[ALIGNED] = ip_p2s<W, H>;
+#define CH_GLUE(CSP, PART, W, H) \
+    p.chroma[CSP].pu[PART].addAvg[NONALIGNED] = addAvg_thunk<W, H>; \
+    p.chroma[CSP].pu[PART].addAvg[ALIGNED] = addAvg_thunk<W, H>; \
+    p.chroma[CSP].pu[PART].copy_pp = copy_pp_thunk<W, H>;
+#define CH420(W, H) CH_FILT(X265_CSP_I420, CHROMA_420_ ## W ## x ## H, W, H) CH_GLUE(X265_CSP_I420, CHROMA_420_ ## W ## x ## H, W, H)
+#define CH422(W, H) CH_FILT(X265_CSP_I422, CHROMA_422_ ## W ## x ## H, W, H) CH_GLUE(X265_CSP_I422, CHROMA_422_ ## W ## x ## H, W, H)
+#define CH444(W, H) CH_FILT(X265_CSP_I444, LUMA_ ## W ## x ## H, W, H)
+    CH_GLUE(X265_CSP_I420, CHROMA_420_2x2, 2, 2)                 // no 2x2 filters in the table (ipfilter.cpp:419-421)
+    CH420(4, 4) CH420(2, 4) CH420(4, 2) CH420(8, 8) CH420(8, 4) CH420(4, 8) CH420(8, 6) CH420(6, 8) CH420(8, 2) CH420(2, 8)
+    CH420(16, 16) CH420(16, 8) CH420(8, 16) CH420(16, 12) CH420(12, 16) CH420(16, 4) CH420(4, 16)
+    CH420(32, 32) CH420(32, 16) CH420(16, 32) CH420(32, 24) CH420(24, 32) CH420(32, 8) CH420(8, 32)
+    CH422(4, 8) CH422(4, 4) CH422(2, 4) CH422(2, 8) CH422(8, 16) CH422(8, 8) CH422(4, 16) CH422(8, 12) CH422(6, 16) CH422(8, 4) CH422(2, 16)
+    CH422(16, 32) CH422(16, 16) CH422(8, 32) CH422(16, 24) CH422(12, 32) CH422(16, 8) CH422(4, 32)
+    CH422(32, 64) CH422(32, 32) CH422(16, 64) CH422(32, 48) CH422(24, 64) CH422(32, 16) CH422(8, 64)
+    CH444(4, 4) CH444(8, 8) CH444(4, 8) CH444(8, 4) CH444(16, 16) CH444(16, 8) CH444(8, 16) CH444(16, 12) CH444(12, 16) CH444(16, 4) CH444(4, 16)
+    CH444(32, 32) CH444(32, 16) CH444(16, 32) CH444(32, 24) CH444(24, 32) CH444(32, 8) CH444(8, 32)
+    CH444(64, 64) CH444(64, 32) CH444(32, 64) CH444(64, 48) CH444(48, 64) CH444(64, 16) CH444(16, 64)
 #undef CH420
+#undef CH422
+#undef CH444
+#undef CH_FILT
+#undef CH_GLUE
+
+    // chroma CU blocks (pixel.cpp:1228-1246, :1307-1325): copies / residual / recon, sse_pp, and the sa8d compositions
+#define CH_CU(CSP, IDX, W, H) \
+    p.chroma[CSP].cu[IDX].copy_sp = copy_sp_thunk<W, H>; p.chroma[CSP].cu[IDX].copy_ps = copy_ps_thunk<W, H>; \
+    p.chroma[CSP].cu[IDX].copy_ss = copy_ss_thunk<W, H>; p.chroma[CSP].cu[IDX].sub_ps = sub_ps_thunk<W, H>; \
+    p.chroma[CSP].cu[IDX].add_ps[NONALIGNED] = add_ps_thunk<W, H>; p.chroma[CSP].cu[IDX].add_ps[ALIGNED] = add_ps_thunk<W, H>;
+    CH_CU(X265_CSP_I420, BLOCK_420_2x2, 2, 2) CH_CU(X265_CSP_I420, BLOCK_420_4x4, 4, 4) CH_CU(X265_CSP_I420, BLOCK_420_8x8, 8, 8)
+    CH_CU(X265_CSP_I420, BLOCK_420_16x16, 16, 16) CH_CU(X265_CSP_I420, BLOCK_420_32x32, 32, 32)
+    CH_CU(X265_CSP_I422, BLOCK_422_2x4, 2, 4) CH_CU(X265_CSP_I422, BLOCK_422_4x8, 4, 8) CH_CU(X265_CSP_I422, BLOCK_422_8x16, 8, 16)
+    CH_CU(X265_CSP_I422, BLOCK_422_16x32, 16, 32) CH_CU(X265_CSP_I422, BLOCK_422_32x64, 32, 64)
+#undef CH_CU
+    p.chroma[X265_CSP_I420].cu[BLOCK_420_4x4].sse_pp = sse_pp_thunk<4, 4>;     p.chroma[X265_CSP_I420].cu[BLOCK_420_8x8].sse_pp = sse_pp_thunk<8, 8>;
+    p.chroma[X265_CSP_I420].cu[BLOCK_420_16x16].sse_pp = sse_pp_thunk<16, 16>; p.chroma[X265_CSP_I420].cu[BLOCK_420_32x32].sse_pp = sse_pp_thunk<32, 32>;
+    p.chroma[X265_CSP_I422].cu[BLOCK_422_4x8].sse_pp = sse_pp_thunk<4, 8>;     p.chroma[X265_CSP_I422].cu[BLOCK_422_8x16].sse_pp = sse_pp_thunk<8, 16>;
+    p.chroma[X265_CSP_I422].cu[BLOCK_422_16x32].sse_pp = sse_pp_thunk<16, 32>; p.chroma[X265_CSP_I422].cu[BLOCK_422_32x64].sse_pp = sse_pp_thunk<32, 64>;
+    p.chroma[X265_CSP_I420].cu[BLOCK_8x8].sa8d   = cmp_thunk<4, 4, X265B200_CMP_SATD>;       // = chroma pu 4x4 satd (pixel.cpp:1243)
+    p.chroma[X265_CSP_I420].cu[BLOCK_16x16].sa8d = cmp_thunk<8, 8, X265B200_CMP_SA8D8>;      // sa8d8<8, 8>
+    p.chroma[X265_CSP_I420].cu[BLOCK_32x32].sa8d = cmp_thunk<16, 16, X265B200_CMP_SA8D>;     // sa8d16<16, 16>
+    p.chroma[X265_CSP_I420].cu[BLOCK_64x64].sa8d = cmp_thunk<32, 32, X265B200_CMP_SA8D>;     // sa8d16<32, 32>
+    p.chroma[X265_CSP_I422].cu[BLOCK_8x8].sa8d   = cmp_thunk<4, 8, X265B200_CMP_SATD>;       // satd4<4, 8> (pixel.cpp:1322)
+    p.chroma[X265_CSP_I422].cu[BLOCK_16x16].sa8d = cmp_thunk<8, 16, X265B200_CMP_SA8D8>;     // sa8d8<8, 16>
+    p.chroma[X265_CSP_I422].cu[BLOCK_32x32].sa8d = cmp_thunk<16, 32, X265B200_CMP_SA8D>;     // sa8d16<16, 32>
+    p.chroma[X265_CSP_I422].cu[BLOCK_64x64].sa8d = cmp_thunk<32, 64, X265B200_CMP_SA8D>;     // sa8d16<32, 64>
 
 #define CU(IDX, N, LOG2) \
     p.cu[IDX].sa8d   = cmp_thunk<N, N, X265B200_CMP_SA8D>; \
@@ -453,6 +574,25 @@ void setupAssemblyPrimitives(EncoderPrimitives& p, int /*cpuMask: SIMD flags are
     p.cu[BLOCK_8x8].lowpass_dct = lowpass_dct_thunk<1, 8>;
     p.cu[BLOCK_16x16].lowpass_dct = lowpass_dct_thunk<2, 16>;
     p.cu[BLOCK_32x32].lowpass_dct = lowpass_dct_thunk<3, 32>;
+
+    // --me sea: pu[].ads per pixel.cpp:1105-1129 and the integral row primitives (framefilter.cpp:142-156)
+#define ADS(W, H, K) p.pu[LUMA_ ## W ## x ## H].ads = ads_thunk<K, (W >> 1)>;
+    ADS(4, 4, 1) ADS(8, 8, 1) ADS(8, 4, 2) ADS(4, 8, 2) ADS(16, 16, 4) ADS(16, 8, 2) ADS(8, 16, 2) ADS(16, 12, 1) ADS(12, 16, 1)
+    ADS(16, 4, 1) ADS(4, 16, 1) ADS(32, 32, 4) ADS(32, 16, 2) ADS(16, 32, 2) ADS(32, 24, 4) ADS(24, 32, 4) ADS(32, 8, 4) ADS(8, 32, 4)
+    ADS(64, 64, 4) ADS(64, 32, 2) ADS(32, 64, 2) ADS(64, 48, 4) ADS(48, 64, 4) ADS(64, 16, 4) ADS(16, 64, 4)
+#undef ADS
+    p.integral_inith[INTEGRAL_4] = integral_inith_thunk<4>;   p.integral_initv[INTEGRAL_4] = integral_initv_thunk<4>;
+    p.integral_inith[INTEGRAL_8] = integral_inith_thunk<8>;   p.integral_initv[INTEGRAL_8] = integral_initv_thunk<8>;
+    p.integral_inith[INTEGRAL_12] = integral_inith_thunk<12>; p.integral_initv[INTEGRAL_12] = integral_initv_thunk<12>;
+    p.integral_inith[INTEGRAL_16] = integral_inith_thunk<16>; p.integral_initv[INTEGRAL_16] = integral_initv_thunk<16>;
+    p.integral_inith[INTEGRAL_24] = integral_inith_thunk<24>; p.integral_initv[INTEGRAL_24] = integral_initv_thunk<24>;
+    p.integral_inith[INTEGRAL_32] = integral_inith_thunk<32>; p.integral_initv[INTEGRAL_32] = integral_initv_thunk<32>;
+
+    p.frameInitLowres = frame_init_lowres_thunk;
+    p.frameInitLowerRes = frame_init_lowres_thunk;
+    p.extendRowBorder = extend_row_border_thunk;
+    p.scale1D_128to64[NONALIGNED] = scale1D_thunk; p.scale1D_128to64[ALIGNED] = scale1D_thunk;
+    p.scale2D_64to32 = scale2D_thunk;
 }
 
 } // namespace X265_NS

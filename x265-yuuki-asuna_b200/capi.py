@@ -392,3 +392,41 @@ def _ctx_me_frame_dev(self, depth, dCur, curStride, refOrigins, refStride, margi
 
 
 Ctx.me_frame_dev = _ctx_me_frame_dev
+
+
+# ---- --me sea --------------------------------------------------------------------------------------
+ADS_JOB = np.dtype([("sumsOff", np.int64), ("thresh", np.int32), ("encDC", np.int32, (4,))], align=True)      # 32 bytes, as the C struct
+SEA_PLANE_W = [32, 32, 32, 24, 16, 16, 16, 12, 8, 8, 4, 4]       # FrameData::m_meIntegral order (framedata.h:171)
+SEA_PLANE_H = [32, 24, 8, 32, 16, 12, 4, 16, 32, 8, 16, 4]
+
+
+def _ctx_sea_integral_dev(self, depth, dReconOrigin, stride, padX, padY, maxHeight, planeOrigins):
+    arr = (ctypes.c_void_p * 12)(*[int(p) for p in planeOrigins])
+    self._chk(self.L.x265b200_sea_integral_dev(self.h, depth, _vp(dReconOrigin), _i64(stride), int(padX), int(padY), int(maxHeight), arr))
+
+
+def _ctx_integral_inith_dev(self, depth, width, dSum, dPix, stride):
+    self._chk(self.L.x265b200_integral_inith_dev(self.h, depth, int(width), _vp(dSum), _vp(dPix), _i64(stride)))
+
+
+def _ctx_integral_initv_dev(self, height, dSum, stride):
+    self._chk(self.L.x265b200_integral_initv_dev(self.h, int(height), _vp(dSum), _i64(stride)))
+
+
+def _ctx_ads_dev(self, kind, lxHalf, dSums, delta, dCostMvX, width, dJobs, n, dMvs, dCounts):
+    self._chk(self.L.x265b200_ads_dev(self.h, int(kind), int(lxHalf), _vp(dSums), _i64(delta), _vp(dCostMvX), int(width), _vp(dJobs), _i64(n),
+                                      _vp(dMvs), _vp(dCounts)))
+
+
+def _ctx_me_batch_sea_dev(self, depth, dFenc, fencStride, dRef, refStride, dIntegralPlanes, dJobs, n, maxW, maxH, subpelRefine,
+                          merange, lam, maxSlices=1, dRefPlanes=None):
+    self._chk(self.L.x265b200_me_batch_sea_dev(self.h, depth, _vp(dFenc), _i64(fencStride), _vp(dRef), _vp(dRefPlanes), _i64(refStride),
+                                               _vp(dIntegralPlanes), _vp(dJobs), _i64(n), int(maxW), int(maxH), int(subpelRefine),
+                                               int(merange), ctypes.c_double(lam), int(maxSlices)))
+
+
+Ctx.sea_integral_dev = _ctx_sea_integral_dev
+Ctx.integral_inith_dev = _ctx_integral_inith_dev
+Ctx.integral_initv_dev = _ctx_integral_initv_dev
+Ctx.ads_dev = _ctx_ads_dev
+Ctx.me_batch_sea_dev = _ctx_me_batch_sea_dev

@@ -85,8 +85,13 @@ int intra_filter_dev(Ctx*, int depth, int log2N, const void* src, void* dst, int
 int intra_allangs_dev(Ctx*, int depth, int log2N, const void* refPix, const void* filtPix, void* dest, int bLuma, int64_t n);
 
 int me_batch_dev(Ctx*, int depth, const void* fencPlane, int64_t fencStride, const void* refPlane, const void* const* refPlanes,
-                 int64_t refStride, const x265b200_me_chroma* chroma, x265b200_me_job* jobs, int64_t n, int maxW, int maxH,
-                 int searchMethod, int subpelRefine, int merange, double lambda, int maxSlices);
+                 int64_t refStride, const x265b200_me_chroma* chroma, const uint32_t* const* seaPlanes, x265b200_me_job* jobs, int64_t n,
+                 int maxW, int maxH, int searchMethod, int subpelRefine, int merange, double lambda, int maxSlices);
+int sea_integral_dev(Ctx*, int depth, const void* reconOrigin, int64_t stride, int padX, int padY, int maxHeight, uint32_t* const planes[12]);
+int integral_inith_dev(Ctx*, int depth, int w, uint32_t* sum, const void* pix, int64_t stride);
+int integral_initv_dev(Ctx*, int h, uint32_t* sum, int64_t stride);
+int ads_dev(Ctx*, int kind, int lxHalf, const uint32_t* sums, int64_t delta, const uint16_t* costMvX, int width,
+            const x265b200_ads_job* jobs, int64_t n, int16_t* mvs, int32_t* counts);
 void host_bitcost_table(double lambda, uint16_t* out);
 int glue_dev(Ctx*, int op, int depth, int w, int h, void* dst, int64_t dstStride, const void* src0, int64_t src0Stride,
              const void* src1, int64_t src1Stride, const x265b200_glue_job* jobs, int64_t n, int p0, int p1, int p2, int p3);
@@ -102,6 +107,7 @@ int me_frame_dev(Ctx*, int depth, const void* curOrigin, int64_t curStride, cons
                  int marginX, int marginY, int rowsTotal, int ctuCols, int ctuRows, int puMask, const int32_t* mvpCtu,
                  int searchMethod, int subpelRefine, int merange, double lambda, int32_t* out);
 int lowres_init_dev(Ctx*, int depth, const void* src, int64_t srcStride, void* const planes[4], int64_t dstStride, int width, int height, int marginX, int marginY);
+int extend_border_dev(Ctx*, int depth, void* origin, int64_t stride, int width, int height, int marginX, int marginY);
 int la_intra_dev(Ctx*, int depth, const void* plane0, int64_t stride, int widthInCU, int heightInCU, const int32_t* invQscale,
                  int intraPenalty, int32_t* intraCost, uint8_t* intraMode, uint16_t* lowresCosts, int32_t* rowSatds, int32_t* sums);
 int la_estimate_dev(Ctx*, int depth, const void* const* planes, int64_t stride, int widthInCU, int heightInCU,
@@ -397,8 +403,41 @@ int x265b200_me_batch_dev(x265b200_ctx* ctx, int depth, const void* fencPlane, i
                           int searchMethod, int subpelRefine, int merange, double lambda, int maxSlices)
 {
     REQUIRE_CTX(ctx);
-    return me_batch_dev(CTX(ctx), depth, fencPlane, fencStride, refPlane, refPlanes, refStride, nullptr, jobs, n, maxW, maxH,
+    return me_batch_dev(CTX(ctx), depth, fencPlane, fencStride, refPlane, refPlanes, refStride, nullptr, nullptr, jobs, n, maxW, maxH,
                         searchMethod, subpelRefine, merange, lambda, maxSlices);
+}
+int x265b200_me_batch_sea_dev(x265b200_ctx* ctx, int depth, const void* fencPlane, int64_t fencStride,
+                              const void* refPlane, const void* const* refPlanes, int64_t refStride,
+                              const uint32_t* const* integralPlanes, x265b200_me_job* jobs, int64_t n, int maxW, int maxH,
+                              int subpelRefine, int merange, double lambda, int maxSlices)
+{
+    REQUIRE_CTX(ctx);
+    if (!integralPlanes) { set_error("me_batch_sea: integralPlanes is NULL"); return -1; }
+    return me_batch_dev(CTX(ctx), depth, fencPlane, fencStride, refPlane, refPlanes, refStride, nullptr, integralPlanes, jobs, n, maxW, maxH,
+                        4 /* X265_SEA */, subpelRefine, merange, lambda, maxSlices);
+}
+int x265b200_sea_integral_dev(x265b200_ctx* ctx, int depth, const void* reconOrigin, int64_t stride, int padX, int padY, int maxHeight,
+                              uint32_t* const planes[12])
+{
+    REQUIRE_CTX(ctx);
+    if (!planes) { set_error("sea_integral: planes is NULL"); return -1; }
+    return sea_integral_dev(CTX(ctx), depth, reconOrigin, stride, padX, padY, maxHeight, planes);
+}
+int x265b200_integral_inith_dev(x265b200_ctx* ctx, int depth, int width, uint32_t* sum, const void* pix, int64_t stride)
+{
+    REQUIRE_CTX(ctx);
+    return integral_inith_dev(CTX(ctx), depth, width, sum, pix, stride);
+}
+int x265b200_integral_initv_dev(x265b200_ctx* ctx, int height, uint32_t* sum, int64_t stride)
+{
+    REQUIRE_CTX(ctx);
+    return integral_initv_dev(CTX(ctx), height, sum, stride);
+}
+int x265b200_ads_dev(x265b200_ctx* ctx, int kind, int lxHalf, const uint32_t* sums, int64_t delta, const uint16_t* costMvX, int width,
+                     const x265b200_ads_job* jobs, int64_t n, int16_t* mvs, int32_t* counts)
+{
+    REQUIRE_CTX(ctx);
+    return ads_dev(CTX(ctx), kind, lxHalf, sums, delta, costMvX, width, jobs, n, mvs, counts);
 }
 int x265b200_me_batch_chroma_dev(x265b200_ctx* ctx, int depth, const void* fencPlane, int64_t fencStride,
                                  const void* refPlane, const void* const* refPlanes, int64_t refStride,
@@ -407,7 +446,7 @@ int x265b200_me_batch_chroma_dev(x265b200_ctx* ctx, int depth, const void* fencP
 {
     REQUIRE_CTX(ctx);
     if (!chroma) { set_error("me_batch_chroma: chroma descriptor is NULL"); return -1; }
-    return me_batch_dev(CTX(ctx), depth, fencPlane, fencStride, refPlane, refPlanes, refStride, chroma, jobs, n, maxW, maxH,
+    return me_batch_dev(CTX(ctx), depth, fencPlane, fencStride, refPlane, refPlanes, refStride, chroma, nullptr, jobs, n, maxW, maxH,
                         searchMethod, subpelRefine, merange, lambda, maxSlices);
 }
 int x265b200_me_frame_dev(x265b200_ctx* ctx, int depth, const void* curOrigin, int64_t curStride, const void* const* refOriginsHost, int numRefs,
@@ -442,6 +481,11 @@ int x265b200_lowres_init_dev(x265b200_ctx* ctx, int depth, const void* src, int6
 {
     REQUIRE_CTX(ctx);
     return lowres_init_dev(CTX(ctx), depth, src, srcStride, planes, dstStride, width, height, marginX, marginY);
+}
+int x265b200_extend_border_dev(x265b200_ctx* ctx, int depth, void* origin, int64_t stride, int width, int height, int marginX, int marginY)
+{
+    REQUIRE_CTX(ctx);
+    return extend_border_dev(CTX(ctx), depth, origin, stride, width, height, marginX, marginY);
 }
 int x265b200_la_intra_dev(x265b200_ctx* ctx, int depth, const void* plane0, int64_t stride, int widthInCU, int heightInCU,
                           const int32_t* invQscale, int intraPenalty, int32_t* intraCost, uint8_t* intraMode,

@@ -72,6 +72,18 @@ __global__ void __launch_bounds__(256) glue_kernel(GlueArgs a)
     case X265B200_GL_WEIGHT_SP:                                                             // weight_sp_c :493
         dp[d] = (pixel)clip_px(((a.p0 * ((int)q0[s0] + 8192) + a.p1) >> a.p2) + a.p3, maxVal);
         break;
+    case X265B200_GL_SCALE1D_128TO64:                                                       // scale1D_128to64 :559 (w = 128, h = 1)
+    {
+        const pixel* s = p0 + job.src0Off + (x >> 6) * 128 + ((x & 63) << 1);
+        dp[job.dstOff + x] = (pixel)(((int)s[0] + (int)s[1] + 1) >> 1);
+        break;
+    }
+    case X265B200_GL_SCALE2D_64TO32:                                                        // scale2D_64to32 :585 (w = h = 32)
+    {
+        const pixel* s = p0 + job.src0Off + (int64_t)(2 * y) * a.src0Stride + 2 * x;
+        dp[job.dstOff + y * 32 + x] = (pixel)(((int)s[0] + (int)s[1] + (int)s[a.src0Stride] + (int)s[a.src0Stride + 1] + 2) >> 2);
+        break;
+    }
     }
 }
 
@@ -87,7 +99,7 @@ static int launch_glue(Ctx* ctx, int op, const GlueArgs& a)
     GL_CASE(X265B200_GL_FILL_S) GL_CASE(X265B200_GL_CPY2DTO1D_SHL) GL_CASE(X265B200_GL_CPY2DTO1D_SHR)
     GL_CASE(X265B200_GL_CPY1DTO2D_SHL) GL_CASE(X265B200_GL_CPY1DTO2D_SHR) GL_CASE(X265B200_GL_SUB_PS) GL_CASE(X265B200_GL_ADD_PS)
     GL_CASE(X265B200_GL_ADDAVG) GL_CASE(X265B200_GL_PIXELAVG_PP) GL_CASE(X265B200_GL_TRANSPOSE)
-    GL_CASE(X265B200_GL_WEIGHT_PP) GL_CASE(X265B200_GL_WEIGHT_SP)
+    GL_CASE(X265B200_GL_WEIGHT_PP) GL_CASE(X265B200_GL_WEIGHT_SP) GL_CASE(X265B200_GL_SCALE1D_128TO64) GL_CASE(X265B200_GL_SCALE2D_64TO32)
     default: set_error("glue: unknown op %d", op); return -1;
     }
 #undef GL_CASE
@@ -100,6 +112,8 @@ int glue_dev(Ctx* ctx, int op, int depth, int w, int h, void* dst, int64_t dstSt
 {
     if (n <= 0 || w <= 0 || h <= 0) return 0;
     if ((op == X265B200_GL_CPY2DTO1D_SHR || op == X265B200_GL_CPY1DTO2D_SHR) && p0 < 1) { set_error("glue: shr needs shift > 0"); return -1; }
+    if (op == X265B200_GL_SCALE1D_128TO64) { w = 128; h = 1; }
+    if (op == X265B200_GL_SCALE2D_64TO32) { w = 32; h = 32; }
     GlueArgs a;
     a.dst = dst; a.dstStride = dstStride; a.src0 = src0; a.src0Stride = src0Stride; a.src1 = src1; a.src1Stride = src1Stride;
     a.jobs = jobs; a.n = n; a.w = w; a.h = h; a.depth = depth; a.p0 = p0; a.p1 = p1; a.p2 = p2; a.p3 = p3;

@@ -145,13 +145,14 @@ intra_filter_kernel(const pixel* __restrict__ src, pixel* __restrict__ dst, int 
 // produces 4 horizontally adjacent pixels from 5 line bytes and issues one 32-bit (64-bit for 16-bit pixels) store.
 // (The first version computed one pixel per thread through ang_pixel: 620 us per 274 MB size at 2160p, 15x off the
 // write roofline; profiles/r01_launches_v5.csv.)
+constexpr int ALLANGS_PITCH = 120;      // bytes/elements per line row: 3N + 2 = 98 entries + the 16-byte read-ahead of the word path
 template<typename pixel>
 __global__ void __launch_bounds__(256)
 intra_allangs_kernel(const pixel* __restrict__ refPix, const pixel* __restrict__ filtPix, pixel* __restrict__ dest,
-                     int log2N, int bLuma, int depth, int64_t n)
+                     int log2N, int bLuma, int depth, int64_t n, int vec16)
 {
     __shared__ pixel sr[132], sf[132];
-    __shared__ __align__(8) pixel line[33][104];          // entry L <-> ref[L - N], L in [0, 3N + 1]
+    __shared__ __align__(16) pixel line[33][ALLANGS_PITCH];   // entry L <-> ref[L - N], L in [0, 3N + 1]
     const int N = 1 << log2N, N2 = N << 1, len = 4 * N + 1, LW = 3 * N + 2;
     const int64_t b = blockIdx.x;
     for (int i = threadIdx.x; i < len; i += blockDim.x) { sr[i] = refPix[b * len + i]; sf[i] = filtPix[b * len + i]; }
@@ -175,6 +176,52 @@ intra_allangs_kernel(const pixel* __restrict__ refPix, const pixel* __restrict__
     __syncthreads();
     pixel* out = dest + b * 33 * N * N;
     const int maxVal = (1 << depth) - 1;
+    if (sizeof(pixel) == 1 && vec16)
+    {
+        // 8-bit fast path: a thread produces 16 consecutive output bytes (one row segment for N >= 16, 2 rows of 8, 4 rows
+        // of 4) from aligned word loads of the line, two pixels per 32-bit multiply-add (16-bit lanes: 255*32 + 16 < 2^16),
+        // and issues one 128-bit store
+        const uint32_t* lw = (const uint32_t*)&line[0][0];
+        const int CH = N < 16 ? N : 16, nw = CH >> 2;
+        for (int q = threadIdx.x; q < 33 * N * N / 16; q += blockDim.x)
+        {
+            const int e = q * 16;
+            const int m = e >> (2 * log2N), r = e & (N * N - 1), mode = m + 2;
+            const bool hor = mode < 18;
+            const int angle = c_angle[8 + (hor ? 10 - mode : mode - 26)];
+            uint32_t ow[4];
+            for (int c = 0; c < 16 / CH; c++)
+            {
+                const int rr = r + c * CH, y = rr >> log2N, x = rr & (N - 1);
+                const int angleSum = (y + 1) * angle, offset = angleSum >> 5;
+                const uint32_t f = (uint32_t)(angleSum & 31), g = 32u - f;
+                const int base = offset + x + N, sh = (base & 3) * 8;
+                const uint32_t* src = lw + m * (ALLANGS_PITCH / 4) + (base >> 2);
+                uint32_t w[5];
+#pragma unroll
+                for (int k = 0; k < 5; k++) w[k] = k <= nw ? src[k] : 0u;
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                {
+                    if (k >= nw) break;
+                    const uint32_t A = __funnelshift_r(w[k], w[k + 1], sh), B = __funnelshift_rc(w[k], w[k + 1], sh + 8);
+                    const uint32_t r02 = (((A & 0x00FF00FFu) * g + (B & 0x00FF00FFu) * f + 0x00100010u) >> 5) & 0x00FF00FFu;
+                    const uint32_t r13 = ((((A >> 8) & 0x00FF00FFu) * g + ((B >> 8) & 0x00FF00FFu) * f + 0x00100010u) >> 5) & 0x00FF00FFu;
+                    ow[c * nw + k] = r02 | (r13 << 8);
+                }
+                if (!angle && bLuma && x == 0)
+                {
+                    // pure horizontal / vertical, first column edge-filtered for luma (:176-189)
+                    const pixel* s = min(abs(mode - 26), abs(mode - 10)) > thr ? sf : sr;
+                    auto nb = [&](int i) -> int { return (!hor || i == 0) ? (int)s[i] : (i <= N2 ? (int)s[N2 + i] : (int)s[i - N2]); };
+                    const int v = (int16_t)(nb(1) + ((nb(N2 + 1 + y) - nb(0)) >> 1));
+                    ow[c * nw] = (ow[c * nw] & 0xFFFFFF00u) | (uint32_t)(v < 0 ? 0 : (v > maxVal ? maxVal : v));
+                }
+            }
+            *(uint4*)(out + e) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        }
+        return;
+    }
     for (int q = threadIdx.x; q < 33 * N * N / 4; q += blockDim.x)
     {
         const int e = q * 4;
@@ -214,6 +261,121 @@ intra_allangs_kernel(const pixel* __restrict__ refPix, const pixel* __restrict__
     }
 }
 
+// 8-bit all-angles, persistent form (the default for 16-byte aligned 8-bit output).  The first two versions launched one
+// CTA per block: at 2160p that is 130 560 CTAs of 8x8 blocks whose fixed cost (neighbour fetch -> barrier -> line build with
+// per-entry divisions and divergent __constant__ lookups -> barrier) dominated: 450 / 251 / 185 us for the 8 / 16 / 32 sizes
+// against a 45 us write floor (profiles/r01_launches_v4.csv).  Here a CTA loops over groups of G blocks: the (mode, L) ->
+// neighbour-index table is built ONCE per CTA, the next group's neighbour bytes are prefetched into registers while the
+// current group is predicted, a thread emits 16 output bytes per 128-bit store from aligned word loads of the line with
+// two pixels per 32-bit multiply-add (16-bit lanes: 255*32 + 16 < 2^16).
+template<int LOG2N>
+__global__ void __launch_bounds__(256)
+intra_allangs8_kernel(const uint8_t* __restrict__ refPix, const uint8_t* __restrict__ filtPix, uint8_t* __restrict__ dest, int bLuma, int64_t n)
+{
+    constexpr int N = 1 << LOG2N, N2 = N << 1, LEN = 4 * N + 1, LW = 3 * N + 2;
+    constexpr int G = N == 32 ? 1 : (N == 16 ? 2 : (N == 8 ? 4 : 8));
+    constexpr int PITCH = (LW + 16 + 7) & ~7;                  // line row: LW entries + the read-ahead of the word path
+    constexpr int SP = 136;                                     // neighbour array pitch (>= LEN)
+    constexpr int CPB = 33 * N * N / 16;                        // 16-byte chunks per block
+    constexpr int CH = N < 16 ? N : 16, NWD = CH / 4;
+    constexpr int TOT = G * 2 * LEN;                            // neighbour bytes staged per group (<= 272)
+    __shared__ uint16_t jtab[33 * LW];
+    __shared__ uint8_t s2[G][2 * SP];                           // per block: [unfiltered | filtered] neighbours
+    __shared__ __align__(16) uint8_t line[G][33][PITCH];        // entry L <-> ref[L - N]
+    const int tid = threadIdx.x;
+    const int thr = N == 8 ? 7 : (N == 16 ? 1 : (N == 32 ? 0 : 99));      // constants.cpp:561 g_intraFilterFlags
+
+    for (int e = tid; e < 33 * LW; e += 256)
+    {
+        const int m = e / LW, L = e - m * LW, idx = L - N, mode = m + 2;
+        const bool hor = mode < 18;
+        const int angleOffset = hor ? 10 - mode : mode - 26;
+        const int angle = c_angle[8 + angleOffset];
+        int i;                                                  // index into the (flipped) neighbour view, intrapred.cpp:146-172
+        if (angle >= 0 || idx >= -1) i = idx + 1;
+        else i = N2 + ((128 + (-1 - idx) * c_invAngle[-angleOffset - 1]) >> 8);
+        i = max(0, min(i, 4 * N));                              // entries outside a mode's reach are never read back
+        const int j = (!hor || i == 0) ? i : (i <= N2 ? N2 + i : i - N2);
+        jtab[e] = (uint16_t)(j + (min(abs(mode - 26), abs(mode - 10)) > thr ? SP : 0));
+    }
+
+    // staging map of this thread's (up to two) neighbour bytes
+    int sOff[2], gOf[2]; int64_t srcOff[2]; bool sFilt[2], sOk[2];
+#pragma unroll
+    for (int u = 0; u < 2; u++)
+    {
+        const int t = tid + u * 256;
+        sOk[u] = t < TOT;
+        const int g = t / (2 * LEN), rem = t - g * (2 * LEN), which = rem >= LEN, i = rem - which * LEN;
+        gOf[u] = g; sFilt[u] = which; sOff[u] = g * (2 * SP) + which * SP + i; srcOff[u] = (int64_t)g * LEN + i;
+    }
+    const int64_t stride = (int64_t)gridDim.x * G;
+    int64_t b0 = (int64_t)blockIdx.x * G;
+    uint8_t v[2] = { 0, 0 };
+#pragma unroll
+    for (int u = 0; u < 2; u++)
+        if (sOk[u] && b0 + gOf[u] < n) v[u] = (sFilt[u] ? filtPix : refPix)[b0 * LEN + srcOff[u]];
+
+    const uint32_t* lw = (const uint32_t*)&line[0][0][0];
+    for (; b0 < n; b0 += stride)
+    {
+#pragma unroll
+        for (int u = 0; u < 2; u++) if (sOk[u]) (&s2[0][0])[sOff[u]] = v[u];
+        __syncthreads();
+        const int64_t nb0 = b0 + stride;
+#pragma unroll
+        for (int u = 0; u < 2; u++)
+            if (sOk[u] && nb0 + gOf[u] < n) v[u] = (sFilt[u] ? filtPix : refPix)[nb0 * LEN + srcOff[u]];
+
+        for (int e = tid; e < G * 33 * LW; e += 256)
+        {
+            const int g = e / (33 * LW), r = e - g * (33 * LW), m = r / LW, L = r - m * LW;
+            line[g][m][L] = s2[g][jtab[r]];
+        }
+        __syncthreads();
+
+        for (int q = tid; q < G * CPB; q += 256)
+        {
+            const int g = q / CPB, e = (q - g * CPB) * 16;
+            if (b0 + g >= n) continue;
+            const int m = e >> (2 * LOG2N), r = e & (N * N - 1), mode = m + 2;
+            const bool hor = mode < 18;
+            const int angle = c_angle[8 + (hor ? 10 - mode : mode - 26)];
+            uint32_t ow[4];
+#pragma unroll
+            for (int c = 0; c < 16 / CH; c++)
+            {
+                const int rr = r + c * CH, y = rr >> LOG2N, x = rr & (N - 1);
+                const int angleSum = (y + 1) * angle, offset = angleSum >> 5;
+                const uint32_t f = (uint32_t)(angleSum & 31), gg = 32u - f;
+                const int base = offset + x + N, sh = (base & 3) * 8;
+                const uint32_t* src = lw + (g * 33 + m) * (PITCH / 4) + (base >> 2);
+                uint32_t w[NWD + 1];
+#pragma unroll
+                for (int k = 0; k <= NWD; k++) w[k] = src[k];
+#pragma unroll
+                for (int k = 0; k < NWD; k++)
+                {
+                    const uint32_t A = __funnelshift_r(w[k], w[k + 1], sh), B = __funnelshift_rc(w[k], w[k + 1], sh + 8);
+                    const uint32_t r02 = (((A & 0x00FF00FFu) * gg + (B & 0x00FF00FFu) * f + 0x00100010u) >> 5) & 0x00FF00FFu;
+                    const uint32_t r13 = ((((A >> 8) & 0x00FF00FFu) * gg + ((B >> 8) & 0x00FF00FFu) * f + 0x00100010u) >> 5) & 0x00FF00FFu;
+                    ow[c * NWD + k] = r02 | (r13 << 8);
+                }
+                if (!angle && bLuma && x == 0)
+                {
+                    // pure horizontal / vertical: first column edge-filtered for luma (intrapred.cpp:176-189)
+                    const uint8_t* s = &s2[g][min(abs(mode - 26), abs(mode - 10)) > thr ? SP : 0];
+                    auto nb = [&](int i) -> int { return (!hor || i == 0) ? (int)s[i] : (i <= N2 ? (int)s[N2 + i] : (int)s[i - N2]); };
+                    const int vv = (int16_t)(nb(1) + ((nb(N2 + 1 + y) - nb(0)) >> 1));
+                    ow[c * NWD] = (ow[c * NWD] & 0xFFFFFF00u) | (uint32_t)(vv < 0 ? 0 : (vv > 255 ? 255 : vv));
+                }
+            }
+            *(uint4*)(dest + (b0 + g) * (int64_t)(33 * N * N) + e) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        }
+        __syncthreads();
+    }
+}
+
 int intra_pred_dev(Ctx* ctx, int depth, int log2N, const void* nbr, void* dst, int64_t dstStride,
                    const x265b200_intra_job* jobs, int64_t n)
 {
@@ -241,8 +403,22 @@ int intra_allangs_dev(Ctx* ctx, int depth, int log2N, const void* refPix, const 
 {
     if (n <= 0) return 0;
     if (log2N < 2 || log2N > 5) { set_error("intra_allangs: log2N %d", log2N); return -1; }
-    if (depth > 8) intra_allangs_kernel<uint16_t><<<(unsigned)n, 256, 0, ctx->stream>>>((const uint16_t*)refPix, (const uint16_t*)filtPix, (uint16_t*)dest, log2N, bLuma, depth, n);
-    else           intra_allangs_kernel<uint8_t><<<(unsigned)n, 256, 0, ctx->stream>>>((const uint8_t*)refPix, (const uint8_t*)filtPix, (uint8_t*)dest, log2N, bLuma, depth, n);
+    if (depth > 8) intra_allangs_kernel<uint16_t><<<(unsigned)n, 256, 0, ctx->stream>>>((const uint16_t*)refPix, (const uint16_t*)filtPix, (uint16_t*)dest, log2N, bLuma, depth, n, 0);
+    else if (((uintptr_t)dest & 15) == 0)
+    {
+        const int G = log2N == 5 ? 1 : (log2N == 4 ? 2 : (log2N == 3 ? 4 : 8));
+        const int64_t groups = (n + G - 1) / G, cap = (int64_t)ctx->smCount * 8;
+        const unsigned grid = (unsigned)(groups < cap ? groups : cap);
+        const uint8_t* r = (const uint8_t*)refPix; const uint8_t* f = (const uint8_t*)filtPix; uint8_t* d = (uint8_t*)dest;
+        switch (log2N)
+        {
+        case 2: intra_allangs8_kernel<2><<<grid, 256, 0, ctx->stream>>>(r, f, d, bLuma, n); break;
+        case 3: intra_allangs8_kernel<3><<<grid, 256, 0, ctx->stream>>>(r, f, d, bLuma, n); break;
+        case 4: intra_allangs8_kernel<4><<<grid, 256, 0, ctx->stream>>>(r, f, d, bLuma, n); break;
+        default: intra_allangs8_kernel<5><<<grid, 256, 0, ctx->stream>>>(r, f, d, bLuma, n); break;
+        }
+    }
+    else           intra_allangs_kernel<uint8_t><<<(unsigned)n, 256, 0, ctx->stream>>>((const uint8_t*)refPix, (const uint8_t*)filtPix, (uint8_t*)dest, log2N, bLuma, depth, n, 0);
     ctx->launches++;
     return check(cudaGetLastError(), "intra_allangs kernel launch");
 }

@@ -83,6 +83,18 @@ int lowres_init_dev(Ctx* ctx, int depth, const void* src, int64_t srcStride, voi
     return 0;
 }
 
+// extendPicBorder (pixel.cpp:1027-1041) / extendCURowColBorder (ipfilter.cpp:59-77, marginY = 0) on their own
+int extend_border_dev(Ctx* ctx, int depth, void* origin, int64_t stride, int width, int height, int marginX, int marginY)
+{
+    if (width <= 0 || height <= 0 || (marginX <= 0 && marginY <= 0)) return 0;
+    const int64_t total = (int64_t)(width + 2 * marginX) * (height + 2 * marginY);
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    if (depth > 8) extend_border_kernel<uint16_t><<<blocks, 256, 0, ctx->stream>>>((uint16_t*)origin, stride, width, height, marginX, marginY);
+    else           extend_border_kernel<uint8_t><<<blocks, 256, 0, ctx->stream>>>((uint8_t*)origin, stride, width, height, marginX, marginY);
+    ctx->launches++;
+    return check(cudaGetLastError(), "extend_border launch");
+}
+
 // ---------------------------------------------------------------------------------------------
 // small per-thread 8x8 helpers (phase 2 and intra estimate)
 // ---------------------------------------------------------------------------------------------

@@ -77,6 +77,10 @@ struct MEState
     int      csize, hshift, vshift;
     const uint16_t* cost;     // centred lambda-scaled MV cost table (bitcost.cpp:31-60)
     int      mvpx, mvpy;      // setMVP(qmvp), bitcost.h:41
+    // --me sea (motion.cpp:1242-1395): MotionEstimate::integral[12] of this reference (plane pointers addressed like the
+    // reference plane) and the PU's element offset in them (search.cpp:2264); warp-cooperative searches only
+    const uint32_t* const* integral;
+    int64_t  integralOff;
 };
 
 constexpr int kMvTableHalf = 2 * 32768;
@@ -1182,6 +1186,157 @@ struct MESearch
     }
 };
 
+#ifndef ME_FORCE_THREAD
+// ---- --me sea: successive elimination (motion.cpp:1242-1395) -------------------------------------------------------
+// One table lookup of the lambda-scaled cost, index clipped to the table like mvcost() above.
+template<typename pixel>
+__device__ __forceinline__ int cost_at(const MEState<pixel>& s, int idx)
+{
+    return (int)s.cost[clip3i(-kMvTableHalf, kMvTableHalf, idx)];
+}
+
+template<typename pixel>
+__device__ __noinline__ void sea_search(MESearch<pixel>& S, const MEState<pixel>& s, MV2 omv, int merange)
+{
+    const int w = s.w, h = s.h, lane = s.lane;
+    const int minX = max(omv.x - merange, S.mvmin.x), minY = max(omv.y - merange, S.mvmin.y);
+    const int maxX = min(omv.x + merange, S.mvmax.x), maxY = min(omv.y + merange, S.mvmax.y);
+    const int width = (maxX - minX + 3) & ~3;                                   // "SEA is fastest in multiples of 4" (:1259-1260)
+    int deltaX = (w <= 8) ? w : (w >> 1);
+    int deltaY = (h <= 8) ? h : (h >> 1);
+
+    // partition classes of :1268-1283
+    const int wh = (w << 8) | h;
+#define ME_IS(a, b) (wh == (((a) << 8) | (b)))
+    const bool smallRect = ME_IS(4, 4) || ME_IS(16, 12) || ME_IS(12, 16) || ME_IS(16, 4) || ME_IS(4, 16);
+    const bool verticalRect = ME_IS(32, 64) || ME_IS(16, 32) || ME_IS(8, 16) || ME_IS(4, 8);
+    const bool horizontalRect = ME_IS(64, 32) || ME_IS(32, 16) || ME_IS(16, 8) || ME_IS(8, 4);
+    const bool asymV = ME_IS(12, 16) || ME_IS(4, 16) || ME_IS(24, 32) || ME_IS(8, 32) || ME_IS(48, 64) || ME_IS(16, 64);
+    const bool asymH = ME_IS(16, 12) || ME_IS(16, 4) || ME_IS(32, 24) || ME_IS(32, 8) || ME_IS(64, 48) || ME_IS(64, 16);
+    // pu[partEnum].ads (pixel.cpp:1105-1129): ads_x1 / ads_x2 / ads_x4 <lx, ly>
+    const int adsKind = (ME_IS(4, 4) || ME_IS(8, 8) || ME_IS(16, 12) || ME_IS(12, 16) || ME_IS(16, 4) || ME_IS(4, 16)) ? 1
+                        : (verticalRect || horizontalRect) ? 2 : 4;
+    // deltaY counts rows of the integral plane for these shapes only (:1349-1355)
+    const bool rowDelta = ME_IS(64, 64) || ME_IS(32, 32) || ME_IS(16, 16) || verticalRect || asymV;
+#undef ME_IS
+    const int lxHalf = w >> 1;
+
+    // tempPartEnum (:1285-1301): the sub-block whose pixel sums form encDC
+    int tw, th;
+    if (verticalRect) { tw = w; th = h >> 1; }
+    else if (horizontalRect) { tw = w >> 1; th = h; }
+    else if (asymV || asymH) { tw = smallRect ? w : (w >> 1); th = smallRect ? h : (h >> 1); }
+    else { tw = (w <= 8) ? w : (w >> 1); th = (w <= 8) ? h : (h >> 1); }
+
+    // encDC = sad_x4(zero, fenc, fenc + deltaX, fenc + deltaY*64, fenc + deltaX + deltaY*64) (:1305-1311).  Where a
+    // sub-block leaves the PU the reference reads whatever an earlier PU left in fencPUYuv; this backend defines those
+    // pixels as 0 (the cache is conceptually cleared by setSourcePU).
+    int encDC[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+    {
+        const int bx = (k & 1) ? deltaX : 0, by = (k & 2) ? deltaY : 0;
+        int acc = 0;
+        for (int e = lane; e < tw * th; e += 32)
+        {
+            const int y = by + e / tw, x = bx + e % tw;
+            if (x < w && y < h) acc += (int)s.fenc[y * 64 + x];
+        }
+        encDC[k] = warp_sum(acc);
+    }
+
+    // integral plane (:1313-1347)
+    int plane;
+    switch (deltaX)
+    {
+    case 32: plane = (deltaY % 24 == 0) ? 1 : (deltaY == 8) ? 2 : 0; break;
+    case 24: plane = 3; break;
+    case 16: plane = (deltaY % 12 == 0) ? 5 : (deltaY == 4) ? 6 : 4; break;
+    case 12: plane = 7; break;
+    case 8:  plane = (deltaY == 32) ? 8 : 9; break;
+    case 4:  plane = (deltaY == 16) ? 10 : 11; break;
+    default: plane = 11; break;
+    }
+    const uint32_t* sumsBase = s.integral[plane] + s.integralOff;
+    int64_t delta = rowDelta ? (int64_t)deltaY * s.stride : (int64_t)deltaY;
+    if (verticalRect) encDC[1] = encDC[2];
+    if (horizontalRect) delta = deltaX;
+
+    for (int ty = minY; ty <= maxY; ty++)
+    {
+        // p_cost_mvy = m_cost_mvy - qmvp.y is indexed with the FULL-PEL y and scaled by 4 (:1250, :1363)
+        const int ycost = cost_at(s, ty - 2 * s.mvpy) << 2;
+        if (S.bcost <= ycost) continue;
+        int bc = S.bcost - ycost;
+        const int thresh = bc;
+        const uint32_t* sums = sumsBase + minX + (int64_t)ty * s.stride;
+
+        // ads() of the row (pixel.cpp:121-165): which x offsets survive, and how many (xn)
+        int xn = 0;
+        for (int base = 0; base < width; base += 32)
+        {
+            const int i = base + lane;
+            bool pass = false;
+            if (i < width)
+            {
+                int64_t ads = llabs((int64_t)encDC[0] - (int64_t)sums[i]);
+                if (adsKind == 2) ads += llabs((int64_t)encDC[1] - (int64_t)sums[i + delta]);
+                if (adsKind == 4)
+                    ads += llabs((int64_t)encDC[1] - (int64_t)sums[i + lxHalf]) + llabs((int64_t)encDC[2] - (int64_t)sums[i + delta]) +
+                           llabs((int64_t)encDC[3] - (int64_t)sums[i + delta + lxHalf]);
+                ads += cost_at(s, ((minX + i) << 2) - s.mvpx);                   // fpelCostMvX[minX + i] (bitcost.cpp:56-75)
+                pass = (int)ads < thresh;
+            }
+            xn += __popc(__ballot_sync(0xffffffffu, pass));
+        }
+        const int nx3 = (xn / 3) * 3;        // survivors costed by COST_MV_X3_ABS; the last xn % 3 go through COST_MV (:1383-1390)
+
+        int k = 0;
+        bool restored = false;
+        for (int base = 0; base < width && k < xn; base += 32)
+        {
+            const int i = base + lane;
+            bool pass = false;
+            if (i < width)
+            {
+                int64_t ads = llabs((int64_t)encDC[0] - (int64_t)sums[i]);
+                if (adsKind == 2) ads += llabs((int64_t)encDC[1] - (int64_t)sums[i + delta]);
+                if (adsKind == 4)
+                    ads += llabs((int64_t)encDC[1] - (int64_t)sums[i + lxHalf]) + llabs((int64_t)encDC[2] - (int64_t)sums[i + delta]) +
+                           llabs((int64_t)encDC[3] - (int64_t)sums[i + delta + lxHalf]);
+                ads += cost_at(s, ((minX + i) << 2) - s.mvpx);
+                pass = (int)ads < thresh;
+            }
+            unsigned m = __ballot_sync(0xffffffffu, pass);
+            while (m)
+            {
+                int ox[4] = { 0, 0, 0, 0 }, oy[4] = { ty, ty, ty, ty }, c[4];
+                int cnt = 0;
+                while (m && cnt < 4) { const int b = __ffs(m) - 1; m &= m - 1; ox[cnt++] = minX + base + b; }
+                warp_sad_k<pixel>(s, cnt, ox, oy, c);
+                for (int q = 0; q < cnt; q++, k++)
+                {
+                    if (k < nx3)
+                    {
+                        // COST_MV_X3_ABS (:300-313): x cost only, through the doubly-offset p_cost_mvx; compared with bcost - ycost
+                        const int cost = c[q] + cost_at(s, (ox[q] << 2) - 2 * s.mvpx);
+                        if (cost < bc) { bc = cost; S.bmv = mv2(ox[q], ty); }
+                    }
+                    else
+                    {
+                        if (!restored) { bc += ycost; restored = true; }
+                        const int cost = c[q] + S.fcost(ox[q], ty);                // COST_MV (:238-244)
+                        if (cost < bc) { bc = cost; S.bmv = mv2(ox[q], ty); }
+                    }
+                }
+            }
+        }
+        if (!restored) bc += ycost;
+        S.bcost = bc;
+    }
+}
+#endif
+
 // Full MotionEstimate::motionEstimate.  Returns the cost; (outx,outy) = outQMv.
 template<typename pixel>
 __device__ int motion_estimate(const MEState<pixel>& s, MV2 mvmin, MV2 mvmax, MV2 qmvp, int numCand, const int* mvc /* [numCand][2] */,
@@ -1410,6 +1565,11 @@ __device__ int motion_estimate(const MEState<pixel>& s, MV2 mvmin, MV2 mvmax, MV
         }
         break;
     }
+#ifndef ME_FORCE_THREAD
+    case ME_SEA:      // motion.cpp:1242-1395
+        sea_search<pixel>(S, s, omv, merange);
+        break;
+#endif
     case ME_FULL:     // motion.cpp:1397-1441 (non-HME)
     {
         for (int ty = mvmin.y; ty <= mvmax.y; ty++)

@@ -1,7 +1,7 @@
 // me_kernels.cu -- batched full-resolution motion estimation: one warp per PU search, bit-exact
 // with MotionEstimate::motionEstimate (source/encoder/motion.cpp:739-1569) for
-// DIA / HEX / UMH / STAR / FULL integer search + hpel/qpel refinement (luma; chroma SATD of
-// subme > 2 is a "next" row).  The device algorithm lives in me_device.cuh.
+// DIA / HEX / UMH / STAR / SEA / FULL integer search + hpel/qpel refinement (luma, plus the chroma
+// SATD term of subme > 2 in the encode-style form).  The device algorithm lives in me_device.cuh.
 //
 // Also here: the BitCost lambda-scaled MV cost table (source/encoder/bitcost.cpp:31-110), built on
 // the HOST with the reference's own float/double expression order and uploaded once per lambda.
@@ -66,6 +66,8 @@ struct MEArgs
     const void* fencC[2]; int64_t fencStrideC;
     const void* refC0[2]; const void* const* refCPlanes[2]; int64_t refStrideC;
     int csp, hshift, vshift;
+    // --me sea: device array [numRefs][12] of integral-plane pointers addressed like the reference planes (else nullptr)
+    const uint32_t* const* seaPlanes;
 };
 
 constexpr int ME_WARPS = 4;
@@ -106,6 +108,8 @@ me_batch_kernel(MEArgs p)
     s.partSizeScale = (job.h * job.h) >> 4;                      // motion.cpp:125-126 sizeScale
     s.cost = p.cost + 2 * 32768;
     s.mvpx = job.mvpX; s.mvpy = job.mvpY;
+    s.integral = p.seaPlanes ? p.seaPlanes + 12 * (p.refPlanes ? job.refIdx : 0) : nullptr;
+    s.integralOff = job.puX + (int64_t)job.puY * p.refStride;
 
     // setSourcePU: copy the PU into the 64-stride cache (motion.cpp:188-189)
     const pixel* fp = (const pixel*)p.fencPlane + job.puX + (int64_t)job.puY * p.fencStride;
@@ -153,11 +157,12 @@ me_batch_kernel(MEArgs p)
 }
 
 int me_batch_dev(Ctx* ctx, int depth, const void* fencPlane, int64_t fencStride, const void* refPlane, const void* const* refPlanes,
-                 int64_t refStride, const x265b200_me_chroma* chroma, x265b200_me_job* jobs, int64_t n, int maxW, int maxH,
-                 int searchMethod, int subpelRefine, int merange, double lambda, int maxSlices)
+                 int64_t refStride, const x265b200_me_chroma* chroma, const uint32_t* const* seaPlanes, x265b200_me_job* jobs, int64_t n,
+                 int maxW, int maxH, int searchMethod, int subpelRefine, int merange, double lambda, int maxSlices)
 {
     if (n <= 0) return 0;
-    if (searchMethod == ME_SEA) { set_error("me_batch: --me sea needs the SEA integral planes (next row, SURVEY.md 8f-3)"); return -1; }
+    if (searchMethod == ME_SEA && !seaPlanes) { set_error("me_batch: --me sea needs the 12 integral planes of every reference (x265b200_me_batch_sea_dev)"); return -1; }
+    if (searchMethod == ME_SEA && (merange < 0 || merange > 16000)) { set_error("me_batch: merange %d", merange); return -1; }
     if (searchMethod < 0 || searchMethod > ME_REFINE) { set_error("me_batch: searchMethod %d", searchMethod); return -1; }
     if (subpelRefine < 0 || subpelRefine > 7) { set_error("me_batch: subpelRefine %d", subpelRefine); return -1; }
     if (maxW < 8 && maxH < 8) { set_error("me_batch: inter PUs are at least 8x4 / 4x8"); return -1; }
@@ -167,6 +172,7 @@ int me_batch_dev(Ctx* ctx, int depth, const void* fencPlane, int64_t fencStride,
     a.fencPlane = fencPlane; a.fencStride = fencStride; a.refPlanes = refPlanes; a.refPlane0 = refPlane; a.refStride = refStride;
     a.jobs = jobs; a.n = n; a.cost = ctx->dMvCost; a.searchMethod = searchMethod; a.subpelRefine = subpelRefine;
     a.merange = merange; a.maxSlices = maxSlices; a.depth = depth; a.maxW = maxW; a.maxH = maxH;
+    a.seaPlanes = searchMethod == ME_SEA ? seaPlanes : nullptr;
     a.csp = 0; a.hshift = a.vshift = 0; a.fencStrideC = a.refStrideC = 0;
     a.fencC[0] = a.fencC[1] = a.refC0[0] = a.refC0[1] = nullptr; a.refCPlanes[0] = a.refCPlanes[1] = nullptr;
     if (chroma && chroma->csp)
