@@ -6,7 +6,9 @@ HEX search, subme 2, merange 57, 3 references, 2Nx2N PUs 64/32/16/8 of every CTU
   1. sad_pred  : SAD at the predictor for every PU level x reference (grid-mode pixelcmp kernel; the
                  streaming "ME SAD" kernel whose HBM GB/s is the second half of BASELINE's metric)
   2. me_search : MotionEstimate::motionEstimate for every PU x reference (me_batch kernel)
-  3. residual  : fenc - ref0 -> DCT32 -> quant -> dequant -> IDCT32 over every 32x32 TU
+  3. mc        : one 8-tap luma interpolation per PU and level (all 15 fractions)
+  4. residual  : fused residual pipeline (fenc - pred -> DCT -> quant -> dequant -> IDCT -> recon -> SSE) on every 32/16/8/4 TU
+  5. intra     : neighbour filter + all 35 modes on every 8/16/32 block
 `value` = frames/s with inputs resident in HBM; `e2e` = the same through the C ABI with the new frame
 coming from pinned HOST memory and the per-PU {MV,cost} results copied back, every step.
 
@@ -212,19 +214,16 @@ def run_reference(args, rank, world):
                 if len(ja):
                     R.ref_interp_batch(kind, part, ctypes.c_void_p(ref0.ctypes.data + origin), ctypes.c_ssize_t(STRIDE),
                                        ctypes.c_void_p(pred[sz].ctypes.data), ctypes.c_ssize_t(W), ctypes.c_void_p(ja.ctypes.data), ctypes.c_int64(len(ja)), cores)
-        # residual of the sample row against the 16x16-level prediction, every TU size: DCT, quant, dequant, IDCT
+        # residual of the sample row against the 16x16-level prediction, every TU size: the table entries chained as
+        # Quant::transformNxN / invtransformNxN chain them (sub_ps, dct, quant, dequant, idct | DC fill | zero, add_ps, sse_pp)
         y0 = sample_rows[0] * CTU
-        curv = cur.reshape(ROWS, STRIDE)[PAD + y0:PAD + y0 + CTU, PAD:PAD + W].astype(np.int16)
-        resid = curv - pred[16].reshape(-1, W)[y0:y0 + CTU].astype(np.int16)
         for idx, N in TU_SIZES:
             nb = (W // N) * (CTU // N)
-            blocks = np.ascontiguousarray(resid.reshape(CTU // N, N, W // N, N).transpose(0, 2, 1, 3)).reshape(-1)
-            coef = np.empty_like(blocks); q = np.empty_like(blocks); dq = np.empty_like(blocks); rec = np.empty_like(blocks)
             qbits, add = quant_params(N)
-            R.ref_dct_batch(idx, ctypes.c_void_p(blocks.ctypes.data), ctypes.c_int64(N * N), ctypes.c_ssize_t(N), ctypes.c_void_p(coef.ctypes.data), ctypes.c_int64(nb), cores)
-            R.ref_quant_dequant_batch(ctypes.c_void_p(coef.ctypes.data), ctypes.c_void_p(qtab.ctypes.data), ctypes.c_void_p(q.ctypes.data), ctypes.c_void_p(dq.ctypes.data),
-                                      ctypes.c_void_p(deltaU.ctypes.data), qbits, add, N * N, ctypes.c_int64(nb), 40 << 5, 9, cores)
-            R.ref_idct_batch(idx, ctypes.c_void_p(dq.ctypes.data), ctypes.c_void_p(rec.ctypes.data), ctypes.c_int64(N * N), ctypes.c_ssize_t(N), ctypes.c_int64(nb), cores)
+            R.ref_tu_pipeline(idx, 0, ctypes.c_void_p(cur.ctypes.data + origin + y0 * STRIDE), ctypes.c_ssize_t(STRIDE),
+                              ctypes.c_void_p(pred[16].ctypes.data + y0 * W), ctypes.c_ssize_t(W), ctypes.c_void_p(recon.ctypes.data), ctypes.c_ssize_t(W),
+                              W // N, CTU // N, ctypes.c_void_p(qtab.ctypes.data), qbits, add, None, 40 << 5, 9,
+                              ctypes.c_void_p(tu_coef.ctypes.data), ctypes.c_void_p(tu_ns.ctypes.data), ctypes.c_void_p(tu_sse.ctypes.data), cores)
         # intra: filter + all 35 modes on every 8/16/32 block of the sample row
         for idx, N, _ in INTRA_SIZES:
             nb = len(nbr[N])
@@ -233,7 +232,8 @@ def run_reference(args, rank, world):
     ip_jobs = {sz: interp_jobs(pkg, sz, sample_rows) for sz in LEVELS}
     pred = {sz: np.zeros(CTU_ROWS * CTU * W, dtype=np.uint8) for sz in LEVELS}
     qtab = np.full(1024, 26214, dtype=np.int32)
-    deltaU = np.zeros(cores * 1024, dtype=np.int32)
+    recon = np.zeros(CTU * W, dtype=np.uint8); tu_coef = np.zeros(CTU * W, dtype=np.int16)
+    tu_ns = np.zeros((W // 4) * (CTU // 4), dtype=np.uint32); tu_sse = np.zeros((W // 4) * (CTU // 4), dtype=np.uint64)
     nbr = {N: neighbour_arrays(cur, N, sample_rows) for _, N, _ in INTRA_SIZES}
     filt = {N: np.empty_like(nbr[N]) for N in nbr}
     intra_out = {N: np.empty(len(nbr[N]) * 35 * N * N, dtype=np.uint8) for N in nbr}
@@ -301,13 +301,11 @@ def main():
     level_n = {s: (W // s) * ((CTU_ROWS * CTU) // s) for s in LEVELS}
     sad_out = {s: torch.empty(NREF * level_n[s], dtype=torch.int32, device=dev) for s in LEVELS}
     n32 = (W // 32) * (CTU_ROWS * 2)
-    resid = torch.empty((CTU_ROWS * CTU, W), dtype=torch.int16, device=dev)
-    coef = torch.empty(n32 * 1024, dtype=torch.int16, device=dev)
-    qcoef = torch.empty_like(coef); deq = torch.empty_like(coef)
+    qcoef = torch.empty(n32 * 1024, dtype=torch.int16, device=dev)
     recon = torch.empty((CTU_ROWS * CTU, W), dtype=torch.uint8, device=dev)
     qtab = torch.full((1024,), 26214, dtype=torch.int32, device=dev)          # quantScales[qp%6=0] flat list
     numsig = torch.empty((W // 4) * (CTU_ROWS * CTU // 4), dtype=torch.int32, device=dev)
-    resid2 = torch.empty((CTU_ROWS * CTU, W), dtype=torch.int16, device=dev)
+    tu_sse = torch.empty((W // 4) * (CTU_ROWS * CTU // 4), dtype=torch.int64, device=dev)
     # MC jobs (static), prediction planes, intra neighbour arrays (taken once from frame 0: static inputs) and outputs
     ip_jobs_h = {sz: interp_jobs(pkg, sz) for sz in LEVELS}
     ip_jobs_d = {sz: {k: torch.from_numpy(a.view(np.uint8).copy()).to(dev) for k, a in ip_jobs_h[sz].items() if len(a)} for sz in LEVELS}
@@ -358,16 +356,12 @@ def main():
         for sz in LEVELS:
             for kind, jd in ip_jobs_d[sz].items():
                 ctx.interp_dev(kind, 8, 8, sz, sz, r0, STRIDE, P(pred[sz]), W, P(jd), len(ip_jobs_h[sz][kind]), 0)
-        # 4. residual against the 16x16-level prediction -> DCT -> quant -> dequant -> IDCT on every TU size -> recon
-        ctx.sub_ps_plane_dev(8, cptr, STRIDE, P(pred[16]), W, P(resid), W, W, HH)
+        # 4. residual against the 16x16-level prediction -> DCT -> quant -> dequant -> IDCT -> recon -> SSE on every TU size:
+        #    the fused residual pipeline (Quant::transformNxN + invtransformNxN chain, one launch per TU size)
         for idx, N in TU_SIZES:
-            nb = (W // N) * (HH // N)
             qbits, add = quant_params(N)
-            ctx.dct_plane_dev(idx, 8, P(resid), W, W // N, HH // N, P(coef))
-            ctx.quant_dev(P(coef), P(qtab), None, P(qcoef), qbits, add, N * N, nb, P(numsig))
-            ctx.dequant_normal_dev(P(qcoef), P(deq), N * N, nb, 40 << 5, 9)
-            ctx.idct_plane_dev(idx, 8, P(deq), P(resid2), W, W // N, HH // N)
-        ctx.add_ps_plane_dev(8, P(recon), W, P(pred[16]), W, P(resid2), W, W, HH)
+            ctx.tu_pipeline_dev(idx, 8, 0, cptr, STRIDE, P(pred[16]), W, P(recon), W, W // N, HH // N, P(qtab), qbits, add, None, 40 << 5, 9,
+                                P(qcoef), P(numsig), P(tu_sse))
         # 5. intra: neighbour filter + 33 angular modes + planar + DC on every 8/16/32 block
         for _, N, log2N in INTRA_SIZES:
             nb = nbr_d[N].shape[0]

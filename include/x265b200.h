@@ -123,6 +123,20 @@ int x265b200_dequant_scaling_dev(x265b200_ctx* ctx, const int16_t* quantCoef, co
                                  int16_t* coef, int num, int64_t n, int mcqp_miper, int shift);
 /* cu[].count_nonzero (primitives.h:163; dct.cpp:714-726): out int32[n] */
 int x265b200_count_nonzero_dev(x265b200_ctx* ctx, const int16_t* quantCoeff, int numCoeff, int64_t n, int32_t* out);
+/* Fused residual pipeline: what Search::residualTransformQuantInter / codeIntraLumaQT do per TU through
+ * Quant::transformNxN (common/quant.cpp:397-480) and Quant::invtransformNxN (quant.cpp:543-605) with rdoqLevel 0, no sign
+ * hiding, no noise reduction, no transform skip / bypass -- for the blocksX x blocksY grid of N x N TUs of a plane, one launch:
+ *   resi = fenc - pred (cu[].sub_ps) -> cu[].dct (dst4x4 when useDST: 4x4 luma intra) -> primitives.quant(qBits, add,
+ *   quantCoeff[N*N]) -> levels coeff[tu][N*N] + numSig[tu] -> dequant_normal(scale = scaleOrPer, dqShift) or, when
+ *   dequantCoef != NULL, dequant_scaling(dequantCoef[N*N], per = scaleOrPer, dqShift) -> residual' = 0 when numSig == 0
+ *   (search.cpp: blockfill_s 0), the DC-only fill of quant.cpp:585-595 when numSig == 1 && level[0] != 0 && !useDST, else
+ *   cu[].idct / idst4x4 -> recon = clip(pred + residual') (cu[].add_ps) -> sse[tu] = cu[].sse_pp(fenc, recon).
+ * TU (bx, by) covers pixels (bx*N, by*N) of all three planes and is entry by*blocksX + bx of coeff / numSig / sse.
+ * sizeIdx 0..3 = 4/8/16/32.  8/16/32 run both transforms on the integer tensor cores inside the same kernel. */
+int x265b200_tu_pipeline_dev(x265b200_ctx* ctx, int sizeIdx, int depth, int useDST, const void* fenc, int64_t fencStride,
+                             const void* pred, int64_t predStride, void* recon, int64_t reconStride, int blocksX, int blocksY,
+                             const int32_t* quantCoeff, int qBits, int add, const int32_t* dequantCoef, int scaleOrPer, int dqShift,
+                             int16_t* coeff, uint32_t* numSig, uint64_t* sse);
 /* The N x N HEVC core-transform matrix the kernels use (host side, no GPU needed); N = 4,8,16,32. */
 int x265b200_dct_table(int N, int16_t* out);
 

@@ -677,3 +677,46 @@ void ref_integral_initv(int h, uint32_t* sum, intptr_t stride)
     primitives.integral_initv[k](sum, stride);
 }
 } /* extern "C" */
+
+/* ---- the residual pipeline of one TU exactly as the encoder chains the table entries: Search (sub_ps) ->
+ * Quant::transformNxN (quant.cpp:397-480, rdoq 0 / no sign hiding) -> Quant::invtransformNxN (quant.cpp:543-605) ->
+ * add_ps -> sse_pp, over the blocksX x blocksY TU grid of a plane.  dequantCoef == NULL selects dequant_normal. */
+extern "C" void ref_tu_pipeline(int sizeIdx, int useDST, const void* fencV, intptr_t fencStride, const void* predV, intptr_t predStride,
+                                void* reconV, intptr_t reconStride, int blocksX, int blocksY, const int32_t* quantCoeff, int qBits, int add,
+                                const int32_t* dequantCoef, int scaleOrPer, int dqShift, int16_t* coeff, uint32_t* numSigOut, uint64_t* sseOut,
+                                int threads)
+{
+    ensure_init();
+    const int N = 4 << sizeIdx, numCoeff = N * N;
+    parallel_for((int64_t)blocksX * blocksY, threads, [&](int64_t b, int) {
+        ALIGN_VAR_32(int16_t, resi[32 * 32]);
+        ALIGN_VAR_32(int16_t, dctc[32 * 32]);
+        ALIGN_VAR_32(int32_t, deltaU[32 * 32]);
+        const int by = (int)(b / blocksX), bx = (int)(b % blocksX);
+        const pixel* fenc = (const pixel*)fencV + (intptr_t)by * N * fencStride + bx * N;
+        const pixel* pred = (const pixel*)predV + (intptr_t)by * N * predStride + bx * N;
+        pixel* recon = (pixel*)reconV + (intptr_t)by * N * reconStride + bx * N;
+        int16_t* qc = coeff + b * numCoeff;
+        primitives.cu[sizeIdx].sub_ps(resi, N, fenc, pred, fencStride, predStride);
+        if (useDST) primitives.dst4x4(resi, dctc, N); else primitives.cu[sizeIdx].dct(resi, dctc, N);
+        uint32_t numSig = primitives.quant(dctc, quantCoeff, deltaU, qc, qBits, add, numCoeff);
+        if (numSig)
+        {
+            if (dequantCoef) primitives.dequant_scaling(qc, dequantCoef, dctc, numCoeff, scaleOrPer, dqShift);
+            else primitives.dequant_normal(qc, dctc, numCoeff, scaleOrPer, dqShift);
+            if (numSig == 1 && qc[0] != 0 && !useDST)
+            {
+                const int shift_1st = 7 - 6, add_1st = 1 << (shift_1st - 1);
+                const int shift_2nd = 12 - (X265_DEPTH - 8) - 3, add_2nd = 1 << (shift_2nd - 1);
+                int dc_val = (((dctc[0] * (64 >> 6) + add_1st) >> shift_1st) * (64 >> 3) + add_2nd) >> shift_2nd;
+                primitives.cu[sizeIdx].blockfill_s[0](resi, N, (int16_t)dc_val);
+            }
+            else if (useDST) primitives.idst4x4(dctc, resi, N);
+            else primitives.cu[sizeIdx].idct(dctc, resi, N);
+        }
+        else primitives.cu[sizeIdx].blockfill_s[0](resi, N, 0);
+        primitives.cu[sizeIdx].add_ps[0](recon, reconStride, pred, resi, predStride, N);
+        numSigOut[b] = numSig;
+        sseOut[b] = (uint64_t)primitives.cu[sizeIdx].sse_pp(fenc, fencStride, recon, reconStride);
+    });
+}

@@ -430,3 +430,13 @@ Ctx.integral_inith_dev = _ctx_integral_inith_dev
 Ctx.integral_initv_dev = _ctx_integral_initv_dev
 Ctx.ads_dev = _ctx_ads_dev
 Ctx.me_batch_sea_dev = _ctx_me_batch_sea_dev
+
+
+def _ctx_tu_pipeline_dev(self, sizeIdx, depth, useDST, dFenc, fencStride, dPred, predStride, dRecon, reconStride, blocksX, blocksY,
+                         dQuantCoeff, qBits, add, dDequantCoef, scaleOrPer, dqShift, dCoeff, dNumSig, dSse):
+    self._chk(self.L.x265b200_tu_pipeline_dev(self.h, int(sizeIdx), int(depth), int(useDST), _vp(dFenc), _i64(fencStride), _vp(dPred), _i64(predStride),
+                                              _vp(dRecon), _i64(reconStride), int(blocksX), int(blocksY), _vp(dQuantCoeff), int(qBits), int(add),
+                                              _vp(dDequantCoef), int(scaleOrPer), int(dqShift), _vp(dCoeff), _vp(dNumSig), _vp(dSse)))
+
+
+Ctx.tu_pipeline_dev = _ctx_tu_pipeline_dev

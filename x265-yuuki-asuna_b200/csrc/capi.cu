@@ -77,6 +77,9 @@ int quant_dev(Ctx*, int isN, const int16_t* coef, const int32_t* quantCoeff, int
               int qBits, int add, int numCoeff, int64_t n, uint32_t* numSig);
 int dequant_dev(Ctx*, int scaling, const int16_t* q, const int32_t* deqCoef, int16_t* coef, int num, int64_t n, int scaleOrPer, int shift);
 int count_nonzero_dev(Ctx*, const int16_t* q, int numCoeff, int64_t n, int32_t* out);
+int tu_pipeline_dev(Ctx*, int sizeIdx, int depth, int useDST, const void* fenc, int64_t fencStride, const void* pred, int64_t predStride,
+                    void* recon, int64_t reconStride, int blocksX, int blocksY, const int32_t* quantCoeff, int qBits, int add,
+                    const int32_t* dequantCoef, int scaleOrPer, int dqShift, int16_t* coeff, uint32_t* numSig, uint64_t* sse);
 void host_dct_table(int N, int16_t* out);
 int interp_dev(Ctx*, int kind, int taps, int depth, int w, int h, const void* src, int64_t srcStride,
                void* dst, int64_t dstStride, const x265b200_interp_job* jobs, int64_t n, int isRowExt);
@@ -319,6 +322,15 @@ int x265b200_count_nonzero_dev(x265b200_ctx* ctx, const int16_t* q, int numCoeff
 {
     REQUIRE_CTX(ctx);
     return count_nonzero_dev(CTX(ctx), q, numCoeff, n, out);
+}
+int x265b200_tu_pipeline_dev(x265b200_ctx* ctx, int sizeIdx, int depth, int useDST, const void* fenc, int64_t fencStride,
+                             const void* pred, int64_t predStride, void* recon, int64_t reconStride, int blocksX, int blocksY,
+                             const int32_t* quantCoeff, int qBits, int add, const int32_t* dequantCoef, int scaleOrPer, int dqShift,
+                             int16_t* coeff, uint32_t* numSig, uint64_t* sse)
+{
+    REQUIRE_CTX(ctx);
+    return tu_pipeline_dev(CTX(ctx), sizeIdx, depth, useDST, fenc, fencStride, pred, predStride, recon, reconStride, blocksX, blocksY,
+                           quantCoeff, qBits, add, dequantCoef, scaleOrPer, dqShift, coeff, numSig, sse);
 }
 int x265b200_dct_table(int N, int16_t* out)
 {

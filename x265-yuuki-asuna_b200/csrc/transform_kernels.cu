@@ -587,6 +587,323 @@ int count_nonzero_dev(Ctx* ctx, const int16_t* q, int numCoeff, int64_t n, int32
     return check(cudaGetLastError(), "count_nonzero kernel launch");
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused residual pipeline: per TU, in one kernel and with nothing but pixels in / pixels + levels out,
+//   residual = fenc - pred                      cu[].sub_ps           (pixel.cpp:814)
+//   coef     = DCT(residual)  (DST for 4x4 luma intra)               Quant::transformNxN (quant.cpp:397-480, rdoq 0,
+//   level    = quant(coef), numSig              primitives.quant      no sign hiding / noise reduction / transform skip)
+//   coef'    = dequant_normal | dequant_scaling(level)                Quant::invtransformNxN (quant.cpp:543-605) incl. its
+//   resi'    = 0 | DC fill | IDCT(coef')                              numSig == 0 (search.cpp blockfill_s 0) and DC-only shortcuts
+//   recon    = clip(pred + resi')               cu[].add_ps           (pixel.cpp:828)
+//   sse      = sum (fenc - recon)^2             cu[].sse_pp           (pixel.cpp:167)
+// N = 8/16/32: one warp per TU (two 8x8 TUs per warp), both transforms on the integer tensor cores exactly as
+// xform_mma_kernel, quant + dequant between them on the smem tile (written back transposed for the inverse).
+// Algorithmic bytes per TU: N*N*(3*sizeof(pixel) + 2) + 12.
+// ---------------------------------------------------------------------------------------------
+struct TuArgs
+{
+    const void* fenc; int64_t fencStride; const void* pred; int64_t predStride; void* recon; int64_t reconStride;
+    int blocksX; int64_t n;
+    const int32_t* quantCoeff; int qBits, add;
+    const int32_t* dequantCoef; int scaleOrPer, dqShift;
+    int16_t* coeff; uint32_t* numSig; uint64_t* sse;
+    int depth, useDST, wordStores;
+};
+
+__device__ __forceinline__ int tu_quant(int c, int q, int add, int qBits, int& cnt)
+{
+    const int sign = c < 0 ? -1 : 1;
+    const int tmplevel = (int)((uint32_t)abs(c) * (uint32_t)q);
+    int level = (tmplevel + add) >> qBits;
+    if (level) cnt++;
+    level *= sign;
+    return clip3i(-32768, 32767, level);
+}
+__device__ __forceinline__ int tu_dequant(const TuArgs& p, int v, int idx)
+{
+    if (!p.dequantCoef)
+        return clip3i(-32768, 32767, (v * p.scaleOrPer + (1 << (p.dqShift - 1))) >> p.dqShift);              // dct.cpp:631-632
+    const int per = p.scaleOrPer, sh = p.dqShift + 4, d = __ldg(p.dequantCoef + idx);
+    if (sh > per) return clip3i(-32768, 32767, (v * d + (1 << (sh - per - 1))) >> (sh - per));                 // :646-652
+    const int c = clip3i(-32768, 32767, v * d);
+    return clip3i(-32768, 32767, (int)((uint32_t)c << (per - sh)));                                           // :656-660
+}
+// DC-only inverse (quant.cpp:585-595)
+__device__ __forceinline__ int tu_dc_val(int deq0, int depth)
+{
+    const int shift_2nd = 12 - (depth - 8) - 3, add_2nd = 1 << (shift_2nd - 1);
+    return (int)(int16_t)(((((deq0 * (64 >> 6) + 1) >> 1) * (64 >> 3)) + add_2nd) >> shift_2nd);
+}
+template<typename pixel> __device__ __forceinline__ uint32_t tu_ldw(const pixel* p);
+template<> __device__ __forceinline__ uint32_t tu_ldw<uint8_t>(const uint8_t* p) { return ld_px4(p); }
+template<> __device__ __forceinline__ uint32_t tu_ldw<uint16_t>(const uint16_t* p) { return ld_px2(p); }
+
+template<typename pixel, int N>
+__global__ void __launch_bounds__(XF_WARPS * 32)
+tu_pipeline_kernel(TuArgs p)
+{
+    constexpr int LD = Tile<N>::LD;
+    constexpr int PER = (N == 8) ? 2 : 1;
+    constexpr int TILE = PER * N * LD;
+    constexpr int PW = 4 / (int)sizeof(pixel);                  // pixels per 32-bit word
+    constexpr int WPT = N * N / PW;                             // words per TU
+    constexpr int WPU = PER * WPT;
+    constexpr int CNT = (WPU + 31) / 32;
+    constexpr int PAIRS = PER * N * N / 2;
+    __shared__ __align__(16) int16_t smem[XF_WARPS][2][TILE];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
+    int16_t* bufA = smem[warp][0];
+    int16_t* bufB = smem[warp][1];
+    const int maxVal = (1 << p.depth) - 1;
+    const int log2N = N == 32 ? 5 : (N == 16 ? 4 : 3);
+
+    uint32_t af32[2][4], ai32[2][4]; uint32_t af16[2], ai16[2];
+    {
+        const int sz = N == 32 ? 0 : (N == 16 ? 1 : 2);
+        const uint32_t* ff = g_xfFrag[0][sz][lane];
+        const uint32_t* fi = g_xfFrag[1][sz][lane];
+        if (N == 32)
+        {
+#pragma unroll
+            for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+                for (int r = 0; r < 4; r++) { af32[mi][r] = ff[mi * 4 + r]; ai32[mi][r] = fi[mi * 4 + r]; }
+        }
+        else { af16[0] = ff[0]; af16[1] = ff[1]; ai16[0] = fi[0]; ai16[1] = fi[1]; }
+    }
+    const int fs1 = log2N - 1 + (p.depth - 8), fs2 = log2N + 6;              // dct.cpp:478-479 etc.
+    const int is1 = 7, is2 = 12 - (p.depth - 8);                             // dct.cpp:529-530
+    const pixel* fenc = (const pixel*)p.fenc; const pixel* pred = (const pixel*)p.pred; pixel* recon = (pixel*)p.recon;
+
+    const int64_t units = (p.n + PER - 1) / PER;
+    for (int64_t u = (int64_t)blockIdx.x * XF_WARPS + warp; u < units; u += (int64_t)gridDim.x * XF_WARPS)
+    {
+        // ---- residual = fenc - pred into the forward tile In[j][n] ----
+        uint32_t fw[CNT], pw[CNT];
+#pragma unroll
+        for (int i = 0; i < CNT; i++)
+        {
+            const int e = lane + 32 * i;
+            fw[i] = pw[i] = 0;
+            if (e < WPU)
+            {
+                const int s = e / WPT, ee = e - s * WPT, row = (ee * PW) >> log2N, col = (ee * PW) & (N - 1);
+                const int64_t b = u * PER + s;
+                int16_t* t = bufA + s * N * LD + row * LD + col;
+                if (b < p.n)
+                {
+                    const int64_t by = b / p.blocksX, bx = b - by * p.blocksX;
+                    fw[i] = tu_ldw<pixel>(fenc + (by * N + row) * p.fencStride + bx * N + col);
+                    pw[i] = tu_ldw<pixel>(pred + (by * N + row) * p.predStride + bx * N + col);
+                }
+                if (sizeof(pixel) == 1)
+                {
+                    const int d0 = (int)(fw[i] & 0xff) - (int)(pw[i] & 0xff), d1 = (int)((fw[i] >> 8) & 0xff) - (int)((pw[i] >> 8) & 0xff);
+                    const int d2 = (int)((fw[i] >> 16) & 0xff) - (int)((pw[i] >> 16) & 0xff), d3 = (int)(fw[i] >> 24) - (int)(pw[i] >> 24);
+                    *(uint2*)t = make_uint2((uint32_t)(d0 & 0xffff) | ((uint32_t)d1 << 16), (uint32_t)(d2 & 0xffff) | ((uint32_t)d3 << 16));
+                }
+                else
+                {
+                    const int d0 = (int)(fw[i] & 0xffff) - (int)(pw[i] & 0xffff), d1 = (int)(fw[i] >> 16) - (int)(pw[i] >> 16);
+                    *(uint32_t*)t = (uint32_t)(d0 & 0xffff) | ((uint32_t)d1 << 16);
+                }
+            }
+        }
+        __syncwarp();
+        if (N == 32)      { pass32<false>(af32, bufA, bufB, 1 << (fs1 - 1), fs1, gid, tig); __syncwarp(); pass32<false>(af32, bufB, bufA, 1 << (fs2 - 1), fs2, gid, tig); }
+        else if (N == 16) { pass16<false>(af16, bufA, bufB, 1 << (fs1 - 1), fs1, gid, tig); __syncwarp(); pass16<false>(af16, bufB, bufA, 1 << (fs2 - 1), fs2, gid, tig); }
+        else              { pass8<false>(af16, bufA, bufB, 1 << (fs1 - 1), fs1, gid, tig);  __syncwarp(); pass8<false>(af16, bufB, bufA, 1 << (fs2 - 1), fs2, gid, tig); }
+        __syncwarp();
+
+        // ---- quant (levels out) + dequant into the inverse tile In'[j][n] = coef'[n][j] ----
+        int cnt[PER], dcq[PER], dcd[PER];
+#pragma unroll
+        for (int s = 0; s < PER; s++) { cnt[s] = 0; dcq[s] = 0; dcd[s] = 0; }
+#pragma unroll 4
+        for (int e2 = lane; e2 < PAIRS; e2 += 32)
+        {
+            const int s = e2 / (N * N / 2), idx = (e2 - s * (N * N / 2)) * 2, k = idx >> log2N, j = idx & (N - 1);
+            const int64_t b = u * PER + s;
+            if (b >= p.n) continue;
+            const uint32_t cw = *(const uint32_t*)(bufA + s * N * LD + k * LD + j);
+            int c0 = 0, c1 = 0;
+            const int l0 = tu_quant((int)(int16_t)(cw & 0xffff), __ldg(p.quantCoeff + idx), p.add, p.qBits, c0);
+            const int l1 = tu_quant((int)(int16_t)(cw >> 16), __ldg(p.quantCoeff + idx + 1), p.add, p.qBits, c1);
+            *(uint32_t*)(p.coeff + b * (N * N) + idx) = (uint32_t)(l0 & 0xffff) | ((uint32_t)l1 << 16);
+            const int d0 = tu_dequant(p, l0, idx), d1 = tu_dequant(p, l1, idx + 1);
+            bufB[s * N * LD + j * LD + k] = (int16_t)d0;
+            bufB[s * N * LD + (j + 1) * LD + k] = (int16_t)d1;
+#pragma unroll
+            for (int ss = 0; ss < PER; ss++)
+                if (ss == s) { cnt[ss] += c0 + c1; if (idx == 0) { dcq[ss] = l0; dcd[ss] = d0; } }
+        }
+        int mode[PER], dcv[PER];           // 0: zero residual, 1: DC fill, 2: full inverse
+        bool anyInv = false;
+#pragma unroll
+        for (int s = 0; s < PER; s++)
+        {
+            cnt[s] = warp_sum(cnt[s]);
+            // lane 0 handled idx 0 of TU 0 (and of TU 1 when N == 8: pair N*N/2 = 32 -> lane 0 again)
+            dcq[s] = __shfl_sync(0xffffffffu, dcq[s], 0); dcd[s] = __shfl_sync(0xffffffffu, dcd[s], 0);
+            mode[s] = cnt[s] == 0 ? 0 : ((cnt[s] == 1 && dcq[s] != 0) ? 1 : 2);
+            dcv[s] = tu_dc_val(dcd[s], p.depth);
+            anyInv = anyInv || mode[s] == 2;
+        }
+        __syncwarp();
+        if (anyInv)
+        {
+            if (N == 32)      { pass32<true>(ai32, bufB, bufA, 1 << (is1 - 1), is1, gid, tig); __syncwarp(); pass32<true>(ai32, bufA, bufB, 1 << (is2 - 1), is2, gid, tig); }
+            else if (N == 16) { pass16<true>(ai16, bufB, bufA, 1 << (is1 - 1), is1, gid, tig); __syncwarp(); pass16<true>(ai16, bufA, bufB, 1 << (is2 - 1), is2, gid, tig); }
+            else              { pass8<true>(ai16, bufB, bufA, 1 << (is1 - 1), is1, gid, tig);  __syncwarp(); pass8<true>(ai16, bufA, bufB, 1 << (is2 - 1), is2, gid, tig); }
+            __syncwarp();
+        }
+
+        // ---- recon = clip(pred + resi'), sse vs fenc; bufB[k][j] = resi'[row j][col k] ----
+        unsigned long long sse[PER];
+#pragma unroll
+        for (int s = 0; s < PER; s++) sse[s] = 0;
+#pragma unroll
+        for (int i = 0; i < CNT; i++)
+        {
+            const int e = lane + 32 * i;
+            if (e >= WPU) continue;
+            const int s = e / WPT, ee = e - s * WPT, row = (ee * PW) >> log2N, col = (ee * PW) & (N - 1);
+            const int64_t b = u * PER + s;
+            if (b >= p.n) continue;
+            int md = mode[0], dv = dcv[0];
+#pragma unroll
+            for (int ss = 1; ss < PER; ss++) if (ss == s) { md = mode[ss]; dv = dcv[ss]; }
+            uint32_t out = 0; unsigned acc = 0;
+#pragma unroll
+            for (int c = 0; c < PW; c++)
+            {
+                const int sh = c * (32 / PW), msk = sizeof(pixel) == 1 ? 0xff : 0xffff;
+                const int pv = (int)((pw[i] >> sh) & msk), fv = (int)((fw[i] >> sh) & msk);
+                const int r = md == 0 ? 0 : (md == 1 ? dv : (int)bufB[s * N * LD + (col + c) * LD + row]);
+                const int rec = clip3i(0, maxVal, pv + r);
+                out |= (uint32_t)rec << sh;
+                acc += (unsigned)((fv - rec) * (fv - rec));
+            }
+            const int64_t by = b / p.blocksX, bx = b - by * p.blocksX;
+            pixel* rp = recon + (by * N + row) * p.reconStride + bx * N + col;
+            if (p.wordStores) *(uint32_t*)rp = out;
+            else
+            {
+#pragma unroll
+                for (int c = 0; c < PW; c++) rp[c] = (pixel)((out >> (c * (32 / PW))) & (sizeof(pixel) == 1 ? 0xff : 0xffff));
+            }
+#pragma unroll
+            for (int ss = 0; ss < PER; ss++) if (ss == s) sse[ss] += acc;
+        }
+#pragma unroll
+        for (int s = 0; s < PER; s++)
+        {
+            unsigned lo = (unsigned)sse[s], hi = (unsigned)(sse[s] >> 32);
+            // per-lane sums stay below 2^32 (<= 32 px * 4095^2); add across lanes in 64 bits
+            unsigned long long tot = sse[s];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+            {
+                const unsigned l2 = __shfl_xor_sync(0xffffffffu, (unsigned)tot, o), h2 = __shfl_xor_sync(0xffffffffu, (unsigned)(tot >> 32), o);
+                tot += ((unsigned long long)h2 << 32) | l2;
+            }
+            (void)lo; (void)hi;
+            const int64_t b = u * PER + s;
+            if (lane == 0 && b < p.n) { p.numSig[b] = (uint32_t)cnt[s]; p.sse[b] = tot; }
+        }
+        __syncwarp();
+    }
+}
+
+// 4x4 TUs: one thread per TU, scalar butterflies (DCT or DST)
+template<typename pixel>
+__global__ void __launch_bounds__(128)
+tu4_pipeline_kernel(TuArgs p)
+{
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.n) return;
+    const int64_t by = b / p.blocksX, bx = b - by * p.blocksX;
+    const pixel* fenc = (const pixel*)p.fenc + by * 4 * p.fencStride + bx * 4;
+    const pixel* pred = (const pixel*)p.pred + by * 4 * p.predStride + bx * 4;
+    pixel* recon = (pixel*)p.recon + by * 4 * p.reconStride + bx * 4;
+    const int maxVal = (1 << p.depth) - 1;
+    int f[16], q[16], in[16], tmp[16], out[16];
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+    {
+        int a[4], c[4];
+        ld4i<pixel>(fenc + r * p.fencStride, a); ld4i<pixel>(pred + r * p.predStride, c);
+#pragma unroll
+        for (int x = 0; x < 4; x++) { f[4 * r + x] = a[x]; q[4 * r + x] = c[x]; in[4 * r + x] = a[x] - c[x]; }
+    }
+    const bool dst = p.useDST != 0;
+    fwd4_pass(in, tmp, 1 + (p.depth - 8), dst); fwd4_pass(tmp, out, 8, dst);          // dct.cpp:444-445 / :461-462
+    int cnt = 0, lv0 = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++)
+    {
+        const int l = tu_quant((int)(int16_t)out[i], __ldg(p.quantCoeff + i), p.add, p.qBits, cnt);
+        p.coeff[b * 16 + i] = (int16_t)l;
+        if (i == 0) lv0 = l;
+        in[i] = tu_dequant(p, l, i);
+    }
+    const int mode = cnt == 0 ? 0 : ((cnt == 1 && lv0 != 0 && !dst) ? 1 : 2);
+    if (mode == 2) { inv4_pass(in, tmp, 7, dst); inv4_pass(tmp, out, 12 - (p.depth - 8), dst); }
+    const int dcv = tu_dc_val(in[0], p.depth);
+    unsigned long long sse = 0;
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int x = 0; x < 4; x++)
+        {
+            const int rs = mode == 0 ? 0 : (mode == 1 ? dcv : out[4 * r + x]);
+            const int rec = clip3i(0, maxVal, q[4 * r + x] + rs);
+            recon[r * p.reconStride + x] = (pixel)rec;
+            sse += (unsigned)((f[4 * r + x] - rec) * (f[4 * r + x] - rec));
+        }
+    p.numSig[b] = (uint32_t)cnt; p.sse[b] = sse;
+}
+
+int tu_pipeline_dev(Ctx* ctx, int sizeIdx, int depth, int useDST, const void* fenc, int64_t fencStride, const void* pred, int64_t predStride,
+                    void* recon, int64_t reconStride, int blocksX, int blocksY, const int32_t* quantCoeff, int qBits, int add,
+                    const int32_t* dequantCoef, int scaleOrPer, int dqShift, int16_t* coeff, uint32_t* numSig, uint64_t* sse)
+{
+    if (sizeIdx < 0 || sizeIdx > 3) { set_error("tu_pipeline: sizeIdx %d (0..3 = 4/8/16/32)", sizeIdx); return -1; }
+    if (useDST && sizeIdx != 0) { set_error("tu_pipeline: DST is the 4x4 luma intra transform only"); return -1; }
+    if (blocksX <= 0 || blocksY <= 0) return 0;
+    if (!fenc || !pred || !recon || !quantCoeff || !coeff || !numSig || !sse) { set_error("tu_pipeline: NULL operand"); return -1; }
+    if (qBits < 8 || qBits > 30 || (!dequantCoef && (dqShift < 1 || dqShift > 10))) { set_error("tu_pipeline: qBits %d / shift %d", qBits, dqShift); return -1; }
+    if ((uintptr_t)coeff & 3) { set_error("tu_pipeline: coeff must be 4-byte aligned"); return -1; }
+    if (upload_tables(ctx)) return -1;
+    TuArgs a;
+    a.fenc = fenc; a.fencStride = fencStride; a.pred = pred; a.predStride = predStride; a.recon = recon; a.reconStride = reconStride;
+    a.blocksX = blocksX; a.n = (int64_t)blocksX * blocksY; a.quantCoeff = quantCoeff; a.qBits = qBits; a.add = add;
+    a.dequantCoef = dequantCoef; a.scaleOrPer = scaleOrPer; a.dqShift = dqShift; a.coeff = coeff; a.numSig = numSig; a.sse = sse;
+    a.depth = depth; a.useDST = useDST;
+    const size_t px = depth > 8 ? 2 : 1;
+    a.wordStores = !(((uintptr_t)recon | (uintptr_t)(reconStride * (int64_t)px)) & 3);
+    const int N = 4 << sizeIdx;
+    if (N == 4)
+    {
+        const unsigned blocks = (unsigned)((a.n + 127) / 128);
+        if (depth > 8) tu4_pipeline_kernel<uint16_t><<<blocks, 128, 0, ctx->stream>>>(a);
+        else           tu4_pipeline_kernel<uint8_t><<<blocks, 128, 0, ctx->stream>>>(a);
+    }
+    else
+    {
+        const int64_t units = N == 8 ? (a.n + 1) / 2 : a.n;
+        const int64_t want = (units + XF_WARPS - 1) / XF_WARPS, cap = (int64_t)ctx->smCount * 4;
+        const unsigned blocks = (unsigned)(want < cap ? want : cap);
+        dim3 block(XF_WARPS * 32);
+#define TU_LAUNCH(PX, NN) tu_pipeline_kernel<PX, NN><<<blocks, block, 0, ctx->stream>>>(a)
+        if (depth > 8) { if (N == 32) TU_LAUNCH(uint16_t, 32); else if (N == 16) TU_LAUNCH(uint16_t, 16); else TU_LAUNCH(uint16_t, 8); }
+        else           { if (N == 32) TU_LAUNCH(uint8_t, 32);  else if (N == 16) TU_LAUNCH(uint8_t, 16);  else TU_LAUNCH(uint8_t, 8); }
+#undef TU_LAUNCH
+    }
+    ctx->launches++;
+    return check(cudaGetLastError(), "tu_pipeline kernel launch");
+}
+
 void host_dct_table(int N, int16_t* out)
 {
     for (int k = 0; k < N; k++)
