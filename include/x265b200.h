@@ -190,6 +190,27 @@ int x265b200_interp_dev(x265b200_ctx* ctx, int kind, int taps, int depth, int w,
                         const void* src, int64_t srcStride, void* dst, int64_t dstStride,
                         const x265b200_interp_job* jobs, int64_t n, int isRowExt);
 
+/* ---- motion compensation driver: Predict::motionCompensation (common/predict.cpp:77-257) for n PUs.
+ * Per job: CUData::clipMv on both MVs (cudata.cpp:1915-1928, from cuX/cuY and the descriptor's picture size / maxCUSize),
+ * then exactly the reference's choice of path -- P slice: list 0 only, weighted (predInter*Short + addWeightUni) when
+ * weightedPred && weight[0][ref][0].present, else predInter*Pixel; B slice: both lists -> addWeightBi when weightedBiPred and
+ * either luma weight is present, else addAvg; one list -> weighted uni or pixel path.  Luma uses the 8-tap filters at
+ * quarter-pel fractions, chroma the 4-tap filters at eighth-pel fractions of mv << (1 - shift) (predict.cpp:312-318).
+ * The prediction of PU (puX, puY, w, h) is written at that position of predY / predCb / predCr (chroma at the shifted
+ * position and size).  refs: DEVICE array [2][maxRefs][3] of plane ORIGINS ({Y, Cb, Cr} of reference r of list l);
+ * weights: DEVICE array [2][maxRefs][3] {inputWeight, inputOffset, log2WeightDenom, wtPresent} or NULL. */
+typedef struct { int32_t puX, puY, w, h, cuX, cuY; int32_t refIdx[2]; int32_t mv[2][2]; } x265b200_mc_job;
+typedef struct { int32_t w, o, shift, present; } x265b200_mc_weight;
+typedef struct {
+    int32_t csp;                                  /* x265.h:588-592: 0 = 4:0:0 ... 3 = 4:4:4 */
+    int32_t isPSlice, weightedPred, weightedBiPred;
+    int32_t picWidth, picHeight, maxCUSize, maxRefs;
+    const void* const* refs; int64_t refStrideY, refStrideC;
+    void* predY; void* predCb; void* predCr; int64_t predStrideY, predStrideC;
+    const x265b200_mc_weight* weights;
+} x265b200_mc_desc;
+int x265b200_mc_dev(x265b200_ctx* ctx, int depth, const x265b200_mc_desc* desc, const x265b200_mc_job* jobs, int64_t n, int bLuma, int bChroma);
+
 /* ---- intra prediction: replaces cu[].intra_pred[35] / intra_filter / intra_pred_allangs
  *      (primitives.h:143-145,304-306; intrapred.cpp:31-234).  Neighbour arrays use the reference
  *      layout [topLeft, top 2N, left 2N] (4N+1 pixels).  log2N = 2..5. */

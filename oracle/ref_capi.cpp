@@ -720,3 +720,101 @@ extern "C" void ref_tu_pipeline(int sizeIdx, int useDST, const void* fencV, intp
         sseOut[b] = (uint64_t)primitives.cu[sizeIdx].sse_pp(fenc, fencStride, recon, reconStride);
     });
 }
+
+/* ---- motion compensation: the reference's OWN Predict::motionCompensation (common/predict.cpp:77-257) driven through
+ * shell CUData / Slice / PicYuv objects (offset tables = {0}, so getLumaAddr(0, 0) is the plane pointer we set per job). */
+#include "predict.h"
+#include "cudata.h"
+#include "slice.h"
+#include "framedata.h"
+#include "shortyuv.h"
+
+extern "C" {
+struct RefMCJob { int32_t puX, puY, w, h, cuX, cuY; int32_t refIdx[2]; int32_t mv[2][2]; };
+struct RefMCWeight { int32_t w, o, shift, present; };
+
+/* refs: [2][maxRefs][3] plane ORIGINS; weights: [2][maxRefs][3] or NULL; pred*: output planes (PU written at its position) */
+int ref_mc_batch(int csp, int isP, int wpP, int wpB, int picW, int picH, int maxCU, int maxRefs,
+                 const void* const* refs, intptr_t refStrideY, intptr_t refStrideC,
+                 void* predY, void* predCb, void* predCr, intptr_t predStrideY, intptr_t predStrideC,
+                 const RefMCWeight* weights, const RefMCJob* jobs, int64_t n, int bLuma, int bChroma)
+{
+    ensure_init();
+    if (maxRefs > MAX_NUM_REF) return -1;
+    const int hs = CHROMA_H_SHIFT(csp), vs = CHROMA_V_SHIFT(csp);
+    x265_param param;
+    x265_param_default(&param);
+    param.maxCUSize = maxCU; param.internalCsp = csp;
+    SPS sps; memset(&sps, 0, sizeof(sps));
+    sps.picWidthInLumaSamples = picW; sps.picHeightInLumaSamples = picH;
+    PPS pps; memset(&pps, 0, sizeof(pps));
+    pps.bUseWeightPred = !!wpP; pps.bUseWeightedBiPred = !!wpB;
+    Slice slice;
+    slice.m_sps = &sps; slice.m_pps = &pps; slice.m_sliceType = isP ? P_SLICE : B_SLICE;
+    slice.m_numRefIdx[0] = slice.m_numRefIdx[1] = maxRefs;
+    FrameData fd;
+    fd.m_param = &param; fd.m_slice = &slice;
+    intptr_t zero = 0;
+    std::vector<PicYuv> pics(2 * maxRefs);
+    for (int l = 0; l < 2; l++)
+        for (int r = 0; r < maxRefs; r++)
+        {
+            PicYuv& pic = pics[l * maxRefs + r];
+            pic.m_cuOffsetY = pic.m_cuOffsetC = pic.m_buOffsetY = pic.m_buOffsetC = &zero;
+            pic.m_stride = refStrideY; pic.m_strideC = refStrideC;
+            slice.m_refReconPicList[l][r] = &pic;
+            for (int p = 0; p < 3; p++)
+            {
+                WeightParam& wp = slice.m_weightPredTable[l][r][p];
+                if (weights)
+                {
+                    const RefMCWeight& w = weights[(l * maxRefs + r) * 3 + p];
+                    wp.inputWeight = w.w; wp.inputOffset = w.o; wp.log2WeightDenom = (uint32_t)w.shift; wp.wtPresent = w.present;
+                }
+                else { wp.inputWeight = 1; wp.inputOffset = 0; wp.log2WeightDenom = 0; wp.wtPresent = 0; }
+            }
+        }
+    Predict pred;
+    if (!pred.allocBuffers(csp)) return -1;
+    Yuv predYuv;
+    if (!predYuv.create(64, csp)) return -1;
+    CUData cu;
+    int8_t refIdx[2][4]; MV mv[2][4];
+    cu.m_slice = &slice; cu.m_encData = &fd;
+    cu.m_refIdx[0] = refIdx[0]; cu.m_refIdx[1] = refIdx[1]; cu.m_mv[0] = mv[0]; cu.m_mv[1] = mv[1];
+    alignas(16) unsigned char puStore[sizeof(PredictionUnit)];
+    PredictionUnit& pu = *(PredictionUnit*)puStore;
+    for (int64_t i = 0; i < n; i++)
+    {
+        const RefMCJob& j = jobs[i];
+        cu.m_cuPelX = j.cuX; cu.m_cuPelY = j.cuY;
+        for (int l = 0; l < 2; l++) { refIdx[l][0] = (int8_t)j.refIdx[l]; mv[l][0] = MV(j.mv[l][0], j.mv[l][1]); }
+        const intptr_t offY = j.puX + (intptr_t)j.puY * refStrideY, offC = (j.puX >> hs) + (intptr_t)(j.puY >> vs) * refStrideC;
+        for (int l = 0; l < 2; l++)
+            for (int r = 0; r < maxRefs; r++)
+            {
+                PicYuv& pic = pics[l * maxRefs + r];
+                const void* const* pl = refs + (l * maxRefs + r) * 3;
+                pic.m_picOrg[0] = (pixel*)pl[0] + offY;
+                pic.m_picOrg[1] = pl[1] ? (pixel*)pl[1] + offC : NULL;
+                pic.m_picOrg[2] = pl[2] ? (pixel*)pl[2] + offC : NULL;
+            }
+        pu.ctuAddr = 0; pu.cuAbsPartIdx = 0; pu.puAbsPartIdx = 0; pu.width = j.w; pu.height = j.h;
+        pred.motionCompensation(cu, pu, predYuv, !!bLuma, !!bChroma && csp != X265_CSP_I400);
+        if (bLuma)
+            for (int y = 0; y < j.h; y++)
+                memcpy((pixel*)predY + j.puX + (intptr_t)(j.puY + y) * predStrideY, predYuv.m_buf[0] + y * predYuv.m_size, j.w * sizeof(pixel));
+        if (bChroma && csp != X265_CSP_I400)
+            for (int c = 0; c < 2; c++)
+            {
+                pixel* d = (pixel*)(c ? predCr : predCb) + (j.puX >> hs) + (intptr_t)(j.puY >> vs) * predStrideC;
+                for (int y = 0; y < (j.h >> vs); y++)
+                    memcpy(d + (intptr_t)y * predStrideC, predYuv.m_buf[1 + c] + y * predYuv.m_csize, (j.w >> hs) * sizeof(pixel));
+            }
+    }
+    for (auto& pic : pics) { pic.m_cuOffsetY = pic.m_cuOffsetC = pic.m_buOffsetY = pic.m_buOffsetC = NULL; pic.m_picOrg[0] = pic.m_picOrg[1] = pic.m_picOrg[2] = NULL; }
+    cu.m_refIdx[0] = cu.m_refIdx[1] = NULL; cu.m_mv[0] = cu.m_mv[1] = NULL;
+    predYuv.destroy();
+    return 0;
+}
+} /* extern "C" */

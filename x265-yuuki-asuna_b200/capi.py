@@ -440,3 +440,25 @@ def _ctx_tu_pipeline_dev(self, sizeIdx, depth, useDST, dFenc, fencStride, dPred,
 
 
 Ctx.tu_pipeline_dev = _ctx_tu_pipeline_dev
+
+
+# ---- motion compensation driver -------------------------------------------------------------------------
+MC_JOB = np.dtype([("puX", np.int32), ("puY", np.int32), ("w", np.int32), ("h", np.int32), ("cuX", np.int32), ("cuY", np.int32),
+                   ("refIdx", np.int32, (2,)), ("mv", np.int32, (2, 2))])
+MC_WEIGHT = np.dtype([("w", np.int32), ("o", np.int32), ("shift", np.int32), ("present", np.int32)])
+
+
+class MC_DESC(ctypes.Structure):
+    """x265b200_mc_desc (include/x265b200.h)"""
+    _fields_ = [("csp", ctypes.c_int32), ("isPSlice", ctypes.c_int32), ("weightedPred", ctypes.c_int32), ("weightedBiPred", ctypes.c_int32),
+                ("picWidth", ctypes.c_int32), ("picHeight", ctypes.c_int32), ("maxCUSize", ctypes.c_int32), ("maxRefs", ctypes.c_int32),
+                ("refs", ctypes.c_void_p), ("refStrideY", ctypes.c_int64), ("refStrideC", ctypes.c_int64),
+                ("predY", ctypes.c_void_p), ("predCb", ctypes.c_void_p), ("predCr", ctypes.c_void_p),
+                ("predStrideY", ctypes.c_int64), ("predStrideC", ctypes.c_int64), ("weights", ctypes.c_void_p)]
+
+
+def _ctx_mc_dev(self, depth, desc, dJobs, n, bLuma=1, bChroma=1):
+    self._chk(self.L.x265b200_mc_dev(self.h, int(depth), ctypes.byref(desc), _vp(dJobs), _i64(n), int(bLuma), int(bChroma)))
+
+
+Ctx.mc_dev = _ctx_mc_dev

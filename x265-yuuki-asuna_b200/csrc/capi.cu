@@ -83,6 +83,7 @@ int tu_pipeline_dev(Ctx*, int sizeIdx, int depth, int useDST, const void* fenc, 
 void host_dct_table(int N, int16_t* out);
 int interp_dev(Ctx*, int kind, int taps, int depth, int w, int h, const void* src, int64_t srcStride,
                void* dst, int64_t dstStride, const x265b200_interp_job* jobs, int64_t n, int isRowExt);
+int mc_dev(Ctx*, int depth, const x265b200_mc_desc* d, const x265b200_mc_job* jobs, int64_t n, int bLuma, int bChroma);
 int intra_pred_dev(Ctx*, int depth, int log2N, const void* nbr, void* dst, int64_t dstStride, const x265b200_intra_job* jobs, int64_t n);
 int intra_filter_dev(Ctx*, int depth, int log2N, const void* src, void* dst, int64_t n);
 int intra_allangs_dev(Ctx*, int depth, int log2N, const void* refPix, const void* filtPix, void* dest, int bLuma, int64_t n);
@@ -345,6 +346,11 @@ int x265b200_interp_dev(x265b200_ctx* ctx, int kind, int taps, int depth, int w,
 {
     REQUIRE_CTX(ctx);
     return interp_dev(CTX(ctx), kind, taps, depth, w, h, src, srcStride, dst, dstStride, jobs, n, isRowExt);
+}
+int x265b200_mc_dev(x265b200_ctx* ctx, int depth, const x265b200_mc_desc* desc, const x265b200_mc_job* jobs, int64_t n, int bLuma, int bChroma)
+{
+    REQUIRE_CTX(ctx);
+    return mc_dev(CTX(ctx), depth, desc, jobs, n, bLuma, bChroma);
 }
 int x265b200_intra_pred_dev(x265b200_ctx* ctx, int depth, int log2N, const void* nbr, void* dst, int64_t dstStride, const x265b200_intra_job* jobs, int64_t n)
 {

@@ -176,4 +176,204 @@ int interp_dev(Ctx* ctx, int kind, int taps, int depth, int w, int h, const void
     return check(cudaGetLastError(), "interp kernel launch");
 }
 
+// ---------------------------------------------------------------------------------------------
+// Motion compensation driver: Predict::motionCompensation (common/predict.cpp:77-257) for a batch of
+// PUs -- CUData::clipMv (cudata.cpp:1915-1928), predInterLumaPixel/Short + predInterChromaPixel/Short (predict.cpp:259-406:
+// copy / hpp / vpp / hps+vsp for the pixel path, p2s / hps / vps / hps+vss for the 14-bit path), then bi-prediction
+// addAvg (pixel.cpp:842), addWeightUni = weight_sp (predict.cpp:525-575, pixel.cpp:493) or addWeightBi (predict.cpp:411-522).
+// One CTA per (PU, plane); the 14-bit intermediates of the two lists live in shared memory and never touch HBM.
+// ---------------------------------------------------------------------------------------------
+struct McArgs
+{
+    const void* const* refs;                 // device array [2][maxRefs][3] of plane origins
+    int64_t refStride[3];
+    void* pred[3]; int64_t predStride[3];
+    const x265b200_mc_job* jobs; int64_t n;
+    const x265b200_mc_weight* weights;       // device array [2][maxRefs][3], or nullptr
+    int maxRefs, hshift, vshift, depth, isP, wpP, wpB, picW, picH, maxCU;
+    int planes[3], nPlanes;
+};
+
+// One block through the interpolation filters.  toShort: 14-bit intermediate into dsh (row pitch w); else pixels into dpix.
+template<typename pixel, int N>
+__device__ void mc_fir(const pixel* src, int64_t ss, int w, int h, int xf, int yf, int depth, bool toShort,
+                       pixel* dpix, int64_t dps, int16_t* dsh, int16_t* immed)
+{
+    const int headRoom = 14 - depth, maxVal = (1 << depth) - 1, half = N / 2 - 1;
+    const int shPS = 6 - headRoom, offPS = (int)((unsigned)-8192 << shPS);
+    int cx[N], cy[N];
+#pragma unroll
+    for (int t = 0; t < N; t++) { cx[t] = N == 8 ? c_lumaFilter[xf & 3][t] : c_chromaFilter[xf][t]; cy[t] = N == 8 ? c_lumaFilter[yf & 3][t] : c_chromaFilter[yf][t]; }
+    if (!xf && !yf)
+    {
+        for (int e = threadIdx.x; e < w * h; e += blockDim.x)
+        {
+            const int y = e / w, x = e - y * w;
+            const int v = src[(int64_t)y * ss + x];
+            if (toShort) dsh[e] = (int16_t)((int16_t)(v << headRoom) - (int16_t)8192);          // filterPixelToShort_c, ipfilter.cpp:40-57
+            else dpix[(int64_t)y * dps + x] = (pixel)v;                                         // copy_pp
+        }
+        return;
+    }
+    if (!xf || !yf)
+    {
+        const int64_t step = yf ? ss : 1;
+        const int* c = yf ? cy : cx;
+        for (int e = threadIdx.x; e < w * h; e += blockDim.x)
+        {
+            const int y = e / w, x = e - y * w;
+            const pixel* q = src + (int64_t)y * ss + x - half * step;
+            int sum = 0;
+#pragma unroll
+            for (int t = 0; t < N; t++) sum += (int)q[t * step] * c[t];
+            if (toShort) dsh[e] = (int16_t)((sum + offPS) >> shPS);                              // interp_horiz_ps_c / interp_vert_ps_c
+            else
+            {
+                const int val = (int16_t)((sum + 32) >> 6);                                      // interp_horiz_pp_c / interp_vert_pp_c
+                dpix[(int64_t)y * dps + x] = (pixel)(val < 0 ? 0 : (val > maxVal ? maxVal : val));
+            }
+        }
+        return;
+    }
+    // hps with row extension into immed (pitch w), then vsp (pixel path, predict.cpp:266 luma_hvpp / :322-326) or vss (:297-303)
+    const int rows = h + N - 1;
+    for (int e = threadIdx.x; e < rows * w; e += blockDim.x)
+    {
+        const int y = e / w, x = e - y * w;
+        const pixel* q = src + (int64_t)(y - half) * ss + x - half;
+        int sum = 0;
+#pragma unroll
+        for (int t = 0; t < N; t++) sum += (int)q[t] * cx[t];
+        immed[e] = (int16_t)((sum + offPS) >> shPS);
+    }
+    __syncthreads();
+    const int shSP = 6 + headRoom, offSP = (1 << (shSP - 1)) + (8192 << 6);
+    for (int e = threadIdx.x; e < w * h; e += blockDim.x)
+    {
+        const int y = e / w, x = e - y * w;
+        int sum = 0;
+#pragma unroll
+        for (int t = 0; t < N; t++) sum += (int)immed[(y + t) * w + x] * cy[t];
+        if (toShort) dsh[e] = (int16_t)(sum >> 6);                                                // interp_vert_ss_c
+        else
+        {
+            const int val = (int16_t)((sum + offSP) >> shSP);                                     // interp_vert_sp_c
+            dpix[(int64_t)y * dps + x] = (pixel)(val < 0 ? 0 : (val > maxVal ? maxVal : val));
+        }
+    }
+    __syncthreads();
+}
+
+template<typename pixel>
+__global__ void __launch_bounds__(128)
+mc_kernel(McArgs a)
+{
+    __shared__ int16_t sh[2][64 * 64];
+    __shared__ int16_t immed[64 * (64 + 7)];
+    const x265b200_mc_job job = a.jobs[blockIdx.x];
+    const int p = a.planes[blockIdx.y];
+    const int hs = p ? a.hshift : 0, vs = p ? a.vshift : 0;
+    const int w = job.w >> hs, h = job.h >> vs, x0 = job.puX >> hs, y0 = job.puY >> vs;
+    if (w <= 0 || h <= 0) return;
+    const int maxVal = (1 << a.depth) - 1, shiftNum = 14 - a.depth;
+
+    // CUData::clipMv
+    const int xmax = (a.picW + 8 - job.cuX - 1) << 2, xmin = -((a.maxCU + 8 + job.cuX - 1) << 2);
+    const int ymax = (a.picH + 8 - job.cuY - 1) << 2, ymin = -((a.maxCU + 8 + job.cuY - 1) << 2);
+    int mvx[2], mvy[2];
+#pragma unroll
+    for (int l = 0; l < 2; l++) { mvx[l] = min(xmax, max(xmin, job.mv[l][0])); mvy[l] = min(ymax, max(ymin, job.mv[l][1])); }
+
+    const int r0 = job.refIdx[0], r1 = a.isP ? -1 : job.refIdx[1];
+    auto W = [&](int l, int r) -> const x265b200_mc_weight* { return a.weights + ((int64_t)l * a.maxRefs + r) * 3; };
+    // mode: 0 uni pixel, 1 uni weighted, 2 bi average, 3 bi weighted
+    int mode, l0 = 0;
+    if (a.isP) mode = (a.wpP && a.weights && W(0, r0)[0].present) ? 1 : 0;
+    else
+    {
+        const bool pw0 = a.wpB && a.weights && r0 >= 0, pw1 = a.wpB && a.weights && r1 >= 0;
+        if (r0 >= 0 && r1 >= 0) mode = (pw0 && pw1 && (W(0, r0)[0].present || W(1, r1)[0].present)) ? 3 : 2;
+        else if (r0 >= 0) mode = (pw0 && W(0, r0)[0].present) ? 1 : 0;
+        else { l0 = 1; mode = (pw1 && W(1, r1)[0].present) ? 1 : 0; }
+    }
+    pixel* dst = (pixel*)a.pred[p] + (int64_t)y0 * a.predStride[p] + x0;
+    const int64_t ds = a.predStride[p];
+
+    const int nl = mode >= 2 ? 2 : 1;
+    for (int k = 0; k < nl; k++)
+    {
+        const int l = mode >= 2 ? k : l0, r = l ? r1 : r0;
+        const pixel* plane = (const pixel*)a.refs[((int64_t)l * a.maxRefs + r) * 3 + p];
+        int ix, iy, xf, yf;
+        if (!p) { ix = mvx[l] >> 2; iy = mvy[l] >> 2; xf = mvx[l] & 3; yf = mvy[l] & 3; }
+        else
+        {
+            const int cx = mvx[l] << (1 - hs), cy = mvy[l] << (1 - vs);                         // predict.cpp:312-313
+            ix = cx >> 3; iy = cy >> 3; xf = cx & 7; yf = cy & 7;
+        }
+        const pixel* src = plane + (int64_t)(y0 + iy) * a.refStride[p] + x0 + ix;
+        if (!p) mc_fir<pixel, 8>(src, a.refStride[p], w, h, xf, yf, a.depth, mode != 0, dst, ds, sh[k], immed);
+        else    mc_fir<pixel, 4>(src, a.refStride[p], w, h, xf, yf, a.depth, mode != 0, dst, ds, sh[k], immed);
+    }
+    if (mode == 0) return;
+    __syncthreads();
+    if (mode == 2)
+    {
+        const int sn = shiftNum + 1, offset = (1 << (sn - 1)) + 2 * 8192;                        // addAvg, pixel.cpp:842-862
+        for (int e = threadIdx.x; e < w * h; e += blockDim.x)
+        {
+            const int y = e / w, x = e - y * w, v = ((int)sh[0][e] + (int)sh[1][e] + offset) >> sn;
+            dst[(int64_t)y * ds + x] = (pixel)(v < 0 ? 0 : (v > maxVal ? maxVal : v));
+        }
+    }
+    else if (mode == 1)
+    {
+        const x265b200_mc_weight wp = W(l0, l0 ? r1 : r0)[p];                                    // addWeightUni -> weight_sp_c
+        const int shift = wp.shift + shiftNum, round = shift ? (1 << (shift - 1)) : 0, offset = wp.o * (1 << (a.depth - 8));
+        for (int e = threadIdx.x; e < w * h; e += blockDim.x)
+        {
+            const int y = e / w, x = e - y * w, v = ((wp.w * ((int)sh[0][e] + 8192) + round) >> shift) + offset;
+            dst[(int64_t)y * ds + x] = (pixel)(v < 0 ? 0 : (v > maxVal ? maxVal : v));
+        }
+    }
+    else
+    {
+        const x265b200_mc_weight w0 = W(0, r0)[p], w1 = W(1, r1)[p];                             // addWeightBi / weightBidir
+        const int offset = (w0.o + w1.o) * (1 << (a.depth - 8)), shift = w0.shift + shiftNum + 1, round = shift ? (1 << (shift - 1)) : 0;
+        for (int e = threadIdx.x; e < w * h; e += blockDim.x)
+        {
+            const int y = e / w, x = e - y * w;
+            const int v = (w0.w * ((int)sh[0][e] + 8192) + w1.w * ((int)sh[1][e] + 8192) + round + (offset * (1 << (shift - 1)))) >> shift;
+            dst[(int64_t)y * ds + x] = (pixel)(v < 0 ? 0 : (v > maxVal ? maxVal : v));
+        }
+    }
+}
+
+int mc_dev(Ctx* ctx, int depth, const x265b200_mc_desc* d, const x265b200_mc_job* jobs, int64_t n, int bLuma, int bChroma)
+{
+    if (n <= 0) return 0;
+    if (!d || !d->refs || !jobs) { set_error("mc: NULL descriptor / reference table / jobs"); return -1; }
+    if (d->csp < 0 || d->csp > 3) { set_error("mc: csp %d", d->csp); return -1; }
+    if (d->maxRefs <= 0) { set_error("mc: maxRefs %d", d->maxRefs); return -1; }
+    if (upload_filters(ctx)) return -1;
+    McArgs a;
+    a.refs = d->refs; a.jobs = jobs; a.n = n; a.weights = d->weights; a.maxRefs = d->maxRefs;
+    a.refStride[0] = d->refStrideY; a.refStride[1] = a.refStride[2] = d->refStrideC;
+    a.pred[0] = d->predY; a.pred[1] = d->predCb; a.pred[2] = d->predCr;
+    a.predStride[0] = d->predStrideY; a.predStride[1] = a.predStride[2] = d->predStrideC;
+    a.hshift = d->csp == 1 || d->csp == 2; a.vshift = d->csp == 1;
+    a.depth = depth; a.isP = d->isPSlice; a.wpP = d->weightedPred; a.wpB = d->weightedBiPred;
+    a.picW = d->picWidth; a.picH = d->picHeight; a.maxCU = d->maxCUSize;
+    a.nPlanes = 0;
+    if (bLuma) a.planes[a.nPlanes++] = 0;
+    if (bChroma && d->csp != 0) { a.planes[a.nPlanes++] = 1; a.planes[a.nPlanes++] = 2; }
+    if (!a.nPlanes) return 0;
+    for (int i = 0; i < a.nPlanes; i++) if (!a.pred[a.planes[i]]) { set_error("mc: prediction plane %d is NULL", a.planes[i]); return -1; }
+    dim3 grid((unsigned)n, (unsigned)a.nPlanes);
+    if (depth > 8) mc_kernel<uint16_t><<<grid, 128, 0, ctx->stream>>>(a);
+    else           mc_kernel<uint8_t><<<grid, 128, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    return check(cudaGetLastError(), "mc kernel launch");
+}
+
 } // namespace x265b200
