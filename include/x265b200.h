@@ -211,6 +211,35 @@ typedef struct {
 } x265b200_mc_desc;
 int x265b200_mc_dev(x265b200_ctx* ctx, int depth, const x265b200_mc_desc* desc, const x265b200_mc_job* jobs, int64_t n, int bLuma, int bChroma);
 
+/* ---- in-loop filter entries: SAO + deblocking line filters ----------------------------------------------
+ * One job = one call of the reference primitive on a CTU-sized block.  Offsets are in elements of the operand they index:
+ * recOff into `rec` (pixels), diffOff into `diff` (int16, row pitch 64 = MAX_CU_SIZE), buf0/buf1 into signBuf (int8),
+ * offsetOff into the offset tables (apply) or into stats/count (statistics, which are ADDED to, as the C code does).
+ *   apply (x265b200_sao_apply_dev), replaces primitives.saoCuOrg* (primitives.h:343-349; loopfilter.cpp:45-139):
+ *     E0       processSaoCUE0(rec, offsetEo, width, signLeft = buf0[2], stride)              2 rows
+ *     E1       processSaoCUE1(rec, upBuff1 = buf0, offsetEo, stride, width)                  1 row
+ *     E1_2ROWS processSaoCUE1_2Rows(...)                                                      2 rows
+ *     E2       processSaoCUE2(rec, bufft = buf0, buff1 = buf1, offsetEo, width, stride)
+ *     E3       processSaoCUE3(rec, upBuff1 = buf0, offsetEo, stride, startX, endX = width)
+ *     B0       processSaoCUB0(rec, offsetBo[32], ctuWidth = width, ctuHeight = height, stride)
+ *     maxWidth = largest job.width (<= 256) of the launch.
+ *   statistics (x265b200_sao_stats_dev), replaces primitives.saoCuStats* (primitives.h:351-355; sao.cpp:1762-1926):
+ *     BO / E0 / E1 (upBuff1 = buf0) / E2 (upBuff1 = buf0, upBufft = buf1) / E3 (upBuff1 = buf0), endX = width, endY = height;
+ *     the sign buffers end in the state the row-by-row C loops leave them in. */
+enum { X265B200_SAO_E0 = 0, X265B200_SAO_E1, X265B200_SAO_E1_2ROWS, X265B200_SAO_E2, X265B200_SAO_E3, X265B200_SAO_B0, X265B200_SAO_BO = X265B200_SAO_B0 };
+typedef struct { int64_t recOff, diffOff, buf0, buf1, offsetOff; int32_t width, height, startX, pad; } x265b200_sao_job;
+int x265b200_sao_apply_dev(x265b200_ctx* ctx, int kind, int depth, void* rec, int64_t stride, const x265b200_sao_job* jobs, int64_t n,
+                           int8_t* signBuf, const int8_t* offsets, int maxWidth);
+int x265b200_sao_stats_dev(x265b200_ctx* ctx, int kind, int depth, const int16_t* diff, const void* rec, int64_t stride,
+                           const x265b200_sao_job* jobs, int64_t n, int8_t* signBuf, int32_t* stats, int32_t* count);
+/* primitives.sign = calSign (primitives.h:357; loopfilter.cpp:39-43): dst[x] = sign(src1[x] - src2[x]) */
+int x265b200_sign_dev(x265b200_ctx* ctx, int depth, int8_t* dst, const void* src1, const void* src2, int64_t n);
+/* pelFilterLumaStrong[2] / pelFilterChroma[2] (primitives.h:372-373; loopfilter.cpp:141-180): job i filters the 4 lines
+ * (UNIT_SIZE) src + k*srcStep, k = 0..3, across the edge at `offset` spacing.  luma: tcP, tcQ; chroma (chroma != 0): tcP = tc,
+ * tcQ = maskP, maskQ = maskQ. */
+typedef struct { int64_t srcOff, srcStep, offset; int32_t tcP, tcQ, maskQ, pad; } x265b200_deblock_job;
+int x265b200_deblock_dev(x265b200_ctx* ctx, int chroma, int depth, void* pic, const x265b200_deblock_job* jobs, int64_t n);
+
 /* ---- intra prediction: replaces cu[].intra_pred[35] / intra_filter / intra_pred_allangs
  *      (primitives.h:143-145,304-306; intrapred.cpp:31-234).  Neighbour arrays use the reference
  *      layout [topLeft, top 2N, left 2N] (4N+1 pixels).  log2N = 2..5. */

@@ -432,6 +432,113 @@ void scale2D_thunk(pixel* dst, const pixel* src, intptr_t stride)
     CK(x265b200_download(C(), dst, dD, 32 * 32 * PX));
 }
 
+// ---- SAO / deblock / sign (loopfilter.cpp:39-180, sao.cpp:1762-1926) -------------------------------------------------
+x265b200_sao_job sao_job(int64_t recOff, int64_t buf0, int64_t buf1, int width, int height, int startX)
+{
+    x265b200_sao_job j; memset(&j, 0, sizeof(j));
+    j.recOff = recOff; j.buf0 = buf0; j.buf1 = buf1; j.width = width; j.height = height; j.startX = startX;
+    return j;
+}
+// runs one apply job on a staged copy of rec[0, ext) and of the sign buffers; bufBytes[k] bytes of hostBuf[k] travel both ways
+void sao_apply_run(int kind, pixel* rec, size_t ext, intptr_t stride, const int8_t* offsets, int nOffsets, int width, int height, int startX,
+                   int8_t* hostBuf0, size_t bytes0, bool write0, const int8_t* hostBuf1, size_t bytes1)
+{
+    void* dR = up1d(0, rec, ext * PX);
+    const size_t off1 = (bytes0 + 15) & ~(size_t)15;
+    int8_t* dB = (int8_t*)dev(1, off1 + bytes1 + 16);
+    if (bytes0) CK(x265b200_upload(C(), dB, hostBuf0, bytes0));
+    if (bytes1) CK(x265b200_upload(C(), dB + off1, hostBuf1, bytes1));
+    void* dO = up1d(2, offsets, nOffsets);
+    x265b200_sao_job job = sao_job(0, 0, (int64_t)off1, width, height, startX);
+    void* dJ = up1d(3, &job, sizeof(job));
+    CK(x265b200_sao_apply_dev(C(), kind, X265_DEPTH, dR, stride, (const x265b200_sao_job*)dJ, 1, dB, (const int8_t*)dO, width));
+    CK(x265b200_download(C(), rec, dR, ext * PX));
+    if (write0 && bytes0) CK(x265b200_download(C(), hostBuf0, dB, bytes0));
+}
+void saoE0_thunk(pixel* rec, int8_t* offsetEo, int width, int8_t* signLeft, intptr_t stride)
+{
+    sao_apply_run(X265B200_SAO_E0, rec, (size_t)stride + width + 1, stride, offsetEo, 5, width, 2, 0, signLeft, 2, false, nullptr, 0);
+}
+void saoE1_thunk(pixel* rec, int8_t* upBuff1, int8_t* offsetEo, intptr_t stride, int width)
+{
+    sao_apply_run(X265B200_SAO_E1, rec, (size_t)stride + width, stride, offsetEo, 5, width, 1, 0, upBuff1, width, true, nullptr, 0);
+}
+void saoE1_2rows_thunk(pixel* rec, int8_t* upBuff1, int8_t* offsetEo, intptr_t stride, int width)
+{
+    sao_apply_run(X265B200_SAO_E1_2ROWS, rec, (size_t)2 * stride + width, stride, offsetEo, 5, width, 2, 0, upBuff1, width, true, nullptr, 0);
+}
+void saoE2_thunk(pixel* rec, int8_t* bufft, int8_t* buff1, int8_t* offsetEo, int width, intptr_t stride)
+{
+    sao_apply_run(X265B200_SAO_E2, rec, (size_t)stride + width + 1, stride, offsetEo, 5, width, 1, 0, bufft, (size_t)width + 1, true, buff1, width);
+}
+void saoE3_thunk(pixel* rec, int8_t* upBuff1, int8_t* offsetEo, intptr_t stride, int startX, int endX)
+{
+    if (endX <= 0) return;
+    sao_apply_run(X265B200_SAO_E3, rec, (size_t)stride + endX, stride, offsetEo, 5, endX, 1, startX, upBuff1, endX, true, nullptr, 0);
+}
+void saoB0_thunk(pixel* rec, const int8_t* offsetBo, int ctuWidth, int ctuHeight, intptr_t stride)
+{
+    if (ctuWidth <= 0 || ctuHeight <= 0) return;
+    sao_apply_run(X265B200_SAO_B0, rec, (size_t)(ctuHeight - 1) * stride + ctuWidth, stride, offsetBo, 32, ctuWidth, ctuHeight, 0, nullptr, 0, false, nullptr, 0);
+}
+// statistics: rec is staged from rec - 1 (E0 / E2 read the left neighbour of column 0) through rec[endY*stride + endX]
+void sao_stats_run(int kind, const int16_t* diff, const pixel* rec, intptr_t stride, int8_t* up1, int8_t* upt, int endX, int endY,
+                   int32_t* stats, int32_t* count)
+{
+    if (endX <= 0 || endY <= 0) return;
+    const int ncls = kind == X265B200_SAO_BO ? 32 : 5;
+    void* dD = up1d(0, diff, ((size_t)(endY - 1) * 64 + endX) * 2);
+    void* dR = up1d(1, rec - 1, ((size_t)endY * stride + endX + 2) * PX);
+    const size_t seg = ((size_t)endX + 2 + 15) & ~(size_t)15;               // bytes [-1, endX] of each sign buffer
+    int8_t* dB = (int8_t*)dev(2, 2 * seg + 16);
+    if (up1) CK(x265b200_upload(C(), dB, up1 - 1, (size_t)endX + 2));
+    if (upt) CK(x265b200_upload(C(), dB + seg, upt - 1, (size_t)endX + 2));
+    int32_t* dS = (int32_t*)dev(3, 64 * 4);
+    CK(x265b200_upload(C(), dS, stats, ncls * 4)); CK(x265b200_upload(C(), dS + 32, count, ncls * 4));
+    x265b200_sao_job job = sao_job(1, 1, (int64_t)seg + 1, endX, endY, 0);
+    void* dJ = up1d(4, &job, sizeof(job));
+    CK(x265b200_sao_stats_dev(C(), kind, X265_DEPTH, (const int16_t*)dD, dR, stride, (const x265b200_sao_job*)dJ, 1, dB, dS, dS + 32));
+    CK(x265b200_download(C(), stats, dS, ncls * 4)); CK(x265b200_download(C(), count, dS + 32, ncls * 4));
+    if (up1 && kind != X265B200_SAO_E0 && kind != X265B200_SAO_BO) CK(x265b200_download(C(), up1 - 1, dB, (size_t)endX + 2));
+    if (upt) CK(x265b200_download(C(), upt - 1, dB + seg, (size_t)endX + 2));
+}
+void saoStatsBO_thunk(const int16_t* diff, const pixel* rec, intptr_t stride, int endX, int endY, int32_t* stats, int32_t* count)
+{ sao_stats_run(X265B200_SAO_BO, diff, rec, stride, nullptr, nullptr, endX, endY, stats, count); }
+void saoStatsE0_thunk(const int16_t* diff, const pixel* rec, intptr_t stride, int endX, int endY, int32_t* stats, int32_t* count)
+{ sao_stats_run(X265B200_SAO_E0, diff, rec, stride, nullptr, nullptr, endX, endY, stats, count); }
+void saoStatsE1_thunk(const int16_t* diff, const pixel* rec, intptr_t stride, int8_t* upBuff1, int endX, int endY, int32_t* stats, int32_t* count)
+{ sao_stats_run(X265B200_SAO_E1, diff, rec, stride, upBuff1, nullptr, endX, endY, stats, count); }
+void saoStatsE2_thunk(const int16_t* diff, const pixel* rec, intptr_t stride, int8_t* upBuff1, int8_t* upBufft, int endX, int endY, int32_t* stats, int32_t* count)
+{ sao_stats_run(X265B200_SAO_E2, diff, rec, stride, upBuff1, upBufft, endX, endY, stats, count); }
+void saoStatsE3_thunk(const int16_t* diff, const pixel* rec, intptr_t stride, int8_t* upBuff1, int endX, int endY, int32_t* stats, int32_t* count)
+{ sao_stats_run(X265B200_SAO_E3, diff, rec, stride, upBuff1, nullptr, endX, endY, stats, count); }
+void sign_thunk(int8_t* dst, const pixel* src1, const pixel* src2, const int endX)
+{
+    if (endX <= 0) return;
+    void* d1 = up1d(0, src1, (size_t)endX * PX); void* d2 = up1d(1, src2, (size_t)endX * PX); void* dD = dev(2, endX);
+    CK(x265b200_sign_dev(C(), X265_DEPTH, (int8_t*)dD, d1, d2, endX));
+    CK(x265b200_download(C(), dst, dD, endX));
+}
+void deblock_run(int chroma, pixel* src, intptr_t srcStep, intptr_t offset, int lowTap, int highTap, int32_t a, int32_t b, int32_t c)
+{
+    intptr_t lo = 0, hi = 0;
+    for (int k = 0; k < 4; k++)
+        for (int m = lowTap; m <= highTap; m++)
+        {
+            const intptr_t o = k * srcStep + m * offset;
+            lo = o < lo ? o : lo; hi = o > hi ? o : hi;
+        }
+    const size_t ext = (size_t)(hi - lo + 1);
+    void* dP = up1d(0, src + lo, ext * PX);
+    x265b200_deblock_job job; memset(&job, 0, sizeof(job));
+    job.srcOff = -lo; job.srcStep = srcStep; job.offset = offset; job.tcP = a; job.tcQ = b; job.maskQ = c;
+    void* dJ = up1d(1, &job, sizeof(job));
+    CK(x265b200_deblock_dev(C(), chroma, X265_DEPTH, dP, (const x265b200_deblock_job*)dJ, 1));
+    CK(x265b200_download(C(), src + lo, dP, ext * PX));
+}
+void pel_filter_luma_thunk(pixel* src, intptr_t srcStep, intptr_t offset, int32_t tcP, int32_t tcQ) { deblock_run(0, src, srcStep, offset, -4, 3, tcP, tcQ, 0); }
+void pel_filter_chroma_thunk(pixel* src, intptr_t srcStep, intptr_t offset, int32_t tc, int32_t maskP, int32_t maskQ) { deblock_run(1, src, srcStep, offset, -2, 1, tc, maskP, maskQ); }
+
 } // namespace
 
 namespace X265_NS {
@@ -593,6 +700,17 @@ void setupAssemblyPrimitives(EncoderPrimitives& p, int /*cpuMask: SIMD flags are
     p.extendRowBorder = extend_row_border_thunk;
     p.scale1D_128to64[NONALIGNED] = scale1D_thunk; p.scale1D_128to64[ALIGNED] = scale1D_thunk;
     p.scale2D_64to32 = scale2D_thunk;
+
+    // in-loop filters (setupLoopFilterPrimitives_c loopfilter.cpp:184-201, setupSaoPrimitives_c sao.cpp:1927-1935)
+    p.saoCuOrgE0 = saoE0_thunk; p.saoCuOrgE1 = saoE1_thunk; p.saoCuOrgE1_2Rows = saoE1_2rows_thunk;
+    p.saoCuOrgE2[0] = saoE2_thunk; p.saoCuOrgE2[1] = saoE2_thunk;
+    p.saoCuOrgE3[0] = saoE3_thunk; p.saoCuOrgE3[1] = saoE3_thunk;
+    p.saoCuOrgB0 = saoB0_thunk;
+    p.saoCuStatsBO = saoStatsBO_thunk; p.saoCuStatsE0 = saoStatsE0_thunk; p.saoCuStatsE1 = saoStatsE1_thunk;
+    p.saoCuStatsE2 = saoStatsE2_thunk; p.saoCuStatsE3 = saoStatsE3_thunk;
+    p.sign = sign_thunk;
+    p.pelFilterLumaStrong[0] = pel_filter_luma_thunk; p.pelFilterLumaStrong[1] = pel_filter_luma_thunk;
+    p.pelFilterChroma[0] = pel_filter_chroma_thunk;   p.pelFilterChroma[1] = pel_filter_chroma_thunk;
 }
 
 } // namespace X265_NS

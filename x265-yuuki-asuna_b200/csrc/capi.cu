@@ -84,6 +84,11 @@ void host_dct_table(int N, int16_t* out);
 int interp_dev(Ctx*, int kind, int taps, int depth, int w, int h, const void* src, int64_t srcStride,
                void* dst, int64_t dstStride, const x265b200_interp_job* jobs, int64_t n, int isRowExt);
 int mc_dev(Ctx*, int depth, const x265b200_mc_desc* d, const x265b200_mc_job* jobs, int64_t n, int bLuma, int bChroma);
+int sao_apply_dev(Ctx*, int kind, int depth, void* rec, int64_t stride, const x265b200_sao_job* jobs, int64_t n, int8_t* signBuf, const int8_t* offsets, int maxWidth);
+int sao_stats_dev(Ctx*, int kind, int depth, const int16_t* diff, const void* rec, int64_t stride, const x265b200_sao_job* jobs, int64_t n,
+                  int8_t* signBuf, int32_t* stats, int32_t* count);
+int sign_dev(Ctx*, int depth, int8_t* dst, const void* src1, const void* src2, int64_t n);
+int deblock_dev(Ctx*, int chroma, int depth, void* pic, const x265b200_deblock_job* jobs, int64_t n);
 int intra_pred_dev(Ctx*, int depth, int log2N, const void* nbr, void* dst, int64_t dstStride, const x265b200_intra_job* jobs, int64_t n);
 int intra_filter_dev(Ctx*, int depth, int log2N, const void* src, void* dst, int64_t n);
 int intra_allangs_dev(Ctx*, int depth, int log2N, const void* refPix, const void* filtPix, void* dest, int bLuma, int64_t n);
@@ -351,6 +356,28 @@ int x265b200_mc_dev(x265b200_ctx* ctx, int depth, const x265b200_mc_desc* desc, 
 {
     REQUIRE_CTX(ctx);
     return mc_dev(CTX(ctx), depth, desc, jobs, n, bLuma, bChroma);
+}
+int x265b200_sao_apply_dev(x265b200_ctx* ctx, int kind, int depth, void* rec, int64_t stride, const x265b200_sao_job* jobs, int64_t n,
+                           int8_t* signBuf, const int8_t* offsets, int maxWidth)
+{
+    REQUIRE_CTX(ctx);
+    return sao_apply_dev(CTX(ctx), kind, depth, rec, stride, jobs, n, signBuf, offsets, maxWidth);
+}
+int x265b200_sao_stats_dev(x265b200_ctx* ctx, int kind, int depth, const int16_t* diff, const void* rec, int64_t stride,
+                           const x265b200_sao_job* jobs, int64_t n, int8_t* signBuf, int32_t* stats, int32_t* count)
+{
+    REQUIRE_CTX(ctx);
+    return sao_stats_dev(CTX(ctx), kind, depth, diff, rec, stride, jobs, n, signBuf, stats, count);
+}
+int x265b200_sign_dev(x265b200_ctx* ctx, int depth, int8_t* dst, const void* src1, const void* src2, int64_t n)
+{
+    REQUIRE_CTX(ctx);
+    return sign_dev(CTX(ctx), depth, dst, src1, src2, n);
+}
+int x265b200_deblock_dev(x265b200_ctx* ctx, int chroma, int depth, void* pic, const x265b200_deblock_job* jobs, int64_t n)
+{
+    REQUIRE_CTX(ctx);
+    return deblock_dev(CTX(ctx), chroma, depth, pic, jobs, n);
 }
 int x265b200_intra_pred_dev(x265b200_ctx* ctx, int depth, int log2N, const void* nbr, void* dst, int64_t dstStride, const x265b200_intra_job* jobs, int64_t n)
 {
