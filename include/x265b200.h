@@ -240,6 +240,23 @@ int x265b200_sign_dev(x265b200_ctx* ctx, int depth, int8_t* dst, const void* src
 typedef struct { int64_t srcOff, srcStep, offset; int32_t tcP, tcQ, maskQ, pad; } x265b200_deblock_job;
 int x265b200_deblock_dev(x265b200_ctx* ctx, int chroma, int depth, void* pic, const x265b200_deblock_job* jobs, int64_t n);
 
+/* ---- cuTree / ingest / ssim-rd entries (SURVEY.md 8f-4 and the rest of the pointer table) -------------------------------
+ * propagateCost = estimateCUPropagateCost (primitives.h:360; pixel.cpp:914-940), fix8Pack / fix8Unpack (pixel.cpp:943-956):
+ * IEEE double arithmetic in the reference's operation order (no FMA contraction), x86 double -> int conversion semantics. */
+int x265b200_propagate_cost_dev(x265b200_ctx* ctx, int* dst, const uint16_t* propagateIn, const int32_t* intraCosts, const uint16_t* interCosts,
+                                const int32_t* invQscales, double fpsFactor, int64_t len);
+int x265b200_fix8_pack_dev(x265b200_ctx* ctx, uint16_t* dst, const double* src, int64_t count);
+int x265b200_fix8_unpack_dev(x265b200_ctx* ctx, double* dst, const uint16_t* src, int64_t count);
+/* planecopy_cp (uint8 source, << shift), planecopy_sp ((uint16 >> shift) & mask), planecopy_sp_shl ((uint16 << shift) & mask),
+ * planecopy_pp_shr (pixel >> shift) (primitives.h:332-335; pixel.cpp:864-910); strides in elements of each side's own type */
+enum { X265B200_PC_CP = 0, X265B200_PC_SP, X265B200_PC_SP_SHL, X265B200_PC_PP_SHR };
+int x265b200_planecopy_dev(x265b200_ctx* ctx, int mode, int depth, const void* src, int64_t srcStride, void* dst, int64_t dstStride,
+                           int width, int height, int shift, int mask);
+/* cu[].ssimDist (ssimDist_c<log2TrSize>, pixel.cpp:958-981) and cu[].normFact (normFact_c, :983-994) over n blocks */
+int x265b200_ssim_dist_dev(x265b200_ctx* ctx, int depth, int log2TrSize, const void* fenc, int64_t fStride, const void* recon, int64_t rStride,
+                           const int64_t* offF, const int64_t* offR, int64_t n, int shift, uint64_t* ssBlock, uint64_t* ac_k);
+int x265b200_norm_fact_dev(x265b200_ctx* ctx, int depth, const void* src, const int64_t* off, int64_t n, int blockSize, int shift, uint64_t* z_k);
+
 /* ---- intra prediction: replaces cu[].intra_pred[35] / intra_filter / intra_pred_allangs
  *      (primitives.h:143-145,304-306; intrapred.cpp:31-234).  Neighbour arrays use the reference
  *      layout [topLeft, top 2N, left 2N] (4N+1 pixels).  log2N = 2..5. */

@@ -539,6 +539,65 @@ void deblock_run(int chroma, pixel* src, intptr_t srcStep, intptr_t offset, int 
 void pel_filter_luma_thunk(pixel* src, intptr_t srcStep, intptr_t offset, int32_t tcP, int32_t tcQ) { deblock_run(0, src, srcStep, offset, -4, 3, tcP, tcQ, 0); }
 void pel_filter_chroma_thunk(pixel* src, intptr_t srcStep, intptr_t offset, int32_t tc, int32_t maskP, int32_t maskQ) { deblock_run(1, src, srcStep, offset, -2, 1, tc, maskP, maskQ); }
 
+// ---- cuTree / ingest / ssim-rd (pixel.cpp:864-994) -----------------------------------------------------------------------
+void propagate_cost_thunk(int* dst, const uint16_t* propagateIn, const int32_t* intraCosts, const uint16_t* interCosts,
+                          const int32_t* invQscales, const double* fpsFactor, int len)
+{
+    if (len <= 0) return;
+    void* dP = up1d(0, propagateIn, (size_t)len * 2); void* dI = up1d(1, intraCosts, (size_t)len * 4);
+    void* dE = up1d(2, interCosts, (size_t)len * 2);  void* dQ = up1d(3, invQscales, (size_t)len * 4);
+    void* dD = dev(4, (size_t)len * 4);
+    CK(x265b200_propagate_cost_dev(C(), (int*)dD, (const uint16_t*)dP, (const int32_t*)dI, (const uint16_t*)dE, (const int32_t*)dQ, *fpsFactor, len));
+    CK(x265b200_download(C(), dst, dD, (size_t)len * 4));
+}
+void fix8_pack_thunk(uint16_t* dst, double* src, int count)
+{
+    if (count <= 0) return;
+    void* dS = up1d(0, src, (size_t)count * 8); void* dD = dev(1, (size_t)count * 2);
+    CK(x265b200_fix8_pack_dev(C(), (uint16_t*)dD, (const double*)dS, count));
+    CK(x265b200_download(C(), dst, dD, (size_t)count * 2));
+}
+void fix8_unpack_thunk(double* dst, uint16_t* src, int count)
+{
+    if (count <= 0) return;
+    void* dS = up1d(0, src, (size_t)count * 2); void* dD = dev(1, (size_t)count * 8);
+    CK(x265b200_fix8_unpack_dev(C(), (double*)dD, (const uint16_t*)dS, count));
+    CK(x265b200_download(C(), dst, dD, (size_t)count * 8));
+}
+void planecopy_run(int mode, const void* src, intptr_t srcStride, int ses, pixel* dst, intptr_t dstStride, int width, int height, int shift, int mask)
+{
+    if (width <= 0 || height <= 0) return;
+    void* dS = up_span(0, src, srcStride, width, height, ses);
+    void* dD = dev(1, (size_t)width * height * PX);
+    CK(x265b200_planecopy_dev(C(), mode, X265_DEPTH, dS, srcStride, dD, width, width, height, shift, mask));
+    down2d(dst, dstStride, dD, width, height, PX);
+}
+void planecopy_cp_thunk(const uint8_t* src, intptr_t srcStride, pixel* dst, intptr_t dstStride, int width, int height, int shift)
+{ planecopy_run(X265B200_PC_CP, src, srcStride, 1, dst, dstStride, width, height, shift, 0); }
+void planecopy_sp_thunk(const uint16_t* src, intptr_t srcStride, pixel* dst, intptr_t dstStride, int width, int height, int shift, uint16_t mask)
+{ planecopy_run(X265B200_PC_SP, src, srcStride, 2, dst, dstStride, width, height, shift, mask); }
+void planecopy_sp_shl_thunk(const uint16_t* src, intptr_t srcStride, pixel* dst, intptr_t dstStride, int width, int height, int shift, uint16_t mask)
+{ planecopy_run(X265B200_PC_SP_SHL, src, srcStride, 2, dst, dstStride, width, height, shift, mask); }
+void planecopy_pp_shr_thunk(const pixel* src, intptr_t srcStride, pixel* dst, intptr_t dstStride, int width, int height, int shift)
+{ planecopy_run(X265B200_PC_PP_SHR, src, srcStride, PX, dst, dstStride, width, height, shift, 0); }
+template<int LOG2>
+void ssim_dist_thunk(const pixel* fenc, uint32_t fStride, const pixel* recon, intptr_t rstride, uint64_t* ssBlock, int shift, uint64_t* ac_k)
+{
+    const int N = 1 << LOG2;
+    void* dF = up_span(0, fenc, fStride, N, N, PX); void* dR = up_span(1, recon, rstride, N, N, PX);
+    int64_t zero = 0; void* dOff = up1d(2, &zero, 8); uint64_t* dO = (uint64_t*)dev(3, 16);
+    CK(x265b200_ssim_dist_dev(C(), X265_DEPTH, LOG2, dF, fStride, dR, rstride, (const int64_t*)dOff, (const int64_t*)dOff, 1, shift, dO, dO + 1));
+    uint64_t r[2]; CK(x265b200_download(C(), r, dO, 16));
+    *ssBlock = r[0]; *ac_k = r[1];
+}
+void norm_fact_thunk(const pixel* src, uint32_t blockSize, int shift, uint64_t* z_k)
+{
+    void* dS = up1d(0, src, (size_t)blockSize * blockSize * PX);
+    int64_t zero = 0; void* dOff = up1d(1, &zero, 8); void* dO = dev(2, 8);
+    CK(x265b200_norm_fact_dev(C(), X265_DEPTH, dS, (const int64_t*)dOff, 1, (int)blockSize, shift, (uint64_t*)dO));
+    CK(x265b200_download(C(), z_k, dO, 8));
+}
+
 } // namespace
 
 namespace X265_NS {
@@ -711,6 +770,15 @@ void setupAssemblyPrimitives(EncoderPrimitives& p, int /*cpuMask: SIMD flags are
     p.sign = sign_thunk;
     p.pelFilterLumaStrong[0] = pel_filter_luma_thunk; p.pelFilterLumaStrong[1] = pel_filter_luma_thunk;
     p.pelFilterChroma[0] = pel_filter_chroma_thunk;   p.pelFilterChroma[1] = pel_filter_chroma_thunk;
+
+    // cuTree propagation / fixed-point packing, picture ingest copies, --ssim-rd sums (pixel.cpp:1337-1357)
+    p.propagateCost = propagate_cost_thunk; p.fix8Pack = fix8_pack_thunk; p.fix8Unpack = fix8_unpack_thunk;
+    p.planecopy_cp = planecopy_cp_thunk; p.planecopy_sp = planecopy_sp_thunk; p.planecopy_sp_shl = planecopy_sp_shl_thunk;
+    p.planecopy_pp_shr = planecopy_pp_shr_thunk;
+    p.cu[BLOCK_4x4].ssimDist = ssim_dist_thunk<2>; p.cu[BLOCK_8x8].ssimDist = ssim_dist_thunk<3>; p.cu[BLOCK_16x16].ssimDist = ssim_dist_thunk<4>;
+    p.cu[BLOCK_32x32].ssimDist = ssim_dist_thunk<5>; p.cu[BLOCK_64x64].ssimDist = ssim_dist_thunk<6>;
+    p.cu[BLOCK_8x8].normFact = norm_fact_thunk; p.cu[BLOCK_16x16].normFact = norm_fact_thunk;
+    p.cu[BLOCK_32x32].normFact = norm_fact_thunk; p.cu[BLOCK_64x64].normFact = norm_fact_thunk;
 }
 
 } // namespace X265_NS

@@ -89,6 +89,12 @@ int sao_stats_dev(Ctx*, int kind, int depth, const int16_t* diff, const void* re
                   int8_t* signBuf, int32_t* stats, int32_t* count);
 int sign_dev(Ctx*, int depth, int8_t* dst, const void* src1, const void* src2, int64_t n);
 int deblock_dev(Ctx*, int chroma, int depth, void* pic, const x265b200_deblock_job* jobs, int64_t n);
+int propagate_cost_dev(Ctx*, int* dst, const uint16_t* propagateIn, const int32_t* intraCosts, const uint16_t* interCosts, const int32_t* invQscales, double fpsFactor, int64_t len);
+int fix8_dev(Ctx*, int unpack, void* dst, const void* src, int64_t n);
+int planecopy_dev(Ctx*, int mode, int depth, const void* src, int64_t srcStride, void* dst, int64_t dstStride, int width, int height, int shift, int mask);
+int ssim_dist_dev(Ctx*, int depth, int log2TrSize, const void* fenc, int64_t fStride, const void* recon, int64_t rStride, const int64_t* offF, const int64_t* offR,
+                  int64_t n, int shift, uint64_t* ssBlock, uint64_t* ack);
+int norm_fact_dev(Ctx*, int depth, const void* src, const int64_t* off, int64_t n, int blockSize, int shift, uint64_t* zk);
 int intra_pred_dev(Ctx*, int depth, int log2N, const void* nbr, void* dst, int64_t dstStride, const x265b200_intra_job* jobs, int64_t n);
 int intra_filter_dev(Ctx*, int depth, int log2N, const void* src, void* dst, int64_t n);
 int intra_allangs_dev(Ctx*, int depth, int log2N, const void* refPix, const void* filtPix, void* dest, int bLuma, int64_t n);
@@ -378,6 +384,31 @@ int x265b200_deblock_dev(x265b200_ctx* ctx, int chroma, int depth, void* pic, co
 {
     REQUIRE_CTX(ctx);
     return deblock_dev(CTX(ctx), chroma, depth, pic, jobs, n);
+}
+int x265b200_propagate_cost_dev(x265b200_ctx* ctx, int* dst, const uint16_t* propagateIn, const int32_t* intraCosts, const uint16_t* interCosts,
+                                const int32_t* invQscales, double fpsFactor, int64_t len)
+{
+    REQUIRE_CTX(ctx);
+    return propagate_cost_dev(CTX(ctx), dst, propagateIn, intraCosts, interCosts, invQscales, fpsFactor, len);
+}
+int x265b200_fix8_pack_dev(x265b200_ctx* ctx, uint16_t* dst, const double* src, int64_t count) { REQUIRE_CTX(ctx); return fix8_dev(CTX(ctx), 0, dst, src, count); }
+int x265b200_fix8_unpack_dev(x265b200_ctx* ctx, double* dst, const uint16_t* src, int64_t count) { REQUIRE_CTX(ctx); return fix8_dev(CTX(ctx), 1, dst, src, count); }
+int x265b200_planecopy_dev(x265b200_ctx* ctx, int mode, int depth, const void* src, int64_t srcStride, void* dst, int64_t dstStride,
+                           int width, int height, int shift, int mask)
+{
+    REQUIRE_CTX(ctx);
+    return planecopy_dev(CTX(ctx), mode, depth, src, srcStride, dst, dstStride, width, height, shift, mask);
+}
+int x265b200_ssim_dist_dev(x265b200_ctx* ctx, int depth, int log2TrSize, const void* fenc, int64_t fStride, const void* recon, int64_t rStride,
+                           const int64_t* offF, const int64_t* offR, int64_t n, int shift, uint64_t* ssBlock, uint64_t* ac_k)
+{
+    REQUIRE_CTX(ctx);
+    return ssim_dist_dev(CTX(ctx), depth, log2TrSize, fenc, fStride, recon, rStride, offF, offR, n, shift, ssBlock, ac_k);
+}
+int x265b200_norm_fact_dev(x265b200_ctx* ctx, int depth, const void* src, const int64_t* off, int64_t n, int blockSize, int shift, uint64_t* z_k)
+{
+    REQUIRE_CTX(ctx);
+    return norm_fact_dev(CTX(ctx), depth, src, off, n, blockSize, shift, z_k);
 }
 int x265b200_intra_pred_dev(x265b200_ctx* ctx, int depth, int log2N, const void* nbr, void* dst, int64_t dstStride, const x265b200_intra_job* jobs, int64_t n)
 {
