@@ -331,7 +331,8 @@ def main():
     sad_events = []
     me_events = []
 
-    def hot_path(t, time_sad=False):
+    def hot_path(t, time_sad=False, out=None):
+        out = me_out if out is None else out
         cur = ring[t % NF]
         refs = [ring[(t - 1 - r) % NF] for r in range(NREF)]
         ref_ptrs = ref_ptr_table[t % NF]
@@ -347,7 +348,7 @@ def main():
         if time_sad:
             m0 = torch.cuda.Event(enable_timing=True); m1 = torch.cuda.Event(enable_timing=True); m0.record()
         ctx.me_frame_dev(8, cptr, STRIDE, [P(r) + origin for r in refs], STRIDE, PAD, PAD, ROWS, CTU_COLS, CTU_ROWS, 15, None,
-                         pkg.ME_HEX, SUBME, MERANGE, lam, P(me_out))
+                         pkg.ME_HEX, SUBME, MERANGE, lam, P(out))
         if time_sad:
             m1.record(); me_events.append((m0, m1))
         # 3. MC: one 8-tap interpolation per PU and level from reference 0 (HPP / VPP / HVPP by fraction)
@@ -375,18 +376,42 @@ def main():
         gathered = torch.empty((world * ROWS, STRIDE), dtype=torch.uint8, device=dev)   # concatenated form
         res_all = [torch.empty((njobs, 3), dtype=torch.int32, device=dev) for _ in range(world)] if rank == 0 else None
 
-    def exchange(t):
+    def exchange(t, out=None):
         if world == 1:
             return
         dist.all_gather_into_tensor(gathered, ring[t % NF])
-        dist.gather(me_out, res_all, dst=0)
+        dist.gather(me_out if out is None else out, res_all, dst=0)
 
-    def e2e_step(t):
-        ring[t % NF].copy_(pinned[t % NF], non_blocking=True)                   # H2D: the new frame
-        hot_path(t)
-        exchange(t)
-        res_h.copy_(me_out, non_blocking=True)                                   # D2H: {mvx, mvy, cost} per PU
-        stream.synchronize()
+    # end-to-end: every step uploads its frame from pinned host memory and reads its {mv,cost} results back.  The copies run on
+    # a second stream so that the upload of frame t+1 and the read-back of step t overlap the kernels of the neighbouring step
+    # (double-buffered result arrays); every copy of every step is inside the timed region.
+    copy_stream = torch.cuda.Stream(device=local)
+    out2 = [me_out, torch.empty_like(me_out)]
+    res_h2 = [res_h, torch.empty((njobs, 3), dtype=torch.int32).pin_memory()]
+
+    def e2e_run(first, count):
+        def upload(t):
+            with torch.cuda.stream(copy_stream):
+                ring[t % NF].copy_(pinned[t % NF], non_blocking=True)           # H2D: the new frame
+                ev = torch.cuda.Event(); ev.record(copy_stream)
+            return ev
+        ev_next = upload(first)
+        d2h_ev = [None, None]
+        for i in range(count):
+            t, k = first + i, i & 1
+            stream.wait_event(ev_next)
+            if i + 1 < count:
+                ev_next = upload(t + 1)
+            if d2h_ev[k] is not None:
+                stream.wait_event(d2h_ev[k])                                     # result buffer k has been read back
+            hot_path(t, out=out2[k])
+            exchange(t, out=out2[k])
+            done = torch.cuda.Event(); done.record(stream)
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(done)
+                res_h2[k].copy_(out2[k], non_blocking=True)                     # D2H: {mvx, mvy, cost} per PU
+                d2h_ev[k] = torch.cuda.Event(); d2h_ev[k].record(copy_stream)
+        torch.cuda.synchronize()
 
     def barrier():
         torch.cuda.synchronize()
@@ -463,12 +488,10 @@ def main():
     del dct_graph, resid_ring, coef_ring
 
     # ---- end-to-end timing (host buffers in, results out) ---------------------------------------------------
-    for i in range(2):
-        e2e_step(NREF + i)
+    e2e_run(NREF, 2)
     barrier()
     t0 = time.perf_counter()
-    for i in range(args.steps):
-        e2e_step(NREF + i)
+    e2e_run(NREF, args.steps)
     barrier()
     e2e_s = time.perf_counter() - t0
     sampler.stop_flag = True; sampler.join(timeout=2)
