@@ -393,6 +393,26 @@ int x265b200_la_estimate_dev(x265b200_ctx* ctx, int depth, const void* const* pl
                              const int32_t* const* invQscale, uint16_t* lowresCosts, int32_t* rowSatds, int32_t* sums,
                              double lambda, int maxSlices);
 
+/* --hme (hierarchical ME, param bEnableHME): estimateFrameCost first runs estimateCUCost(..., hme = true) over the
+ * quarter-resolution planes (Lowres::lowerResPlane[4], built by primitives.frameInitLowerRes + extendPicBorder,
+ * lowres.cpp:304-313 -- use x265b200_lowres_init_dev on lowresPlane[0]) with hmeSearchMethod[0] / hmeRange[0], then the
+ * 8x8 level with hmeSearchMethod[1] / hmeRange[1] and the doubled quarter-resolution MV as one more candidate
+ * (slicetype.cpp:3177-3188, :3216-3325; motion.cpp:751-754,817).  lowerPlanes = device array [numFrames][4] of plane
+ * origins (row pitch lowerStride = lumaStride / 2); width4 x height4 = Lookahead::m_4x4Width x m_4x4Height
+ * (slicetype.cpp:979-980); lowerMvPool / lowerMvCostPool = lowerResMvs / lowerResMvCosts, same slot numbering as mvPool
+ * with width4*height4 entries per slot.  Everything else as x265b200_la_estimate_dev. */
+typedef struct {
+    const void* const* lowerPlanes; int64_t lowerStride;
+    int32_t width4, height4;
+    int32_t* lowerMvPool; int32_t* lowerMvCostPool;
+    int32_t searchMethod[2];       /* hmeSearchMethod[0], [1] (x265.h:492-497 numbering; defaults HEX, UMH) */
+    int32_t range[2];              /* hmeRange[0], [1] (defaults 16, 32) */
+} x265b200_la_hme;
+int x265b200_la_estimate_hme_dev(x265b200_ctx* ctx, int depth, const void* const* planes, int64_t stride, int widthInCU, int heightInCU,
+                                 const x265b200_la_hme* hme, const x265b200_la_triple* triplesHost, int numTriples, int32_t* mvPool, int32_t* mvCostPool,
+                                 const int32_t* const* intraCost, const int32_t* const* invQscale, uint16_t* lowresCosts,
+                                 int32_t* rowSatds, int32_t* sums, double lambda, int maxSlices);
+
 #ifdef __cplusplus
 }
 #endif

@@ -397,7 +397,11 @@ struct RefLA
 
 extern "C" {
 
-void* ref_la_create(int width, int height, int bframes, int aq)
+static void* la_create(int width, int height, int bframes, int aq, int hme);
+void* ref_la_create(int width, int height, int bframes, int aq) { return la_create(width, height, bframes, aq, 0); }
+/* --hme with the defaults of x265_param_default (hmeSearchMethod = hex, umh, umh; hmeRange = 16, 32, 48) */
+void* ref_la_create_hme(int width, int height, int bframes, int aq) { return la_create(width, height, bframes, aq, 1); }
+static void* la_create(int width, int height, int bframes, int aq, int hme)
 {
     ensure_init();
     RefLA* h = new RefLA;
@@ -409,7 +413,7 @@ void* ref_la_create(int width, int height, int bframes, int aq)
     h->param->bframes = bframes;
     h->param->bEnableWeightedPred = 0; h->param->bEnableWeightedBiPred = 0;
     h->param->lookaheadSlices = 0;
-    h->param->bEnableHME = 0;
+    h->param->bEnableHME = hme;
     h->param->rc.aqMode = aq ? X265_AQ_VARIANCE : X265_AQ_NONE;
     h->param->rc.cuTree = 0;
     h->param->logLevel = X265_LOG_NONE;
@@ -475,6 +479,19 @@ const uint16_t* ref_la_lowres_costs(void* hv, int b, int d0, int d1) { return ((
 const int32_t* ref_la_row_satds(void* hv, int b, int d0, int d1) { return ((RefLA*)hv)->lowres[b]->rowSatds[d0][d1]; }
 int64_t ref_la_cost_est(void* hv, int b, int d0, int d1, int aq) { Lowres* l = ((RefLA*)hv)->lowres[b]; return aq ? l->costEstAq[d0][d1] : l->costEst[d0][d1]; }
 int ref_la_intra_mbs(void* hv, int b, int d0) { return ((RefLA*)hv)->lowres[b]->intraMbs[d0]; }
+
+/* --hme: geometry out[0] = m_4x4Width, [1] = m_4x4Height, [2] = hmeSearchMethod[0], [3] = [1], [4] = hmeRange[0], [5] = [1],
+ * [6] = element offset of lowerResPlane[0] inside lowerResBuffer[0], [7] = elements between consecutive lower-res planes */
+void ref_la_hme_geometry(void* hv, int64_t* out)
+{
+    RefLA* h = (RefLA*)hv; Lowres* lr = h->lowres[0];
+    out[0] = h->la->m_4x4Width; out[1] = h->la->m_4x4Height;
+    out[2] = h->param->hmeSearchMethod[0]; out[3] = h->param->hmeSearchMethod[1]; out[4] = h->param->hmeRange[0]; out[5] = h->param->hmeRange[1];
+    out[6] = lr->lowerResPlane[0] - lr->lowerResBuffer[0]; out[7] = lr->lowerResBuffer[1] - lr->lowerResBuffer[0];
+}
+const void* ref_la_lower_buffer(void* hv, int idx) { return ((RefLA*)hv)->lowres[idx]->lowerResBuffer[0]; }
+const int32_t* ref_la_lower_mvs(void* hv, int b, int list, int dist) { return (const int32_t*)((RefLA*)hv)->lowres[b]->lowerResMvs[list][dist]; }
+const int32_t* ref_la_lower_mvcosts(void* hv, int b, int list, int dist) { return ((RefLA*)hv)->lowres[b]->lowerResMvCosts[list][dist]; }
 
 void ref_la_destroy(void* hv)
 {

@@ -164,3 +164,119 @@ def test_lookahead_matches_reference(ctx, depth, W, H, aq):
         for bb in (dLC, dRS, dSm):
             bb.free()
     R.ref_la_destroy(h)
+
+
+@pytest.mark.parametrize("depth,W,H", [(8, 320, 192), (8, 424, 240), (10, 320, 192)])
+def test_lookahead_hme_matches_reference(ctx, depth, W, H):
+    """--hme: quarter-resolution planes (frameInitLowerRes + borders), the level-0 search (lowerResMvs / lowerResMvCosts) and the
+    8x8 level with hmeSearchMethod[1] (UMH) / hmeRange[1] and the extra doubled candidate -- all against the reference's own
+    Lookahead with bEnableHME = 1.  424 wide makes m_4x4Width differ from m_8x8Width / 2 (the candidate index pitch quirk)."""
+    R = oracle.ref(depth)
+    assert R is not None, "oracle/_ref missing"
+    _bind(R)
+    R.ref_la_create_hme.restype = ctypes.c_void_p
+    for f in ("ref_la_lower_buffer", "ref_la_lower_mvs", "ref_la_lower_mvcosts"):
+        getattr(R, f).restype = ctypes.c_void_p
+    NF, BF = 4, 2
+    h = ctypes.c_void_p(R.ref_la_create_hme(W, H, BF, 0))
+    frames = _frames(W, H, NF, depth, seed=7 * W + depth)
+    for f in frames:
+        R.ref_la_add_frame(h, ctypes.c_void_p(f.ctypes.data), ctypes.c_ssize_t(W))
+    g = (ctypes.c_int64 * 11)()
+    R.ref_la_geometry(h, g)
+    lw, ll, ls, mx, my, wcu, hcu, fs, fmx, fmy, frows = [int(v) for v in g]
+    hg = (ctypes.c_int64 * 8)()
+    R.ref_la_hme_geometry(h, hg)
+    w4, h4, m0, m1, r0, r1, lowOff, lowPlane = [int(v) for v in hg]
+    ncu, n4 = wcu * hcu, w4 * h4
+    dt = pdtype(depth)
+    px = np.dtype(dt).itemsize
+    ct = ctypes.c_uint8 if depth == 8 else ctypes.c_uint16
+    planesize, padoff = ls * (ll + 2 * my), ls * my + mx
+    ls2, lw2, ll2, mx2, my2 = ls // 2, lw // 2, ll // 2, mx // 2, my // 2
+    rows2 = ll2 + 2 * my2 + 8
+    plane2size, pad2 = ls2 * rows2, ls2 * my2 + mx2
+
+    plane_ptrs = np.zeros((NF, 4), dtype=np.int64)
+    lower_ptrs = np.zeros((NF, 4), dtype=np.int64)
+    keep = []
+    for i in range(NF):
+        full = _arr(R.ref_la_fullres_buffer(h, i), ct, (fs * frows,))
+        dFull = ctx.to_device(full)
+        bufs = [ctx.to_device(np.zeros(planesize, dtype=dt)) for _ in range(4)]
+        ctx.lowres_init_dev(depth, dFull.ptr + (fmy * fs + fmx) * px, fs, [b.ptr + padoff * px for b in bufs], ls, lw, ll, mx, my)
+        low = [ctx.to_device(np.zeros(plane2size, dtype=dt)) for _ in range(4)]
+        # Lowres::init, lowres.cpp:304-313: frameInitLowerRes(lowresPlane[0], ..., lumaStride, lumaStride/2, width/2, lines/2) + extendPicBorder
+        ctx.lowres_init_dev(depth, bufs[0].ptr + padoff * px, ls, [b.ptr + pad2 * px for b in low], ls2, lw2, ll2, mx2, my2)
+        ref_low = _arr(R.ref_la_lower_buffer(h, i), ct, (4 * lowPlane,))
+        for k in range(4):
+            plane_ptrs[i, k] = bufs[k].ptr + padoff * px
+            lower_ptrs[i, k] = low[k].ptr + pad2 * px
+            got = low[k].download(dt).reshape(rows2, ls2)
+            for r in (-my2, -1, 0, ll2 // 2, ll2 - 1, ll2 + my2 - 1):
+                e = ref_low[k * lowPlane + lowOff + r * ls2 - mx2: k * lowPlane + lowOff + r * ls2 + lw2 + mx2]
+                assert np.array_equal(got[my2 + r, :lw2 + 2 * mx2], e), ("lower-res plane", i, k, r)
+        keep += bufs + low
+        dFull.free()
+    dPlanePtrs, dLowerPtrs = ctx.to_device(plane_ptrs), ctx.to_device(lower_ptrs)
+
+    lam = pkg.lambda_for_qp(12 + 6 * (depth - 8), depth)
+    intraPenalty = 5 * int(lam)
+    intra_ptrs = np.zeros(NF, dtype=np.int64)
+    for i in range(NF):
+        R.ref_la_intra(h, i)
+        dIC, dIM, dLC, dRS, dSm = ctx.empty(ncu * 4), ctx.empty(ncu), ctx.empty(ncu * 2), ctx.empty(hcu * 4), ctx.empty(8)
+        ctx.la_intra_dev(depth, plane_ptrs[i, 0], ls, wcu, hcu, None, intraPenalty, dIC, dIM, dLC, dRS, dSm)
+        intra_ptrs[i] = dIC.ptr
+        keep += [dIC, dIM, dLC, dRS, dSm]
+    dIntraPtrs = ctx.to_device(intra_ptrs)
+
+    def slot(b, lst, dist):
+        return (b * 2 + lst) * (BF + 2) + dist
+    nslots = NF * 2 * (BF + 2)
+    dMv, dMvC = ctx.to_device(np.zeros(nslots * ncu * 2, dtype=np.int32)), ctx.to_device(np.zeros(nslots * ncu, dtype=np.int32))
+    dMv4, dMvC4 = ctx.to_device(np.zeros(nslots * n4 * 2, dtype=np.int32)), ctx.to_device(np.zeros(nslots * n4, dtype=np.int32))
+    hme = pkg.LA_HME(dLowerPtrs.ptr, ls2, w4, h4, dMv4.ptr, dMvC4.ptr, (ctypes.c_int32 * 2)(m0, m1), (ctypes.c_int32 * 2)(r0, r1))
+    assert (m0, m1, r0, r1) == (pkg.ME_HEX, pkg.ME_UMH, 16, 32)
+    searched = set()
+    for wave in ([(0, 3, 1), (0, 3, 2), (0, 3, 3)], [(0, 2, 1), (1, 3, 2), (2, 3, 3)]):
+        tr = np.zeros(len(wave), dtype=pkg.LA_TRIPLE)
+        for t, (p0, p1, b) in enumerate(wave):
+            tr[t]["b"], tr[t]["p0"], tr[t]["p1"] = b, p0, p1
+            for lst, dist in ((0, b - p0), (1, p1 - b)):
+                key = (b, lst, dist)
+                tr[t]["mvSlot"][lst] = slot(*key)
+                need = key not in searched and (lst == 0 or p1 > b)
+                tr[t]["doSearch"][lst] = int(need)
+                if need:
+                    searched.add(key)
+            R.ref_la_frame_cost(h, p0, p1, b, 0)
+        dLC, dRS, dSm = ctx.empty(len(wave) * ncu * 2), ctx.empty(len(wave) * hcu * 4), ctx.empty(len(wave) * 16)
+        ctx.la_estimate_hme_dev(depth, dPlanePtrs, ls, wcu, hcu, hme, tr, dMv, dMvC, dIntraPtrs, None, dLC, dRS, dSm, lam)
+        lc = dLC.download(np.uint16).reshape(len(wave), ncu)
+        sm = dSm.download(np.int32).reshape(len(wave), 4)
+        mv, mvc = dMv.download(np.int32).reshape(nslots, ncu, 2), dMvC.download(np.int32).reshape(nslots, ncu)
+        mv4, mvc4 = dMv4.download(np.int32).reshape(nslots, n4, 2), dMvC4.download(np.int32).reshape(nslots, n4)
+        for t, (p0, p1, b) in enumerate(wave):
+            for lst, dist in ((0, b - p0), (1, p1 - b)):
+                if lst == 1 and p1 == b:
+                    continue
+                s_ = slot(b, lst, dist)
+                e4 = _arr(R.ref_la_lower_mvs(h, b, lst, dist), ctypes.c_int32, (n4, 2))
+                c4 = _arr(R.ref_la_lower_mvcosts(h, b, lst, dist), ctypes.c_int32, (n4,))
+                bad = np.nonzero((mv4[s_] != e4).any(axis=1) | (mvc4[s_] != c4))[0]
+                assert not len(bad), ("level-0 MV/cost", wave[t], lst, int(bad[0]), mv4[s_][bad[0]].tolist(), e4[bad[0]].tolist(), len(bad))
+                emv = _arr(R.ref_la_mvs(h, b, lst, dist), ctypes.c_int32, (ncu, 2))
+                emc = _arr(R.ref_la_mvcosts(h, b, lst, dist), ctypes.c_int32, (ncu,))
+                bad = np.nonzero((mv[s_] != emv).any(axis=1) | (mvc[s_] != emc))[0]
+                assert not len(bad), ("MV/cost", wave[t], lst, int(bad[0]), mv[s_][bad[0]].tolist(), emv[bad[0]].tolist(), len(bad))
+            assert np.array_equal(lc[t], _arr(R.ref_la_lowres_costs(h, b, b - p0, p1 - b), ctypes.c_uint16, (ncu,))), ("lowresCosts", wave[t])
+            score = int(sm[t][0])
+            if b != p1:
+                score = score * 100 // 130
+            assert score == R.ref_la_cost_est(h, b, b - p0, p1 - b, 0), ("costEst", wave[t])
+        for bb in (dLC, dRS, dSm):
+            bb.free()
+    for b in keep + [dPlanePtrs, dLowerPtrs, dIntraPtrs, dMv, dMvC, dMv4, dMvC4]:
+        b.free()
+    R.ref_la_destroy(h)

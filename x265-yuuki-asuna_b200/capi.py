@@ -462,3 +462,22 @@ def _ctx_mc_dev(self, depth, desc, dJobs, n, bLuma=1, bChroma=1):
 
 
 Ctx.mc_dev = _ctx_mc_dev
+
+
+# ---- --hme lookahead ----------------------------------------------------------------------------------
+class LA_HME(ctypes.Structure):
+    """x265b200_la_hme (include/x265b200.h)"""
+    _fields_ = [("lowerPlanes", ctypes.c_void_p), ("lowerStride", ctypes.c_int64), ("width4", ctypes.c_int32), ("height4", ctypes.c_int32),
+                ("lowerMvPool", ctypes.c_void_p), ("lowerMvCostPool", ctypes.c_void_p),
+                ("searchMethod", ctypes.c_int32 * 2), ("range", ctypes.c_int32 * 2)]
+
+
+def _ctx_la_estimate_hme_dev(self, depth, dPlanes, stride, wcu, hcu, hme, triples, dMvPool, dMvCostPool, dIntraCostPtrs, dInvQPtrs,
+                             dLowresCosts, dRowSatds, dSums, lam, maxSlices=1):
+    triples = np.ascontiguousarray(triples, dtype=LA_TRIPLE)
+    self._chk(self.L.x265b200_la_estimate_hme_dev(self.h, depth, _vp(dPlanes), _i64(stride), int(wcu), int(hcu), ctypes.byref(hme), _vp(triples),
+                                                  len(triples), _vp(dMvPool), _vp(dMvCostPool), _vp(dIntraCostPtrs), _vp(dInvQPtrs),
+                                                  _vp(dLowresCosts), _vp(dRowSatds), _vp(dSums), ctypes.c_double(lam), int(maxSlices)))
+
+
+Ctx.la_estimate_hme_dev = _ctx_la_estimate_hme_dev

@@ -18,7 +18,9 @@ namespace x265b200 {
 
 constexpr int LAT_WARPS = 2;
 
-template<typename pixel>
+// HME = false: the plain lookahead (search method and range are compile-time constants of the hot kernel);
+// HME = true: either level of --hme (runtime method / range, optional quarter-resolution candidate)
+template<typename pixel, bool HME>
 __global__ void __launch_bounds__(LAT_WARPS * 32)
 la_search_thread_kernel(LASearchArgs p)
 {
@@ -87,7 +89,7 @@ la_search_thread_kernel(LASearchArgs p)
                 s.fref = s.lowres[0]; s.gfref = s.lowres[0]; s.gstride = p.stride;
 
                 // reverse-order MV prediction candidates (slicetype.cpp:3269-3280)
-                int mvc[4][2], numc = 0;
+                int mvc[5][2], numc = 0;
                 if (cuX < W - 1) { mvc[numc][0] = rightX; mvc[numc][1] = rightY; numc++; }
                 if (!lastRow)
                 {
@@ -95,6 +97,14 @@ la_search_thread_kernel(LASearchArgs p)
                     mvc[numc][0] = row[0]; mvc[numc][1] = row[1]; numc++;
                     if (cuX > 0) { mvc[numc][0] = row[-2]; mvc[numc][1] = row[-1]; numc++; }
                     if (cuX < W - 1) { mvc[numc][0] = row[2]; mvc[numc][1] = row[3]; numc++; }
+                }
+                if (HME && p.hmeMvPool)
+                {
+                    // the quarter-resolution MV of the co-located CU, doubled (slicetype.cpp:3281-3284).  Index as written at
+                    // :3228: (cuX / 2) + (cuY / 2) * widthInCU / 2 -- the product is halved, not the width, and the pitch is
+                    // this level's width rather than m_4x4Width
+                    const int64_t i4 = (int64_t)ch.mvSlot * p.hmeNcu + (cuX >> 1) + (((cuY >> 1) * W) >> 1);
+                    if (p.hmeMvCostPool[i4] > 0) { mvc[numc][0] = p.hmeMvPool[i4 * 2] * 2; mvc[numc][1] = p.hmeMvPool[i4 * 2 + 1] * 2; numc++; }
                 }
                 int mvpx = 0, mvpy = 0, skipCost = 0x7fffffff;
                 if (numc)
@@ -110,7 +120,7 @@ la_search_thread_kernel(LASearchArgs p)
                 s.mvpx = mvpx; s.mvpy = mvpy;
                 const MV2 mvmin = mv2(-cuX * 8 - 8, -cuY * 8 - 8), mvmax = mv2((W - cuX - 1) * 8 + 8, (Hc - cuY - 1) * 8 + 8);
                 int ox, oy;
-                int fencCost = motion_estimate<pixel>(s, mvmin, mvmax, mv2(mvpx, mvpy), 0, nullptr, p.merange, ME_HEX, 1, p.maxSlices, 0, ox, oy);
+                int fencCost = motion_estimate<pixel>(s, mvmin, mvmax, mv2(mvpx, mvpy), 0, nullptr, p.merange, HME ? p.searchMethod : (int)ME_HEX, 1, p.maxSlices, 0, ox, oy);
                 if (skipCost < 64 && skipCost < fencCost && ch.bBidir) { fencCost = skipCost; ox = 0; oy = 0; }
                 rightX = ox; rightY = oy;
                 mvs[cuXY * 2] = ox; mvs[cuXY * 2 + 1] = oy; mvcosts[cuXY] = fencCost;
@@ -132,8 +142,13 @@ int la_search_thread_launch(Ctx* ctx, int depth, const LASearchArgs& a)
     int64_t blocksWanted = (items + LAT_WARPS - 1) / LAT_WARPS;
     int64_t cap = (int64_t)ctx->smCount * 8;
     unsigned blocks = (unsigned)(blocksWanted < cap ? blocksWanted : cap);
-    if (depth > 8) la_search_thread_kernel<uint16_t><<<blocks, LAT_WARPS * 32, 0, ctx->stream>>>(a);
-    else           la_search_thread_kernel<uint8_t><<<blocks, LAT_WARPS * 32, 0, ctx->stream>>>(a);
+    if (a.hme)
+    {
+        if (depth > 8) la_search_thread_kernel<uint16_t, true><<<blocks, LAT_WARPS * 32, 0, ctx->stream>>>(a);
+        else           la_search_thread_kernel<uint8_t, true><<<blocks, LAT_WARPS * 32, 0, ctx->stream>>>(a);
+    }
+    else if (depth > 8) la_search_thread_kernel<uint16_t, false><<<blocks, LAT_WARPS * 32, 0, ctx->stream>>>(a);
+    else                la_search_thread_kernel<uint8_t, false><<<blocks, LAT_WARPS * 32, 0, ctx->stream>>>(a);
     ctx->launches++;
     return check(cudaGetLastError(), "la_search (per-thread) launch");
 }

@@ -18,6 +18,13 @@ struct LASearchArgs
     int* progress;                 // [numChains][heightInCU], zeroed
     int* workCounter;              // zeroed
     const uint16_t* cost;
+    // --hme (slicetype.cpp:3216-3325 with bEnableHME): the search method / range of this level (hmeSearchMethod[],
+    // hmeRange[]) and, for the 8x8 level, the quarter-resolution result that becomes one more MV candidate (:3281-3284)
+    int hme;                       // 0: plain lookahead (HEX, s_merange)
+    int searchMethod;
+    const int32_t* hmeMvPool;      // [slot][hmeNcu][2] lowerResMvs, or nullptr (the quarter-resolution level itself)
+    const int32_t* hmeMvCostPool;  // [slot][hmeNcu]    lowerResMvCosts
+    int hmeNcu;
 };
 
 int la_search_thread_launch(Ctx* ctx, int depth, const LASearchArgs& a);

@@ -464,9 +464,16 @@ la_finish_kernel(LAFinishArgs p)
 int la_estimate_dev(Ctx* ctx, int depth, const void* const* planes, int64_t stride, int widthInCU, int heightInCU,
                     const x265b200_la_triple* triplesHost, int numTriples,
                     int32_t* mvPool, int32_t* mvCostPool, const int32_t* const* intraCost, const int32_t* const* invQscale,
-                    uint16_t* lowresCosts, int32_t* rowSatds, int32_t* sums, double lambda, int maxSlices)
+                    uint16_t* lowresCosts, int32_t* rowSatds, int32_t* sums, double lambda, int maxSlices, const x265b200_la_hme* hme)
 {
     if (numTriples <= 0) return 0;
+    if (hme)
+    {
+        if (!hme->lowerPlanes || !hme->lowerMvPool || !hme->lowerMvCostPool || hme->width4 <= 0 || hme->height4 <= 0) { set_error("la_estimate: incomplete HME descriptor"); return -1; }
+        for (int l = 0; l < 2; l++)
+            if (hme->searchMethod[l] < 0 || hme->searchMethod[l] > ME_FULL || hme->searchMethod[l] == ME_SEA || hme->range[l] < 1)
+            { set_error("la_estimate: HME level %d search method %d / range %d", l, hme->searchMethod[l], hme->range[l]); return -1; }
+    }
     if (maxSlices > 1) { set_error("la_estimate: maxSlices > 1 is not supported on the lowres path"); return -1; }
     if (ensure_mvcost(ctx, lambda)) return -1;
     void* dTriplesV = nullptr;
@@ -485,7 +492,7 @@ int la_estimate_dev(Ctx* ctx, int depth, const void* const* planes, int64_t stri
     const int numChains = (int)chains.size();
     void* scratch = nullptr;
     size_t chainBytes = ((sizeof(LAChain) * (numChains ? numChains : 1) + 255) / 256) * 256;
-    size_t progBytes = sizeof(int) * ((size_t)numChains * heightInCU + 64);
+    size_t progBytes = sizeof(int) * ((size_t)numChains * heightInCU + 64) * (hme ? 2 : 1);
     if (scratch_dev(ctx, 7, chainBytes + progBytes, &scratch)) return -1;
     LAChain* dChains = (LAChain*)scratch;
     int* dProg = (int*)((char*)scratch + chainBytes);
@@ -496,6 +503,23 @@ int la_estimate_dev(Ctx* ctx, int depth, const void* const* planes, int64_t stri
         LASearchArgs a; a.planes = planes; a.stride = stride; a.chains = dChains; a.numChains = numChains;
         a.widthInCU = widthInCU; a.heightInCU = heightInCU; a.depth = depth; a.merange = 16; a.maxSlices = maxSlices;   // s_merange, slicetype.h:259
         a.mvPool = mvPool; a.mvCostPool = mvCostPool; a.progress = dProg; a.workCounter = dProg + (size_t)numChains * heightInCU; a.cost = ctx->dMvCost;
+        a.hme = 0; a.searchMethod = ME_HEX; a.hmeMvPool = nullptr; a.hmeMvCostPool = nullptr; a.hmeNcu = 0;
+        if (hme)
+        {
+            // level 0 (slicetype.cpp:3177-3188): the same chains over the quarter-resolution planes, hmeSearchMethod[0] / hmeRange[0];
+            // its MVs / costs (lowerResMvs, lowerResMvCosts) feed the 8x8 level, which runs hmeSearchMethod[1] / hmeRange[1]
+            // (motion.cpp:817: isHMELowres selects searchMethodL0 / L1)
+            LASearchArgs h = a;
+            h.planes = hme->lowerPlanes; h.stride = hme->lowerStride; h.widthInCU = hme->width4; h.heightInCU = hme->height4;
+            h.merange = hme->range[0]; h.searchMethod = hme->searchMethod[0]; h.hme = 1;
+            h.mvPool = hme->lowerMvPool; h.mvCostPool = hme->lowerMvCostPool;
+            h.progress = dProg + (size_t)numChains * heightInCU + 64; h.workCounter = h.progress + (size_t)numChains * hme->height4;
+            if (hme->height4 > heightInCU) { set_error("la_estimate: HME level taller than the 8x8 level"); return -1; }
+            X265B200_CHECK(cudaStreamSynchronize(ctx->stream));
+            if (la_search_thread_launch(ctx, depth, h)) return -1;
+            a.hme = 1; a.searchMethod = hme->searchMethod[1]; a.merange = hme->range[1];
+            a.hmeMvPool = hme->lowerMvPool; a.hmeMvCostPool = hme->lowerMvCostPool; a.hmeNcu = hme->width4 * hme->height4;
+        }
         // every claimed row must be able to make progress: rows are claimed bottom-up, so any grid size is deadlock-free
         int64_t rows = (int64_t)numChains * heightInCU;
         int64_t blocksWanted = (rows + LA_WARPS - 1) / LA_WARPS;
@@ -506,6 +530,7 @@ int la_estimate_dev(Ctx* ctx, int depth, const void* const* planes, int64_t stri
         // default: one lane per CU, 32 staggered rows per warp (la_search_thread.cu); X265B200_LA_WARP=1 selects the
         // older one-warp-per-CU kernel (kept for A/B measurements, same results)
         static const bool useWarpKernel = getenv("X265B200_LA_WARP") && atoi(getenv("X265B200_LA_WARP")) != 0;
+        if (useWarpKernel && hme) { set_error("la_estimate: --hme is implemented by the per-thread search kernel only (unset X265B200_LA_WARP)"); return -1; }
         if (!useWarpKernel)
         {
             if (la_search_thread_launch(ctx, depth, a)) return -1;
