@@ -553,8 +553,12 @@ template<> __device__ __forceinline__ void pack4<uint16_t>(const int v[4], uint3
     out[0] = (uint32_t)v[0] | ((uint32_t)v[1] << 16); out[1] = (uint32_t)v[2] | ((uint32_t)v[3] << 16);
 }
 
+// cost of one predicted 4x4 cell against fenc.  NOT inlined: the three producers of thread_subpel_cost (and the lowres
+// average) share one copy -- the sub-pel code is instruction-fetch bound (profiles/r01_me_frame_v5.txt), so the prediction
+// rows travel packed in registers (4 x NW words) and the Hadamard / SAD code exists once.
+template<typename pixel> struct CellRows { uint32_t w[4 * (4 * (int)sizeof(pixel) / 4)]; };
 template<typename pixel>
-__device__ __forceinline__ int cell_cost(const pixel* f, const int o[4][4], bool useSatd)
+__device__ __noinline__ int cell_cost_packed(const pixel* f, CellRows<pixel> rows, bool useSatd)
 {
     constexpr int NW = 4 * (int)sizeof(pixel) / 4;
     if (useSatd)
@@ -563,10 +567,11 @@ __device__ __forceinline__ int cell_cost(const pixel* f, const int o[4][4], bool
 #pragma unroll
         for (int i = 0; i < 4; i++)
         {
-            int a[4];
+            int a[4], o[4];
             unpack4<pixel>((const uint32_t*)(f + i * 64), a);
+            unpack4<pixel>(&rows.w[i * NW], o);
 #pragma unroll
-            for (int k = 0; k < 4; k++) d[i][k] = a[k] - o[i][k];
+            for (int k = 0; k < 4; k++) d[i][k] = a[k] - o[k];
             me_hadamard4(d[i][0], d[i][1], d[i][2], d[i][3]);
         }
         int t = 0;
@@ -582,13 +587,20 @@ __device__ __forceinline__ int cell_cost(const pixel* f, const int o[4][4], bool
 #pragma unroll
     for (int i = 0; i < 4; i++)
     {
-        uint32_t pw[NW];
-        pack4<pixel>(o[i], pw);
         const uint32_t* fw = (const uint32_t*)(f + i * 64);
 #pragma unroll
-        for (int j = 0; j < NW; j++) acc += sad_word<pixel>(fw[j], pw[j]);
+        for (int j = 0; j < NW; j++) acc += sad_word<pixel>(fw[j], rows.w[i * NW + j]);
     }
     return (int)acc;
+}
+template<typename pixel>
+__device__ __forceinline__ int cell_cost(const pixel* f, const int o[4][4], bool useSatd)
+{
+    constexpr int NW = 4 * (int)sizeof(pixel) / 4;
+    CellRows<pixel> rows;
+#pragma unroll
+    for (int i = 0; i < 4; i++) pack4<pixel>(o[i], &rows.w[i * NW]);
+    return cell_cost_packed<pixel>(f, rows, useSatd);
 }
 
 template<typename pixel>
