@@ -41,7 +41,7 @@ LEVELS = [64, 32, 16, 8]
 SAD_PYRAMID_DRAM_BYTES = 33437696
 WORKLOAD = ("2160p-8bit-medium primitive mix (SURVEY.md 8d config 3): SAD at the predictor + HEX subme2 merange57 search of every 2Nx2N PU 64..8 x 3 refs; "
             "one 8-tap MC interpolation per PU and level (all 15 fractions); residual -> DCT/quant/dequant/IDCT on every 32/16/8/4 TU -> recon; "
-            "intra filter + all 35 modes on every 8/16/32 block")
+            "intra neighbour smoothing + all 35 modes on every 8/16/32 block (fused)")
 METRIC = "2160p preset-medium fps at 1/2/4/8 B200; ME SAD achieved HBM GB/s vs peak"
 
 
@@ -311,18 +311,12 @@ def main():
     ip_jobs_d = {sz: {k: torch.from_numpy(a.view(np.uint8).copy()).to(dev) for k, a in ip_jobs_h[sz].items() if len(a)} for sz in LEVELS}
     n_interp = sum(len(a) for d in ip_jobs_h.values() for a in d.values())
     pred = {sz: torch.zeros((CTU_ROWS * CTU, W), dtype=torch.uint8, device=dev) for sz in LEVELS}
-    nbr_d, filt_d, pd_jobs_d, n_intra = {}, {}, {}, 0
+    nbr_d, n_intra = {}, 0
     for _, N, _ in INTRA_SIZES:
         a = neighbour_arrays(frames_h[0].ravel(), N)
-        nbr_d[N] = torch.from_numpy(a).to(dev); filt_d[N] = torch.empty_like(nbr_d[N])
-        pj = np.zeros(2 * len(a), dtype=pkg.INTRA_JOB)
-        idx = np.arange(len(a), dtype=np.int64)
-        pj["srcOff"] = np.repeat(idx * (4 * N + 1), 2); pj["dstOff"] = np.arange(2 * len(a), dtype=np.int64) * N * N
-        pj["mode"] = np.tile([0, 1], len(a)); pj["bFilter"] = int(N <= 16)
-        pd_jobs_d[N] = torch.from_numpy(pj.view(np.uint8).copy()).to(dev)
+        nbr_d[N] = torch.from_numpy(a).to(dev)
         n_intra += len(a)
-    allangs_out = torch.empty(33 * W * CTU_ROWS * CTU, dtype=torch.uint8, device=dev)       # 33 modes x every pixel, reused per size
-    pd_out = torch.empty(2 * W * CTU_ROWS * CTU, dtype=torch.uint8, device=dev)
+    allangs_out = torch.empty(35 * W * CTU_ROWS * CTU, dtype=torch.uint8, device=dev)       # 35 modes x every pixel, reused per size
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
     me_out = torch.empty((njobs, 3), dtype=torch.int32, device=dev)
     res_h = torch.empty((njobs, 3), dtype=torch.int32).pin_memory()
@@ -363,12 +357,10 @@ def main():
             qbits, add = quant_params(N)
             ctx.tu_pipeline_dev(idx, 8, 0, cptr, STRIDE, P(pred[16]), W, P(recon), W, W // N, HH // N, P(qtab), qbits, add, None, 40 << 5, 9,
                                 P(qcoef), P(numsig), P(tu_sse))
-        # 5. intra: neighbour filter + 33 angular modes + planar + DC on every 8/16/32 block
+        # 5. intra: neighbour smoothing + DC + planar + the 33 angular modes of every 8/16/32 block, one fused launch per size
+        #    (the prediction half of Search::estIntraPredQT, search.cpp:1358-1400)
         for _, N, log2N in INTRA_SIZES:
-            nb = nbr_d[N].shape[0]
-            ctx.intra_filter_dev(8, log2N, P(nbr_d[N]), P(filt_d[N]), nb)
-            ctx.intra_allangs_dev(8, log2N, P(nbr_d[N]), P(filt_d[N]), P(allangs_out), 1, nb)
-            ctx.intra_pred_dev(8, log2N, P(nbr_d[N]), P(pd_out), N, P(pd_jobs_d[N]), 2 * nb)
+            ctx.intra_modes_dev(8, log2N, P(nbr_d[N]), P(allangs_out), int(N <= 16), nbr_d[N].shape[0])
 
     # ---- N > 1: the path's one real exchange: every rank needs the reference pixels the others
     # produced, and rank 0 collects the per-PU {mv,cost}.  One all_gather of the new luma plane + one gather.

@@ -269,6 +269,14 @@ int x265b200_intra_filter_dev(x265b200_ctx* ctx, int depth, int log2N, const voi
 int x265b200_intra_allangs_dev(x265b200_ctx* ctx, int depth, int log2N, const void* refPix, const void* filtPix,
                                void* dest, int bLuma, int64_t n);
 
+/* The prediction half of the intra mode search as the asm table drives it (Search::estIntraPredQT, encoder/search.cpp:1358-1400):
+ * per block, cu[].intra_filter on the neighbour array, cu[].intra_pred[DC_IDX] (raw neighbours, edge filter = bLuma),
+ * cu[].intra_pred[PLANAR_IDX] (smoothed neighbours for N = 8/16/32, raw for N = 4) and cu[].intra_pred_allangs(raw, smoothed,
+ * bLuma) -- one launch, only the raw neighbour arrays are read.  dest: block i holds 35 predictions of N*N at
+ * dest + i*35*N*N: [0] planar, [1] DC, [2..34] the all-angles layout (modes < 18 transposed, intrapred.cpp:206-234).
+ * bLuma = (N <= 16) in the reference's calls. */
+int x265b200_intra_modes_dev(x265b200_ctx* ctx, int depth, int log2N, const void* neighbours, void* dest, int bLuma, int64_t n);
+
 /* ---- motion estimation: replaces MotionEstimate::setSourcePU + MotionEstimate::motionEstimate
  *      (encoder/motion.h:81-98; encoder/motion.cpp:167-191, :739-1569) for n independent PU
  *      searches.  One job = one call of motionEstimate(); per-job semantics are identical:

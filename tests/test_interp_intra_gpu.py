@@ -184,3 +184,40 @@ def test_intra_filter_and_allangs(ctx, depth):
                     assert np.array_equal(ga[i, mode - 2], e), (depth, log2N, i, mode, bLuma)
         for b in (dS, dF, dA):
             b.free()
+
+
+@pytest.mark.parametrize("depth", [8, 10])
+def test_intra_modes_fused(ctx, depth):
+    """x265b200_intra_modes_dev = intra_filter + DC + planar + intra_pred_allangs per block (the prediction half of
+    Search::estIntraPredQT, search.cpp:1358-1400) against the reference's per-mode primitives; also from an unaligned
+    destination (generic kernel) and for block counts that leave a partial group."""
+    R = _ref(depth)
+    dt = pdtype(depth)
+    for log2N in (2, 3, 4, 5):
+        N = 1 << log2N
+        L = 4 * N + 1
+        for n, misalign in ((13, 0), (5, 4)):      # +4 pixels: 4-byte aligned only -> the generic (one CTA per block) kernel
+            nbr = _pix(depth, L * n, 500 + log2N + n)
+            filt = np.zeros_like(nbr)
+            for i in range(n):
+                R.ref_intra_filter(log2N - 2, vpo(nbr, i * L), vpo(filt, i * L))
+            bLuma = int(N <= 16)
+            dS = ctx.to_device(nbr)
+            dD = ctx.empty((n * 35 * N * N + 8) * nbr.itemsize)
+            ctx.intra_modes_dev(depth, log2N, dS, dD.ptr + misalign * nbr.itemsize, bLuma, n)
+            got = dD.download(dt)[misalign:misalign + n * 35 * N * N].reshape(n, 35, N, N)
+            thr = {2: 99, 3: 7, 4: 1, 5: 0}[log2N]
+            for i in range(n):
+                for mode in range(35):
+                    if mode == 0:
+                        src, bf = (filt if N >= 8 else nbr), 0
+                    elif mode == 1:
+                        src, bf = nbr, bLuma
+                    else:
+                        src, bf = (filt if min(abs(mode - 26), abs(mode - 10)) > thr else nbr), bLuma
+                    e = np.empty((N, N), dtype=dt)
+                    R.ref_intra_pred(log2N - 2, mode, vpo(e, 0), ssz(N), vpo(src, i * L), bf)
+                    if 2 <= mode < 18:
+                        e = e.T
+                    assert np.array_equal(got[i, mode], e), (depth, log2N, n, i, mode)
+            dS.free(); dD.free()

@@ -481,3 +481,10 @@ def _ctx_la_estimate_hme_dev(self, depth, dPlanes, stride, wcu, hcu, hme, triple
 
 
 Ctx.la_estimate_hme_dev = _ctx_la_estimate_hme_dev
+
+
+def _ctx_intra_modes_dev(self, depth, log2N, dNbr, dDest, bLuma, n):
+    self._chk(self.L.x265b200_intra_modes_dev(self.h, int(depth), int(log2N), _vp(dNbr), _vp(dDest), int(bLuma), _i64(n)))
+
+
+Ctx.intra_modes_dev = _ctx_intra_modes_dev

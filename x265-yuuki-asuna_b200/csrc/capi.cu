@@ -83,6 +83,7 @@ int tu_pipeline_dev(Ctx*, int sizeIdx, int depth, int useDST, const void* fenc, 
 void host_dct_table(int N, int16_t* out);
 int interp_dev(Ctx*, int kind, int taps, int depth, int w, int h, const void* src, int64_t srcStride,
                void* dst, int64_t dstStride, const x265b200_interp_job* jobs, int64_t n, int isRowExt);
+int intra_modes_dev(Ctx*, int depth, int log2N, const void* neighbours, void* dest, int bLuma, int64_t n);
 int mc_dev(Ctx*, int depth, const x265b200_mc_desc* d, const x265b200_mc_job* jobs, int64_t n, int bLuma, int bChroma);
 int sao_apply_dev(Ctx*, int kind, int depth, void* rec, int64_t stride, const x265b200_sao_job* jobs, int64_t n, int8_t* signBuf, const int8_t* offsets, int maxWidth);
 int sao_stats_dev(Ctx*, int kind, int depth, const int16_t* diff, const void* rec, int64_t stride, const x265b200_sao_job* jobs, int64_t n,
@@ -424,6 +425,12 @@ int x265b200_intra_allangs_dev(x265b200_ctx* ctx, int depth, int log2N, const vo
 {
     REQUIRE_CTX(ctx);
     return intra_allangs_dev(CTX(ctx), depth, log2N, refPix, filtPix, dest, bLuma, n);
+}
+
+int x265b200_intra_modes_dev(x265b200_ctx* ctx, int depth, int log2N, const void* neighbours, void* dest, int bLuma, int64_t n)
+{
+    REQUIRE_CTX(ctx);
+    return intra_modes_dev(CTX(ctx), depth, log2N, neighbours, dest, bLuma, n);
 }
 
 // ---- glue ---------------------------------------------------------------------------------------

@@ -149,14 +149,28 @@ constexpr int ALLANGS_PITCH = 120;      // bytes/elements per line row: 3N + 2 =
 template<typename pixel>
 __global__ void __launch_bounds__(256)
 intra_allangs_kernel(const pixel* __restrict__ refPix, const pixel* __restrict__ filtPix, pixel* __restrict__ dest,
-                     int log2N, int bLuma, int depth, int64_t n, int vec16)
+                     int log2N, int bLuma, int depth, int64_t n, int vec16, int all35)
 {
     __shared__ pixel sr[132], sf[132];
     __shared__ __align__(16) pixel line[33][ALLANGS_PITCH];   // entry L <-> ref[L - N], L in [0, 3N + 1]
     const int N = 1 << log2N, N2 = N << 1, len = 4 * N + 1, LW = 3 * N + 2;
     const int64_t b = blockIdx.x;
-    for (int i = threadIdx.x; i < len; i += blockDim.x) { sr[i] = refPix[b * len + i]; sf[i] = filtPix[b * len + i]; }
+    for (int i = threadIdx.x; i < len; i += blockDim.x) { sr[i] = refPix[b * len + i]; if (!all35) sf[i] = filtPix[b * len + i]; }
     __syncthreads();
+    if (all35)
+    {
+        // all-35-modes form: the smoothed neighbours are produced here (intraFilter<N>, :31-51)
+        for (int i = threadIdx.x; i < len; i += blockDim.x)
+        {
+            int v;
+            if (i == 0) v = ((sr[0] << 1) + sr[1] + sr[N2 + 1] + 2) >> 2;
+            else if (i == N2 || i == 2 * N2) v = sr[i];
+            else if (i == N2 + 1) v = ((sr[N2 + 1] << 1) + sr[0] + sr[N2 + 2] + 2) >> 2;
+            else v = ((sr[i] << 1) + sr[i - 1] + sr[i + 1] + 2) >> 2;
+            sf[i] = (pixel)v;
+        }
+        __syncthreads();
+    }
     // smoothing thresholds (constants.cpp:561): filtered when min(|m-26|,|m-10|) > {7,1,0} for N = 8,16,32; never for 4
     const int thr = N == 8 ? 7 : (N == 16 ? 1 : (N == 32 ? 0 : 99));
     for (int e = threadIdx.x; e < 33 * LW; e += blockDim.x)
@@ -174,8 +188,29 @@ intra_allangs_kernel(const pixel* __restrict__ refPix, const pixel* __restrict__
         line[m][L] = s[j];
     }
     __syncthreads();
-    pixel* out = dest + b * 33 * N * N;
+    pixel* out = dest + (all35 ? b * 35 * N * N + 2 * N * N : b * 33 * N * N);
     const int maxVal = (1 << depth) - 1;
+    if (all35)
+    {
+        // planar from the smoothed neighbours for N = 8/16/32, DC from the raw ones with the edge filter for N <= 16
+        // (Search::estIntraPredQT, search.cpp:1358-1375)
+        __shared__ int sDcAll;
+        if (threadIdx.x < 32)
+        {
+            int v = 0;
+            for (int i = threadIdx.x; i < N; i += 32) v += sr[1 + i] + sr[N2 + 1 + i];
+            v = warp_sum(v);
+            if (threadIdx.x == 0) sDcAll = (N + v) / (N + N);
+        }
+        __syncthreads();
+        pixel* pd = dest + b * 35 * N * N;
+        const pixel* pl = N >= 8 ? sf : sr;
+        for (int e = threadIdx.x; e < 2 * N * N; e += blockDim.x)
+        {
+            const int mode = e >> (2 * log2N), r = e & (N * N - 1), y = r >> log2N, x = r & (N - 1);
+            pd[e] = (pixel)intra_pixel<pixel>(mode ? sr : pl, N, log2N, mode, mode ? bLuma : 0, y, x, depth, sDcAll);
+        }
+    }
     if (sizeof(pixel) == 1 && vec16)
     {
         // 8-bit fast path: a thread produces 16 consecutive output bytes (one row segment for N >= 16, 2 rows of 8, 4 rows
@@ -268,7 +303,9 @@ intra_allangs_kernel(const pixel* __restrict__ refPix, const pixel* __restrict__
 // neighbour-index table is built ONCE per CTA, the next group's neighbour bytes are prefetched into registers while the
 // current group is predicted, a thread emits 16 output bytes per 128-bit store from aligned word loads of the line with
 // two pixels per 32-bit multiply-add (16-bit lanes: 255*32 + 16 < 2^16).
-template<int LOG2N>
+// ALL35: the fused mode-search form (x265b200_intra_modes_dev): only the raw neighbours are read, the smoothed ones are
+// produced in shared memory, and planar + DC are emitted in front of the 33 angular blocks (35 x N x N per block).
+template<int LOG2N, bool ALL35>
 __global__ void __launch_bounds__(256)
 intra_allangs8_kernel(const uint8_t* __restrict__ refPix, const uint8_t* __restrict__ filtPix, uint8_t* __restrict__ dest, int bLuma, int64_t n)
 {
@@ -276,9 +313,11 @@ intra_allangs8_kernel(const uint8_t* __restrict__ refPix, const uint8_t* __restr
     constexpr int G = N == 32 ? 1 : (N == 16 ? 2 : (N == 8 ? 4 : 8));
     constexpr int PITCH = (LW + 16 + 7) & ~7;                  // line row: LW entries + the read-ahead of the word path
     constexpr int SP = 136;                                     // neighbour array pitch (>= LEN)
-    constexpr int CPB = 33 * N * N / 16;                        // 16-byte chunks per block
+    constexpr int NM = ALL35 ? 35 : 33;                         // prediction blocks per input block
+    constexpr int CPB = NM * N * N / 16;                        // 16-byte chunks per block
     constexpr int CH = N < 16 ? N : 16, NWD = CH / 4;
-    constexpr int TOT = G * 2 * LEN;                            // neighbour bytes staged per group (<= 272)
+    constexpr int TOT = G * (ALL35 ? 1 : 2) * LEN;              // neighbour bytes staged per group (<= 272)
+    __shared__ int sDc[G];
     __shared__ uint16_t jtab[33 * LW];
     __shared__ uint8_t s2[G][2 * SP];                           // per block: [unfiltered | filtered] neighbours
     __shared__ __align__(16) uint8_t line[G][33][PITCH];        // entry L <-> ref[L - N]
@@ -306,7 +345,7 @@ intra_allangs8_kernel(const uint8_t* __restrict__ refPix, const uint8_t* __restr
     {
         const int t = tid + u * 256;
         sOk[u] = t < TOT;
-        const int g = t / (2 * LEN), rem = t - g * (2 * LEN), which = rem >= LEN, i = rem - which * LEN;
+        const int g = t / ((ALL35 ? 1 : 2) * LEN), rem = t - g * ((ALL35 ? 1 : 2) * LEN), which = rem >= LEN, i = rem - which * LEN;
         gOf[u] = g; sFilt[u] = which; sOff[u] = g * (2 * SP) + which * SP + i; srcOff[u] = (int64_t)g * LEN + i;
     }
     const int64_t stride = (int64_t)gridDim.x * G;
@@ -322,6 +361,29 @@ intra_allangs8_kernel(const uint8_t* __restrict__ refPix, const uint8_t* __restr
 #pragma unroll
         for (int u = 0; u < 2; u++) if (sOk[u]) (&s2[0][0])[sOff[u]] = v[u];
         __syncthreads();
+        if (ALL35)
+        {
+            // intraFilter<N> (intrapred.cpp:31-51) into the second half of s2, and the DC value of each block
+            for (int e = tid; e < G * LEN; e += 256)
+            {
+                const int g = e / LEN, i = e - g * LEN;
+                const uint8_t* sr = s2[g];
+                int fv;
+                if (i == 0) fv = ((sr[0] << 1) + sr[1] + sr[N2 + 1] + 2) >> 2;
+                else if (i == N2 || i == 2 * N2) fv = sr[i];
+                else if (i == N2 + 1) fv = ((sr[N2 + 1] << 1) + sr[0] + sr[N2 + 2] + 2) >> 2;
+                else fv = ((sr[i] << 1) + sr[i - 1] + sr[i + 1] + 2) >> 2;
+                s2[g][SP + i] = (uint8_t)fv;
+            }
+            if (tid >= 256 - G)
+            {
+                const uint8_t* sr = s2[255 - tid];
+                int sum = N;
+                for (int i = 0; i < N; i++) sum += sr[1 + i] + sr[N2 + 1 + i];
+                sDc[255 - tid] = sum / (N + N);
+            }
+            __syncthreads();
+        }
         const int64_t nb0 = b0 + stride;
 #pragma unroll
         for (int u = 0; u < 2; u++)
@@ -338,7 +400,29 @@ intra_allangs8_kernel(const uint8_t* __restrict__ refPix, const uint8_t* __restr
         {
             const int g = q / CPB, e = (q - g * CPB) * 16;
             if (b0 + g >= n) continue;
-            const int m = e >> (2 * LOG2N), r = e & (N * N - 1), mode = m + 2;
+            if (ALL35 && e < 2 * N * N)
+            {
+                // planar (smoothed neighbours for N >= 8) / DC (raw neighbours, edge filter when bLuma): search.cpp:1358-1375
+                const int pm = e >> (2 * LOG2N), r0 = e & (N * N - 1);
+                const uint8_t* sn = &s2[g][(pm == 0 && N >= 8) ? SP : 0];
+                uint32_t ow[4];
+#pragma unroll
+                for (int wq = 0; wq < 4; wq++)
+                {
+                    uint32_t word = 0;
+#pragma unroll
+                    for (int c = 0; c < 4; c++)
+                    {
+                        const int rr = r0 + wq * 4 + c, y = rr >> LOG2N, x = rr & (N - 1);
+                        word |= (uint32_t)intra_pixel<uint8_t>(sn, N, LOG2N, pm, pm ? bLuma : 0, y, x, 8, sDc[g]) << (8 * c);
+                    }
+                    ow[wq] = word;
+                }
+                *(uint4*)(dest + (b0 + g) * (int64_t)(NM * N * N) + e) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                continue;
+            }
+            const int eAng = ALL35 ? e - 2 * N * N : e;
+            const int m = eAng >> (2 * LOG2N), r = eAng & (N * N - 1), mode = m + 2;
             const bool hor = mode < 18;
             const int angle = c_angle[8 + (hor ? 10 - mode : mode - 26)];
             uint32_t ow[4];
@@ -370,7 +454,7 @@ intra_allangs8_kernel(const uint8_t* __restrict__ refPix, const uint8_t* __restr
                     ow[c * NWD] = (ow[c * NWD] & 0xFFFFFF00u) | (uint32_t)(vv < 0 ? 0 : (vv > 255 ? 255 : vv));
                 }
             }
-            *(uint4*)(dest + (b0 + g) * (int64_t)(33 * N * N) + e) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            *(uint4*)(dest + (b0 + g) * (int64_t)(NM * N * N) + e) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
         }
         __syncthreads();
     }
@@ -399,28 +483,43 @@ int intra_filter_dev(Ctx* ctx, int depth, int log2N, const void* src, void* dst,
     return check(cudaGetLastError(), "intra_filter kernel launch");
 }
 
-int intra_allangs_dev(Ctx* ctx, int depth, int log2N, const void* refPix, const void* filtPix, void* dest, int bLuma, int64_t n)
+static int intra_allangs_launch(Ctx* ctx, int depth, int log2N, const void* refPix, const void* filtPix, void* dest, int bLuma, int64_t n, int all35)
 {
     if (n <= 0) return 0;
     if (log2N < 2 || log2N > 5) { set_error("intra_allangs: log2N %d", log2N); return -1; }
-    if (depth > 8) intra_allangs_kernel<uint16_t><<<(unsigned)n, 256, 0, ctx->stream>>>((const uint16_t*)refPix, (const uint16_t*)filtPix, (uint16_t*)dest, log2N, bLuma, depth, n, 0);
+    if ((uintptr_t)dest & (depth > 8 ? 7 : 3)) { set_error("intra_allangs: dest must be %d-byte aligned (4 pixels per store)", depth > 8 ? 8 : 4); return -1; }
+    if (depth > 8) intra_allangs_kernel<uint16_t><<<(unsigned)n, 256, 0, ctx->stream>>>((const uint16_t*)refPix, (const uint16_t*)filtPix, (uint16_t*)dest, log2N, bLuma, depth, n, 0, all35);
     else if (((uintptr_t)dest & 15) == 0)
     {
         const int G = log2N == 5 ? 1 : (log2N == 4 ? 2 : (log2N == 3 ? 4 : 8));
         const int64_t groups = (n + G - 1) / G, cap = (int64_t)ctx->smCount * 8;
         const unsigned grid = (unsigned)(groups < cap ? groups : cap);
         const uint8_t* r = (const uint8_t*)refPix; const uint8_t* f = (const uint8_t*)filtPix; uint8_t* d = (uint8_t*)dest;
+#define AA_LAUNCH(L) do { if (all35) intra_allangs8_kernel<L, true><<<grid, 256, 0, ctx->stream>>>(r, f, d, bLuma, n); \
+                          else intra_allangs8_kernel<L, false><<<grid, 256, 0, ctx->stream>>>(r, f, d, bLuma, n); } while (0)
         switch (log2N)
         {
-        case 2: intra_allangs8_kernel<2><<<grid, 256, 0, ctx->stream>>>(r, f, d, bLuma, n); break;
-        case 3: intra_allangs8_kernel<3><<<grid, 256, 0, ctx->stream>>>(r, f, d, bLuma, n); break;
-        case 4: intra_allangs8_kernel<4><<<grid, 256, 0, ctx->stream>>>(r, f, d, bLuma, n); break;
-        default: intra_allangs8_kernel<5><<<grid, 256, 0, ctx->stream>>>(r, f, d, bLuma, n); break;
+        case 2: AA_LAUNCH(2); break;
+        case 3: AA_LAUNCH(3); break;
+        case 4: AA_LAUNCH(4); break;
+        default: AA_LAUNCH(5); break;
         }
+#undef AA_LAUNCH
     }
-    else           intra_allangs_kernel<uint8_t><<<(unsigned)n, 256, 0, ctx->stream>>>((const uint8_t*)refPix, (const uint8_t*)filtPix, (uint8_t*)dest, log2N, bLuma, depth, n, 0);
+    else           intra_allangs_kernel<uint8_t><<<(unsigned)n, 256, 0, ctx->stream>>>((const uint8_t*)refPix, (const uint8_t*)filtPix, (uint8_t*)dest, log2N, bLuma, depth, n, 0, all35);
     ctx->launches++;
     return check(cudaGetLastError(), "intra_allangs kernel launch");
+}
+
+int intra_allangs_dev(Ctx* ctx, int depth, int log2N, const void* refPix, const void* filtPix, void* dest, int bLuma, int64_t n)
+{
+    return intra_allangs_launch(ctx, depth, log2N, refPix, filtPix, dest, bLuma, n, 0);
+}
+// the prediction half of the intra mode search (Search::estIntraPredQT, search.cpp:1358-1400, as the asm table drives it):
+// intra_filter + DC + planar + intra_pred_allangs of every block in one launch, 35 x N x N predictions per block
+int intra_modes_dev(Ctx* ctx, int depth, int log2N, const void* neighbours, void* dest, int bLuma, int64_t n)
+{
+    return intra_allangs_launch(ctx, depth, log2N, neighbours, nullptr, dest, bLuma, n, 1);
 }
 
 } // namespace x265b200
