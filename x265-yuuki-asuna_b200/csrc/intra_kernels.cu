@@ -310,13 +310,14 @@ __global__ void __launch_bounds__(256)
 intra_allangs8_kernel(const uint8_t* __restrict__ refPix, const uint8_t* __restrict__ filtPix, uint8_t* __restrict__ dest, int bLuma, int64_t n)
 {
     constexpr int N = 1 << LOG2N, N2 = N << 1, LEN = 4 * N + 1, LW = 3 * N + 2;
-    constexpr int G = N == 32 ? 1 : (N == 16 ? 2 : (N == 8 ? 4 : 8));
+    constexpr int G = N == 32 ? 1 : (N == 16 ? 2 : (N == 8 ? 8 : 16));          // blocks per group (work between two barriers)
     constexpr int PITCH = (LW + 16 + 7) & ~7;                  // line row: LW entries + the read-ahead of the word path
     constexpr int SP = 136;                                     // neighbour array pitch (>= LEN)
     constexpr int NM = ALL35 ? 35 : 33;                         // prediction blocks per input block
     constexpr int CPB = NM * N * N / 16;                        // 16-byte chunks per block
     constexpr int CH = N < 16 ? N : 16, NWD = CH / 4;
-    constexpr int TOT = G * (ALL35 ? 1 : 2) * LEN;              // neighbour bytes staged per group (<= 272)
+    constexpr int TOT = G * (ALL35 ? 1 : 2) * LEN;              // neighbour bytes staged per group
+    constexpr int NU = (TOT + 255) / 256;                       // ... = NU bytes per thread
     __shared__ int sDc[G];
     __shared__ uint16_t jtab[33 * LW];
     __shared__ uint8_t s2[G][2 * SP];                           // per block: [unfiltered | filtered] neighbours
@@ -339,9 +340,9 @@ intra_allangs8_kernel(const uint8_t* __restrict__ refPix, const uint8_t* __restr
     }
 
     // staging map of this thread's (up to two) neighbour bytes
-    int sOff[2], gOf[2]; int64_t srcOff[2]; bool sFilt[2], sOk[2];
+    int sOff[NU], gOf[NU]; int64_t srcOff[NU]; bool sFilt[NU], sOk[NU];
 #pragma unroll
-    for (int u = 0; u < 2; u++)
+    for (int u = 0; u < NU; u++)
     {
         const int t = tid + u * 256;
         sOk[u] = t < TOT;
@@ -350,16 +351,19 @@ intra_allangs8_kernel(const uint8_t* __restrict__ refPix, const uint8_t* __restr
     }
     const int64_t stride = (int64_t)gridDim.x * G;
     int64_t b0 = (int64_t)blockIdx.x * G;
-    uint8_t v[2] = { 0, 0 };
+    uint8_t v[NU];
 #pragma unroll
-    for (int u = 0; u < 2; u++)
+    for (int u = 0; u < NU; u++)
+    {
+        v[u] = 0;
         if (sOk[u] && b0 + gOf[u] < n) v[u] = (sFilt[u] ? filtPix : refPix)[b0 * LEN + srcOff[u]];
+    }
 
     const uint32_t* lw = (const uint32_t*)&line[0][0][0];
     for (; b0 < n; b0 += stride)
     {
 #pragma unroll
-        for (int u = 0; u < 2; u++) if (sOk[u]) (&s2[0][0])[sOff[u]] = v[u];
+        for (int u = 0; u < NU; u++) if (sOk[u]) (&s2[0][0])[sOff[u]] = v[u];
         __syncthreads();
         if (ALL35)
         {
@@ -375,18 +379,19 @@ intra_allangs8_kernel(const uint8_t* __restrict__ refPix, const uint8_t* __restr
                 else fv = ((sr[i] << 1) + sr[i - 1] + sr[i + 1] + 2) >> 2;
                 s2[g][SP + i] = (uint8_t)fv;
             }
-            if (tid >= 256 - G)
+            // DC values (intrapred.cpp:72-78): warp w sums the 2N neighbours of blocks w, w + 8, ...
+            for (int g = tid >> 5; g < G; g += 8)
             {
-                const uint8_t* sr = s2[255 - tid];
-                int sum = N;
-                for (int i = 0; i < N; i++) sum += sr[1 + i] + sr[N2 + 1 + i];
-                sDc[255 - tid] = sum / (N + N);
+                const int lane = tid & 31;
+                int sum = lane < N ? (int)s2[g][1 + lane] + (int)s2[g][N2 + 1 + lane] : 0;
+                sum = warp_sum(sum);
+                if (lane == 0) sDc[g] = (N + sum) / (N + N);
             }
             __syncthreads();
         }
         const int64_t nb0 = b0 + stride;
 #pragma unroll
-        for (int u = 0; u < 2; u++)
+        for (int u = 0; u < NU; u++)
             if (sOk[u] && nb0 + gOf[u] < n) v[u] = (sFilt[u] ? filtPix : refPix)[nb0 * LEN + srcOff[u]];
 
         for (int e = tid; e < G * 33 * LW; e += 256)
@@ -491,7 +496,7 @@ static int intra_allangs_launch(Ctx* ctx, int depth, int log2N, const void* refP
     if (depth > 8) intra_allangs_kernel<uint16_t><<<(unsigned)n, 256, 0, ctx->stream>>>((const uint16_t*)refPix, (const uint16_t*)filtPix, (uint16_t*)dest, log2N, bLuma, depth, n, 0, all35);
     else if (((uintptr_t)dest & 15) == 0)
     {
-        const int G = log2N == 5 ? 1 : (log2N == 4 ? 2 : (log2N == 3 ? 4 : 8));
+        const int G = log2N == 5 ? 1 : (log2N == 4 ? 2 : (log2N == 3 ? 8 : 16));
         const int64_t groups = (n + G - 1) / G, cap = (int64_t)ctx->smCount * 8;
         const unsigned grid = (unsigned)(groups < cap ? groups : cap);
         const uint8_t* r = (const uint8_t*)refPix; const uint8_t* f = (const uint8_t*)filtPix; uint8_t* d = (uint8_t*)dest;
