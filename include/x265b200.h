@@ -257,6 +257,15 @@ int x265b200_ssim_dist_dev(x265b200_ctx* ctx, int depth, int log2TrSize, const v
                            const int64_t* offF, const int64_t* offR, int64_t n, int shift, uint64_t* ssBlock, uint64_t* ac_k);
 int x265b200_norm_fact_dev(x265b200_ctx* ctx, int depth, const void* src, const int64_t* off, int64_t n, int blockSize, int shift, uint64_t* z_k);
 
+/* ssim_4x4x2_core (primitives.h:345; pixel.cpp:631-658): sums[i][2][4] of the two adjacent 4x4 blocks at pix1 + off1[i] / pix2 + off2[i];
+ * ssim_end_4 (pixel.cpp:660-702): out[i] = sum over widths[i] (1..4) window positions of ssim_end_1 on sum0[i][5][4] / sum1[i][5][4];
+ * planeClipAndMax (pixel.cpp:996-1016): clip the plane to [minPix, maxPix] in place, *outsum = sum, *outmax = maximum. */
+int x265b200_ssim_4x4x2_dev(x265b200_ctx* ctx, int depth, const void* pix1, int64_t stride1, const void* pix2, int64_t stride2,
+                            const int64_t* off1, const int64_t* off2, int64_t n, int32_t* sums);
+int x265b200_ssim_end4_dev(x265b200_ctx* ctx, int depth, const int32_t* sum0, const int32_t* sum1, const int32_t* widths, int64_t n, float* out);
+int x265b200_plane_clip_max_dev(x265b200_ctx* ctx, int depth, void* src, int64_t stride, int width, int height, int minPix, int maxPix,
+                                uint64_t* outsum, uint32_t* outmax);
+
 /* ---- intra prediction: replaces cu[].intra_pred[35] / intra_filter / intra_pred_allangs
  *      (primitives.h:143-145,304-306; intrapred.cpp:31-234).  Neighbour arrays use the reference
  *      layout [topLeft, top 2N, left 2N] (4N+1 pixels).  log2N = 2..5. */

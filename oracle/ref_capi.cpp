@@ -835,3 +835,16 @@ int ref_mc_batch(int csp, int isP, int wpP, int wpB, int picW, int picH, int max
     return 0;
 }
 } /* extern "C" */
+
+extern "C" {
+float ref_ssim_end4(int (*sum0)[4], int (*sum1)[4], int width) { ensure_init(); return primitives.ssim_end_4(sum0, sum1, width); }
+void ref_ssim_core(const void* p1, intptr_t s1, const void* p2, intptr_t s2, int (*sums)[4]) { ensure_init(); primitives.ssim_4x4x2_core((const pixel*)p1, s1, (const pixel*)p2, s2, sums); }
+int ref_plane_clip_max(void* src, intptr_t stride, int width, int height, uint64_t* outsum, int minPix, int maxPix)
+{
+    ensure_init();
+    if (!primitives.planeClipAndMax) return -1;
+    return (int)primitives.planeClipAndMax((pixel*)src, stride, width, height, outsum, (pixel)minPix, (pixel)maxPix);
+}
+void ref_propagate_cost(int* dst, const uint16_t* propagateIn, const int32_t* intraCosts, const uint16_t* interCosts, const int32_t* invQscales, double fps, int len)
+{ ensure_init(); primitives.propagateCost(dst, propagateIn, intraCosts, interCosts, invQscales, &fps, len); }
+}

@@ -598,6 +598,37 @@ void norm_fact_thunk(const pixel* src, uint32_t blockSize, int shift, uint64_t* 
     CK(x265b200_download(C(), z_k, dO, 8));
 }
 
+// ---- SSIM metric helpers and the HDR luma clip (pixel.cpp:631-702, :996-1016) ------------------------------------------------
+void ssim_core_thunk(const pixel* pix1, intptr_t stride1, const pixel* pix2, intptr_t stride2, int sums[2][4])
+{
+    void* d1 = up_span(0, pix1, stride1, 8, 4, PX); void* d2 = up_span(1, pix2, stride2, 8, 4, PX);
+    int64_t zero = 0; void* dOff = up1d(2, &zero, 8); void* dO = dev(3, 32);
+    CK(x265b200_ssim_4x4x2_dev(C(), X265_DEPTH, d1, stride1, d2, stride2, (const int64_t*)dOff, (const int64_t*)dOff, 1, (int32_t*)dO));
+    CK(x265b200_download(C(), sums, dO, 32));
+}
+float ssim_end4_thunk(int sum0[5][4], int sum1[5][4], int width)
+{
+    void* d0 = up1d(0, sum0, 80); void* d1 = up1d(1, sum1, 80);
+    int32_t w = width; void* dW = up1d(2, &w, 4); void* dO = dev(3, 4);
+    CK(x265b200_ssim_end4_dev(C(), X265_DEPTH, (const int32_t*)d0, (const int32_t*)d1, (const int32_t*)dW, 1, (float*)dO));
+    float r; CK(x265b200_download(C(), &r, dO, 4));
+    return r;
+}
+#if HIGH_BIT_DEPTH
+pixel plane_clip_max_thunk(pixel* src, intptr_t stride, int width, int height, uint64_t* outsum, const pixel minPix, const pixel maxPix)
+{
+    *outsum = 0;
+    if (width <= 0 || height <= 0) return 0;
+    void* dS = up_span(0, src, stride, width, height, PX);
+    char* dO = (char*)dev(1, 16);
+    CK(x265b200_plane_clip_max_dev(C(), X265_DEPTH, dS, stride, width, height, minPix, maxPix, (uint64_t*)dO, (uint32_t*)(dO + 8)));
+    CK(x265b200_download(C(), src, dS, ((size_t)(height - 1) * stride + width) * PX));
+    uint64_t r[2]; CK(x265b200_download(C(), r, dO, 16));
+    *outsum = r[0];
+    return (pixel)(uint32_t)r[1];
+}
+#endif
+
 } // namespace
 
 namespace X265_NS {
@@ -779,6 +810,10 @@ void setupAssemblyPrimitives(EncoderPrimitives& p, int /*cpuMask: SIMD flags are
     p.cu[BLOCK_32x32].ssimDist = ssim_dist_thunk<5>; p.cu[BLOCK_64x64].ssimDist = ssim_dist_thunk<6>;
     p.cu[BLOCK_8x8].normFact = norm_fact_thunk; p.cu[BLOCK_16x16].normFact = norm_fact_thunk;
     p.cu[BLOCK_32x32].normFact = norm_fact_thunk; p.cu[BLOCK_64x64].normFact = norm_fact_thunk;
+    p.ssim_4x4x2_core = ssim_core_thunk; p.ssim_end_4 = ssim_end4_thunk;
+#if HIGH_BIT_DEPTH
+    p.planeClipAndMax = plane_clip_max_thunk;
+#endif
 }
 
 } // namespace X265_NS

@@ -488,3 +488,25 @@ def _ctx_intra_modes_dev(self, depth, log2N, dNbr, dDest, bLuma, n):
 
 
 Ctx.intra_modes_dev = _ctx_intra_modes_dev
+
+
+def _ctx_ssim_4x4x2_dev(self, depth, d1, s1, d2, s2, dOff1, dOff2, n, dSums):
+    self._chk(self.L.x265b200_ssim_4x4x2_dev(self.h, int(depth), _vp(d1), _i64(s1), _vp(d2), _i64(s2), _vp(dOff1), _vp(dOff2), _i64(n), _vp(dSums)))
+
+
+def _ctx_ssim_end4_dev(self, depth, dSum0, dSum1, dWidths, n, dOut):
+    self._chk(self.L.x265b200_ssim_end4_dev(self.h, int(depth), _vp(dSum0), _vp(dSum1), _vp(dWidths), _i64(n), _vp(dOut)))
+
+
+def _ctx_plane_clip_max_dev(self, depth, dSrc, stride, width, height, minPix, maxPix, dSum, dMax):
+    self._chk(self.L.x265b200_plane_clip_max_dev(self.h, int(depth), _vp(dSrc), _i64(stride), int(width), int(height), int(minPix), int(maxPix), _vp(dSum), _vp(dMax)))
+
+
+def _ctx_propagate_cost_dev(self, dDst, dIn, dIntra, dInter, dInvQ, fps, n):
+    self._chk(self.L.x265b200_propagate_cost_dev(self.h, _vp(dDst), _vp(dIn), _vp(dIntra), _vp(dInter), _vp(dInvQ), ctypes.c_double(fps), _i64(n)))
+
+
+Ctx.ssim_4x4x2_dev = _ctx_ssim_4x4x2_dev
+Ctx.ssim_end4_dev = _ctx_ssim_end4_dev
+Ctx.plane_clip_max_dev = _ctx_plane_clip_max_dev
+Ctx.propagate_cost_dev = _ctx_propagate_cost_dev

@@ -96,6 +96,9 @@ int planecopy_dev(Ctx*, int mode, int depth, const void* src, int64_t srcStride,
 int ssim_dist_dev(Ctx*, int depth, int log2TrSize, const void* fenc, int64_t fStride, const void* recon, int64_t rStride, const int64_t* offF, const int64_t* offR,
                   int64_t n, int shift, uint64_t* ssBlock, uint64_t* ack);
 int norm_fact_dev(Ctx*, int depth, const void* src, const int64_t* off, int64_t n, int blockSize, int shift, uint64_t* zk);
+int ssim_core_dev(Ctx*, int depth, const void* p1, int64_t s1, const void* p2, int64_t s2, const int64_t* off1, const int64_t* off2, int64_t n, int32_t* sums);
+int ssim_end4_dev(Ctx*, int depth, const int32_t* sum0, const int32_t* sum1, const int32_t* widths, int64_t n, float* out);
+int plane_clip_max_dev(Ctx*, int depth, void* src, int64_t stride, int width, int height, int minPix, int maxPix, uint64_t* outsum, uint32_t* outmax);
 int intra_pred_dev(Ctx*, int depth, int log2N, const void* nbr, void* dst, int64_t dstStride, const x265b200_intra_job* jobs, int64_t n);
 int intra_filter_dev(Ctx*, int depth, int log2N, const void* src, void* dst, int64_t n);
 int intra_allangs_dev(Ctx*, int depth, int log2N, const void* refPix, const void* filtPix, void* dest, int bLuma, int64_t n);
@@ -410,6 +413,23 @@ int x265b200_norm_fact_dev(x265b200_ctx* ctx, int depth, const void* src, const 
 {
     REQUIRE_CTX(ctx);
     return norm_fact_dev(CTX(ctx), depth, src, off, n, blockSize, shift, z_k);
+}
+int x265b200_ssim_4x4x2_dev(x265b200_ctx* ctx, int depth, const void* pix1, int64_t stride1, const void* pix2, int64_t stride2,
+                            const int64_t* off1, const int64_t* off2, int64_t n, int32_t* sums)
+{
+    REQUIRE_CTX(ctx);
+    return ssim_core_dev(CTX(ctx), depth, pix1, stride1, pix2, stride2, off1, off2, n, sums);
+}
+int x265b200_ssim_end4_dev(x265b200_ctx* ctx, int depth, const int32_t* sum0, const int32_t* sum1, const int32_t* widths, int64_t n, float* out)
+{
+    REQUIRE_CTX(ctx);
+    return ssim_end4_dev(CTX(ctx), depth, sum0, sum1, widths, n, out);
+}
+int x265b200_plane_clip_max_dev(x265b200_ctx* ctx, int depth, void* src, int64_t stride, int width, int height, int minPix, int maxPix,
+                                uint64_t* outsum, uint32_t* outmax)
+{
+    REQUIRE_CTX(ctx);
+    return plane_clip_max_dev(CTX(ctx), depth, src, stride, width, height, minPix, maxPix, outsum, outmax);
 }
 int x265b200_intra_pred_dev(x265b200_ctx* ctx, int depth, int log2N, const void* nbr, void* dst, int64_t dstStride, const x265b200_intra_job* jobs, int64_t n)
 {
