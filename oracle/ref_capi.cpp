@@ -848,3 +848,40 @@ int ref_plane_clip_max(void* src, intptr_t stride, int width, int height, uint64
 void ref_propagate_cost(int* dst, const uint16_t* propagateIn, const int32_t* intraCosts, const uint16_t* interCosts, const int32_t* invQscales, double fps, int len)
 { ensure_init(); primitives.propagateCost(dst, propagateIn, intraCosts, interCosts, invQscales, &fps, len); }
 }
+
+/* ---- SAO / deblock table entries, one call each (kinds as X265B200_SAO_*: 0 E0, 1 E1, 2 E1_2Rows, 3 E2, 4 E3, 5 B0 / BO) ---- */
+extern "C" {
+void ref_sao_apply(int kind, void* recV, intptr_t stride, int8_t* buf0, int8_t* buf1, int8_t* offsets, int width, int height, int startX)
+{
+    ensure_init();
+    pixel* rec = (pixel*)recV;
+    switch (kind)
+    {
+    case 0: primitives.saoCuOrgE0(rec, offsets, width, buf0, stride); break;
+    case 1: primitives.saoCuOrgE1(rec, buf0, offsets, stride, width); break;
+    case 2: primitives.saoCuOrgE1_2Rows(rec, buf0, offsets, stride, width); break;
+    case 3: primitives.saoCuOrgE2[0](rec, buf0, buf1, offsets, width, stride); break;
+    case 4: primitives.saoCuOrgE3[0](rec, buf0, offsets, stride, startX, width); break;
+    default: primitives.saoCuOrgB0(rec, offsets, width, height, stride); break;
+    }
+}
+void ref_sao_stats(int kind, const int16_t* diff, const void* recV, intptr_t stride, int8_t* up1, int8_t* upt, int endX, int endY, int32_t* stats, int32_t* count)
+{
+    ensure_init();
+    const pixel* rec = (const pixel*)recV;
+    switch (kind)
+    {
+    case 0: primitives.saoCuStatsE0(diff, rec, stride, endX, endY, stats, count); break;
+    case 1: primitives.saoCuStatsE1(diff, rec, stride, up1, endX, endY, stats, count); break;
+    case 3: primitives.saoCuStatsE2(diff, rec, stride, up1, upt, endX, endY, stats, count); break;
+    case 4: primitives.saoCuStatsE3(diff, rec, stride, up1, endX, endY, stats, count); break;
+    default: primitives.saoCuStatsBO(diff, rec, stride, endX, endY, stats, count); break;
+    }
+}
+void ref_deblock(int chroma, void* src, intptr_t srcStep, intptr_t offset, int a, int b, int c)
+{
+    ensure_init();
+    if (chroma) primitives.pelFilterChroma[0]((pixel*)src, srcStep, offset, a, b, c);
+    else primitives.pelFilterLumaStrong[0]((pixel*)src, srcStep, offset, a, b);
+}
+}

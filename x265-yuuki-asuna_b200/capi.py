@@ -510,3 +510,28 @@ Ctx.ssim_4x4x2_dev = _ctx_ssim_4x4x2_dev
 Ctx.ssim_end4_dev = _ctx_ssim_end4_dev
 Ctx.plane_clip_max_dev = _ctx_plane_clip_max_dev
 Ctx.propagate_cost_dev = _ctx_propagate_cost_dev
+
+
+SAO_E0, SAO_E1, SAO_E1_2ROWS, SAO_E2, SAO_E3, SAO_B0 = range(6)
+SAO_BO = SAO_B0
+SAO_JOB = np.dtype([("recOff", np.int64), ("diffOff", np.int64), ("buf0", np.int64), ("buf1", np.int64), ("offsetOff", np.int64),
+                    ("width", np.int32), ("height", np.int32), ("startX", np.int32), ("pad", np.int32)])
+DEBLOCK_JOB = np.dtype([("srcOff", np.int64), ("srcStep", np.int64), ("offset", np.int64), ("tcP", np.int32), ("tcQ", np.int32),
+                        ("maskQ", np.int32), ("pad", np.int32)])
+
+
+def _ctx_sao_apply_dev(self, kind, depth, dRec, stride, dJobs, n, dBuf, dOffsets, maxWidth):
+    self._chk(self.L.x265b200_sao_apply_dev(self.h, int(kind), int(depth), _vp(dRec), _i64(stride), _vp(dJobs), _i64(n), _vp(dBuf), _vp(dOffsets), int(maxWidth)))
+
+
+def _ctx_sao_stats_dev(self, kind, depth, dDiff, dRec, stride, dJobs, n, dBuf, dStats, dCount):
+    self._chk(self.L.x265b200_sao_stats_dev(self.h, int(kind), int(depth), _vp(dDiff), _vp(dRec), _i64(stride), _vp(dJobs), _i64(n), _vp(dBuf), _vp(dStats), _vp(dCount)))
+
+
+def _ctx_deblock_dev(self, chroma, depth, dPic, dJobs, n):
+    self._chk(self.L.x265b200_deblock_dev(self.h, int(chroma), int(depth), _vp(dPic), _vp(dJobs), _i64(n)))
+
+
+Ctx.sao_apply_dev = _ctx_sao_apply_dev
+Ctx.sao_stats_dev = _ctx_sao_stats_dev
+Ctx.deblock_dev = _ctx_deblock_dev
