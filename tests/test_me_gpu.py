@@ -203,3 +203,40 @@ def test_me_frame_tma_window(ctx, depth, method, subme, merange):
         assert not len(bad), (r, int(bad[0]), jobs[bad[0]], got[r, bad[0]].tolist(), int(ex[bad[0]]), int(ey[bad[0]]), int(ec[bad[0]]), len(bad))
     for b in [dC, dMvp, dOut] + dR:
         b.free()
+
+
+def test_me_frame_ctu_row_bands_equal_full_frame(ctx):
+    """CTU-row sharding: a rank that owns CTU rows [y0, y1) calls the frame search with the plane origins
+    advanced by y0 * 64 rows and marginY increased by the same amount; the union of the bands must equal the full-frame call."""
+    depth, merange = 8, 24
+    ctuCols, ctuRows, NREF = 3, 4, 2
+    W, H = ctuCols * 64, ctuRows * 64
+    pad = 96
+    cur, ref0, S, origin = synth_pair(W, H, pad, depth=depth, seed=91, motion=(3, 5))
+    _, ref1, _, _ = synth_pair(W, H, pad, depth=depth, seed=92, motion=(-6, -2))
+    rowsTotal = H + 2 * pad
+    lam = pkg.lambda_for_qp(30, depth)
+    dC, dR = ctx.to_device(cur), [ctx.to_device(ref0), ctx.to_device(ref1)]
+
+    def run(y0, rows):
+        per_level = [ctuCols * rows * (1 << l) ** 2 for l in range(4)]
+        dOut = ctx.empty(NREF * sum(per_level) * 12)
+        sh = y0 * 64 * S
+        ctx.me_frame_dev(depth, dC.ptr + origin + sh, S, [d.ptr + origin + sh for d in dR], S, pad, pad + y0 * 64, rowsTotal, ctuCols, rows, 15,
+                         None, pkg.ME_HEX, 2, merange, lam, dOut)
+        out = dOut.download(np.int32).reshape(NREF, sum(per_level), 3)
+        dOut.free()
+        return out, per_level
+
+    full, pl_full = run(0, ctuRows)
+    for (y0, rows) in ((0, 1), (1, 2), (3, 1)):
+        band, pl = run(y0, rows)
+        off_f = off_b = 0
+        for level in range(4):
+            per = 1 << level
+            rowlen = ctuCols * per
+            fsl = full[:, off_f + y0 * per * rowlen: off_f + (y0 + rows) * per * rowlen]
+            assert np.array_equal(band[:, off_b:off_b + pl[level]], fsl), (y0, rows, level)
+            off_f += pl_full[level]; off_b += pl[level]
+    for b in [dC] + dR:
+        b.free()

@@ -47,12 +47,18 @@ template<int N> __device__ __forceinline__ void load_taps(int idx, int c[8])
     for (int i = 0; i < N; i++) c[i] = (N == 8) ? c_lumaFilter[idx][i] : c_chromaFilter[idx][i];
 }
 
+// One CTA serves JPC jobs (blocks of <= 16x16 share a CTA: 128 threads on a 64-pixel block would idle half of them and
+// cost one CTA launch per 8x8 block); the TPJ = 128 / JPC threads of a job stride over its pixels.
 template<typename pixel, int N>
 __global__ void __launch_bounds__(128)
-interp_kernel(InterpArgs p)
+interp_kernel(InterpArgs p, int jpc)
 {
-    extern __shared__ int16_t immed[];        // HVPP only: w * (h + N - 1)
-    const x265b200_interp_job job = p.jobs[blockIdx.x];
+    extern __shared__ int16_t immedAll[];     // HVPP only: jpc * w * (h + N - 1)
+    const int tpj = 128 / jpc, sub = threadIdx.x / tpj, tid = threadIdx.x - sub * tpj;
+    const int64_t jidx = (int64_t)blockIdx.x * jpc + sub;
+    const bool live = jidx < p.n;
+    x265b200_interp_job job; job.srcOff = 0; job.dstOff = 0; job.idxX = 0; job.idxY = 0;
+    if (live) job = p.jobs[jidx];
     const int w = p.w, h = p.h, depth = p.depth;
     const int maxVal = (1 << depth) - 1;
     const int headRoom = 14 - depth;
@@ -60,25 +66,28 @@ interp_kernel(InterpArgs p)
 
     if (p.kind == X265B200_IP_HVPP)
     {
+        int16_t* immed = immedAll + (size_t)sub * w * (h + N - 1);
         // horizontal ps pass with row extension: rows -(N/2-1) .. h+N/2-1
         load_taps<N>(job.idxX, c);
         const pixel* s = (const pixel*)p.src + job.srcOff - (N / 2 - 1) - (int64_t)(N / 2 - 1) * p.srcStride;
         const int shift = 6 - headRoom, offset = (int)((unsigned)-8192 << shift);
         const int rows = h + N - 1;
-        for (int e = threadIdx.x; e < rows * w; e += blockDim.x)
-        {
-            int y = e / w, x = e - y * w;
-            const pixel* q = s + (int64_t)y * p.srcStride + x;
-            int sum = 0;
+        if (live)
+            for (int e = tid; e < rows * w; e += tpj)
+            {
+                int y = e / w, x = e - y * w;
+                const pixel* q = s + (int64_t)y * p.srcStride + x;
+                int sum = 0;
 #pragma unroll
-            for (int t = 0; t < N; t++) sum += (int)q[t] * c[t];
-            immed[e] = (int16_t)((sum + offset) >> shift);
-        }
+                for (int t = 0; t < N; t++) sum += (int)q[t] * c[t];
+                immed[e] = (int16_t)((sum + offset) >> shift);
+            }
         __syncthreads();
+        if (!live) return;
         load_taps<N>(job.idxY, c);
         const int shift2 = 6 + headRoom, offset2 = (1 << (shift2 - 1)) + (8192 << 6);
         pixel* d = (pixel*)p.dst + job.dstOff;
-        for (int e = threadIdx.x; e < h * w; e += blockDim.x)
+        for (int e = tid; e < h * w; e += tpj)
         {
             int y = e / w, x = e - y * w;
             int sum = 0;
@@ -90,12 +99,13 @@ interp_kernel(InterpArgs p)
         }
         return;
     }
+    if (!live) return;
 
     if (p.kind == X265B200_IP_P2S)
     {
         const pixel* s = (const pixel*)p.src + job.srcOff;
         int16_t* d = (int16_t*)p.dst + job.dstOff;
-        for (int e = threadIdx.x; e < h * w; e += blockDim.x)
+        for (int e = tid; e < h * w; e += tpj)
         {
             int y = e / w, x = e - y * w;
             int16_t val = (int16_t)((int)s[(int64_t)y * p.srcStride + x] << headRoom);
@@ -122,7 +132,7 @@ interp_kernel(InterpArgs p)
     default /* VSS */:    shift = 6; offset = 0; break;
     }
 
-    for (int e = threadIdx.x; e < rows * w; e += blockDim.x)
+    for (int e = tid; e < rows * w; e += tpj)
     {
         int y = e / w, x = e - y * w;
         int64_t o = base + (int64_t)y * p.srcStride + x;
@@ -160,17 +170,19 @@ int interp_dev(Ctx* ctx, int kind, int taps, int depth, int w, int h, const void
     if (upload_filters(ctx)) return -1;
     InterpArgs a; a.src = src; a.srcStride = srcStride; a.dst = dst; a.dstStride = dstStride; a.jobs = jobs; a.n = n;
     a.kind = kind; a.taps = taps; a.depth = depth; a.w = w; a.h = h; a.isRowExt = isRowExt;
-    size_t smem = kind == X265B200_IP_HVPP ? (size_t)w * (h + taps - 1) * sizeof(int16_t) : 0;
-    dim3 grid((unsigned)n), block(128);
+    // jobs per CTA: ~64 output pixels per thread-group keeps every thread busy for small blocks
+    const int jpc = w * h <= 32 ? 8 : (w * h <= 64 ? 4 : (w * h <= 128 ? 2 : 1));
+    size_t smem = kind == X265B200_IP_HVPP ? (size_t)jpc * w * (h + taps - 1) * sizeof(int16_t) : 0;
+    dim3 grid((unsigned)((n + jpc - 1) / jpc)), block(128);
     if (depth > 8)
     {
-        if (taps == 8) interp_kernel<uint16_t, 8><<<grid, block, smem, ctx->stream>>>(a);
-        else           interp_kernel<uint16_t, 4><<<grid, block, smem, ctx->stream>>>(a);
+        if (taps == 8) interp_kernel<uint16_t, 8><<<grid, block, smem, ctx->stream>>>(a, jpc);
+        else           interp_kernel<uint16_t, 4><<<grid, block, smem, ctx->stream>>>(a, jpc);
     }
     else
     {
-        if (taps == 8) interp_kernel<uint8_t, 8><<<grid, block, smem, ctx->stream>>>(a);
-        else           interp_kernel<uint8_t, 4><<<grid, block, smem, ctx->stream>>>(a);
+        if (taps == 8) interp_kernel<uint8_t, 8><<<grid, block, smem, ctx->stream>>>(a, jpc);
+        else           interp_kernel<uint8_t, 4><<<grid, block, smem, ctx->stream>>>(a, jpc);
     }
     ctx->launches++;
     return check(cudaGetLastError(), "interp kernel launch");
