@@ -11,6 +11,7 @@
 // quarter-pel average built and costed per 4x4 cell in registers) -- a 64-pixel CU cannot feed 32 lanes (the
 // one-warp-per-CU kernel in lookahead_kernels.cu tops out at 0.85 ms per 32 640-CU field; profiles/r01_lookahead.txt).
 #define ME_FORCE_THREAD 1
+#define ME_LOWRES_ONLY 1
 #include "me_device.cuh"
 #include "lookahead_args.cuh"
 
@@ -21,7 +22,7 @@ constexpr int LAT_WARPS = 2;
 // HME = false: the plain lookahead (search method and range are compile-time constants of the hot kernel);
 // HME = true: either level of --hme (runtime method / range, optional quarter-resolution candidate)
 template<typename pixel, bool HME>
-__global__ void __launch_bounds__(LAT_WARPS * 32)
+__global__ void __launch_bounds__(LAT_WARPS * 32, 8)
 la_search_thread_kernel(LASearchArgs p)
 {
     // 8 lanes share one 8-row x 64-pixel tile: lane L's cached source CU sits at column (L & 7) * 8, row stride 64

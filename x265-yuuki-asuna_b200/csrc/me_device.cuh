@@ -13,14 +13,28 @@
 // A translation unit whose searches ALL run in per-thread mode defines ME_FORCE_THREAD before including this header:
 // the warp-cooperative bodies are then compiled out (smaller kernel, see me_frame_kernels.cu).  The variant lives in
 // its own inline namespace so the differently-compiled templates never share a symbol.
+// A thread-only translation unit may also fix the plane kind at compile time: ME_LOWRES_ONLY (the lookahead: every search
+// runs on the 4 hpel planes) or ME_FULLRES_ONLY (the frame search) drops the other sub-pel machinery from the kernel, which
+// keeps its register allocation independent of code it never executes.
 #ifdef ME_FORCE_THREAD
 #define ME_IS_THREAD(s) true
 #define ME_PU_W(s) 8                      /* every lane searches an 8-pixel-wide sub-block */
+#if defined(ME_LOWRES_ONLY)
+#define ME_VARIANT me_thread_lowres
+#define ME_IS_LOWRES(s) true
+#elif defined(ME_FULLRES_ONLY)
+#define ME_VARIANT me_thread_fullres
+#define ME_IS_LOWRES(s) false
+#else
 #define ME_VARIANT me_thread_only
+#endif
 #else
 #define ME_IS_THREAD(s) ((s).perThread)
 #define ME_PU_W(s) ((s).w)
 #define ME_VARIANT me_generic
+#endif
+#ifndef ME_IS_LOWRES
+#define ME_IS_LOWRES(s) ((s).isLowres)
 #endif
 
 namespace x265b200 {
@@ -634,85 +648,151 @@ __device__ __noinline__ int thread_subpel_cost(const MEState<pixel>& s, const pi
     int acc = 0;
     if (!yFrac)
     {
-        // luma_hpp
+        // luma_hpp.  One row of 4 pixels per loop iteration (~55 instructions) so that the loop plus the shared cell cost stay
+        // inside the per-scheduler L0 instruction cache: the kernel is bound by instruction supply (ncu: stall_no_instruction is
+        // ~60 % of the samples everywhere in this function; L1.5 -> L0 delivers ~2 instructions/clk/SM), not by issue slots.
 #pragma unroll 1
         for (int y0 = 0; y0 < H; y0 += 4)
 #pragma unroll 1
             for (int x = 0; x < W; x += 4)
             {
-                int o[4][4];
+                CellRows<pixel> rows;
 #pragma unroll
+                for (int j = 0; j < 4 * NW4; j++) rows.w[j] = 0;
+#pragma unroll 1
                 for (int r = 0; r < 4; r++)
                 {
-                    int sums[4];
+                    int sums[4], o[4];
                     hsums(src + (int64_t)(y0 + r) * s.stride + x - 3, sums);
 #pragma unroll
                     for (int k = 0; k < 4; k++)
                     {
                         int val = (int16_t)((sums[k] + 32) >> 6);
-                        o[r][k] = val < 0 ? 0 : (val > maxVal ? maxVal : val);
+                        o[k] = val < 0 ? 0 : (val > maxVal ? maxVal : val);
                     }
+#pragma unroll
+                    for (int j = 0; j < 3 * NW4; j++) rows.w[j] = rows.w[j + NW4];
+                    pack4<pixel>(o, &rows.w[3 * NW4]);
                 }
-                acc += cell_cost<pixel>(s.fenc + y0 * 64 + x, o, useSatd);
+                acc += cell_cost_packed<pixel>(s.fenc + y0 * 64 + x, rows, useSatd);
             }
         return acc;
     }
-    // luma_vpp (xFrac == 0) or luma_hvpp = hps(isRowExt) + vsp
+    // luma_vpp (xFrac == 0) or luma_hvpp = hps(isRowExt) + vsp, again one (first-stage) row per loop iteration: the 8 rows
+    // under the vertical taps live in a small register window that moves down by one row per iteration.  Output row i needs
+    // source rows i-3 .. i+4, so iteration i brings in row i+4; the first 7 iterations only fill the window.
     int cv[8];
 #pragma unroll
     for (int t = 0; t < 8; t++) cv[t] = c_meLumaFilter[yFrac][t];
+    if constexpr (sizeof(pixel) == 1)
+    {
+        if (!xFrac)
+        {
+            // 8-bit luma_vpp: the window holds pixel words; per output row the two 4x4 byte blocks are transposed (8 PRMT each)
+            // and every pixel is two u8 x s8 dot products (DP4A) down its column
+            const uint32_t cvlo = pack_taps(cv, 0), cvhi = pack_taps(cv, 4);
+#pragma unroll 1
+            for (int x = 0; x < W; x += 4)
+            {
+                uint32_t wq[8];
+#pragma unroll
+                for (int t = 0; t < 8; t++) wq[t] = 0;
+                CellRows<pixel> rows;
+#pragma unroll
+                for (int j = 0; j < 4; j++) rows.w[j] = 0;
+#pragma unroll 1
+                for (int i = -7; i < H; i++)
+                {
+#pragma unroll
+                    for (int t = 0; t < 7; t++) wq[t] = wq[t + 1];
+                    ld_words<pixel, 1>(src + (int64_t)(i + 4) * s.stride + x, &wq[7]);
+                    if (i < 0) continue;
+                    uint32_t ca[4], cb[4];
+                    {
+                        const uint32_t t0 = __byte_perm(wq[0], wq[1], 0x5140), t1 = __byte_perm(wq[2], wq[3], 0x5140);
+                        const uint32_t t2 = __byte_perm(wq[0], wq[1], 0x7362), t3 = __byte_perm(wq[2], wq[3], 0x7362);
+                        ca[0] = __byte_perm(t0, t1, 0x5410); ca[1] = __byte_perm(t0, t1, 0x7632);
+                        ca[2] = __byte_perm(t2, t3, 0x5410); ca[3] = __byte_perm(t2, t3, 0x7632);
+                        const uint32_t u0 = __byte_perm(wq[4], wq[5], 0x5140), u1 = __byte_perm(wq[6], wq[7], 0x5140);
+                        const uint32_t u2 = __byte_perm(wq[4], wq[5], 0x7362), u3 = __byte_perm(wq[6], wq[7], 0x7362);
+                        cb[0] = __byte_perm(u0, u1, 0x5410); cb[1] = __byte_perm(u0, u1, 0x7632);
+                        cb[2] = __byte_perm(u2, u3, 0x5410); cb[3] = __byte_perm(u2, u3, 0x7632);
+                    }
+                    int o[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                    {
+                        const int val = (int16_t)((dp4a_us(cb[k], cvhi, dp4a_us(ca[k], cvlo, 0)) + 32) >> 6);
+                        o[k] = val < 0 ? 0 : (val > maxVal ? maxVal : val);
+                    }
+                    rows.w[0] = rows.w[1]; rows.w[1] = rows.w[2]; rows.w[2] = rows.w[3];
+                    pack4<pixel>(o, &rows.w[3]);
+                    if ((i & 3) == 3) acc += cell_cost_packed<pixel>(s.fenc + (i - 3) * 64 + x, rows, useSatd);
+                }
+            }
+            return acc;
+        }
+    }
+    // first-stage rows as int16 pairs (two words per row of 4); the vertical taps run as DP2A on row pairs
     const int sh1 = 6 - headRoom, off1 = (int)((unsigned)-8192 << sh1);
     const int sh2 = xFrac ? 6 + headRoom : 6, off2 = xFrac ? (1 << (sh2 - 1)) + (8192 << 6) : 32;
+    uint32_t tp[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) tp[q] = (uint32_t)(cv[2 * q] & 0xff) | ((uint32_t)(cv[2 * q + 1] & 0xff) << 8);
 #pragma unroll 1
     for (int x = 0; x < W; x += 4)
     {
-        int win[11][4];                      // win[r] = (first-stage) row y0 + r - 3 of this strip
+        uint32_t wp[8][2];
 #pragma unroll
-        for (int r = 0; r < 11; r++)
+        for (int t = 0; t < 8; t++) { wp[t][0] = 0; wp[t][1] = 0; }
+        CellRows<pixel> rows;
 #pragma unroll
-            for (int k = 0; k < 4; k++) win[r][k] = 0;
-        // two lead-in steps (y0 = -8, -4) fill rows -3..3; each later step adds 4 rows and emits one cell
+        for (int j = 0; j < 4 * NW4; j++) rows.w[j] = 0;
 #pragma unroll 1
-        for (int y0 = -8; y0 < H; y0 += 4)
+        for (int i = -7; i < H; i++)
         {
 #pragma unroll
-            for (int r = 0; r < 4; r++)
+            for (int t = 0; t < 7; t++) { wp[t][0] = wp[t + 1][0]; wp[t][1] = wp[t + 1][1]; }
             {
-                const pixel* p = src + (int64_t)(y0 + 4 + r) * s.stride + x;
+                const pixel* p = src + (int64_t)(i + 4) * s.stride + x;
+                int v[4];
                 if (xFrac)
                 {
                     int sums[4];
                     hsums(p - 3, sums);
 #pragma unroll
-                    for (int k = 0; k < 4; k++) win[7 + r][k] = (int16_t)((sums[k] + off1) >> sh1);
+                    for (int k = 0; k < 4; k++) v[k] = (sums[k] + off1) >> sh1;
                 }
                 else
                 {
                     uint32_t rw[NW4];
                     ld_words<pixel, NW4>(p, rw);
-                    unpack4<pixel>(rw, win[7 + r]);
+                    unpack4<pixel>(rw, v);
                 }
+                wp[7][0] = (uint32_t)(v[0] & 0xffff) | ((uint32_t)v[1] << 16);
+                wp[7][1] = (uint32_t)(v[2] & 0xffff) | ((uint32_t)v[3] << 16);
             }
-            if (y0 >= 0)
+            if (i < 0) continue;
+            int o[4];
+#pragma unroll
+            for (int hf = 0; hf < 2; hf++)
             {
-                int o[4][4];
+                int s0 = 0, s1 = 0;
 #pragma unroll
-                for (int r = 0; r < 4; r++)
-#pragma unroll
-                    for (int k = 0; k < 4; k++)
-                    {
-                        int sum = 0;
-#pragma unroll
-                        for (int t = 0; t < 8; t++) sum += win[r + t][k] * cv[t];
-                        int val = (int16_t)((sum + off2) >> sh2);
-                        o[r][k] = val < 0 ? 0 : (val > maxVal ? maxVal : val);
-                    }
-                acc += cell_cost<pixel>(s.fenc + y0 * 64 + x, o, useSatd);
+                for (int q = 0; q < 4; q++)
+                {
+                    const uint32_t ra = wp[2 * q][hf], rb = wp[2 * q + 1][hf];
+                    s0 = __dp2a_lo((int)__byte_perm(ra, rb, 0x5410), (int)tp[q], s0);      // pixel 2*hf    : rows 2q, 2q+1
+                    s1 = __dp2a_lo((int)__byte_perm(ra, rb, 0x7632), (int)tp[q], s1);      // pixel 2*hf + 1
+                }
+                const int v0 = (int16_t)((s0 + off2) >> sh2), v1 = (int16_t)((s1 + off2) >> sh2);
+                o[2 * hf] = v0 < 0 ? 0 : (v0 > maxVal ? maxVal : v0);
+                o[2 * hf + 1] = v1 < 0 ? 0 : (v1 > maxVal ? maxVal : v1);
             }
 #pragma unroll
-            for (int r = 0; r < 7; r++)
-#pragma unroll
-                for (int k = 0; k < 4; k++) win[r][k] = win[r + 4][k];
+            for (int j = 0; j < 3 * NW4; j++) rows.w[j] = rows.w[j + NW4];
+            pack4<pixel>(o, &rows.w[3 * NW4]);
+            if ((i & 3) == 3) acc += cell_cost_packed<pixel>(s.fenc + (i - 3) * 64 + x, rows, useSatd);
         }
     }
     return acc;
@@ -1354,6 +1434,9 @@ template<typename pixel>
 __device__ int motion_estimate(const MEState<pixel>& s, MV2 mvmin, MV2 mvmax, MV2 qmvp, int numCand, const int* mvc /* [numCand][2] */,
                                int merange, int searchMethod, int subpelRefine, int maxSlices, int partEnumIs64, int& outx, int& outy)
 {
+#ifdef ME_LOWRES_ONLY
+    numCand = 0; maxSlices = 1;      // the lookahead passes neither MV candidates nor slice bounds (slicetype.cpp:3313-3315)
+#endif
     MESearch<pixel> S(s);
     S.mvmin = mvmin; S.mvmax = mvmax;
     const MV2 qmvmin = mv2(mvmin.x << 2, mvmin.y << 2), qmvmax = mv2(mvmax.x << 2, mvmax.y << 2);
@@ -1361,7 +1444,7 @@ __device__ int motion_estimate(const MEState<pixel>& s, MV2 mvmin, MV2 mvmax, MV
     // measure SAD cost at clipped QPEL MVP (motion.cpp:770-778)
     MV2 pmv = mv2(max(min(qmvp.x, qmvmax.x), qmvmin.x), max(min(qmvp.y, qmvmax.y), qmvmin.y));
     MV2 bestpre = pmv;
-    int bprecost = s.isLowres ? lowres_qpel_cost<pixel>(s, pmv.x, pmv.y, false) : subpel_compare<pixel>(s, pmv.x, pmv.y, false);
+    int bprecost = ME_IS_LOWRES(s) ? lowres_qpel_cost<pixel>(s, pmv.x, pmv.y, false) : subpel_compare<pixel>(s, pmv.x, pmv.y, false);
 
     // re-measure full pel rounded MVP with SAD as search start point (:780-784)
     S.bmv = mv2((pmv.x + 2) >> 2, (pmv.y + 2) >> 2);
@@ -1609,7 +1692,7 @@ __device__ int motion_estimate(const MEState<pixel>& s, MV2 mvmin, MV2 mvmax, MV
 
     if (!bcost && !refineOnly)
         bcost = mvcost(s, bmv.x, bmv.y);                                  // :1465-1470 (refineMV has no such exit)
-    else if (s.isLowres)                                                  // :1471-1503
+    else if (ME_IS_LOWRES(s))                                             // :1471-1503
     {
         int bdir = 0;
         for (int i = 1; i <= wl.hpel_dirs; i++)

@@ -13,6 +13,7 @@
 // numCandidates = 0, merange, ...) with the CTU's predictor mvp shared by all its PUs (Search::setSearchRange
 // shape, search.cpp:2724-2769, before picture-boundary clipping).
 #define ME_FORCE_THREAD 1
+#define ME_FULLRES_ONLY 1
 #include "me_device.cuh"
 #include "x265b200.h"
 #include <cuda.h>
