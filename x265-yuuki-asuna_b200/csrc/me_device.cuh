@@ -107,14 +107,22 @@ __device__ __forceinline__ int mvcost(const MEState<pixel>& s, int qx, int qy)
     return ((int)s.cost[ix] + (int)s.cost[iy]) & 0xffff;      // bitcost.h:45 returns uint16_t
 }
 
+// The cached source PU (fenc) lives in shared memory in every kernel that uses this header: say so at the load sites.
+template<typename T> __device__ __forceinline__ const T* smem_hint(const T* p) { __builtin_assume(__isShared(p)); return p; }
+
 // ---- row loaders ---------------------------------------------------------------------------------
 // NW consecutive 32-bit words of pixels starting at ANY pixel address (generic pointer: global plane or
 // shared-memory window).  Loads NW+1 aligned words and funnel-shifts.
-template<typename pixel, int NW>
+// A translation unit whose reference blocks always sit in the shared-memory window defines ME_REF_IN_SMEM: the loader
+// then tells the compiler so (LDS with 32-bit addresses instead of generic LD + address-space resolution).
+template<typename pixel, int NW, bool ANYSPACE = false>
 __device__ __forceinline__ void ld_words(const pixel* p, uint32_t out[NW])
 {
     uintptr_t a = (uintptr_t)p;
     const uint32_t* w = (const uint32_t*)(a & ~(uintptr_t)3);
+#ifdef ME_REF_IN_SMEM
+    if (!ANYSPACE) __builtin_assume(__isShared(w));
+#endif
     const uint32_t sh = (uint32_t)(a & 3) * 8;
     uint32_t t[NW + 1];
 #pragma unroll
@@ -135,7 +143,7 @@ __device__ __forceinline__ int sad_seg(const pixel* f, const pixel* r)
     constexpr int NW = SEG * (int)sizeof(pixel) / 4;
     uint32_t rw[NW];
     ld_words<pixel, NW>(r, rw);
-    const uint32_t* fw = (const uint32_t*)f;
+    const uint32_t* fw = smem_hint((const uint32_t*)f);
     uint32_t acc = 0;
 #pragma unroll
     for (int i = 0; i < NW; i++) acc += sad_word<pixel>(fw[i], rw[i]);
@@ -230,7 +238,7 @@ __device__ __forceinline__ int thread_sad_w8(const MEState<pixel>& s, const pixe
         for (int y = 0; y < 8; y++)
         {
             ld_words<pixel, NW>(r + (int64_t)(y0 + y) * rs, rw[y]);
-            f[y] = *(const fvec*)(s.fenc + (y0 + y) * 64);
+            f[y] = *smem_hint((const fvec*)(s.fenc + (y0 + y) * 64));
         }
 #pragma unroll
         for (int y = 0; y < 8; y++)
@@ -239,6 +247,23 @@ __device__ __forceinline__ int thread_sad_w8(const MEState<pixel>& s, const pixe
 #pragma unroll
             for (int i = 0; i < NW; i++) acc += sad_word<pixel>(fw[i], rw[y][i]);
         }
+    }
+    return (int)acc;
+}
+// per-thread SAD of the 8-wide sub-block against a block in ANY address space (row by row; rare path)
+template<typename pixel>
+__device__ __noinline__ int thread_sad_anyspace(const MEState<pixel>& s, const pixel* r, int64_t rs)
+{
+    constexpr int NW = 8 * (int)sizeof(pixel) / 4;
+    uint32_t acc = 0;
+#pragma unroll 1
+    for (int y = 0; y < s.h; y++)
+    {
+        uint32_t rw[NW];
+        ld_words<pixel, NW, true>(r + (int64_t)y * rs, rw);
+        const uint32_t* fw = smem_hint((const uint32_t*)(s.fenc + y * 64));
+#pragma unroll
+        for (int i = 0; i < NW; i++) acc += sad_word<pixel>(fw[i], rw[i]);
     }
     return (int)acc;
 }
@@ -281,7 +306,7 @@ __device__ __forceinline__ int thread_satd(const MEState<pixel>& s, const pixel*
             {
                 int a[4], b[4];
                 uint32_t rw[NW];
-                unpack4<pixel>((const uint32_t*)(s.fenc + (cy + i) * 64 + cx), a);
+                unpack4<pixel>(smem_hint((const uint32_t*)(s.fenc + (cy + i) * 64 + cx)), a);
                 ld_words<pixel, NW>(r + (int64_t)(cy + i) * rs + cx, rw);
                 unpack4<pixel>(rw, b);
 #pragma unroll
@@ -343,7 +368,7 @@ __device__ __noinline__ int warp_satd(const MEState<pixel>& s, const pixel* r, i
         {
             int a[4], b[4];
             uint32_t rw[NW];
-            unpack4<pixel>((const uint32_t*)(f + i * 64), a);
+            unpack4<pixel>(smem_hint((const uint32_t*)(f + i * 64)), a);
             ld_words<pixel, NW>(q + i * rs, rw);
             unpack4<pixel>(rw, b);
 #pragma unroll
@@ -582,7 +607,7 @@ __device__ __noinline__ int cell_cost_packed(const pixel* f, CellRows<pixel> row
         for (int i = 0; i < 4; i++)
         {
             int a[4], o[4];
-            unpack4<pixel>((const uint32_t*)(f + i * 64), a);
+            unpack4<pixel>(smem_hint((const uint32_t*)(f + i * 64)), a);
             unpack4<pixel>(&rows.w[i * NW], o);
 #pragma unroll
             for (int k = 0; k < 4; k++) d[i][k] = a[k] - o[k];
@@ -601,7 +626,7 @@ __device__ __noinline__ int cell_cost_packed(const pixel* f, CellRows<pixel> row
 #pragma unroll
     for (int i = 0; i < 4; i++)
     {
-        const uint32_t* fw = (const uint32_t*)(f + i * 64);
+        const uint32_t* fw = smem_hint((const uint32_t*)(f + i * 64));
 #pragma unroll
         for (int j = 0; j < NW; j++) acc += sad_word<pixel>(fw[j], rows.w[i * NW + j]);
     }
@@ -1459,7 +1484,12 @@ __device__ int motion_estimate(const MEState<pixel>& s, MV2 mvmin, MV2 mvmax, MV
     // measure SAD cost at MV(0) if MVP is not zero (:786-796)
     if ((pmv.x | pmv.y) && !refineOnly)
     {
+#ifdef ME_REF_IN_SMEM
+        // the zero-MV block may lie outside the staged window: read it from the global plane
+        int cost = group_sum<pixel>(s, thread_sad_anyspace<pixel>(s, s.gfref, s.gstride)) + mvcost(s, 0, 0);
+#else
         int cost = warp_sad_block<pixel>(s, s.gfref, s.gstride) + mvcost(s, 0, 0);
+#endif
         if (cost < S.bcost)
         {
             S.bcost = cost;

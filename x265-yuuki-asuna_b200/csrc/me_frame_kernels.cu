@@ -14,6 +14,7 @@
 // shape, search.cpp:2724-2769, before picture-boundary clipping).
 #define ME_FORCE_THREAD 1
 #define ME_FULLRES_ONLY 1
+#define ME_REF_IN_SMEM 1          /* every reference block the search reads is inside the TMA-staged window */
 #include "me_device.cuh"
 #include "x265b200.h"
 #include <cuda.h>
@@ -92,7 +93,7 @@ __device__ unsigned long long g_mfCycles[MF_WARPS + 1];
 // Residency: 3 CTAs per SM at 168 registers measured best (3.21 ms per 2160p frame x 3 refs; 4 CTAs at 128 registers: 3.31 ms,
 // 2 CTAs at 212 registers: 3.49 ms).
 template<typename pixel>
-__global__ void __launch_bounds__(MF_WARPS * 32, 3)
+__global__ void __launch_bounds__(MF_WARPS * 32, 4)
 me_frame_kernel(const __grid_constant__ MEFrameMaps maps, MEFrameArgs p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
