@@ -319,22 +319,22 @@ intra_allangs8_kernel(const uint8_t* __restrict__ refPix, const uint8_t* __restr
     constexpr int TOT = G * (ALL35 ? 1 : 2) * LEN;              // neighbour bytes staged per group
     constexpr int NU = (TOT + 255) / 256;                       // ... = NU bytes per thread
     __shared__ int sDc[G];
-    __shared__ uint16_t jtab[33 * LW];
+    __shared__ __align__(8) uint16_t jtab[33 * PITCH];          // (mode, L) -> neighbour index, rows padded to the line pitch
     __shared__ uint8_t s2[G][2 * SP];                           // per block: [unfiltered | filtered] neighbours
     __shared__ __align__(16) uint8_t line[G][33][PITCH];        // entry L <-> ref[L - N]
     const int tid = threadIdx.x;
     const int thr = N == 8 ? 7 : (N == 16 ? 1 : (N == 32 ? 0 : 99));      // constants.cpp:561 g_intraFilterFlags
 
-    for (int e = tid; e < 33 * LW; e += 256)
+    for (int e = tid; e < 33 * PITCH; e += 256)
     {
-        const int m = e / LW, L = e - m * LW, idx = L - N, mode = m + 2;
+        const int m = e / PITCH, L = e - m * PITCH, idx = L - N, mode = m + 2;
         const bool hor = mode < 18;
         const int angleOffset = hor ? 10 - mode : mode - 26;
         const int angle = c_angle[8 + angleOffset];
         int i;                                                  // index into the (flipped) neighbour view, intrapred.cpp:146-172
         if (angle >= 0 || idx >= -1) i = idx + 1;
         else i = N2 + ((128 + (-1 - idx) * c_invAngle[-angleOffset - 1]) >> 8);
-        i = max(0, min(i, 4 * N));                              // entries outside a mode's reach are never read back
+        i = max(0, min(i, 4 * N));                              // entries outside a mode's reach (and the row padding) are never used
         const int j = (!hor || i == 0) ? i : (i <= N2 ? N2 + i : i - N2);
         jtab[e] = (uint16_t)(j + (min(abs(mode - 26), abs(mode - 10)) > thr ? SP : 0));
     }
@@ -394,10 +394,14 @@ intra_allangs8_kernel(const uint8_t* __restrict__ refPix, const uint8_t* __restr
         for (int u = 0; u < NU; u++)
             if (sOk[u] && nb0 + gOf[u] < n) v[u] = (sFilt[u] ? filtPix : refPix)[nb0 * LEN + srcOff[u]];
 
-        for (int e = tid; e < G * 33 * LW; e += 256)
+        // the 33 projected reference lines of every block, four entries (one word) per thread
+        for (int e = tid; e < G * 33 * (PITCH / 4); e += 256)
         {
-            const int g = e / (33 * LW), r = e - g * (33 * LW), m = r / LW, L = r - m * LW;
-            line[g][m][L] = s2[g][jtab[r]];
+            const int g = e / (33 * (PITCH / 4)), r = e - g * (33 * (PITCH / 4));
+            const uint2 jt = *(const uint2*)&jtab[r * 4];
+            const uint8_t* sn = s2[g];
+            const uint32_t word = (uint32_t)sn[jt.x & 0xffff] | ((uint32_t)sn[jt.x >> 16] << 8) | ((uint32_t)sn[jt.y & 0xffff] << 16) | ((uint32_t)sn[jt.y >> 16] << 24);
+            ((uint32_t*)&line[g][0][0])[r] = word;
         }
         __syncthreads();
 
@@ -442,13 +446,23 @@ intra_allangs8_kernel(const uint8_t* __restrict__ refPix, const uint8_t* __restr
                 uint32_t w[NWD + 1];
 #pragma unroll
                 for (int k = 0; k <= NWD; k++) w[k] = src[k];
+                // source bytes s0..s4k+4 of the line; E = (s0, s2), O = (s1, s3), X = (s2, s4) as 16-bit lanes per word:
+                // even outputs g*E + f*O, odd outputs g*O + f*X (255*32 + 16 < 2^16: no carry between lanes), PRMT repacks
+                uint32_t E[NWD + 1], O[NWD];
 #pragma unroll
                 for (int k = 0; k < NWD; k++)
                 {
-                    const uint32_t A = __funnelshift_r(w[k], w[k + 1], sh), B = __funnelshift_rc(w[k], w[k + 1], sh + 8);
-                    const uint32_t r02 = (((A & 0x00FF00FFu) * gg + (B & 0x00FF00FFu) * f + 0x00100010u) >> 5) & 0x00FF00FFu;
-                    const uint32_t r13 = ((((A >> 8) & 0x00FF00FFu) * gg + ((B >> 8) & 0x00FF00FFu) * f + 0x00100010u) >> 5) & 0x00FF00FFu;
-                    ow[c * NWD + k] = r02 | (r13 << 8);
+                    const uint32_t A = __funnelshift_r(w[k], w[k + 1], sh);
+                    E[k] = __byte_perm(A, 0u, 0x4240); O[k] = __byte_perm(A, 0u, 0x4341);
+                }
+                E[NWD] = __byte_perm(w[NWD] >> sh, 0u, 0x4240);
+#pragma unroll
+                for (int k = 0; k < NWD; k++)
+                {
+                    const uint32_t X = __byte_perm(E[k], E[k + 1], 0x5432);
+                    const uint32_t ev = (E[k] * gg + (O[k] * f + 0x00100010u)) >> 5;
+                    const uint32_t od = (O[k] * gg + (X * f + 0x00100010u)) >> 5;
+                    ow[c * NWD + k] = __byte_perm(ev, od, 0x6240);
                 }
                 if (!angle && bLuma && x == 0)
                 {
