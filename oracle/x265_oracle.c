@@ -465,3 +465,228 @@ void orc_intra_pred(int depth, int log2N, int mode, int bFilter, const void* src
         for (int x = 0; x < N; x++)
             put_px(dst, depth, y * ds + x, hor ? pred[x][y] : pred[y][x]);
 }
+
+/* ======================================================================================================================
+ * Families added late in round 1: SEA support, in-loop filters, cuTree helpers, the residual pipeline chain.
+ * ====================================================================================================================== */
+
+/* common/pixel.cpp:121-165  ads_x1 / ads_x2 / ads_x4<lx,ly>: kind = 1, 2, 4; lxHalf = lx >> 1 */
+int orc_ads(int kind, int lxHalf, const int* encDC, const uint32_t* sums, intptr_t delta, const uint16_t* costMvX, int16_t* mvs, int width, int thresh)
+{
+    int nmv = 0;
+    for (int i = 0; i < width; i++, sums++)
+    {
+        long long ads = llabs((long long)encDC[0] - (long long)sums[0]);
+        if (kind == 2) ads += llabs((long long)encDC[1] - (long long)sums[delta]);
+        if (kind == 4)
+            ads += llabs((long long)encDC[1] - (long long)sums[lxHalf]) + llabs((long long)encDC[2] - (long long)sums[delta]) +
+                   llabs((long long)encDC[3] - (long long)sums[delta + lxHalf]);
+        ads += costMvX[i];
+        if ((int)ads < thresh) mvs[nmv++] = (int16_t)i;
+    }
+    return nmv;
+}
+
+/* encoder/framefilter.cpp:39-140 (integral_init{4..32}h / v) driven as FrameFilter::computeMEIntegral drives them (:722-825):
+ * running column sums of horizontal w-sums, turned into w x h box sums h rows later.  planes[k]: origin (pixel 0,0). */
+void orc_sea_integral(int depth, const void* reconOrigin, intptr_t stride, int padX, int padY, int maxHeight, uint32_t* const planes[12])
+{
+    static const int W[12] = { 32, 32, 32, 24, 16, 16, 16, 12, 8, 8, 4, 4 }, H[12] = { 32, 24, 8, 32, 16, 12, 4, 16, 32, 8, 16, 4 };
+    for (int k = 0; k < 12; k++)
+    {
+        uint32_t* base = planes[k] - padY * stride - padX;
+        memset(base, 0, stride * sizeof(uint32_t));                                   /* :757 */
+        const int height = maxHeight + padY - 1;                                      /* lastRow: height += padY - 1 */
+        for (int y = -padY; y < height; y++)
+        {
+            const void* pix = padd(reconOrigin, depth, y * stride - padX);
+            uint32_t* sum = planes[k] + (y + 1) * stride - padX;
+            int32_t v = 0;
+            for (int i = 0; i < W[k]; i++) v += px(pix, depth, i);
+            for (int x = 0; x < stride - W[k]; x++)                                    /* integral_initNh_c */
+            {
+                sum[x] = (uint32_t)v + sum[x - stride];
+                v += px(pix, depth, x + W[k]) - px(pix, depth, x);
+            }
+            if (y >= H[k] - padY)                                                      /* integral_initNv_c on the row H rows up */
+            {
+                uint32_t* top = sum - H[k] * stride;
+                for (int x = 0; x < stride; x++) top[x] = top[x + H[k] * stride] - top[x];
+            }
+        }
+    }
+}
+
+static int sgn_of(int x) { return (x > 0) - (x < 0); }                                /* common/loopfilter.cpp:33-36 signOf */
+static int clip_px(int v, int depth) { int m = (1 << depth) - 1; return v < 0 ? 0 : (v > m ? m : v); }
+static void put_pix(void* p, int depth, intptr_t i, int v)
+{
+    if (depth == 8) ((uint8_t*)p)[i] = (uint8_t)v; else ((uint16_t*)p)[i] = (uint16_t)v;
+}
+
+/* common/loopfilter.cpp:45-139: kind 0 processSaoCUE0, 1 E1, 2 E1_2Rows, 3 E2, 4 E3, 5 B0 (sequential, in place, as written there) */
+void orc_sao_apply(int kind, int depth, void* rec, intptr_t stride, int8_t* buf0, int8_t* buf1, const int8_t* offset, int width, int height, int startX)
+{
+    if (kind == 0)
+        for (int y = 0; y < 2; y++)
+        {
+            int signLeft0 = buf0[y];
+            for (int x = 0; x < width; x++)
+            {
+                int d = px(rec, depth, y * stride + x) - px(rec, depth, y * stride + x + 1);
+                int signRight = sgn_of(d), edgeType = signRight + signLeft0 + 2;
+                signLeft0 = -signRight;
+                put_pix(rec, depth, y * stride + x, clip_px(px(rec, depth, y * stride + x) + offset[edgeType], depth));
+            }
+        }
+    else if (kind == 1 || kind == 2)
+        for (int y = 0; y < (kind == 1 ? 1 : 2); y++)
+            for (int x = 0; x < width; x++)
+            {
+                int signDown = sgn_of(px(rec, depth, y * stride + x) - px(rec, depth, (y + 1) * stride + x));
+                int edgeType = signDown + buf0[x] + 2;
+                buf0[x] = (int8_t)-signDown;
+                put_pix(rec, depth, y * stride + x, clip_px(px(rec, depth, y * stride + x) + offset[edgeType], depth));
+            }
+    else if (kind == 3)
+        for (int x = 0; x < width; x++)
+        {
+            int signDown = sgn_of(px(rec, depth, x) - px(rec, depth, x + stride + 1));
+            int edgeType = signDown + buf1[x] + 2;
+            buf0[x + 1] = (int8_t)-signDown;                                          /* bufft */
+            put_pix(rec, depth, x, clip_px(px(rec, depth, x) + offset[edgeType], depth));
+        }
+    else if (kind == 4)
+        for (int x = startX + 1; x < width; x++)                                       /* width carries endX */
+        {
+            int signDown = sgn_of(px(rec, depth, x) - px(rec, depth, x + stride));
+            int edgeType = signDown + buf0[x] + 2;
+            buf0[x - 1] = (int8_t)-signDown;
+            put_pix(rec, depth, x, clip_px(px(rec, depth, x) + offset[edgeType], depth));
+        }
+    else
+        for (int y = 0; y < height; y++)
+            for (int x = 0; x < width; x++)
+            {
+                int v = px(rec, depth, y * stride + x);
+                put_pix(rec, depth, y * stride + x, clip_px(v + offset[v >> (depth - 5)], depth));
+            }
+}
+
+/* encoder/sao.cpp:1762-1926: kind 5 saoCuStatsBO, 0 E0, 1 E1, 3 E2, 4 E3; diff pitch is MAX_CU_SIZE = 64 */
+void orc_sao_stats(int kind, int depth, const int16_t* diff, const void* rec, intptr_t stride, int8_t* upBuff1, int8_t* upBufft,
+                   int endX, int endY, int32_t* stats, int32_t* count)
+{
+    static const int eoTable[5] = { 1, 2, 0, 3, 4 };                                   /* SAO::s_eoTable, sao.cpp:65-72 */
+    int32_t ts[5] = { 0 }, tc[5] = { 0 };
+    for (int y = 0; y < endY; y++)
+    {
+        const intptr_t r = y * stride;
+        if (kind == 5)
+        {
+            for (int x = 0; x < endX; x++) { int c = px(rec, depth, r + x) >> (depth - 5); stats[c] += diff[y * 64 + x]; count[c]++; }
+            continue;
+        }
+        int signLeft = kind == 0 ? sgn_of(px(rec, depth, r) - px(rec, depth, r - 1)) : 0;
+        if (kind == 3) upBufft[0] = (int8_t)sgn_of(px(rec, depth, r + stride) - px(rec, depth, r - 1));
+        for (int x = 0; x < endX; x++)
+        {
+            int c = px(rec, depth, r + x), edgeType;
+            if (kind == 0) { int sr = sgn_of(c - px(rec, depth, r + x + 1)); edgeType = sr + signLeft + 2; signLeft = -sr; }
+            else if (kind == 1) { int sd = sgn_of(c - px(rec, depth, r + x + stride)); edgeType = sd + upBuff1[x] + 2; upBuff1[x] = (int8_t)-sd; }
+            else if (kind == 3) { int sd = sgn_of(c - px(rec, depth, r + x + stride + 1)); edgeType = sd + upBuff1[x] + 2; upBufft[x + 1] = (int8_t)-sd; }
+            else { int sd = sgn_of(c - px(rec, depth, r + x + stride - 1)); edgeType = sd + upBuff1[x] + 2; upBuff1[x - 1] = (int8_t)-sd; }
+            ts[edgeType] += diff[y * 64 + x]; tc[edgeType]++;
+        }
+        if (kind == 3) { int8_t* t = upBuff1; upBuff1 = upBufft; upBufft = t; }
+        if (kind == 4) upBuff1[endX - 1] = (int8_t)sgn_of(px(rec, depth, r + endX - 1 + stride) - px(rec, depth, r + endX));
+    }
+    if (kind != 5)
+        for (int x = 0; x < 5; x++) { stats[eoTable[x]] += ts[x]; count[eoTable[x]] += tc[x]; }
+}
+
+/* common/loopfilter.cpp:141-180: pelFilterLumaStrong_c (chroma = 0: a = tcP, b = tcQ) / pelFilterChroma_c (a = tc, b = maskP, c = maskQ) */
+void orc_deblock(int chroma, int depth, void* src, intptr_t srcStep, intptr_t o, int a, int b, int c)
+{
+#define CL3(lo, hi, v) ((v) < (lo) ? (lo) : ((v) > (hi) ? (hi) : (v)))
+    for (int i = 0; i < 4; i++)
+    {
+        const intptr_t p = i * srcStep;
+        int m4 = (int16_t)px(src, depth, p), m3 = (int16_t)px(src, depth, p - o), m5 = (int16_t)px(src, depth, p + o), m2 = (int16_t)px(src, depth, p - 2 * o);
+        if (chroma)
+        {
+            int delta = CL3(-a, a, ((((m4 - m3) * 4) + m2 - m5 + 4) >> 3));
+            put_pix(src, depth, p - o, clip_px(m3 + (delta & b), depth));
+            put_pix(src, depth, p, clip_px(m4 - (delta & c), depth));
+            continue;
+        }
+        int m6 = (int16_t)px(src, depth, p + 2 * o), m1 = (int16_t)px(src, depth, p - 3 * o), m7 = (int16_t)px(src, depth, p + 3 * o), m0 = (int16_t)px(src, depth, p - 4 * o);
+        put_pix(src, depth, p - 3 * o, CL3(-a, a, ((2 * m0 + 3 * m1 + m2 + m3 + m4 + 4) >> 3) - m1) + m1);
+        put_pix(src, depth, p - 2 * o, CL3(-a, a, ((m1 + m2 + m3 + m4 + 2) >> 2) - m2) + m2);
+        put_pix(src, depth, p - o,     CL3(-a, a, ((m1 + 2 * m2 + 2 * m3 + 2 * m4 + m5 + 4) >> 3) - m3) + m3);
+        put_pix(src, depth, p,         CL3(-b, b, ((m2 + 2 * m3 + 2 * m4 + 2 * m5 + m6 + 4) >> 3) - m4) + m4);
+        put_pix(src, depth, p + o,     CL3(-b, b, ((m3 + m4 + m5 + m6 + 2) >> 2) - m5) + m5);
+        put_pix(src, depth, p + 2 * o, CL3(-b, b, ((m3 + m4 + m5 + 3 * m6 + 2 * m7 + 4) >> 3) - m6) + m6);
+    }
+#undef CL3
+}
+
+/* common/pixel.cpp:914-940 estimateCUPropagateCost (double arithmetic, one rounding per operation) */
+void orc_propagate_cost(int* dst, const uint16_t* propagateIn, const int32_t* intraCosts, const uint16_t* interCosts, const int32_t* invQscales,
+                        double fpsFactor, int len)
+{
+    volatile double fps = fpsFactor / 256;
+    for (int i = 0; i < len; i++)
+    {
+        int intraCost = intraCosts[i];
+        int inter = interCosts[i] & ((1 << 14) - 1);
+        int interCost = intraCost < inter ? intraCost : inter;
+        volatile double propagateIntra = (double)(int)((uint32_t)intraCost * (uint32_t)invQscales[i]);
+        volatile double t = propagateIntra * fps;
+        volatile double propagateAmount = (double)propagateIn[i] + t;
+        volatile double propagateNum = (double)(intraCost - interCost);
+        volatile double q = propagateAmount * propagateNum;
+        volatile double r = q / (double)intraCost;
+        double v = r + 0.5;
+        dst[i] = (v > -2147483649.0 && v < 2147483648.0) ? (int)v : (int)0x80000000;   /* cvttsd2si semantics */
+    }
+}
+
+/* the TU chain of Quant::transformNxN + invtransformNxN (common/quant.cpp:397-480, :543-605; rdoq 0, no sign hiding) around
+ * cu[].sub_ps / add_ps / sse_pp for one N x N TU; returns numSig */
+uint32_t orc_tu_chain(int depth, int sizeIdx, int useDST, const void* fenc, intptr_t fencStride, const void* pred, intptr_t predStride,
+                      void* recon, intptr_t reconStride, const int32_t* quantCoeff, int qBits, int add,
+                      const int32_t* dequantCoef, int scaleOrPer, int dqShift, int16_t* coeff, uint64_t* sse)
+{
+    const int N = 4 << sizeIdx, n2 = N * N;
+    int16_t resi[32 * 32], dctc[32 * 32];
+    int32_t deltaU[32 * 32];
+    for (int y = 0; y < N; y++)
+        for (int x = 0; x < N; x++) resi[y * N + x] = (int16_t)(px(fenc, depth, y * fencStride + x) - px(pred, depth, y * predStride + x));
+    orc_dct(depth, useDST ? 4 : sizeIdx, resi, dctc, N);
+    uint32_t numSig = orc_quant(dctc, quantCoeff, deltaU, coeff, qBits, add, n2);
+    if (numSig)
+    {
+        if (dequantCoef) orc_dequant_scaling(coeff, dequantCoef, dctc, n2, scaleOrPer, dqShift);
+        else orc_dequant_normal(coeff, dctc, n2, scaleOrPer, dqShift);
+        if (numSig == 1 && coeff[0] != 0 && !useDST)
+        {
+            const int shift_2nd = 12 - (depth - 8) - 3, add_2nd = 1 << (shift_2nd - 1);
+            int dc_val = (((dctc[0] * (64 >> 6) + 1) >> 1) * (64 >> 3) + add_2nd) >> shift_2nd;
+            for (int i = 0; i < n2; i++) resi[i] = (int16_t)dc_val;
+        }
+        else orc_idct(depth, useDST ? 4 : sizeIdx, dctc, resi, N);
+    }
+    else memset(resi, 0, sizeof(int16_t) * n2);
+    uint64_t s = 0;
+    for (int y = 0; y < N; y++)
+        for (int x = 0; x < N; x++)
+        {
+            int r = clip_px(px(pred, depth, y * predStride + x) + resi[y * N + x], depth);
+            put_pix(recon, depth, y * reconStride + x, r);
+            int d = px(fenc, depth, y * fencStride + x) - r;
+            s += (uint64_t)(d * d);
+        }
+    *sse = s;
+    return numSig;
+}

@@ -51,3 +51,23 @@ void     orc_intra_filter(int depth, int log2N, const void* src, void* dst);
 #ifdef __cplusplus
 }
 #endif
+
+/* ---- SEA support, in-loop filters, cuTree, the residual chain (restatements of pixel.cpp:121-165, framefilter.cpp:39-140 + :722-825,
+ *      loopfilter.cpp:39-180, sao.cpp:1762-1926, pixel.cpp:914-940, quant.cpp:397-480 + :543-605) ---- */
+#ifdef __cplusplus
+extern "C" {
+#endif
+int      orc_ads(int kind, int lxHalf, const int* encDC, const uint32_t* sums, intptr_t delta, const uint16_t* costMvX, int16_t* mvs, int width, int thresh);
+void     orc_sea_integral(int depth, const void* reconOrigin, intptr_t stride, int padX, int padY, int maxHeight, uint32_t* const planes[12]);
+void     orc_sao_apply(int kind, int depth, void* rec, intptr_t stride, int8_t* buf0, int8_t* buf1, const int8_t* offset, int width, int height, int startX);
+void     orc_sao_stats(int kind, int depth, const int16_t* diff, const void* rec, intptr_t stride, int8_t* upBuff1, int8_t* upBufft,
+                       int endX, int endY, int32_t* stats, int32_t* count);
+void     orc_deblock(int chroma, int depth, void* src, intptr_t srcStep, intptr_t offset, int a, int b, int c);
+void     orc_propagate_cost(int* dst, const uint16_t* propagateIn, const int32_t* intraCosts, const uint16_t* interCosts, const int32_t* invQscales,
+                            double fpsFactor, int len);
+uint32_t orc_tu_chain(int depth, int sizeIdx, int useDST, const void* fenc, intptr_t fencStride, const void* pred, intptr_t predStride,
+                      void* recon, intptr_t reconStride, const int32_t* quantCoeff, int qBits, int add,
+                      const int32_t* dequantCoef, int scaleOrPer, int dqShift, int16_t* coeff, uint64_t* sse);
+#ifdef __cplusplus
+}
+#endif

@@ -163,3 +163,137 @@ def test_intra_restatement_matches_reference(depth):
                     R.ref_intra_pred(log2N - 2, mode, vpo(a, 0), ssz(N + 1), vpo(nb, 0), bf)
                     O.orc_intra_pred(depth, log2N, mode, bf, vpo(nb, 0), vpo(b, 0), ssz(N + 1))
                     assert np.array_equal(a, b), (log2N, mode, bf)
+
+
+# ---- families added late in round 1: SEA support, in-loop filters, cuTree, the residual chain ------------------------------------
+import ctypes  # noqa: E402
+
+from util import pdtype, vp, vpo, ssz  # noqa: E402
+
+
+@needs_ref
+def test_ads_restatement():
+    R, O = oracle.ref(8), oracle.orc()
+    rng = np.random.default_rng(1)
+    stride, width = 256, 100
+    sums = rng.integers(0, 30000, stride * 24).astype(np.uint32)
+    cost = rng.integers(0, 200, width).astype(np.uint16)
+    for (w, h), kind in (((8, 8), 1), ((16, 4), 1), ((16, 8), 2), ((32, 64), 2), ((16, 16), 4), ((64, 64), 4), ((32, 24), 4)):
+        part = LUMA_PU_SIZES.index((w, h))
+        for trial in range(6):
+            enc = rng.integers(0, 30000, 4).astype(np.int32)
+            delta = int(rng.choice([8, 12, 8 * stride]))
+            thresh = int(rng.integers(1000, 50000))
+            off = int(rng.integers(0, stride * 10))
+            m1, m2 = np.zeros(width + 8, dtype=np.int16), np.zeros(width + 8, dtype=np.int16)
+            n1 = R.ref_ads(part, vp(enc), vpo(sums, off), delta, vp(cost), vp(m1), width, thresh)
+            n2 = O.orc_ads(kind, w >> 1, vp(enc), vpo(sums, off), ssz(delta), vp(cost), vp(m2), width, thresh)
+            assert n1 == n2 and np.array_equal(m1[:n1], m2[:n2]), (w, h, trial)
+
+
+@needs_ref
+@pytest.mark.parametrize("depth", [8, 10])
+def test_sea_integral_restatement(depth):
+    R, O = oracle.ref(depth), oracle.orc()
+    W, H, padX, padY = 128, 64, 96, 80
+    stride, rows = W + 2 * padX, H + 2 * padY
+    rng = np.random.default_rng(2)
+    plane = rng.integers(0, 1 << depth, stride * rows).astype(pdtype(depth))
+    origin = padY * stride + padX
+    a = [np.full(stride * rows, 0xAAAAAAAA, dtype=np.uint32) for _ in range(12)]
+    b = [x.copy() for x in a]
+    pa = (ctypes.c_void_p * 12)(*[x.ctypes.data + origin * 4 for x in a])
+    pb = (ctypes.c_void_p * 12)(*[x.ctypes.data + origin * 4 for x in b])
+    R.ref_sea_integrals(vpo(plane, origin), ssz(stride), padX, padY, H, pa)
+    O.orc_sea_integral(depth, vpo(plane, origin), ssz(stride), padX, padY, H, pb)
+    for k in range(12):
+        assert np.array_equal(a[k], b[k]), k
+
+
+@needs_ref
+@pytest.mark.parametrize("depth", [8, 10])
+def test_sao_and_deblock_restatement(depth):
+    R, O = oracle.ref(depth), oracle.orc()
+    rng = np.random.default_rng(3 + depth)
+    S, rows = 200, 80
+    base = rng.integers(0, 1 << depth, (rows // 4 + 1, S // 4 + 1))
+    img = (np.kron(base, np.ones((4, 4), dtype=np.int64))[:rows, :S] + rng.integers(-2, 3, (rows, S))).clip(0, (1 << depth) - 1).astype(pdtype(depth)).ravel()
+    for kind in range(6):
+        for trial in range(5):
+            r1, r2 = img.copy(), img.copy()
+            buf = rng.integers(-1, 2, 200).astype(np.int8)
+            b1, b2 = buf.copy(), buf.copy()
+            offs = rng.integers(-7, 8, 32).astype(np.int8)
+            width, height, startX = int(rng.integers(16, 65)), int(rng.integers(1, 9)), int(rng.integers(0, 2))
+            ro = S * 3 + 5
+            R.ref_sao_apply(kind, vpo(r1, ro), ssz(S), vpo(b1, 1), vpo(b1, 101), vp(offs), width, height, startX)
+            O.orc_sao_apply(kind, depth, vpo(r2, ro), ssz(S), vpo(b2, 1), vpo(b2, 101), vp(offs), width, height, startX)
+            assert np.array_equal(r1, r2) and np.array_equal(b1, b2), (kind, trial)
+    diff = rng.integers(-50, 51, 64 * 64).astype(np.int16)
+    for kind in (5, 0, 1, 3, 4):
+        for trial in range(5):
+            buf = rng.integers(-1, 2, 200).astype(np.int8)
+            b1, b2 = buf.copy(), buf.copy()
+            st = rng.integers(-100, 100, 32).astype(np.int32); ct = rng.integers(0, 100, 32).astype(np.int32)
+            s1, c1, s2, c2 = st.copy(), ct.copy(), st.copy(), ct.copy()
+            endX, endY = int(rng.integers(30, 64)), int(rng.integers(1, 64))
+            ro = S * 2 + 3
+            R.ref_sao_stats(kind, vp(diff), vpo(img, ro), ssz(S), vpo(b1, 2), vpo(b1, 102), endX, endY, vp(s1), vp(c1))
+            O.orc_sao_stats(kind, depth, vp(diff), vpo(img, ro), ssz(S), vpo(b2, 2), vpo(b2, 102), endX, endY, vp(s2), vp(c2))
+            assert np.array_equal(s1, s2) and np.array_equal(c1, c2) and np.array_equal(b1, b2), (kind, trial)
+    for chroma in (0, 1):
+        for trial in range(20):
+            p1, p2 = img.copy(), img.copy()
+            vert = trial & 1
+            step, off = (S, 1) if vert else (1, S)
+            a_, b_, c_ = int(rng.integers(0, 1 << (depth - 2))), int(rng.integers(-1, 40)), int(rng.integers(-1, 1))
+            so = S * 20 + 50
+            R.ref_deblock(chroma, vpo(p1, so), ssz(step), ssz(off), a_, b_, c_)
+            O.orc_deblock(chroma, depth, vpo(p2, so), ssz(step), ssz(off), a_, b_, c_)
+            assert np.array_equal(p1, p2), (chroma, trial)
+
+
+@needs_ref
+def test_propagate_cost_restatement():
+    R, O = oracle.ref(8), oracle.orc()
+    rng = np.random.default_rng(5)
+    n = 4000
+    pin = rng.integers(0, 65536, n).astype(np.uint16); intra = rng.integers(0, 50000, n).astype(np.int32); intra[::53] = 0
+    inter = rng.integers(0, 65536, n).astype(np.uint16); invq = rng.integers(1, 70000, n).astype(np.int32)
+    a, b = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
+    R.ref_propagate_cost(vp(a), vp(pin), vp(intra), vp(inter), vp(invq), ctypes.c_double(200.0), n)
+    O.orc_propagate_cost(vp(b), vp(pin), vp(intra), vp(inter), vp(invq), ctypes.c_double(200.0), n)
+    assert np.array_equal(a, b)
+
+
+@needs_ref
+@pytest.mark.parametrize("depth", [8, 10])
+def test_tu_chain_restatement(depth):
+    R, O = oracle.ref(depth), oracle.orc()
+    rng = np.random.default_rng(6 + depth)
+    for sizeIdx in range(4):
+        N = 4 << sizeIdx
+        for trial in range(12):
+            fenc = rng.integers(0, 1 << depth, N * N).astype(pdtype(depth))
+            kind = trial % 4
+            noise = {0: 0, 1: 0, 2: 3, 3: 60}[kind] << (depth - 8)
+            pred = fenc.astype(np.int64) + (int(rng.integers(-10, 11)) << (depth - 8) if kind == 1 else 0) + (rng.integers(-noise, noise + 1, N * N) if noise else 0)
+            pred = pred.clip(0, (1 << depth) - 1).astype(pdtype(depth))
+            useDST = int(sizeIdx == 0 and trial % 2)
+            scaling = trial % 3 == 0
+            qp = int(rng.integers(10, 45)) + 6 * (depth - 8)
+            per, rem = qp // 6, qp % 6
+            ts = 15 - depth - (sizeIdx + 2)
+            qbits = 14 + per + ts
+            add = 171 << (qbits - 9)
+            qc = (np.full(N * N, [26214, 23302, 20560, 18396, 16384, 14564][rem]) * 16 // (rng.integers(8, 40, N * N) if scaling else 16)).astype(np.int32)
+            dqc = ([40, 45, 51, 57, 64, 72][rem] * rng.integers(8, 40, N * N)).astype(np.int32) if scaling else None
+            sop = per if scaling else [40, 45, 51, 57, 64, 72][rem] << per
+            r1, r2 = np.zeros_like(fenc), np.zeros_like(fenc)
+            c1, c2 = np.zeros(N * N, dtype=np.int16), np.zeros(N * N, dtype=np.int16)
+            ns1, ss1, ss2 = np.zeros(1, dtype=np.uint32), np.zeros(1, dtype=np.uint64), np.zeros(1, dtype=np.uint64)
+            R.ref_tu_pipeline(sizeIdx, useDST, vp(fenc), ssz(N), vp(pred), ssz(N), vp(r1), ssz(N), 1, 1, vp(qc), qbits, add,
+                              vp(dqc) if scaling else None, sop, 6 - ts, vp(c1), vp(ns1), vp(ss1), 1)
+            ns2 = O.orc_tu_chain(depth, sizeIdx, useDST, vp(fenc), ssz(N), vp(pred), ssz(N), vp(r2), ssz(N), vp(qc), qbits, add,
+                                 vp(dqc) if scaling else None, sop, 6 - ts, vp(c2), vp(ss2))
+            assert int(ns1[0]) == ns2 and np.array_equal(c1, c2) and np.array_equal(r1, r2) and ss1[0] == ss2[0], (depth, N, trial)
