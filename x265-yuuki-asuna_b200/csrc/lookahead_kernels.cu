@@ -61,6 +61,8 @@ extend_border_kernel(pixel* __restrict__ pic, int64_t stride, int width, int hei
 int lowres_init_dev(Ctx* ctx, int depth, const void* src, int64_t srcStride, void* const planes[4], int64_t dstStride,
                     int width, int height, int marginX, int marginY)
 {
+    if (width <= 0 || height <= 0) return 0;
+    if (height > 65535) { set_error("lowres_init: height %d", height); return -1; }
     dim3 grid((width + 255) / 256, height), block(256);
     if (depth > 8)
         lowres_init_kernel<uint16_t><<<grid, block, 0, ctx->stream>>>((const uint16_t*)src, srcStride, (uint16_t*)planes[0], (uint16_t*)planes[1], (uint16_t*)planes[2], (uint16_t*)planes[3], dstStride, width, height);
@@ -278,6 +280,7 @@ la_intra_kernel(LAIntraArgs p)
 int la_intra_dev(Ctx* ctx, int depth, const void* plane0, int64_t stride, int widthInCU, int heightInCU, const int32_t* invQscale,
                  int intraPenalty, int32_t* intraCost, uint8_t* intraMode, uint16_t* lowresCosts, int32_t* rowSatds, int32_t* sums)
 {
+    if (widthInCU <= 0 || heightInCU <= 0) return 0;
     LAIntraArgs a; a.plane0 = plane0; a.stride = stride; a.invQscale = invQscale; a.widthInCU = widthInCU; a.heightInCU = heightInCU;
     a.depth = depth; a.intraPenalty = intraPenalty; a.intraCost = intraCost; a.intraMode = intraMode; a.lowresCosts = lowresCosts;
     a.rowSatds = rowSatds; a.sums = sums;
