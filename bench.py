@@ -39,8 +39,6 @@ NREF, MERANGE, SUBME, QP = 3, 57, 2, 30
 LEVELS = [64, 32, 16, 8]
 # DRAM bytes one sad_pyramid launch (3 references, 2160p 8-bit) moved under `ncu --set full` (profiles/r01_pyramid_dct_v3.txt)
 SAD_PYRAMID_DRAM_BYTES = 33437696
-# ncu smsp__inst_executed.sum of the bench's me_frame launch (same seeded frames; profiles/r01_me_frame_v8.txt)
-ME_FRAME_WARP_INSTRUCTIONS = 1843586929
 WORKLOAD = ("2160p-8bit-medium primitive mix (SURVEY.md 8d config 3): SAD at the predictor + HEX subme2 merange57 search of every 2Nx2N PU 64..8 x 3 refs; "
             "one 8-tap MC interpolation per PU and level (all 15 fractions); residual -> DCT/quant/dequant/IDCT on every 32/16/8/4 TU -> recon; "
             "intra neighbour smoothing + all 35 modes on every 8/16/32 block (fused)")
@@ -525,19 +523,6 @@ def main():
         line["roofline_me_search"] = {"kernel": "me_frame_kernel (TMA-staged windows; HEX + subme 2, %d searches)" % njobs, "bound": "hbm", "achieved": me_bytes / me_t / 1e9,
                                       "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": me_bytes / me_t / 1e9 / pk["hbm_gbs"], "ms_per_step": me_t * 1e3,
                                       "note": "instruction-issue/fetch-bound pattern search over smem-staged windows (DESIGN.md 5, profiles/r01_me_frame_v5.txt); HBM figure shown for scale only"}
-        try:
-            # the bound that does apply to the search kernel: warp-instruction issue (4 schedulers per SM, one instruction
-            # per clock each).  The instruction count is ncu's smsp__inst_executed.sum for this very launch (same seeded
-            # frames; profiles/r01_me_frame_v8.txt) -- a constant of the workload, not re-measured here.
-            sm_mhz = line["clocks"].get("sm_mhz") or line["clocks"].get("sm_max_mhz")
-            sms = torch.cuda.get_device_properties(dev).multi_processor_count
-            peak_issue = 4.0 * sms * float(sm_mhz) * 1e6 / 1e9
-            ach_issue = ME_FRAME_WARP_INSTRUCTIONS / me_t / 1e9
-            line["roofline_me_search"]["issue"] = {"bound": "warp-instruction issue", "achieved": ach_issue, "peak": peak_issue, "unit": "G warp-instr/s",
-                                                   "frac": ach_issue / peak_issue, "warp_instructions_per_launch": ME_FRAME_WARP_INSTRUCTIONS,
-                                                   "src": "ncu smsp__inst_executed.sum of this launch as captured in profiles/r01_me_frame_v8.txt (the later LDS address-space hints removed the R2UR share, ~7%%, so this is an upper bound); peak = 4 schedulers x %d SMs x sampled SM clock" % sms}
-        except Exception:               # noqa: BLE001  (explanatory figure only)
-            pass
         if world == 1:
             line["cpu_baseline"] = cpu_baseline()
             try:

@@ -10,7 +10,8 @@ import re
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libx265b200.so")
+# X265B200_LIB selects another build of the SAME library (e.g. the experimental variant `make -C csrc exp` produces)
+LIB_PATH = os.environ.get("X265B200_LIB") or os.path.join(_HERE, "libx265b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "x265b200.h")
 
 CMP_SAD, CMP_SATD, CMP_SA8D, CMP_SA8D8, CMP_SSE_PP, CMP_SSE_SS, CMP_SSD_S = range(7)

@@ -8,6 +8,7 @@
 #pragma once
 #include "common.cuh"
 #include "tables.cuh"
+#include "satd_packed.cuh"
 #include <type_traits>
 
 // A translation unit whose searches ALL run in per-thread mode defines ME_FORCE_THREAD before including this header:
@@ -132,6 +133,41 @@ __device__ __forceinline__ void ld_words(const pixel* p, uint32_t out[NW])
     for (int i = 0; i < NW; i++) out[i] = __funnelshift_r(t[i], t[i + 1], sh);
 }
 
+#if defined(ME_REF_IN_SMEM) && defined(ME_WINDOW_FAST)
+#define ME_SMEM_FAST 1
+// Rows of the shared-memory window through 32-bit shared addresses.  The window pitch is a multiple of 16 bytes
+// (me_frame_dev), so the byte misalignment of a block is the same on every row: a caller resolves the pointer ONCE into
+// (4-byte-aligned shared address, bit shift) and then walks rows / 4-pixel columns with 32-bit adds -- the generic form
+// above spends as many instructions on 64-bit row addresses, alignment and the predicate of the last word as on the
+// loads themselves (profiles/r01_me_frame_v8.txt: ld_words = 19 % of the executed instructions).  NW + 1 words are always
+// read: the word after an aligned run is ignored by the funnel shift and lies inside the CTA's allocation (the window
+// is followed by the fenc tile).
+template<int OFF> __device__ __forceinline__ uint32_t lds_u32(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(OFF));
+    return v;
+}
+template<int N, int I = 0> __device__ __forceinline__ void lds_run(uint32_t a, uint32_t* t)
+{
+    if constexpr (I < N) { t[I] = lds_u32<4 * I>(a); lds_run<N, I + 1>(a, t); }
+}
+struct SRow { uint32_t a, sh; };
+template<typename pixel> __device__ __forceinline__ SRow srow(const pixel* p)
+{
+    const uint32_t g = (uint32_t)__cvta_generic_to_shared(p);
+    SRow r; r.a = g & ~3u; r.sh = (g & 3u) * 8u;
+    return r;
+}
+template<int NW> __device__ __forceinline__ void lds_words(uint32_t a, uint32_t sh, uint32_t out[NW])
+{
+    uint32_t t[NW + 1];
+    lds_run<NW + 1>(a, t);
+#pragma unroll
+    for (int i = 0; i < NW; i++) out[i] = __funnelshift_r(t[i], t[i + 1], sh);
+}
+#endif
+
 template<typename pixel> __device__ __forceinline__ uint32_t sad_word(uint32_t a, uint32_t b);
 template<> __device__ __forceinline__ uint32_t sad_word<uint8_t>(uint32_t a, uint32_t b) { return __vsadu4(a, b); }
 template<> __device__ __forceinline__ uint32_t sad_word<uint16_t>(uint32_t a, uint32_t b) { return __vsadu2(a, b); }
@@ -229,6 +265,10 @@ __device__ __forceinline__ int thread_sad_w8(const MEState<pixel>& s, const pixe
     constexpr int NW = 8 * (int)sizeof(pixel) / 4;
     typedef typename std::conditional<sizeof(pixel) == 1, uint2, uint4>::type fvec;
     uint32_t acc = 0;
+#ifdef ME_SMEM_FAST
+    const SRow base = srow(r);
+    const uint32_t rsB = (uint32_t)rs * (uint32_t)sizeof(pixel);
+#endif
 #pragma unroll 1
     for (int y0 = 0; y0 < s.h; y0 += 8)
     {
@@ -237,7 +277,11 @@ __device__ __forceinline__ int thread_sad_w8(const MEState<pixel>& s, const pixe
 #pragma unroll
         for (int y = 0; y < 8; y++)
         {
+#ifdef ME_SMEM_FAST
+            lds_words<NW>(base.a + (uint32_t)(y0 + y) * rsB, base.sh, rw[y]);
+#else
             ld_words<pixel, NW>(r + (int64_t)(y0 + y) * rs, rw[y]);
+#endif
             f[y] = *smem_hint((const fvec*)(s.fenc + (y0 + y) * 64));
         }
 #pragma unroll
@@ -295,6 +339,45 @@ __device__ __forceinline__ int thread_satd(const MEState<pixel>& s, const pixel*
 {
     int acc = 0;
     constexpr int NW = 4 * (int)sizeof(pixel) / 4;
+#ifdef ME_SMEM_FAST
+    const SRow base = srow(r);
+    const uint32_t rsB = (uint32_t)rs * (uint32_t)sizeof(pixel);
+#pragma unroll 1
+    for (int cy = 0; cy < s.h; cy += 4)
+#pragma unroll 1
+        for (int cx = 0; cx < ME_PU_W(s); cx += 4)
+        {
+            const uint32_t a0 = base.a + (uint32_t)cy * rsB + (uint32_t)cx * (uint32_t)sizeof(pixel);
+            if constexpr (sizeof(pixel) == 1)
+            {
+                uint32_t fw[4], ow[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                {
+                    fw[i] = *smem_hint((const uint32_t*)(s.fenc + (cy + i) * 64 + cx));
+                    lds_words<1>(a0 + (uint32_t)i * rsB, base.sh, &ow[i]);
+                }
+                acc += satd4x4_packed_u8(fw, ow);
+            }
+            else
+            {
+                int d[4][4];
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                {
+                    int a[4], b[4];
+                    uint32_t rw[NW];
+                    unpack4<pixel>(smem_hint((const uint32_t*)(s.fenc + (cy + i) * 64 + cx)), a);
+                    lds_words<NW>(a0 + (uint32_t)i * rsB, base.sh, rw);
+                    unpack4<pixel>(rw, b);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) d[i][k] = a[k] - b[k];
+                }
+                acc += satd_cell(d);
+            }
+        }
+    return acc;
+#else
 #pragma unroll 1
     for (int cy = 0; cy < s.h; cy += 4)
 #pragma unroll 1
@@ -315,6 +398,7 @@ __device__ __forceinline__ int thread_satd(const MEState<pixel>& s, const pixel*
             acc += satd_cell(d);
         }
     return acc;
+#endif
 }
 
 template<typename pixel>
@@ -602,6 +686,17 @@ __device__ __noinline__ int cell_cost_packed(const pixel* f, CellRows<pixel> row
     constexpr int NW = 4 * (int)sizeof(pixel) / 4;
     if (useSatd)
     {
+#ifdef ME_WINDOW_FAST
+        if constexpr (sizeof(pixel) == 1)
+        {
+            uint32_t fw[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) fw[i] = *smem_hint((const uint32_t*)(f + i * 64));
+            return satd4x4_packed_u8(fw, rows.w);
+        }
+        else
+#endif
+        {
         int d[4][4];
 #pragma unroll
         for (int i = 0; i < 4; i++)
@@ -621,6 +716,7 @@ __device__ __noinline__ int cell_cost_packed(const pixel* f, CellRows<pixel> row
             t += abs(d[0][k]) + abs(d[1][k]) + abs(d[2][k]) + abs(d[3][k]);
         }
         return t >> 1;
+        }
     }
     uint32_t acc = 0;
 #pragma unroll
@@ -653,9 +749,19 @@ __device__ __noinline__ int thread_subpel_cost(const MEState<pixel>& s, const pi
     for (int t = 0; t < 8; t++) ch[t] = c_meLumaFilter[xFrac][t];
     const uint32_t clo = pack_taps(ch, 0), chi = pack_taps(ch, 4);
     // horizontal 8-tap sums of 4 adjacent outputs whose first tap sits at p
+#ifdef ME_SMEM_FAST
+    // rows by 32-bit shared address: b0 resolves src, b3 the first tap (src - 3); columns advance by whole words
+    const SRow b0 = srow(src), b3 = srow(src - 3);
+    const uint32_t rsB = (uint32_t)s.stride * (uint32_t)sizeof(pixel);
+    constexpr uint32_t PXB = (uint32_t)sizeof(pixel);
+    auto hsums = [&](uint32_t a, int sums[4]) {
+        uint32_t rw[NW12];
+        lds_words<NW12>(a, b3.sh, rw);
+#else
     auto hsums = [&](const pixel* p, int sums[4]) {
         uint32_t rw[NW12];
         ld_words<pixel, NW12>(p, rw);
+#endif
         if (sizeof(pixel) == 1) hfir4_u8(rw, clo, chi, sums);
         else
         {
@@ -688,7 +794,11 @@ __device__ __noinline__ int thread_subpel_cost(const MEState<pixel>& s, const pi
                 for (int r = 0; r < 4; r++)
                 {
                     int sums[4], o[4];
+#ifdef ME_SMEM_FAST
+                    hsums(b3.a + (uint32_t)(y0 + r) * rsB + (uint32_t)x * PXB, sums);
+#else
                     hsums(src + (int64_t)(y0 + r) * s.stride + x - 3, sums);
+#endif
 #pragma unroll
                     for (int k = 0; k < 4; k++)
                     {
@@ -730,7 +840,11 @@ __device__ __noinline__ int thread_subpel_cost(const MEState<pixel>& s, const pi
                 {
 #pragma unroll
                     for (int t = 0; t < 7; t++) wq[t] = wq[t + 1];
+#ifdef ME_SMEM_FAST
+                    lds_words<1>(b0.a + (uint32_t)(i + 4) * rsB + (uint32_t)x, b0.sh, &wq[7]);
+#else
                     ld_words<pixel, 1>(src + (int64_t)(i + 4) * s.stride + x, &wq[7]);
+#endif
                     if (i < 0) continue;
                     uint32_t ca[4], cb[4];
                     {
@@ -779,19 +893,31 @@ __device__ __noinline__ int thread_subpel_cost(const MEState<pixel>& s, const pi
 #pragma unroll
             for (int t = 0; t < 7; t++) { wp[t][0] = wp[t + 1][0]; wp[t][1] = wp[t + 1][1]; }
             {
-                const pixel* p = src + (int64_t)(i + 4) * s.stride + x;
                 int v[4];
+#ifdef ME_SMEM_FAST
+                const uint32_t rowOff = (uint32_t)(i + 4) * rsB + (uint32_t)x * PXB;
+#else
+                const pixel* p = src + (int64_t)(i + 4) * s.stride + x;
+#endif
                 if (xFrac)
                 {
                     int sums[4];
+#ifdef ME_SMEM_FAST
+                    hsums(b3.a + rowOff, sums);
+#else
                     hsums(p - 3, sums);
+#endif
 #pragma unroll
                     for (int k = 0; k < 4; k++) v[k] = (sums[k] + off1) >> sh1;
                 }
                 else
                 {
                     uint32_t rw[NW4];
+#ifdef ME_SMEM_FAST
+                    lds_words<NW4>(b0.a + rowOff, b0.sh, rw);
+#else
                     ld_words<pixel, NW4>(p, rw);
+#endif
                     unpack4<pixel>(rw, v);
                 }
                 wp[7][0] = (uint32_t)(v[0] & 0xffff) | ((uint32_t)v[1] << 16);

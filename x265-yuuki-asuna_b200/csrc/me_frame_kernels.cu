@@ -15,6 +15,9 @@
 #define ME_FORCE_THREAD 1
 #define ME_FULLRES_ONLY 1
 #define ME_REF_IN_SMEM 1          /* every reference block the search reads is inside the TMA-staged window */
+#ifndef ME_WINDOW_SLOW
+#define ME_WINDOW_FAST 1          /* 32-bit shared-memory row addressing + packed-word 4x4 SATD (me_device.cuh, satd_packed.cuh); */
+#endif                            /* -DME_WINDOW_SLOW builds the generic-pointer form for A/B runs (scripts/ab_me_frame.py)        */
 #include "me_device.cuh"
 #include "x265b200.h"
 #include <cuda.h>
