@@ -1,6 +1,8 @@
 #!/usr/bin/env python
-"""A/B of two builds of libx265b200.so on the frame-search kernel (x265b200_me_frame_dev), in ONE process, no torch:
-   python scripts/ab_me_frame.py [--exp PATH] [--skip-sweep] [--reps N]
+"""A/B of builds of libx265b200.so on the frame-search kernel (x265b200_me_frame_dev), in ONE process, no torch:
+   make -C x265-yuuki-asuna_b200/csrc exp EXPNAME=x EXPFLAGS=-D...      # -> libx265b200_x.so (only me_frame differs)
+   python scripts/ab_me_frame.py [--exp PATH ...] [--skip-sweep] [--reps N]
+Every --exp library is compared with the default one in turn:
 1. parity sweep: both libraries search the same small frames (3x2 CTUs, 2 references, random per-CTU predictors) for
    depth 8/10 x DIA/HEX/UMH/STAR x subme 0..7 x merange 16/57 (+ FULL at merange 8); every {mv, cost} must be equal.
    The default library is the one the parity tests pin to the reference, so equality here carries that parity over.
@@ -80,18 +82,10 @@ def run(ctx, depth, bufs, S, R, pad, ctuCols, ctuRows, mvp, method, subme, meran
                      mvp, method, subme, merange, pkg.lambda_for_qp(30, depth), dOut)
 
 
-def main():
-    global LOG
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--exp", default=os.path.join(ROOT, "x265-yuuki-asuna_b200", "libx265b200_exp.so"))
-    ap.add_argument("--skip-sweep", action="store_true")
-    ap.add_argument("--reps", type=int, default=10)
-    args = ap.parse_args()
-    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    LOG = open(os.path.join(ROOT, "gpurun_out", "ab_me_frame.log"), "a")
-    t00 = time.time()
-    A, B = open_ctx(pkg.LIB_PATH), open_ctx(args.exp)
-    say(stage="init", base=pkg.LIB_PATH, exp=args.exp, s=round(time.time() - t00, 2))
+def compare(A, path, args, t00):
+    B = open_ctx(path)
+    name = os.path.basename(path)
+    say(stage="init", exp=name, s=round(time.time() - t00, 2))
 
     if not args.skip_sweep:
         ctuCols, ctuRows, NREF, pad = 3, 2, 2, 144
@@ -117,7 +111,7 @@ def main():
                         dA.free(); dB.free()
             for x in bufsA + bufsB + [outA, outB]:
                 x.free()
-        say(stage="sweep", cases=ncase, mismatching_cases=len(bad), first=bad[:8], s=round(time.time() - t00, 2))
+        say(stage="sweep", exp=name, cases=ncase, mismatching_cases=len(bad), first=bad[:8], s=round(time.time() - t00, 2))
 
     # ---- 2160p ------------------------------------------------------------------------------------------------
     W, H, pad, NREF = 3840, 2176, 128, 3
@@ -129,7 +123,7 @@ def main():
     go = lambda c, bufs, out: run(c, 8, bufs, S, R, pad, ctuCols, ctuRows, None, pkg.ME_HEX, 2, 57, out)
     go(A, bufsA, outA); go(B, bufsB, outB)
     a, b = outA.download(np.int32), outB.download(np.int32)
-    say(stage="2160p_parity", searches=NREF * nPU, equal=bool(np.array_equal(a, b)), differing=int(np.count_nonzero((a != b).reshape(-1, 3).any(axis=1))),
+    say(stage="2160p_parity", exp=name, searches=NREF * nPU, equal=bool(np.array_equal(a, b)), differing=int(np.count_nonzero((a != b).reshape(-1, 3).any(axis=1))),
         checksum=int(a.astype(np.int64).sum()), s=round(time.time() - t00, 2))
     tA, tB = [], []
     for rep in range(args.reps + 2):
@@ -138,9 +132,29 @@ def main():
             go(c, bufs, out)
             c.sync(); acc.append((time.perf_counter() - t0) * 1e3)
     tA, tB = tA[2:], tB[2:]
-    say(stage="2160p_timing", base_ms=round(float(np.median(tA)), 4), exp_ms=round(float(np.median(tB)), 4), base_min=round(min(tA), 4), exp_min=round(min(tB), 4),
+    say(stage="2160p_timing", exp=name, base_ms=round(float(np.median(tA)), 4), exp_ms=round(float(np.median(tB)), 4), base_min=round(min(tA), 4), exp_min=round(min(tB), 4),
         speedup=round(float(np.median(tA) / np.median(tB)), 4), reps=args.reps, s=round(time.time() - t00, 2))
-    A.close(); B.close()
+    for x in bufsA + bufsB + [outA, outB]:
+        x.free()
+    B.close()
+
+
+def main():
+    global LOG
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--exp", action="append", default=None, help="variant library (repeatable); default libx265b200_exp.so")
+    ap.add_argument("--skip-sweep", action="store_true")
+    ap.add_argument("--reps", type=int, default=10)
+    args = ap.parse_args()
+    exps = args.exp or [os.path.join(ROOT, "x265-yuuki-asuna_b200", "libx265b200_exp.so")]
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    LOG = open(os.path.join(ROOT, "gpurun_out", "ab_me_frame.log"), "a")
+    t00 = time.time()
+    A = open_ctx(pkg.LIB_PATH)
+    say(stage="init", base=pkg.LIB_PATH, s=round(time.time() - t00, 2))
+    for path in exps:
+        compare(A, path, args, t00)
+    A.close()
 
 
 if __name__ == "__main__":
