@@ -9,6 +9,7 @@
 #include "common.cuh"
 #include "tables.cuh"
 #include "satd_packed.cuh"
+#include "subpel_packed.cuh"
 #include <type_traits>
 
 // A translation unit whose searches ALL run in per-thread mode defines ME_FORCE_THREAD before including this header:
@@ -798,6 +799,56 @@ __device__ __noinline__ int thread_subpel_cost(const MEState<pixel>& s, const pi
         }
     };
     int acc = 0;
+#if defined(ME_SMEM_FAST) && defined(ME_SUBPEL_PACKED)
+    // STAGED (off by default, not yet measured): the 8-bit one-pass cases on packed words (subpel_packed.cuh, checked on the
+    // host against the oracle): horizontal rows with the folded rounding / one-instruction clip, vertical cells from their
+    // 11 source rows with ONE transpose per cell instead of one per row and no sliding window
+    if constexpr (sizeof(pixel) == 1)
+    {
+        if (!yFrac)
+        {
+#pragma unroll 1
+            for (int y0 = 0; y0 < H; y0 += 4)
+#pragma unroll 1
+                for (int x = 0; x < W; x += 4)
+                {
+                    CellRows<pixel> rows;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) rows.w[j] = 0;
+#pragma unroll 1
+                    for (int r = 0; r < 4; r++)
+                    {
+                        uint32_t rw[3];
+                        lds_words<3>(b3.a + (uint32_t)(y0 + r) * rsB + (uint32_t)x, b3.sh, rw);
+                        rows.w[0] = rows.w[1]; rows.w[1] = rows.w[2]; rows.w[2] = rows.w[3];
+                        rows.w[3] = hpp_row4_u8(rw, clo, chi);
+                    }
+                    acc += cell_cost_packed<pixel>(s.fenc + y0 * 64 + x, rows, useSatd);
+                }
+            return acc;
+        }
+        if (!xFrac)
+        {
+            int16_t cvt[8];
+#pragma unroll
+            for (int t = 0; t < 8; t++) cvt[t] = c_meLumaFilter[yFrac][t];
+            const uint32_t cvlo = sp_taps(cvt, 0), cvhi = sp_taps(cvt, 4);
+#pragma unroll 1
+            for (int x = 0; x < W; x += 4)
+#pragma unroll 1
+                for (int y0 = 0; y0 < H; y0 += 4)
+                {
+                    uint32_t r[11];
+#pragma unroll
+                    for (int j = 0; j < 11; j++) lds_words<1>(b0.a + (uint32_t)(y0 - 3 + j) * rsB + (uint32_t)x, b0.sh, &r[j]);
+                    CellRows<pixel> rows;
+                    vpp_cell_u8(r, cvlo, cvhi, rows.w);
+                    acc += cell_cost_packed<pixel>(s.fenc + y0 * 64 + x, rows, useSatd);
+                }
+            return acc;
+        }
+    }
+#endif
     if (!yFrac)
     {
         // luma_hpp.  One row of 4 pixels per loop iteration (~55 instructions) so that the loop plus the shared cell cost stay
