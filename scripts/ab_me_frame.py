@@ -60,7 +60,17 @@ def box_blur(a, k=5):
     return a
 
 
+_FRAMES = {}
+
+
 def frames(W, H, pad, depth, nref, seed):
+    key = (W, H, pad, depth, nref, seed)
+    if key not in _FRAMES:
+        _FRAMES[key] = _frames(W, H, pad, depth, nref, seed)
+    return _FRAMES[key]
+
+
+def _frames(W, H, pad, depth, nref, seed):
     rng = np.random.default_rng(seed)
     S, R = W + 2 * pad, H + 2 * pad
     big = box_blur(rng.uniform(0, 255, (R + 64, S + 64)))

@@ -408,9 +408,9 @@ __device__ __noinline__ void warp_sad_k(const MEState<pixel>& s, int K, const in
     if (ME_IS_THREAD(s))
     {
 #ifdef ME_BATCH_GROUPSUM
-        // STAGED (off by default, not yet measured): the K partial SADs first, then ONE butterfly over the lanes of the PU for
-        // all of them -- K independent shuffles per round instead of K dependent 5-round chains (the reduction was 2.6 % of the
-        // instructions but 8.8 % of the stall samples in profiles/r01_me_frame_v8_lines.txt).  Same sums, same results.
+        // the K partial SADs first, then ONE butterfly over the lanes of the PU for all of them -- K independent shuffles per
+        // round instead of K dependent 5-round chains (the reduction was 2.6 % of the instructions but 8.8 % of the stall
+        // samples in profiles/r01_me_frame_v8_lines.txt; -3.8 % kernel time, profiles/r01_me_frame_v10_ab.txt).  Same sums.
         int part[4] = { 0, 0, 0, 0 };
 #pragma unroll 1
         for (int k = 0; k < K; k++)
@@ -800,9 +800,9 @@ __device__ __noinline__ int thread_subpel_cost(const MEState<pixel>& s, const pi
     };
     int acc = 0;
 #if defined(ME_SMEM_FAST) && defined(ME_SUBPEL_PACKED)
-    // STAGED (off by default, not yet measured): the 8-bit one-pass cases on packed words (subpel_packed.cuh, checked on the
-    // host against the oracle): horizontal rows with the folded rounding / one-instruction clip, vertical cells from their
-    // 11 source rows with ONE transpose per cell instead of one per row and no sliding window
+    // the 8-bit one-pass cases on packed words (subpel_packed.cuh, checked on the host against the oracle): horizontal rows
+    // with the folded rounding / one-instruction clip, vertical cells from their 11 source rows with ONE transpose per cell
+    // instead of one per row and no sliding window (-6 % kernel time, profiles/r01_me_frame_v10_ab.txt)
     if constexpr (sizeof(pixel) == 1)
     {
         if (!yFrac)

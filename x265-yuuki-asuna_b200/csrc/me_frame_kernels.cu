@@ -15,9 +15,17 @@
 #define ME_FORCE_THREAD 1
 #define ME_FULLRES_ONLY 1
 #define ME_REF_IN_SMEM 1          /* every reference block the search reads is inside the TMA-staged window */
+// Measured variants of the shared device code, all on by default here (A/B history: profiles/r01_me_frame_v10_ab.txt).  Each
+// can be switched off for an A/B build (`make -C csrc exp EXPFLAGS=-DME_..._OFF=1`, scripts/ab_me_frame.py):
 #ifndef ME_WINDOW_SLOW
-#define ME_WINDOW_FAST 1          /* 32-bit shared-memory row addressing + packed-word 4x4 SATD (me_device.cuh, satd_packed.cuh); */
-#endif                            /* -DME_WINDOW_SLOW builds the generic-pointer form for A/B runs (scripts/ab_me_frame.py)        */
+#define ME_WINDOW_FAST 1          /* 32-bit shared-memory row addressing + packed-word 4x4 SATD (me_device.cuh, satd_packed.cuh) */
+#endif
+#ifndef ME_SUBPEL_PACKED_OFF
+#define ME_SUBPEL_PACKED 1        /* 8-bit one-pass sub-pel paths on packed words; vertical cells from 11 rows (subpel_packed.cuh) */
+#endif
+#ifndef ME_BATCH_GROUPSUM_OFF
+#define ME_BATCH_GROUPSUM 1       /* the K partial SADs of a sad_x3/x4 step reduced over the PU's lanes together                   */
+#endif
 #include "me_device.cuh"
 #include "x265b200.h"
 #include <cuda.h>

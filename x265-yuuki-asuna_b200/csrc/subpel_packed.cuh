@@ -1,4 +1,4 @@
-// subpel_packed.cuh -- STAGED (not yet used by the default build): 8-bit luma sub-pel arithmetic of the frame search on
+// subpel_packed.cuh -- 8-bit luma sub-pel arithmetic of the frame search (me_frame_kernels.cu, ME_SUBPEL_PACKED) on
 // packed words, written so that the same source also compiles for the host (tests/test_subpel_packed_cpu.py checks it
 // against the oracle's luma_hpp / luma_vpp, ipfilter.cpp:79-118 / 164-203).
 //
