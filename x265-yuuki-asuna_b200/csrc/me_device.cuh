@@ -6,7 +6,11 @@
 //
 // Shared by me_kernels.cu (full-resolution batched ME) and lookahead_kernels.cu (lowres path).
 #pragma once
+#ifdef ME_HOST_EMU                      /* tests/host_emu: the same source compiled for the host (test infrastructure) */
+#include "me_host_emu.h"
+#else
 #include "common.cuh"
+#endif
 #include "tables.cuh"
 #include "satd_packed.cuh"
 #include "subpel_packed.cuh"
@@ -145,9 +149,13 @@ __device__ __forceinline__ void ld_words(const pixel* p, uint32_t out[NW])
 // is followed by the fenc tile).
 template<int OFF> __device__ __forceinline__ uint32_t lds_u32(uint32_t a)
 {
+#ifdef ME_HOST_EMU
+    return *(const uint32_t*)(emu::smem_base + a + OFF);
+#else
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(OFF));
     return v;
+#endif
 }
 template<int N, int I = 0> __device__ __forceinline__ void lds_run(uint32_t a, uint32_t* t)
 {
@@ -520,9 +528,13 @@ template<> __device__ __forceinline__ void store_px4<uint16_t>(uint16_t* p, cons
 // per output (DP4A): out[k] = sum_t px[k+t]*c[t], taps packed 4 per word (|c| <= 58 fits s8).
 __device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c)
 {
+#ifdef ME_HOST_EMU
+    return sp_dp4a_us(a, b, c);
+#else
     int d;
     asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
+#endif
 }
 __device__ __forceinline__ void hfir4_u8(const uint32_t w[3], uint32_t clo, uint32_t chi, int out[4])
 {
