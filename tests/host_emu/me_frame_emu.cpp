@@ -15,6 +15,9 @@
 #ifndef EMU_BATCH_GROUPSUM_OFF
 #define ME_BATCH_GROUPSUM 1
 #endif
+#ifdef EMU_HPEL_PAIRS
+#define ME_HPEL_PAIRS 1
+#endif
 #include "me_device.cuh"
 #include <vector>
 

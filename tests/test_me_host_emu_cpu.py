@@ -20,11 +20,15 @@ pkg = importlib.import_module("x265-yuuki-asuna_b200")
 needs_ref = pytest.mark.skipif(not oracle.have_ref(8), reason="oracle/_ref not built (no /root/reference here)")
 
 
-@pytest.fixture(scope="module")
-def emu(tmp_path_factory):
-    so = str(tmp_path_factory.mktemp("emu") / "me_frame_emu.so")
-    subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-pthread", "-Wno-unknown-pragmas",
-                    "-I", os.path.join(ROOT, "tests", "host_emu"), "-I", os.path.join(ROOT, "x265-yuuki-asuna_b200", "csrc"),
+# the build the kernel ships, the staged half-pel pair variant (-DME_HPEL_PAIRS), and the generic-pointer form kept for A/B runs
+VARIANTS = {"default": [], "hpel_pairs": ["-DEMU_HPEL_PAIRS=1"], "window_slow": ["-DEMU_WINDOW_SLOW=1"]}
+
+
+@pytest.fixture(scope="module", params=sorted(VARIANTS))
+def emu(request, tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("emu") / ("me_frame_emu_%s.so" % request.param))
+    subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-pthread", "-Wno-unknown-pragmas"] + VARIANTS[request.param] +
+                   ["-I", os.path.join(ROOT, "tests", "host_emu"), "-I", os.path.join(ROOT, "x265-yuuki-asuna_b200", "csrc"),
                     "-I", os.path.join(ROOT, "include"), "-o", so, os.path.join(ROOT, "tests", "host_emu", "me_frame_emu.cpp")], check=True)
     return ctypes.CDLL(so)
 

@@ -1150,6 +1150,71 @@ __device__ __noinline__ int warp_chroma_cost(const MEState<pixel>& s, int qx, in
 }
 #endif
 
+#if defined(ME_SMEM_FAST) && defined(ME_SUBPEL_PACKED) && defined(ME_HPEL_PAIRS)
+#define ME_HAS_HPEL_PAIRS 1
+// STAGED (off by default, not yet measured; results checked on the host, tests/test_me_host_emu_cpu.py): the two half-pel
+// candidates either side of the FULL-PEL block at `src` in one filter pass -- (0,-2)/(0,+2) are the same vertical half-pel
+// plane one row apart (vert), (-2,0)/(+2,0) the same horizontal one a column apart.  8-bit only (subpel_packed.cuh).
+template<typename pixel>
+__device__ __noinline__ void thread_hpel_pair_cost(const MEState<pixel>& s, const pixel* src, bool vert, bool useSatd, int& costA, int& costB)
+{
+    int accA = 0, accB = 0;
+    if constexpr (sizeof(pixel) == 1)
+    {
+        const int W = ME_PU_W(s), H = s.h;
+        int16_t cf[8];
+#pragma unroll
+        for (int t = 0; t < 8; t++) cf[t] = c_meLumaFilter[2][t];
+        const uint32_t clo = sp_taps(cf, 0), chi = sp_taps(cf, 4);
+        const uint32_t rsB = (uint32_t)s.stride;
+        if (vert)
+        {
+            const SRow b0 = srow(src);
+#pragma unroll 1
+            for (int x = 0; x < W; x += 4)
+#pragma unroll 1
+                for (int y0 = 0; y0 < H; y0 += 4)
+                {
+                    uint32_t r[12], P[5];
+#pragma unroll
+                    for (int j = 0; j < 12; j++) lds_words<1>(b0.a + (uint32_t)(y0 - 4 + j) * rsB + (uint32_t)x, b0.sh, &r[j]);
+                    vpp_cell_pair_u8(r, clo, chi, P);
+                    CellRows<pixel> ra, rb;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) { ra.w[j] = P[j]; rb.w[j] = P[j + 1]; }
+                    accA += cell_cost_packed<pixel>(s.fenc + y0 * 64 + x, ra, useSatd);
+                    accB += cell_cost_packed<pixel>(s.fenc + y0 * 64 + x, rb, useSatd);
+                }
+        }
+        else
+        {
+            const SRow b4 = srow(src - 4);
+#pragma unroll 1
+            for (int y0 = 0; y0 < H; y0 += 4)
+#pragma unroll 1
+                for (int x = 0; x < W; x += 4)
+                {
+                    CellRows<pixel> ra, rb;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) { ra.w[j] = 0; rb.w[j] = 0; }
+#pragma unroll 1
+                    for (int r = 0; r < 4; r++)
+                    {
+                        uint32_t w[3];
+                        lds_words<3>(b4.a + (uint32_t)(y0 + r) * rsB + (uint32_t)x, b4.sh, w);
+#pragma unroll
+                        for (int j = 0; j < 3; j++) { ra.w[j] = ra.w[j + 1]; rb.w[j] = rb.w[j + 1]; }
+                        hpp_row_pair_u8(w, clo, chi, ra.w[3], rb.w[3]);
+                    }
+                    accA += cell_cost_packed<pixel>(s.fenc + y0 * 64 + x, ra, useSatd);
+                    accB += cell_cost_packed<pixel>(s.fenc + y0 * 64 + x, rb, useSatd);
+                }
+        }
+    }
+    costA = accA; costB = accB;
+}
+#endif
+
 // MotionEstimate::subpelCompare (motion.cpp:1571-1599); useSatd selects cmp
 template<typename pixel>
 __device__ __noinline__ int subpel_compare(const MEState<pixel>& s, int qx, int qy, bool useSatd)
@@ -1964,6 +2029,30 @@ __device__ int motion_estimate(const MEState<pixel>& s, MV2 mvmin, MV2 mvmax, MV
             int bdir = 0;
             for (int i = 1; i <= wl.hpel_dirs; i++)
             {
+#ifdef ME_HAS_HPEL_PAIRS
+                // directions (1,2) and (3,4) around a full-pel vector are one filter pass each (thread_hpel_pair_cost); the
+                // two costs are compared in the reference's order
+                if (sizeof(pixel) == 1 && (i == 1 || i == 3) && !((bmv.x | bmv.y) & 3))
+                {
+                    const int ax = bmv.x + c_square1[i][0] * 2, ay = bmv.y + c_square1[i][1] * 2;
+                    const int bx = bmv.x + c_square1[i + 1][0] * 2, by = bmv.y + c_square1[i + 1][1] * 2;
+                    if ((ay >= qmvmin.y) & (ay <= qmvmax.y) & (by >= qmvmin.y) & (by <= qmvmax.y))
+                    {
+                        int ca, cb;
+                        thread_hpel_pair_cost<pixel>(s, s.fref + (bmv.x >> 2) + (int64_t)(bmv.y >> 2) * s.stride, i == 1, hpelSatd, ca, cb);
+                        for (int o = 1; o < s.groupSize; o <<= 1)
+                        {
+                            ca += __shfl_xor_sync(s.groupMask, ca, o);
+                            cb += __shfl_xor_sync(s.groupMask, cb, o);
+                        }
+                        ca += mvcost(s, ax, ay); cb += mvcost(s, bx, by);
+                        if (ca < bcost) { bcost = ca; bdir = i; }
+                        if (cb < bcost) { bcost = cb; bdir = i + 1; }
+                        i++;
+                        continue;
+                    }
+                }
+#endif
                 int qx = bmv.x + c_square1[i][0] * 2, qy = bmv.y + c_square1[i][1] * 2;
                 if ((qy < qmvmin.y) | (qy > qmvmax.y)) continue;
                 int cost = subpel_compare<pixel>(s, qx, qy, hpelSatd) + mvcost(s, qx, qy);
