@@ -17,6 +17,8 @@
 #include "common.cuh"
 #include "tables.cuh"
 #include "x265b200.h"
+#include "interp_cell.cuh"
+#include <cstdlib>
 
 namespace x265b200 {
 
@@ -32,14 +34,6 @@ int upload_filters(Ctx* ctx)
     if (ctx->device < 16) g_filtUploaded[ctx->device] = true;
     return 0;
 }
-
-struct InterpArgs
-{
-    const void* src; int64_t srcStride;
-    void* dst;       int64_t dstStride;
-    const x265b200_interp_job* jobs; int64_t n;
-    int kind, taps, depth, w, h, isRowExt;
-};
 
 template<int N> __device__ __forceinline__ void load_taps(int idx, int c[8])
 {
@@ -160,6 +154,21 @@ interp_kernel(InterpArgs p, int jpc)
     }
 }
 
+// STAGED cell form of the 8-bit luma pp kinds (interp_cell.cuh): one thread per 4x4 output cell.  Off unless the
+// environment says X265B200_INTERP_FAST=1 -- it has been checked on the host only (tests/test_interp_cell_cpu.py).
+__global__ void __launch_bounds__(128)
+interp_pp8_cell_kernel(InterpArgs p)
+{
+    interp_pp8_cell_thread(p, (int64_t)blockIdx.x * 128 + threadIdx.x, c_lumaFilter);
+}
+
+static bool interp_fast_enabled()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("X265B200_INTERP_FAST"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+
 int interp_dev(Ctx* ctx, int kind, int taps, int depth, int w, int h, const void* src, int64_t srcStride,
                void* dst, int64_t dstStride, const x265b200_interp_job* jobs, int64_t n, int isRowExt)
 {
@@ -170,6 +179,17 @@ int interp_dev(Ctx* ctx, int kind, int taps, int depth, int w, int h, const void
     if (upload_filters(ctx)) return -1;
     InterpArgs a; a.src = src; a.srcStride = srcStride; a.dst = dst; a.dstStride = dstStride; a.jobs = jobs; a.n = n;
     a.kind = kind; a.taps = taps; a.depth = depth; a.w = w; a.h = h; a.isRowExt = isRowExt;
+    if (interp_fast_enabled() && depth == 8 && taps == 8 && !(w & 3) && !(h & 3) && !(srcStride & 3) &&
+        (kind == X265B200_IP_HPP || kind == X265B200_IP_VPP || kind == X265B200_IP_HVPP))
+    {
+        const int64_t threads = n * (w >> 2) * (h >> 2);
+        if ((threads + 127) / 128 < 0x7fffffffLL)
+        {
+            interp_pp8_cell_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(a);
+            ctx->launches++;
+            return check(cudaGetLastError(), "interp cell kernel launch");
+        }
+    }
     // jobs per CTA: ~64 output pixels per thread-group keeps every thread busy for small blocks
     const int jpc = w * h <= 32 ? 8 : (w * h <= 64 ? 4 : (w * h <= 128 ? 2 : 1));
     size_t smem = kind == X265B200_IP_HVPP ? (size_t)jpc * w * (h + taps - 1) * sizeof(int16_t) : 0;

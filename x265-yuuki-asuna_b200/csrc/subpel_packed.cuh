@@ -151,3 +151,46 @@ SP_FN void hpp_row_pair_u8(const uint32_t w[3], uint32_t clo, uint32_t chi, uint
     rowA = sp_pack4(o[0], o[1], o[2], o[3]);
     rowB = sp_pack4(o[1], o[2], o[3], o[4]);
 }
+
+// ---- two-pass case (luma_hvpp = hps with row extension + vsp, ipfilter.cpp:362-369), 8-bit ------------------------------
+// w[j][0..2], j = 0..10: the 12 pixels of source row (y0 - 3 + j) starting 3 left of the cell; clo / chi: horizontal taps;
+// cv: vertical taps.  First stage at 8 bits: shift 0, offset -8192 (rides in the accumulator); it lies in [-14312, 14248].
+// Second stage: (sum + 2048 + (8192 << 6)) >> 12 lies in [-262, 436], so the int16 cast is the identity here too.
+SP_FN void hvpp_cell_u8(const uint32_t w[11][3], uint32_t clo, uint32_t chi, const int16_t cv[8], uint32_t out[4])
+{
+    int v[11][4];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < 11; j++)
+    {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int k = 0; k < 4; k++)
+        {
+            const uint32_t lo = sp_funnel_r(w[j][0], w[j][1], 8 * k), hi = sp_funnel_r(w[j][1], w[j][2], 8 * k);
+            v[j][k] = sp_dp4a_us(hi, chi, sp_dp4a_us(lo, clo, -8192));
+        }
+    }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 4; i++)
+    {
+        int o[4];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int k = 0; k < 4; k++)
+        {
+            int sum = 2048 + (8192 << 6);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int t = 0; t < 8; t++) sum += v[i + t][k] * (int)cv[t];
+            o[k] = sp_min_relu(sum >> 12, 255);
+        }
+        out[i] = sp_pack4(o[0], o[1], o[2], o[3]);
+    }
+}
