@@ -1,0 +1,78 @@
+// la_search_emu.cpp -- TEST INFRASTRUCTURE: the lookahead list search (csrc/la_search_thread.cu = estimateCUCost phase 1,
+// slicetype.cpp:3216-3325) on the host.  The device source of the search (csrc/me_device.cuh, lowres thread-only build) is
+// compiled unchanged through me_host_emu.h; this file restates only the kernel's thin per-CU role code and walks the CUs in
+// reverse raster order (the order the wavefront of the kernel is equivalent to).
+#define ME_HOST_EMU 1
+#define ME_FORCE_THREAD 1
+#define ME_LOWRES_ONLY 1
+#ifdef EMU_LA_PACKED_SATD
+#define ME_PACKED_SATD 1
+#endif
+#include "me_device.cuh"
+#include <vector>
+
+namespace x265b200 {
+namespace emu {
+unsigned char* smem_base = nullptr;
+thread_local Group* t_group = nullptr;
+thread_local int t_q = 0;
+}
+
+template<typename pixel>
+static int run_field(int depth, const pixel* const fencPlanes[4], const pixel* const refPlanes[4], int64_t stride, int W, int Hc, int bBidir,
+                     int merange, const uint16_t* costTable, int32_t* mvs, int32_t* mvcosts)
+{
+    std::vector<pixel> fencBuf(8 * 64);
+    for (int cuY = Hc - 1; cuY >= 0; cuY--)
+        for (int cuX = W - 1; cuX >= 0; cuX--)
+        {
+            const int cuXY = cuX + cuY * W;
+            const bool lastRow = cuY == Hc - 1;
+            const int64_t pelOffset = 8 * cuX + (int64_t)8 * cuY * stride;
+            MEState<pixel> s;
+            memset(&s, 0, sizeof(s));
+            s.fenc = fencBuf.data();
+            s.stride = stride; s.isLowres = true; s.perThread = true; s.chromaSatd = false; s.groupSize = 1; s.groupMask = 1u;
+            s.w = 8; s.h = 8; s.lane = 0; s.depth = depth; s.partSizeScale = 4; s.cost = costTable + 2 * 32768;
+            for (int y = 0; y < 8; y++) memcpy(fencBuf.data() + y * 64, fencPlanes[0] + pelOffset + (int64_t)y * stride, 8 * sizeof(pixel));
+            for (int k = 0; k < 4; k++) s.lowres[k] = refPlanes[k] + pelOffset;
+            s.fref = s.lowres[0]; s.gfref = s.lowres[0]; s.gstride = stride;
+
+            int mvc[5][2], numc = 0;
+            if (cuX < W - 1) { mvc[numc][0] = mvs[(cuXY + 1) * 2]; mvc[numc][1] = mvs[(cuXY + 1) * 2 + 1]; numc++; }
+            if (!lastRow)
+            {
+                const int32_t* row = mvs + (int64_t)(cuXY + W) * 2;
+                mvc[numc][0] = row[0]; mvc[numc][1] = row[1]; numc++;
+                if (cuX > 0) { mvc[numc][0] = row[-2]; mvc[numc][1] = row[-1]; numc++; }
+                if (cuX < W - 1) { mvc[numc][0] = row[2]; mvc[numc][1] = row[3]; numc++; }
+            }
+            int mvpx = 0, mvpy = 0, skipCost = 0x7fffffff;
+            if (numc)
+            {
+                int mvpcost = ME_COST_MAX;
+                for (int idx = 0; idx < numc; idx++)
+                {
+                    int cost = lowres_qpel_cost<pixel>(s, mvc[idx][0], mvc[idx][1], true);
+                    if (cost < mvpcost) { mvpcost = cost; mvpx = mvc[idx][0]; mvpy = mvc[idx][1]; }
+                    if (!(mvpx | mvpy) && bBidir) skipCost = cost;
+                }
+            }
+            s.mvpx = mvpx; s.mvpy = mvpy;
+            const MV2 mvmin = mv2(-cuX * 8 - 8, -cuY * 8 - 8), mvmax = mv2((W - cuX - 1) * 8 + 8, (Hc - cuY - 1) * 8 + 8);
+            int ox, oy;
+            int fencCost = motion_estimate<pixel>(s, mvmin, mvmax, mv2(mvpx, mvpy), 0, nullptr, merange, (int)ME_HEX, 1, 1, 0, ox, oy);
+            if (skipCost < 64 && skipCost < fencCost && bBidir) { fencCost = skipCost; ox = 0; oy = 0; }
+            mvs[cuXY * 2] = ox; mvs[cuXY * 2 + 1] = oy; mvcosts[cuXY] = fencCost;
+        }
+    return 0;
+}
+} // namespace x265b200
+
+extern "C" int emu_la_search_field(int depth, const void* const fencPlanes[4], const void* const refPlanes[4], int64_t stride, int widthInCU, int heightInCU,
+                                   int bBidir, int merange, const uint16_t* costTable, int32_t* mvs, int32_t* mvcosts)
+{
+    using namespace x265b200;
+    if (depth > 8) return run_field<uint16_t>(depth, (const uint16_t* const*)fencPlanes, (const uint16_t* const*)refPlanes, stride, widthInCU, heightInCU, bBidir, merange, costTable, mvs, mvcosts);
+    return run_field<uint8_t>(depth, (const uint8_t* const*)fencPlanes, (const uint8_t* const*)refPlanes, stride, widthInCU, heightInCU, bBidir, merange, costTable, mvs, mvcosts);
+}

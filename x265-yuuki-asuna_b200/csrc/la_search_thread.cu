@@ -12,6 +12,9 @@
 // one-warp-per-CU kernel in lookahead_kernels.cu tops out at 0.85 ms per 32 640-CU field; profiles/r01_lookahead.txt).
 #define ME_FORCE_THREAD 1
 #define ME_LOWRES_ONLY 1
+#ifdef LA_PACKED_SATD                 /* staged, not yet measured: packed-word 4x4 SATD (satd_packed.cuh) in the lowres search */
+#define ME_PACKED_SATD 1
+#endif
 #include "me_device.cuh"
 #include "lookahead_args.cuh"
 

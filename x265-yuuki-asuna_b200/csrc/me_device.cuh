@@ -387,6 +387,27 @@ __device__ __forceinline__ int thread_satd(const MEState<pixel>& s, const pixel*
         }
     return acc;
 #else
+#ifdef ME_PACKED_SATD
+    // STAGED for the lookahead kernel (off by default, not yet measured): the packed-word SATD on rows from any address space
+    if constexpr (sizeof(pixel) == 1)
+    {
+#pragma unroll 1
+        for (int cy = 0; cy < s.h; cy += 4)
+#pragma unroll 1
+            for (int cx = 0; cx < ME_PU_W(s); cx += 4)
+            {
+                uint32_t fw[4], ow[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                {
+                    fw[i] = *smem_hint((const uint32_t*)(s.fenc + (cy + i) * 64 + cx));
+                    ld_words<pixel, 1>(r + (int64_t)(cy + i) * rs + cx, &ow[i]);
+                }
+                acc += satd4x4_packed_u8(fw, ow);
+            }
+        return acc;
+    }
+#endif
 #pragma unroll 1
     for (int cy = 0; cy < s.h; cy += 4)
 #pragma unroll 1
@@ -720,7 +741,7 @@ __device__ __noinline__ int cell_cost_packed(const pixel* f, CellRows<pixel> row
     constexpr int NW = 4 * (int)sizeof(pixel) / 4;
     if (useSatd)
     {
-#ifdef ME_WINDOW_FAST
+#if defined(ME_WINDOW_FAST) || defined(ME_PACKED_SATD)
         if constexpr (sizeof(pixel) == 1)
         {
             uint32_t fw[4];
