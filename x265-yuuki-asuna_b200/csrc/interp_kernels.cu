@@ -162,11 +162,10 @@ interp_pp8_cell_kernel(InterpArgs p)
     interp_pp8_cell_thread(p, (int64_t)blockIdx.x * 128 + threadIdx.x, c_lumaFilter);
 }
 
-static bool interp_fast_enabled()
+static bool interp_fast_enabled()          // read on every call so that an A/B script can flip it inside one process
 {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("X265B200_INTERP_FAST"); v = (e && e[0] == '1') ? 1 : 0; }
-    return v == 1;
+    const char* e = getenv("X265B200_INTERP_FAST");
+    return e && e[0] == '1';
 }
 
 int interp_dev(Ctx* ctx, int kind, int taps, int depth, int w, int h, const void* src, int64_t srcStride,
