@@ -405,9 +405,10 @@ __device__ __forceinline__ int thread_satd(const MEState<pixel>& s, const pixel*
                 }
                 acc += satd4x4_packed_u8(fw, ow);
             }
-        return acc;
     }
+    else
 #endif
+    {
 #pragma unroll 1
     for (int cy = 0; cy < s.h; cy += 4)
 #pragma unroll 1
@@ -427,6 +428,7 @@ __device__ __forceinline__ int thread_satd(const MEState<pixel>& s, const pixel*
             }
             acc += satd_cell(d);
         }
+    }
     return acc;
 #endif
 }
