@@ -25,3 +25,7 @@ if [ -f $P/libx265b200_la.so ]; then
   done
   tail -12 gpurun_out/staged_la.log
 fi
+# 4. intra: cell form vs persistent shared-memory form on the bench's intra stage, then the parity tests with the cell form on
+timeout 120 python scripts/ab_intra.py
+X265B200_INTRA_FAST=1 timeout 120 python -m pytest tests/test_interp_intra_gpu.py tests/test_fullsize_gpu.py -k intra -x -q > gpurun_out/staged_intra_tests.log 2>&1
+tail -3 gpurun_out/staged_intra_tests.log
