@@ -78,9 +78,34 @@ SP_FN int intra_cell_inv_angle(int k)                       // :124 invAngle tab
     return k == 0 ? 4096 : (k == 1 ? 1638 : (k == 2 ? 910 : (k == 3 ? 630 : (k == 4 ? 482 : (k == 5 ? 390 : (k == 6 ? 315 : 256))))));
 }
 
-// CH (8 or 16) bytes of row y starting at column x of angular mode `mode` predicted from neighbour array arr
-SP_FN void intra_cell_ang_seg(const uint8_t* arr, int N, int mode, int bEdge, int y, int x, int CH, uint32_t* ow)
+// out[i] = bytes 4i .. 4i+3 of the run that starts at p, of which only bytes [from, nbytes) are wanted: aligned words that hold
+// none of them are not read, and the unwanted low bytes come back as zero
+template<int NW> SP_FN void xc_bytes_from(const uint8_t* p, int from, int nbytes, uint32_t out[NW])
 {
+    const intptr_t a = (intptr_t)p;
+    const intptr_t w0 = a & ~(intptr_t)3;
+    const uint32_t sh = (uint32_t)(a & 3) * 8;
+    const int first = (int)(((a + from) >> 2) - (a >> 2)), last = (int)(((a + nbytes - 1) >> 2) - (a >> 2));
+    uint32_t t[NW + 1];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i <= NW; i++) t[i] = (i >= first && i <= last) ? xc_ld32((const uint32_t*)(w0 + 4 * i)) : 0u;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < NW; i++)
+    {
+        const int lo = from - 4 * i;                         // bytes below `lo` of this word are not wanted
+        const uint32_t keep = lo <= 0 ? 0xFFFFFFFFu : (lo >= 4 ? 0u : 0xFFFFFFFFu << (8 * lo));
+        out[i] = sp_funnel_r(t[i], t[i + 1], sh) & keep;
+    }
+}
+
+// CH (8 or 16) bytes of row y starting at column x of angular mode `mode` predicted from neighbour array arr
+template<int CH> SP_FN void intra_cell_ang_seg(const uint8_t* arr, int N, int mode, int bEdge, int y, int x, uint32_t* ow)
+{
+    constexpr int NW = CH / 4, NE = NW + 1;
     const int N2 = N << 1;
     const bool hor = mode < 18;
     const int angleOffset = hor ? 10 - mode : mode - 26;
@@ -89,37 +114,38 @@ SP_FN void intra_cell_ang_seg(const uint8_t* arr, int N, int mode, int bEdge, in
     const uint8_t* side = arr + (hor ? 0 : N2);             // nb(2N + j) = side[j]
     const int angleSum = (y + 1) * angle, offset = angleSum >> 5;
     const uint32_t f = (uint32_t)(angleSum & 31), g = 32u - f;
-    const int first = offset + x, need = CH + (f ? 1 : 0), nw = CH >> 2;
-    uint32_t e[5];
-    if (first >= 0) xc_bytes<5>(mainp + 1 + first, need, e);
+    const int first = offset + x, need = CH + (f ? 1 : 0);
+    uint32_t e[NE];
+    if (first >= 0) xc_bytes<NE>(mainp + 1 + first, need, e);
     else
     {
-        // some entries lie left of ref[0]: ref[-1] is the corner, ref[idx < -1] the inverse-angle projection of the side (:146-172)
-        const int inv = angle < 0 ? intra_cell_inv_angle(-angleOffset - 1) : 0;
+        // the first ng entries lie left of ref[0]: ref[-1] is the corner, ref[idx < -1] the inverse-angle projection of the side
+        // (:146-172); they are gathered byte by byte, the rest of the segment is the contiguous run that starts at ref[0]
+        const int ng = -first < need ? -first : need;
+        if (ng < need) xc_bytes_from<NE>(mainp + 1 + first, ng, need, e);
+        else
+        {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-        for (int k = 0; k < 5; k++) e[k] = 0;
-        for (int k = 0; k < need; k++)
+            for (int k = 0; k < NE; k++) e[k] = 0;
+        }
+        const int inv = intra_cell_inv_angle(-angleOffset - 1);
+        for (int k = 0; k < ng; k++)
         {
             const int idx = first + k;
-            uint32_t v;
-            if (idx >= 0) v = xc_ld8(mainp + 1 + idx);
-            else if (idx == -1) v = xc_ld8(arr);
-            else v = xc_ld8(side + ((128 + (-1 - idx) * inv) >> 8));
-            const uint32_t sh = (uint32_t)(k & 3) * 8;
+            const uint32_t v = xc_ld8(idx == -1 ? arr : side + ((128 + (-1 - idx) * inv) >> 8)) << ((uint32_t)(k & 3) * 8);
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-            for (int j = 0; j < 5; j++) e[j] |= j == (k >> 2) ? v << sh : 0u;
+            for (int j = 0; j < NE; j++) e[j] |= j == (k >> 2) ? v : 0u;
         }
     }
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int k = 0; k < 4; k++)
+    for (int k = 0; k < NW; k++)
     {
-        if (k >= nw) break;
         const uint32_t A = e[k];
         if (f)
         {
@@ -219,7 +245,8 @@ SP_FN void intra_modes8_cell_thread(const IntraCellArgs& p, int64_t g)
         {
             const int d26 = mode > 26 ? mode - 26 : 26 - mode, d10 = mode > 10 ? mode - 10 : 10 - mode;
             const uint8_t* arr = (d26 < d10 ? d26 : d10) > thr ? filt : raw;
-            intra_cell_ang_seg(arr, N, mode, p.bLuma, y, x, CH, o);
+            if (CH == 8) intra_cell_ang_seg<8>(arr, N, mode, p.bLuma, y, x, o);
+            else         intra_cell_ang_seg<16>(arr, N, mode, p.bLuma, y, x, o);
         }
     }
     uint8_t* dst = p.dest + ((int64_t)b * NM + mi) * (N * N) + r;
