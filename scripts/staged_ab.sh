@@ -3,6 +3,8 @@
 #   gpurun --timeout 240 -- 'bash scripts/staged_ab.sh'
 # after building the variant libraries HERE (they travel with the snapshot):
 #   make -C x265-yuuki-asuna_b200/csrc exp EXPNAME=hp EXPFLAGS=-DME_HPEL_PAIRS=1
+#   make -C x265-yuuki-asuna_b200/csrc exp EXPNAME=vr EXPFLAGS=-DME_VCELL_REUSE=1
+#   make -C x265-yuuki-asuna_b200/csrc exp EXPNAME=hpvr EXPFLAGS='-DME_HPEL_PAIRS=1 -DME_VCELL_REUSE=1'
 #   make -C x265-yuuki-asuna_b200/csrc exp EXPNAME=la EXPSRC=la_search_thread EXPFLAGS=-DLA_PACKED_SATD=1
 # Results: gpurun_out/ab_me_frame.log, ab_interp.log, staged_la.log, staged_interp_tests.log
 set -u
@@ -10,7 +12,8 @@ cd "$(dirname "$0")/.."
 P=x265-yuuki-asuna_b200
 mkdir -p gpurun_out
 # 1. frame search: half-pel candidate pairs (equal results on 144 cases + a 2160p frame, then timing)
-[ -f $P/libx265b200_hp.so ] && timeout 60 python scripts/ab_me_frame.py --exp $P/libx265b200_hp.so
+EXPS=""; for v in hp vr hpvr; do [ -f $P/libx265b200_$v.so ] && EXPS="$EXPS --exp $P/libx265b200_$v.so"; done
+[ -n "$EXPS" ] && timeout 90 python scripts/ab_me_frame.py $EXPS
 # 2. interpolation: cell form vs pixel form on the bench's 173 400 blocks, then the parity tests with the cell form on
 timeout 60 python scripts/ab_interp.py
 X265B200_INTERP_FAST=1 timeout 120 python -m pytest tests/test_interp_intra_gpu.py tests/test_mc_gpu.py -x -q > gpurun_out/staged_interp_tests.log 2>&1

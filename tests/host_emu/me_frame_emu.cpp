@@ -18,6 +18,9 @@
 #ifdef EMU_HPEL_PAIRS
 #define ME_HPEL_PAIRS 1
 #endif
+#ifdef EMU_VCELL_REUSE
+#define ME_VCELL_REUSE 1
+#endif
 #include "me_device.cuh"
 #include <vector>
 

@@ -868,6 +868,34 @@ __device__ __noinline__ int thread_subpel_cost(const MEState<pixel>& s, const pi
 #pragma unroll
             for (int t = 0; t < 8; t++) cvt[t] = c_meLumaFilter[yFrac][t];
             const uint32_t cvlo = sp_taps(cvt, 0), cvhi = sp_taps(cvt, 4);
+#ifdef ME_VCELL_REUSE
+            // STAGED (off by default, not yet measured): vertically adjacent cells share two of their three transposed 4-row blocks;
+            // per cell only rows y0+5..y0+8 are loaded and transposed (the window keeps spare rows below the 8-tap footprint)
+#pragma unroll 1
+            for (int x = 0; x < W; x += 4)
+            {
+                uint32_t c0[4], c1[4], c2[4], r[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) lds_words<1>(b0.a + (uint32_t)(j - 3) * rsB + (uint32_t)x, b0.sh, &r[j]);
+                sp_transpose4(r[0], r[1], r[2], r[3], c0);
+#pragma unroll
+                for (int j = 0; j < 4; j++) lds_words<1>(b0.a + (uint32_t)(j + 1) * rsB + (uint32_t)x, b0.sh, &r[j]);
+                sp_transpose4(r[0], r[1], r[2], r[3], c1);
+#pragma unroll 1
+                for (int y0 = 0; y0 < H; y0 += 4)
+                {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) lds_words<1>(b0.a + (uint32_t)(y0 + 5 + j) * rsB + (uint32_t)x, b0.sh, &r[j]);
+                    sp_transpose4(r[0], r[1], r[2], r[3], c2);
+                    CellRows<pixel> rows;
+                    vpp_cell_from_cols_u8(c0, c1, c2, cvlo, cvhi, rows.w);
+                    acc += cell_cost_packed<pixel>(s.fenc + y0 * 64 + x, rows, useSatd);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) { c0[k] = c1[k]; c1[k] = c2[k]; }
+                }
+            }
+            return acc;
+#else
 #pragma unroll 1
             for (int x = 0; x < W; x += 4)
 #pragma unroll 1
@@ -881,6 +909,7 @@ __device__ __noinline__ int thread_subpel_cost(const MEState<pixel>& s, const pi
                     acc += cell_cost_packed<pixel>(s.fenc + y0 * 64 + x, rows, useSatd);
                 }
             return acc;
+#endif
         }
     }
 #endif

@@ -194,3 +194,33 @@ SP_FN void hvpp_cell_u8(const uint32_t w[11][3], uint32_t clo, uint32_t chi, con
         out[i] = sp_pack4(o[0], o[1], o[2], o[3]);
     }
 }
+
+// ---- the vertical cell in two halves, for loops that carry the transposed blocks from one cell to the next ------------------
+// c[k] = rows r0..r3 of column k, one byte each
+SP_FN void sp_transpose4(uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3, uint32_t c[4])
+{
+    const uint32_t t0 = sp_prmt(r0, r1, 0x5140), t1 = sp_prmt(r2, r3, 0x5140);
+    const uint32_t t2 = sp_prmt(r0, r1, 0x7362), t3 = sp_prmt(r2, r3, 0x7362);
+    c[0] = sp_prmt(t0, t1, 0x5410); c[1] = sp_prmt(t0, t1, 0x7632);
+    c[2] = sp_prmt(t2, t3, 0x5410); c[3] = sp_prmt(t2, t3, 0x7632);
+}
+// c0 / c1 / c2: source rows y0-3..y0, y0+1..y0+4, y0+5..y0+8 of the cell's four columns (sp_transpose4); out[i]: predicted row y0+i
+SP_FN void vpp_cell_from_cols_u8(const uint32_t c0[4], const uint32_t c1[4], const uint32_t c2[4], uint32_t cvlo, uint32_t cvhi, uint32_t out[4])
+{
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 4; i++)
+    {
+        int o[4];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int k = 0; k < 4; k++)
+        {
+            const uint32_t lo = sp_funnel_r(c0[k], c1[k], 8 * i), hi = sp_funnel_r(c1[k], c2[k], 8 * i);
+            o[k] = sp_min_relu(sp_dp4a_us(hi, cvhi, sp_dp4a_us(lo, cvlo, 32)) >> 6, 255);
+        }
+        out[i] = sp_pack4(o[0], o[1], o[2], o[3]);
+    }
+}
