@@ -4,10 +4,11 @@
 // (64 + 2*(merange+8) pixels square, enough for every integer candidate, the hex/square overshoot and the
 // 8-tap sub-pel footprint) are brought into shared memory by two TMA tile loads
 // (cp.async.bulk.tensor.2d, SASS UTMALDG) signalled on an mbarrier; all 85 2Nx2N PU searches of the CTU
-// (64x64, 4x 32x32, 16x 16x16, 64x 8x8) then run out of shared memory, one warp per PU search, with the
-// same warp-cooperative bit-exact device algorithm as me_batch_kernel (me_device.cuh =
-// MotionEstimate::motionEstimate, motion.cpp:739-1569).  The window pitch is 16*k bytes chosen so that 8
-// consecutive rows fall in distinct banks; the box start is aligned down to 16 bytes as TMA requires.
+// (64x64, 4x 32x32, 16x 16x16, 64x 8x8) then run out of shared memory with the per-thread form of the
+// bit-exact device algorithm of me_device.cuh (= MotionEstimate::motionEstimate, motion.cpp:739-1569): a lane
+// owns an 8-wide sub-block of a PU, the lanes of a PU add their partial costs (roles below).  The window pitch
+// is 16*k bytes chosen so that 8 consecutive rows fall in distinct banks; the box start is aligned down to 16
+// bytes as TMA requires.
 //
 // Per-PU semantics: motionEstimate(ref, mvmin = (mvp>>2) - merange, mvmax = (mvp>>2) + merange, qmvp = mvp,
 // numCandidates = 0, merange, ...) with the CTU's predictor mvp shared by all its PUs (Search::setSearchRange
@@ -101,8 +102,8 @@ __device__ unsigned long long g_mfCycles[MF_WARPS + 1];
 //   warp 2 : the sixteen 16x16 PUs, eight at a time, 4 lanes x 8x8 each
 //   warp 3 : the sixty-four 8x8 PUs, thirty-two at a time, one lane each
 // No scratch at all: sub-pel predictions are produced and costed cell by cell in registers (thread_subpel_cost).
-// Residency: 3 CTAs per SM at 168 registers measured best (3.21 ms per 2160p frame x 3 refs; 4 CTAs at 128 registers: 3.31 ms,
-// 2 CTAs at 212 registers: 3.49 ms).
+// Residency: 4 CTAs per SM at 128 registers (shared-memory limited: 43 KB window + 4 KB fenc); 3 CTAs at 168 registers measured
+// the same after the sub-pel rewrite, 2 CTAs at 212 registers slower.
 template<typename pixel>
 __global__ void __launch_bounds__(MF_WARPS * 32, 4)
 me_frame_kernel(const __grid_constant__ MEFrameMaps maps, MEFrameArgs p)
