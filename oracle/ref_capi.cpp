@@ -19,6 +19,7 @@
 #include "x265.h"
 
 #include <thread>
+#include <atomic>
 #include <vector>
 #include <cstring>
 
@@ -37,23 +38,50 @@ void ensure_init()
     g_init = true;
 }
 
-/* run fn(i) for i in [0,n) on `threads` std::threads, disjoint contiguous ranges */
+/* run fn(i, t) for i in [0,n) on `threads` std::threads.  Work is handed out dynamically in small chunks from an atomic
+ * counter (jobs differ in cost by two orders of magnitude -- a 64x64 search against an 8x8 one -- so static contiguous ranges
+ * would leave most threads idle).  t is the worker index, stable for the lifetime of the call. */
 template<class F> void parallel_for(int64_t n, int threads, F fn)
 {
     if (threads <= 1 || n < 2) { for (int64_t i = 0; i < n; i++) fn(i, 0); return; }
+    if ((int64_t)threads > n) threads = (int)n;
+    std::atomic<int64_t> next(0);
+    int64_t chunk = n / ((int64_t)threads * 64);
+    if (chunk < 1) chunk = 1;
+    if (chunk > 64) chunk = 64;
     std::vector<std::thread> pool;
-    int64_t chunk = (n + threads - 1) / threads;
     for (int t = 0; t < threads; t++)
-    {
-        int64_t lo = t * chunk, hi = lo + chunk < n ? lo + chunk : n;
-        if (lo >= hi) break;
-        pool.emplace_back([=]() { for (int64_t i = lo; i < hi; i++) fn(i, t); });
-    }
+        pool.emplace_back([&, t]() {
+            for (;;)
+            {
+                int64_t lo = next.fetch_add(chunk);
+                if (lo >= n) break;
+                int64_t hi = lo + chunk < n ? lo + chunk : n;
+                for (int64_t i = lo; i < hi; i++) fn(i, t);
+            }
+        });
     for (auto& th : pool) th.join();
 }
 }
 
 extern "C" {
+
+/* Installs the reference's SSE-intrinsic entries (vec/vec-primitives.cpp:62 setupInstrinsicPrimitives: cu[8/16/32].idct,
+ * cu[16/32].dct, dequant_scaling) over the C table -- the only optimised table that builds without nasm.  Opt-in: the parity
+ * tests keep comparing against the plain C table; bench.py's CPU legs call this so the baseline is the reference's best
+ * buildable path.  Returns the number of slots that changed. */
+int ref_enable_intrinsics(void)
+{
+    ensure_init();
+    EncoderPrimitives before = primitives;
+    setupInstrinsicPrimitives(primitives, X265_CPU_SSE2 | X265_CPU_SSE3 | X265_CPU_SSSE3 | X265_CPU_SSE4);
+    int changed = 0;
+    for (int i = 0; i < NUM_CU_SIZES; i++)
+        changed += (before.cu[i].dct != primitives.cu[i].dct) + (before.cu[i].idct != primitives.cu[i].idct);
+    changed += before.dequant_scaling != primitives.dequant_scaling;
+    for (int i = 0; i < NUM_CU_SIZES; i++) primitives.cu[i].standard_dct = primitives.cu[i].dct;
+    return changed;
+}
 
 int ref_depth(void) { return X265_DEPTH; }
 int ref_pixel_bytes(void) { return (int)sizeof(pixel); }

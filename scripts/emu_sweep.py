@@ -1,12 +1,12 @@
 """Extended CPU sweep of the frame search's device source through the host emulation (tests/host_emu): DIA / HEX / UMH / STAR x
 subme 0..7 x 8/10-bit (+ FULL), two CTUs each, every 2Nx2N PU against the reference's MotionEstimate -- for the shipped build and
-for all staged variants together.  ~3 minutes on 16 cores; the pytest subset is tests/test_me_host_emu_cpu.py."""
+with the shared vertical cells switched off.  ~3 minutes on 16 cores; the pytest subset is tests/test_me_host_emu_cpu.py."""
 import sys, ctypes, subprocess, os, itertools, time
 sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests')
 import test_me_host_emu_cpu as t
 ROOT='/root/repo'
 libs={}
-for name,flags in {"default":[], "all_staged":["-DEMU_HPEL_PAIRS=1","-DEMU_VCELL_REUSE=1"]}.items():
+for name,flags in {"default":[], "no_vcell_reuse":["-DEMU_VCELL_REUSE_OFF=1"]}.items():
     so='/tmp/emu_sweep_%s.so'%name
     subprocess.run(["g++","-O1","-std=c++17","-shared","-fPIC","-pthread","-Wno-unknown-pragmas"]+flags+["-I",ROOT+"/tests/host_emu","-I",ROOT+"/x265-yuuki-asuna_b200/csrc","-I",ROOT+"/include","-o",so,ROOT+"/tests/host_emu/me_frame_emu.cpp"],check=True)
     libs[name]=ctypes.CDLL(so)

@@ -5,7 +5,7 @@
 #define ME_HOST_EMU 1
 #define ME_FORCE_THREAD 1
 #define ME_LOWRES_ONLY 1
-#ifdef EMU_LA_PACKED_SATD
+#ifndef EMU_LA_PACKED_SATD_OFF
 #define ME_PACKED_SATD 1
 #endif
 #include "me_device.cuh"

@@ -15,10 +15,7 @@
 #ifndef EMU_BATCH_GROUPSUM_OFF
 #define ME_BATCH_GROUPSUM 1
 #endif
-#ifdef EMU_HPEL_PAIRS
-#define ME_HPEL_PAIRS 1
-#endif
-#ifdef EMU_VCELL_REUSE
+#ifndef EMU_VCELL_REUSE_OFF
 #define ME_VCELL_REUSE 1
 #endif
 #include "me_device.cuh"

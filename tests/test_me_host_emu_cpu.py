@@ -20,8 +20,8 @@ pkg = importlib.import_module("x265-yuuki-asuna_b200")
 needs_ref = pytest.mark.skipif(not oracle.have_ref(8), reason="oracle/_ref not built (no /root/reference here)")
 
 
-# the build the kernel ships, the staged variants (-DME_HPEL_PAIRS, -DME_VCELL_REUSE), and the generic-pointer form kept for A/B runs
-VARIANTS = {"default": [], "hpel_pairs": ["-DEMU_HPEL_PAIRS=1"], "vcell_reuse": ["-DEMU_VCELL_REUSE=1"], "window_slow": ["-DEMU_WINDOW_SLOW=1"]}
+# the build the kernel ships, the same without the shared vertical cells, and the generic-pointer form kept for A/B runs
+VARIANTS = {"default": [], "no_vcell_reuse": ["-DEMU_VCELL_REUSE_OFF=1"], "window_slow": ["-DEMU_WINDOW_SLOW=1"]}
 
 
 @pytest.fixture(scope="module", params=sorted(VARIANTS))

@@ -413,7 +413,10 @@ void extend_row_border_thunk(pixel* txt, intptr_t stride, int width, int height,
     char* d = (char*)dev(0, span * PX);
     CK(x265b200_upload(C(), d, txt - marginX, span * PX));
     CK(x265b200_extend_border_dev(C(), X265_DEPTH, d + (size_t)marginX * PX, stride, width, height, marginX, 0));
-    CK(x265b200_download(C(), txt - marginX, d, span * PX));
+    // only what extendCURowColBorder writes (ipfilter.cpp:59-77) travels back: the left and right margins of each row.  The
+    // picture columns in between belong to other rows' worker threads (WPP / frame filter) and must not be rewritten.
+    CK(x265b200_download2d(C(), txt - marginX, (size_t)stride * PX, d, (size_t)stride * PX, (size_t)marginX * PX, height));
+    CK(x265b200_download2d(C(), txt + width, (size_t)stride * PX, d + (size_t)(marginX + width) * PX, (size_t)stride * PX, (size_t)marginX * PX, height));
 }
 void scale1D_thunk(pixel* dst, const pixel* src)
 {
@@ -439,11 +442,13 @@ x265b200_sao_job sao_job(int64_t recOff, int64_t buf0, int64_t buf1, int width, 
     j.recOff = recOff; j.buf0 = buf0; j.buf1 = buf1; j.width = width; j.height = height; j.startX = startX;
     return j;
 }
-// runs one apply job on a staged copy of rec[0, ext) and of the sign buffers; bufBytes[k] bytes of hostBuf[k] travel both ways
+// runs one apply job on a staged copy of rec[0, ext) and of the sign buffers.  Only what the C loop writes travels back
+// (loopfilter.cpp:45-139): columns [x0, x1) of `height` rows of rec, and bytes [w0, w1) of hostBuf0 -- the neighbour rows and
+// columns that were staged for reading belong to other CTUs' worker threads and are never rewritten.
 void sao_apply_run(int kind, pixel* rec, size_t ext, intptr_t stride, const int8_t* offsets, int nOffsets, int width, int height, int startX,
-                   int8_t* hostBuf0, size_t bytes0, bool write0, const int8_t* hostBuf1, size_t bytes1)
+                   int x0, int x1, int8_t* hostBuf0, size_t bytes0, size_t w0, size_t w1, const int8_t* hostBuf1, size_t bytes1)
 {
-    void* dR = up1d(0, rec, ext * PX);
+    char* dR = (char*)up1d(0, rec, ext * PX);
     const size_t off1 = (bytes0 + 15) & ~(size_t)15;
     int8_t* dB = (int8_t*)dev(1, off1 + bytes1 + 16);
     if (bytes0) CK(x265b200_upload(C(), dB, hostBuf0, bytes0));
@@ -452,36 +457,39 @@ void sao_apply_run(int kind, pixel* rec, size_t ext, intptr_t stride, const int8
     x265b200_sao_job job = sao_job(0, 0, (int64_t)off1, width, height, startX);
     void* dJ = up1d(3, &job, sizeof(job));
     CK(x265b200_sao_apply_dev(C(), kind, X265_DEPTH, dR, stride, (const x265b200_sao_job*)dJ, 1, dB, (const int8_t*)dO, width));
-    CK(x265b200_download(C(), rec, dR, ext * PX));
-    if (write0 && bytes0) CK(x265b200_download(C(), hostBuf0, dB, bytes0));
+    if (x1 > x0)
+        CK(x265b200_download2d(C(), rec + x0, (size_t)stride * PX, dR + (size_t)x0 * PX, (size_t)stride * PX, (size_t)(x1 - x0) * PX, height));
+    if (w1 > w0) CK(x265b200_download(C(), hostBuf0 + w0, dB + w0, w1 - w0));
 }
 void saoE0_thunk(pixel* rec, int8_t* offsetEo, int width, int8_t* signLeft, intptr_t stride)
 {
-    sao_apply_run(X265B200_SAO_E0, rec, (size_t)stride + width + 1, stride, offsetEo, 5, width, 2, 0, signLeft, 2, false, nullptr, 0);
+    sao_apply_run(X265B200_SAO_E0, rec, (size_t)stride + width + 1, stride, offsetEo, 5, width, 2, 0, 0, width, signLeft, 2, 0, 0, nullptr, 0);
 }
 void saoE1_thunk(pixel* rec, int8_t* upBuff1, int8_t* offsetEo, intptr_t stride, int width)
 {
-    sao_apply_run(X265B200_SAO_E1, rec, (size_t)stride + width, stride, offsetEo, 5, width, 1, 0, upBuff1, width, true, nullptr, 0);
+    sao_apply_run(X265B200_SAO_E1, rec, (size_t)stride + width, stride, offsetEo, 5, width, 1, 0, 0, width, upBuff1, width, 0, width, nullptr, 0);
 }
 void saoE1_2rows_thunk(pixel* rec, int8_t* upBuff1, int8_t* offsetEo, intptr_t stride, int width)
 {
-    sao_apply_run(X265B200_SAO_E1_2ROWS, rec, (size_t)2 * stride + width, stride, offsetEo, 5, width, 2, 0, upBuff1, width, true, nullptr, 0);
+    sao_apply_run(X265B200_SAO_E1_2ROWS, rec, (size_t)2 * stride + width, stride, offsetEo, 5, width, 2, 0, 0, width, upBuff1, width, 0, width, nullptr, 0);
 }
 void saoE2_thunk(pixel* rec, int8_t* bufft, int8_t* buff1, int8_t* offsetEo, int width, intptr_t stride)
 {
-    sao_apply_run(X265B200_SAO_E2, rec, (size_t)stride + width + 1, stride, offsetEo, 5, width, 1, 0, bufft, (size_t)width + 1, true, buff1, width);
+    // bufft[x + 1] is written for x in [0, width)
+    sao_apply_run(X265B200_SAO_E2, rec, (size_t)stride + width + 1, stride, offsetEo, 5, width, 1, 0, 0, width, bufft, (size_t)width + 1, 1, (size_t)width + 1, buff1, width);
 }
 void saoE3_thunk(pixel* rec, int8_t* upBuff1, int8_t* offsetEo, intptr_t stride, int startX, int endX)
 {
-    if (endX <= 0) return;
-    sao_apply_run(X265B200_SAO_E3, rec, (size_t)stride + endX, stride, offsetEo, 5, endX, 1, startX, upBuff1, endX, true, nullptr, 0);
+    if (endX <= startX + 1) return;
+    // x runs over (startX, endX): rec[x] and upBuff1[x - 1] are written
+    sao_apply_run(X265B200_SAO_E3, rec, (size_t)stride + endX, stride, offsetEo, 5, endX, 1, startX, startX + 1, endX, upBuff1, endX, startX, (size_t)endX - 1, nullptr, 0);
 }
 void saoB0_thunk(pixel* rec, const int8_t* offsetBo, int ctuWidth, int ctuHeight, intptr_t stride)
 {
     if (ctuWidth <= 0 || ctuHeight <= 0) return;
-    sao_apply_run(X265B200_SAO_B0, rec, (size_t)(ctuHeight - 1) * stride + ctuWidth, stride, offsetBo, 32, ctuWidth, ctuHeight, 0, nullptr, 0, false, nullptr, 0);
+    sao_apply_run(X265B200_SAO_B0, rec, (size_t)(ctuHeight - 1) * stride + ctuWidth, stride, offsetBo, 32, ctuWidth, ctuHeight, 0, 0, ctuWidth, nullptr, 0, 0, 0, nullptr, 0);
 }
-// statistics: rec is staged from rec - 1 (E0 / E2 read the left neighbour of column 0) through rec[endY*stride + endX]
+
 void sao_stats_run(int kind, const int16_t* diff, const pixel* rec, intptr_t stride, int8_t* up1, int8_t* upt, int endX, int endY,
                    int32_t* stats, int32_t* count)
 {

@@ -1,4 +1,4 @@
-// interp_cell.cuh -- STAGED (off unless X265B200_INTERP_FAST=1; not yet run on a GPU): 8-bit luma pp interpolation
+// interp_cell.cuh -- 8-bit luma pp interpolation of the batched entry (x265b200_interp_dev; measured 2.78x, profiles/r02_staged_ab.txt):
 // (luma_hpp / luma_vpp / luma_hvpp) with ONE THREAD PER 4x4 OUTPUT CELL on packed words (subpel_packed.cuh) instead of one
 // thread per pixel with byte loads: ~10 / 12 / 26 instructions per pixel against ~45 / 45 / 115.
 // The whole per-thread function lives here so that the same source runs on the host (tests/test_interp_cell_cpu.py executes

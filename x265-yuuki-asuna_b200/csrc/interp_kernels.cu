@@ -154,18 +154,13 @@ interp_kernel(InterpArgs p, int jpc)
     }
 }
 
-// STAGED cell form of the 8-bit luma pp kinds (interp_cell.cuh): one thread per 4x4 output cell.  Off unless the
-// environment says X265B200_INTERP_FAST=1 -- it has been checked on the host only (tests/test_interp_cell_cpu.py).
+// Cell form of the 8-bit luma pp kinds (interp_cell.cuh): one thread per 4x4 output cell on packed words.  Measured 2.78x the
+// pixel-per-thread kernel on the bench's 173 400 blocks with identical planes (profiles/r02_staged_ab.txt); the same source
+// runs on the host in tests/test_interp_cell_cpu.py.
 __global__ void __launch_bounds__(128)
 interp_pp8_cell_kernel(InterpArgs p)
 {
     interp_pp8_cell_thread(p, (int64_t)blockIdx.x * 128 + threadIdx.x, c_lumaFilter);
-}
-
-static bool interp_fast_enabled()          // read on every call so that an A/B script can flip it inside one process
-{
-    const char* e = getenv("X265B200_INTERP_FAST");
-    return e && e[0] == '1';
 }
 
 int interp_dev(Ctx* ctx, int kind, int taps, int depth, int w, int h, const void* src, int64_t srcStride,
@@ -178,7 +173,7 @@ int interp_dev(Ctx* ctx, int kind, int taps, int depth, int w, int h, const void
     if (upload_filters(ctx)) return -1;
     InterpArgs a; a.src = src; a.srcStride = srcStride; a.dst = dst; a.dstStride = dstStride; a.jobs = jobs; a.n = n;
     a.kind = kind; a.taps = taps; a.depth = depth; a.w = w; a.h = h; a.isRowExt = isRowExt;
-    if (interp_fast_enabled() && depth == 8 && taps == 8 && !(w & 3) && !(h & 3) && !(srcStride & 3) &&
+    if (depth == 8 && taps == 8 && !(w & 3) && !(h & 3) && !(srcStride & 3) &&
         (kind == X265B200_IP_HPP || kind == X265B200_IP_VPP || kind == X265B200_IP_HVPP))
     {
         const int64_t threads = n * (w >> 2) * (h >> 2);

@@ -13,7 +13,6 @@
 // Roofline: HBM-bound, (4N+1) + N*N pixels per (block, mode).
 #include "common.cuh"
 #include "x265b200.h"
-#include "intra_cell.cuh"
 #include <cstdlib>
 
 namespace x265b200 {
@@ -504,49 +503,12 @@ int intra_filter_dev(Ctx* ctx, int depth, int log2N, const void* src, void* dst,
     return check(cudaGetLastError(), "intra_filter kernel launch");
 }
 
-// STAGED cell form of the 8-bit all-modes prediction (intra_cell.cuh): one thread per 16 output bytes, no shared memory.
-// Off unless the environment says X265B200_INTRA_FAST=1 (read per call, so an A/B script can flip it inside one process) --
-// it has been checked on the host only (tests/test_intra_cell_cpu.py).
-__global__ void __launch_bounds__(128)
-intra_modes8_cell_kernel(IntraCellArgs p)
-{
-    intra_modes8_cell_thread(p, (int64_t)blockIdx.x * 128 + threadIdx.x);
-}
-
 int scratch_dev(Ctx* ctx, int slot, size_t bytes, void** out);
-
-static bool intra_fast_enabled()
-{
-    const char* e = getenv("X265B200_INTRA_FAST");
-    return e && e[0] == '1';
-}
 
 static int intra_allangs_launch(Ctx* ctx, int depth, int log2N, const void* refPix, const void* filtPix, void* dest, int bLuma, int64_t n, int all35)
 {
     if (n <= 0) return 0;
     if (log2N < 2 || log2N > 5) { set_error("intra_allangs: log2N %d", log2N); return -1; }
-    if (intra_fast_enabled() && depth == 8 && log2N >= 3)
-    {
-        const int N = 1 << log2N;
-        IntraCellArgs a; a.raw = (const uint8_t*)refPix; a.filt = (const uint8_t*)filtPix; a.dest = (uint8_t*)dest;
-        a.log2N = log2N; a.bLuma = bLuma; a.all35 = all35; a.n = n;
-        if (!filtPix)
-        {
-            // the 35-mode form gets only the raw neighbours: smooth them into scratch first (intraFilter<N>, intrapred.cpp:31-51)
-            void* scr = nullptr;
-            if (scratch_dev(ctx, 6, (size_t)n * (4 * N + 1), &scr)) return -1;
-            intra_filter_kernel<uint8_t><<<(unsigned)n, 128, 0, ctx->stream>>>((const uint8_t*)refPix, (uint8_t*)scr, N, n);
-            ctx->launches++;
-            a.filt = (const uint8_t*)scr;
-        }
-        const int64_t threads = n * (all35 ? 35 : 33) * ((N * N) >> 4);
-        if ((threads + 127) / 128 < 0x7fffffffLL)
-        {
-            intra_modes8_cell_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(a);
-            ctx->launches++;
-            return check(cudaGetLastError(), "intra cell kernel launch");
-        }
-    }
     if ((uintptr_t)dest & (depth > 8 ? 7 : 3)) { set_error("intra_allangs: dest must be %d-byte aligned (4 pixels per store)", depth > 8 ? 8 : 4); return -1; }
     if (depth > 8) intra_allangs_kernel<uint16_t><<<(unsigned)n, 256, 0, ctx->stream>>>((const uint16_t*)refPix, (const uint16_t*)filtPix, (uint16_t*)dest, log2N, bLuma, depth, n, 0, all35);
     else if (((uintptr_t)dest & 15) == 0)

@@ -12,7 +12,7 @@
 // one-warp-per-CU kernel in lookahead_kernels.cu tops out at 0.85 ms per 32 640-CU field; profiles/r01_lookahead.txt).
 #define ME_FORCE_THREAD 1
 #define ME_LOWRES_ONLY 1
-#ifdef LA_PACKED_SATD                 /* staged, not yet measured: packed-word 4x4 SATD (satd_packed.cuh) in the lowres search */
+#ifndef LA_PACKED_SATD_OFF            /* packed-word 4x4 SATD (satd_packed.cuh) in the lowres search: -2 % (profiles/r02_staged_ab.txt) */
 #define ME_PACKED_SATD 1
 #endif
 #include "me_device.cuh"

@@ -24,8 +24,15 @@
 // keeps its register allocation independent of code it never executes.
 #ifdef ME_FORCE_THREAD
 #define ME_IS_THREAD(s) true
+#ifdef ME_LANE_W_VAR
+#define ME_PU_W(s) ((s).w)                /* a lane searches a 4- or 8-pixel-wide sub-block (rect / AMP PUs, me_ctu_kernels.cu) */
+#else
 #define ME_PU_W(s) 8                      /* every lane searches an 8-pixel-wide sub-block */
-#if defined(ME_LOWRES_ONLY)
+#endif
+#if defined(ME_CTU_KERNEL)
+#define ME_VARIANT me_thread_ctu
+#define ME_IS_LOWRES(s) false
+#elif defined(ME_LOWRES_ONLY)
 #define ME_VARIANT me_thread_lowres
 #define ME_IS_LOWRES(s) true
 #elif defined(ME_FULLRES_ONLY)
@@ -101,7 +108,27 @@ struct MEState
     // reference plane) and the PU's element offset in them (search.cpp:2264); warp-cooperative searches only
     const uint32_t* const* integral;
     int64_t  integralOff;
+#ifdef ME_WINDOW_CHECK
+    // Full-pel MVs (relative to the PU) for which the whole PU block lies inside the staged shared-memory window, inclusive;
+    // anything else is read from the global plane through gfref (predictors far from the CTU's window centre, the zero-MV
+    // candidate, overshoot of the pattern searches).  Sub-pel reads shrink the rectangle by the filter footprint.
+    int      winX0, winX1, winY0, winY1;
+#endif
+#ifdef ME_COST_SMEM
+    const uint16_t* costS;    // cost[-costK .. costK] staged in shared memory, centred like `cost`
+    int      costK;
+#endif
+#ifdef ME_THREAD_CHROMA
+    // per-thread chroma term: the lane's Cb / Cr sub-block in the staged chroma windows (frefC, strideC) and in the global
+    // planes (gfrefC, gstrideC); the window rectangle in whole chroma samples, inclusive, footprint of the 4-tap filter included
+    const pixel* gfrefC[2];
+    int64_t  gstrideC;
+    int      cwinX0, cwinX1, cwinY0, cwinY1;
+#endif
 };
+
+// The cached source PU (fenc) lives in shared memory in every kernel that uses this header: say so at the load sites.
+template<typename T> __device__ __forceinline__ const T* smem_hint(const T* p) { __builtin_assume(__isShared(p)); return p; }
 
 constexpr int kMvTableHalf = 2 * 32768;
 
@@ -110,11 +137,18 @@ __device__ __forceinline__ int mvcost(const MEState<pixel>& s, int qx, int qy)
 {
     int ix = clip3i(-kMvTableHalf, kMvTableHalf, qx - s.mvpx);
     int iy = clip3i(-kMvTableHalf, kMvTableHalf, qy - s.mvpy);
+#ifdef ME_COST_SMEM
+    // the differences a search produces stay within a few multiples of merange: those entries sit in shared memory
+    // (one LDS instead of an L2 round trip on the critical path of every candidate); the rest comes from the full table
+    const int K = s.costK;
+    const int cx = (ix >= -K && ix <= K) ? (int)smem_hint(s.costS)[ix] : (int)s.cost[ix];
+    const int cy = (iy >= -K && iy <= K) ? (int)smem_hint(s.costS)[iy] : (int)s.cost[iy];
+    return (cx + cy) & 0xffff;
+#else
     return ((int)s.cost[ix] + (int)s.cost[iy]) & 0xffff;      // bitcost.h:45 returns uint16_t
+#endif
 }
 
-// The cached source PU (fenc) lives in shared memory in every kernel that uses this header: say so at the load sites.
-template<typename T> __device__ __forceinline__ const T* smem_hint(const T* p) { __builtin_assume(__isShared(p)); return p; }
 
 // ---- row loaders ---------------------------------------------------------------------------------
 // NW consecutive 32-bit words of pixels starting at ANY pixel address (generic pointer: global plane or
@@ -268,6 +302,7 @@ __device__ __forceinline__ int thread_sad_one(const MEState<pixel>& s, const pix
 }
 // 8-pixel-wide sub-block (the me_frame layout): 8 rows at a time with every load issued before the first use, so one
 // candidate costs one load latency per 8 rows instead of one per row; fenc rows are 8-pixel aligned (one vector load).
+// Heights that are not a multiple of 8 (12- and 24-row AMP pieces, 4-row tails) finish with a batch of 4 rows.
 template<typename pixel>
 __device__ __forceinline__ int thread_sad_w8(const MEState<pixel>& s, const pixel* r, int64_t rs)
 {
@@ -278,8 +313,9 @@ __device__ __forceinline__ int thread_sad_w8(const MEState<pixel>& s, const pixe
     const SRow base = srow(r);
     const uint32_t rsB = (uint32_t)rs * (uint32_t)sizeof(pixel);
 #endif
+    int y0 = 0;
 #pragma unroll 1
-    for (int y0 = 0; y0 < s.h; y0 += 8)
+    for (; y0 + 8 <= s.h; y0 += 8)
     {
         uint32_t rw[8][NW];
         fvec f[8];
@@ -301,33 +337,80 @@ __device__ __forceinline__ int thread_sad_w8(const MEState<pixel>& s, const pixe
             for (int i = 0; i < NW; i++) acc += sad_word<pixel>(fw[i], rw[y][i]);
         }
     }
+#ifdef ME_LANE_W_VAR
+    if (y0 < s.h)
+    {
+        uint32_t rw[4][NW];
+        fvec f[4];
+#pragma unroll
+        for (int y = 0; y < 4; y++)
+        {
+#ifdef ME_SMEM_FAST
+            lds_words<NW>(base.a + (uint32_t)(y0 + y) * rsB, base.sh, rw[y]);
+#else
+            ld_words<pixel, NW>(r + (int64_t)(y0 + y) * rs, rw[y]);
+#endif
+            f[y] = *smem_hint((const fvec*)(s.fenc + (y0 + y) * 64));
+        }
+#pragma unroll
+        for (int y = 0; y < 4; y++)
+        {
+            const uint32_t* fw = (const uint32_t*)&f[y];
+#pragma unroll
+            for (int i = 0; i < NW; i++) acc += sad_word<pixel>(fw[i], rw[y][i]);
+        }
+    }
+#endif
     return (int)acc;
 }
-// per-thread SAD of the 8-wide sub-block against a block in ANY address space (row by row; rare path)
+// per-thread SAD of the sub-block against a block in ANY address space (row by row; rare path: the zero-MV candidate of
+// the frame search, and every block outside the staged window when ME_WINDOW_CHECK is on)
 template<typename pixel>
 __device__ __noinline__ int thread_sad_anyspace(const MEState<pixel>& s, const pixel* r, int64_t rs)
 {
-    constexpr int NW = 8 * (int)sizeof(pixel) / 4;
+    constexpr int NW = 4 * (int)sizeof(pixel) / 4;
     uint32_t acc = 0;
 #pragma unroll 1
     for (int y = 0; y < s.h; y++)
-    {
-        uint32_t rw[NW];
-        ld_words<pixel, NW, true>(r + (int64_t)y * rs, rw);
-        const uint32_t* fw = smem_hint((const uint32_t*)(s.fenc + y * 64));
+#pragma unroll 1
+        for (int x = 0; x < ME_PU_W(s); x += 4)
+        {
+            uint32_t rw[NW];
+            ld_words<pixel, NW, true>(r + (int64_t)y * rs + x, rw);
+            const uint32_t* fw = smem_hint((const uint32_t*)(s.fenc + y * 64 + x));
 #pragma unroll
-        for (int i = 0; i < NW; i++) acc += sad_word<pixel>(fw[i], rw[i]);
-    }
+            for (int i = 0; i < NW; i++) acc += sad_word<pixel>(fw[i], rw[i]);
+        }
     return (int)acc;
 }
 template<typename pixel>
 __device__ __forceinline__ int thread_sad_any(const MEState<pixel>& s, const pixel* r, int64_t rs)
 {
+#ifdef ME_LANE_W_VAR
+    if (ME_PU_W(s) == 8) return thread_sad_w8<pixel>(s, r, rs);
+    return thread_sad_one<pixel, 4>(s, r, rs);
+#else
     if (ME_PU_W(s) == 8 && !(s.h & 7)) return thread_sad_w8<pixel>(s, r, rs);
     if (!(ME_PU_W(s) & 15)) return thread_sad_one<pixel, 16>(s, r, rs);
     if (!(ME_PU_W(s) & 7))  return thread_sad_one<pixel, 8>(s, r, rs);
     return thread_sad_one<pixel, 4>(s, r, rs);
+#endif
 }
+#ifdef ME_WINDOW_CHECK
+// is the PU block at full-pel MV (mx, my), grown by `lt` pixels left / above and `rb` right / below, inside the staged window?
+template<typename pixel>
+__device__ __forceinline__ bool in_window(const MEState<pixel>& s, int mx, int my, int lt, int rb)
+{
+    return (mx >= s.winX0 + lt) & (mx <= s.winX1 - rb) & (my >= s.winY0 + lt) & (my <= s.winY1 - rb);
+}
+// one full-pel candidate of the lane's sub-block: from the window when the whole PU block is inside it, else from the plane
+template<typename pixel>
+__device__ __noinline__ int thread_sad_cand(const MEState<pixel>& s, int mx, int my)
+{
+    if (in_window(s, mx, my, 0, 0)) return thread_sad_any<pixel>(s, s.fref + mx + (int64_t)my * s.stride, s.stride);
+    return thread_sad_anyspace<pixel>(s, s.gfref + mx + (int64_t)my * s.gstride, s.gstride);
+}
+#endif
 // 4x4 Hadamard cost of d[i][k] = a - b rows already differenced: sum |H d H^T| >> 1
 __device__ __forceinline__ int satd_cell(int d[4][4])
 {
@@ -388,7 +471,7 @@ __device__ __forceinline__ int thread_satd(const MEState<pixel>& s, const pixel*
     return acc;
 #else
 #ifdef ME_PACKED_SATD
-    // STAGED for the lookahead kernel (off by default, not yet measured): the packed-word SATD on rows from any address space
+    // the lookahead kernel: the packed-word SATD on rows from any address space (-2 % per launch, profiles/r02_staged_ab.txt)
     if constexpr (sizeof(pixel) == 1)
     {
 #pragma unroll 1
@@ -433,6 +516,27 @@ __device__ __forceinline__ int thread_satd(const MEState<pixel>& s, const pixel*
 #endif
 }
 
+#ifdef ME_WINDOW_CHECK
+// Frame-search form (me_ctu_kernels.cu): inlined into its callers so that the K candidate offsets stay in registers (as a
+// __noinline__ function taking ox[] / oy[] the arrays lived in local memory and every candidate began with two dependent
+// LDL -- 7 % of the stall samples of profiles/r02_me_frame_v11.txt); the per-candidate work is the call to thread_sad_cand.
+// The K partial SADs are then reduced over the PU's lanes together (K independent shuffles per butterfly round).
+template<typename pixel>
+__device__ __forceinline__ void warp_sad_k(const MEState<pixel>& s, int K, const int ox[4], const int oy[4], int costs[4])
+{
+    int part[4] = { 0, 0, 0, 0 };
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        if (k < K) part[k] = thread_sad_cand<pixel>(s, ox[k], oy[k]);
+    for (int o = 1; o < s.groupSize; o <<= 1)
+    {
+#pragma unroll
+        for (int k = 0; k < 4; k++) part[k] += __shfl_xor_sync(s.groupMask, part[k], o);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) if (k < K) costs[k] = part[k];
+}
+#else
 template<typename pixel>
 __device__ __noinline__ void warp_sad_k(const MEState<pixel>& s, int K, const int ox[4], const int oy[4], int costs[4])
 {
@@ -469,6 +573,7 @@ __device__ __noinline__ void warp_sad_k(const MEState<pixel>& s, int K, const in
     else                 sad_k_impl<pixel, 4>(s, K, ox, oy, costs);
 #endif
 }
+#endif
 
 // SAD of the cached PU against an arbitrary block (global or shared) with row stride rs
 template<typename pixel>
@@ -869,7 +974,7 @@ __device__ __noinline__ int thread_subpel_cost(const MEState<pixel>& s, const pi
             for (int t = 0; t < 8; t++) cvt[t] = c_meLumaFilter[yFrac][t];
             const uint32_t cvlo = sp_taps(cvt, 0), cvhi = sp_taps(cvt, 4);
 #ifdef ME_VCELL_REUSE
-            // STAGED (off by default, not yet measured): vertically adjacent cells share two of their three transposed 4-row blocks;
+            // vertically adjacent cells share two of their three transposed 4-row blocks (+2.4 % on the frame search, profiles/r02_staged_ab.txt);
             // per cell only rows y0+5..y0+8 are loaded and transposed (the window keeps spare rows below the 8-tap footprint)
 #pragma unroll 1
             for (int x = 0; x < W; x += 4)
@@ -1202,68 +1307,198 @@ __device__ __noinline__ int warp_chroma_cost(const MEState<pixel>& s, int qx, in
 }
 #endif
 
-#if defined(ME_SMEM_FAST) && defined(ME_SUBPEL_PACKED) && defined(ME_HPEL_PAIRS)
-#define ME_HAS_HPEL_PAIRS 1
-// STAGED (off by default, not yet measured; results checked on the host, tests/test_me_host_emu_cpu.py): the two half-pel
-// candidates either side of the FULL-PEL block at `src` in one filter pass -- (0,-2)/(0,+2) are the same vertical half-pel
-// plane one row apart (vert), (-2,0)/(+2,0) the same horizontal one a column apart.  8-bit only (subpel_packed.cuh).
-template<typename pixel>
-__device__ __noinline__ void thread_hpel_pair_cost(const MEState<pixel>& s, const pixel* src, bool vert, bool useSatd, int& costA, int& costB)
+#ifdef ME_WINDOW_CHECK
+// ---- blocks outside the staged window: the same arithmetic from the global plane (generic pointers, compact loops) -------
+// N consecutive pixels from any address in any space as ints
+template<typename pixel, int N>
+__device__ __forceinline__ void ld_px_run(const pixel* p, int v[N])
 {
-    int accA = 0, accB = 0;
-    if constexpr (sizeof(pixel) == 1)
-    {
-        const int W = ME_PU_W(s), H = s.h;
-        int16_t cf[8];
+    constexpr int PW = 4 / (int)sizeof(pixel), NW = (N + PW - 1) / PW;
+    uint32_t w[NW];
+    ld_words<pixel, NW, true>(p, w);
 #pragma unroll
-        for (int t = 0; t < 8; t++) cf[t] = c_meLumaFilter[2][t];
-        const uint32_t clo = sp_taps(cf, 0), chi = sp_taps(cf, 4);
-        const uint32_t rsB = (uint32_t)s.stride;
-        if (vert)
+    for (int i = 0; i < N; i++)
+        v[i] = sizeof(pixel) == 1 ? (int)((w[i / PW] >> (8 * (i % PW))) & 0xff) : (int)((w[i / PW] >> (16 * (i % PW))) & 0xffff);
+}
+template<typename pixel>
+__device__ __noinline__ int thread_satd_gen(const MEState<pixel>& s, const pixel* r, int64_t rs)
+{
+    int acc = 0;
+#pragma unroll 1
+    for (int cy = 0; cy < s.h; cy += 4)
+#pragma unroll 1
+        for (int cx = 0; cx < ME_PU_W(s); cx += 4)
         {
-            const SRow b0 = srow(src);
-#pragma unroll 1
-            for (int x = 0; x < W; x += 4)
-#pragma unroll 1
-                for (int y0 = 0; y0 < H; y0 += 4)
-                {
-                    uint32_t r[12], P[5];
+            int o[4][4];
 #pragma unroll
-                    for (int j = 0; j < 12; j++) lds_words<1>(b0.a + (uint32_t)(y0 - 4 + j) * rsB + (uint32_t)x, b0.sh, &r[j]);
-                    vpp_cell_pair_u8(r, clo, chi, P);
-                    CellRows<pixel> ra, rb;
-#pragma unroll
-                    for (int j = 0; j < 4; j++) { ra.w[j] = P[j]; rb.w[j] = P[j + 1]; }
-                    accA += cell_cost_packed<pixel>(s.fenc + y0 * 64 + x, ra, useSatd);
-                    accB += cell_cost_packed<pixel>(s.fenc + y0 * 64 + x, rb, useSatd);
-                }
+            for (int i = 0; i < 4; i++) ld_px_run<pixel, 4>(r + (int64_t)(cy + i) * rs + cx, o[i]);
+            acc += cell_cost<pixel>(s.fenc + cy * 64 + cx, o, true);
         }
-        else
-        {
-            const SRow b4 = srow(src - 4);
-#pragma unroll 1
-            for (int y0 = 0; y0 < H; y0 += 4)
-#pragma unroll 1
-                for (int x = 0; x < W; x += 4)
-                {
-                    CellRows<pixel> ra, rb;
+    return acc;
+}
+// luma_hpp / luma_vpp / luma_hvpp (ipfilter.cpp:79-118,164-203,362-369) of the lane's sub-block, 4x4 cell by cell
+template<typename pixel>
+__device__ __noinline__ int thread_subpel_cost_gen(const MEState<pixel>& s, const pixel* src, int64_t rs, int xFrac, int yFrac, bool useSatd)
+{
+    const int maxVal = (1 << s.depth) - 1, headRoom = 14 - s.depth;
+    int ch[8], cv[8];
 #pragma unroll
-                    for (int j = 0; j < 4; j++) { ra.w[j] = 0; rb.w[j] = 0; }
+    for (int t = 0; t < 8; t++) { ch[t] = c_meLumaFilter[xFrac][t]; cv[t] = c_meLumaFilter[yFrac][t]; }
+    const int sh1 = 6 - headRoom, off1 = (int)((unsigned)-8192 << sh1);
+    const int sh2 = xFrac ? 6 + headRoom : 6, off2 = xFrac ? (1 << (sh2 - 1)) + (8192 << 6) : 32;
+    int acc = 0;
 #pragma unroll 1
-                    for (int r = 0; r < 4; r++)
+    for (int cy = 0; cy < s.h; cy += 4)
+#pragma unroll 1
+        for (int cx = 0; cx < ME_PU_W(s); cx += 4)
+        {
+            int o[4][4];
+            if (!yFrac)
+            {
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                {
+                    int v[11];
+                    ld_px_run<pixel, 11>(src + (int64_t)(cy + i) * rs + cx - 3, v);
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
                     {
-                        uint32_t w[3];
-                        lds_words<3>(b4.a + (uint32_t)(y0 + r) * rsB + (uint32_t)x, b4.sh, w);
+                        int sum = 0;
 #pragma unroll
-                        for (int j = 0; j < 3; j++) { ra.w[j] = ra.w[j + 1]; rb.w[j] = rb.w[j + 1]; }
-                        hpp_row_pair_u8(w, clo, chi, ra.w[3], rb.w[3]);
+                        for (int t = 0; t < 8; t++) sum += v[k + t] * ch[t];
+                        const int val = (int16_t)((sum + 32) >> 6);
+                        o[i][k] = val < 0 ? 0 : (val > maxVal ? maxVal : val);
                     }
-                    accA += cell_cost_packed<pixel>(s.fenc + y0 * 64 + x, ra, useSatd);
-                    accB += cell_cost_packed<pixel>(s.fenc + y0 * 64 + x, rb, useSatd);
                 }
+            }
+            else
+            {
+                int win[11][4];
+#pragma unroll
+                for (int r = 0; r < 11; r++)
+                {
+                    int q[4];
+                    if (xFrac)
+                    {
+                        int v[11];
+                        ld_px_run<pixel, 11>(src + (int64_t)(cy + r - 3) * rs + cx - 3, v);
+#pragma unroll
+                        for (int k = 0; k < 4; k++)
+                        {
+                            int sum = 0;
+#pragma unroll
+                            for (int t = 0; t < 8; t++) sum += v[k + t] * ch[t];
+                            q[k] = (int16_t)((sum + off1) >> sh1);
+                        }
+                    }
+                    else
+                        ld_px_run<pixel, 4>(src + (int64_t)(cy + r - 3) * rs + cx, q);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) win[r][k] = q[k];
+                }
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                    {
+                        int sum = 0;
+#pragma unroll
+                        for (int t = 0; t < 8; t++) sum += win[i + t][k] * cv[t];
+                        const int val = (int16_t)((sum + off2) >> sh2);
+                        o[i][k] = val < 0 ? 0 : (val > maxVal ? maxVal : val);
+                    }
+            }
+            acc += cell_cost<pixel>(s.fenc + cy * 64 + cx, o, useSatd);
         }
+    return acc;
+}
+#endif
+
+#ifdef ME_THREAD_CHROMA
+// ---- chroma term of subpelCompare (motion.cpp:1601-1661), per-thread form ---------------------------------------------------
+// The lane's Cb / Cr sub-blocks (its luma sub-block >> the chroma shifts; the host splits PUs so that they are multiples of
+// 4x4) are predicted 4x4 cell by cell with the 4-tap filters (chroma[csp].pu[].filter_hpp / filter_vpp / filter_hps(isRowExt)
+// + filter_vsp, ipfilter.cpp:79-162,164-203,241-282 with N = 4) and costed with the SATD on the spot.  The source CTU's Cb /
+// Cr live in shared memory at a row pitch of 64 like the luma, the reference samples come from the staged chroma windows
+// or, outside them, from the global planes.
+__constant__ int16_t c_meChromaFilterT[8][4] = {
+    { 0, 64, 0, 0 }, { -2, 58, 10, -2 }, { -4, 54, 16, -2 }, { -6, 46, 28, -4 },
+    { -4, 36, 36, -4 }, { -4, 28, 46, -6 }, { -2, 16, 54, -4 }, { -2, 10, 58, -2 } };   // == g_chromaFilter, constants.cpp:258-268
+template<typename pixel>
+__device__ __noinline__ int thread_chroma_cost(const MEState<pixel>& s, int qx, int qy)
+{
+    const int mvx = qx << (1 - s.hshift), mvy = qy << (1 - s.vshift);
+    const int ix = mvx >> 3, iy = mvy >> 3, xFrac = mvx & 7, yFrac = mvy & 7;
+    const int wC = ME_PU_W(s) >> s.hshift, hC = s.h >> s.vshift;
+    const int maxVal = (1 << s.depth) - 1, headRoom = 14 - s.depth;
+    const bool inw = (ix >= s.cwinX0) & (ix <= s.cwinX1) & (iy >= s.cwinY0) & (iy <= s.cwinY1);
+    const int64_t rs = inw ? s.strideC : s.gstrideC;
+    int ch[4], cv[4];
+#pragma unroll
+    for (int t = 0; t < 4; t++) { ch[t] = c_meChromaFilterT[xFrac][t]; cv[t] = c_meChromaFilterT[yFrac][t]; }
+    const int sh1 = 6 - headRoom, off1 = (int)((unsigned)-8192 << sh1);
+    const int sh2 = xFrac ? 6 + headRoom : 6, off2 = xFrac ? (1 << (sh2 - 1)) + (8192 << 6) : 32;
+    int acc = 0;
+#pragma unroll 1
+    for (int c = 0; c < 2; c++)
+    {
+        const pixel* src = (inw ? s.frefC[c] : s.gfrefC[c]) + ix + (int64_t)iy * rs;
+#pragma unroll 1
+        for (int cy = 0; cy < hC; cy += 4)
+#pragma unroll 1
+            for (int cx = 0; cx < wC; cx += 4)
+            {
+                int o[4][4];
+                if (!(xFrac | yFrac))
+                {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) ld_px_run<pixel, 4>(src + (int64_t)(cy + i) * rs + cx, o[i]);
+                }
+                else if (!yFrac)
+                {
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+                    {
+                        int v[7];
+                        ld_px_run<pixel, 7>(src + (int64_t)(cy + i) * rs + cx - 1, v);
+#pragma unroll
+                        for (int k = 0; k < 4; k++)
+                        {
+                            const int val = (int16_t)((v[k] * ch[0] + v[k + 1] * ch[1] + v[k + 2] * ch[2] + v[k + 3] * ch[3] + 32) >> 6);
+                            o[i][k] = val < 0 ? 0 : (val > maxVal ? maxVal : val);
+                        }
+                    }
+                }
+                else
+                {
+                    int win[7][4];
+#pragma unroll
+                    for (int r = 0; r < 7; r++)
+                    {
+                        if (xFrac)
+                        {
+                            int v[7];
+                            ld_px_run<pixel, 7>(src + (int64_t)(cy + r - 1) * rs + cx - 1, v);
+#pragma unroll
+                            for (int k = 0; k < 4; k++)
+                                win[r][k] = (int16_t)((v[k] * ch[0] + v[k + 1] * ch[1] + v[k + 2] * ch[2] + v[k + 3] * ch[3] + off1) >> sh1);
+                        }
+                        else
+                            ld_px_run<pixel, 4>(src + (int64_t)(cy + r - 1) * rs + cx, win[r]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+#pragma unroll
+                        for (int k = 0; k < 4; k++)
+                        {
+                            const int val = (int16_t)((win[i][k] * cv[0] + win[i + 1][k] * cv[1] + win[i + 2][k] * cv[2] + win[i + 3][k] * cv[3] + off2) >> sh2);
+                            o[i][k] = val < 0 ? 0 : (val > maxVal ? maxVal : val);
+                        }
+                }
+                acc += cell_cost<pixel>(s.fencC[c] + cy * 64 + cx, o, true);
+            }
     }
-    costA = accA; costB = accB;
+    return acc;
 }
 #endif
 
@@ -1275,9 +1510,30 @@ __device__ __noinline__ int subpel_compare(const MEState<pixel>& s, int qx, int 
     const int xFrac = qx & 3, yFrac = qy & 3;
     if (ME_IS_THREAD(s))
     {
+#ifdef ME_WINDOW_CHECK
+        // lane partials first (luma from the window or, outside it, from the plane; then the chroma term), ONE reduction
+        int c;
+        const int mx = qx >> 2, my = qy >> 2;
+        if (in_window(s, mx, my, 4, 5))
+        {
+            if (!(xFrac | yFrac)) c = useSatd ? thread_satd<pixel>(s, fref, s.stride) : thread_sad_any<pixel>(s, fref, s.stride);
+            else c = thread_subpel_cost<pixel>(s, fref, xFrac, yFrac, useSatd);
+        }
+        else
+        {
+            const pixel* g = s.gfref + mx + (int64_t)my * s.gstride;
+            if (!(xFrac | yFrac)) c = useSatd ? thread_satd_gen<pixel>(s, g, s.gstride) : thread_sad_anyspace<pixel>(s, g, s.gstride);
+            else c = thread_subpel_cost_gen<pixel>(s, g, s.gstride, xFrac, yFrac, useSatd);
+        }
+#ifdef ME_THREAD_CHROMA
+        if (s.chromaSatd) c += thread_chroma_cost<pixel>(s, qx, qy);      // motion.cpp:1601
+#endif
+        return group_sum<pixel>(s, c);
+#else
         if (!(xFrac | yFrac))
             return useSatd ? warp_satd<pixel>(s, fref, s.stride) : warp_sad_block<pixel>(s, fref, s.stride);
         return group_sum<pixel>(s, thread_subpel_cost<pixel>(s, fref, xFrac, yFrac, useSatd));
+#endif
     }
 #ifndef ME_FORCE_THREAD
     int c;
@@ -1811,7 +2067,9 @@ __device__ int motion_estimate(const MEState<pixel>& s, MV2 mvmin, MV2 mvmax, MV
     // measure SAD cost at MV(0) if MVP is not zero (:786-796)
     if ((pmv.x | pmv.y) && !refineOnly)
     {
-#ifdef ME_REF_IN_SMEM
+#if defined(ME_WINDOW_CHECK)
+        int cost = S.sadAt(0, 0) + mvcost(s, 0, 0);            // the window test of every candidate covers it
+#elif defined(ME_REF_IN_SMEM)
         // the zero-MV block may lie outside the staged window: read it from the global plane
         int cost = group_sum<pixel>(s, thread_sad_anyspace<pixel>(s, s.gfref, s.gstride)) + mvcost(s, 0, 0);
 #else
@@ -2081,30 +2339,6 @@ __device__ int motion_estimate(const MEState<pixel>& s, MV2 mvmin, MV2 mvmax, MV
             int bdir = 0;
             for (int i = 1; i <= wl.hpel_dirs; i++)
             {
-#ifdef ME_HAS_HPEL_PAIRS
-                // directions (1,2) and (3,4) around a full-pel vector are one filter pass each (thread_hpel_pair_cost); the
-                // two costs are compared in the reference's order
-                if (sizeof(pixel) == 1 && (i == 1 || i == 3) && !((bmv.x | bmv.y) & 3))
-                {
-                    const int ax = bmv.x + c_square1[i][0] * 2, ay = bmv.y + c_square1[i][1] * 2;
-                    const int bx = bmv.x + c_square1[i + 1][0] * 2, by = bmv.y + c_square1[i + 1][1] * 2;
-                    if ((ay >= qmvmin.y) & (ay <= qmvmax.y) & (by >= qmvmin.y) & (by <= qmvmax.y))
-                    {
-                        int ca, cb;
-                        thread_hpel_pair_cost<pixel>(s, s.fref + (bmv.x >> 2) + (int64_t)(bmv.y >> 2) * s.stride, i == 1, hpelSatd, ca, cb);
-                        for (int o = 1; o < s.groupSize; o <<= 1)
-                        {
-                            ca += __shfl_xor_sync(s.groupMask, ca, o);
-                            cb += __shfl_xor_sync(s.groupMask, cb, o);
-                        }
-                        ca += mvcost(s, ax, ay); cb += mvcost(s, bx, by);
-                        if (ca < bcost) { bcost = ca; bdir = i; }
-                        if (cb < bcost) { bcost = cb; bdir = i + 1; }
-                        i++;
-                        continue;
-                    }
-                }
-#endif
                 int qx = bmv.x + c_square1[i][0] * 2, qy = bmv.y + c_square1[i][1] * 2;
                 if ((qy < qmvmin.y) | (qy > qmvmax.y)) continue;
                 int cost = subpel_compare<pixel>(s, qx, qy, hpelSatd) + mvcost(s, qx, qy);

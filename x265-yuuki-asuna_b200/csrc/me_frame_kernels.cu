@@ -27,6 +27,9 @@
 #ifndef ME_BATCH_GROUPSUM_OFF
 #define ME_BATCH_GROUPSUM 1       /* the K partial SADs of a sad_x3/x4 step reduced over the PU's lanes together                   */
 #endif
+#ifndef ME_VCELL_REUSE_OFF
+#define ME_VCELL_REUSE 1          /* vertical cells share their transposed row blocks (+2.4 %, profiles/r02_staged_ab.txt)         */
+#endif
 #include "me_device.cuh"
 #include "x265b200.h"
 #include <cuda.h>

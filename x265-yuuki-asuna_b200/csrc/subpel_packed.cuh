@@ -96,62 +96,6 @@ SP_FN void vpp_cell_u8(const uint32_t r[11], uint32_t cvlo, uint32_t cvhi, uint3
     }
 }
 
-// ---- candidate PAIRS of the half-pel step around a full-pel vector ------------------------------------------------
-// (0,-2)/(0,+2) are the same vertical half-pel plane one row apart, (-2,0)/(+2,0) the same horizontal one a column
-// apart: a pair costs one filter pass over a block that is one row (column) larger.
-
-// r[j], j = 0..11: the 4 pixels of source rows (y0 - 4 + j); out[m], m = 0..4: predicted picture rows y0 - 1 + m.
-// Candidate A (row offset -1) uses out[0..3] against fenc rows y0..y0+3, candidate B out[1..4].
-SP_FN void vpp_cell_pair_u8(const uint32_t r[12], uint32_t cvlo, uint32_t cvhi, uint32_t out[5])
-{
-    uint32_t c[3][4];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int b = 0; b < 3; b++)
-    {
-        const uint32_t t0 = sp_prmt(r[4 * b], r[4 * b + 1], 0x5140), t1 = sp_prmt(r[4 * b + 2], r[4 * b + 3], 0x5140);
-        const uint32_t t2 = sp_prmt(r[4 * b], r[4 * b + 1], 0x7362), t3 = sp_prmt(r[4 * b + 2], r[4 * b + 3], 0x7362);
-        c[b][0] = sp_prmt(t0, t1, 0x5410); c[b][1] = sp_prmt(t0, t1, 0x7632);
-        c[b][2] = sp_prmt(t2, t3, 0x5410); c[b][3] = sp_prmt(t2, t3, 0x7632);
-    }
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int m = 0; m < 5; m++)
-    {
-        int o[4];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-        for (int k = 0; k < 4; k++)
-        {
-            const uint32_t lo = m == 4 ? c[1][k] : sp_funnel_r(c[0][k], c[1][k], 8 * m);
-            const uint32_t hi = m == 4 ? c[2][k] : sp_funnel_r(c[1][k], c[2][k], 8 * m);
-            o[k] = sp_min_relu(sp_dp4a_us(hi, cvhi, sp_dp4a_us(lo, cvlo, 32)) >> 6, 255);
-        }
-        out[m] = sp_pack4(o[0], o[1], o[2], o[3]);
-    }
-}
-
-// w[0..2]: the 12 pixels of one row starting 4 left of the cell's first column; rowA = outputs at columns -1..2
-// (candidate A, column offset -1), rowB = outputs at columns 0..3 (candidate B)
-SP_FN void hpp_row_pair_u8(const uint32_t w[3], uint32_t clo, uint32_t chi, uint32_t& rowA, uint32_t& rowB)
-{
-    int o[5];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int m = 0; m < 5; m++)
-    {
-        const uint32_t lo = m == 4 ? w[1] : sp_funnel_r(w[0], w[1], 8 * m);
-        const uint32_t hi = m == 4 ? w[2] : sp_funnel_r(w[1], w[2], 8 * m);
-        o[m] = sp_min_relu(sp_dp4a_us(hi, chi, sp_dp4a_us(lo, clo, 32)) >> 6, 255);
-    }
-    rowA = sp_pack4(o[0], o[1], o[2], o[3]);
-    rowB = sp_pack4(o[1], o[2], o[3], o[4]);
-}
-
 // ---- two-pass case (luma_hvpp = hps with row extension + vsp, ipfilter.cpp:362-369), 8-bit ------------------------------
 // w[j][0..2], j = 0..10: the 12 pixels of source row (y0 - 3 + j) starting 3 left of the cell; clo / chi: horizontal taps;
 // cv: vertical taps.  First stage at 8 bits: shift 0, offset -8192 (rides in the accumulator); it lies in [-14312, 14248].
