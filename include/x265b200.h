@@ -373,8 +373,54 @@ int x265b200_me_frame_dev(x265b200_ctx* ctx, int depth, const void* curOrigin, i
                           const void* const* refOriginsHost, int numRefs, int64_t refStride,
                           int marginX, int marginY, int rowsTotal, int ctuCols, int ctuRows, int puMask,
                           const int32_t* mvpCtu, int searchMethod, int subpelRefine, int merange, double lambda, int32_t* out);
-/* profiling aid: cumulative busy cycles of the 8 warp roles of me_frame CTAs (out9[8] = number of CTAs) */
-int x265b200_debug_me_frame_cycles(x265b200_ctx* ctx, uint64_t* out9);
+/* General frame form: what Search::predInterSearch asks of MotionEstimate for every PU of every CTU of a frame
+ * (search.cpp:2181-2436 -> setSearchRange :2724-2769 -> motionEstimate motion.cpp:739-1569 with the encode-style setSourcePU
+ * :193-222), for the partition sets, CTU sizes, bit depths and ranges of all presets (param.cpp:396-555):
+ *   ctuSize 64 / 32 / 16 with CUs down to minCuSize; 2Nx2N always, 2NxN / Nx2N with `rect`, the four AMP modes with `amp`
+ *   (CUs >= 16); per-PU predictor mvp and up to maxCand MV candidates mvc[] (AMVP / neighbour / lowres MVs: produced by the
+ *   caller's analysis, they are inputs here); csp != 0 with subpelRefine > 2 adds the Cb / Cr SATD to every subpelCompare
+ *   (bChromaSATD, motion.cpp:212,1601-1661) for the shapes whose chroma block is a multiple of 4x4; DIA/HEX/UMH/STAR/FULL.
+ * The search range of a PU is computed as the reference does: mvp +- merange, CUData::clipMv against the picture
+ * (picWidth x picHeight; 0 = ctuCols*ctuSize x (firstCtuRow+ctuRows)*ctuSize) with the PU's CU position, slice rows when
+ * maxSlices > 1 and frameParallel (the band semantics of --slices), refLagPixels (0 = no clamp), maxMvLen.
+ * A call may cover a BAND of CTU rows of a larger frame (CTU-row sharding): pass the plane origins advanced to the
+ * band's first CTU row (marginY grown by the same rows), firstCtuRow = that row inside the whole frame, picHeight = the whole
+ * frame's and sliceTotalRows = the whole frame's CTU rows; CU positions for clipMv and the slice rows are then the frame's.  PUs of CUs that leave the picture
+ * are not searched (cost -1).
+ * One CTA per (CTU, reference) stages the search window around the CTU's window centre mvpCtu[ref][ctu] (quarter-pel, NULL =
+ * 0; also the predictor when mvpPu is NULL) with TMA; blocks outside the window are read from the plane, so the results do
+ * not depend on the centre.  Planes are given by their ORIGIN (pixel 0,0) with marginX / marginY pixels of padding around
+ * the picture and rowsTotal rows allocated (PicYuv layout; chroma margins and rows are the luma ones >> the chroma shifts).
+ * PU order inside a CTU: x265b200_me_frame_layout.  Arrays: mvpPu int32 [ref][ctu][pu][2], numCandPu uint8 [ref][ctu][pu],
+ * mvcPu int32 [ref][ctu][pu][maxCand][2], out int32 [ref][ctu][pu][3] = {mvx, mvy, cost} (all device memory). */
+typedef struct
+{
+    int32_t depth;                            /* 8, 10 or 12 */
+    int32_t ctuSize, minCuSize, rect, amp;
+    int32_t picWidth, picHeight;
+    int32_t ctuCols, ctuRows;
+    int32_t marginX, marginY, rowsTotal;
+    int32_t numRefs;
+    int32_t searchMethod, subpelRefine, merange;
+    int32_t csp;                              /* 0 = luma only, 1 = 4:2:0, 2 = 4:2:2, 3 = 4:4:4 (x265.h:588-592) */
+    int32_t maxCand;
+    int32_t maxSlices, frameParallel, firstCtuRow, sliceTotalRows;
+    int32_t refLagPixels;
+    double  lambda;
+} x265b200_me_frame_params;
+typedef struct
+{
+    const void* curY; const void* curCb; const void* curCr;      /* device plane origins of the source picture */
+    int64_t curStride, curStrideC;
+    const void* const* refY; const void* const* refCb; const void* const* refCr;   /* HOST arrays [numRefs] of device plane origins */
+    int64_t refStride, refStrideC;
+} x265b200_me_frame_planes;
+int x265b200_me_frame_ex_dev(x265b200_ctx* ctx, const x265b200_me_frame_params* params, const x265b200_me_frame_planes* planes,
+                             const int32_t* mvpCtu, const int32_t* mvpPu, const uint8_t* numCandPu, const int32_t* mvcPu, int32_t* out);
+/* The PUs of one CTU in the order x265b200_me_frame_ex_dev uses: {x, y, w, h} inside the CTU, CU sizes from ctuSize down to
+ * minCuSize, CUs in raster order, per CU the part modes in PartSize order (2Nx2N, 2NxN, Nx2N, 2NxnU, 2NxnD, nLx2N, nRx2N;
+ * common/cudata.h).  Writes at most cap entries; returns the number of PUs (host side, no GPU needed), -1 on bad arguments. */
+int x265b200_me_frame_layout(int ctuSize, int minCuSize, int rect, int amp, int32_t* outXYWH, int cap);
 /* The lambda-scaled MV cost table the kernels use (host side, no GPU needed):
  * out[2*32768 + i] = cost of a quarter-pel MV difference i, i in [-65536, 65536]. */
 int x265b200_bitcost_table(double lambda, uint16_t* out);

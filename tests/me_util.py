@@ -97,3 +97,93 @@ def ref_me_chroma(depth, csp, cur, ref, stride, origin, curC, refC, strideC, ori
                                int(csp), vp(rj), ctypes.c_int64(len(rj)), int(method), int(subme), int(merange), int(qp), int(maxSlices), int(threads))
     assert rc == 0
     return rj["outMvX"].copy(), rj["outMvY"].copy(), rj["outCost"].copy()
+
+
+# ---- the general frame search (x265b200_me_frame_ex_dev / csrc/me_ctu_kernels.cu) ------------------------------------------
+def ctu_layout(C, minCu, rect, amp):
+    """The PUs of one CTU in the order the C ABI documents (x265b200_me_frame_layout), with the CU that owns each:
+    rows of (x, y, w, h, cuX, cuY, cuSize)."""
+    out = []
+    S = C
+    while S >= minCu:
+        for cy in range(0, C, S):
+            for cx in range(0, C, S):
+                pus = [(0, 0, S, S)]
+                if rect:
+                    pus += [(0, 0, S, S // 2), (0, S // 2, S, S // 2), (0, 0, S // 2, S), (S // 2, 0, S // 2, S)]
+                if amp and S >= 16:
+                    q = S // 4
+                    pus += [(0, 0, S, q), (0, q, S, 3 * q), (0, 0, S, 3 * q), (0, 3 * q, S, q),
+                            (0, 0, q, S), (q, 0, 3 * q, S), (0, 0, 3 * q, S), (3 * q, 0, q, S)]
+                out += [(cx + x, cy + y, w, h, cx, cy, S) for (x, y, w, h) in pus]
+        S //= 2
+    return np.array(out, dtype=np.int32)
+
+
+def search_range(picW, picH, C, cuPelX, cuPelY, mvp, merange, slice_bounds=None, ref_lag=None):
+    """Search::setSearchRange (search.cpp:2724-2769) with CUData::clipMv (cudata.cpp:1915-1928); returns full-pel (mvmin, mvmax)."""
+    mn = [int(mvp[0]) - (merange << 2), int(mvp[1]) - (merange << 2)]
+    mx = [int(mvp[0]) + (merange << 2), int(mvp[1]) + (merange << 2)]
+    xmax, xmin = (picW + 8 - cuPelX - 1) << 2, -((C + 8 + cuPelX - 1) << 2)
+    ymax, ymin = (picH + 8 - cuPelY - 1) << 2, -((C + 8 + cuPelY - 1) << 2)
+    for v in (mn, mx):
+        v[0] = min(xmax, max(xmin, v[0])); v[1] = min(ymax, max(ymin, v[1]))
+    if slice_bounds is not None:
+        mn[1] = max(mn[1], int(slice_bounds[0])); mx[1] = min(mx[1], int(slice_bounds[1]))
+    L = (1 << 15) - 1
+    mn = [max(mn[0], -L) >> 2, max(mn[1], -L) >> 2]
+    mx = [min(mx[0], L) >> 2, min(mx[1], L) >> 2]
+    if ref_lag is not None:
+        mn[1] = min(mn[1], ref_lag); mx[1] = min(mx[1], ref_lag)
+    mx[1] = max(mx[1], mn[1])
+    return mn, mx
+
+
+def ctu_jobs(pkg, layout, C, ctuX, ctuY, picW, picH, mvp, merange, ncand=None, mvc=None, slice_bounds=None, ref_lag=None):
+    """ME_JOB records (for the reference's MotionEstimate) of the PUs of one CTU: mvp [nPU][2], optional candidates.
+    Returns (jobs, searched) -- searched[i] False for PUs of CUs that leave the picture."""
+    n = len(layout)
+    job = np.zeros(n, dtype=pkg.ME_JOB)
+    searched = np.ones(n, dtype=bool)
+    for i, (x, y, w, h, cuX, cuY, S) in enumerate(layout.tolist()):
+        cuPelX, cuPelY = ctuX * C + cuX, ctuY * C + cuY
+        if cuPelX + S > picW or cuPelY + S > picH:
+            searched[i] = False
+            continue
+        mn, mx = search_range(picW, picH, C, cuPelX, cuPelY, mvp[i], merange, slice_bounds, ref_lag)
+        job[i]["puX"], job[i]["puY"], job[i]["w"], job[i]["h"] = ctuX * C + x, ctuY * C + y, w, h
+        job[i]["mvminX"], job[i]["mvminY"], job[i]["mvmaxX"], job[i]["mvmaxY"] = mn[0], mn[1], mx[0], mx[1]
+        job[i]["mvpX"], job[i]["mvpY"] = int(mvp[i][0]), int(mvp[i][1])
+        if ncand is not None:
+            k = int(ncand[i])
+            job[i]["numCand"] = k
+            job[i]["mvc"][:k] = mvc[i][:k]
+    return job, searched
+
+
+def box_blur(a, k=5):
+    """separable k-tap box filter by cumulative sums (fast band-limiting for full-size frames)"""
+    for ax in (0, 1):
+        c = np.cumsum(a, axis=ax, dtype=np.float64)
+        pad = [(0, 0), (0, 0)]; pad[ax] = (k, 0)
+        c = np.pad(c, pad)
+        n = a.shape[ax]
+        a = (np.take(c, np.arange(k, n + k), axis=ax) - np.take(c, np.arange(0, n), axis=ax)) / k
+    return a
+
+
+def synth_sequence(W, H, padX, padY, depth, nframes, seed, max_motion=12, noise=2.5):
+    """nframes padded planes (stride W + 2*padX, H + 2*padY rows): band-limited noise under per-frame global motion + noise.
+    Returns (list of flat arrays, stride, rows, origin offset in elements)."""
+    rng = np.random.default_rng(seed)
+    S, R = W + 2 * padX, H + 2 * padY
+    m = max_motion + 8
+    big = box_blur(rng.uniform(0, 255, (R + 2 * m, S + 2 * m)))
+    big = (big - big.min()) / (big.max() - big.min()) * 255.0
+    scale, pmax = 1 << (depth - 8), (1 << depth) - 1
+    out = []
+    for f in range(nframes):
+        dx, dy = (0, 0) if f == 0 else rng.integers(-max_motion, max_motion + 1, 2)
+        fr = big[m + dy:m + dy + R, m + dx:m + dx + S] + rng.normal(0, noise, (R, S))
+        out.append(np.clip(np.rint(fr * scale), 0, pmax).astype(pdtype(depth)).ravel())
+    return out, S, R, padY * S + padX

@@ -30,6 +30,9 @@ int main(void)
     S(x265b200_deblock_job); F(x265b200_deblock_job, offset); F(x265b200_deblock_job, tcP); F(x265b200_deblock_job, maskQ);
     S(x265b200_me_chroma); F(x265b200_me_chroma, fencCb); F(x265b200_me_chroma, fencStrideC); F(x265b200_me_chroma, refCbPlanes); F(x265b200_me_chroma, refStrideC);
     S(x265b200_la_hme); F(x265b200_la_hme, lowerStride); F(x265b200_la_hme, width4); F(x265b200_la_hme, lowerMvPool); F(x265b200_la_hme, searchMethod); F(x265b200_la_hme, range);
+    S(x265b200_me_frame_params); F(x265b200_me_frame_params, minCuSize); F(x265b200_me_frame_params, picWidth); F(x265b200_me_frame_params, numRefs);
+    F(x265b200_me_frame_params, merange); F(x265b200_me_frame_params, maxCand); F(x265b200_me_frame_params, sliceTotalRows); F(x265b200_me_frame_params, refLagPixels);
+    S(x265b200_me_frame_planes); F(x265b200_me_frame_planes, curCr); F(x265b200_me_frame_planes, curStrideC); F(x265b200_me_frame_planes, refY); F(x265b200_me_frame_planes, refStrideC);
     return 0;
 }
 '''
@@ -61,9 +64,19 @@ def test_record_layouts_match_the_header():
         for (n, f), off in c.items():
             if n == name and f != "size":
                 assert dt.fields[f][1] == off, (name, f, dt.fields[f][1], off)
-    structs = {"x265b200_mc_desc": pkg.MC_DESC, "x265b200_me_chroma": pkg.ME_CHROMA, "x265b200_la_hme": pkg.LA_HME}
+    structs = {"x265b200_mc_desc": pkg.MC_DESC, "x265b200_me_chroma": pkg.ME_CHROMA, "x265b200_la_hme": pkg.LA_HME,
+               "x265b200_me_frame_params": pkg.ME_FRAME_PARAMS, "x265b200_me_frame_planes": pkg.ME_FRAME_PLANES}
     for name, st in structs.items():
         assert ctypes.sizeof(st) == c[(name, "size")], (name, ctypes.sizeof(st), c[(name, "size")])
         for (n, f), off in c.items():
             if n == name and f != "size":
                 assert getattr(st, f).offset == off, (name, f, getattr(st, f).offset, off)
+    assert pkg.ME_FRAME_PARAMS.lambda_.offset == _probe_lambda_offset()
+
+
+def _probe_lambda_offset():
+    with tempfile.TemporaryDirectory() as d:
+        src, exe = os.path.join(d, "p.c"), os.path.join(d, "p")
+        open(src, "w").write('#include <stdio.h>\n#include <stddef.h>\n#include "x265b200.h"\nint main(void){printf("%zu", offsetof(x265b200_me_frame_params, lambda));return 0;}')
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", exe, src], check=True)
+        return int(subprocess.run([exe], capture_output=True, text=True, check=True).stdout)

@@ -395,6 +395,51 @@ def _ctx_me_frame_dev(self, depth, dCur, curStride, refOrigins, refStride, margi
 Ctx.me_frame_dev = _ctx_me_frame_dev
 
 
+class ME_FRAME_PARAMS(ctypes.Structure):      # x265b200_me_frame_params
+    _fields_ = [(k, ctypes.c_int32) for k in ("depth", "ctuSize", "minCuSize", "rect", "amp", "picWidth", "picHeight", "ctuCols", "ctuRows",
+                                              "marginX", "marginY", "rowsTotal", "numRefs", "searchMethod", "subpelRefine", "merange", "csp",
+                                              "maxCand", "maxSlices", "frameParallel", "firstCtuRow", "sliceTotalRows", "refLagPixels")] + [("lambda_", ctypes.c_double)]
+
+
+class ME_FRAME_PLANES(ctypes.Structure):      # x265b200_me_frame_planes
+    _fields_ = [("curY", ctypes.c_void_p), ("curCb", ctypes.c_void_p), ("curCr", ctypes.c_void_p), ("curStride", ctypes.c_int64), ("curStrideC", ctypes.c_int64),
+                ("refY", ctypes.POINTER(ctypes.c_void_p)), ("refCb", ctypes.POINTER(ctypes.c_void_p)), ("refCr", ctypes.POINTER(ctypes.c_void_p)),
+                ("refStride", ctypes.c_int64), ("refStrideC", ctypes.c_int64)]
+
+
+def me_frame_layout(ctuSize, minCuSize, rect, amp):
+    """x265b200_me_frame_layout: [nPU][4] = {x, y, w, h} inside the CTU, in the order of the frame search's arrays."""
+    L = load()
+    n = L.x265b200_me_frame_layout(int(ctuSize), int(minCuSize), int(rect), int(amp), None, 0)
+    if n < 0:
+        raise X265B200Error(L.x265b200_last_error().decode())
+    out = np.zeros((n, 4), dtype=np.int32)
+    L.x265b200_me_frame_layout(int(ctuSize), int(minCuSize), int(rect), int(amp), out.ctypes.data_as(ctypes.c_void_p), n)
+    return out
+
+
+def _ctx_me_frame_ex_dev(self, params, curY, curStride, refY, refStride, dOut, dMvpCtu=None, dMvpPu=None, dNumCand=None, dMvc=None,
+                         curC=None, curStrideC=0, refCb=None, refCr=None, refStrideC=0):
+    """params: dict of x265b200_me_frame_params fields (lambda under 'lambda'); curY / curC = device addresses of plane origins;
+    refY / refCb / refCr = lists of device addresses."""
+    P = ME_FRAME_PARAMS()
+    for k, v in params.items():
+        setattr(P, "lambda_" if k == "lambda" else k, v)
+    P.numRefs = len(refY)
+    arrs = [(ctypes.c_void_p * len(refY))(*[int(x) for x in lst]) if lst is not None else None for lst in (refY, refCb, refCr)]
+    pl = ME_FRAME_PLANES()
+    pl.curY = int(curY); pl.curStride = int(curStride); pl.curStrideC = int(curStrideC)
+    pl.curCb = int(curC[0]) if curC is not None else None; pl.curCr = int(curC[1]) if curC is not None else None
+    pl.refY = ctypes.cast(arrs[0], ctypes.POINTER(ctypes.c_void_p))
+    pl.refCb = ctypes.cast(arrs[1], ctypes.POINTER(ctypes.c_void_p)) if arrs[1] is not None else None
+    pl.refCr = ctypes.cast(arrs[2], ctypes.POINTER(ctypes.c_void_p)) if arrs[2] is not None else None
+    pl.refStride = int(refStride); pl.refStrideC = int(refStrideC)
+    self._chk(self.L.x265b200_me_frame_ex_dev(self.h, ctypes.byref(P), ctypes.byref(pl), _vp(dMvpCtu), _vp(dMvpPu), _vp(dNumCand), _vp(dMvc), _vp(dOut)))
+
+
+Ctx.me_frame_ex_dev = _ctx_me_frame_ex_dev
+
+
 # ---- --me sea --------------------------------------------------------------------------------------
 ADS_JOB = np.dtype([("sumsOff", np.int64), ("thresh", np.int32), ("encDC", np.int32, (4,))], align=True)      # 32 bytes, as the C struct
 SEA_PLANE_W = [32, 32, 32, 24, 16, 16, 16, 12, 8, 8, 4, 4]       # FrameData::m_meIntegral order (framedata.h:171)

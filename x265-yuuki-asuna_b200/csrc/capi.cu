@@ -121,7 +121,10 @@ int copy_cnt_dev(Ctx*, int size, int16_t* coeff, const int16_t* resi, int64_t st
 int denoise_dct_dev(Ctx*, int16_t* coef, uint32_t* resSum, const uint16_t* offset, int numCoeff, int64_t n);
 int lowpass_front_dev(Ctx*, const int16_t* src, int64_t srcBlockStride, int64_t srcStride, int64_t n, int N, int16_t* avg, int32_t* total);
 int lowpass_back_dev(Ctx*, const int16_t* coefHalf, const int32_t* total, int64_t n, int N, int16_t* dst);
-int debug_me_frame_cycles(unsigned long long* out);
+int me_frame_ex_dev(Ctx*, const x265b200_me_frame_params* P, const x265b200_me_frame_planes* pl, const int32_t* mvpCtu, const int32_t* mvpPu,
+                    const uint8_t* numCandPu, const int32_t* mvcPu, int32_t* out);
+int me_frame_layout(int ctuSize, int minCuSize, int rect, int amp, int32_t* outXYWH, int cap);
+void me_ctu_release(Ctx* ctx);
 int me_frame_dev(Ctx*, int depth, const void* curOrigin, int64_t curStride, const void* const* refOriginsHost, int numRefs, int64_t refStride,
                  int marginX, int marginY, int rowsTotal, int ctuCols, int ctuRows, int puMask, const int32_t* mvpCtu,
                  int searchMethod, int subpelRefine, int merange, double lambda, int32_t* out);
@@ -193,6 +196,7 @@ void x265b200_destroy(x265b200_ctx* ctx)
         if (ctx->c.hPinned[i]) cudaFreeHost(ctx->c.hPinned[i]);
     }
     if (ctx->c.dMvCost) cudaFree(ctx->c.dMvCost);
+    me_ctu_release(&ctx->c);
     if (ctx->c.ownsStream) cudaStreamDestroy(ctx->c.stream);
     delete ctx;
 }
@@ -560,11 +564,15 @@ int x265b200_me_frame_dev(x265b200_ctx* ctx, int depth, const void* curOrigin, i
     return me_frame_dev(CTX(ctx), depth, curOrigin, curStride, refOriginsHost, numRefs, refStride, marginX, marginY, rowsTotal,
                         ctuCols, ctuRows, puMask, mvpCtu, searchMethod, subpelRefine, merange, lambda, out);
 }
-int x265b200_debug_me_frame_cycles(x265b200_ctx* ctx, uint64_t* out9)
+int x265b200_me_frame_ex_dev(x265b200_ctx* ctx, const x265b200_me_frame_params* params, const x265b200_me_frame_planes* planes,
+                             const int32_t* mvpCtu, const int32_t* mvpPu, const uint8_t* numCandPu, const int32_t* mvcPu, int32_t* out)
 {
     REQUIRE_CTX(ctx);
-    X265B200_CHECK(cudaStreamSynchronize(ctx->c.stream));
-    return debug_me_frame_cycles((unsigned long long*)out9);
+    return me_frame_ex_dev(CTX(ctx), params, planes, mvpCtu, mvpPu, numCandPu, mvcPu, out);
+}
+int x265b200_me_frame_layout(int ctuSize, int minCuSize, int rect, int amp, int32_t* outXYWH, int cap)
+{
+    return me_frame_layout(ctuSize, minCuSize, rect, amp, outXYWH, cap);
 }
 int x265b200_bitcost_table(double lambda, uint16_t* out)
 {

@@ -128,7 +128,14 @@ struct MEState
 };
 
 // The cached source PU (fenc) lives in shared memory in every kernel that uses this header: say so at the load sites.
-template<typename T> __device__ __forceinline__ const T* smem_hint(const T* p) { __builtin_assume(__isShared(p)); return p; }
+template<typename T> __device__ __forceinline__ const T* smem_hint(const T* p)
+{
+#ifdef ME_HOST_EMU
+    if ((uintptr_t)p % sizeof(T)) abort();      // the host emulation enforces the natural alignment the GPU faults on
+#endif
+    __builtin_assume(__isShared(p));
+    return p;
+}
 
 constexpr int kMvTableHalf = 2 * 32768;
 

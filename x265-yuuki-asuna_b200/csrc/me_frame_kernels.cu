@@ -92,8 +92,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 }
 
 constexpr int MF_WARPS = 4;
-// per-role busy cycles, accumulated by every CTA (profiling aid, read with x265b200_debug_me_frame_cycles)
-__device__ unsigned long long g_mfCycles[MF_WARPS + 1];
 
 // CTA roles (4 warps).  EVERY search runs in per-thread mode: a lane owns an 8-pixel-wide sub-block of the PU, runs the
 // whole bit-exact search on it and the lanes of one PU sum their SAD/SATD partials with shuffles (they then hold
@@ -142,7 +140,6 @@ me_frame_kernel(const __grid_constant__ MEFrameMaps maps, MEFrameArgs p)
         tma_load_2d(fencCtu, &maps.cur, bar, ctuX * 64 + p.marginX, ctuY * 64 + p.marginY);
     }
     mbar_wait(bar, 0);
-    const long long tStart = clock64();
 
     // ---- roles ---------------------------------------------------------------------------------------------------
     MEState<pixel> s;
@@ -184,7 +181,6 @@ me_frame_kernel(const __grid_constant__ MEFrameMaps maps, MEFrameArgs p)
             }
         }
     }
-    if (lane == 0) { atomicAdd(&g_mfCycles[warp], (unsigned long long)(clock64() - tStart)); if (warp == 0) atomicAdd(&g_mfCycles[MF_WARPS], 1ull); }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -286,12 +282,6 @@ int me_frame_dev(Ctx* ctx, int depth, const void* curOrigin, int64_t curStride, 
     }
     ctx->launches++;
     return check(cudaGetLastError(), "me_frame kernel launch");
-}
-
-int debug_me_frame_cycles(unsigned long long* out)
-{
-    X265B200_CHECK(cudaMemcpyFromSymbol(out, g_mfCycles, sizeof(unsigned long long) * (MF_WARPS + 1)));
-    return 0;
 }
 
 } // namespace x265b200

@@ -20,17 +20,18 @@ namespace x265b200 {
 void host_bitcost_table(double lambda, uint16_t* out /* 4*32768+1, centred at out[2*32768] */)
 {
     const int M = 32768;
-    static std::vector<float> bits;
-    if (bits.empty())
-    {
-        bits.resize(2 * M + 1);
-        bits[0] = 0.718f;
+    // built once, thread-safely (a C++11 magic static; the reference guards the same initialisation with s_costCalcLock,
+    // bitcost.cpp:34-58): contexts are per thread, so two encoder worker threads can arrive here together
+    static const std::vector<float> bits = []() {
+        std::vector<float> b(2 * 32768 + 1);
+        b[0] = 0.718f;
         // NB: inside a .cu file `log(float)` would bind to CUDA's float overload; the reference (plain
         // g++) calls the double `log`, so spell the promotions out.
-        float log2_2 = (float)((double)2.0f / log((double)2.0f));
-        for (int i = 1; i <= 2 * M; i++)
-            bits[i] = (float)(log((double)(float)(i + 1)) * (double)log2_2 + (double)1.718f);
-    }
+        const float log2_2 = (float)((double)2.0f / log((double)2.0f));
+        for (int i = 1; i <= 2 * 32768; i++)
+            b[i] = (float)(log((double)(float)(i + 1)) * (double)log2_2 + (double)1.718f);
+        return b;
+    }();
     uint16_t* c = out + 2 * M;
     for (int i = 0; i <= 2 * M; i++)
     {
@@ -88,6 +89,13 @@ me_batch_kernel(MEArgs p)
     const int64_t j = (int64_t)blockIdx.x * ME_WARPS + warp;
     if (j >= p.n) return;
     x265b200_me_job job = p.jobs[j];
+    // a job the launch was not sized for (or not a multiple of 4x4) would overrun this warp's shared-memory areas: refuse it
+    // visibly instead (cost -1, MV untouched); x265b200_me_batch_dev documents maxW / maxH
+    if (job.w > p.maxW || job.h > p.maxH || job.w < 4 || job.h < 4 || ((job.w | job.h) & 3))
+    {
+        if (lane == 0) p.jobs[j].outCost = -1;
+        return;
+    }
 
     MEState<pixel> s;
     s.fenc = (pixel*)base;
