@@ -81,6 +81,21 @@ int x265b200_sad_pyramid_dev(x265b200_ctx* ctx, int depth, const void* cur, int6
                              int ctuCols, int ctuRows, const int16_t* mvCtu,
                              int32_t* out8, int32_t* out16, int32_t* out32, int32_t* out64);
 
+/* Streaming form over a frame POOL, many (frame, references) groups per launch -- the kernel BASELINE's "ME SAD achieved HBM
+ * GB/s" is measured on.  The pool is numFrames equal planes (PicYuv layout: `stride` pixels per row, rowsTotal rows, marginX /
+ * marginY of padding), frame f at poolOrigin + f * framePitch pixels (poolOrigin = pixel (0,0) of frame 0) -- the shape of a
+ * decoded-picture buffer.  groupsHost[g] = { source frame, reference frames[numRefs] } (indices into the pool).  Per group and
+ * reference the SADs at zero displacement of every 2Nx2N PU (pu[LUMA_8x8 .. LUMA_64x64].sad, pixel.cpp:40-55; the
+ * cost-at-predictor step of motionEstimate, motion.cpp:771-784, with mvp = 0) are written to outN[(g * numRefs + r)] as raster
+ * grids of NxN blocks (ctuCols*64/N per row).  8-, 10- and 12-bit.  Persistent CTAs stream 16 KB tiles through a 6-stage
+ * shared-memory ring with TMA; every plane byte is fetched once per use.  Base, stride, frame pitch and marginX must be
+ * multiples of 16 bytes. */
+typedef struct { int32_t cur; int32_t ref[8]; } x265b200_sad_group;
+int x265b200_sad_stream_dev(x265b200_ctx* ctx, int depth, const void* poolOrigin, int64_t framePitch, int64_t stride,
+                            int marginX, int marginY, int rowsTotal, int numFrames, int ctuCols, int ctuRows,
+                            const x265b200_sad_group* groupsHost, int numGroups, int numRefs,
+                            int32_t* out8, int32_t* out16, int32_t* out32, int32_t* out64);
+
 /* sad_x3 / sad_x4: replaces pu[].sad_x3 / pu[].sad_x4 (primitives.h:139-140,248-249;
  * pixel.cpp:74-119).  Item i compares the cached 64-stride PU at fenc + i*fencBlockStride with
  * K (=3 or 4; 1..4 accepted) blocks ref + refOff[i*K+k], common refStride.  res: int32[n][K]. */

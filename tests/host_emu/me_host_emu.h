@@ -22,6 +22,8 @@
 
 struct uint2 { uint32_t x, y; };
 struct uint4 { uint32_t x, y, z, w; };
+struct int4 { int x, y, z, w; };
+inline int4 make_int4(int x, int y, int z, int w) { int4 r = { x, y, z, w }; return r; }
 
 namespace x265b200 {
 namespace emu {
@@ -76,6 +78,7 @@ inline uint32_t __vsadu2(uint32_t a, uint32_t b)
     for (int i = 0; i < 2; i++) { int d = (int)((a >> (16 * i)) & 0xffff) - (int)((b >> (16 * i)) & 0xffff); s += d < 0 ? -d : d; }
     return s;
 }
+inline uint32_t sad_u16x2(uint32_t a, uint32_t b) { return __vsadu2(a, b); }      // common.cuh's 16-bit SAD helper (same value)
 inline uint32_t __vavgu4(uint32_t a, uint32_t b)
 {
     uint32_t r = 0;

@@ -30,6 +30,7 @@ int main(void)
     S(x265b200_deblock_job); F(x265b200_deblock_job, offset); F(x265b200_deblock_job, tcP); F(x265b200_deblock_job, maskQ);
     S(x265b200_me_chroma); F(x265b200_me_chroma, fencCb); F(x265b200_me_chroma, fencStrideC); F(x265b200_me_chroma, refCbPlanes); F(x265b200_me_chroma, refStrideC);
     S(x265b200_la_hme); F(x265b200_la_hme, lowerStride); F(x265b200_la_hme, width4); F(x265b200_la_hme, lowerMvPool); F(x265b200_la_hme, searchMethod); F(x265b200_la_hme, range);
+    S(x265b200_sad_group); F(x265b200_sad_group, ref);
     S(x265b200_me_frame_params); F(x265b200_me_frame_params, minCuSize); F(x265b200_me_frame_params, picWidth); F(x265b200_me_frame_params, numRefs);
     F(x265b200_me_frame_params, merange); F(x265b200_me_frame_params, maxCand); F(x265b200_me_frame_params, sliceTotalRows); F(x265b200_me_frame_params, refLagPixels);
     S(x265b200_me_frame_planes); F(x265b200_me_frame_planes, curCr); F(x265b200_me_frame_planes, curStrideC); F(x265b200_me_frame_planes, refY); F(x265b200_me_frame_planes, refStrideC);
@@ -55,7 +56,7 @@ def test_record_layouts_match_the_header():
     c = _probe()
     dtypes = {"x265b200_me_job": pkg.ME_JOB, "x265b200_interp_job": pkg.INTERP_JOB, "x265b200_intra_job": pkg.INTRA_JOB,
               "x265b200_la_triple": pkg.LA_TRIPLE, "x265b200_ads_job": pkg.ADS_JOB, "x265b200_mc_job": pkg.MC_JOB,
-              "x265b200_mc_weight": pkg.MC_WEIGHT, "x265b200_sao_job": pkg.SAO_JOB, "x265b200_deblock_job": pkg.DEBLOCK_JOB}
+              "x265b200_mc_weight": pkg.MC_WEIGHT, "x265b200_sad_group": pkg.SAD_GROUP, "x265b200_sao_job": pkg.SAO_JOB, "x265b200_deblock_job": pkg.DEBLOCK_JOB}
     if hasattr(pkg, "GLUE_JOB"):
         dtypes["x265b200_glue_job"] = pkg.GLUE_JOB
     for name, dt in dtypes.items():

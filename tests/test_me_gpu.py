@@ -240,3 +240,48 @@ def test_me_frame_ctu_row_bands_equal_full_frame(ctx):
             off_f += pl_full[level]; off_b += pl[level]
     for b in [dC] + dR:
         b.free()
+
+
+@pytest.mark.parametrize("method", [pkg.ME_HEX, pkg.ME_UMH, pkg.ME_STAR])
+def test_me_frame_predictors_far_from_zero_on_static_content(ctx, method):
+    """per-CTU predictors with |mvp >> 2| > merange on STATIC content -- the zero-MV candidate wins, so the search
+    continues around (0, clampY(0)), far outside a window centred on the predictor.  Calls with predictors run on the general
+    kernel (window test per block, plane fallback) and must still equal the reference's motionEstimate."""
+    depth, merange, subme = 8, 16, 2
+    ctuCols, ctuRows, NREF = 3, 2, 2
+    W, H, pad = ctuCols * 64, ctuRows * 64, 256
+    cur, _, S, origin = synth_pair(W, H, pad, depth=depth, seed=1717, motion=(0, 0), noise=0.0)
+    refs = [cur.copy(), cur.copy()]                       # static: zero MV is the exact match
+    refs[1][::7] ^= 1                                     # second reference: almost static
+    rowsTotal = H + 2 * pad
+    rng = np.random.default_rng(6)
+    mvp = (rng.choice([-1, 1], (NREF, ctuCols * ctuRows, 2)) * rng.integers(4 * (merange + 2), 4 * (merange + 40), (NREF, ctuCols * ctuRows, 2))).astype(np.int32)
+    mvp[0, 1] = [4 * (merange + 1), 0]                    # just past the range: UMH / hex overshoot at the window edge
+    mvp[1, 2] = [0, -4 * merange]
+    lam = pkg.lambda_for_qp(30, depth)
+    dC = ctx.to_device(cur); dR = [ctx.to_device(r) for r in refs]; dMvp = ctx.to_device(mvp)
+    per_level = [ctuCols * ctuRows * (1 << l) ** 2 for l in range(4)]
+    nPU = sum(per_level)
+    dOut = ctx.empty(NREF * nPU * 12)
+    ctx.me_frame_dev(depth, dC.ptr + origin, S, [d.ptr + origin for d in dR], S, pad, pad, rowsTotal, ctuCols, ctuRows, 15, dMvp, method, subme, merange, lam, dOut)
+    got = dOut.download(np.int32).reshape(NREF, nPU, 3)
+    for r in range(NREF):
+        jobs = []
+        for level in range(4):
+            s, per = 64 >> level, 1 << level
+            for gy in range(ctuRows * per):
+                for gx in range(ctuCols * per):
+                    ctu = (gy // per) * ctuCols + (gx // per)
+                    jobs.append((gx * s, gy * s, s, int(mvp[r, ctu, 0]), int(mvp[r, ctu, 1])))
+        job = np.zeros(len(jobs), dtype=pkg.ME_JOB)
+        for i, (x, y, s, px, py) in enumerate(jobs):
+            job[i]["puX"], job[i]["puY"], job[i]["w"], job[i]["h"] = x, y, s, s
+            job[i]["mvpX"], job[i]["mvpY"] = px, py
+            job[i]["mvminX"], job[i]["mvminY"] = (px >> 2) - merange, (py >> 2) - merange
+            job[i]["mvmaxX"], job[i]["mvmaxY"] = (px >> 2) + merange, (py >> 2) + merange
+        ex, ey, ec = ref_me(depth, cur, refs[r], S, origin, job, method, subme, merange, 30)
+        bad = np.nonzero((got[r, :, 0] != ex) | (got[r, :, 1] != ey) | (got[r, :, 2] != ec))[0]
+        assert not len(bad), (r, int(bad[0]), jobs[bad[0]], got[r, bad[0]].tolist(), int(ex[bad[0]]), int(ey[bad[0]]), int(ec[bad[0]]), len(bad))
+        assert (ex == 0).sum() > len(ex) // 4          # the zero MV does win for many PUs
+    for b in [dC, dMvp, dOut] + dR:
+        b.free()

@@ -162,3 +162,40 @@ def test_sad_pyramid_matches_per_level_sad(ctx, with_mv):
                 offB.append(base + (by * s + my) * S + bx * s + mx)
             exp = orc_cmp("sad", 8, s, s, cur, S, refs[r], S, np.array(offA), np.array(offB))
             assert list(map(int, got[r])) == exp, (s, with_mv, r)
+
+
+@pytest.mark.parametrize("depth,ctuCols,ctuRows,nref,ngroups", [(8, 5, 2, 2, 3), (8, 9, 3, 3, 4), (10, 5, 2, 2, 3), (10, 3, 3, 1, 2)])
+def test_sad_stream_pool_matches_per_level_sad(ctx, depth, ctuCols, ctuRows, nref, ngroups):
+    """the streaming form over a frame pool (TMA ring, many groups per launch) = pu[8x8..64x64].sad at zero displacement of every
+    2Nx2N PU, per group and reference; odd CTU counts leave the last 256-byte tile partly outside the picture."""
+    from util import pdtype
+    rng = np.random.default_rng(13 + depth)
+    padX, padY = 96, 80
+    W, H = ctuCols * 64, ctuRows * 64
+    S, R = W + 2 * padX, H + 2 * padY
+    item = 2 if depth > 8 else 1
+    NF = 6
+    pitch = S * R + 64                                            # frames need not be back to back
+    pool = rng.integers(0, 1 << depth, NF * pitch, dtype=np.int64).astype(pdtype(depth))
+    groups = np.zeros(ngroups, dtype=pkg.SAD_GROUP)
+    for g in range(ngroups):
+        idx = rng.permutation(NF)
+        groups[g]["cur"] = idx[0]
+        groups[g]["ref"][:nref] = idx[1:1 + nref]
+    origin = padY * S + padX
+    dP = ctx.to_device(pool)
+    outs = {s: ctx.empty(ngroups * nref * (W // s) * (H // s) * 4) for s in (8, 16, 32, 64)}
+    ctx.sad_stream_dev(depth, dP.ptr + origin * item, pitch, S, padX, padY, R, NF, ctuCols, ctuRows, groups, nref, outs[8], outs[16], outs[32], outs[64])
+    for s in (8, 16, 32, 64):
+        got = outs[s].download(np.int32).reshape(ngroups, nref, -1)
+        cols = W // s
+        off = np.array([origin + (i // cols) * s * S + (i % cols) * s for i in range(cols * (H // s))], dtype=np.int64)
+        for g in range(ngroups):
+            cur = pool[int(groups[g]["cur"]) * pitch:][:S * R]
+            for r in range(nref):
+                ref = pool[int(groups[g]["ref"][r]) * pitch:][:S * R]
+                exp = orc_cmp("sad", depth, s, s, cur, S, ref, S, off, off)
+                assert list(map(int, got[g, r])) == exp, (s, g, r)
+    dP.free()
+    for b in outs.values():
+        b.free()

@@ -384,6 +384,20 @@ def _ctx_sad_pyramid_dev(self, depth, dCur, strideCur, dRefPtrs, numRefs, stride
 Ctx.sad_pyramid_dev = _ctx_sad_pyramid_dev
 
 
+SAD_GROUP = np.dtype([("cur", np.int32), ("ref", np.int32, (8,))])          # x265b200_sad_group
+
+
+def _ctx_sad_stream_dev(self, depth, poolOrigin, framePitch, stride, marginX, marginY, rowsTotal, numFrames, ctuCols, ctuRows, groups, numRefs,
+                        dOut8, dOut16, dOut32, dOut64):
+    """groups: numpy array of SAD_GROUP (host)"""
+    g = np.ascontiguousarray(groups, dtype=SAD_GROUP)
+    self._chk(self.L.x265b200_sad_stream_dev(self.h, int(depth), _vp(poolOrigin), _i64(framePitch), _i64(stride), int(marginX), int(marginY), int(rowsTotal),
+                                             int(numFrames), int(ctuCols), int(ctuRows), _vp(g), len(g), int(numRefs), _vp(dOut8), _vp(dOut16), _vp(dOut32), _vp(dOut64)))
+
+
+Ctx.sad_stream_dev = _ctx_sad_stream_dev
+
+
 def _ctx_me_frame_dev(self, depth, dCur, curStride, refOrigins, refStride, marginX, marginY, rowsTotal, ctuCols, ctuRows, puMask,
                       dMvpCtu, searchMethod, subpelRefine, merange, lam, dOut):
     arr = (ctypes.c_void_p * len(refOrigins))(*[int(p) for p in refOrigins])

@@ -123,6 +123,9 @@ int lowpass_front_dev(Ctx*, const int16_t* src, int64_t srcBlockStride, int64_t 
 int lowpass_back_dev(Ctx*, const int16_t* coefHalf, const int32_t* total, int64_t n, int N, int16_t* dst);
 int me_frame_ex_dev(Ctx*, const x265b200_me_frame_params* P, const x265b200_me_frame_planes* pl, const int32_t* mvpCtu, const int32_t* mvpPu,
                     const uint8_t* numCandPu, const int32_t* mvcPu, int32_t* out);
+int sad_stream_dev(Ctx*, int depth, const void* poolOrigin, int64_t framePitch, int64_t stride, int marginX, int marginY, int rowsTotal, int numFrames,
+                   int ctuCols, int ctuRows, const x265b200_sad_group* groupsHost, int numGroups, int numRefs,
+                   int32_t* out8, int32_t* out16, int32_t* out32, int32_t* out64);
 int me_frame_layout(int ctuSize, int minCuSize, int rect, int amp, int32_t* outXYWH, int cap);
 void me_ctu_release(Ctx* ctx);
 int me_frame_dev(Ctx*, int depth, const void* curOrigin, int64_t curStride, const void* const* refOriginsHost, int numRefs, int64_t refStride,
@@ -569,6 +572,15 @@ int x265b200_me_frame_ex_dev(x265b200_ctx* ctx, const x265b200_me_frame_params* 
 {
     REQUIRE_CTX(ctx);
     return me_frame_ex_dev(CTX(ctx), params, planes, mvpCtu, mvpPu, numCandPu, mvcPu, out);
+}
+int x265b200_sad_stream_dev(x265b200_ctx* ctx, int depth, const void* poolOrigin, int64_t framePitch, int64_t stride,
+                            int marginX, int marginY, int rowsTotal, int numFrames, int ctuCols, int ctuRows,
+                            const x265b200_sad_group* groupsHost, int numGroups, int numRefs,
+                            int32_t* out8, int32_t* out16, int32_t* out32, int32_t* out64)
+{
+    REQUIRE_CTX(ctx);
+    return sad_stream_dev(CTX(ctx), depth, poolOrigin, framePitch, stride, marginX, marginY, rowsTotal, numFrames, ctuCols, ctuRows,
+                          groupsHost, numGroups, numRefs, out8, out16, out32, out64);
 }
 int x265b200_me_frame_layout(int ctuSize, int minCuSize, int rect, int amp, int32_t* outXYWH, int cap)
 {

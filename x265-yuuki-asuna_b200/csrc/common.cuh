@@ -89,6 +89,14 @@ __device__ __forceinline__ void ld4s(const int16_t* p, int v[4])
     v[0] = (int16_t)(x & 0xffff); v[1] = (int16_t)(x >> 16); v[2] = (int16_t)(y & 0xffff); v[3] = (int16_t)(y >> 16);
 }
 
+// SAD of the two 16-bit pixels of a word pair.  __vsadu2 is emulated on sm_100a (~10 instructions: PRMT / IMAD / IABS per lane,
+// scripts' SASS count of the first 16-bit streaming kernel); per-halfword max - min cannot borrow across the halves, so
+// VIMNMX.U16x2 x2 + IADD + IDP.2A (both halves summed by a dot product with 1, 1) gives the same number in 4.
+__device__ __forceinline__ uint32_t sad_u16x2(uint32_t a, uint32_t b)
+{
+    return __dp2a_lo(__vmaxu2(a, b) - __vminu2(a, b), 0x0101u, 0u);
+}
+
 // sum of absolute differences of 4 pixels
 template<typename pixel> __device__ __forceinline__ int sad4(const pixel* a, const pixel* b);
 template<> __device__ __forceinline__ int sad4<uint8_t>(const uint8_t* a, const uint8_t* b)
@@ -97,7 +105,7 @@ template<> __device__ __forceinline__ int sad4<uint8_t>(const uint8_t* a, const 
 }
 template<> __device__ __forceinline__ int sad4<uint16_t>(const uint16_t* a, const uint16_t* b)
 {
-    return (int)(__vsadu2(ld_px2(a), ld_px2(b)) + __vsadu2(ld_px2(a + 2), ld_px2(b + 2)));
+    return (int)(sad_u16x2(ld_px2(a), ld_px2(b)) + sad_u16x2(ld_px2(a + 2), ld_px2(b + 2)));
 }
 
 __device__ __forceinline__ int clip3i(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }

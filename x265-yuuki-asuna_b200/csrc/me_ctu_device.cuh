@@ -56,6 +56,7 @@ struct MECtuArgs
     const int32_t* sliceBounds;       // [ctuRows][2] quarter-pel m_sliceMinY / m_sliceMaxY (frameencoder.cpp:1448-1453), or null
     int maxSlices;
     int refLagPixels;                 // Search::m_refLagPixels (search.cpp:92), full-pel
+    int rawRange;                     // 1: mvmin / mvmax = (mvp >> 2) -+ merange, no picture clipping (x265b200_me_frame_dev semantics)
 };
 
 // where the CTA's staged data lives (shared memory) and which picture area it shows
@@ -101,20 +102,23 @@ __device__ void me_ctu_lane(const MECtuArgs& p, const MECtuStage<pixel>& st, uin
 
     // Search::setSearchRange (search.cpp:2724-2769)
     int minx = mvpx - (p.merange << 2), miny = mvpy - (p.merange << 2), maxx = mvpx + (p.merange << 2), maxy = mvpy + (p.merange << 2);
+    if (!p.rawRange)
     {
-        // CUData::clipMv (cudata.cpp:1915-1928)
-        const int xmax = (p.picW + 8 - cuPelX - 1) << 2, xmin = -((C + 8 + cuPelX - 1) << 2);
-        const int ymax = (p.picH + 8 - cuPelY - 1) << 2, ymin = -((C + 8 + cuPelY - 1) << 2);
-        minx = min(xmax, max(xmin, minx)); miny = min(ymax, max(ymin, miny));
-        maxx = min(xmax, max(xmin, maxx)); maxy = min(ymax, max(ymin, maxy));
+        {
+            // CUData::clipMv (cudata.cpp:1915-1928)
+            const int xmax = (p.picW + 8 - cuPelX - 1) << 2, xmin = -((C + 8 + cuPelX - 1) << 2);
+            const int ymax = (p.picH + 8 - cuPelY - 1) << 2, ymin = -((C + 8 + cuPelY - 1) << 2);
+            minx = min(xmax, max(xmin, minx)); miny = min(ymax, max(ymin, miny));
+            maxx = min(xmax, max(xmin, maxx)); maxy = min(ymax, max(ymin, maxy));
+        }
+        if (p.sliceBounds)          // (m_param->maxSlices > 1) & m_bFrameParallel
+        {
+            miny = max(miny, p.sliceBounds[2 * ctuY]);
+            maxy = min(maxy, p.sliceBounds[2 * ctuY + 1]);
+        }
+        const int maxMvLen = (1 << 15) - 1;
+        minx = max(minx, -maxMvLen); miny = max(miny, -maxMvLen); maxx = min(maxx, maxMvLen); maxy = min(maxy, maxMvLen);
     }
-    if (p.sliceBounds)          // (m_param->maxSlices > 1) & m_bFrameParallel
-    {
-        miny = max(miny, p.sliceBounds[2 * ctuY]);
-        maxy = min(maxy, p.sliceBounds[2 * ctuY + 1]);
-    }
-    const int maxMvLen = (1 << 15) - 1;
-    minx = max(minx, -maxMvLen); miny = max(miny, -maxMvLen); maxx = min(maxx, maxMvLen); maxy = min(maxy, maxMvLen);
     minx >>= 2; miny >>= 2; maxx >>= 2; maxy >>= 2;
     miny = min(miny, p.refLagPixels); maxy = min(maxy, p.refLagPixels);
     maxy = max(maxy, miny);

@@ -174,17 +174,17 @@ static int mc_encode_plane(CUtensorMap* m, int depth, const void* origin, int64_
 
 // the PU / item tables of a layout live on the device for the lifetime of the context
 struct MECtuTables { void* dPus; void* dItems; int numPu, numItems; };
-static std::map<std::tuple<Ctx*, int, int, int, int, int, int>, MECtuTables> g_mcTables;
+static std::map<std::tuple<Ctx*, int, int, int, int, int, int, int>, MECtuTables> g_mcTables;
 static std::mutex g_mcLock;
 
-static int mc_tables(Ctx* ctx, int ctuSize, int minCu, int rect, int amp, int csp, int chromaSatd, MECtuTables& out)
+static int mc_tables(Ctx* ctx, int ctuSize, int minCu, int rect, int amp, int csp, int chromaSatd, int sizeMask, MECtuTables& out)
 {
     std::lock_guard<std::mutex> lk(g_mcLock);
-    auto key = std::make_tuple(ctx, ctuSize, minCu, rect, amp, csp, chromaSatd);
+    auto key = std::make_tuple(ctx, ctuSize, minCu, rect, amp, csp, chromaSatd, sizeMask);
     auto it = g_mcTables.find(key);
     if (it != g_mcTables.end()) { out = it->second; return 0; }
     MECtuLayout L;
-    me_ctu_build_layout(ctuSize, minCu, rect != 0, amp != 0, csp, chromaSatd != 0, L);
+    me_ctu_build_layout(ctuSize, minCu, rect != 0, amp != 0, csp, chromaSatd != 0, L, sizeMask);
     MECtuTables t; t.numPu = (int)L.pus.size(); t.numItems = L.numItems;
     X265B200_CHECK(cudaMalloc(&t.dPus, L.pus.size() * sizeof(MECtuPU)));
     X265B200_CHECK(cudaMalloc(&t.dItems, L.items.size() * sizeof(uint32_t)));
@@ -220,8 +220,8 @@ int me_frame_layout(int ctuSize, int minCuSize, int rect, int amp, int32_t* outX
     return (int)v.size();
 }
 
-int me_frame_ex_dev(Ctx* ctx, const x265b200_me_frame_params* P, const x265b200_me_frame_planes* pl, const int32_t* mvpCtu, const int32_t* mvpPu,
-                    const uint8_t* numCandPu, const int32_t* mvcPu, int32_t* out)
+static int me_ctu_launch(Ctx* ctx, const x265b200_me_frame_params* P, const x265b200_me_frame_planes* pl, const int32_t* mvpCtu, const int32_t* mvpPu,
+                         const uint8_t* numCandPu, const int32_t* mvcPu, int32_t* out, int rawRange, int sizeMask)
 {
     if (!P || !pl) { set_error("me_frame_ex: null params"); return -1; }
     if (P->numRefs <= 0 || P->ctuCols <= 0 || P->ctuRows <= 0) return 0;
@@ -233,7 +233,7 @@ int me_frame_ex_dev(Ctx* ctx, const x265b200_me_frame_params* P, const x265b200_
     if (P->csp < 0 || P->csp > 3) { set_error("me_frame_ex: csp %d (0 = luma only, 1 = 4:2:0, 2 = 4:2:2, 3 = 4:4:4)", P->csp); return -1; }
     if (P->maxCand < 0 || P->maxCand > 16) { set_error("me_frame_ex: maxCand %d", P->maxCand); return -1; }
     if (P->maxCand && (!numCandPu || !mvcPu)) { set_error("me_frame_ex: maxCand > 0 needs numCandPu and mvcPu"); return -1; }
-    const int depth = P->depth, px = depth > 8 ? 2 : 1, APX = 16 / px;
+    const int depth = P->depth, px = depth > 8 ? 2 : 1;
     const int C = P->ctuSize;
     const int hs = (P->csp == 1 || P->csp == 2) ? 1 : 0, vs = P->csp == 1 ? 1 : 0;
     const int chromaSatd = P->csp != 0 && P->subpelRefine > 2;            // motion.cpp:212 (per PU: && chroma satd exists)
@@ -255,7 +255,7 @@ int me_frame_ex_dev(Ctx* ctx, const x265b200_me_frame_params* P, const x265b200_
     if (ensure_mvcost(ctx, P->lambda)) return -1;
 
     MECtuTables T;
-    if (mc_tables(ctx, C, P->minCuSize, P->rect, P->amp, P->csp, chromaSatd, T)) return -1;
+    if (mc_tables(ctx, C, P->minCuSize, P->rect, P->amp, P->csp, chromaSatd, sizeMask, T)) return -1;
 
     MECtuMaps maps; memset(&maps, 0, sizeof(maps));
     const int rowsC = P->rowsTotal >> vs;
@@ -336,6 +336,7 @@ int me_frame_ex_dev(Ctx* ctx, const x265b200_me_frame_params* P, const x265b200_
     a.sliceBounds = sliced ? (const int32_t*)((char*)dScr + ptrBytes) : nullptr;
     a.maxSlices = P->maxSlices > 1 ? P->maxSlices : 1;
     a.refLagPixels = P->refLagPixels > 0 ? P->refLagPixels : INT_MAX / 2;
+    a.rawRange = rawRange;
 
     // warps per CTA: about 16 resident warps per SM at 128 registers per thread
     const int ctasPerSm = (int)std::max<size_t>(1, std::min<size_t>(4, (size_t)(227 * 1024) / (smem + 1024)));
@@ -355,6 +356,62 @@ int me_frame_ex_dev(Ctx* ctx, const x265b200_me_frame_params* P, const x265b200_
     }
     ctx->launches++;
     return check(cudaGetLastError(), "me_frame_ex kernel launch");
+}
+
+int me_frame_ex_dev(Ctx* ctx, const x265b200_me_frame_params* P, const x265b200_me_frame_planes* pl, const int32_t* mvpCtu, const int32_t* mvpPu,
+                    const uint8_t* numCandPu, const int32_t* mvcPu, int32_t* out)
+{
+    return me_ctu_launch(ctx, P, pl, mvpCtu, mvpPu, numCandPu, mvcPu, out, 0, 0);
+}
+
+// ---- x265b200_me_frame_dev with per-CTU predictors ---------------------------------------------------------------------------
+// The 2Nx2N-only kernel of me_frame_kernels.cu reads every block from its staged window, which is only safe while the search
+// cannot leave it -- true for mvp = 0, not for arbitrary predictors (a zero-MV winner far from the window centre).  With
+// predictors the entry therefore runs on the general kernel (window test per block, plane fallback) with the entry's
+// unclipped range semantics, and its [ref][ctu][pu] results are re-ordered into the entry's level grids.
+__global__ void me_ctu_to_levels_kernel(const int32_t* in, int32_t* out, const MECtuPU* pus, int numPu, int ctuCols, int ctuRows, int numRefs,
+                                        int64_t off64, int64_t off32, int64_t off16, int64_t off8, int64_t perRef)
+{
+    const int64_t total = (int64_t)numRefs * ctuCols * ctuRows * numPu;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    {
+        const int pu = (int)(i % numPu);
+        const int64_t t = i / numPu;
+        const int ctu = (int)(t % (ctuCols * ctuRows)), ref = (int)(t / (ctuCols * ctuRows));
+        const MECtuPU u = pus[pu];
+        const int S = u.w, per = 64 / S;
+        const int64_t lo = S == 64 ? off64 : (S == 32 ? off32 : (S == 16 ? off16 : off8));
+        const int gx = (ctu % ctuCols) * per + u.x / S, gy = (ctu / ctuCols) * per + u.y / S;
+        int32_t* o = out + ((int64_t)ref * perRef + lo + (int64_t)gy * (ctuCols * per) + gx) * 3;
+        o[0] = in[3 * i]; o[1] = in[3 * i + 1]; o[2] = in[3 * i + 2];
+    }
+}
+
+int me_frame_general_2Nx2N(Ctx* ctx, int depth, const void* curOrigin, int64_t curStride, const void* const* refOriginsHost, int numRefs, int64_t refStride,
+                           int marginX, int marginY, int rowsTotal, int ctuCols, int ctuRows, int puMask, const int32_t* mvpCtu,
+                           int searchMethod, int subpelRefine, int merange, double lambda, int32_t* out)
+{
+    puMask &= 15;
+    if (!puMask) return 0;
+    x265b200_me_frame_params P; memset(&P, 0, sizeof(P));
+    P.depth = depth; P.ctuSize = 64; P.minCuSize = 8; P.ctuCols = ctuCols; P.ctuRows = ctuRows;
+    P.marginX = marginX; P.marginY = marginY; P.rowsTotal = rowsTotal; P.numRefs = numRefs;
+    P.searchMethod = searchMethod; P.subpelRefine = subpelRefine; P.merange = merange; P.maxSlices = 1; P.lambda = lambda;
+    x265b200_me_frame_planes pl; memset(&pl, 0, sizeof(pl));
+    pl.curY = curOrigin; pl.curStride = curStride; pl.refY = refOriginsHost; pl.refStride = refStride;
+    MECtuTables T;
+    if (mc_tables(ctx, 64, 8, 0, 0, 0, 0, puMask, T)) return -1;
+    void* tmp = nullptr;
+    if (scratch_dev(ctx, 6, (size_t)numRefs * ctuCols * ctuRows * T.numPu * 12, &tmp)) return -1;
+    if (me_ctu_launch(ctx, &P, &pl, mvpCtu, nullptr, nullptr, nullptr, (int32_t*)tmp, 1, puMask)) return -1;
+    int64_t off[4], o = 0;
+    for (int l = 0; l < 4; l++) { off[l] = o; if (puMask & (1 << l)) o += (int64_t)ctuCols * ctuRows * (1 << l) * (1 << l); }
+    const int64_t total = (int64_t)numRefs * ctuCols * ctuRows * T.numPu;
+    const unsigned blocks = (unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)ctx->smCount * 8);
+    me_ctu_to_levels_kernel<<<blocks, 256, 0, ctx->stream>>>((const int32_t*)tmp, out, (const MECtuPU*)T.dPus, T.numPu, ctuCols, ctuRows, numRefs,
+                                                              off[0], off[1], off[2], off[3], o);
+    ctx->launches++;
+    return check(cudaGetLastError(), "me_frame level re-order launch");
 }
 
 } // namespace x265b200

@@ -48,12 +48,15 @@ inline void me_ctu_add_pu(std::vector<MECtuPU>& v, int cuX, int cuY, int S, int 
 }
 
 // csp: 0 = luma only, 1 = 4:2:0, 2 = 4:2:2, 3 = 4:4:4 (x265.h:588-592)
-inline void me_ctu_build_pus(int ctuSize, int minCu, bool rect, bool amp, int csp, std::vector<MECtuPU>& v)
+// sizeMask: bit k set = CUs of size 64 >> k are searched (0 = all sizes from ctuSize down to minCu)
+inline void me_ctu_build_pus(int ctuSize, int minCu, bool rect, bool amp, int csp, std::vector<MECtuPU>& v, int sizeMask = 0)
 {
     const int hs = (csp == 1 || csp == 2) ? 1 : 0, vs = csp == 1 ? 1 : 0;
     const bool ch = csp != 0;
     v.clear();
     for (int S = ctuSize; S >= minCu; S >>= 1)
+    {
+        if (sizeMask && !(sizeMask & (64 / S))) continue;
         for (int cy = 0; cy < ctuSize; cy += S)
             for (int cx = 0; cx < ctuSize; cx += S)
             {
@@ -77,6 +80,7 @@ inline void me_ctu_build_pus(int ctuSize, int minCu, bool rect, bool amp, int cs
                     me_ctu_add_pu(v, cx, cy, S, 3 * S / 4, 0, S / 4, S, hs, vs, ch);
                 }
             }
+    }
 }
 
 // Lanes of one PU.  A lane owns a sub-block 8 (or, for the 4-wide remainder of 4- and 12-wide PUs, 4) pixels wide and a
@@ -120,9 +124,9 @@ inline int me_ctu_split_pu(const MECtuPU& pu, bool chromaSatd, int vshift, MECtu
     return G;
 }
 
-inline void me_ctu_build_layout(int ctuSize, int minCu, bool rect, bool amp, int csp, bool chromaSatd, MECtuLayout& L)
+inline void me_ctu_build_layout(int ctuSize, int minCu, bool rect, bool amp, int csp, bool chromaSatd, MECtuLayout& L, int sizeMask = 0)
 {
-    me_ctu_build_pus(ctuSize, minCu, rect, amp, csp, L.pus);
+    me_ctu_build_pus(ctuSize, minCu, rect, amp, csp, L.pus, sizeMask);
     const int vs = csp == 1 ? 1 : 0;
     struct Grp { int pu, G, work; MECtuSub sub[32]; };
     std::vector<Grp> groups(L.pus.size());

@@ -220,7 +220,7 @@ template<int NW> __device__ __forceinline__ void lds_words(uint32_t a, uint32_t 
 
 template<typename pixel> __device__ __forceinline__ uint32_t sad_word(uint32_t a, uint32_t b);
 template<> __device__ __forceinline__ uint32_t sad_word<uint8_t>(uint32_t a, uint32_t b) { return __vsadu4(a, b); }
-template<> __device__ __forceinline__ uint32_t sad_word<uint16_t>(uint32_t a, uint32_t b) { return __vsadu2(a, b); }
+template<> __device__ __forceinline__ uint32_t sad_word<uint16_t>(uint32_t a, uint32_t b) { return sad_u16x2(a, b); }      // common.cuh: 4 native instructions
 
 // SAD of one SEG-pixel row segment: fenc in smem (aligned), ref anywhere
 template<typename pixel, int SEG>
@@ -410,13 +410,6 @@ __device__ __forceinline__ bool in_window(const MEState<pixel>& s, int mx, int m
 {
     return (mx >= s.winX0 + lt) & (mx <= s.winX1 - rb) & (my >= s.winY0 + lt) & (my <= s.winY1 - rb);
 }
-// one full-pel candidate of the lane's sub-block: from the window when the whole PU block is inside it, else from the plane
-template<typename pixel>
-__device__ __noinline__ int thread_sad_cand(const MEState<pixel>& s, int mx, int my)
-{
-    if (in_window(s, mx, my, 0, 0)) return thread_sad_any<pixel>(s, s.fref + mx + (int64_t)my * s.stride, s.stride);
-    return thread_sad_anyspace<pixel>(s, s.gfref + mx + (int64_t)my * s.gstride, s.gstride);
-}
 #endif
 // 4x4 Hadamard cost of d[i][k] = a - b rows already differenced: sum |H d H^T| >> 1
 __device__ __forceinline__ int satd_cell(int d[4][4])
@@ -524,24 +517,58 @@ __device__ __forceinline__ int thread_satd(const MEState<pixel>& s, const pixel*
 }
 
 #ifdef ME_WINDOW_CHECK
-// Frame-search form (me_ctu_kernels.cu): inlined into its callers so that the K candidate offsets stay in registers (as a
-// __noinline__ function taking ox[] / oy[] the arrays lived in local memory and every candidate began with two dependent
-// LDL -- 7 % of the stall samples of profiles/r02_me_frame_v11.txt); the per-candidate work is the call to thread_sad_cand.
-// The K partial SADs are then reduced over the PU's lanes together (K independent shuffles per butterfly round).
+// Frame-search form (me_ctu_kernels.cu): ONE out-of-line function costs the K (1..4) full-pel candidates of a search step.
+// The candidate offsets arrive packed in registers ((x & 0xffff) | (y << 16); as ox[] / oy[] arrays of a __noinline__ function
+// they lived in local memory and every candidate began with two dependent LDL -- 7 % of the stall samples of
+// profiles/r02_me_frame_v11.txt), each candidate is read from the staged window or, outside it, from the plane, the K partial
+// SADs are reduced over the PU's lanes together, and the MV cost of each candidate is added here -- every caller wants
+// SAD + mvcost, and the callers (hexSearch, squareRefine, starPattern ...) stay small enough for the instruction caches
+// (inlined, this code made them 5-13 KB each and stall_no_instruction rose from 0.23 to 1.75 per issue,
+// profiles/r02_me_ctu_v1.txt).
+__device__ __forceinline__ uint32_t pack_cand(int x, int y) { return ((uint32_t)x & 0xffffu) | ((uint32_t)y << 16); }
 template<typename pixel>
-__device__ __forceinline__ void warp_sad_k(const MEState<pixel>& s, int K, const int ox[4], const int oy[4], int costs[4])
+__device__ __noinline__ int4 thread_cand_costs(const MEState<pixel>& s, int K, uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3, bool addMvCost)
 {
     int part[4] = { 0, 0, 0, 0 };
+#pragma unroll 1
+    for (int k = 0; k < K; k++)
+    {
+        const uint32_t pk = k == 0 ? p0 : (k == 1 ? p1 : (k == 2 ? p2 : p3));
+        const int mx = (int)(int16_t)(pk & 0xffffu), my = (int)pk >> 16;
+        int v;
+        if (in_window(s, mx, my, 0, 0)) v = thread_sad_any<pixel>(s, s.fref + mx + (int64_t)my * s.stride, s.stride);
+        else v = thread_sad_anyspace<pixel>(s, s.gfref + mx + (int64_t)my * s.gstride, s.gstride);
 #pragma unroll
-    for (int k = 0; k < 4; k++)
-        if (k < K) part[k] = thread_sad_cand<pixel>(s, ox[k], oy[k]);
+        for (int j = 0; j < 4; j++) part[j] = j == k ? v : part[j];      // stays in registers (no dynamic indexing)
+    }
     for (int o = 1; o < s.groupSize; o <<= 1)
     {
 #pragma unroll
         for (int k = 0; k < 4; k++) part[k] += __shfl_xor_sync(s.groupMask, part[k], o);
     }
+    if (addMvCost)
+    {
+#pragma unroll 1
+        for (int k = 0; k < K; k++)
+        {
+            const uint32_t pk = k == 0 ? p0 : (k == 1 ? p1 : (k == 2 ? p2 : p3));
+            const int c = mvcost(s, (int)(int16_t)(pk & 0xffffu) << 2, ((int)pk >> 16) << 2);
 #pragma unroll
-    for (int k = 0; k < 4; k++) if (k < K) costs[k] = part[k];
+            for (int j = 0; j < 4; j++) part[j] += j == k ? c : 0;
+        }
+    }
+    return make_int4(part[0], part[1], part[2], part[3]);
+}
+// the array form the search code uses; addMvCost = false leaves the plain SADs
+template<typename pixel>
+__device__ __forceinline__ void warp_sad_k(const MEState<pixel>& s, int K, const int ox[4], const int oy[4], int costs[4], bool addMvCost = false)
+{
+    const int4 c = thread_cand_costs<pixel>(s, K, pack_cand(ox[0], oy[0]), K > 1 ? pack_cand(ox[1], oy[1]) : 0u, K > 2 ? pack_cand(ox[2], oy[2]) : 0u,
+                                            K > 3 ? pack_cand(ox[3], oy[3]) : 0u, addMvCost);
+    costs[0] = c.x;
+    if (K > 1) costs[1] = c.y;
+    if (K > 2) costs[2] = c.z;
+    if (K > 3) costs[3] = c.w;
 }
 #else
 template<typename pixel>
@@ -1660,13 +1687,31 @@ struct MESearch
         return c[0];
     }
     __device__ __forceinline__ int fcost(int mx, int my) const { return mvcost(s, mx << 2, my << 2); }
+    // SAD + mvcost of one / K full-pel candidates (COST_MV's and COST_MV_X4's operands, motion.cpp:238-298)
+    __device__ __forceinline__ int costAt(int mx, int my) const
+    {
+#ifdef ME_WINDOW_CHECK
+        return thread_cand_costs<pixel>(s, 1, pack_cand(mx, my), 0u, 0u, 0u, true).x;
+#else
+        return sadAt(mx, my) + fcost(mx, my);
+#endif
+    }
+    __device__ __forceinline__ void candCosts(int K, const int ox[4], const int oy[4], int costs[4]) const
+    {
+#ifdef ME_WINDOW_CHECK
+        warp_sad_k<pixel>(s, K, ox, oy, costs, true);
+#else
+        warp_sad_k<pixel>(s, K, ox, oy, costs);
+        for (int k = 0; k < K; k++) costs[k] += fcost(ox[k], oy[k]);
+#endif
+    }
     __device__ __forceinline__ bool inRange(int x, int y) const { return x >= mvmin.x && x <= mvmax.x && y >= mvmin.y && y <= mvmax.y; }
     __device__ __forceinline__ bool yOk(int y) const { return (y >= mvmin.y) & (y <= mvmax.y); }
 
     // COST_MV (motion.cpp:238-244)
     __device__ __noinline__ void costMv(int mx, int my)
     {
-        int cost = sadAt(mx, my) + fcost(mx, my);
+        int cost = costAt(mx, my);
         if (cost < bcost) { bcost = cost; bmv = mv2(mx, my); }
     }
     // COST_MV_X4 (motion.cpp:277-298): only the y range is checked (quirk)
@@ -1676,9 +1721,7 @@ struct MESearch
         int costs[4], ox[4], oy[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) { ox[k] = omv.x + dx[k]; oy[k] = omv.y + dy[k]; }
-        warp_sad_k<pixel>(s, 4, ox, oy, costs);
-#pragma unroll
-        for (int k = 0; k < 4; k++) costs[k] += fcost(ox[k], oy[k]);
+        candCosts(4, ox, oy, costs);
 #pragma unroll
         for (int k = 0; k < 4; k++)
             if (yOk(omv.y + dy[k]) && costs[k] < bcost) { bcost = costs[k]; bmv = mv2(omv.x + dx[k], omv.y + dy[k]); }
@@ -1688,8 +1731,7 @@ struct MESearch
     {
         int ox[4] = { 0, 0, 0, 0 }, oy[4] = { 0, 0, 0, 0 };
         for (int k = 0; k < n; k++) { ox[k] = bmv.x + dx[k]; oy[k] = bmv.y + dy[k]; }
-        warp_sad_k<pixel>(s, n, ox, oy, costs);
-        for (int k = 0; k < n; k++) costs[k] += fcost(ox[k], oy[k]);
+        candCosts(n, ox, oy, costs);
     }
     // CROSS (motion.cpp:336-360)
     __device__ __noinline__ void cross(MV2 omv, int start, int x_max, int y_max)
@@ -1715,7 +1757,7 @@ struct MESearch
     // COST_MV_PT_DIST (motion.cpp:224-236)
     __device__ __noinline__ void ptDist(int mx, int my, int point, int dist, int& bPointNr, int& bDistance)
     {
-        int cost = sadAt(mx, my) + fcost(mx, my);
+        int cost = costAt(mx, my);
         if (cost < bcost) { bcost = cost; bmv = mv2(mx, my); bPointNr = point; bDistance = dist; }
     }
 
@@ -2065,7 +2107,7 @@ __device__ int motion_estimate(const MEState<pixel>& s, MV2 mvmin, MV2 mvmax, MV
     S.bmv = mv2((pmv.x + 2) >> 2, (pmv.y + 2) >> 2);
     S.bcost = bprecost;
     if ((pmv.x | pmv.y) & 3)
-        S.bcost = S.sadAt(S.bmv.x, S.bmv.y) + S.fcost(S.bmv.x, S.bmv.y);
+        S.bcost = S.costAt(S.bmv.x, S.bmv.y);
 
     // refineMV (:606-737) measures neither the zero MV nor candidates: predictor, square refine, workload[5] subpel
     const bool refineOnly = searchMethod == ME_REFINE;
@@ -2075,7 +2117,7 @@ __device__ int motion_estimate(const MEState<pixel>& s, MV2 mvmin, MV2 mvmax, MV
     if ((pmv.x | pmv.y) && !refineOnly)
     {
 #if defined(ME_WINDOW_CHECK)
-        int cost = S.sadAt(0, 0) + mvcost(s, 0, 0);            // the window test of every candidate covers it
+        int cost = S.costAt(0, 0);                             // the window test of every candidate covers it
 #elif defined(ME_REF_IN_SMEM)
         // the zero-MV block may lie outside the staged window: read it from the global plane
         int cost = group_sum<pixel>(s, thread_sad_anyspace<pixel>(s, s.gfref, s.gstride)) + mvcost(s, 0, 0);
@@ -2211,7 +2253,7 @@ __device__ int motion_estimate(const MEState<pixel>& s, MV2 mvmin, MV2 mvmax, MV
                 {
                     int hx = c_hex4[k][0], hy = c_hex4[k][1];
                     int mx = omv.x + hx * i, my = omv.y + hy * i;
-                    int cost = S.sadAt(mx, my) + S.fcost(mx, my);
+                    int cost = S.costAt(mx, my);
                     // MIN_MV checks the UNSCALED dy (quirk, :1078)
                     if (S.yOk(omv.y + hy) && cost < S.bcost) { S.bcost = cost; dir = hx * 16 + (hy & 15); }
                 }

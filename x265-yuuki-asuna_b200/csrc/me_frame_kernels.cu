@@ -40,6 +40,9 @@ namespace x265b200 {
 
 int scratch_dev(Ctx* ctx, int slot, size_t bytes, void** out);
 int ensure_mvcost(Ctx* ctx, double lambda);
+int me_frame_general_2Nx2N(Ctx* ctx, int depth, const void* curOrigin, int64_t curStride, const void* const* refOriginsHost, int numRefs, int64_t refStride,
+                           int marginX, int marginY, int rowsTotal, int ctuCols, int ctuRows, int puMask, const int32_t* mvpCtu,
+                           int searchMethod, int subpelRefine, int merange, double lambda, int32_t* out);
 
 constexpr int MF_MAX_REFS = 6;
 // TMA descriptors travel as a __grid_constant__ kernel parameter (the canonical, fence-free way)
@@ -224,6 +227,13 @@ int me_frame_dev(Ctx* ctx, int depth, const void* curOrigin, int64_t curStride, 
     if (numRefs <= 0 || ctuCols <= 0 || ctuRows <= 0) return 0;
     if (searchMethod == ME_SEA || searchMethod < 0 || searchMethod > ME_FULL) { set_error("me_frame: searchMethod %d unsupported", searchMethod); return -1; }
     if (subpelRefine < 0 || subpelRefine > 7) { set_error("me_frame: subpelRefine %d", subpelRefine); return -1; }
+    // This kernel reads every reference block from its staged window.  That is safe exactly when no search can leave the
+    // window: predictor 0 (then the zero-MV candidate IS the predictor, and the patterns stay within merange + 3).  With per-CTU
+    // predictors a zero-MV winner can sit anywhere, so those calls run on the general kernel, which tests every block against
+    // its window and falls back to the plane (me_ctu_kernels.cu); same results, same output order.
+    if (mvpCtu)
+        return me_frame_general_2Nx2N(ctx, depth, curOrigin, curStride, refOriginsHost, numRefs, refStride, marginX, marginY, rowsTotal, ctuCols, ctuRows,
+                                      puMask, mvpCtu, searchMethod, subpelRefine, merange, lambda, out);
     const int px = depth > 8 ? 2 : 1;
     const int R = merange + 8;
     int winW = 64 + 2 * R + (16 / px - 1);            // + slack for the 16-byte alignment of the TMA box start
