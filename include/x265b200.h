@@ -2,11 +2,15 @@
  *
  * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.
  * Each entry point names the reference interface it replaces (file:line under
- * /root/reference/source).  Two flavours exist for every family:
- *   *_dev  : all pointers are DEVICE pointers; asynchronous on the context's stream.
- *   *_host : all pointers are HOST pointers; the call stages H2D, runs the same kernel and
- *            copies results back before returning (this is what the pointer-compatible
- *            EncoderPrimitives slots and the end-to-end bench use).
+ * /root/reference/source).  Two flavours of entry point:
+ *   *_dev  : all pointers are DEVICE pointers; asynchronous on the context's stream.  Every family has it.
+ *   *_host : HOST buffers in and out; the call stages H2D, runs the same kernel and copies the results back before
+ *            returning.  Provided where a caller hands over host memory per call: the block compares
+ *            (x265b200_pixelcmp_host) and the frame searches (x265b200_me_frame_host / x265b200_me_frame_ex_host: the new
+ *            source picture comes from the host, the reference pictures stay resident on the device like a decoded-picture
+ *            buffer, the {mv, cost} results return to the host) -- the latter are what bench.py's end-to-end number goes
+ *            through.  The pointer-compatible EncoderPrimitives slots (adapter/) stage their operands with
+ *            x265b200_upload / x265b200_download around the *_dev entries.
  * Return value: 0 on success, negative on error (message via x265b200_last_error()).
  * There is NO CPU fallback anywhere in this library: without a CUDA device every compute
  * entry point fails loudly.
@@ -432,6 +436,23 @@ typedef struct
 } x265b200_me_frame_planes;
 int x265b200_me_frame_ex_dev(x265b200_ctx* ctx, const x265b200_me_frame_params* params, const x265b200_me_frame_planes* planes,
                              const int32_t* mvpCtu, const int32_t* mvpPu, const uint8_t* numCandPu, const int32_t* mvcPu, int32_t* out);
+/* Host-buffer forms of the two frame searches (the end-to-end path): the source picture arrives from HOST memory -- hostCurBase
+ * points at the first byte of the padded plane (origin - marginY*stride - marginX), planeBytes bytes are copied to devCurBase
+ * (caller-owned device plane of the same layout: it becomes a reference picture later) --, the search runs against the
+ * device-resident references, and the {mvx, mvy, cost} records are copied to hostOut (outBytes; pinned memory makes both copies
+ * DMA transfers).  Synchronous: returns when hostOut is complete.  devOut is the caller's device result buffer (same layout). */
+int x265b200_me_frame_host(x265b200_ctx* ctx, int depth, const void* hostCurBase, size_t planeBytes, void* devCurBase, int64_t curStride,
+                           const void* const* refOriginsHost, int numRefs, int64_t refStride,
+                           int marginX, int marginY, int rowsTotal, int ctuCols, int ctuRows, int puMask,
+                           const int32_t* mvpCtu, int searchMethod, int subpelRefine, int merange, double lambda,
+                           int32_t* devOut, int32_t* hostOut, size_t outBytes);
+/* planes->curY / curCb / curCr are the device ORIGINS as in x265b200_me_frame_ex_dev; hostCur*Base / devCur*Base the padded
+ * planes' first bytes (Cb / Cr may be NULL when params->csp == 0 or subpelRefine <= 2). */
+int x265b200_me_frame_ex_host(x265b200_ctx* ctx, const x265b200_me_frame_params* params, const x265b200_me_frame_planes* planes,
+                              const void* hostCurYBase, void* devCurYBase, size_t bytesY,
+                              const void* hostCurCbBase, void* devCurCbBase, const void* hostCurCrBase, void* devCurCrBase, size_t bytesC,
+                              const int32_t* mvpCtu, const int32_t* mvpPu, const uint8_t* numCandPu, const int32_t* mvcPu,
+                              int32_t* devOut, int32_t* hostOut, size_t outBytes);
 /* The PUs of one CTU in the order x265b200_me_frame_ex_dev uses: {x, y, w, h} inside the CTU, CU sizes from ctuSize down to
  * minCuSize, CUs in raster order, per CU the part modes in PartSize order (2Nx2N, 2NxN, Nx2N, 2NxnU, 2NxnD, nLx2N, nRx2N;
  * common/cudata.h).  Writes at most cap entries; returns the number of PUs (host side, no GPU needed), -1 on bad arguments. */
@@ -449,8 +470,11 @@ double x265b200_lambda(int qp, int depth);
  * x265b200_la_intra_dev: replaces LookaheadTLD::lowresIntraEstimate (slicetype.cpp:696-805) for one
  *   frame.  intraPenalty = 5 * (int)x265_lambda_tab[X265_LOOKAHEAD_QP].  sums[2] = costEst, costEstAq.
  * x265b200_la_estimate_dev: replaces CostEstimateGroup::estimateFrameCost / estimateCUCost
- *   (slicetype.cpp:3115-3388; non-cooperative path, weightp off, HME off) for a batch of frame
- *   triples.  `planes` = device array [numFrames][4] of plane origins; MVs and MV costs of list i live
+ *   (slicetype.cpp:3115-3388; weightp off, HME off) for a batch of frame triples.  lookaheadSlices = the effective
+ *   --lookahead-slices (param.cpp:173 default 8 at medium; 0 or 1 = the non-cooperative path): the field is cut into
+ *   cooperative slices as Lookahead::create does (slicetype.cpp:1029-1041: heightInCU / slices rows each, at least 10; the
+ *   last slice runs to the bottom) and the bottom row of every slice is searched with lastRow = true (processTasks,
+ *   slicetype.cpp:3079-3107) -- bit-exact with the reference's coop-slice path, and the slices are independent wavefronts.  `planes` = device array [numFrames][4] of plane origins; MVs and MV costs of list i live
  *   in slot mvSlot[i] of mvPool ([slot][ncu][2] int32) / mvCostPool ([slot][ncu] int32) -- the
  *   reference's lowresMvs[i][dist] / lowresMvCosts[i][dist] cache; doSearch[i] = 0 reuses the slot.
  *   Outputs per triple t: lowresCosts[t][ncu] (uint16), rowSatds[t][heightInCU], sums[t][4] =
@@ -469,7 +493,7 @@ int x265b200_la_estimate_dev(x265b200_ctx* ctx, int depth, const void* const* pl
                              int widthInCU, int heightInCU, const x265b200_la_triple* triplesHost, int numTriples,
                              int32_t* mvPool, int32_t* mvCostPool, const int32_t* const* intraCost,
                              const int32_t* const* invQscale, uint16_t* lowresCosts, int32_t* rowSatds, int32_t* sums,
-                             double lambda, int maxSlices);
+                             double lambda, int lookaheadSlices);
 
 /* --hme (hierarchical ME, param bEnableHME): estimateFrameCost first runs estimateCUCost(..., hme = true) over the
  * quarter-resolution planes (Lowres::lowerResPlane[4], built by primitives.frameInitLowerRes + extendPicBorder,
@@ -489,7 +513,7 @@ typedef struct {
 int x265b200_la_estimate_hme_dev(x265b200_ctx* ctx, int depth, const void* const* planes, int64_t stride, int widthInCU, int heightInCU,
                                  const x265b200_la_hme* hme, const x265b200_la_triple* triplesHost, int numTriples, int32_t* mvPool, int32_t* mvCostPool,
                                  const int32_t* const* intraCost, const int32_t* const* invQscale, uint16_t* lowresCosts,
-                                 int32_t* rowSatds, int32_t* sums, double lambda, int maxSlices);
+                                 int32_t* rowSatds, int32_t* sums, double lambda, int lookaheadSlices);
 
 #ifdef __cplusplus
 }

@@ -500,6 +500,51 @@ int64_t ref_la_frame_cost(void* hv, int p0, int p1, int b, int intraPenalty)
     CostEstimateGroup est(*h->la, h->framePtrs.data());
     return est.singleCost(p0, p1, b, !!intraPenalty);
 }
+/* The cooperative-slice path of estimateFrameCost (slicetype.cpp:3143-3175), which the reference only takes with a thread pool:
+ * the slice geometry is set as Lookahead::create sets it (slicetype.cpp:1029-1041), the Coop job is posted as :3150-3160 post it,
+ * and the reference's own processTasks (:3049-3113, non-batch branch) runs every slice on this thread -- the same
+ * estimateCUCost calls with the same lastRow / slice arguments the pool workers would make, in slice order.  The per-slice sums
+ * are then folded as :3166-3173 and the frame score scaled as :3201-3206.  lookaheadSlices is the value the CLI would pass. */
+int64_t ref_la_frame_cost_slices(void* hv, int p0, int p1, int b, int lookaheadSlices)
+{
+    RefLA* h = (RefLA*)hv;
+    Lookahead& la = *h->la;
+    if (lookaheadSlices > 1)
+    {
+        la.m_numRowsPerSlice = la.m_8x8Height / lookaheadSlices;
+        la.m_numRowsPerSlice = X265_MAX(la.m_numRowsPerSlice, 10);
+        la.m_numRowsPerSlice = X265_MIN(la.m_numRowsPerSlice, la.m_8x8Height);
+        la.m_numCoopSlices = la.m_8x8Height / la.m_numRowsPerSlice;
+    }
+    else { la.m_numRowsPerSlice = la.m_8x8Height; la.m_numCoopSlices = 1; }
+    h->param->lookaheadSlices = la.m_numCoopSlices;            /* the HME branch of processTasks divides by it */
+    CostEstimateGroup est(la, h->framePtrs.data());
+    if (la.m_numCoopSlices <= 1) return est.singleCost(p0, p1, b, false);
+    Lowres* fenc = h->lowres[b];
+    bool doSearch[2];
+    doSearch[0] = fenc->lowresMvs[0][b - p0][0].x == 0x7FFF;
+    doSearch[1] = p1 > b && fenc->lowresMvs[1][p1 - b][0].x == 0x7FFF;
+    fenc->weightedRef[b - p0].isWeighted = false;
+    fenc->costEst[b - p0][p1 - b] = 0;
+    fenc->costEstAq[b - p0][p1 - b] = 0;
+    memset(&est.m_slice, 0, sizeof(est.m_slice[0]) * la.m_numCoopSlices);
+    est.m_coop.p0 = p0; est.m_coop.p1 = p1; est.m_coop.b = b;
+    est.m_coop.bDoSearch[0] = doSearch[0]; est.m_coop.bDoSearch[1] = doSearch[1];
+    est.m_jobTotal = la.m_numCoopSlices; est.m_jobAcquired = 0;
+    static_cast<BondedTaskGroup&>(est).processTasks(-1);
+    for (int i = 0; i < la.m_numCoopSlices; i++)
+    {
+        fenc->costEst[b - p0][p1 - b] += est.m_slice[i].costEst;
+        fenc->costEstAq[b - p0][p1 - b] += est.m_slice[i].costEstAq;
+        if (p1 == b) fenc->intraMbs[b - p0] += est.m_slice[i].intraMbs;
+    }
+    int64_t score = fenc->costEst[b - p0][p1 - b];
+    if (b != p1) score = score * 100 / (130 + h->param->bFrameBias);
+    fenc->costEst[b - p0][p1 - b] = score;
+    est.m_jobTotal = est.m_jobAcquired = 0;
+    return score;
+}
+int ref_la_num_coop_slices(void* hv) { return ((RefLA*)hv)->la->m_numCoopSlices; }
 /* outputs cached on frame b (common/lowres.h) */
 const int32_t* ref_la_mvs(void* hv, int b, int list, int dist) { return (const int32_t*)((RefLA*)hv)->lowres[b]->lowresMvs[list][dist]; }
 const int32_t* ref_la_mvcosts(void* hv, int b, int list, int dist) { return ((RefLA*)hv)->lowres[b]->lowresMvCosts[list][dist]; }

@@ -45,6 +45,9 @@ dMv, dMvC = ctx.to_device(np.zeros(nslots * ncu * 2, dtype=np.int32)), ctx.to_de
 def slot(b, lst, dist): return (b * 2 + lst) * (BF + 2) + dist
 # every (b, list, dist <= BF+1) search that exists among NF frames, issued as B-triples (p0, p1, b) with 2 new searches each
 allt = [(b - dd, b + dd, b) for dd in range(1, BF + 2) for b in range(NF) if b - dd >= 0 and b + dd < NF]
+import sys
+SLICES = int(sys.argv[1]) if len(sys.argv) > 1 else 0          # --lookahead-slices (0 = non-cooperative path)
+print("lookahead slices:", SLICES)
 for k in (1, 4, 8, 16, 24, 32, len(allt)):
     wave = allt[:k]
     tr = np.zeros(len(wave), dtype=pkg.LA_TRIPLE)
@@ -54,6 +57,6 @@ for k in (1, 4, 8, 16, 24, 32, len(allt)):
             tr[t]["mvSlot"][lst] = slot(b, lst, dist)
             tr[t]["doSearch"][lst] = 1
     dLC, dRS, dSm = ctx.empty(len(wave) * ncu * 2), ctx.empty(len(wave) * hcu * 4), ctx.empty(len(wave) * 16)
-    ms = timeit(lambda: ctx.la_estimate_dev(8, dPlanePtrs, ls, wcu, hcu, tr, dMv, dMvC, dIntraPtrs, None, dLC, dRS, dSm, lam), reps=2)
+    ms = timeit(lambda: ctx.la_estimate_dev(8, dPlanePtrs, ls, wcu, hcu, tr, dMv, dMvC, dIntraPtrs, None, dLC, dRS, dSm, lam, lookaheadSlices=SLICES), reps=2)
     ns = 2 * len(wave)
     print("la_estimate  %3d triples = %3d list searches: %8.3f ms  (%.3f ms per search of %d CUs)" % (len(wave), ns, ms, ms / ns, ncu))

@@ -19,6 +19,7 @@ pytestmark = pytest.mark.gpu
 def _bind(R):
     R.ref_la_create.restype = ctypes.c_void_p
     R.ref_la_frame_cost.restype = ctypes.c_int64
+    R.ref_la_frame_cost_slices.restype = ctypes.c_int64
     R.ref_la_cost_est.restype = ctypes.c_int64
     for f in ("ref_la_mvs", "ref_la_mvcosts", "ref_la_lowres_costs", "ref_la_row_satds", "ref_la_intra_cost", "ref_la_intra_mode",
               "ref_la_fullres_buffer", "ref_la_lowres_buffer", "ref_la_inv_qscale"):
@@ -48,8 +49,11 @@ def _frames(W, H, n, depth, seed):
     return out
 
 
-@pytest.mark.parametrize("depth,W,H,aq", [(8, 320, 192, 0), (8, 416, 240, 1), (10, 320, 192, 1)])
-def test_lookahead_matches_reference(ctx, depth, W, H, aq):
+@pytest.mark.parametrize("depth,W,H,aq,slices", [(8, 320, 192, 0, 0), (8, 416, 240, 1, 0), (10, 320, 192, 1, 0),
+                                                   # --lookahead-slices (coop slices, slicetype.cpp:3079-3107): 4 slices of 11 rows; 8 asked -> 6 of 10
+                                                   # rows (+ a last one of 18); 2 slices of 34 rows (two 32-row bands per slice)
+                                                   (8, 320, 704, 0, 4), (8, 256, 1088, 1, 8), (8, 256, 1088, 0, 2), (10, 320, 704, 1, 4)])
+def test_lookahead_matches_reference(ctx, depth, W, H, aq, slices):
     R = oracle.ref(depth)
     assert R is not None, "oracle/_ref missing"
     _bind(R)
@@ -134,9 +138,13 @@ def test_lookahead_matches_reference(ctx, depth, W, H, aq):
                 tr[t]["doSearch"][lst] = int(need)
                 if need:
                     searched.add(key)
-            R.ref_la_frame_cost(h, p0, p1, b, 0)
+            if slices:
+                R.ref_la_frame_cost_slices(h, p0, p1, b, slices)      # the reference's processTasks runs every coop slice
+            else:
+                R.ref_la_frame_cost(h, p0, p1, b, 0)
         dLC, dRS, dSm = ctx.empty(len(wave) * ncu * 2), ctx.empty(len(wave) * hcu * 4), ctx.empty(len(wave) * 16)
-        ctx.la_estimate_dev(depth, dPlanePtrs, ls, wcu, hcu, tr, dMv, dMvC, dIntraPtrs, dInvQPtrs if aq else None, dLC, dRS, dSm, lam)
+        ctx.la_estimate_dev(depth, dPlanePtrs, ls, wcu, hcu, tr, dMv, dMvC, dIntraPtrs, dInvQPtrs if aq else None, dLC, dRS, dSm, lam,
+                            lookaheadSlices=slices)
         lc = dLC.download(np.uint16).reshape(len(wave), ncu)
         rs = dRS.download(np.int32).reshape(len(wave), hcu)
         sm = dSm.download(np.int32).reshape(len(wave), 4)
@@ -163,6 +171,8 @@ def test_lookahead_matches_reference(ctx, depth, W, H, aq):
                 assert int(sm[t][2]) == R.ref_la_intra_mbs(h, b, b - p0), ("intraMbs", wave[t])
         for bb in (dLC, dRS, dSm):
             bb.free()
+    if slices:
+        assert R.ref_la_num_coop_slices(h) == {4: 4, 8: 6, 2: 2}[slices]
     R.ref_la_destroy(h)
 
 

@@ -364,11 +364,11 @@ def _ctx_la_intra_dev(self, depth, dPlane0, stride, wcu, hcu, dInvQ, intraPenalt
 
 
 def _ctx_la_estimate_dev(self, depth, dPlanes, stride, wcu, hcu, triples, dMvPool, dMvCostPool, dIntraCostPtrs, dInvQPtrs,
-                         dLowresCosts, dRowSatds, dSums, lam, maxSlices=1):
+                         dLowresCosts, dRowSatds, dSums, lam, lookaheadSlices=0):
     triples = np.ascontiguousarray(triples, dtype=LA_TRIPLE)
     self._chk(self.L.x265b200_la_estimate_dev(self.h, depth, _vp(dPlanes), _i64(stride), int(wcu), int(hcu), _vp(triples), len(triples),
                                               _vp(dMvPool), _vp(dMvCostPool), _vp(dIntraCostPtrs), _vp(dInvQPtrs), _vp(dLowresCosts),
-                                              _vp(dRowSatds), _vp(dSums), ctypes.c_double(lam), int(maxSlices)))
+                                              _vp(dRowSatds), _vp(dSums), ctypes.c_double(lam), int(lookaheadSlices)))
 
 
 Ctx.lowres_init_dev = _ctx_lowres_init_dev
@@ -436,6 +436,14 @@ def _ctx_me_frame_ex_dev(self, params, curY, curStride, refY, refStride, dOut, d
                          curC=None, curStrideC=0, refCb=None, refCr=None, refStrideC=0):
     """params: dict of x265b200_me_frame_params fields (lambda under 'lambda'); curY / curC = device addresses of plane origins;
     refY / refCb / refCr = lists of device addresses."""
+    P, pl, _keep = _me_frame_structs(params, curY, curStride, refY, refStride, curC, curStrideC, refCb, refCr, refStrideC)
+    self._chk(self.L.x265b200_me_frame_ex_dev(self.h, ctypes.byref(P), ctypes.byref(pl), _vp(dMvpCtu), _vp(dMvpPu), _vp(dNumCand), _vp(dMvc), _vp(dOut)))
+
+
+Ctx.me_frame_ex_dev = _ctx_me_frame_ex_dev
+
+
+def _me_frame_structs(params, curY, curStride, refY, refStride, curC, curStrideC, refCb, refCr, refStrideC):
     P = ME_FRAME_PARAMS()
     for k, v in params.items():
         setattr(P, "lambda_" if k == "lambda" else k, v)
@@ -448,10 +456,34 @@ def _ctx_me_frame_ex_dev(self, params, curY, curStride, refY, refStride, dOut, d
     pl.refCb = ctypes.cast(arrs[1], ctypes.POINTER(ctypes.c_void_p)) if arrs[1] is not None else None
     pl.refCr = ctypes.cast(arrs[2], ctypes.POINTER(ctypes.c_void_p)) if arrs[2] is not None else None
     pl.refStride = int(refStride); pl.refStrideC = int(refStrideC)
-    self._chk(self.L.x265b200_me_frame_ex_dev(self.h, ctypes.byref(P), ctypes.byref(pl), _vp(dMvpCtu), _vp(dMvpPu), _vp(dNumCand), _vp(dMvc), _vp(dOut)))
+    return P, pl, arrs
 
 
-Ctx.me_frame_ex_dev = _ctx_me_frame_ex_dev
+def _ctx_me_frame_ex_host(self, params, curY, curStride, refY, refStride, hostY, devYBase, bytesY, devOut, hostOut, outBytes,
+                          dMvpCtu=None, dMvpPu=None, dNumCand=None, dMvc=None, curC=None, curStrideC=0, refCb=None, refCr=None, refStrideC=0,
+                          hostC=None, devCBase=None, bytesC=0):
+    """x265b200_me_frame_ex_host: hostY / hostC = host addresses of the padded planes (hostC = (Cb, Cr) or None), devYBase / devCBase
+    their device destinations; hostOut = host address of the result buffer."""
+    P, pl, _keep = _me_frame_structs(params, curY, curStride, refY, refStride, curC, curStrideC, refCb, refCr, refStrideC)
+    hc = hostC if hostC is not None else (None, None)
+    dc = devCBase if devCBase is not None else (None, None)
+    self._chk(self.L.x265b200_me_frame_ex_host(self.h, ctypes.byref(P), ctypes.byref(pl), _vp(hostY), _vp(devYBase), ctypes.c_size_t(bytesY),
+                                               _vp(hc[0]), _vp(dc[0]), _vp(hc[1]), _vp(dc[1]), ctypes.c_size_t(bytesC),
+                                               _vp(dMvpCtu), _vp(dMvpPu), _vp(dNumCand), _vp(dMvc), _vp(devOut), _vp(hostOut), ctypes.c_size_t(outBytes)))
+
+
+Ctx.me_frame_ex_host = _ctx_me_frame_ex_host
+
+
+def _ctx_me_frame_host(self, depth, hostCurBase, planeBytes, devCurBase, curStride, refOrigins, refStride, marginX, marginY, rowsTotal, ctuCols, ctuRows,
+                       puMask, dMvpCtu, searchMethod, subpelRefine, merange, lam, devOut, hostOut, outBytes):
+    arr = (ctypes.c_void_p * len(refOrigins))(*[int(p) for p in refOrigins])
+    self._chk(self.L.x265b200_me_frame_host(self.h, depth, _vp(hostCurBase), ctypes.c_size_t(planeBytes), _vp(devCurBase), _i64(curStride), arr, len(refOrigins),
+                                            _i64(refStride), int(marginX), int(marginY), int(rowsTotal), int(ctuCols), int(ctuRows), int(puMask), _vp(dMvpCtu),
+                                            int(searchMethod), int(subpelRefine), int(merange), ctypes.c_double(lam), _vp(devOut), _vp(hostOut), ctypes.c_size_t(outBytes)))
+
+
+Ctx.me_frame_host = _ctx_me_frame_host
 
 
 # ---- --me sea --------------------------------------------------------------------------------------
@@ -533,11 +565,11 @@ class LA_HME(ctypes.Structure):
 
 
 def _ctx_la_estimate_hme_dev(self, depth, dPlanes, stride, wcu, hcu, hme, triples, dMvPool, dMvCostPool, dIntraCostPtrs, dInvQPtrs,
-                             dLowresCosts, dRowSatds, dSums, lam, maxSlices=1):
+                             dLowresCosts, dRowSatds, dSums, lam, lookaheadSlices=0):
     triples = np.ascontiguousarray(triples, dtype=LA_TRIPLE)
     self._chk(self.L.x265b200_la_estimate_hme_dev(self.h, depth, _vp(dPlanes), _i64(stride), int(wcu), int(hcu), ctypes.byref(hme), _vp(triples),
                                                   len(triples), _vp(dMvPool), _vp(dMvCostPool), _vp(dIntraCostPtrs), _vp(dInvQPtrs),
-                                                  _vp(dLowresCosts), _vp(dRowSatds), _vp(dSums), ctypes.c_double(lam), int(maxSlices)))
+                                                  _vp(dLowresCosts), _vp(dRowSatds), _vp(dSums), ctypes.c_double(lam), int(lookaheadSlices)))
 
 
 Ctx.la_estimate_hme_dev = _ctx_la_estimate_hme_dev

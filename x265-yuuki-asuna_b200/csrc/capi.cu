@@ -138,7 +138,7 @@ int la_intra_dev(Ctx*, int depth, const void* plane0, int64_t stride, int widthI
 int la_estimate_dev(Ctx*, int depth, const void* const* planes, int64_t stride, int widthInCU, int heightInCU,
                     const x265b200_la_triple* triplesHost, int numTriples, int32_t* mvPool, int32_t* mvCostPool,
                     const int32_t* const* intraCost, const int32_t* const* invQscale, uint16_t* lowresCosts, int32_t* rowSatds, int32_t* sums,
-                    double lambda, int maxSlices, const x265b200_la_hme* hme);
+                    double lambda, int maxSlices, int lookaheadSlices, const x265b200_la_hme* hme);
 int sub_ps_plane_dev(Ctx*, int depth, const void* a, int64_t strideA, const void* b, int64_t strideB, int16_t* dst, int64_t dstStride, int w, int h);
 int add_ps_plane_dev(Ctx*, int depth, void* dst, int64_t dstStride, const void* pred, int64_t predStride, const int16_t* resi, int64_t resiStride, int w, int h);
 
@@ -582,6 +582,39 @@ int x265b200_sad_stream_dev(x265b200_ctx* ctx, int depth, const void* poolOrigin
     return sad_stream_dev(CTX(ctx), depth, poolOrigin, framePitch, stride, marginX, marginY, rowsTotal, numFrames, ctuCols, ctuRows,
                           groupsHost, numGroups, numRefs, out8, out16, out32, out64);
 }
+int x265b200_me_frame_host(x265b200_ctx* ctx, int depth, const void* hostCurBase, size_t planeBytes, void* devCurBase, int64_t curStride,
+                           const void* const* refOriginsHost, int numRefs, int64_t refStride,
+                           int marginX, int marginY, int rowsTotal, int ctuCols, int ctuRows, int puMask,
+                           const int32_t* mvpCtu, int searchMethod, int subpelRefine, int merange, double lambda,
+                           int32_t* devOut, int32_t* hostOut, size_t outBytes)
+{
+    REQUIRE_CTX(ctx);
+    if (!hostCurBase || !devCurBase || !devOut || !hostOut) { set_error("me_frame_host: null buffer"); return -1; }
+    const int px = depth > 8 ? 2 : 1;
+    X265B200_CHECK(cudaMemcpyAsync(devCurBase, hostCurBase, planeBytes, cudaMemcpyHostToDevice, ctx->c.stream));
+    const char* origin = (const char*)devCurBase + ((int64_t)marginY * curStride + marginX) * px;
+    if (me_frame_dev(CTX(ctx), depth, origin, curStride, refOriginsHost, numRefs, refStride, marginX, marginY, rowsTotal, ctuCols, ctuRows, puMask,
+                     mvpCtu, searchMethod, subpelRefine, merange, lambda, devOut)) return -1;
+    X265B200_CHECK(cudaMemcpyAsync(hostOut, devOut, outBytes, cudaMemcpyDeviceToHost, ctx->c.stream));
+    X265B200_CHECK(cudaStreamSynchronize(ctx->c.stream));
+    return 0;
+}
+int x265b200_me_frame_ex_host(x265b200_ctx* ctx, const x265b200_me_frame_params* params, const x265b200_me_frame_planes* planes,
+                              const void* hostCurYBase, void* devCurYBase, size_t bytesY,
+                              const void* hostCurCbBase, void* devCurCbBase, const void* hostCurCrBase, void* devCurCrBase, size_t bytesC,
+                              const int32_t* mvpCtu, const int32_t* mvpPu, const uint8_t* numCandPu, const int32_t* mvcPu,
+                              int32_t* devOut, int32_t* hostOut, size_t outBytes)
+{
+    REQUIRE_CTX(ctx);
+    if (!hostCurYBase || !devCurYBase || !devOut || !hostOut) { set_error("me_frame_ex_host: null buffer"); return -1; }
+    X265B200_CHECK(cudaMemcpyAsync(devCurYBase, hostCurYBase, bytesY, cudaMemcpyHostToDevice, ctx->c.stream));
+    if (hostCurCbBase && devCurCbBase) X265B200_CHECK(cudaMemcpyAsync(devCurCbBase, hostCurCbBase, bytesC, cudaMemcpyHostToDevice, ctx->c.stream));
+    if (hostCurCrBase && devCurCrBase) X265B200_CHECK(cudaMemcpyAsync(devCurCrBase, hostCurCrBase, bytesC, cudaMemcpyHostToDevice, ctx->c.stream));
+    if (me_frame_ex_dev(CTX(ctx), params, planes, mvpCtu, mvpPu, numCandPu, mvcPu, devOut)) return -1;
+    X265B200_CHECK(cudaMemcpyAsync(hostOut, devOut, outBytes, cudaMemcpyDeviceToHost, ctx->c.stream));
+    X265B200_CHECK(cudaStreamSynchronize(ctx->c.stream));
+    return 0;
+}
 int x265b200_me_frame_layout(int ctuSize, int minCuSize, int rect, int amp, int32_t* outXYWH, int cap)
 {
     return me_frame_layout(ctuSize, minCuSize, rect, amp, outXYWH, cap);
@@ -620,21 +653,21 @@ int x265b200_la_intra_dev(x265b200_ctx* ctx, int depth, const void* plane0, int6
 int x265b200_la_estimate_dev(x265b200_ctx* ctx, int depth, const void* const* planes, int64_t stride, int widthInCU, int heightInCU,
                              const x265b200_la_triple* triplesHost, int numTriples, int32_t* mvPool, int32_t* mvCostPool,
                              const int32_t* const* intraCost, const int32_t* const* invQscale, uint16_t* lowresCosts,
-                             int32_t* rowSatds, int32_t* sums, double lambda, int maxSlices)
+                             int32_t* rowSatds, int32_t* sums, double lambda, int lookaheadSlices)
 {
     REQUIRE_CTX(ctx);
     return la_estimate_dev(CTX(ctx), depth, planes, stride, widthInCU, heightInCU, triplesHost, numTriples, mvPool, mvCostPool,
-                           intraCost, invQscale, lowresCosts, rowSatds, sums, lambda, maxSlices, nullptr);
+                           intraCost, invQscale, lowresCosts, rowSatds, sums, lambda, 1, lookaheadSlices, nullptr);
 }
 int x265b200_la_estimate_hme_dev(x265b200_ctx* ctx, int depth, const void* const* planes, int64_t stride, int widthInCU, int heightInCU,
                                  const x265b200_la_hme* hme, const x265b200_la_triple* triplesHost, int numTriples, int32_t* mvPool, int32_t* mvCostPool,
                                  const int32_t* const* intraCost, const int32_t* const* invQscale, uint16_t* lowresCosts,
-                                 int32_t* rowSatds, int32_t* sums, double lambda, int maxSlices)
+                                 int32_t* rowSatds, int32_t* sums, double lambda, int lookaheadSlices)
 {
     REQUIRE_CTX(ctx);
     if (!hme) { set_error("la_estimate_hme: hme descriptor is NULL"); return -1; }
     return la_estimate_dev(CTX(ctx), depth, planes, stride, widthInCU, heightInCU, triplesHost, numTriples, mvPool, mvCostPool,
-                           intraCost, invQscale, lowresCosts, rowSatds, sums, lambda, maxSlices, hme);
+                           intraCost, invQscale, lowresCosts, rowSatds, sums, lambda, 1, lookaheadSlices, hme);
 }
 
 } // extern "C"

@@ -32,26 +32,32 @@ la_search_thread_kernel(LASearchArgs p)
     __shared__ __align__(16) pixel sFenc[LAT_WARPS][4][8 * 64];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int W = p.widthInCU, Hc = p.heightInCU, ncu = W * Hc;
-    const int bands = (Hc + 31) >> 5;
+    // work items: (chain, 32-row band of a slice), bands counted bottom-up inside their slice; item ids are ordered band-major
+    // inside a chain, so the band an item waits for (the one below it in the same slice) always has a smaller id
+    const int nSl = p.numSlices, R = p.rowsPerSlice;
+    const int maxRows = Hc - (nSl - 1) * R;                          // the last slice is the tallest (>= R rows)
+    const int bands = (max(maxRows, R) + 31) >> 5, perChain = bands * nSl;
 
     for (;;)
     {
         int id = 0;
         if (lane == 0) id = atomicAdd(p.workCounter, 1);
         id = __shfl_sync(0xffffffffu, id, 0);
-        if (id >= p.numChains * bands) return;
-        const int chain = id / bands, band = id - chain * bands;
+        if (id >= p.numChains * perChain) return;
+        const int chain = id / perChain, rem = id - chain * perChain;
+        const int band = rem / nSl, slice = rem - band * nSl;
         const LAChain ch = p.chains[chain];
-        const int cuY = Hc - 1 - band * 32 - lane;                  // this lane's row (bottom-up inside the band)
-        const bool rowValid = cuY >= 0;
-        const bool lastRow = cuY == Hc - 1;
+        const int firstY = slice * R, lastY = slice == nSl - 1 ? Hc - 1 : (slice + 1) * R - 1;
+        const int cuY = lastY - band * 32 - lane;                   // this lane's row (bottom-up inside the slice)
+        const bool rowValid = cuY >= firstY;
+        const bool lastRow = cuY == lastY;                          // estimateCUCost's lastRow: bottom row of the slice
         volatile int* below = p.progress + chain * Hc + cuY + 1;
         int32_t* mvs = p.mvPool + (int64_t)ch.mvSlot * ncu * 2;
         int32_t* mvcosts = p.mvCostPool + (int64_t)ch.mvSlot * ncu;
         const pixel* const* fencPlanes = (const pixel* const*)p.planes + ch.b * 4;
         const pixel* const* refPlanes = (const pixel* const*)p.planes + ch.ref * 4;
-        // the row above this lane belongs to another warp when this is the band's top lane (or the band's last valid row)
-        const bool publishes = rowValid && cuY > 0 && (lane == 31);
+        // the row above this lane belongs to another warp when this is the band's top lane and the slice goes on above it
+        const bool publishes = rowValid && cuY > firstY && (lane == 31);
 
         MEState<pixel> s;
         s.fenc = &sFenc[warp][lane >> 3][(lane & 7) * 8];
@@ -141,8 +147,9 @@ la_search_thread_kernel(LASearchArgs p)
 
 int la_search_thread_launch(Ctx* ctx, int depth, const LASearchArgs& a)
 {
-    const int bands = (a.heightInCU + 31) >> 5;
-    const int64_t items = (int64_t)a.numChains * bands;
+    const int maxRows = a.heightInCU - (a.numSlices - 1) * a.rowsPerSlice;
+    const int bands = ((maxRows > a.rowsPerSlice ? maxRows : a.rowsPerSlice) + 31) >> 5;
+    const int64_t items = (int64_t)a.numChains * bands * a.numSlices;
     int64_t blocksWanted = (items + LAT_WARPS - 1) / LAT_WARPS;
     int64_t cap = (int64_t)ctx->smCount * 8;
     unsigned blocks = (unsigned)(blocksWanted < cap ? blocksWanted : cap);

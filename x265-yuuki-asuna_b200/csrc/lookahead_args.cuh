@@ -25,6 +25,10 @@ struct LASearchArgs
     const int32_t* hmeMvPool;      // [slot][hmeNcu][2] lowerResMvs, or nullptr (the quarter-resolution level itself)
     const int32_t* hmeMvCostPool;  // [slot][hmeNcu]    lowerResMvCosts
     int hmeNcu;
+    // cooperative slices (--lookahead-slices, slicetype.cpp:3079-3107): rows [k*rowsPerSlice, (k+1)*rowsPerSlice) form slice k
+    // (the last slice runs to the bottom row); the bottom row of every slice is searched with lastRow = true, i.e. without the
+    // MV candidates of the row below, so the slices are independent wavefronts.  numSlices = 1: the whole field is one slice.
+    int rowsPerSlice, numSlices;
 };
 
 int la_search_thread_launch(Ctx* ctx, int depth, const LASearchArgs& a);

@@ -294,102 +294,8 @@ int la_intra_dev(Ctx* ctx, int depth, const void* plane0, int64_t stride, int wi
 }
 
 // ---------------------------------------------------------------------------------------------
-// estimateCUCost phase 1: per (triple, list) MV search chains, one warp per CU row
+// estimateCUCost phase 1 (the MV search chains of every (triple, list) field) lives in la_search_thread.cu: one lane per CU
 // ---------------------------------------------------------------------------------------------
-constexpr int LA_WARPS = 4;
-
-template<typename pixel>
-__global__ void __launch_bounds__(LA_WARPS * 32)
-la_search_kernel(LASearchArgs p)
-{
-    __shared__ __align__(16) pixel sFenc[LA_WARPS][8 * 64];
-    __shared__ __align__(16) pixel sPred[LA_WARPS][64];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int W = p.widthInCU, Hc = p.heightInCU, ncu = W * Hc;
-
-    for (;;)
-    {
-        int id = 0;
-        if (lane == 0) id = atomicAdd(p.workCounter, 1);
-        id = __shfl_sync(0xffffffffu, id, 0);
-        if (id >= p.numChains * Hc) return;
-        const int chain = id / Hc, cuY = Hc - 1 - (id % Hc);
-        const LAChain ch = p.chains[chain];
-        const bool lastRow = (cuY == Hc - 1);
-        volatile int* below = p.progress + chain * Hc + cuY + 1;
-        int* mine = p.progress + chain * Hc + cuY;
-        int32_t* mvs = p.mvPool + (int64_t)ch.mvSlot * ncu * 2;
-        int32_t* mvcosts = p.mvCostPool + (int64_t)ch.mvSlot * ncu;
-        const pixel* const* fencPlanes = (const pixel* const*)p.planes + ch.b * 4;
-        const pixel* const* refPlanes = (const pixel* const*)p.planes + ch.ref * 4;
-
-        MEState<pixel> s;
-        s.fenc = sFenc[warp]; s.pred = sPred[warp]; s.immed = nullptr;
-        s.stride = p.stride; s.isLowres = true; s.perThread = false; s.chromaSatd = false; s.groupSize = 1; s.groupMask = 0xffffffffu; s.w = 8; s.h = 8; s.lane = lane; s.depth = p.depth;
-        s.partSizeScale = 4; s.cost = p.cost + 2 * 32768;
-
-        int rightX = 0, rightY = 0;       // fencMV[1] of the previous iteration
-        for (int cuX = W - 1; cuX >= 0; cuX--)
-        {
-            const int cuXY = cuX + cuY * W;
-            const int64_t pelOffset = 8 * cuX + (int64_t)8 * cuY * p.stride;
-            if (!lastRow)
-            {
-                const int need = min(W, W - cuX + 1);
-                if (lane == 0) { while (*below < need) __nanosleep(64); }
-                __syncwarp();
-                __threadfence();
-            }
-            // setSourcePU: cache the 8x8 source block (motion.cpp:188-189)
-            __syncwarp();
-            if (lane < 16)
-            {
-                int y = lane >> 1, x = (lane & 1) * 4;
-                const pixel* fp = fencPlanes[0] + pelOffset + (int64_t)y * p.stride + x;
-                if (sizeof(pixel) == 1) *(uint32_t*)((uint8_t*)s.fenc + y * 64 + x) = ld_px4((const uint8_t*)fp);
-                else { uint32_t* d = (uint32_t*)((uint16_t*)s.fenc + y * 64 + x); d[0] = ld_px2((const uint16_t*)fp); d[1] = ld_px2((const uint16_t*)fp + 2); }
-            }
-            __syncwarp();
-            for (int k = 0; k < 4; k++) s.lowres[k] = refPlanes[k] + pelOffset;
-            s.fref = s.lowres[0]; s.gfref = s.lowres[0]; s.gstride = p.stride;
-
-            // reverse-order MV prediction candidates (slicetype.cpp:3269-3280)
-            int mvc[4][2], numc = 0;
-            if (cuX < W - 1) { mvc[numc][0] = rightX; mvc[numc][1] = rightY; numc++; }
-            if (!lastRow)
-            {
-                const volatile int32_t* row = mvs + (int64_t)(cuXY + W) * 2;
-                mvc[numc][0] = row[0]; mvc[numc][1] = row[1]; numc++;
-                if (cuX > 0) { mvc[numc][0] = row[-2]; mvc[numc][1] = row[-1]; numc++; }
-                if (cuX < W - 1) { mvc[numc][0] = row[2]; mvc[numc][1] = row[3]; numc++; }
-            }
-            int mvpx = 0, mvpy = 0, skipCost = 0x7fffffff;
-            if (numc)
-            {
-                int mvpcost = ME_COST_MAX;
-                for (int idx = 0; idx < numc; idx++)
-                {
-                    int cost = lowres_qpel_cost<pixel>(s, mvc[idx][0], mvc[idx][1], true);     // lowresMC + bufSATD
-                    if (cost < mvpcost) { mvpcost = cost; mvpx = mvc[idx][0]; mvpy = mvc[idx][1]; }
-                    if (!(mvpx | mvpy) && ch.bBidir) skipCost = cost;                          // :3304-3305 (as written)
-                }
-            }
-            s.mvpx = mvpx; s.mvpy = mvpy;
-            MV2 mvmin = mv2(-cuX * 8 - 8, -cuY * 8 - 8), mvmax = mv2((W - cuX - 1) * 8 + 8, (Hc - cuY - 1) * 8 + 8);
-            int ox, oy;
-            int fencCost = motion_estimate<pixel>(s, mvmin, mvmax, mv2(mvpx, mvpy), 0, nullptr, p.merange, ME_HEX, 1, p.maxSlices, 0, ox, oy);
-            if (skipCost < 64 && skipCost < fencCost && ch.bBidir) { fencCost = skipCost; ox = 0; oy = 0; }
-            rightX = ox; rightY = oy;
-            if (lane == 0)
-            {
-                mvs[cuXY * 2] = ox; mvs[cuXY * 2 + 1] = oy; mvcosts[cuXY] = fencCost;
-                __threadfence();
-                *(volatile int*)mine = W - cuX;
-            }
-            __syncwarp();
-        }
-    }
-}
 
 // ---------------------------------------------------------------------------------------------
 // estimateCUCost phase 2 (slicetype.cpp:3253-3262 list costs, :3326-3387): one thread per CU
@@ -467,7 +373,7 @@ la_finish_kernel(LAFinishArgs p)
 int la_estimate_dev(Ctx* ctx, int depth, const void* const* planes, int64_t stride, int widthInCU, int heightInCU,
                     const x265b200_la_triple* triplesHost, int numTriples,
                     int32_t* mvPool, int32_t* mvCostPool, const int32_t* const* intraCost, const int32_t* const* invQscale,
-                    uint16_t* lowresCosts, int32_t* rowSatds, int32_t* sums, double lambda, int maxSlices, const x265b200_la_hme* hme)
+                    uint16_t* lowresCosts, int32_t* rowSatds, int32_t* sums, double lambda, int maxSlices, int lookaheadSlices, const x265b200_la_hme* hme)
 {
     if (numTriples <= 0) return 0;
     if (hme)
@@ -477,7 +383,16 @@ int la_estimate_dev(Ctx* ctx, int depth, const void* const* planes, int64_t stri
             if (hme->searchMethod[l] < 0 || hme->searchMethod[l] > ME_FULL || hme->searchMethod[l] == ME_SEA || hme->range[l] < 1)
             { set_error("la_estimate: HME level %d search method %d / range %d", l, hme->searchMethod[l], hme->range[l]); return -1; }
     }
-    if (maxSlices > 1) { set_error("la_estimate: maxSlices > 1 is not supported on the lowres path"); return -1; }
+    if (maxSlices > 1) { set_error("la_estimate: maxSlices > 1 (--slices) is not supported on the lowres path"); return -1; }
+    // cooperative slices (Lookahead::create, slicetype.cpp:1029-1041): at least 10 rows per slice, no more than the field
+    int rowsPerSlice = heightInCU, numSlices = 1;
+    if (lookaheadSlices > 1)
+    {
+        rowsPerSlice = heightInCU / lookaheadSlices;
+        if (rowsPerSlice < 10) rowsPerSlice = 10;
+        if (rowsPerSlice > heightInCU) rowsPerSlice = heightInCU;
+        numSlices = heightInCU / rowsPerSlice;
+    }
     if (ensure_mvcost(ctx, lambda)) return -1;
     void* dTriplesV = nullptr;
     if (scratch_dev(ctx, 6, sizeof(x265b200_la_triple) * numTriples, &dTriplesV)) return -1;
@@ -507,6 +422,7 @@ int la_estimate_dev(Ctx* ctx, int depth, const void* const* planes, int64_t stri
         a.widthInCU = widthInCU; a.heightInCU = heightInCU; a.depth = depth; a.merange = 16; a.maxSlices = maxSlices;   // s_merange, slicetype.h:259
         a.mvPool = mvPool; a.mvCostPool = mvCostPool; a.progress = dProg; a.workCounter = dProg + (size_t)numChains * heightInCU; a.cost = ctx->dMvCost;
         a.hme = 0; a.searchMethod = ME_HEX; a.hmeMvPool = nullptr; a.hmeMvCostPool = nullptr; a.hmeNcu = 0;
+        a.rowsPerSlice = rowsPerSlice; a.numSlices = numSlices;
         if (hme)
         {
             // level 0 (slicetype.cpp:3177-3188): the same chains over the quarter-resolution planes, hmeSearchMethod[0] / hmeRange[0];
@@ -517,34 +433,24 @@ int la_estimate_dev(Ctx* ctx, int depth, const void* const* planes, int64_t stri
             h.merange = hme->range[0]; h.searchMethod = hme->searchMethod[0]; h.hme = 1;
             h.mvPool = hme->lowerMvPool; h.mvCostPool = hme->lowerMvCostPool;
             h.progress = dProg + (size_t)numChains * heightInCU + 64; h.workCounter = h.progress + (size_t)numChains * hme->height4;
+            if (numSlices > 1)
+            {
+                // the quarter-resolution level is cut into the same NUMBER of slices (processTasks, slicetype.cpp:3086-3092)
+                int r4 = hme->height4 / lookaheadSlices;
+                r4 = r4 < 5 ? 5 : r4; r4 = r4 > hme->height4 ? hme->height4 : r4;
+                if ((int64_t)r4 * (numSlices - 1) >= hme->height4) { set_error("la_estimate: %d slices do not fit the %d rows of the HME level", numSlices, hme->height4); return -1; }
+                h.rowsPerSlice = r4; h.numSlices = numSlices;
+            }
+            else { h.rowsPerSlice = hme->height4; h.numSlices = 1; }
             if (hme->height4 > heightInCU) { set_error("la_estimate: HME level taller than the 8x8 level"); return -1; }
             X265B200_CHECK(cudaStreamSynchronize(ctx->stream));
             if (la_search_thread_launch(ctx, depth, h)) return -1;
             a.hme = 1; a.searchMethod = hme->searchMethod[1]; a.merange = hme->range[1];
             a.hmeMvPool = hme->lowerMvPool; a.hmeMvCostPool = hme->lowerMvCostPool; a.hmeNcu = hme->width4 * hme->height4;
         }
-        // every claimed row must be able to make progress: rows are claimed bottom-up, so any grid size is deadlock-free
-        int64_t rows = (int64_t)numChains * heightInCU;
-        int64_t blocksWanted = (rows + LA_WARPS - 1) / LA_WARPS;
-        int64_t cap = (int64_t)ctx->smCount * 8;
-        unsigned blocks = (unsigned)(blocksWanted < cap ? blocksWanted : cap);
         // the host must not free `chains` before the async copy is consumed
         X265B200_CHECK(cudaStreamSynchronize(ctx->stream));
-        // default: one lane per CU, 32 staggered rows per warp (la_search_thread.cu); X265B200_LA_WARP=1 selects the
-        // older one-warp-per-CU kernel (kept for A/B measurements, same results)
-        static const bool useWarpKernel = getenv("X265B200_LA_WARP") && atoi(getenv("X265B200_LA_WARP")) != 0;
-        if (useWarpKernel && hme) { set_error("la_estimate: --hme is implemented by the per-thread search kernel only (unset X265B200_LA_WARP)"); return -1; }
-        if (!useWarpKernel)
-        {
-            if (la_search_thread_launch(ctx, depth, a)) return -1;
-        }
-        else
-        {
-            if (depth > 8) la_search_kernel<uint16_t><<<blocks, LA_WARPS * 32, 0, ctx->stream>>>(a);
-            else           la_search_kernel<uint8_t><<<blocks, LA_WARPS * 32, 0, ctx->stream>>>(a);
-            ctx->launches++;
-            if (check(cudaGetLastError(), "la_search launch")) return -1;
-        }
+        if (la_search_thread_launch(ctx, depth, a)) return -1;
     }
     X265B200_CHECK(cudaMemsetAsync(rowSatds, 0, sizeof(int32_t) * (size_t)numTriples * heightInCU, ctx->stream));
     X265B200_CHECK(cudaMemsetAsync(sums, 0, sizeof(int32_t) * (size_t)numTriples * 4, ctx->stream));
