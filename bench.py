@@ -1,19 +1,29 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the B200 x265 hot-path backend (contract in the task brief).
 
-Workload ("step" = one 2160p 8-bit frame through the hot path, BASELINE.json configs[2] knobs:
-HEX search, subme 2, merange 57, 3 references, 2Nx2N PUs 64/32/16/8 of every CTU, mvp = 0):
-  1. sad_pred  : SAD at the predictor for every PU level x reference (grid-mode pixelcmp kernel; the
-                 streaming "ME SAD" kernel whose HBM GB/s is the second half of BASELINE's metric)
-  2. me_search : MotionEstimate::motionEstimate for every PU x reference (me_batch kernel)
+`--config N` selects one of BASELINE.json's configurations (default 3, the one the metric is quoted on):
+  2  1080p 8-bit ultrafast : CTU 32 / minCU 16, DIA, subme 0, merange 57, 1 reference   -- "ME primitives": streaming SAD + frame search
+  3  2160p 8-bit medium    : the full primitive mix of SURVEY.md 8d config 3 (below)    -- DEFAULT
+  4  2160p 10-bit slow     : STAR, subme 3 (chroma SATD), 4 references, rect PUs        -- streaming SAD + frame search
+  5  4320p 8-bit placebo   : STAR, merange 128, subme 5, 5 references, rect + AMP       -- streaming SAD + frame search
+
+A "step" is one frame through the hot path.  Config 3 (HEX, subme 2, merange 57, 3 references, 2Nx2N PUs 64..8, mvp = 0):
+  1. sad_pred  : SAD at the predictor of every PU level x reference (the streaming TMA kernel of sad_stream_kernels.cu)
+  2. me_search : MotionEstimate::motionEstimate for every PU x reference (me_frame kernel, TMA-staged windows)
   3. mc        : one 8-tap luma interpolation per PU and level (all 15 fractions)
   4. residual  : fused residual pipeline (fenc - pred -> DCT -> quant -> dequant -> IDCT -> recon -> SSE) on every 32/16/8/4 TU
   5. intra     : neighbour filter + all 35 modes on every 8/16/32 block
-`value` = frames/s with inputs resident in HBM; `e2e` = the same through the C ABI with the new frame
-coming from pinned HOST memory and the per-PU {MV,cost} results copied back, every step.
-
---impl reference times the reference's own C implementation (oracle/_ref, compiled from the
-unmodified x265 sources) of the same step on the host cores, on a bounded sample of the frame.
+  6. lookahead : Lowres::init + lowresIntraEstimate of the new frame and, per batch of 8 frames, the estimateFrameCost list
+                 searches medium triggers (bframes 4: 5 frame-triples = 10 list searches per frame, --lookahead-slices 8),
+                 on a second stream, overlapped with 1-5 and INSIDE the timed region.
+`value` = frames/s with frames resident in HBM (ring of 32 frames = 318 MB > L2, no flush needed);
+`e2e`   = the same with every new frame arriving from pinned HOST memory through the host-buffer C-ABI entry
+          (x265b200_me_frame_host / x265b200_me_frame_ex_host: H2D of the frame, search, D2H of the {mv,cost} records).
+`--impl reference` times the reference's own CPU code (oracle/_ref, compiled from the unmodified x265 sources; C table +
+the SSE-intrinsic DCT table, no nasm here) for the same step on all host cores, on a bounded sample of CTU rows.
+`--shard frames` (default; weak scaling: every rank its own frames + all_gather of the new reference plane + gather of the
+results, on a comm stream overlapped with the next step) or `--shard ctu-rows` (strong scaling of ONE frame: a band of CTU
+rows per rank).
 """
 import argparse
 import ctypes
@@ -31,18 +41,30 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
+# ---- config 3 geometry (module-level names: tests/ and scripts/ use them) ------------------------------------------------------
 W, H, CTU, PAD = 3840, 2160, 64, 128          # luma; PAD >= merange + 8 + halo, multiple of 64
 STRIDE = W + 2 * PAD
 ROWS = H + 2 * PAD + (64 - (H % 64)) % 64      # 34 CTU rows (2176) + margins
 CTU_COLS, CTU_ROWS = W // CTU, (H + CTU - 1) // CTU
 NREF, MERANGE, SUBME, QP = 3, 57, 2, 30
 LEVELS = [64, 32, 16, 8]
-# DRAM bytes one sad_pyramid launch (3 references, 2160p 8-bit) moved under `ncu --set full` (profiles/r01_pyramid_dct_v3.txt)
-SAD_PYRAMID_DRAM_BYTES = 33437696
-WORKLOAD = ("2160p-8bit-medium primitive mix (SURVEY.md 8d config 3): SAD at the predictor + HEX subme2 merange57 search of every 2Nx2N PU 64..8 x 3 refs; "
-            "one 8-tap MC interpolation per PU and level (all 15 fractions); residual -> DCT/quant/dequant/IDCT on every 32/16/8/4 TU -> recon; "
-            "intra neighbour smoothing + all 35 modes on every 8/16/32 block (fused)")
 METRIC = "2160p preset-medium fps at 1/2/4/8 B200; ME SAD achieved HBM GB/s vs peak"
+LA_BATCH, LA_BFRAMES, LA_SLICES = 8, 4, 8      # frames per estimateFrameCost launch; bframes; --lookahead-slices (param.cpp:173)
+
+ME_DIA, ME_HEX, ME_UMH, ME_STAR = 0, 1, 2, 3
+CONFIGS = {
+    2: dict(name="1080p 8-bit ultrafast: CTU 32 / minCU 16, DIA, subme 0, merange 57, 1 reference (param.cpp:396-410)", W=1920, H=1080, depth=8, C=32, minCu=16,
+            rect=0, amp=0, method=ME_DIA, subme=0, merange=57, nref=1, csp=0, NF=64),
+    3: dict(name="2160p 8-bit medium primitive mix", W=W, H=H, depth=8, C=64, minCu=8, rect=0, amp=0, method=ME_HEX, subme=SUBME, merange=MERANGE, nref=NREF, csp=0, NF=32),
+    4: dict(name="2160p 10-bit slow: STAR, subme 3 (chroma SATD), 4 references, rect PUs, 4:2:0", W=3840, H=2160, depth=10, C=64, minCu=8, rect=1, amp=0,
+            method=ME_STAR, subme=3, merange=57, nref=4, csp=1, NF=8),
+    5: dict(name="4320p 8-bit placebo: STAR, merange 128, subme 5, 5 references, rect + AMP, 4:2:0", W=7680, H=4320, depth=8, C=64, minCu=8, rect=1, amp=1,
+            method=ME_STAR, subme=5, merange=128, nref=5, csp=1, NF=8),
+}
+WORKLOAD3 = ("2160p-8bit-medium primitive mix (SURVEY.md 8d config 3): SAD at the predictor + HEX subme2 merange57 search of every 2Nx2N PU 64..8 x 3 refs; "
+             "one 8-tap MC interpolation per PU and level (all 15 fractions); residual -> DCT/quant/dequant/IDCT on every 32/16/8/4 TU -> recon; "
+             "intra neighbour smoothing + all 35 modes on every 8/16/32 block (fused); lookahead (lowres init + intra estimate + 10 estimateFrameCost list "
+             "searches per frame, --lookahead-slices 8) on a second stream, inside the timed region")
 
 
 def peaks():
@@ -52,27 +74,41 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
 
 
-def synth_frames(nframes, seed=1234):
-    """band-limited noise + per-frame global translation + noise."""
-    rng = np.random.default_rng(seed)
-    big = rng.integers(0, 256, (ROWS + 96, STRIDE + 96), dtype=np.uint8).astype(np.float32)
-    k = np.ones(5, dtype=np.float32) / 5
+def box_blur(a, k=5):
     for ax in (0, 1):
-        big = np.apply_along_axis(lambda r: np.convolve(r, k, mode="same"), ax, big)
-    big = (big - big.min()) / (big.max() - big.min()) * 255.0
+        c = np.cumsum(a, axis=ax, dtype=np.float64)
+        pad = [(0, 0), (0, 0)]; pad[ax] = (k, 0)
+        c = np.pad(c, pad)
+        n = a.shape[ax]
+        a = (np.take(c, np.arange(k, n + k), axis=ax) - np.take(c, np.arange(0, n), axis=ax)) / k
+    return a
+
+
+def synth_planes(nframes, rows, stride, depth=8, seed=1234, step=6, noise=2.0):
+    """band-limited noise + per-frame global translation + noise, padded planes of rows x stride pixels"""
+    rng = np.random.default_rng(seed)
+    big = box_blur(rng.integers(0, 256, (rows + 96, stride + 96)).astype(np.float64))
+    big = ((big - big.min()) / (big.max() - big.min()) * 255.0).astype(np.float32)
     mrng = np.random.default_rng(5678)
+    scale, pmax = 1 << (depth - 8), (1 << depth) - 1
+    dt = np.uint16 if depth > 8 else np.uint8
     frames = []
     x, y = 48, 48
     for f in range(nframes):
-        dx, dy = mrng.integers(-6, 7, 2)
+        dx, dy = mrng.integers(-step, step + 1, 2)
         x = int(np.clip(x + dx, 0, 95)); y = int(np.clip(y + dy, 0, 95))
-        fr = big[y:y + ROWS, x:x + STRIDE] + rng.normal(0, 2.0, (ROWS, STRIDE)).astype(np.float32)
-        frames.append(np.clip(np.rint(fr), 0, 255).astype(np.uint8))
+        fr = big[y:y + rows, x:x + stride] + rng.normal(0, noise, (rows, stride)).astype(np.float32)
+        frames.append(np.clip(np.rint(fr * scale), 0, pmax).astype(dt))
     return frames
 
 
+def synth_frames(nframes, seed=1234):
+    """the config-3 frames (ROWS x STRIDE, 8-bit)"""
+    return synth_planes(nframes, ROWS, STRIDE, 8, seed)
+
+
 def build_jobs(pkg, ctu_rows=None):
-    """one job per (ref, level, PU): mvp = 0, window = +-merange."""
+    """one ME job per (ref, level, PU) of config 3: mvp = 0, window = +-merange."""
     rows = range(CTU_ROWS) if ctu_rows is None else ctu_rows
     js = []
     for r in range(NREF):
@@ -82,8 +118,6 @@ def build_jobs(pkg, ctu_rows=None):
                 for cx in range(CTU_COLS):
                     for py in range(per):
                         y = cy * CTU + py * s
-                        if y + s > H + (64 - H % 64) % 64:
-                            continue
                         for px in range(per):
                             js.append((cx * CTU + px * s, y, s, r))
     a = np.array(js, dtype=np.int32)
@@ -177,58 +211,103 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons)}
 
 
+def geometry(cfg):
+    """PicYuv-style padded geometry of a config (picyuv.cpp:87-89: marginX = maxCU + 32, marginY = maxCU + 16); config 3 keeps the
+    128-pixel pad of the round-1 bench (tests share its constants)."""
+    C = cfg["C"]
+    cols, rows = (cfg["W"] + C - 1) // C, (cfg["H"] + C - 1) // C
+    if cfg is CONFIGS[3]:
+        return dict(cols=cols, rows=rows, padX=PAD, padY=PAD, stride=STRIDE, planeRows=ROWS)
+    padX, padY = C + 32, C + 16
+    if cfg["merange"] > 64:                      # the search window of merange 128 reaches further than the encoder's own padding
+        padX, padY = 64 + cfg["merange"] + 16, 64 + cfg["merange"] + 16
+    padX = (padX + 31) & ~31; padY = (padY + 1) & ~1
+    return dict(cols=cols, rows=rows, padX=padX, padY=padY, stride=cols * C + 2 * padX, planeRows=rows * C + 2 * padY)
+
+
+# =====================================================================================================================
+# the reference arm: the reference's own CPU code on the host cores
+# =====================================================================================================================
 def run_reference(args, rank, world):
-    """The reference's own C path (oracle/_ref) on host cores, bounded sample: one CTU row."""
     if rank != 0:
         return
     import oracle
-    from me_util import REF_ME_JOB
     pkg = importlib.import_module("x265-yuuki-asuna_b200")
-    R = oracle.ref(8)
+    cfg = CONFIGS[args.config]
+    R = oracle.ref(cfg["depth"])
     cores = os.cpu_count() or 1
     if R is None:
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libx265ref8.so not present"}))
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libx265ref%d.so not present" % cfg["depth"]}))
         return
-    frames = synth_frames(NREF + 1)
-    sample_rows = [CTU_ROWS // 2]
+    intr = R.ref_enable_intrinsics()              # the SSE-intrinsic DCT table (vec/): the optimised table that builds without nasm
+    if args.config == 3:
+        step, frac, sample, la = reference_mix(R, pkg, cores)
+    else:
+        step, frac, sample, la = reference_me(R, pkg, cfg, cores)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    per_frame = dt / frac + la["s_per_frame_all_cores"]
+    fps = 1.0 / per_frame
+    line = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": per_frame * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8" if cfg["depth"] == 8 else "u16",
+            "data": "synthetic", "impl": "reference",
+            "config": {"workload": WORKLOAD3 if args.config == 3 else cfg["name"], "baseline_config": args.config, "sample": sample},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "reference",
+                             "sample": sample + "; C table + %d SSE-intrinsic slots (common/vec), no nasm asm in this image; ME / MC / TU / intra jobs handed to %d "
+                                       "threads from an atomic queue; lookahead leg: %s" % (intr, cores, la["how"])},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def reference_lookahead(R, frames, stride, origin, width, height, cores, depth=8):
+    """one frame's worth of lookahead on the reference's own Lookahead objects: Lowres::init + lowresIntraEstimate + the 5
+    frame-triples of `bframes 4` (singleCost, the non-pool path: one thread); reported per frame as if the encoder's pool
+    scaled it perfectly over the cores (the most favourable reading for the CPU)."""
+    R.ref_la_create.restype = ctypes.c_void_p
+    R.ref_la_frame_cost.restype = ctypes.c_int64
+    n = 2 * (LA_BFRAMES + 1) + 1
+    h = ctypes.c_void_p(R.ref_la_create(width, height, LA_BFRAMES, 0))
+    item = frames[0].itemsize
+    t0 = time.perf_counter()
+    for f in frames[:n]:
+        R.ref_la_add_frame(h, ctypes.c_void_p(f.ctypes.data + origin * item), ctypes.c_ssize_t(stride))
+    t_init = (time.perf_counter() - t0) / n
+    t0 = time.perf_counter()
+    R.ref_la_intra(h, LA_BFRAMES + 1)
+    t_intra = time.perf_counter() - t0
+    b = LA_BFRAMES + 1
+    t0 = time.perf_counter()
+    for dd in range(1, LA_BFRAMES + 2):
+        R.ref_la_frame_cost(h, b - dd, b + dd, b, 0)
+    t_est = time.perf_counter() - t0
+    R.ref_la_destroy(h)
+    one = t_init + t_intra + t_est
+    return {"s_per_frame_1thread": one, "s_per_frame_all_cores": one / cores,
+            "how": "Lowres::init %.1f ms + lowresIntraEstimate %.1f ms + 5 frame-triples (10 list searches) %.1f ms on ONE thread, divided by %d cores" % (
+                t_init * 1e3, t_intra * 1e3, t_est * 1e3, cores)}
+
+
+def reference_mix(R, pkg, cores):
+    from me_util import REF_ME_JOB
+    frames = synth_frames(max(NREF + 1, 2 * (LA_BFRAMES + 1) + 1))
+    sample_rows = [0, CTU_ROWS // 3, (2 * CTU_ROWS) // 3, CTU_ROWS - 1]          # top, two interior rows, bottom
     job = build_jobs(pkg, sample_rows)
     frac = len(sample_rows) / CTU_ROWS
     origin = PAD * STRIDE + PAD
     cur = frames[NREF].ravel()
-
-    def step():
-        for r in range(NREF):
-            jr = job[job["refIdx"] == r]
-            rj = np.zeros(len(jr), dtype=REF_ME_JOB)
-            for f in ("puX", "puY", "w", "h", "mvminX", "mvminY", "mvmaxX", "mvmaxY", "mvpX", "mvpY", "numCand", "mvc"):
-                rj[f] = jr[f]
-            ref = frames[NREF - 1 - r].ravel()
-            R.ref_me_batch(ctypes.c_void_p(cur.ctypes.data + origin), ctypes.c_ssize_t(STRIDE),
-                           ctypes.c_void_p(ref.ctypes.data + origin), ctypes.c_ssize_t(STRIDE),
-                           ctypes.c_void_p(rj.ctypes.data), ctypes.c_int64(len(rj)), 1, SUBME, MERANGE, QP, 1, cores)
-        # MC: one luma interpolation per PU of the sample row, all 15 fractions
-        ref0 = frames[NREF - 1].ravel()
-        for sz in LEVELS:
-            part = R.ref_partition_from_sizes(sz, sz)
-            for kind, ja in ip_jobs[sz].items():
-                if len(ja):
-                    R.ref_interp_batch(kind, part, ctypes.c_void_p(ref0.ctypes.data + origin), ctypes.c_ssize_t(STRIDE),
-                                       ctypes.c_void_p(pred[sz].ctypes.data), ctypes.c_ssize_t(W), ctypes.c_void_p(ja.ctypes.data), ctypes.c_int64(len(ja)), cores)
-        # residual of the sample row against the 16x16-level prediction, every TU size: the table entries chained as
-        # Quant::transformNxN / invtransformNxN chain them (sub_ps, dct, quant, dequant, idct | DC fill | zero, add_ps, sse_pp)
-        y0 = sample_rows[0] * CTU
-        for idx, N in TU_SIZES:
-            nb = (W // N) * (CTU // N)
-            qbits, add = quant_params(N)
-            R.ref_tu_pipeline(idx, 0, ctypes.c_void_p(cur.ctypes.data + origin + y0 * STRIDE), ctypes.c_ssize_t(STRIDE),
-                              ctypes.c_void_p(pred[16].ctypes.data + y0 * W), ctypes.c_ssize_t(W), ctypes.c_void_p(recon.ctypes.data), ctypes.c_ssize_t(W),
-                              W // N, CTU // N, ctypes.c_void_p(qtab.ctypes.data), qbits, add, None, 40 << 5, 9,
-                              ctypes.c_void_p(tu_coef.ctypes.data), ctypes.c_void_p(tu_ns.ctypes.data), ctypes.c_void_p(tu_sse.ctypes.data), cores)
-        # intra: filter + all 35 modes on every 8/16/32 block of the sample row
-        for idx, N, _ in INTRA_SIZES:
-            nb = len(nbr[N])
-            R.ref_intra_batch(idx, ctypes.c_void_p(nbr[N].ctypes.data), ctypes.c_void_p(filt[N].ctypes.data), ctypes.c_void_p(intra_out[N].ctypes.data), ctypes.c_int64(nb), cores)
-
+    # everything a step needs is prepared here, outside the timed region
+    rjs = []
+    rng = np.random.default_rng(3)
+    for r in range(NREF):
+        jr = job[job["refIdx"] == r]
+        rj = np.zeros(len(jr), dtype=REF_ME_JOB)
+        for f in ("puX", "puY", "w", "h", "mvminX", "mvminY", "mvmaxX", "mvmaxY", "mvpX", "mvpY", "numCand", "mvc"):
+            rj[f] = jr[f]
+        rjs.append(rj[rng.permutation(len(rj))])      # sizes interleaved as well (the queue is dynamic anyway)
     ip_jobs = {sz: interp_jobs(pkg, sz, sample_rows) for sz in LEVELS}
     pred = {sz: np.zeros(CTU_ROWS * CTU * W, dtype=np.uint8) for sz in LEVELS}
     qtab = np.full(1024, 26214, dtype=np.int32)
@@ -237,30 +316,402 @@ def run_reference(args, rank, world):
     nbr = {N: neighbour_arrays(cur, N, sample_rows) for _, N, _ in INTRA_SIZES}
     filt = {N: np.empty_like(nbr[N]) for N in nbr}
     intra_out = {N: np.empty(len(nbr[N]) * 35 * N * N, dtype=np.uint8) for N in nbr}
+    parts = {sz: R.ref_partition_from_sizes(sz, sz) for sz in LEVELS}
+    refs = [frames[NREF - 1 - r].ravel() for r in range(NREF)]
+    vp = lambda a, off=0: ctypes.c_void_p(a.ctypes.data + off)
 
-    for _ in range(args.warmup):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
-    dt = (time.perf_counter() - t0) / args.steps
-    fps = frac / dt
-    line = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
-            "data": "synthetic", "impl": "reference",
-            "config": {"workload": WORKLOAD, "sample": "1 of %d CTU rows, scaled" % CTU_ROWS},
-            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "reference",
-                             "sample": "CTU row %d of %d (x%d to a frame): %d PU searches (3 refs), %d MC interpolations, DCT/quant/dequant/IDCT of its 32/16/8/4 TUs, 35 intra modes on its 8/16/32 blocks; C table, no nasm asm" % (sample_rows[0], CTU_ROWS, CTU_ROWS, len(job), sum(len(a) for d in ip_jobs.values() for a in d.values()))},
-            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    def step():
+        for r in range(NREF):
+            R.ref_me_batch(vp(cur, origin), ctypes.c_ssize_t(STRIDE), vp(refs[r], origin), ctypes.c_ssize_t(STRIDE),
+                           vp(rjs[r]), ctypes.c_int64(len(rjs[r])), 1, SUBME, MERANGE, QP, 1, cores)
+        for sz in LEVELS:
+            for kind, ja in ip_jobs[sz].items():
+                if len(ja):
+                    R.ref_interp_batch(kind, parts[sz], vp(refs[0], origin), ctypes.c_ssize_t(STRIDE), vp(pred[sz]), ctypes.c_ssize_t(W), vp(ja), ctypes.c_int64(len(ja)), cores)
+        for cy in sample_rows:
+            y0 = cy * CTU
+            for idx, N in TU_SIZES:
+                qbits, add = quant_params(N)
+                R.ref_tu_pipeline(idx, 0, vp(cur, origin + y0 * STRIDE), ctypes.c_ssize_t(STRIDE), vp(pred[16], y0 * W), ctypes.c_ssize_t(W), vp(recon), ctypes.c_ssize_t(W),
+                                  W // N, CTU // N, vp(qtab), qbits, add, None, 40 << 5, 9, vp(tu_coef), vp(tu_ns), vp(tu_sse), cores)
+        for idx, N, _ in INTRA_SIZES:
+            R.ref_intra_batch(idx, vp(nbr[N]), vp(filt[N]), vp(intra_out[N]), ctypes.c_int64(len(nbr[N])), cores)
+
+    la = reference_lookahead(R, frames, STRIDE, origin, W, CTU_ROWS * CTU, cores)
+    sample = "CTU rows %s of %d (x%.1f to a frame): %d PU searches (3 refs), %d MC interpolations, DCT/quant/dequant/IDCT of their 32/16/8/4 TUs, 35 intra modes on their 8/16/32 blocks" % (
+        sample_rows, CTU_ROWS, 1 / frac, len(job), sum(len(a) for d in ip_jobs.values() for a in d.values()))
+    return step, frac, sample, la
+
+
+def reference_me(R, pkg, cfg, cores):
+    """configs 2 / 4 / 5: the frame search of the config's partition set on sampled CTU rows, through the reference's MotionEstimate"""
+    from me_util import REF_ME_JOB, ctu_jobs, ctu_layout
+    g = geometry(cfg)
+    C, depth, nref = cfg["C"], cfg["depth"], cfg["nref"]
+    ys = synth_planes(nref + 1, g["planeRows"], g["stride"], depth, seed=1234)
+    origin = g["padY"] * g["stride"] + g["padX"]
+    item = ys[0].itemsize
+    lay = ctu_layout(C, cfg["minCu"], cfg["rect"], cfg["amp"])
+    rows = sorted(set([0, g["rows"] // 2, g["rows"] - 1]))
+    if args_budget_small(cfg):
+        rows = [g["rows"] // 2]
+    mvp0 = np.zeros((len(lay), 2), dtype=np.int32)
+    jobs = []
+    for cy in rows:
+        for cx in range(g["cols"]):
+            j, searched = ctu_jobs(pkg, lay, C, cx, cy, cfg["W"], cfg["H"], mvp0, cfg["merange"])
+            jobs.append(j[searched])
+    job = np.concatenate(jobs)
+    rj = np.zeros(len(job), dtype=REF_ME_JOB)
+    for f in ("puX", "puY", "w", "h", "mvminX", "mvminY", "mvmaxX", "mvmaxY", "mvpX", "mvpY", "numCand", "mvc"):
+        rj[f] = job[f]
+    rj = rj[np.random.default_rng(3).permutation(len(rj))]
+    frac = len(rows) / g["rows"]
+    cur = ys[nref].ravel()
+    refs = [ys[nref - 1 - r].ravel() for r in range(nref)]
+    vp = lambda a, off=0: ctypes.c_void_p(a.ctypes.data + off * item)
+    if cfg["csp"]:
+        sc, rc = g["stride"] // 2, g["planeRows"] // 2
+        oc = (g["padY"] // 2) * sc + g["padX"] // 2
+        cbs = [p.ravel() for p in synth_planes(nref + 1, rc, sc, depth, seed=77, step=3)]
+        crs = [p.ravel() for p in synth_planes(nref + 1, rc, sc, depth, seed=99, step=3)]
+
+    def step():
+        for r in range(nref):
+            if cfg["csp"]:
+                R.ref_me_batch_chroma(vp(cur, origin), vp(cbs[nref], oc), vp(crs[nref], oc), ctypes.c_ssize_t(g["stride"]), ctypes.c_ssize_t(sc),
+                                      vp(refs[r], origin), vp(cbs[nref - 1 - r], oc), vp(crs[nref - 1 - r], oc), ctypes.c_ssize_t(g["stride"]), ctypes.c_ssize_t(sc),
+                                      int(cfg["csp"]), ctypes.c_void_p(rj.ctypes.data), ctypes.c_int64(len(rj)), int(cfg["method"]), int(cfg["subme"]), int(cfg["merange"]), QP, 1, cores)
+            else:
+                R.ref_me_batch(vp(cur, origin), ctypes.c_ssize_t(g["stride"]), vp(refs[r], origin), ctypes.c_ssize_t(g["stride"]),
+                               ctypes.c_void_p(rj.ctypes.data), ctypes.c_int64(len(rj)), int(cfg["method"]), int(cfg["subme"]), int(cfg["merange"]), QP, 1, cores)
+
+    sample = "CTU rows %s of %d: %d PU searches per reference x %d references (the reference's MotionEstimate::motionEstimate, %d PUs per CTU)" % (
+        rows, g["rows"], len(rj), nref, len(lay))
+    return step, frac, sample, {"s_per_frame_all_cores": 0.0, "how": "not part of this config's step"}
+
+
+def args_budget_small(cfg):
+    """configs whose per-row CPU cost is large get one sampled CTU row (the run must end within minutes)"""
+    return cfg["merange"] > 64 or cfg["subme"] >= 3
+
+
+# =====================================================================================================================
+# the B200 arm
+# =====================================================================================================================
+class Workload:
+    """frames of one config resident in a pool; step(t) = one frame through the config's hot path"""
+
+    def __init__(self, args, cfg, pkg, torch, ctx, dev, stream, rank, world, band=None):
+        self.args, self.cfg, self.pkg, self.torch, self.ctx, self.dev, self.stream = args, cfg, pkg, torch, ctx, dev, stream
+        self.rank, self.world = rank, world
+        g = self.g = geometry(cfg)
+        self.depth, self.C, self.nref = cfg["depth"], cfg["C"], cfg["nref"]
+        self.item = 2 if self.depth > 8 else 1
+        self.tdt = torch.int16 if self.item == 2 else torch.uint8
+        self.NF = cfg["NF"]
+        self.lam = pkg.lambda_for_qp(QP, self.depth)
+        seed = 1234 + (rank if args.shard == "frames" else 0)        # ctu-rows: every rank holds the SAME frames
+        ys = synth_planes(self.NF, g["planeRows"], g["stride"], self.depth, seed)
+        self.host_y = [torch.from_numpy(f.view(np.int16) if self.item == 2 else f).pin_memory() for f in ys]
+        self.pool = torch.empty((self.NF, g["planeRows"], g["stride"]), dtype=self.tdt, device=dev)
+        for i, h in enumerate(self.host_y):
+            self.pool[i].copy_(h)
+        self.origin = (g["padY"] * g["stride"] + g["padX"]) * self.item            # bytes from a plane's base to pixel (0,0)
+        self.plane_bytes = g["planeRows"] * g["stride"] * self.item
+        self.csp = cfg["csp"]
+        if self.csp:
+            sc, rc = g["stride"] // 2, g["planeRows"] // 2
+            self.sc, self.rc = sc, rc
+            self.originC = ((g["padY"] // 2) * sc + g["padX"] // 2) * self.item
+            self.poolC = []
+            self.hostC = []
+            for k, sd in enumerate((77, 99)):
+                cs = synth_planes(self.NF, rc, sc, self.depth, sd + seed, step=3)
+                hp = [torch.from_numpy(f.view(np.int16) if self.item == 2 else f).pin_memory() for f in cs]
+                p = torch.empty((self.NF, rc, sc), dtype=self.tdt, device=dev)
+                for i, h in enumerate(hp):
+                    p[i].copy_(h)
+                self.poolC.append(p); self.hostC.append(hp)
+            self.planeC_bytes = rc * sc * self.item
+        # CTU rows this rank searches (ctu-rows sharding: a band of ONE frame per rank)
+        self.row0, self.rows = (0, g["rows"]) if band is None else band
+        # streaming SAD outputs: [group][ref][grid]
+        nctu = g["cols"] * g["rows"]
+        self.sad_out = [torch.empty(max(1, self.NF // (self.nref + 1)) * self.nref * nctu * (64 // s) ** 2, dtype=torch.int32, device=dev) for s in (8, 16, 32, 64)]
+        self.launches_extra = 0
+
+    def frame(self, t):
+        return t % self.NF
+
+    def refs_of(self, t):
+        return [(t - 1 - r) % self.NF for r in range(self.nref)]
+
+    def yptr(self, f, base=False):
+        return self.pool[f].data_ptr() + (0 if base else self.origin)
+
+    def sad_stream(self, groups, out=None):
+        g = self.g
+        out = out or self.sad_out
+        self.ctx.sad_stream_dev(self.depth, self.pool.data_ptr() + self.origin, g["planeRows"] * g["stride"], g["stride"], g["padX"], g["padY"], g["planeRows"], self.NF,
+                                (self.cfg["W"] + 63) // 64 if self.C != 64 else g["cols"], (g["rows"] * self.C) // 64, groups, self.nref, *[o.data_ptr() for o in out])
+
+    def one_group(self, t):
+        grp = np.zeros(1, dtype=self.pkg.SAD_GROUP)
+        grp[0]["cur"] = self.frame(t)
+        grp[0]["ref"][:self.nref] = self.refs_of(t)
+        return grp
+
+    def sad_bytes(self, ngroups):
+        g = self.g
+        w64, h64 = ((self.cfg["W"] + 63) // 64 if self.C != 64 else g["cols"]) * 64, ((g["rows"] * self.C) // 64) * 64
+        nb = sum((w64 // s) * (h64 // s) for s in (8, 16, 32, 64))
+        return ngroups * ((1 + self.nref) * w64 * h64 * self.item + self.nref * nb * 4)
+
+    def join(self):
+        pass
+
+
+class MEWorkload(Workload):
+    """configs 2 / 4 / 5: streaming SAD at the predictor + the frame search with the config's partition set"""
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        cfg, g, pkg, torch = self.cfg, self.g, self.pkg, self.torch
+        self.npu = len(pkg.me_frame_layout(self.C, cfg["minCu"], cfg["rect"], cfg["amp"]))
+        self.nout = self.nref * g["cols"] * self.rows * self.npu
+        self.me_out = [torch.empty((self.nout, 3), dtype=torch.int32, device=self.dev) for _ in range(2)]
+        self.res_h = [torch.empty((self.nout, 3), dtype=torch.int32).pin_memory() for _ in range(2)]
+        self.params = dict(depth=self.depth, ctuSize=self.C, minCuSize=cfg["minCu"], rect=cfg["rect"], amp=cfg["amp"], picWidth=cfg["W"], picHeight=cfg["H"],
+                           ctuCols=g["cols"], ctuRows=self.rows, marginX=g["padX"], marginY=g["padY"] + self.row0 * self.C, rowsTotal=g["planeRows"],
+                           searchMethod=cfg["method"], subpelRefine=cfg["subme"], merange=cfg["merange"], csp=cfg["csp"], maxCand=0, maxSlices=1,
+                           firstCtuRow=self.row0, sliceTotalRows=g["rows"])
+        self.params["lambda"] = self.lam
+        self.shY = self.row0 * self.C * g["stride"] * self.item
+        self.shC = self.row0 * (self.C // 2) * (g["stride"] // 2) * self.item if self.csp else 0
+        self.units = {"pu_searches": None, "pus_per_ctu": self.npu, "ctus": g["cols"] * self.rows, "references": self.nref}
+        self.workload = cfg["name"] + "; step = streaming SAD at the predictor (all 2Nx2N levels x refs) + the frame search of every PU of the partition set, mvp = 0"
+
+    def chroma_kw(self, t):
+        if not self.csp:
+            return {}
+        f, refs = self.frame(t), self.refs_of(t)
+        o = self.originC + self.shC
+        return dict(curC=(self.poolC[0][f].data_ptr() + o, self.poolC[1][f].data_ptr() + o), curStrideC=self.sc,
+                    refCb=[self.poolC[0][r].data_ptr() + o for r in refs], refCr=[self.poolC[1][r].data_ptr() + o for r in refs], refStrideC=self.sc)
+
+    def step(self, t, k=0):
+        if self.row0 == 0:
+            self.sad_stream(self.one_group(t))
+        f, refs = self.frame(t), self.refs_of(t)
+        self.ctx.me_frame_ex_dev(self.params, self.yptr(f) + self.shY, self.g["stride"], [self.yptr(r) + self.shY for r in refs], self.g["stride"], self.me_out[k].data_ptr(),
+                                 **self.chroma_kw(t))
+        return self.me_out[k]
+
+    def e2e_step(self, t, k=0):
+        """the new frame arrives from pinned host memory through the host-buffer C-ABI entry; results land in pinned host memory"""
+        f, refs = self.frame(t), self.refs_of(t)
+        kw = self.chroma_kw(t)
+        if self.csp:
+            kw.update(hostC=(self.hostC[0][f].data_ptr(), self.hostC[1][f].data_ptr()), devCBase=(self.poolC[0][f].data_ptr(), self.poolC[1][f].data_ptr()),
+                      bytesC=self.planeC_bytes)
+        self.ctx.me_frame_ex_host(self.params, self.yptr(f) + self.shY, self.g["stride"], [self.yptr(r) + self.shY for r in refs], self.g["stride"],
+                                  self.host_y[f].data_ptr(), self.yptr(f, base=True), self.plane_bytes, self.me_out[k].data_ptr(), self.res_h[k].data_ptr(),
+                                  self.nout * 12, **kw)
+        if self.row0 == 0:
+            self.sad_stream(self.one_group(t))
+
+    def h2d_bytes(self):
+        return self.plane_bytes + (2 * self.planeC_bytes if self.csp else 0)
+
+    def d2h_bytes(self):
+        return self.nout * 12
+
+    def count_units(self):
+        out = self.me_out[0].cpu().numpy()
+        self.units["pu_searches"] = int((out[:, 2] >= 0).sum())
+
+
+class MixWorkload(Workload):
+    """config 3: the full primitive mix + the lookahead on a second stream"""
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        pkg, torch, dev, ctx = self.pkg, self.torch, self.dev, self.ctx
+        P = lambda t: t.data_ptr()
+        self.P = P
+        job_h = build_jobs(pkg)
+        self.njobs = len(job_h)
+        self.me_out = [torch.empty((self.njobs, 3), dtype=torch.int32, device=dev) for _ in range(2)]
+        self.res_h = [torch.empty((self.njobs, 3), dtype=torch.int32).pin_memory() for _ in range(2)]
+        n32 = (W // 32) * (CTU_ROWS * 2)
+        self.n32 = n32
+        self.qcoef = torch.empty(n32 * 1024, dtype=torch.int16, device=dev)
+        self.recon = torch.empty((CTU_ROWS * CTU, W), dtype=torch.uint8, device=dev)
+        self.qtab = torch.full((1024,), 26214, dtype=torch.int32, device=dev)          # quantScales[qp%6=0] flat list
+        self.numsig = torch.empty((W // 4) * (CTU_ROWS * CTU // 4), dtype=torch.int32, device=dev)
+        self.tu_sse = torch.empty((W // 4) * (CTU_ROWS * CTU // 4), dtype=torch.int64, device=dev)
+        self.ip_jobs_h = {sz: interp_jobs(pkg, sz) for sz in LEVELS}
+        self.ip_jobs_d = {sz: {k: torch.from_numpy(a.view(np.uint8).copy()).to(dev) for k, a in self.ip_jobs_h[sz].items() if len(a)} for sz in LEVELS}
+        self.n_interp = sum(len(a) for d in self.ip_jobs_h.values() for a in d.values())
+        self.pred = {sz: torch.zeros((CTU_ROWS * CTU, W), dtype=torch.uint8, device=dev) for sz in LEVELS}
+        frame0 = self.host_y[0].numpy().ravel()
+        self.nbr_d, self.n_intra = {}, 0
+        for _, N, _ in INTRA_SIZES:
+            a = neighbour_arrays(frame0, N)
+            self.nbr_d[N] = torch.from_numpy(a).to(dev)
+            self.n_intra += len(a)
+        self.allangs_out = torch.empty(35 * W * CTU_ROWS * CTU, dtype=torch.uint8, device=dev)       # 35 modes x every pixel, reused per size
+        self.units = {"pu_searches": self.njobs, "mc_interpolations": self.n_interp, "tu_per_size": {str(N): (W // N) * (CTU_ROWS * CTU // N) for _, N in TU_SIZES},
+                      "intra_blocks_x35_modes": self.n_intra, "lookahead_list_searches_per_frame": 2 * (LA_BFRAMES + 1)}
+        self.workload = WORKLOAD3
+        self.init_lookahead()
+
+    # ---- the lookahead half of the path, on its own stream / context --------------------------------------------------
+    def init_lookahead(self):
+        torch, pkg, dev = self.torch, self.pkg, self.dev
+        # same priority as the main stream: measured 4.25 ms/step; giving the lookahead priority makes its CTAs displace frame-search
+        # CTAs on every SM and costs more than it hides (5.2 ms/step), see DESIGN.md 7
+        self.la_stream = torch.cuda.Stream(device=dev)
+        self.la_ctx = pkg.Ctx(dev.index, stream=self.la_stream.cuda_stream)
+        Wc, Hc = W, CTU_ROWS * CTU
+        mx, my = PAD, 80
+        self.wcu, self.hcu = (Wc // 2 + 7) // 8, (Hc // 2 + 7) // 8
+        self.lw, self.ll = self.wcu * 8, self.hcu * 8
+        self.ls = (Wc // 2 + 2 * mx + 31) & ~31
+        self.lmx, self.lmy = mx, my
+        planesize, padoff, ncu = self.ls * (self.ll + 2 * my), self.ls * my + mx, self.wcu * self.hcu
+        self.ncu = ncu
+        NL = self.NF
+        self.la_planes = torch.zeros((NL, 4, planesize), dtype=torch.uint8, device=dev)
+        self.la_ptrs = np.array([[self.la_planes[i, k].data_ptr() + padoff for k in range(4)] for i in range(NL)], dtype=np.int64)
+        self.la_plane_ptrs_d = torch.from_numpy(self.la_ptrs.copy()).to(dev)
+        self.la_intra_cost = torch.empty((NL, ncu), dtype=torch.int32, device=dev)
+        self.la_intra_ptrs_d = torch.tensor([self.la_intra_cost[i].data_ptr() for i in range(NL)], dtype=torch.int64, device=dev)
+        self.la_im = torch.empty(ncu, dtype=torch.uint8, device=dev)
+        self.la_lc0 = torch.empty(ncu, dtype=torch.int16, device=dev)
+        self.la_rs0 = torch.empty(self.hcu, dtype=torch.int32, device=dev)
+        self.la_sm0 = torch.empty(2, dtype=torch.int32, device=dev)
+        self.la_lam = pkg.lambda_for_qp(12, 8)
+        nslots = NL * 2 * (LA_BFRAMES + 2)
+        self.la_mv = torch.zeros(nslots * ncu * 2, dtype=torch.int32, device=dev)
+        self.la_mvc = torch.zeros(nslots * ncu, dtype=torch.int32, device=dev)
+        ntr = LA_BATCH * (LA_BFRAMES + 1)
+        self.la_lc = torch.empty(ntr * ncu, dtype=torch.int16, device=dev)
+        self.la_rs = torch.empty(ntr * self.hcu, dtype=torch.int32, device=dev)
+        self.la_sm = torch.empty(ntr * 4, dtype=torch.int32, device=dev)
+        self.la_pending = []
+        # every frame of the ring gets its lowres planes + intra costs once (the triples reach LA_BFRAMES + 1 frames back and forth)
+        for i in range(NL):
+            self.la_frame(i)
+        self.la_ctx.sync()
+
+    def la_frame(self, f):
+        """Lowres::init + lowresIntraEstimate of frame f"""
+        c, P = self.la_ctx, self.P
+        c.lowres_init_dev(8, self.yptr(f), STRIDE, self.la_ptrs[f], self.ls, self.lw, self.ll, self.lmx, self.lmy)
+        c.la_intra_dev(8, self.la_ptrs[f, 0], self.ls, self.wcu, self.hcu, None, 5 * int(self.la_lam), P(self.la_intra_cost[f]), P(self.la_im), P(self.la_lc0), P(self.la_rs0), P(self.la_sm0))
+
+    def la_estimate(self, frames):
+        """estimateFrameCost for the queued frames: per frame b the triples (b - d, b + d, b), d = 1 .. bframes + 1, both lists searched"""
+        NL = self.NF
+        # (the ring wraps: frames within bframes + 1 of its ends search the same amount of work around a legal centre)
+        centre = lambda b: min(max(b, LA_BFRAMES + 1), NL - LA_BFRAMES - 2)
+        wave = [(centre(b) - d, centre(b) + d, centre(b)) for b in frames for d in range(1, LA_BFRAMES + 2)]
+        tr = np.zeros(len(wave), dtype=self.pkg.LA_TRIPLE)
+        for t, (p0, p1, b) in enumerate(wave):
+            d = t % (LA_BFRAMES + 1) + 1
+            # frame indices must be ordered p0 < b < p1 for the kernel only as identities of planes; keep the ring's
+            tr[t]["b"], tr[t]["p0"], tr[t]["p1"] = b, p0, p1
+            for lst in (0, 1):
+                tr[t]["mvSlot"][lst] = (b * 2 + lst) * (LA_BFRAMES + 2) + d
+                tr[t]["doSearch"][lst] = 1
+        P = self.P
+        self.la_ctx.la_estimate_dev(8, P(self.la_plane_ptrs_d), self.ls, self.wcu, self.hcu, tr, P(self.la_mv), P(self.la_mvc), P(self.la_intra_ptrs_d), None,
+                                    P(self.la_lc), P(self.la_rs), P(self.la_sm), self.la_lam, lookaheadSlices=LA_SLICES)
+
+    def lookahead_step(self, t, ev_frame_ready):
+        """called once per step: the new frame's lowres work now, the batch's list searches every LA_BATCH frames"""
+        self.la_stream.wait_event(ev_frame_ready)
+        f = self.frame(t)
+        self.la_frame(f)
+        self.la_pending.append(f)
+        if len(self.la_pending) == LA_BATCH:
+            self.la_estimate(self.la_pending)
+            self.la_pending = []
+
+    def join(self):
+        if self.la_pending:                       # a partial batch at the end of the timed region still has to be searched
+            self.la_estimate(self.la_pending)
+            self.la_pending = []
+        self.stream.wait_stream(self.la_stream)
+
+    # ---- one frame ------------------------------------------------------------------------------------------------------
+    def stages_after_search(self, t):
+        ctx, P = self.ctx, self.P
+        f, refs = self.frame(t), self.refs_of(t)
+        cptr, r0 = self.yptr(f), self.yptr(refs[0])
+        HH = CTU_ROWS * CTU
+        for sz in LEVELS:
+            for kind, jd in self.ip_jobs_d[sz].items():
+                ctx.interp_dev(kind, 8, 8, sz, sz, r0, STRIDE, P(self.pred[sz]), W, P(jd), len(self.ip_jobs_h[sz][kind]), 0)
+        for idx, N in TU_SIZES:
+            qbits, add = quant_params(N)
+            ctx.tu_pipeline_dev(idx, 8, 0, cptr, STRIDE, P(self.pred[16]), W, P(self.recon), W, W // N, HH // N, P(self.qtab), qbits, add, None, 40 << 5, 9,
+                                P(self.qcoef), P(self.numsig), P(self.tu_sse))
+        for _, N, log2N in INTRA_SIZES:
+            ctx.intra_modes_dev(8, log2N, P(self.nbr_d[N]), P(self.allangs_out), int(N <= 16), self.nbr_d[N].shape[0])
+
+    def step(self, t, k=0, events=None):
+        torch = self.torch
+        parts = os.environ.get("BENCH_PARTS", "both")          # diagnosis only: "main" / "la" time one half of the step alone
+        if parts != "main":
+            ev = torch.cuda.Event(); ev.record(self.stream)
+            self.lookahead_step(t, ev)
+        if parts == "la":
+            return self.me_out[k]
+        f, refs = self.frame(t), self.refs_of(t)
+        if events is not None:
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            e[0].record(self.stream)
+        self.sad_stream(self.one_group(t))
+        if events is not None:
+            e[1].record(self.stream)
+        self.ctx.me_frame_dev(8, self.yptr(f), STRIDE, [self.yptr(r) for r in refs], STRIDE, PAD, PAD, ROWS, CTU_COLS, CTU_ROWS, 15, None,
+                              ME_HEX, SUBME, MERANGE, self.lam, self.P(self.me_out[k]))
+        if events is not None:
+            e[2].record(self.stream); events.append(e)
+        self.stages_after_search(t)
+        return self.me_out[k]
+
+    def e2e_step(self, t, k=0):
+        torch = self.torch
+        f, refs = self.frame(t), self.refs_of(t)
+        self.ctx.me_frame_host(8, self.host_y[f].data_ptr(), self.plane_bytes, self.yptr(f, base=True), STRIDE, [self.yptr(r) for r in refs], STRIDE, PAD, PAD, ROWS,
+                               CTU_COLS, CTU_ROWS, 15, None, ME_HEX, SUBME, MERANGE, self.lam, self.P(self.me_out[k]), self.res_h[k].data_ptr(), self.njobs * 12)
+        ev = torch.cuda.Event(); ev.record(self.stream)
+        self.lookahead_step(t, ev)
+        self.sad_stream(self.one_group(t))
+        self.stages_after_search(t)
+
+    def h2d_bytes(self):
+        return self.plane_bytes
+
+    def d2h_bytes(self):
+        return self.njobs * 12
+
+    def count_units(self):
+        pass
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
+    ap.add_argument("--config", type=int, default=3, choices=sorted(CONFIGS))
+    ap.add_argument("--shard", default="frames", choices=["frames", "ctu-rows"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
@@ -277,133 +728,51 @@ def main():
     ctx = pkg.Ctx(local, stream=stream.cuda_stream)       # fails loudly without the CUDA library
     assert stream.cuda_stream != 0 and ctx.stream == stream.cuda_stream
     dev = torch.device("cuda", local)
-    lam = pkg.lambda_for_qp(QP, 8)
+    cfg = CONFIGS[args.config]
+    warm = max(args.warmup, 3)
+    K = args.steps
 
-    # ---- resident data: a ring of frames (> L2), static PU descriptors ------------------------------
-    NF = 32                       # 32 x 9.9 MB padded planes = 318 MB > L2 (126 MB)
-    frames_h = synth_frames(NF, seed=1234 + rank)
-    pinned = [torch.from_numpy(f).pin_memory() for f in frames_h]
-    ring = [torch.empty((ROWS, STRIDE), dtype=torch.uint8, device=dev) for _ in range(NF)]
-    for d, h in zip(ring, pinned):
-        d.copy_(h)
-    job_h = build_jobs(pkg)
-    job_h = job_h[np.argsort(-job_h["w"], kind="stable")]          # group by PU size (64, 32, 16, 8)
-    njobs = len(job_h)
-    job_bytes = job_h.dtype.itemsize
-    level_ranges = {}
-    for s in LEVELS:
-        idx = np.nonzero(job_h["w"] == s)[0]
-        level_ranges[s] = (int(idx[0]), int(len(idx)))
-    jobs_d = torch.from_numpy(job_h.view(np.uint8).reshape(njobs, -1).copy()).to(dev)
-    origin = PAD * STRIDE + PAD
-    ref_ptr_table = torch.tensor([[ring[(t - 1 - r) % NF].data_ptr() + origin for r in range(NREF)] for t in range(NF)],
-                                 dtype=torch.int64).to(dev)
-    level_n = {s: (W // s) * ((CTU_ROWS * CTU) // s) for s in LEVELS}
-    sad_out = {s: torch.empty(NREF * level_n[s], dtype=torch.int32, device=dev) for s in LEVELS}
-    n32 = (W // 32) * (CTU_ROWS * 2)
-    qcoef = torch.empty(n32 * 1024, dtype=torch.int16, device=dev)
-    recon = torch.empty((CTU_ROWS * CTU, W), dtype=torch.uint8, device=dev)
-    qtab = torch.full((1024,), 26214, dtype=torch.int32, device=dev)          # quantScales[qp%6=0] flat list
-    numsig = torch.empty((W // 4) * (CTU_ROWS * CTU // 4), dtype=torch.int32, device=dev)
-    tu_sse = torch.empty((W // 4) * (CTU_ROWS * CTU // 4), dtype=torch.int64, device=dev)
-    # MC jobs (static), prediction planes, intra neighbour arrays (taken once from frame 0: static inputs) and outputs
-    ip_jobs_h = {sz: interp_jobs(pkg, sz) for sz in LEVELS}
-    ip_jobs_d = {sz: {k: torch.from_numpy(a.view(np.uint8).copy()).to(dev) for k, a in ip_jobs_h[sz].items() if len(a)} for sz in LEVELS}
-    n_interp = sum(len(a) for d in ip_jobs_h.values() for a in d.values())
-    pred = {sz: torch.zeros((CTU_ROWS * CTU, W), dtype=torch.uint8, device=dev) for sz in LEVELS}
-    nbr_d, n_intra = {}, 0
-    for _, N, _ in INTRA_SIZES:
-        a = neighbour_arrays(frames_h[0].ravel(), N)
-        nbr_d[N] = torch.from_numpy(a).to(dev)
-        n_intra += len(a)
-    allangs_out = torch.empty(35 * W * CTU_ROWS * CTU, dtype=torch.uint8, device=dev)       # 35 modes x every pixel, reused per size
-    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
-    me_out = torch.empty((njobs, 3), dtype=torch.int32, device=dev)
-    res_h = torch.empty((njobs, 3), dtype=torch.int32).pin_memory()
-    P = lambda t: t.data_ptr()
+    band = None
+    if args.shard == "ctu-rows" and world > 1:
+        rows_all = geometry(cfg)["rows"]
+        lo = (rows_all * rank) // world; hi = (rows_all * (rank + 1)) // world
+        band = (lo, hi - lo)
+    if args.config == 3 and args.shard == "ctu-rows":
+        raise SystemExit("--shard ctu-rows applies to the frame-search configs (2, 4, 5)")
+    wl = (MixWorkload if args.config == 3 else MEWorkload)(args, cfg, pkg, torch, ctx, dev, stream, rank, world, band)
 
-    sad_events = []
-    me_events = []
-
-    def hot_path(t, time_sad=False, out=None):
-        out = me_out if out is None else out
-        cur = ring[t % NF]
-        refs = [ring[(t - 1 - r) % NF] for r in range(NREF)]
-        ref_ptrs = ref_ptr_table[t % NF]
-        cptr = P(cur) + origin
-        # 1. SAD at the predictor for every PU level x ref: ONE streaming pass per reference (SAD pyramid)
-        if time_sad:
-            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True); e0.record()
-        ctx.sad_pyramid_dev(8, cptr, STRIDE, P(ref_ptrs), NREF, STRIDE, CTU_COLS, CTU_ROWS, None,
-                            P(sad_out[8]), P(sad_out[16]), P(sad_out[32]), P(sad_out[64]))
-        if time_sad:
-            e1.record(); sad_events.append((e0, e1))
-        # 2. full motion search for every PU x ref: TMA-staged windows, one CTA per (CTU, ref)
-        if time_sad:
-            m0 = torch.cuda.Event(enable_timing=True); m1 = torch.cuda.Event(enable_timing=True); m0.record()
-        ctx.me_frame_dev(8, cptr, STRIDE, [P(r) + origin for r in refs], STRIDE, PAD, PAD, ROWS, CTU_COLS, CTU_ROWS, 15, None,
-                         pkg.ME_HEX, SUBME, MERANGE, lam, P(out))
-        if time_sad:
-            m1.record(); me_events.append((m0, m1))
-        # 3. MC: one 8-tap interpolation per PU and level from reference 0 (HPP / VPP / HVPP by fraction)
-        HH = CTU_ROWS * CTU
-        r0 = P(refs[0]) + origin
-        for sz in LEVELS:
-            for kind, jd in ip_jobs_d[sz].items():
-                ctx.interp_dev(kind, 8, 8, sz, sz, r0, STRIDE, P(pred[sz]), W, P(jd), len(ip_jobs_h[sz][kind]), 0)
-        # 4. residual against the 16x16-level prediction -> DCT -> quant -> dequant -> IDCT -> recon -> SSE on every TU size:
-        #    the fused residual pipeline (Quant::transformNxN + invtransformNxN chain, one launch per TU size)
-        for idx, N in TU_SIZES:
-            qbits, add = quant_params(N)
-            ctx.tu_pipeline_dev(idx, 8, 0, cptr, STRIDE, P(pred[16]), W, P(recon), W, W // N, HH // N, P(qtab), qbits, add, None, 40 << 5, 9,
-                                P(qcoef), P(numsig), P(tu_sse))
-        # 5. intra: neighbour smoothing + DC + planar + the 33 angular modes of every 8/16/32 block, one fused launch per size
-        #    (the prediction half of Search::estIntraPredQT, search.cpp:1358-1400)
-        for _, N, log2N in INTRA_SIZES:
-            ctx.intra_modes_dev(8, log2N, P(nbr_d[N]), P(allangs_out), int(N <= 16), nbr_d[N].shape[0])
-
-    # ---- N > 1: the path's one real exchange: every rank needs the reference pixels the others
-    # produced, and rank 0 collects the per-PU {mv,cost}.  One all_gather of the new luma plane + one gather.
+    # ---- N > 1: the path's exchange on a comm stream, overlapped with the next step ----------------------------
+    comm = torch.cuda.Stream(device=local) if world > 1 else None
+    g = wl.g
     if world > 1:
-        gathered = torch.empty((world * ROWS, STRIDE), dtype=torch.uint8, device=dev)   # concatenated form
-        res_all = [torch.empty((njobs, 3), dtype=torch.int32, device=dev) for _ in range(world)] if rank == 0 else None
+        if args.shard == "frames":
+            # every rank needs the reference pixels the others produced: all_gather of the new luma plane; rank 0 collects the {mv,cost} records
+            gathered = [torch.empty((world,) + tuple(wl.pool[0].shape), dtype=wl.tdt, device=dev) for _ in range(2)]
+        else:
+            # ctu-rows: the bands of reconstructed rows are all_gathered (equal-sized chunks of the plane), results gathered
+            rows_px = g["rows"] * wl.C
+            chunk = (rows_px + world - 1) // world
+            gathered = [torch.empty((world, chunk, g["stride"]), dtype=wl.tdt, device=dev) for _ in range(2)]
+        nres = wl.me_out[0].shape[0]
+        res_max = torch.tensor([nres], device=dev); dist.all_reduce(res_max, op=dist.ReduceOp.MAX); res_max = int(res_max)
+        send = [torch.zeros((res_max, 3), dtype=torch.int32, device=dev) for _ in range(2)]
+        res_all = [[torch.empty((res_max, 3), dtype=torch.int32, device=dev) for _ in range(world)] for _ in range(2)] if rank == 0 else [None, None]
+    comm_events = [None, None]
 
-    def exchange(t, out=None):
+    def exchange(t, k, out):
         if world == 1:
             return
-        dist.all_gather_into_tensor(gathered, ring[t % NF])
-        dist.gather(me_out if out is None else out, res_all, dst=0)
-
-    # end-to-end: every step uploads its frame from pinned host memory and reads its {mv,cost} results back.  The copies run on
-    # a second stream so that the upload of frame t+1 and the read-back of step t overlap the kernels of the neighbouring step
-    # (double-buffered result arrays); every copy of every step is inside the timed region.
-    copy_stream = torch.cuda.Stream(device=local)
-    out2 = [me_out, torch.empty_like(me_out)]
-    res_h2 = [res_h, torch.empty((njobs, 3), dtype=torch.int32).pin_memory()]
-
-    def e2e_run(first, count):
-        def upload(t):
-            with torch.cuda.stream(copy_stream):
-                ring[t % NF].copy_(pinned[t % NF], non_blocking=True)           # H2D: the new frame
-                ev = torch.cuda.Event(); ev.record(copy_stream)
-            return ev
-        ev_next = upload(first)
-        d2h_ev = [None, None]
-        for i in range(count):
-            t, k = first + i, i & 1
-            stream.wait_event(ev_next)
-            if i + 1 < count:
-                ev_next = upload(t + 1)
-            if d2h_ev[k] is not None:
-                stream.wait_event(d2h_ev[k])                                     # result buffer k has been read back
-            hot_path(t, out=out2[k])
-            exchange(t, out=out2[k])
-            done = torch.cuda.Event(); done.record(stream)
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(done)
-                res_h2[k].copy_(out2[k], non_blocking=True)                     # D2H: {mvx, mvy, cost} per PU
-                d2h_ev[k] = torch.cuda.Event(); d2h_ev[k].record(copy_stream)
-        torch.cuda.synchronize()
+        done = torch.cuda.Event(); done.record(stream)
+        with torch.cuda.stream(comm):
+            comm.wait_event(done)
+            if args.shard == "frames":
+                dist.all_gather_into_tensor(gathered[k], wl.pool[wl.frame(t)])
+            else:
+                y0 = wl.g["padY"] + rank * gathered[k].shape[1]
+                dist.all_gather_into_tensor(gathered[k], wl.pool[wl.frame(t)][y0:y0 + gathered[k].shape[1]].contiguous())
+            send[k][:out.shape[0]].copy_(out)
+            dist.gather(send[k], res_all[k], dst=0)
+            comm_events[k] = torch.cuda.Event(); comm_events[k].record(comm)
 
     def barrier():
         torch.cuda.synchronize()
@@ -411,79 +780,105 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    t_first = wl.nref + LA_BFRAMES + 2
+
+    def run_steps(first, count, events=None):
+        for i in range(count):
+            k = i & 1
+            if comm_events[k] is not None:
+                stream.wait_event(comm_events[k])          # result buffer k has been gathered
+            out = wl.step(first + i, k, events) if isinstance(wl, MixWorkload) else wl.step(first + i, k)
+            exchange(first + i, k, out)
+        wl.join()
+        if comm is not None:
+            stream.wait_stream(comm)
+
     # ---- warm-up ---------------------------------------------------------------------------------------
-    for i in range(max(args.warmup, 3)):
-        hot_path(NREF + i)
-        exchange(NREF + i)
+    run_steps(t_first, warm)
     barrier()
-    launches0 = ctx.launches
+    wl.count_units()
+    launches0 = ctx.launches + (wl.la_ctx.launches if hasattr(wl, "la_ctx") else 0)
 
     sampler = ClockSampler(local); sampler.start()
-    # ---- device-resident timing: per-step CUDA events, L2 flushed between steps -----------------------------
-    evs = []
+    # ---- device-resident timing: K steps between two events on the main stream (the lookahead and comm streams are joined
+    # before the closing event); frames come from a ring larger than L2, so no flush is needed
     barrier()
-    for i in range(args.steps):
-        flush.fill_(i & 255)                                                   # > L2 (126 MB): evicts frames and tables
-        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-        e0.record()
-        hot_path(NREF + i, time_sad=True)
-        exchange(NREF + i)
-        e1.record()
-        evs.append((e0, e1))
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    run_steps(t_first + warm, K)
+    e1.record(stream)
     barrier()
-    step_ms = [a.elapsed_time(b) for a, b in evs]
-    total_ms = float(sum(step_ms))
-    sad_ms = [a.elapsed_time(b) for a, b in sad_events]
-    me_ms = [a.elapsed_time(b) for a, b in me_events]
-    launches = ctx.launches - launches0
+    total_ms = e0.elapsed_time(e1)
+    launches = ctx.launches + (wl.la_ctx.launches if hasattr(wl, "la_ctx") else 0) - launches0
 
-    # ---- roofline of the streaming ME-SAD kernel: 8 back-to-back launches over DISJOINT frame sets (each plane
-    # byte comes from HBM exactly once: L2 flushed first, 8 x 4 planes = 318 MB > L2), CUDA events around the loop
-    groups = NF // (NREF + 1)
-    grp_ptrs = torch.tensor([[ring[g * (NREF + 1) + 1 + r].data_ptr() + origin for r in range(NREF)] for g in range(groups)], dtype=torch.int64).to(dev)
+    # ---- per-kernel times of the two ME kernels (a separate short pass: events inside the step) ---------------------------
+    stage_events = []
+    if isinstance(wl, MixWorkload):
+        run_steps(t_first, 4, stage_events)
+        torch.cuda.synchronize()
+    sad_ms = [e[0].elapsed_time(e[1]) for e in stage_events]
+    me_ms = [e[1].elapsed_time(e[2]) for e in stage_events]
 
-    def sad_loop():
-        for g in range(groups):
-            ctx.sad_pyramid_dev(8, P(ring[g * (NREF + 1)]) + origin, STRIDE, P(grp_ptrs[g]), NREF, STRIDE, CTU_COLS, CTU_ROWS, None,
-                                P(sad_out[8]), P(sad_out[16]), P(sad_out[32]), P(sad_out[64]))
-    # the 8 launches are captured in a CUDA graph so the GPU is not waiting on Python/ctypes launch overhead
-    sad_loop(); torch.cuda.synchronize()
+    # ---- roofline of the streaming ME-SAD kernel: ONE launch over `groups` disjoint (frame, references) groups -- every plane
+    # byte comes from HBM exactly once (the ring is larger than L2 and each launch walks all of it), timed as a CUDA graph so
+    # that the events bracket GPU time only
+    groups = max(1, wl.NF // (wl.nref + 1))
+    grp = np.zeros(groups, dtype=pkg.SAD_GROUP)
+    for gi in range(groups):
+        grp[gi]["cur"] = gi * (wl.nref + 1)
+        grp[gi]["ref"][:wl.nref] = [gi * (wl.nref + 1) + 1 + r for r in range(wl.nref)]
+    wl.sad_stream(grp); torch.cuda.synchronize()
     sad_graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(sad_graph, stream=stream):
-        sad_loop()
+        wl.sad_stream(grp)
     sad_loop_ms = []
-    for rep in range(max(args.steps, 3) + 1):
-        flush.fill_(rep & 255)
+    for rep in range(max(K, 5) + 1):
         r0 = torch.cuda.Event(enable_timing=True); r1 = torch.cuda.Event(enable_timing=True)
-        r0.record(); sad_graph.replay(); r1.record()
+        r0.record(stream); sad_graph.replay(); r1.record(stream)
         torch.cuda.synchronize()
         if rep:                                  # first repetition is the warm-up
-            sad_loop_ms.append(r0.elapsed_time(r1) / groups)
+            sad_loop_ms.append(r0.elapsed_time(r1))
+    del sad_graph
 
-    # the transform stage measured the same way (DCT32 over the residual plane, 8 back-to-back launches on 8 planes)
-    resid_ring = [torch.randint(-255, 256, (CTU_ROWS * CTU, W), dtype=torch.int16, device=dev) for _ in range(8)]
-    coef_ring = [torch.empty(n32 * 1024, dtype=torch.int16, device=dev) for _ in range(8)]
-    def dct_loop():
-        for k in range(8):
-            ctx.dct_plane_dev(3, 8, P(resid_ring[k]), W, W // 32, (CTU_ROWS * CTU) // 32, P(coef_ring[k]))
-    dct_loop(); torch.cuda.synchronize()
-    dct_graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(dct_graph, stream=stream):
-        dct_loop()
-    dct_ms = []
-    for rep in range(4):
-        flush.fill_(rep)
-        r0 = torch.cuda.Event(enable_timing=True); r1 = torch.cuda.Event(enable_timing=True)
-        r0.record(); dct_graph.replay(); r1.record(); torch.cuda.synchronize()
-        if rep:
-            dct_ms.append(r0.elapsed_time(r1) / 8)
-    del dct_graph, resid_ring, coef_ring
+    dct_line = None
+    if isinstance(wl, MixWorkload):
+        # the transform stage measured the same way (DCT32 over the residual plane, 8 back-to-back launches on 8 planes)
+        resid_ring = [torch.randint(-255, 256, (CTU_ROWS * CTU, W), dtype=torch.int16, device=dev) for _ in range(8)]
+        coef_ring = [torch.empty(wl.n32 * 1024, dtype=torch.int16, device=dev) for _ in range(8)]
 
-    # ---- end-to-end timing (host buffers in, results out) ---------------------------------------------------
-    e2e_run(NREF, 2)
+        def dct_loop():
+            for kk in range(8):
+                ctx.dct_plane_dev(3, 8, resid_ring[kk].data_ptr(), W, W // 32, (CTU_ROWS * CTU) // 32, coef_ring[kk].data_ptr())
+        dct_loop(); torch.cuda.synchronize()
+        dct_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(dct_graph, stream=stream):
+            dct_loop()
+        dct_ms = []
+        for rep in range(4):
+            r0 = torch.cuda.Event(enable_timing=True); r1 = torch.cuda.Event(enable_timing=True)
+            r0.record(stream); dct_graph.replay(); r1.record(stream); torch.cuda.synchronize()
+            if rep:
+                dct_ms.append(r0.elapsed_time(r1) / 8)
+        del dct_graph, resid_ring, coef_ring
+        dct_line = dct_ms
+
+    # ---- end-to-end timing (host buffers in, results out, through the host-buffer C-ABI entry) ---------------------------
+    def e2e_run(first, count):
+        for i in range(count):
+            k = i & 1
+            if comm_events[k] is not None:
+                stream.wait_event(comm_events[k])
+            wl.e2e_step(first + i, k)
+            exchange(first + i, k, wl.me_out[k])
+        wl.join()
+        if comm is not None:
+            stream.wait_stream(comm)
+        torch.cuda.synchronize()
+
+    e2e_run(t_first, 2)
     barrier()
     t0 = time.perf_counter()
-    e2e_run(NREF, args.steps)
+    e2e_run(t_first + 2, K)
     barrier()
     e2e_s = time.perf_counter() - t0
     sampler.stop_flag = True; sampler.join(timeout=2)
@@ -495,100 +890,61 @@ def main():
 
     if rank == 0:
         pk, pk_kind = peaks()
-        fps = world * args.steps / (total_ms / 1e3)
-        e2e_fps = world * args.steps / e2e_s
-        # roofline of the streaming ME-SAD kernel: algorithmic bytes = 2*W*H + nPU*4 per (level, ref) launch
-        sad_launches = 1
-        sad_bytes = (2 * W * (CTU_ROWS * CTU) + sum(level_n[s] * 4 for s in LEVELS)) * NREF
-        sad_t = float(np.mean(sad_loop_ms)) / 1e3
+        frames_done = K * (world if args.shard == "frames" else 1)
+        fps = frames_done / (total_ms / 1e3)
+        e2e_fps = frames_done / e2e_s
+        sad_bytes = wl.sad_bytes(groups)
+        sad_t = float(np.median(sad_loop_ms)) / 1e3
         achieved = sad_bytes / sad_t / 1e9
-        line = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "u8", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "units_per_step": {"pu_searches": njobs, "mc_interpolations": n_interp, "tu_per_size": {str(N): (W // N) * (CTU_ROWS * CTU // N) for _, N in TU_SIZES}, "intra_blocks_x35_modes": n_intra},
-                           "l2": "512 MiB flush between timed steps", "parallelism": "frame-parallel x%d" % world},
+        traffic = SAD_STREAM_DRAM_BYTES.get((args.config, groups))
+        line = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": warm,
+                "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak" if args.shard == "frames" else "strong", "vs_baseline": None,
+                "dtype": "u8" if cfg["depth"] == 8 else "u16", "data": "synthetic",
+                "config": {"workload": wl.workload, "baseline_config": args.config, "units_per_step": wl.units,
+                           "l2": "frames come from a ring of %d frames (%.0f MB) larger than L2; no flush" % (wl.NF, wl.NF * wl.plane_bytes / 1e6),
+                           "parallelism": ("frame-parallel x%d (all_gather of the new plane + gather of results on a comm stream)" % world) if args.shard == "frames"
+                                          else ("CTU-row bands of one frame x%d (all_gather of the bands' rows + gather of results)" % world)},
                 "clocks": sampler.summary(), "gpu_launches": int(launches),
-                "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": ROWS * STRIDE, "d2h_bytes_per_step": njobs * 12},
-                "roofline": {"kernel": "sad_pyramid_kernel (streaming ME SAD at the predictor, all 4 PU levels in one pass per reference)", "bound": "hbm", "achieved": achieved,
-                             "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": SAD_PYRAMID_DRAM_BYTES,
-                             "traffic_src": "profiles/r01_pyramid_dct_v3.txt (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum per launch; the current frame is fetched from DRAM once and re-read by the 2 other references through L2, outputs stay in L2)",
-                             "peak_kind": pk_kind, "launches_per_step": sad_launches, "us_per_launch": sad_t * 1e6,
-                             "how": "%d back-to-back launches (one CUDA graph) on disjoint frame sets after an L2 flush, CUDA events; in-step (single launch between events): %.1f us" % (groups, float(np.mean(sad_ms)) * 1e3)}}
-        dct_bytes = n32 * 1024 * 2 * 2
-        dct_t = float(np.mean(dct_ms)) / 1e3
-        line["roofline_dct32"] = {"kernel": "xform_mma_kernel<32,fwd> (IMMA)", "bound": "hbm", "achieved": dct_bytes / dct_t / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                                  "frac": dct_bytes / dct_t / 1e9 / pk["hbm_gbs"], "us_per_launch": dct_t * 1e6, "blocks": n32}
-        me_bytes = NREF * (2 * W * (CTU_ROWS * CTU)) + njobs * 8
-        me_t = float(np.mean(me_ms)) / 1e3
-        line["roofline_me_search"] = {"kernel": "me_frame_kernel (TMA-staged windows; HEX + subme 2, %d searches)" % njobs, "bound": "hbm", "achieved": me_bytes / me_t / 1e9,
-                                      "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": me_bytes / me_t / 1e9 / pk["hbm_gbs"], "ms_per_step": me_t * 1e3,
-                                      "note": "instruction-issue/fetch-bound pattern search over smem-staged windows (DESIGN.md 5, profiles/r01_me_frame_v5.txt); HBM figure shown for scale only"}
+                "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": wl.h2d_bytes(), "d2h_bytes_per_step": wl.d2h_bytes(),
+                        "how": "x265b200_me_frame%s_host: the frame is copied from pinned host memory, searched, and the {mv,cost} records are copied back, per step" % ("" if args.config == 3 else "_ex")},
+                "roofline": {"kernel": "sad_stream_kernel (streaming ME SAD at the predictor: all 4 PU levels x %d references, %d frame groups in one launch, TMA ring)" % (wl.nref, groups),
+                             "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": traffic,
+                             "traffic_src": "profiles/r02_sad_stream.txt (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum of the same launch)" if traffic else None,
+                             "peak_kind": pk_kind, "algorithmic_bytes": sad_bytes,
+                             "bytes_formula": "groups x ((1 + refs) x W x H x sizeof(pixel) + 4 x refs x (n8 + n16 + n32 + n64)): the source frame is counted ONCE per group",
+                             "us_per_launch": sad_t * 1e6,
+                             "how": "one launch over %d disjoint groups (%d planes, %.0f MB > L2), CUDA-graph replay between events on the launching stream, median of %d"
+                                    % (groups, groups * (wl.nref + 1), groups * (wl.nref + 1) * wl.plane_bytes / 1e6, len(sad_loop_ms)) +
+                                    ("; in-step single-group launch: %.1f us" % (float(np.mean(sad_ms)) * 1e3) if sad_ms else "")}}
+        if dct_line:
+            dct_bytes = wl.n32 * 1024 * 2 * 2
+            dct_t = float(np.mean(dct_line)) / 1e3
+            line["roofline_dct32"] = {"kernel": "xform_mma_kernel<32,fwd> (IMMA)", "bound": "hbm", "achieved": dct_bytes / dct_t / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                      "frac": dct_bytes / dct_t / 1e9 / pk["hbm_gbs"], "us_per_launch": dct_t * 1e6, "blocks": wl.n32}
+        if me_ms:
+            me_bytes = (1 + NREF) * W * (CTU_ROWS * CTU) + wl.njobs * 12
+            me_t = float(np.mean(me_ms)) / 1e3
+            line["roofline_me_search"] = {"kernel": "me_frame_kernel (TMA-staged windows; HEX + subme 2, %d searches)" % wl.njobs, "bound": "hbm", "achieved": me_bytes / me_t / 1e9,
+                                          "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": me_bytes / me_t / 1e9 / pk["hbm_gbs"], "ms_per_step": me_t * 1e3,
+                                          "note": "instruction-issue bound pattern search over smem-staged windows (DESIGN.md 5); HBM figure shown for scale only"}
         if world == 1:
-            line["cpu_baseline"] = cpu_baseline()
-            try:
-                line["lookahead"] = lookahead_leg(pkg, ctx, ring, origin)
-            except Exception as e:      # noqa: BLE001  (extra measurement; never lose the main line to it)
-                line["lookahead"] = {"unavailable": str(e)[:200]}
+            line["cpu_baseline"] = cpu_baseline(args.config)
         print(json.dumps(line))
+    if hasattr(wl, "la_ctx"):
+        wl.la_ctx.close()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
 
 
-def lookahead_leg(pkg, ctx, ring, origin, nframes=8, bframes=4):
-    """The lookahead half of the path (NOT part of `value`): Lowres::init + lowresIntraEstimate per frame and the
-    estimateFrameCost list searches `nframes` frames trigger at preset medium (bframes 4: 2 x 5 per frame), batched
-    into ONE launch the way the encoder's lookahead queue allows.  Timed with host clocks around stream syncs."""
-    Wc, Hc = W, CTU_ROWS * CTU
-    mx, my = PAD, 80
-    wcu, hcu = (Wc // 2 + 7) // 8, (Hc // 2 + 7) // 8
-    lw, ll = wcu * 8, hcu * 8
-    ls = (Wc // 2 + 2 * mx + 31) & ~31
-    planesize, padoff, ncu = ls * (ll + 2 * my), ls * my + mx, wcu * hcu
-    NF = nframes + 2 * (bframes + 1)
-    planes = [[ctx.to_device(np.zeros(planesize, dtype=np.uint8)) for _ in range(4)] for _ in range(NF)]
-    ptrs = np.array([[b.ptr + padoff for b in fr] for fr in planes], dtype=np.int64)
-    lam = pkg.lambda_for_qp(12, 8)
-    dIC = [ctx.empty(ncu * 4) for _ in range(NF)]
-    dIM, dLC0, dRS0, dSm0 = ctx.empty(ncu), ctx.empty(ncu * 2), ctx.empty(hcu * 4), ctx.empty(8)
-
-    def init_and_intra():
-        for i in range(NF):
-            ctx.lowres_init_dev(8, ring[i].data_ptr() + origin, STRIDE, ptrs[i], ls, lw, ll, mx, my)
-            ctx.la_intra_dev(8, ptrs[i, 0], ls, wcu, hcu, None, 5 * int(lam), dIC[i], dIM, dLC0, dRS0, dSm0)
-    init_and_intra(); ctx.sync()
-    t0 = time.perf_counter(); init_and_intra(); ctx.sync()
-    pre_ms = (time.perf_counter() - t0) * 1e3 / NF
-    dPlanePtrs = ctx.to_device(ptrs)
-    dIntraPtrs = ctx.to_device(np.array([b.ptr for b in dIC], dtype=np.int64))
-    nslots = NF * 2 * (bframes + 2)
-    dMv, dMvC = ctx.to_device(np.zeros(nslots * ncu * 2, dtype=np.int32)), ctx.to_device(np.zeros(nslots * ncu, dtype=np.int32))
-    wave = [(b - dd, b + dd, b) for b in range(bframes + 1, bframes + 1 + nframes) for dd in range(1, bframes + 2)]
-    tr = np.zeros(len(wave), dtype=pkg.LA_TRIPLE)
-    for t, (p0, p1, b) in enumerate(wave):
-        tr[t]["b"], tr[t]["p0"], tr[t]["p1"] = b, p0, p1
-        for lst, dist in ((0, b - p0), (1, p1 - b)):
-            tr[t]["mvSlot"][lst] = (b * 2 + lst) * (bframes + 2) + dist
-            tr[t]["doSearch"][lst] = 1
-    dLC, dRS, dSm = ctx.empty(len(wave) * ncu * 2), ctx.empty(len(wave) * hcu * 4), ctx.empty(len(wave) * 16)
-    run = lambda: ctx.la_estimate_dev(8, dPlanePtrs, ls, wcu, hcu, tr, dMv, dMvC, dIntraPtrs, None, dLC, dRS, dSm, lam)
-    run(); ctx.sync()
-    t0 = time.perf_counter(); run(); ctx.sync()
-    est_ms = (time.perf_counter() - t0) * 1e3
-    for b in [x for fr in planes for x in fr] + dIC + [dIM, dLC0, dRS0, dSm0, dPlanePtrs, dIntraPtrs, dMv, dMvC, dLC, dRS, dSm]:
-        b.free()
-    per_frame = pre_ms + est_ms / nframes
-    return {"included_in_value": False, "lowres": "%dx%d (%dx%d CUs)" % (lw, ll, wcu, hcu), "frames_batched": nframes,
-            "list_searches": 2 * len(wave), "lowres_init_plus_intra_ms_per_frame": pre_ms, "estimate_launch_ms": est_ms,
-            "ms_per_frame": per_frame, "frames_per_s": 1e3 / per_frame,
-            "note": "estimateFrameCost is a dependent wavefront (~560 CU steps of ~30 us per (frame, list) field): one launch costs ~17-25 ms "
-                    "whatever the batch, so throughput comes from batching the fields of several queued frames (DESIGN.md 5b, profiles/r01_lookahead.txt)"}
+# DRAM bytes of one sad_stream launch under `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum), keyed by (config, groups)
+SAD_STREAM_DRAM_BYTES = {(3, 8): 292216832}          # profiles/r02_sad_stream.txt: 278.55 MB read + 13.67 MB written; algorithmic 284.03 MB
 
 
-def cpu_baseline():
+def cpu_baseline(config):
     """bounded sample of the same step on the host cores through the compiled reference (kind 'reference')."""
-    out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2", "--warmup", "1"],
-                         capture_output=True, text=True, timeout=600)
+    out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--config", str(config), "--steps", "2", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=900)
     try:
         ref = json.loads(out.stdout.strip().splitlines()[-1])
         return ref.get("cpu_baseline", {"unavailable": ref.get("unavailable")})

@@ -21,6 +21,9 @@ CONFIGS = {
     3: dict(W=3840, H=2176, depth=8, C=64, minCu=8, rect=0, amp=0, method=pkg.ME_HEX, subme=2, merange=57, nref=3, csp=0, padX=128, padY=128),
     4: dict(W=3840, H=2160, depth=10, C=64, minCu=8, rect=1, amp=0, method=pkg.ME_STAR, subme=3, merange=57, nref=4, csp=1, padX=96, padY=80),
     5: dict(W=7680, H=4320, depth=8, C=64, minCu=8, rect=1, amp=1, method=pkg.ME_STAR, subme=5, merange=128, nref=5, csp=1, padX=96, padY=80),
+    # reduced frames of configs 4 / 5 for profiling runs (same per-CTU work)
+    40: dict(W=1280, H=704, depth=10, C=64, minCu=8, rect=1, amp=0, method=pkg.ME_STAR, subme=3, merange=57, nref=2, csp=1, padX=96, padY=80),
+    50: dict(W=1280, H=704, depth=8, C=64, minCu=8, rect=1, amp=1, method=pkg.ME_STAR, subme=5, merange=128, nref=2, csp=1, padX=224, padY=208),
 }
 
 

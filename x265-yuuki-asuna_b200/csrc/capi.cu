@@ -55,6 +55,29 @@ int scratch_pinned(Ctx* ctx, int slot, size_t bytes, void** out)
     return 0;
 }
 
+// Asynchronous upload of a small host temporary (the caller may free or reuse hostSrc as soon as this returns): the bytes are
+// copied into one of four pinned staging buffers and travel from there.  A buffer is reused only after the copy that last read
+// it has completed (its event; in practice long ago), so no call waits for the stream's other work.
+int stage_small(Ctx* ctx, void* dDst, const void* hostSrc, size_t bytes)
+{
+    if (!bytes) return 0;
+    const int k = ctx->hStageNext++ & 3;
+    if (ctx->hStageEv[k]) X265B200_CHECK(cudaEventSynchronize(ctx->hStageEv[k]));
+    else X265B200_CHECK(cudaEventCreateWithFlags(&ctx->hStageEv[k], cudaEventDisableTiming));
+    if (ctx->hStageBytes[k] < bytes)
+    {
+        if (ctx->hStage[k]) cudaFreeHost(ctx->hStage[k]);
+        ctx->hStage[k] = nullptr; ctx->hStageBytes[k] = 0;
+        const size_t cap = bytes + bytes / 2 + 4096;
+        X265B200_CHECK(cudaMallocHost(&ctx->hStage[k], cap));
+        ctx->hStageBytes[k] = cap;
+    }
+    memcpy(ctx->hStage[k], hostSrc, bytes);
+    X265B200_CHECK(cudaMemcpyAsync(dDst, ctx->hStage[k], bytes, cudaMemcpyHostToDevice, ctx->stream));
+    X265B200_CHECK(cudaEventRecord(ctx->hStageEv[k], ctx->stream));
+    return 0;
+}
+
 // H2D of an arbitrary (possibly pageable) host buffer into scratch slot `slot`
 int stage_in(Ctx* ctx, int slot, const void* host, size_t bytes, void** dev)
 {
@@ -199,6 +222,11 @@ void x265b200_destroy(x265b200_ctx* ctx)
         if (ctx->c.hPinned[i]) cudaFreeHost(ctx->c.hPinned[i]);
     }
     if (ctx->c.dMvCost) cudaFree(ctx->c.dMvCost);
+    for (int i = 0; i < 4; i++)
+    {
+        if (ctx->c.hStage[i]) cudaFreeHost(ctx->c.hStage[i]);
+        if (ctx->c.hStageEv[i]) cudaEventDestroy(ctx->c.hStageEv[i]);
+    }
     me_ctu_release(&ctx->c);
     if (ctx->c.ownsStream) cudaStreamDestroy(ctx->c.stream);
     delete ctx;

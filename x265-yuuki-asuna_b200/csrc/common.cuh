@@ -31,9 +31,16 @@ struct Ctx
     uint16_t*    dMvCost;
     double       mvCostLambda;
     bool         mvCostValid;
+    // small host -> device parameter uploads (job lists, pointer tables) without a stream-wide sync: a ring of pinned staging
+    // buffers, each guarded by the event of its last copy (stage_small, capi.cu)
+    void*        hStage[4];
+    size_t       hStageBytes[4];
+    cudaEvent_t  hStageEv[4];
+    int          hStageNext;
 };
 
 void set_error(const char* fmt, ...);
+int  stage_small(Ctx* ctx, void* dDst, const void* hostSrc, size_t bytes);
 int  check(cudaError_t e, const char* what);
 
 #define X265B200_CHECK(expr) do { if (x265b200::check((expr), #expr)) return -1; } while (0)

@@ -154,7 +154,7 @@ __device__ __forceinline__ void lowres_mc_arr(const pixel* const planes[4], int6
 }
 
 // ---------------------------------------------------------------------------------------------
-// lowresIntraEstimate (slicetype.cpp:696-805), one thread per 8x8 CU
+// lowresIntraEstimate (slicetype.cpp:696-805), four lanes per 8x8 CU
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ int la_intra_pixel(const int* s /* 33 neighbours */, int mode, int bFilter, int y, int x, int dcVal, int depth)
 {
@@ -205,58 +205,96 @@ struct LAIntraArgs
     int32_t* intraCost; uint8_t* intraMode; uint16_t* lowresCosts; int32_t* rowSatds; int32_t* sums /* [2]: costEst, costEstAq */;
 };
 
+// SATD of one predicted 4x4 cell (rows y0..y0+3, columns x0..x0+3 of the 8x8 CU) of `mode` against the lane's source cell.
+// Out of line: the three callers (DC, planar, the angular candidates) share one copy of the 16 inlined pixel formulas.
+__device__ __noinline__ int la_intra_cell_cost(const int* nb /* 33 neighbours, shared memory */, int mode, int bFilter, int dcVal, int depth,
+                                               int x0, int y0, const int* fenc /* [16] */)
+{
+    int d[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+    {
+#pragma unroll
+        for (int k = 0; k < 4; k++) d[i][k] = fenc[i * 4 + k] - la_intra_pixel(nb, mode, bFilter, y0 + i, x0 + k, dcVal, depth);
+        me_hadamard4(d[i][0], d[i][1], d[i][2], d[i][3]);
+    }
+    int t = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+    {
+        me_hadamard4(d[0][k], d[1][k], d[2][k], d[3][k]);
+        t += abs(d[0][k]) + abs(d[1][k]) + abs(d[2][k]) + abs(d[3][k]);
+    }
+    return t >> 1;
+}
+
+// FOUR LANES PER CU: a lane owns one 4x4 cell of the 8x8 CU (pu[LUMA_8x8].satd is the sum of its four 4x4 Hadamard costs,
+// pixel.cpp:210-261), predicts only that cell for every mode tried and the four partial costs meet in two shuffles, so the
+// lanes of a CU hold identical costs and walk the mode decision together.  The raw and the 1:2:1-filtered neighbour arrays of
+// a CU are built once in shared memory (the per-thread form kept 64-entry fenc / pred arrays and two 33-entry neighbour
+// arrays in local memory: 0.31 ms per 2160p frame, 15 % of the serialised step in profiles/r02_launches_summary.txt).
+constexpr int LAI_CUS = 16;                                     // CUs per CTA of 64 threads
 template<typename pixel>
 __global__ void __launch_bounds__(64)
 la_intra_kernel(LAIntraArgs p)
 {
-    const int cuXY = blockIdx.x * blockDim.x + threadIdx.x;
-    if (cuXY >= p.widthInCU * p.heightInCU) return;
+    __shared__ int sSmp[LAI_CUS][34], sFlt[LAI_CUS][34];
+    const int slot = threadIdx.x >> 2, cell = threadIdx.x & 3;
+    const int ncu = p.widthInCU * p.heightInCU;
+    const int cuXY = min(blockIdx.x * LAI_CUS + slot, ncu - 1);     // surplus lanes shadow the last CU (they take part in the shuffles)
+    const bool live = blockIdx.x * LAI_CUS + slot < ncu;
     const int cuX = cuXY % p.widthInCU, cuY = cuXY / p.widthInCU;
     const pixel* pixCur = (const pixel*)p.plane0 + 8 * cuX + (int64_t)8 * cuY * p.stride;
-    int fenc[64];
-    for (int y = 0; y < 8; y++)
-        for (int x = 0; x < 8; x++) fenc[y * 8 + x] = pixCur[y * p.stride + x];
-    // neighbours (slicetype.cpp:731-735) and their 1:2:1 filtered version (intrapred.cpp:31-51)
-    int smp[33], flt[33];
+    const int x0 = (cell & 1) * 4, y0 = (cell >> 1) * 4;
+    int fenc[16];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) fenc[i * 4 + k] = pixCur[(int64_t)(y0 + i) * p.stride + x0 + k];
+    // neighbours (slicetype.cpp:731-735) and their 1:2:1 filtered version (intrapred.cpp:31-51): the 4 lanes of a CU share the work
+    int* smp = sSmp[slot]; int* flt = sFlt[slot];
     const pixel* tl = pixCur - p.stride - 1;
-    for (int i = 0; i <= 16; i++) smp[i] = tl[i];
-    for (int i = 1; i <= 16; i++) smp[16 + i] = tl[(int64_t)i * p.stride];
-    flt[0] = ((smp[0] << 1) + smp[1] + smp[17] + 2) >> 2;
-    for (int i = 1; i < 16; i++) flt[i] = ((smp[i] << 1) + smp[i - 1] + smp[i + 1] + 2) >> 2;
-    flt[16] = smp[16];
-    flt[17] = ((smp[17] << 1) + smp[0] + smp[18] + 2) >> 2;
-    for (int i = 18; i < 32; i++) flt[i] = ((smp[i] << 1) + smp[i - 1] + smp[i + 1] + 2) >> 2;
-    flt[32] = smp[32];
+    for (int i = cell; i <= 16; i += 4) smp[i] = tl[i];
+    for (int i = 1 + cell; i <= 16; i += 4) smp[16 + i] = tl[(int64_t)i * p.stride];
+    __syncwarp();
+    for (int i = cell; i < 33; i += 4)
+    {
+        int v;
+        if (i == 0) v = ((smp[0] << 1) + smp[1] + smp[17] + 2) >> 2;
+        else if (i == 16 || i == 32) v = smp[i];
+        else if (i == 17) v = ((smp[17] << 1) + smp[0] + smp[18] + 2) >> 2;
+        else v = ((smp[i] << 1) + smp[i - 1] + smp[i + 1] + 2) >> 2;
+        flt[i] = v;
+    }
+    __syncwarp();
+    auto cuSum = [](int v) { v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2); return v; };
 
-    int pred[64];
     int icost = ME_COST_MAX, ilowmode = 0;
     // DC (unfiltered neighbours, edge filter on since cuSize <= 16)
     {
         int dc = 8;
         for (int i = 0; i < 8; i++) dc += smp[1 + i] + smp[17 + i];
         dc = dc / 16;
-        for (int e = 0; e < 64; e++) pred[e] = la_intra_pixel(smp, 1, 1, e >> 3, e & 7, dc, p.depth);
-        int cost = satd8x8_arr(fenc, pred);
+        const int cost = cuSum(la_intra_cell_cost(smp, 1, 1, dc, p.depth, x0, y0, fenc));
         if (cost < icost) { icost = cost; ilowmode = 1; }
     }
     // planar uses the FILTERED neighbours (planar = !!(cuSize >= 8), slicetype.cpp:712,751)
     {
-        for (int e = 0; e < 64; e++) pred[e] = la_intra_pixel(flt, 0, 0, e >> 3, e & 7, 0, p.depth);
-        int cost = satd8x8_arr(fenc, pred);
+        const int cost = cuSum(la_intra_cell_cost(flt, 0, 0, 0, p.depth, x0, y0, fenc));
         if (cost < icost) { icost = cost; ilowmode = 0; }
     }
     auto angCost = [&](int mode) -> int {
-        int dist = min(abs(mode - 26), abs(mode - 10));
-        const int* nbp = dist > 7 ? flt : smp;            // g_intraFilterFlags[mode] & 8
-        for (int e = 0; e < 64; e++) pred[e] = la_intra_pixel(nbp, mode, 1, e >> 3, e & 7, 0, p.depth);
-        return satd8x8_arr(fenc, pred);
+        const int dist = min(abs(mode - 26), abs(mode - 10));
+        return cuSum(la_intra_cell_cost(dist > 7 ? flt : smp, mode, 1, 0, p.depth, x0, y0, fenc));            // g_intraFilterFlags[mode] & 8
     };
     int acost = ME_COST_MAX, alowmode = 4;
+#pragma unroll 1
     for (int mode = 5; mode < 35; mode += 5)
     {
         int cost = angCost(mode);
         if (cost < acost) { acost = cost; alowmode = mode; }
     }
+#pragma unroll 1
     for (int dist = 2; dist >= 1; dist--)
     {
         int minusmode = alowmode - dist, plusmode = alowmode + dist;
@@ -268,6 +306,7 @@ la_intra_kernel(LAIntraArgs p)
     if (acost < icost) { icost = acost; ilowmode = alowmode; }
     icost += p.intraPenalty + 4;
 
+    if (!live || cell) return;
     p.lowresCosts[cuXY] = (uint16_t)min(icost, (1 << 14) - 1);
     p.intraCost[cuXY] = icost;
     p.intraMode[cuXY] = (uint8_t)ilowmode;
@@ -287,8 +326,8 @@ int la_intra_dev(Ctx* ctx, int depth, const void* plane0, int64_t stride, int wi
     X265B200_CHECK(cudaMemsetAsync(rowSatds, 0, sizeof(int32_t) * heightInCU, ctx->stream));
     X265B200_CHECK(cudaMemsetAsync(sums, 0, sizeof(int32_t) * 2, ctx->stream));
     int n = widthInCU * heightInCU;
-    if (depth > 8) la_intra_kernel<uint16_t><<<(n + 63) / 64, 64, 0, ctx->stream>>>(a);
-    else           la_intra_kernel<uint8_t><<<(n + 63) / 64, 64, 0, ctx->stream>>>(a);
+    if (depth > 8) la_intra_kernel<uint16_t><<<(n + LAI_CUS - 1) / LAI_CUS, 64, 0, ctx->stream>>>(a);
+    else           la_intra_kernel<uint8_t><<<(n + LAI_CUS - 1) / LAI_CUS, 64, 0, ctx->stream>>>(a);
     ctx->launches++;
     return check(cudaGetLastError(), "la_intra launch");
 }
@@ -396,7 +435,7 @@ int la_estimate_dev(Ctx* ctx, int depth, const void* const* planes, int64_t stri
     if (ensure_mvcost(ctx, lambda)) return -1;
     void* dTriplesV = nullptr;
     if (scratch_dev(ctx, 6, sizeof(x265b200_la_triple) * numTriples, &dTriplesV)) return -1;
-    X265B200_CHECK(cudaMemcpyAsync(dTriplesV, triplesHost, sizeof(x265b200_la_triple) * numTriples, cudaMemcpyHostToDevice, ctx->stream));
+    if (stage_small(ctx, dTriplesV, triplesHost, sizeof(x265b200_la_triple) * numTriples)) return -1;
     const x265b200_la_triple* triples = (const x265b200_la_triple*)dTriplesV;
     // build the chain list (host) and upload it with the sync words
     std::vector<LAChain> chains;
@@ -416,7 +455,7 @@ int la_estimate_dev(Ctx* ctx, int depth, const void* const* planes, int64_t stri
     int* dProg = (int*)((char*)scratch + chainBytes);
     if (numChains)
     {
-        X265B200_CHECK(cudaMemcpyAsync(dChains, chains.data(), sizeof(LAChain) * numChains, cudaMemcpyHostToDevice, ctx->stream));
+        if (stage_small(ctx, dChains, chains.data(), sizeof(LAChain) * numChains)) return -1;       // no stream-wide sync: the lookahead runs beside other streams
         X265B200_CHECK(cudaMemsetAsync(dProg, 0, progBytes, ctx->stream));
         LASearchArgs a; a.planes = planes; a.stride = stride; a.chains = dChains; a.numChains = numChains;
         a.widthInCU = widthInCU; a.heightInCU = heightInCU; a.depth = depth; a.merange = 16; a.maxSlices = maxSlices;   // s_merange, slicetype.h:259
@@ -443,13 +482,10 @@ int la_estimate_dev(Ctx* ctx, int depth, const void* const* planes, int64_t stri
             }
             else { h.rowsPerSlice = hme->height4; h.numSlices = 1; }
             if (hme->height4 > heightInCU) { set_error("la_estimate: HME level taller than the 8x8 level"); return -1; }
-            X265B200_CHECK(cudaStreamSynchronize(ctx->stream));
             if (la_search_thread_launch(ctx, depth, h)) return -1;
             a.hme = 1; a.searchMethod = hme->searchMethod[1]; a.merange = hme->range[1];
             a.hmeMvPool = hme->lowerMvPool; a.hmeMvCostPool = hme->lowerMvCostPool; a.hmeNcu = hme->width4 * hme->height4;
         }
-        // the host must not free `chains` before the async copy is consumed
-        X265B200_CHECK(cudaStreamSynchronize(ctx->stream));
         if (la_search_thread_launch(ctx, depth, a)) return -1;
     }
     X265B200_CHECK(cudaMemsetAsync(rowSatds, 0, sizeof(int32_t) * (size_t)numTriples * heightInCU, ctx->stream));

@@ -315,9 +315,8 @@ static int me_ctu_launch(Ctx* ctx, const x265b200_me_frame_params* P, const x265
     const size_t ptrBytes = sizeof(ptrs), sliceBytes = slice.size() * sizeof(int32_t);
     void* dScr = nullptr;
     if (scratch_dev(ctx, 5, ptrBytes + sliceBytes + 64, &dScr)) return -1;
-    X265B200_CHECK(cudaMemcpyAsync(dScr, ptrs, ptrBytes, cudaMemcpyHostToDevice, ctx->stream));
-    if (sliceBytes) X265B200_CHECK(cudaMemcpyAsync((char*)dScr + ptrBytes, slice.data(), sliceBytes, cudaMemcpyHostToDevice, ctx->stream));
-    X265B200_CHECK(cudaStreamSynchronize(ctx->stream));      // ptrs / slice are host temporaries
+    if (stage_small(ctx, dScr, ptrs, ptrBytes)) return -1;                     // host temporaries: staged through pinned memory, no sync
+    if (sliceBytes && stage_small(ctx, (char*)dScr + ptrBytes, slice.data(), sliceBytes)) return -1;
 
     MECtuArgs a; memset(&a, 0, sizeof(a));
     a.refY = (const void* const*)dScr; a.refCb = a.refY + MC_MAX_REFS; a.refCr = a.refY + 2 * MC_MAX_REFS;

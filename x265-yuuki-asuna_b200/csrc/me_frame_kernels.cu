@@ -264,7 +264,7 @@ int me_frame_dev(Ctx* ctx, int depth, const void* curOrigin, int64_t curStride, 
     void* dScr = nullptr;
     size_t ptrBytes = sizeof(void*) * numRefs;
     if (scratch_dev(ctx, 5, ptrBytes + 64, &dScr)) return -1;
-    X265B200_CHECK(cudaMemcpyAsync(dScr, refOriginsHost, ptrBytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (stage_small(ctx, dScr, refOriginsHost, ptrBytes)) return -1;
 
     MEFrameArgs a;
     a.refOrigins = (const void* const*)dScr; a.refStride = refStride;
