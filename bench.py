@@ -747,12 +747,12 @@ def main():
     if world > 1:
         if args.shard == "frames":
             # every rank needs the reference pixels the others produced: all_gather of the new luma plane; rank 0 collects the {mv,cost} records
-            gathered = [torch.empty((world,) + tuple(wl.pool[0].shape), dtype=wl.tdt, device=dev) for _ in range(2)]
+            gathered = [torch.empty((world, wl.pool[0].shape[0], wl.pool[0].shape[1] * wl.item), dtype=torch.uint8, device=dev) for _ in range(2)]   # bytes: NCCL has no int16
         else:
             # ctu-rows: the bands of reconstructed rows are all_gathered (equal-sized chunks of the plane), results gathered
             rows_px = g["rows"] * wl.C
             chunk = (rows_px + world - 1) // world
-            gathered = [torch.empty((world, chunk, g["stride"]), dtype=wl.tdt, device=dev) for _ in range(2)]
+            gathered = [torch.empty((world, chunk, g["stride"] * wl.item), dtype=torch.uint8, device=dev) for _ in range(2)]
         nres = wl.me_out[0].shape[0]
         res_max = torch.tensor([nres], device=dev); dist.all_reduce(res_max, op=dist.ReduceOp.MAX); res_max = int(res_max)
         send = [torch.zeros((res_max, 3), dtype=torch.int32, device=dev) for _ in range(2)]
@@ -766,10 +766,10 @@ def main():
         with torch.cuda.stream(comm):
             comm.wait_event(done)
             if args.shard == "frames":
-                dist.all_gather_into_tensor(gathered[k], wl.pool[wl.frame(t)])
+                dist.all_gather_into_tensor(gathered[k], wl.pool[wl.frame(t)].view(torch.uint8))
             else:
                 y0 = wl.g["padY"] + rank * gathered[k].shape[1]
-                dist.all_gather_into_tensor(gathered[k], wl.pool[wl.frame(t)][y0:y0 + gathered[k].shape[1]].contiguous())
+                dist.all_gather_into_tensor(gathered[k], wl.pool[wl.frame(t)][y0:y0 + gathered[k].shape[1]].view(torch.uint8))
             send[k][:out.shape[0]].copy_(out)
             dist.gather(send[k], res_all[k], dst=0)
             comm_events[k] = torch.cuda.Event(); comm_events[k].record(comm)

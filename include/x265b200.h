@@ -409,7 +409,8 @@ int x265b200_me_frame_dev(x265b200_ctx* ctx, int depth, const void* curOrigin, i
  * One CTA per (CTU, reference) stages the search window around the CTU's window centre mvpCtu[ref][ctu] (quarter-pel, NULL =
  * 0; also the predictor when mvpPu is NULL) with TMA; blocks outside the window are read from the plane, so the results do
  * not depend on the centre.  Planes are given by their ORIGIN (pixel 0,0) with marginX / marginY pixels of padding around
- * the picture and rowsTotal rows allocated (PicYuv layout; chroma margins and rows are the luma ones >> the chroma shifts).
+ * the picture and rowsTotal rows allocated (PicYuv layout; chroma rows are the luma ones >> the vertical chroma shift, chroma margins see
+ * chromaMarginX / chromaMarginY).
  * PU order inside a CTU: x265b200_me_frame_layout.  Arrays: mvpPu int32 [ref][ctu][pu][2], numCandPu uint8 [ref][ctu][pu],
  * mvcPu int32 [ref][ctu][pu][maxCand][2], out int32 [ref][ctu][pu][3] = {mvx, mvy, cost} (all device memory). */
 typedef struct
@@ -419,6 +420,8 @@ typedef struct
     int32_t picWidth, picHeight;
     int32_t ctuCols, ctuRows;
     int32_t marginX, marginY, rowsTotal;
+    int32_t chromaMarginX, chromaMarginY;     /* padding of the Cb / Cr planes; 0 = marginX >> hshift / marginY >> vshift.  PicYuv itself keeps
+                                                 chromaMarginX = lumaMarginX (picyuv.cpp:104-106): pass its values when binding real PicYuv planes */
     int32_t numRefs;
     int32_t searchMethod, subpelRefine, merange;
     int32_t csp;                              /* 0 = luma only, 1 = 4:2:0, 2 = 4:2:2, 3 = 4:4:4 (x265.h:588-592) */
@@ -514,6 +517,31 @@ int x265b200_la_estimate_hme_dev(x265b200_ctx* ctx, int depth, const void* const
                                  const x265b200_la_hme* hme, const x265b200_la_triple* triplesHost, int numTriples, int32_t* mvPool, int32_t* mvCostPool,
                                  const int32_t* const* intraCost, const int32_t* const* invQscale, uint16_t* lowresCosts,
                                  int32_t* rowSatds, int32_t* sums, double lambda, int lookaheadSlices);
+
+/* Lookahead::estimateCUPropagate (slicetype.cpp:2641-2747), the cuTree propagation step of one (p0, p1, b): per 8x8 CU of frame b
+ * the amount estimateCUPropagateCost yields (from propagateCostB = frames[b]->propagateCost, NULL for a non-referenced frame whose
+ * source costs are zero; intraCost, lowresCosts[b-p0][p1-b], invQscaleFactor(8x8) of frame b; fpsFactor as computed at :2654) is
+ * split over the lists the CU used (bipredWeight = 32, or 64 - (distScaleFactor >> 2) with weighted bi-prediction, :2644-2646),
+ * follows mvs0 / mvs1 = lowresMvs[list][listDist[list]] and is added, saturating at 65535, to refCost0 / refCost1 =
+ * frames[p0] / frames[p1]->propagateCost (refCost1 may be NULL or equal refCost0's frame for P frames).  The cuTreeFinish call at
+ * the end of the reference function (VBV lookahead only) stays with the caller.  All arrays are device memory, widthInCU*heightInCU. */
+int x265b200_cutree_propagate_dev(x265b200_ctx* ctx, int widthInCU, int heightInCU, const uint16_t* propagateCostB, const int32_t* intraCost,
+                                  const uint16_t* lowresCosts, const int32_t* invQscale, const int32_t* mvs0, const int32_t* mvs1,
+                                  uint16_t* refCost0, uint16_t* refCost1, int bipredWeight, double fpsFactor);
+
+/* The block loop of LookaheadTLD::calcAdaptiveQuantFrame (slicetype.cpp:444-694): acEnergyCu (:252-275 = acEnergyPlane + acEnergyVar,
+ * :49-86) for every qgSize x qgSize block of a frame, blocks in raster order over ceil(picWidth / qgSize) x ceil(picHeight / qgSize)
+ * (edge blocks read the picture's padding, as the reference does).  energy[block] = the 32-bit sum over Y, Cb, Cr of
+ * ssd - (sum^2 >> shift); wpSumSsd[0..2] / [3..5] = Lowres::wp_sum / wp_ssd of the three planes (what weightsAnalyse consumes).
+ * csp: 0 = 4:0:0, 1 = 4:2:0, 2 = 4:2:2, 3 = 4:4:4; planes by ORIGIN.  The qp-offset formulas of the AQ modes are float / double
+ * (X265_LOG2, pow) and stay on the host, fed with these integers. */
+int x265b200_aq_energy_dev(x265b200_ctx* ctx, int depth, int csp, int qgSize, const void* y, int64_t strideY, const void* cb, const void* cr,
+                           int64_t strideC, int picWidth, int picHeight, uint32_t* energy, uint64_t* wpSumSsd);
+/* MotionReference::applyWeight for a whole plane (encoder/reference.cpp:119-185, weights set up as MotionReference::init :96-103):
+ * dst = weight_pp(src) with (inputWeight, inputOffset, log2WeightDenom) of the slice's WeightParam, then the left / right / top /
+ * bottom margins replicated -- the weighted reference plane the main motion search reads when weightp is on. */
+int x265b200_apply_weight_dev(x265b200_ctx* ctx, int depth, const void* srcOrigin, void* dstOrigin, int64_t stride, int width, int height,
+                              int marginX, int marginY, int inputWeight, int inputOffset, int log2WeightDenom);
 
 #ifdef __cplusplus
 }

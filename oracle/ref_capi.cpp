@@ -408,7 +408,9 @@ int ref_me_batch(const void* fencPlane, intptr_t fencStride, const void* refPlan
 /* ---- lookahead: Lowres::init, LookaheadTLD::lowresIntraEstimate, CostEstimateGroup::singleCost ----
  * Built on the reference's own Lookahead / Lowres / PicYuv objects (no pool => non-cooperative path,
  * slicetype.cpp:3175-3199).  weightp, HME and cutree are off; AQ factors can be injected. */
+#define protected public          /* test infrastructure: reach Lookahead::estimateCUPropagate (the reference source is not modified) */
 #include "slicetype.h"
+#undef protected
 #include "picyuv.h"
 #include "frame.h"
 
@@ -436,6 +438,7 @@ static void* la_create(int width, int height, int bframes, int aq, int hme)
     h->param = x265_param_alloc();
     x265_param_default_preset(h->param, "medium", NULL);
     h->param->sourceWidth = width; h->param->sourceHeight = height;
+    h->param->fpsNum = 25; h->param->fpsDenom = 1;             /* the CLI always sets them; estimateCUPropagate divides by fpsNum */
     h->param->internalCsp = X265_CSP_I400;
     h->param->internalBitDepth = X265_DEPTH;
     h->param->bframes = bframes;
@@ -543,6 +546,21 @@ int64_t ref_la_frame_cost_slices(void* hv, int p0, int p1, int b, int lookaheadS
     fenc->costEst[b - p0][p1 - b] = score;
     est.m_jobTotal = est.m_jobAcquired = 0;
     return score;
+}
+/* Lookahead::estimateCUPropagate (slicetype.cpp:2641-2747) on the frames of the handle; fps = fpsNum / fpsDenom of the param */
+void ref_la_cutree_propagate(void* hv, int p0, int p1, int b, int referenced, double averageDuration)
+{
+    RefLA* h = (RefLA*)hv;
+    h->la->estimateCUPropagate(h->framePtrs.data(), averageDuration, p0, p1, b, referenced);
+}
+uint16_t* ref_la_propagate_cost(void* hv, int idx) { return ((RefLA*)hv)->lowres[idx]->propagateCost; }
+double ref_la_fps_factor(void* hv, double averageDuration)
+{
+    RefLA* h = (RefLA*)hv;
+    double a = (double)h->param->fpsDenom / h->param->fpsNum;
+    a = a < 0.01 ? 0.01 : (a > 1.00 ? 1.00 : a);                 /* CLIP_DURATION, ratecontrol.h:45-47 */
+    double d = averageDuration < 0.01 ? 0.01 : (averageDuration > 1.00 ? 1.00 : averageDuration);
+    return a / d;
 }
 int ref_la_num_coop_slices(void* hv) { return ((RefLA*)hv)->la->m_numCoopSlices; }
 /* outputs cached on frame b (common/lowres.h) */
@@ -958,3 +976,80 @@ void ref_deblock(int chroma, void* src, intptr_t srcStep, intptr_t offset, int a
     else primitives.pelFilterLumaStrong[0]((pixel*)src, srcStep, offset, a, b);
 }
 }
+
+
+/* ---- AQ energies and weighted reference planes: the reference's own LookaheadTLD::acEnergyCu and MotionReference::applyWeight ---- */
+#include "reference.h"
+extern "C" {
+struct RefPic { x265_param* param; PicYuv* pic; Frame* frame; };
+/* a PicYuv (with the encoder's padding) from planar input; csp as x265.h:588-592 */
+void* ref_pic_create(int width, int height, int csp, const void* y, const void* cb, const void* cr, intptr_t strideY, intptr_t strideC)
+{
+    ensure_init();
+    RefPic* h = new RefPic;
+    h->param = x265_param_alloc();
+    x265_param_default_preset(h->param, "medium", NULL);
+    h->param->sourceWidth = width; h->param->sourceHeight = height;
+    h->param->internalCsp = csp; h->param->internalBitDepth = X265_DEPTH; h->param->logLevel = X265_LOG_NONE;
+    h->param->bCopyPicToFrame = 1;
+    h->pic = new PicYuv;
+    h->pic->create(h->param, true);
+    x265_picture in;
+    x265_picture_init(h->param, &in);
+    in.planes[0] = (void*)y; in.planes[1] = (void*)cb; in.planes[2] = (void*)cr;
+    in.stride[0] = (int)(strideY * sizeof(pixel)); in.stride[1] = in.stride[2] = (int)(strideC * sizeof(pixel));
+    in.bitDepth = X265_DEPTH; in.colorSpace = csp;
+    h->pic->copyFromPicture(in, *h->param, 0, 0);
+    h->frame = new Frame;
+    h->frame->m_fencPic = h->pic;
+    h->frame->m_param = h->param;
+    return h;
+}
+/* out[0] = stride, [1] = strideC, [2] = lumaMarginX, [3] = lumaMarginY, [4] = chromaMarginX, [5] = chromaMarginY, [6] = luma rows allocated, [7] = chroma rows */
+void ref_pic_geometry(void* hv, int64_t* out)
+{
+    RefPic* h = (RefPic*)hv; PicYuv* p = h->pic;
+    uint32_t nh = (p->m_picHeight + h->param->maxCUSize - 1) / h->param->maxCUSize;
+    out[0] = p->m_stride; out[1] = p->m_strideC; out[2] = p->m_lumaMarginX; out[3] = p->m_lumaMarginY; out[4] = p->m_chromaMarginX; out[5] = p->m_chromaMarginY;
+    out[6] = nh * h->param->maxCUSize + 2 * p->m_lumaMarginY; out[7] = ((nh * h->param->maxCUSize) >> p->m_vChromaShift) + 2 * p->m_chromaMarginY;
+}
+const void* ref_pic_buffer(void* hv, int plane) { return ((RefPic*)hv)->pic->m_picBuf[plane]; }
+/* acEnergyCu over the block loop of calcAdaptiveQuantFrame (slicetype.cpp:519-523); wp[0..2] = wp_sum, wp[3..5] = wp_ssd */
+void ref_aq_energy(void* hv, int qgSize, uint32_t* energy, uint64_t* wp)
+{
+    RefPic* h = (RefPic*)hv;
+    LookaheadTLD tld;
+    for (int i = 0; i < 3; i++) h->frame->m_lowres.wp_sum[i] = h->frame->m_lowres.wp_ssd[i] = 0;
+    int k = 0;
+    for (int by = 0; by < (int)h->pic->m_picHeight; by += qgSize)
+        for (int bx = 0; bx < (int)h->pic->m_picWidth; bx += qgSize)
+            energy[k++] = tld.acEnergyCu(h->frame, bx, by, h->param->internalCsp, qgSize);
+    for (int i = 0; i < 3; i++) { wp[i] = h->frame->m_lowres.wp_sum[i]; wp[3 + i] = h->frame->m_lowres.wp_ssd[i]; }
+}
+/* MotionReference::init + applyWeight over all rows (reference.cpp:51-185); outFull receives the whole padded weighted luma buffer */
+int ref_apply_weight(void* hv, int inputWeight, int inputOffset, int log2Denom, void* outFull)
+{
+    RefPic* h = (RefPic*)hv;
+    x265_param p = *h->param;
+    p.subpelRefine = 2; p.maxSlices = 1;
+    WeightParam wp[3];
+    memset(wp, 0, sizeof(wp));
+    wp[0].wtPresent = 1; wp[0].inputWeight = inputWeight; wp[0].inputOffset = inputOffset; wp[0].log2WeightDenom = log2Denom;
+    MotionReference ref;
+    if (ref.init(h->pic, wp, p)) return -1;
+    const uint32_t rows = (h->pic->m_picHeight + p.maxCUSize - 1) / p.maxCUSize;
+    ref.applyWeight(rows - 1, rows, rows, 0);
+    const size_t padheight = rows * p.maxCUSize + 2 * h->pic->m_lumaMarginY;
+    memcpy(outFull, ref.weightBuffer[0], (size_t)h->pic->m_stride * padheight * sizeof(pixel));
+    return 0;
+}
+void ref_pic_destroy(void* hv)
+{
+    RefPic* h = (RefPic*)hv;
+    h->frame->m_fencPic = NULL;
+    delete h->frame;
+    h->pic->destroy(); delete h->pic;
+    x265_param_free(h->param);
+    delete h;
+}
+} /* extern "C" */

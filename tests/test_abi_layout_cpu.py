@@ -31,7 +31,7 @@ int main(void)
     S(x265b200_me_chroma); F(x265b200_me_chroma, fencCb); F(x265b200_me_chroma, fencStrideC); F(x265b200_me_chroma, refCbPlanes); F(x265b200_me_chroma, refStrideC);
     S(x265b200_la_hme); F(x265b200_la_hme, lowerStride); F(x265b200_la_hme, width4); F(x265b200_la_hme, lowerMvPool); F(x265b200_la_hme, searchMethod); F(x265b200_la_hme, range);
     S(x265b200_sad_group); F(x265b200_sad_group, ref);
-    S(x265b200_me_frame_params); F(x265b200_me_frame_params, minCuSize); F(x265b200_me_frame_params, picWidth); F(x265b200_me_frame_params, numRefs);
+    S(x265b200_me_frame_params); F(x265b200_me_frame_params, minCuSize); F(x265b200_me_frame_params, picWidth); F(x265b200_me_frame_params, chromaMarginX); F(x265b200_me_frame_params, numRefs);
     F(x265b200_me_frame_params, merange); F(x265b200_me_frame_params, maxCand); F(x265b200_me_frame_params, sliceTotalRows); F(x265b200_me_frame_params, refLagPixels);
     S(x265b200_me_frame_planes); F(x265b200_me_frame_planes, curCr); F(x265b200_me_frame_planes, curStrideC); F(x265b200_me_frame_planes, refY); F(x265b200_me_frame_planes, refStrideC);
     return 0;

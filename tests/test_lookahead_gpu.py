@@ -290,3 +290,58 @@ def test_lookahead_hme_matches_reference(ctx, depth, W, H):
     for b in keep + [dPlanePtrs, dLowerPtrs, dIntraPtrs, dMv, dMvC, dMv4, dMvC4]:
         b.free()
     R.ref_la_destroy(h)
+
+
+@pytest.mark.parametrize("depth,W,H", [(8, 416, 240), (10, 320, 192)])
+def test_cutree_propagate_matches_reference(ctx, depth, W, H):
+    """Lookahead::estimateCUPropagate (slicetype.cpp:2641-2747) for a B triple and a P triple, referenced and not: the reference's own
+    function runs on its Lowres objects, the device driver on copies of the same arrays; the saturating scatter must agree entry for
+    entry (incl. CUs whose MVs land partly outside the frame and entries that saturate at 65535)."""
+    R = oracle.ref(depth)
+    assert R is not None, "oracle/_ref missing"
+    _bind(R)
+    R.ref_la_propagate_cost.restype = ctypes.c_void_p
+    R.ref_la_fps_factor.restype = ctypes.c_double
+    NF, BF = 5, 3
+    h = ctypes.c_void_p(R.ref_la_create(W, H, BF, 1))
+    for f in _frames(W, H, NF, depth, seed=3 * W + depth):
+        R.ref_la_add_frame(h, ctypes.c_void_p(f.ctypes.data), ctypes.c_ssize_t(W))
+    g = (ctypes.c_int64 * 11)()
+    R.ref_la_geometry(h, g)
+    wcu, hcu = int(g[5]), int(g[6])
+    ncu = wcu * hcu
+    rng = np.random.default_rng(5)
+    for i in range(NF):
+        q = rng.integers(128, 512, ncu).astype(np.int32)
+        ctypes.memmove(R.ref_la_inv_qscale(h, i), q.ctypes.data, q.nbytes)
+        R.ref_la_intra(h, i)
+    avg_dur = 1 / 25.0
+    for (p0, p1, b, referenced) in ((0, 4, 2, 1), (0, 4, 4, 1), (2, 4, 3, 0), (0, 2, 1, 1)):
+        R.ref_la_frame_cost(h, p0, p1, b, 0)
+        # random, partly near-saturated source / target costs on the reference's arrays
+        for i in {p0, p1, b}:
+            pc = rng.integers(0, 65536 if i != b else 3000, ncu).astype(np.uint16)
+            ctypes.memmove(R.ref_la_propagate_cost(h, i), pc.ctypes.data, pc.nbytes)
+        before = {i: _arr(R.ref_la_propagate_cost(h, i), ctypes.c_uint16, (ncu,)) for i in {p0, p1, b}}
+        intra = _arr(R.ref_la_intra_cost(h, b), ctypes.c_int32, (ncu,))
+        lc = _arr(R.ref_la_lowres_costs(h, b, b - p0, p1 - b), ctypes.c_uint16, (ncu,))
+        invq = _arr(R.ref_la_inv_qscale(h, b), ctypes.c_int32, (ncu,))
+        mv0 = _arr(R.ref_la_mvs(h, b, 0, b - p0), ctypes.c_int32, (ncu, 2))
+        mv1 = _arr(R.ref_la_mvs(h, b, 1, p1 - b), ctypes.c_int32, (ncu, 2)) if p1 > b else None
+        fps = R.ref_la_fps_factor(h, ctypes.c_double(avg_dur))
+        R.ref_la_cutree_propagate(h, p0, p1, b, referenced, ctypes.c_double(avg_dur))
+        want0 = _arr(R.ref_la_propagate_cost(h, p0), ctypes.c_uint16, (ncu,))
+        want1 = _arr(R.ref_la_propagate_cost(h, p1), ctypes.c_uint16, (ncu,))
+        d = {k: ctx.to_device(v) for k, v in dict(pb=before[b], intra=intra, lc=lc, invq=invq, mv0=mv0, r0=before[p0], r1=before[p1]).items()}
+        dmv1 = ctx.to_device(mv1) if mv1 is not None else None
+        ctx.cutree_propagate_dev(wcu, hcu, d["pb"] if referenced else None, d["intra"], d["lc"], d["invq"], d["mv0"], dmv1, d["r0"],
+                                 d["r1"] if p1 != b else None, 32, fps)
+        got0 = d["r0"].download(np.uint16)
+        assert np.array_equal(got0, want0), ((p0, p1, b), int(np.count_nonzero(got0 != want0)))
+        if p1 != b:
+            got1 = d["r1"].download(np.uint16)
+            assert np.array_equal(got1, want1), ((p0, p1, b), "list 1", int(np.count_nonzero(got1 != want1)))
+        assert (want0 != before[p0]).any()
+        for v in list(d.values()) + ([dmv1] if dmv1 is not None else []):
+            v.free()
+    R.ref_la_destroy(h)

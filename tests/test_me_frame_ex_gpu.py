@@ -20,15 +20,17 @@ pytestmark = pytest.mark.gpu
 class Frames:
     """a source picture + nref references (+ chroma for csp 1) resident on the device, PicYuv-style padding"""
 
-    def __init__(self, ctx, W, H, padX, padY, depth, nref, csp, seed):
+    def __init__(self, ctx, W, H, padX, padY, depth, nref, csp, seed, picyuv_chroma=False):
         self.ctx, self.W, self.H, self.padX, self.padY, self.depth, self.csp = ctx, W, H, padX, padY, depth, csp
+        # PicYuv keeps chromaMarginX = lumaMarginX (picyuv.cpp:104-106); the default test planes halve it
+        self.cpadX, self.cpadY = (padX if picyuv_chroma else padX // 2), padY // 2
         self.item = 2 if depth > 8 else 1
         self.y, self.S, self.R, self.origin = synth_sequence(W, H, padX, padY, depth, nref + 1, seed)
         self.dY = [ctx.to_device(a) for a in self.y]
         if csp:
             assert csp == 1
-            self.cb, self.Sc, self.Rc, self.originC = synth_sequence(W // 2, H // 2, padX // 2, padY // 2, depth, nref + 1, seed + 101, max_motion=6)
-            self.cr, _, _, _ = synth_sequence(W // 2, H // 2, padX // 2, padY // 2, depth, nref + 1, seed + 202, max_motion=6)
+            self.cb, self.Sc, self.Rc, self.originC = synth_sequence(W // 2, H // 2, self.cpadX, self.cpadY, depth, nref + 1, seed + 101, max_motion=6)
+            self.cr, _, _, _ = synth_sequence(W // 2, H // 2, self.cpadX, self.cpadY, depth, nref + 1, seed + 202, max_motion=6)
             self.dCb = [ctx.to_device(a) for a in self.cb]
             self.dCr = [ctx.to_device(a) for a in self.cr]
 
@@ -62,7 +64,8 @@ def run_frame(ctx, F, C, minCu, rect, amp, method, subme, merange, nref, rng, ma
     shY = ctuRow0 * C * F.S * F.item
     params = dict(depth=F.depth, ctuSize=C, minCuSize=minCu, rect=int(rect), amp=int(amp), picWidth=picW or F.W, picHeight=picH or F.H, firstCtuRow=ctuRow0,
                   ctuCols=ctuCols, ctuRows=ctuRows, marginX=F.padX, marginY=F.padY + ctuRow0 * C, rowsTotal=F.R, searchMethod=int(method),
-                  subpelRefine=subme, merange=merange, csp=F.csp, maxCand=maxCand, maxSlices=1)
+                  subpelRefine=subme, merange=merange, csp=F.csp, maxCand=maxCand, maxSlices=1,
+                  chromaMarginX=F.cpadX if F.csp else 0, chromaMarginY=(F.cpadY + ctuRow0 * (C // 2)) if F.csp else 0)
     params["lambda"] = lam
     dOut = ctx.empty(nref * nctu * n * 12)
     dev = [ctx.to_device(a) if a is not None else None for a in (mvpCtu, mvpPu, ncand, mvc)]
@@ -131,6 +134,15 @@ def test_small_frame_every_pu(ctx, depth, C, minCu, rect, amp, method, subme, me
     pad = (pad + 31) & ~31
     F = Frames(ctx, cols * C, rows * C, pad, pad, depth, nref, csp, seed=7000 + depth + C + subme)
     r = run_frame(ctx, F, C, minCu, rect, amp, method, subme, merange, nref, np.random.default_rng(11 + subme), maxCand=maxCand, per_pu_mvp=perPu, far_frac=far)
+    check_ctus(F, r, [(x, y) for y in range(rows) for x in range(cols)])
+    F.free()
+
+
+def test_picyuv_chroma_margins(ctx):
+    """the chroma planes of a real PicYuv keep chromaMarginX = lumaMarginX (picyuv.cpp:104-106): explicit chroma margins in the params"""
+    C, cols, rows, nref, merange = 64, 3, 2, 2, 24
+    F = Frames(ctx, cols * C, rows * C, 160, 160, 8, nref, 1, seed=7150, picyuv_chroma=True)
+    r = run_frame(ctx, F, C, 8, True, False, pkg.ME_HEX, 3, merange, nref, np.random.default_rng(7), maxCand=2, per_pu_mvp=True)
     check_ctus(F, r, [(x, y) for y in range(rows) for x in range(cols)])
     F.free()
 

@@ -411,7 +411,7 @@ Ctx.me_frame_dev = _ctx_me_frame_dev
 
 class ME_FRAME_PARAMS(ctypes.Structure):      # x265b200_me_frame_params
     _fields_ = [(k, ctypes.c_int32) for k in ("depth", "ctuSize", "minCuSize", "rect", "amp", "picWidth", "picHeight", "ctuCols", "ctuRows",
-                                              "marginX", "marginY", "rowsTotal", "numRefs", "searchMethod", "subpelRefine", "merange", "csp",
+                                              "marginX", "marginY", "rowsTotal", "chromaMarginX", "chromaMarginY", "numRefs", "searchMethod", "subpelRefine", "merange", "csp",
                                               "maxCand", "maxSlices", "frameParallel", "firstCtuRow", "sliceTotalRows", "refLagPixels")] + [("lambda_", ctypes.c_double)]
 
 
@@ -627,3 +627,25 @@ def _ctx_deblock_dev(self, chroma, depth, dPic, dJobs, n):
 Ctx.sao_apply_dev = _ctx_sao_apply_dev
 Ctx.sao_stats_dev = _ctx_sao_stats_dev
 Ctx.deblock_dev = _ctx_deblock_dev
+
+
+def _ctx_cutree_propagate_dev(self, wcu, hcu, dPropB, dIntra, dLowresCosts, dInvQ, dMvs0, dMvs1, dRef0, dRef1, bipredWeight, fpsFactor):
+    self._chk(self.L.x265b200_cutree_propagate_dev(self.h, int(wcu), int(hcu), _vp(dPropB), _vp(dIntra), _vp(dLowresCosts), _vp(dInvQ), _vp(dMvs0), _vp(dMvs1),
+                                                   _vp(dRef0), _vp(dRef1), int(bipredWeight), ctypes.c_double(fpsFactor)))
+
+
+Ctx.cutree_propagate_dev = _ctx_cutree_propagate_dev
+
+
+def _ctx_aq_energy_dev(self, depth, csp, qgSize, dY, strideY, dCb, dCr, strideC, picW, picH, dEnergy, dWp):
+    self._chk(self.L.x265b200_aq_energy_dev(self.h, int(depth), int(csp), int(qgSize), _vp(dY), _i64(strideY), _vp(dCb), _vp(dCr), _i64(strideC),
+                                            int(picW), int(picH), _vp(dEnergy), _vp(dWp)))
+
+
+def _ctx_apply_weight_dev(self, depth, dSrc, dDst, stride, width, height, marginX, marginY, weight, offset, log2Denom):
+    self._chk(self.L.x265b200_apply_weight_dev(self.h, int(depth), _vp(dSrc), _vp(dDst), _i64(stride), int(width), int(height), int(marginX), int(marginY),
+                                               int(weight), int(offset), int(log2Denom)))
+
+
+Ctx.aq_energy_dev = _ctx_aq_energy_dev
+Ctx.apply_weight_dev = _ctx_apply_weight_dev

@@ -149,6 +149,13 @@ int me_frame_ex_dev(Ctx*, const x265b200_me_frame_params* P, const x265b200_me_f
 int sad_stream_dev(Ctx*, int depth, const void* poolOrigin, int64_t framePitch, int64_t stride, int marginX, int marginY, int rowsTotal, int numFrames,
                    int ctuCols, int ctuRows, const x265b200_sad_group* groupsHost, int numGroups, int numRefs,
                    int32_t* out8, int32_t* out16, int32_t* out32, int32_t* out64);
+int cutree_propagate_dev(Ctx*, int widthInCU, int heightInCU, const uint16_t* propagateCostB, const int32_t* intraCost, const uint16_t* lowresCosts,
+                         const int32_t* invQscale, const int32_t* mvs0, const int32_t* mvs1, uint16_t* refCost0, uint16_t* refCost1,
+                         int bipredWeight, double fpsFactor);
+int aq_energy_dev(Ctx*, int depth, int csp, int qgSize, const void* y, int64_t strideY, const void* cb, const void* cr, int64_t strideC,
+                  int picWidth, int picHeight, uint32_t* energy, uint64_t* wpSumSsd);
+int apply_weight_dev(Ctx*, int depth, const void* srcOrigin, void* dstOrigin, int64_t stride, int width, int height, int marginX, int marginY,
+                     int inputWeight, int inputOffset, int log2WeightDenom);
 int me_frame_layout(int ctuSize, int minCuSize, int rect, int amp, int32_t* outXYWH, int cap);
 void me_ctu_release(Ctx* ctx);
 int me_frame_dev(Ctx*, int depth, const void* curOrigin, int64_t curStride, const void* const* refOriginsHost, int numRefs, int64_t refStride,
@@ -642,6 +649,26 @@ int x265b200_me_frame_ex_host(x265b200_ctx* ctx, const x265b200_me_frame_params*
     X265B200_CHECK(cudaMemcpyAsync(hostOut, devOut, outBytes, cudaMemcpyDeviceToHost, ctx->c.stream));
     X265B200_CHECK(cudaStreamSynchronize(ctx->c.stream));
     return 0;
+}
+int x265b200_cutree_propagate_dev(x265b200_ctx* ctx, int widthInCU, int heightInCU, const uint16_t* propagateCostB, const int32_t* intraCost,
+                                  const uint16_t* lowresCosts, const int32_t* invQscale, const int32_t* mvs0, const int32_t* mvs1,
+                                  uint16_t* refCost0, uint16_t* refCost1, int bipredWeight, double fpsFactor)
+{
+    REQUIRE_CTX(ctx);
+    return cutree_propagate_dev(CTX(ctx), widthInCU, heightInCU, propagateCostB, intraCost, lowresCosts, invQscale, mvs0, mvs1, refCost0, refCost1,
+                                bipredWeight, fpsFactor);
+}
+int x265b200_aq_energy_dev(x265b200_ctx* ctx, int depth, int csp, int qgSize, const void* y, int64_t strideY, const void* cb, const void* cr,
+                           int64_t strideC, int picWidth, int picHeight, uint32_t* energy, uint64_t* wpSumSsd)
+{
+    REQUIRE_CTX(ctx);
+    return aq_energy_dev(CTX(ctx), depth, csp, qgSize, y, strideY, cb, cr, strideC, picWidth, picHeight, energy, wpSumSsd);
+}
+int x265b200_apply_weight_dev(x265b200_ctx* ctx, int depth, const void* srcOrigin, void* dstOrigin, int64_t stride, int width, int height,
+                              int marginX, int marginY, int inputWeight, int inputOffset, int log2WeightDenom)
+{
+    REQUIRE_CTX(ctx);
+    return apply_weight_dev(CTX(ctx), depth, srcOrigin, dstOrigin, stride, width, height, marginX, marginY, inputWeight, inputOffset, log2WeightDenom);
 }
 int x265b200_me_frame_layout(int ctuSize, int minCuSize, int rect, int amp, int32_t* outXYWH, int cap)
 {

@@ -248,7 +248,7 @@ static int me_ctu_launch(Ctx* ctx, const x265b200_me_frame_params* P, const x265
     const int R = L.R, costK = L.costK, winPitch = L.winPitch, winRows = L.winRows, cwinPitch = L.cwinPitch, cwinRows = L.cwinRows;
     const size_t smem = L.smemBytes;
 
-    const int cmarginX = P->marginX >> hs, cmarginY = P->marginY >> vs;
+    const int cmarginX = P->chromaMarginX > 0 ? P->chromaMarginX : P->marginX >> hs, cmarginY = P->chromaMarginY > 0 ? P->chromaMarginY : P->marginY >> vs;
     if ((P->marginX * px) & 15) { set_error("me_frame_ex: marginX*sizeof(pixel) must be a multiple of 16 bytes (TMA box alignment)"); return -1; }
     if (chromaSatd && ((cmarginX * px) & 15)) { set_error("me_frame_ex: chroma marginX*sizeof(pixel) must be a multiple of 16 bytes"); return -1; }
     if (P->marginX < 64 || P->marginY < 16) { set_error("me_frame_ex: plane margins (%d,%d) smaller than the reference's PicYuv padding", P->marginX, P->marginY); return -1; }
@@ -258,7 +258,7 @@ static int me_ctu_launch(Ctx* ctx, const x265b200_me_frame_params* P, const x265
     if (mc_tables(ctx, C, P->minCuSize, P->rect, P->amp, P->csp, chromaSatd, sizeMask, T)) return -1;
 
     MECtuMaps maps; memset(&maps, 0, sizeof(maps));
-    const int rowsC = P->rowsTotal >> vs;
+    const int rowsC = ((P->rowsTotal - 2 * P->marginY) >> vs) + 2 * cmarginY;
     if (mc_encode_plane(&maps.cur[0], depth, pl->curY, pl->curStride, P->marginX, P->marginY, P->rowsTotal, 64, L.fencRows, false, "source luma")) return -1;
     for (int r = 0; r < P->numRefs; r++)
         if (mc_encode_plane(&maps.ref[0][r], depth, pl->refY[r], pl->refStride, P->marginX, P->marginY, P->rowsTotal, winPitch / px, L.winBoxRows, true, "reference luma")) return -1;

@@ -33,6 +33,61 @@ __global__ void propagate_cost_kernel(int* dst, const uint16_t* propagateIn, con
     dst[i] = x86_double_to_int(__dadd_rn(__ddiv_rn(__dmul_rn(propagateAmount, propagateNum), propagateDenom), 0.5));
 }
 
+// ---- Lookahead::estimateCUPropagate (slicetype.cpp:2641-2747): the cuTree propagation step of one (p0, p1, b) ------------------
+// Per 8x8 CU of frame b: the amount to propagate (estimateCUPropagateCost, the arithmetic of propagate_cost_kernel above), split by
+// the lists the CU used, follows its lowres MVs into the reference frames and is spread bilinearly over the four CUs it lands on.
+// The reference adds with CLIP_ADD (saturate at 65535) in raster order; every addend is >= 0, so the final value of an entry is
+// min(old + sum of its addends, 65535) whatever the order: the addends are summed with 64-bit atomics, then one pass clamps.
+struct CuTreeArgs
+{
+    const uint16_t* propagateIn;          // frames[b]->propagateCost, or nullptr (non-referenced frame: zeros)
+    const int32_t* intraCost; const uint16_t* lowresCosts; const int32_t* invQscale;
+    const int32_t* mvs[2];                // lowresMvs[list][listDist[list]] ({x, y} int32 pairs), may be nullptr when the list is unused
+    unsigned long long* acc[2];           // zeroed accumulators for frames[p0] / frames[p1]->propagateCost
+    int widthInCU, heightInCU, bipredWeight;
+    double fpsFactor;
+};
+__global__ void cutree_propagate_kernel(CuTreeArgs p)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int W = p.widthInCU, Hc = p.heightInCU;
+    if (i >= W * Hc) return;
+    const int blockx = i % W, blocky = i / W;
+    const double fps = __ddiv_rn(p.fpsFactor, 256.0);
+    const int intraCost = p.intraCost[i];
+    const int interCost = min(intraCost, (int)(p.lowresCosts[i] & ((1 << 14) - 1)));
+    const double propagateIntra = (double)(int)((uint32_t)intraCost * (uint32_t)p.invQscale[i]);
+    const double propagateAmount = __dadd_rn((double)(p.propagateIn ? p.propagateIn[i] : (uint16_t)0), __dmul_rn(propagateIntra, fps));
+    const int amount = x86_double_to_int(__dadd_rn(__ddiv_rn(__dmul_rn(propagateAmount, (double)(intraCost - interCost)), (double)intraCost), 0.5));
+    if (amount <= 0) return;                                       // don't propagate for an intra block
+    const int listsUsed = p.lowresCosts[i] >> 14;
+    for (int list = 0; list < 2; list++)
+    {
+        if (!((listsUsed >> list) & 1)) continue;
+        int listamount = amount;
+        if (listsUsed == 3) listamount = (listamount * (list ? 64 - p.bipredWeight : p.bipredWeight) + 32) >> 6;
+        unsigned long long* acc = p.acc[list];
+        int x = p.mvs[list][2 * i], y = p.mvs[list][2 * i + 1];
+        if (!(x | y)) { atomicAdd(&acc[i], (unsigned long long)listamount); continue; }
+        const int cux = (x >> 5) + blockx, cuy = (y >> 5) + blocky;
+        const int idx0 = cux + cuy * W;
+        x &= 31; y &= 31;
+        const int w0 = (32 - y) * (32 - x), w1 = (32 - y) * x, w2 = y * (32 - x), w3 = y * x;
+        // (the reference's fast path for fully-inside targets and its per-target checks select the same targets)
+        if (cux >= 0 && cux < W && cuy >= 0 && cuy < Hc)             atomicAdd(&acc[idx0], (unsigned long long)((listamount * w0 + 512) >> 10));
+        if (cux + 1 >= 0 && cux + 1 < W && cuy >= 0 && cuy < Hc)     atomicAdd(&acc[idx0 + 1], (unsigned long long)((listamount * w1 + 512) >> 10));
+        if (cux >= 0 && cux < W && cuy + 1 >= 0 && cuy + 1 < Hc)     atomicAdd(&acc[idx0 + W], (unsigned long long)((listamount * w2 + 512) >> 10));
+        if (cux + 1 >= 0 && cux + 1 < W && cuy + 1 >= 0 && cuy + 1 < Hc) atomicAdd(&acc[idx0 + W + 1], (unsigned long long)((listamount * w3 + 512) >> 10));
+    }
+}
+__global__ void cutree_clamp_kernel(uint16_t* cost, const unsigned long long* acc, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long v = (unsigned long long)cost[i] + acc[i];
+    cost[i] = (uint16_t)(v < 65535ull ? v : 65535ull);
+}
+
 __global__ void fix8_pack_kernel(uint16_t* dst, const double* src, int64_t n)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -179,6 +234,110 @@ __global__ void plane_clip_max_kernel(pixel* src, int64_t stride, int width, int
 }
 
 } // namespace
+
+int scratch_dev(Ctx* ctx, int slot, size_t bytes, void** out);
+int extend_border_dev(Ctx* ctx, int depth, void* origin, int64_t stride, int width, int height, int marginX, int marginY);
+
+// ---- LookaheadTLD::acEnergyCu for every quantisation-group block of a frame (slicetype.cpp:49-86, :252-275) ----------------------
+// One warp per block: pixel_var (sum | sqr << 32, pixel.cpp:703-720) of the luma block and of the two chroma blocks, each folded as
+// acEnergyVar folds it (ssd - (sum * sum >> shift), 32-bit) and added; the per-plane sums / ssds also go to the frame's wp_sum /
+// wp_ssd (the inputs of weightsAnalyse).  The float qp-offset arithmetic of calcAdaptiveQuantFrame stays on the host.
+template<typename pixel>
+__global__ void aq_energy_kernel(const pixel* y, int64_t strideY, const pixel* cb, const pixel* cr, int64_t strideC, int hShift, int vShift,
+                                 int blocksX, int blocksY, int qg, int csp, uint32_t* energy, unsigned long long* wp /* [6]: sum Y,Cb,Cr, ssd Y,Cb,Cr */)
+{
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= blocksX * blocksY) return;
+    const int bx = (b % blocksX) * qg, by = (b / blocksX) * qg;
+    uint32_t total = 0;
+    for (int plane = 0; plane < (csp ? 3 : 1); plane++)
+    {
+        const bool sub = plane && csp != 3;                       // 4:2:0 / 4:2:2 chroma blocks are half size (copied to 4x4 / 8x8, :62-77)
+        const int size = sub ? qg >> 1 : qg;
+        const pixel* p = plane == 0 ? y + bx + (int64_t)by * strideY
+                                    : (plane == 1 ? cb : cr) + (bx >> hShift) + (int64_t)(by >> vShift) * strideC;
+        const int64_t st = plane ? strideC : strideY;
+        uint32_t sum = 0, sqr = 0;
+        for (int e = lane; e < size * size; e += 32)
+        {
+            const int yy = e / size, xx = e - yy * size;
+            const uint32_t v = p[(int64_t)yy * st + xx];
+            sum += v; sqr += v * v;
+        }
+        sum = (uint32_t)warp_sum((int)sum); sqr = (uint32_t)warp_sum((int)sqr);
+        const int shift = size == 16 ? 8 : (size == 8 ? 6 : 4);
+        total += sqr - (uint32_t)(((unsigned long long)sum * sum) >> shift);
+        if (lane == 0) { atomicAdd(&wp[plane], (unsigned long long)sum); atomicAdd(&wp[3 + plane], (unsigned long long)sqr); }
+    }
+    if (lane == 0) energy[b] = total;
+}
+
+int aq_energy_dev(Ctx* ctx, int depth, int csp, int qgSize, const void* y, int64_t strideY, const void* cb, const void* cr, int64_t strideC,
+                  int picWidth, int picHeight, uint32_t* energy, uint64_t* wpSumSsd)
+{
+    if (qgSize != 8 && qgSize != 16) { set_error("aq_energy: qgSize %d (8 or 16)", qgSize); return -1; }
+    if (csp < 0 || csp > 3 || (csp && (!cb || !cr))) { set_error("aq_energy: csp %d / chroma planes", csp); return -1; }
+    const int bxn = (picWidth + qgSize - 1) / qgSize, byn = (picHeight + qgSize - 1) / qgSize;
+    if (bxn <= 0 || byn <= 0) return 0;
+    X265B200_CHECK(cudaMemsetAsync(wpSumSsd, 0, 6 * sizeof(uint64_t), ctx->stream));
+    const int hs = (csp == 1 || csp == 2) ? 1 : 0, vs = csp == 1 ? 1 : 0;
+    const int n = bxn * byn;
+    if (depth > 8) aq_energy_kernel<uint16_t><<<(n + 7) / 8, 256, 0, ctx->stream>>>((const uint16_t*)y, strideY, (const uint16_t*)cb, (const uint16_t*)cr, strideC, hs, vs, bxn, byn, qgSize, csp, energy, (unsigned long long*)wpSumSsd);
+    else           aq_energy_kernel<uint8_t><<<(n + 7) / 8, 256, 0, ctx->stream>>>((const uint8_t*)y, strideY, (const uint8_t*)cb, (const uint8_t*)cr, strideC, hs, vs, bxn, byn, qgSize, csp, energy, (unsigned long long*)wpSumSsd);
+    ctx->launches++;
+    return check(cudaGetLastError(), "aq_energy launch");
+}
+
+// ---- MotionReference::applyWeight for a whole plane (reference.cpp:119-185) ------------------------------------------------------
+template<typename pixel>
+__global__ void apply_weight_kernel(const pixel* src, pixel* dst, int64_t stride, int width, int height, int w0, int round, int shift, int offset, int corr, int maxVal)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)width * height) return;
+    const int r = (int)(i / width), c = (int)(i - (int64_t)r * width);
+    const int v = ((w0 * ((int)src[(int64_t)r * stride + c] << corr) + round) >> shift) + offset;          // weight_pp_c, pixel.cpp:516-543
+    dst[(int64_t)r * stride + c] = (pixel)(v < 0 ? 0 : (v > maxVal ? maxVal : v));
+}
+
+int apply_weight_dev(Ctx* ctx, int depth, const void* srcOrigin, void* dstOrigin, int64_t stride, int width, int height, int marginX, int marginY,
+                     int inputWeight, int inputOffset, int log2WeightDenom)
+{
+    if (width <= 0 || height <= 0) return 0;
+    // MotionReference::init (:100-103) and applyWeight (:160-161): offset scaled to the bit depth, rounding and shift in the
+    // 14-bit intermediate domain of weight_pp
+    const int corr = 14 - depth;
+    const int offset = inputOffset * (1 << (depth - 8));
+    const int round = (log2WeightDenom ? 1 << (log2WeightDenom - 1) : 0) << corr, shift = log2WeightDenom + corr;
+    const int64_t n = (int64_t)width * height;
+    if (depth > 8) apply_weight_kernel<uint16_t><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((const uint16_t*)srcOrigin, (uint16_t*)dstOrigin, stride, width, height, inputWeight, round, shift, offset, corr, (1 << depth) - 1);
+    else           apply_weight_kernel<uint8_t><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((const uint8_t*)srcOrigin, (uint8_t*)dstOrigin, stride, width, height, inputWeight, round, shift, offset, corr, 255);
+    ctx->launches++;
+    if (check(cudaGetLastError(), "apply_weight launch")) return -1;
+    return extend_border_dev(ctx, depth, dstOrigin, stride, width, height, marginX, marginY);     // extendRowBorder + the rows above / below (:163-182)
+}
+
+int cutree_propagate_dev(Ctx* ctx, int widthInCU, int heightInCU, const uint16_t* propagateCostB, const int32_t* intraCost, const uint16_t* lowresCosts,
+                         const int32_t* invQscale, const int32_t* mvs0, const int32_t* mvs1, uint16_t* refCost0, uint16_t* refCost1,
+                         int bipredWeight, double fpsFactor)
+{
+    const int n = widthInCU * heightInCU;
+    if (n <= 0) return 0;
+    if (!intraCost || !lowresCosts || !invQscale || !refCost0) { set_error("cutree_propagate: null array"); return -1; }
+    void* scr = nullptr;
+    if (scratch_dev(ctx, 6, (size_t)n * 16, &scr)) return -1;
+    X265B200_CHECK(cudaMemsetAsync(scr, 0, (size_t)n * 16, ctx->stream));
+    CuTreeArgs a;
+    a.propagateIn = propagateCostB; a.intraCost = intraCost; a.lowresCosts = lowresCosts; a.invQscale = invQscale;
+    a.mvs[0] = mvs0; a.mvs[1] = mvs1; a.acc[0] = (unsigned long long*)scr; a.acc[1] = (unsigned long long*)scr + n;
+    a.widthInCU = widthInCU; a.heightInCU = heightInCU; a.bipredWeight = bipredWeight; a.fpsFactor = fpsFactor;
+    if (!mvs0) { set_error("cutree_propagate: list 0 MVs missing"); return -1; }
+    if (!mvs1) a.mvs[1] = mvs0;                          // never dereferenced: list 1 is only used by CUs of B frames
+    cutree_propagate_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(a);
+    cutree_clamp_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(refCost0, a.acc[0], n);
+    if (refCost1 && refCost1 != refCost0) cutree_clamp_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(refCost1, a.acc[1], n);
+    ctx->launches += 2 + (refCost1 && refCost1 != refCost0);
+    return check(cudaGetLastError(), "cutree_propagate launch");
+}
 
 int propagate_cost_dev(Ctx* ctx, int* dst, const uint16_t* propagateIn, const int32_t* intraCosts, const uint16_t* interCosts,
                        const int32_t* invQscales, double fpsFactor, int64_t len)
