@@ -57,9 +57,9 @@ CONFIGS = {
             rect=0, amp=0, method=ME_DIA, subme=0, merange=57, nref=1, csp=0, NF=64),
     3: dict(name="2160p 8-bit medium primitive mix", W=W, H=H, depth=8, C=64, minCu=8, rect=0, amp=0, method=ME_HEX, subme=SUBME, merange=MERANGE, nref=NREF, csp=0, NF=32),
     4: dict(name="2160p 10-bit slow: STAR, subme 3 (chroma SATD), 4 references, rect PUs, 4:2:0", W=3840, H=2160, depth=10, C=64, minCu=8, rect=1, amp=0,
-            method=ME_STAR, subme=3, merange=57, nref=4, csp=1, NF=8),
+            method=ME_STAR, subme=3, merange=57, nref=4, csp=1, NF=20),
     5: dict(name="4320p 8-bit placebo: STAR, merange 128, subme 5, 5 references, rect + AMP, 4:2:0", W=7680, H=4320, depth=8, C=64, minCu=8, rect=1, amp=1,
-            method=ME_STAR, subme=5, merange=128, nref=5, csp=1, NF=8),
+            method=ME_STAR, subme=5, merange=128, nref=5, csp=1, NF=12),
 }
 WORKLOAD3 = ("2160p-8bit-medium primitive mix (SURVEY.md 8d config 3): SAD at the predictor + HEX subme2 merange57 search of every 2Nx2N PU 64..8 x 3 refs; "
              "one 8-tap MC interpolation per PU and level (all 15 fractions); residual -> DCT/quant/dequant/IDCT on every 32/16/8/4 TU -> recon; "
