@@ -734,9 +734,7 @@ def main():
 
     band = None
     if args.shard == "ctu-rows" and world > 1:
-        rows_all = geometry(cfg)["rows"]
-        lo = (rows_all * rank) // world; hi = (rows_all * (rank + 1)) // world
-        band = (lo, hi - lo)
+        band = pkg.band_rows(geometry(cfg)["rows"], rank, world)
     if args.config == 3 and args.shard == "ctu-rows":
         raise SystemExit("--shard ctu-rows applies to the frame-search configs (2, 4, 5)")
     wl = (MixWorkload if args.config == 3 else MEWorkload)(args, cfg, pkg, torch, ctx, dev, stream, rank, world, band)
@@ -751,7 +749,7 @@ def main():
         else:
             # ctu-rows: the bands of reconstructed rows are all_gathered (equal-sized chunks of the plane), results gathered
             rows_px = g["rows"] * wl.C
-            chunk = (rows_px + world - 1) // world
+            chunk = pkg.plane_chunk(rows_px, world)
             gathered = [torch.empty((world, chunk, g["stride"] * wl.item), dtype=torch.uint8, device=dev) for _ in range(2)]
         nres = wl.me_out[0].shape[0]
         res_max = torch.tensor([nres], device=dev); dist.all_reduce(res_max, op=dist.ReduceOp.MAX); res_max = int(res_max)

@@ -68,3 +68,82 @@ def test_frame_sharding_allgather_gather_gloo():
     assert len(res) == 3 and all(len(step) == world for step in res)
     # rank r's second-step SADs are against the plane the other rank produced in step 0
     assert all(len(v) == 8 for step in res for v in step)
+
+
+def _band_worker(rank, world, port, q):
+    """--shard ctu-rows: every rank holds the same frame, searches its band of CTU rows with the frame-relative clipping
+    (firstCtuRow), contributes its rows of the plane to the all-gather and its padded records to the gather"""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import importlib
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pkg = importlib.import_module("x265-yuuki-asuna_b200")
+    import me_util
+    C, W, H, pad, merange, nref = 16, 96, 80, 48, 16, 2                   # 5 CTU rows: bands of 2 and 3 rows
+    cols, rows = W // C, H // C
+    frames, stride, _, origin = me_util.synth_sequence(W, H, pad, pad, 8, nref + 1, seed=5, max_motion=6)
+    layout = me_util.ctu_layout(C, 8, False, False)
+    npu = len(layout)
+    mvp = np.zeros((npu, 2), dtype=np.int32)
+
+    def search(row0, nrows):
+        out = np.zeros((nref, nrows * cols * npu, 3), dtype=np.int32)
+        for r in range(nref):
+            for cy in range(row0, row0 + nrows):
+                for cx in range(cols):
+                    job, searched = me_util.ctu_jobs(pkg, layout, C, cx, cy, W, H, mvp, merange)   # picH of the WHOLE frame
+                    mx, my, cost = me_util.ref_me(8, frames[0], frames[1 + r], stride, origin, job, 1, 2, merange, 30)
+                    base = ((cy - row0) * cols + cx) * npu
+                    out[r, base:base + npu] = np.stack([mx, my, cost], axis=1)
+        return out.reshape(-1, 3)
+
+    lo, n = pkg.band_rows(rows, rank, world)
+    mine = search(lo, n)
+    assert mine.shape[0] == pkg.records_per_band(rows, cols, npu, nref, rank, world)
+    res_max = torch.tensor([mine.shape[0]]); dist.all_reduce(res_max, op=dist.ReduceOp.MAX); res_max = int(res_max)
+    send = torch.zeros((res_max, 3), dtype=torch.int32); send[:mine.shape[0]] = torch.from_numpy(mine)
+    parts = [torch.empty_like(send) for _ in range(world)] if rank == 0 else None
+    dist.gather(send, parts, dst=0)
+    # the bands' rows of the (reconstructed) plane: equal chunks, the last one padded
+    chunk = pkg.plane_chunk(H, world)
+    plane = torch.from_numpy(frames[0].reshape(-1, stride)[pad:pad + H].copy())
+    padded = torch.zeros((world * chunk, stride), dtype=torch.uint8); padded[:H] = plane
+    flat = torch.empty((world * chunk, stride), dtype=torch.uint8)
+    dist.all_gather_into_tensor(flat, padded[rank * chunk:(rank + 1) * chunk].contiguous())
+    assert torch.equal(flat[:H], plane)
+    if rank == 0:
+        whole = search(0, rows).reshape(nref, -1, 3)
+        got = pkg.assemble_bands([p.numpy() for p in parts], rows, cols, npu, nref, world)
+        q.put(bool(np.array_equal(got, whole)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_ctu_row_bands_gather_gloo():
+    from util import oracle
+    if oracle.ref(8) is None:
+        pytest.skip("oracle/_ref not built")
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_band_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    ok = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert ok, "bands searched with firstCtuRow and put back in rank order differ from the whole-frame search"
+
+
+def test_band_partition_arithmetic():
+    import importlib
+    pkg = importlib.import_module("x265-yuuki-asuna_b200")
+    for rows in (1, 5, 17, 34, 68):
+        for world in (1, 2, 3, 4, 8):
+            bands = [pkg.band_rows(rows, r, world) for r in range(world)]
+            assert bands[0][0] == 0 and sum(n for _, n in bands) == rows
+            assert all(bands[i][0] + bands[i][1] == bands[i + 1][0] for i in range(world - 1))
+            assert max(n for _, n in bands) - min(n for _, n in bands) <= 1
+            assert pkg.plane_chunk(rows * 64, world) * world >= rows * 64
