@@ -473,7 +473,7 @@ double x265b200_lambda(int qp, int depth);
  * x265b200_la_intra_dev: replaces LookaheadTLD::lowresIntraEstimate (slicetype.cpp:696-805) for one
  *   frame.  intraPenalty = 5 * (int)x265_lambda_tab[X265_LOOKAHEAD_QP].  sums[2] = costEst, costEstAq.
  * x265b200_la_estimate_dev: replaces CostEstimateGroup::estimateFrameCost / estimateCUCost
- *   (slicetype.cpp:3115-3388; weightp off, HME off) for a batch of frame triples.  lookaheadSlices = the effective
+ *   (slicetype.cpp:3115-3388; HME off) for a batch of frame triples.  lookaheadSlices = the effective
  *   --lookahead-slices (param.cpp:173 default 8 at medium; 0 or 1 = the non-cooperative path): the field is cut into
  *   cooperative slices as Lookahead::create does (slicetype.cpp:1029-1041: heightInCU / slices rows each, at least 10; the
  *   last slice runs to the bottom) and the bottom row of every slice is searched with lastRow = true (processTasks,
@@ -482,7 +482,29 @@ double x265b200_lambda(int qp, int depth);
  *   reference's lowresMvs[i][dist] / lowresMvCosts[i][dist] cache; doSearch[i] = 0 reuses the slot.
  *   Outputs per triple t: lowresCosts[t][ncu] (uint16), rowSatds[t][heightInCU], sums[t][4] =
  *   {costEst (raw sum, before the b-frame 100/130 scaling of :3203-3204), costEstAq, intraMbs, 0}. */
-typedef struct { int32_t b, p0, p1; int32_t doSearch[2]; int32_t mvSlot[2]; } x265b200_la_triple;
+typedef struct {
+    int32_t b, p0, p1; int32_t doSearch[2]; int32_t mvSlot[2];
+    int32_t weightIdx0;            /* weightp: 0 = list 0 searches p0's planes; k > 0 = when weights[k-1].isWeighted (x265b200_la_weights_analyse_dev) ... */
+    int32_t weightPlanes0;         /* ... the list-0 search reads planes[weightPlanes0][4] (the wbuffer planes) instead (slicetype.cpp:3222) */
+} x265b200_la_triple;
+/* weightp in the lookahead: LookaheadTLD::weightsAnalyse (slicetype.cpp:860-961; weightCostLuma :805-841), called by
+ * estimateFrameCost before every list-0 search when param->bEnableWeightedPred (:3136-3138).  One job = one (fenc, ref) pair:
+ * fencPlane0 = fenc.lowresPlane[0] (origin), intraCost = fenc.intraCost, refBuffer[k] = ref.buffer[k] and weighted[k] = wbuffer[k]
+ * (the FIRST element of each padded plane: weight_pp runs over stride x paddedLines elements, :947-956), fencSum / fencSsd /
+ * refSum / refSsd = wp_sum[0] / wp_ssd[0] of the two frames as calcAdaptiveQuantFrame leaves them (:672-674;
+ * x265b200_aq_energy_dev yields the raw sums).  The float scale / offset guess is evaluated on the host exactly as the reference
+ * evaluates it; the two weightCostLuma passes (8x8 SATD against the unweighted and the weighted reference, each block capped by
+ * its intra cost), the accept test and the weighting of the four planes run on the device without a host round trip.
+ * out[j] (device): isWeighted and the chosen weight, origscore / score = the two weightCostLuma sums (0 when the early
+ * termination of :895-897 applied).  x265b200_la_estimate_dev reads isWeighted through x265b200_la_triple.weightIdx0. */
+typedef struct {
+    const void* fencPlane0; const int32_t* intraCost;
+    const void* refBuffer[4]; void* weighted[4];
+    uint64_t fencSum, fencSsd, refSum, refSsd;
+} x265b200_la_weight_job;
+typedef struct { int32_t isWeighted, inputWeight, log2WeightDenom, inputOffset; uint32_t origscore, score; } x265b200_la_weight;
+int x265b200_la_weights_analyse_dev(x265b200_ctx* ctx, int depth, const x265b200_la_weight_job* jobsHost, int numJobs,
+                                    int64_t stride, int paddedLines, int64_t padOffset, int width, int lines, x265b200_la_weight* out);
 int x265b200_lowres_init_dev(x265b200_ctx* ctx, int depth, const void* src, int64_t srcStride,
                              void* const planes[4], int64_t dstStride, int width, int height, int marginX, int marginY);
 /* extendPicBorder (pixel.cpp:1027-1041: PicYuv / Lowres margins) and, with marginY = 0, primitives.extendRowBorder =
@@ -496,7 +518,7 @@ int x265b200_la_estimate_dev(x265b200_ctx* ctx, int depth, const void* const* pl
                              int widthInCU, int heightInCU, const x265b200_la_triple* triplesHost, int numTriples,
                              int32_t* mvPool, int32_t* mvCostPool, const int32_t* const* intraCost,
                              const int32_t* const* invQscale, uint16_t* lowresCosts, int32_t* rowSatds, int32_t* sums,
-                             double lambda, int lookaheadSlices);
+                             double lambda, int lookaheadSlices, const x265b200_la_weight* weights /* device, or NULL: weightp off */);
 
 /* --hme (hierarchical ME, param bEnableHME): estimateFrameCost first runs estimateCUCost(..., hme = true) over the
  * quarter-resolution planes (Lowres::lowerResPlane[4], built by primitives.frameInitLowerRes + extendPicBorder,
@@ -516,7 +538,7 @@ typedef struct {
 int x265b200_la_estimate_hme_dev(x265b200_ctx* ctx, int depth, const void* const* planes, int64_t stride, int widthInCU, int heightInCU,
                                  const x265b200_la_hme* hme, const x265b200_la_triple* triplesHost, int numTriples, int32_t* mvPool, int32_t* mvCostPool,
                                  const int32_t* const* intraCost, const int32_t* const* invQscale, uint16_t* lowresCosts,
-                                 int32_t* rowSatds, int32_t* sums, double lambda, int lookaheadSlices);
+                                 int32_t* rowSatds, int32_t* sums, double lambda, int lookaheadSlices, const x265b200_la_weight* weights);
 
 /* Lookahead::estimateCUPropagate (slicetype.cpp:2641-2747), the cuTree propagation step of one (p0, p1, b): per 8x8 CU of frame b
  * the amount estimateCUPropagateCost yields (from propagateCostB = frames[b]->propagateCost, NULL for a non-referenced frame whose

@@ -528,6 +528,8 @@ int64_t ref_la_frame_cost_slices(void* hv, int p0, int p1, int b, int lookaheadS
     doSearch[0] = fenc->lowresMvs[0][b - p0][0].x == 0x7FFF;
     doSearch[1] = p1 > b && fenc->lowresMvs[1][p1 - b][0].x == 0x7FFF;
     fenc->weightedRef[b - p0].isWeighted = false;
+    if (h->param->bEnableWeightedPred && doSearch[0])                 /* :3136-3138 */
+        la.m_tld[0].weightsAnalyse(*fenc, *h->lowres[p0]);
     fenc->costEst[b - p0][p1 - b] = 0;
     fenc->costEstAq[b - p0][p1 - b] = 0;
     memset(&est.m_slice, 0, sizeof(est.m_slice[0]) * la.m_numCoopSlices);
@@ -547,6 +549,28 @@ int64_t ref_la_frame_cost_slices(void* hv, int p0, int p1, int b, int lookaheadS
     est.m_jobTotal = est.m_jobAcquired = 0;
     return score;
 }
+/* ---- weightp in the lookahead (slicetype.cpp:860-961, hook at :3136-3138) ----
+ * ref_la_set_weightp: param->bEnableWeightedPred of the handle (estimateFrameCost then calls weightsAnalyse before a list-0 search).
+ * ref_la_set_wp_stats: Lowres::wp_sum[0] / wp_ssd[0] as calcAdaptiveQuantFrame leaves them (:672-674).
+ * ref_la_weights_analyse: LookaheadTLD::weightsAnalyse(frames[b], frames[p0]) alone; out = {isWeighted, paddedLines}.
+ * ref_la_weighted_buffer: LookaheadTLD::wbuffer[k] (start of the padded plane) of the TLD singleCost uses without a pool. */
+void ref_la_set_weightp(void* hv, int on) { ((RefLA*)hv)->param->bEnableWeightedPred = on; }
+void ref_la_set_wp_stats(void* hv, int idx, uint64_t sum0, uint64_t ssd0)
+{
+    Lowres* l = ((RefLA*)hv)->lowres[idx];
+    l->wp_sum[0] = sum0; l->wp_ssd[0] = ssd0;
+}
+void ref_la_weights_analyse(void* hv, int b, int p0, int32_t* out)
+{
+    RefLA* h = (RefLA*)hv;
+    Lowres* fenc = h->lowres[b];
+    fenc->weightedRef[b - p0].isWeighted = false;
+    h->la->m_tld[0].weightsAnalyse(*fenc, *h->lowres[p0]);
+    out[0] = fenc->weightedRef[b - p0].isWeighted; out[1] = h->la->m_tld[0].paddedLines;
+}
+int ref_la_is_weighted(void* hv, int b, int d0) { return ((RefLA*)hv)->lowres[b]->weightedRef[d0].isWeighted; }
+const void* ref_la_weighted_buffer(void* hv, int k) { return ((RefLA*)hv)->la->m_tld[0].wbuffer[k]; }
+
 /* Lookahead::estimateCUPropagate (slicetype.cpp:2641-2747) on the frames of the handle; fps = fpsNum / fpsDenom of the param */
 void ref_la_cutree_propagate(void* hv, int p0, int p1, int b, int referenced, double averageDuration)
 {

@@ -22,7 +22,9 @@ int main(void)
     S(x265b200_me_job); F(x265b200_me_job, puX); F(x265b200_me_job, w); F(x265b200_me_job, mvminX); F(x265b200_me_job, mvpX); F(x265b200_me_job, numCand);
     F(x265b200_me_job, mvc); F(x265b200_me_job, refIdx); F(x265b200_me_job, outMvX); F(x265b200_me_job, outCost);
     S(x265b200_glue_job); S(x265b200_interp_job); F(x265b200_interp_job, idxX); S(x265b200_intra_job); F(x265b200_intra_job, mode);
-    S(x265b200_la_triple); F(x265b200_la_triple, doSearch); F(x265b200_la_triple, mvSlot);
+    S(x265b200_la_triple); F(x265b200_la_triple, doSearch); F(x265b200_la_triple, mvSlot); F(x265b200_la_triple, weightIdx0); F(x265b200_la_triple, weightPlanes0);
+    S(x265b200_la_weight_job); F(x265b200_la_weight_job, intraCost); F(x265b200_la_weight_job, refBuffer); F(x265b200_la_weight_job, weighted); F(x265b200_la_weight_job, fencSum); F(x265b200_la_weight_job, refSsd);
+    S(x265b200_la_weight); F(x265b200_la_weight, inputOffset); F(x265b200_la_weight, origscore); F(x265b200_la_weight, score);
     S(x265b200_ads_job); F(x265b200_ads_job, thresh); F(x265b200_ads_job, encDC);
     S(x265b200_mc_job); F(x265b200_mc_job, cuX); F(x265b200_mc_job, refIdx); F(x265b200_mc_job, mv);
     S(x265b200_mc_weight); S(x265b200_mc_desc); F(x265b200_mc_desc, refs); F(x265b200_mc_desc, predY); F(x265b200_mc_desc, predStrideY); F(x265b200_mc_desc, weights);
@@ -55,7 +57,7 @@ def _probe():
 def test_record_layouts_match_the_header():
     c = _probe()
     dtypes = {"x265b200_me_job": pkg.ME_JOB, "x265b200_interp_job": pkg.INTERP_JOB, "x265b200_intra_job": pkg.INTRA_JOB,
-              "x265b200_la_triple": pkg.LA_TRIPLE, "x265b200_ads_job": pkg.ADS_JOB, "x265b200_mc_job": pkg.MC_JOB,
+              "x265b200_la_triple": pkg.LA_TRIPLE, "x265b200_la_weight_job": pkg.LA_WEIGHT_JOB, "x265b200_la_weight": pkg.LA_WEIGHT, "x265b200_ads_job": pkg.ADS_JOB, "x265b200_mc_job": pkg.MC_JOB,
               "x265b200_mc_weight": pkg.MC_WEIGHT, "x265b200_sad_group": pkg.SAD_GROUP, "x265b200_sao_job": pkg.SAO_JOB, "x265b200_deblock_job": pkg.DEBLOCK_JOB}
     if hasattr(pkg, "GLUE_JOB"):
         dtypes["x265b200_glue_job"] = pkg.GLUE_JOB

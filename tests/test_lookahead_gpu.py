@@ -176,6 +176,161 @@ def test_lookahead_matches_reference(ctx, depth, W, H, aq, slices):
     R.ref_la_destroy(h)
 
 
+def _fade_frames(W, H, n, depth, seed, gains, offsets):
+    """a moving scene whose brightness follows gains / offsets per frame (what weightp is for)"""
+    rng = np.random.default_rng(seed)
+    base = rng.integers(0, 256, (H + 96, W + 96)).astype(np.float32)
+    k = np.ones(5) / 5
+    for ax in (0, 1):
+        base = np.apply_along_axis(lambda r: np.convolve(r, k, mode="same"), ax, base)
+    base = (base - base.min()) / (base.max() - base.min()) * 200 + 20
+    out = []
+    x = y = 40
+    for i in range(n):
+        x += int(rng.integers(-4, 5)); y += int(rng.integers(-3, 4))
+        fr = base[y:y + H, x:x + W] * gains[i] + offsets[i] + rng.normal(0, 1.5, (H, W))
+        out.append(np.ascontiguousarray(np.clip(np.rint(fr * (1 << (depth - 8))), 0, (1 << depth) - 1).astype(pdtype(depth))))
+    return out
+
+
+@pytest.mark.parametrize("depth,W,H,slices", [(8, 320, 192, 0), (10, 320, 192, 0), (8, 320, 704, 4)])
+def test_lookahead_weightp_matches_reference(ctx, depth, W, H, slices):
+    """weightp in the lookahead (slicetype.cpp:860-961 weightsAnalyse, hook :3136-3138, use :3222): the reference's Lookahead with
+    bEnableWeightedPred = 1 runs weightsAnalyse before every list-0 search; ours runs x265b200_la_weights_analyse_dev for the
+    wave's (fenc, ref) pairs and x265b200_la_estimate_dev reads the device-side decision.  Frames 0..2 fade (pure gain: the reference takes its means from full-resolution sums over lowres areas, so offsets never survive),
+    frames 3..4 do not: weighted pairs, pairs that terminate early and pairs measured but rejected all occur."""
+    R = oracle.ref(depth)
+    assert R is not None, "oracle/_ref missing"
+    _bind(R)
+    R.ref_la_weighted_buffer.restype = ctypes.c_void_p
+    NF, BF = 5, 3
+    h = ctypes.c_void_p(R.ref_la_create(W, H, BF, 0))
+    R.ref_la_set_weightp(h, 1)
+    frames = _fade_frames(W, H, NF, depth, seed=11 * W + depth, gains=[0.55, 0.7, 0.85, 1.0, 1.0], offsets=[0, 0, 0, 0, 0])
+    for f in frames:
+        R.ref_la_add_frame(h, ctypes.c_void_p(f.ctypes.data), ctypes.c_ssize_t(W))
+    g = (ctypes.c_int64 * 11)()
+    R.ref_la_geometry(h, g)
+    lw, ll, ls, mx, my, wcu, hcu, fs, fmx, fmy, frows = [int(v) for v in g]
+    ncu = wcu * hcu
+    dt = pdtype(depth)
+    px = np.dtype(dt).itemsize
+    ct = ctypes.c_uint8 if depth == 8 else ctypes.c_uint16
+    planesize, padoff = ls * (ll + 2 * my), ls * my + mx
+    paddedLines = planesize // ls
+    # wp_sum[0] / wp_ssd[0] as calcAdaptiveQuantFrame leaves them (slicetype.cpp:672-674), on both sides
+    stats = []
+    for i, f in enumerate(frames):
+        v = f.astype(np.int64)
+        sm, ssd = int(v.sum()), int((v * v).sum())
+        ssd = ssd - (sm * sm + (W * H) // 2) // (W * H)
+        stats.append((sm, ssd))
+        R.ref_la_set_wp_stats(h, i, ctypes.c_uint64(sm), ctypes.c_uint64(ssd))
+
+    bufs_all, plane_ptrs = [], np.zeros((NF + 4, 4), dtype=np.int64)
+    for i in range(NF):
+        full = _arr(R.ref_la_fullres_buffer(h, i), ct, (fs * frows,))
+        dFull = ctx.to_device(full)
+        bufs = [ctx.to_device(np.zeros(planesize, dtype=dt)) for _ in range(4)]
+        ctx.lowres_init_dev(depth, dFull.ptr + (fmy * fs + fmx) * px, fs, [b.ptr + padoff * px for b in bufs], ls, lw, ll, mx, my)
+        plane_ptrs[i] = [b.ptr + padoff * px for b in bufs]
+        bufs_all.append(bufs)
+        dFull.free()
+    # one set of wbuffer planes per pair of a wave (the reference reuses ONE per thread, sequentially)
+    wbufs = [[ctx.to_device(np.full(planesize, 7, dtype=dt)) for _ in range(4)] for _ in range(4)]
+    for j in range(4):
+        plane_ptrs[NF + j] = [b.ptr + padoff * px for b in wbufs[j]]
+    dPlanePtrs = ctx.to_device(plane_ptrs)
+
+    lam = pkg.lambda_for_qp(12 + 6 * (depth - 8), depth)
+    intraPenalty = 5 * int(lam)
+    dIntraCost, intra_ptrs = [], np.zeros(NF, dtype=np.int64)
+    for i in range(NF):
+        R.ref_la_intra(h, i)
+        dIC, dIM, dLC, dRS, dSm = ctx.empty(ncu * 4), ctx.empty(ncu), ctx.empty(ncu * 2), ctx.empty(hcu * 4), ctx.empty(8)
+        ctx.la_intra_dev(depth, plane_ptrs[i, 0], ls, wcu, hcu, None, intraPenalty, dIC, dIM, dLC, dRS, dSm)
+        dIntraCost.append(dIC); intra_ptrs[i] = dIC.ptr
+    dIntraPtrs = ctx.to_device(intra_ptrs)
+
+    def slot(b, lst, dist):
+        return (b * 2 + lst) * (BF + 2) + dist
+    nslots = NF * 2 * (BF + 2)
+    dMv, dMvC = ctx.to_device(np.zeros(nslots * ncu * 2, dtype=np.int32)), ctx.to_device(np.zeros(nslots * ncu, dtype=np.int32))
+    searched = set()
+    waves = [[(0, 4, 2), (0, 4, 4), (3, 4, 4), (1, 3, 2)],      # B with a fading list 0, P across the fade, P without fade, B
+             [(0, 2, 2), (2, 4, 3), (0, 1, 1), (1, 4, 2)]]
+    seen = {"weighted": 0, "early": 0, "rejected": 0}
+    for wave in waves:
+        tr = np.zeros(len(wave), dtype=pkg.LA_TRIPLE)
+        jobs = np.zeros(len(wave), dtype=pkg.LA_WEIGHT_JOB)
+        njobs = 0
+        expect = []
+        for t, (p0, p1, b) in enumerate(wave):
+            tr[t]["b"], tr[t]["p0"], tr[t]["p1"] = b, p0, p1
+            for lst, dist in ((0, b - p0), (1, p1 - b)):
+                key = (b, lst, dist)
+                tr[t]["mvSlot"][lst] = slot(*key)
+                need = key not in searched and (lst == 0 or p1 > b)
+                tr[t]["doSearch"][lst] = int(need)
+                if need:
+                    searched.add(key)
+            if tr[t]["doSearch"][0]:
+                J = jobs[njobs]
+                J["fencPlane0"], J["intraCost"] = plane_ptrs[b, 0], intra_ptrs[b]
+                J["refBuffer"] = [bb.ptr for bb in bufs_all[p0]]
+                J["weighted"] = [bb.ptr for bb in wbufs[njobs]]
+                J["fencSum"], J["fencSsd"], J["refSum"], J["refSsd"] = stats[b][0], stats[b][1], stats[p0][0], stats[p0][1]
+                tr[t]["weightIdx0"], tr[t]["weightPlanes0"] = njobs + 1, NF + njobs
+                njobs += 1
+            if slices:
+                R.ref_la_frame_cost_slices(h, p0, p1, b, slices)
+            else:
+                R.ref_la_frame_cost(h, p0, p1, b, 0)
+            if tr[t]["doSearch"][0]:
+                w = int(R.ref_la_is_weighted(h, b, b - p0))
+                planes = [_arr(R.ref_la_weighted_buffer(h, k), ct, (planesize,)) for k in range(4)] if w else None
+                expect.append((w, planes))
+        dW = ctx.to_device(np.zeros(max(njobs, 1), dtype=pkg.LA_WEIGHT))
+        ctx.la_weights_analyse_dev(depth, jobs[:njobs], ls, paddedLines, padoff, lw, ll, dW)
+        dLC, dRS, dSm = ctx.empty(len(wave) * ncu * 2), ctx.empty(len(wave) * hcu * 4), ctx.empty(len(wave) * 16)
+        ctx.la_estimate_dev(depth, dPlanePtrs, ls, wcu, hcu, tr, dMv, dMvC, dIntraPtrs, None, dLC, dRS, dSm, lam,
+                            lookaheadSlices=slices, dWeights=dW)
+        got = dW.download(pkg.LA_WEIGHT)
+        for j, (w, planes) in enumerate(expect):
+            assert int(got[j]["isWeighted"]) == w, ("isWeighted", wave, j, got[j])
+            if w:
+                seen["weighted"] += 1
+                for k in range(4):
+                    assert np.array_equal(wbufs[j][k].download(dt), planes[k]), ("weighted plane", wave, j, k)
+            elif int(got[j]["origscore"]) == 0:
+                seen["early"] += 1
+            else:
+                seen["rejected"] += 1
+        lc = dLC.download(np.uint16).reshape(len(wave), ncu)
+        rs = dRS.download(np.int32).reshape(len(wave), hcu)
+        sm = dSm.download(np.int32).reshape(len(wave), 4)
+        mv = dMv.download(np.int32).reshape(nslots, ncu, 2)
+        mvc = dMvC.download(np.int32).reshape(nslots, ncu)
+        for t, (p0, p1, b) in enumerate(wave):
+            for lst, dist in ((0, b - p0), (1, p1 - b)):
+                if lst == 1 and p1 == b:
+                    continue
+                emv = _arr(R.ref_la_mvs(h, b, lst, dist), ctypes.c_int32, (ncu, 2))
+                emc = _arr(R.ref_la_mvcosts(h, b, lst, dist), ctypes.c_int32, (ncu,))
+                bad = np.nonzero((mv[slot(b, lst, dist)] != emv).any(axis=1) | (mvc[slot(b, lst, dist)] != emc))[0]
+                assert not len(bad), ("MV/cost", (p0, p1, b), lst, int(bad[0]), len(bad))
+            assert np.array_equal(lc[t], _arr(R.ref_la_lowres_costs(h, b, b - p0, p1 - b), ctypes.c_uint16, (ncu,))), ("lowresCosts", wave[t])
+            assert np.array_equal(rs[t], _arr(R.ref_la_row_satds(h, b, b - p0, p1 - b), ctypes.c_int32, (hcu,))), ("rowSatds", wave[t])
+            score = int(sm[t][0])
+            if b != p1:
+                score = score * 100 // 130
+            assert score == R.ref_la_cost_est(h, b, b - p0, p1 - b, 0), ("costEst", wave[t])
+        for bb in (dLC, dRS, dSm, dW):
+            bb.free()
+    assert seen["weighted"] >= 2 and seen["early"] >= 1, seen
+    R.ref_la_destroy(h)
+
+
 @pytest.mark.parametrize("depth,W,H", [(8, 320, 192), (8, 424, 240), (10, 320, 192)])
 def test_lookahead_hme_matches_reference(ctx, depth, W, H):
     """--hme: quarter-resolution planes (frameInitLowerRes + borders), the level-0 search (lowerResMvs / lowerResMvCosts) and the

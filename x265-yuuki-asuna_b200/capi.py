@@ -350,7 +350,12 @@ Ctx.add_ps_plane_dev = _ctx_add_ps_plane_dev
 
 
 # ---- lookahead -------------------------------------------------------------------------------------
-LA_TRIPLE = np.dtype([("b", np.int32), ("p0", np.int32), ("p1", np.int32), ("doSearch", np.int32, (2,)), ("mvSlot", np.int32, (2,))])
+LA_TRIPLE = np.dtype([("b", np.int32), ("p0", np.int32), ("p1", np.int32), ("doSearch", np.int32, (2,)), ("mvSlot", np.int32, (2,)),
+                      ("weightIdx0", np.int32), ("weightPlanes0", np.int32)])
+LA_WEIGHT_JOB = np.dtype([("fencPlane0", np.uint64), ("intraCost", np.uint64), ("refBuffer", np.uint64, (4,)), ("weighted", np.uint64, (4,)),
+                          ("fencSum", np.uint64), ("fencSsd", np.uint64), ("refSum", np.uint64), ("refSsd", np.uint64)])      # x265b200_la_weight_job
+LA_WEIGHT = np.dtype([("isWeighted", np.int32), ("inputWeight", np.int32), ("log2WeightDenom", np.int32), ("inputOffset", np.int32),
+                      ("origscore", np.uint32), ("score", np.uint32)])                                                        # x265b200_la_weight
 
 
 def _ctx_lowres_init_dev(self, depth, dSrc, srcStride, planePtrs, dstStride, width, height, marginX, marginY):
@@ -364,13 +369,21 @@ def _ctx_la_intra_dev(self, depth, dPlane0, stride, wcu, hcu, dInvQ, intraPenalt
 
 
 def _ctx_la_estimate_dev(self, depth, dPlanes, stride, wcu, hcu, triples, dMvPool, dMvCostPool, dIntraCostPtrs, dInvQPtrs,
-                         dLowresCosts, dRowSatds, dSums, lam, lookaheadSlices=0):
+                         dLowresCosts, dRowSatds, dSums, lam, lookaheadSlices=0, dWeights=None):
     triples = np.ascontiguousarray(triples, dtype=LA_TRIPLE)
     self._chk(self.L.x265b200_la_estimate_dev(self.h, depth, _vp(dPlanes), _i64(stride), int(wcu), int(hcu), _vp(triples), len(triples),
                                               _vp(dMvPool), _vp(dMvCostPool), _vp(dIntraCostPtrs), _vp(dInvQPtrs), _vp(dLowresCosts),
-                                              _vp(dRowSatds), _vp(dSums), ctypes.c_double(lam), int(lookaheadSlices)))
+                                              _vp(dRowSatds), _vp(dSums), ctypes.c_double(lam), int(lookaheadSlices), _vp(dWeights)))
 
 
+def _ctx_la_weights_analyse_dev(self, depth, jobs, stride, paddedLines, padOffset, width, lines, dOut):
+    """jobs: numpy array of LA_WEIGHT_JOB (host); dOut: device array of LA_WEIGHT records"""
+    j = np.ascontiguousarray(jobs, dtype=LA_WEIGHT_JOB)
+    self._chk(self.L.x265b200_la_weights_analyse_dev(self.h, int(depth), _vp(j), len(j), _i64(stride), int(paddedLines), _i64(padOffset),
+                                                     int(width), int(lines), _vp(dOut)))
+
+
+Ctx.la_weights_analyse_dev = _ctx_la_weights_analyse_dev
 Ctx.lowres_init_dev = _ctx_lowres_init_dev
 Ctx.la_intra_dev = _ctx_la_intra_dev
 Ctx.la_estimate_dev = _ctx_la_estimate_dev
@@ -565,11 +578,11 @@ class LA_HME(ctypes.Structure):
 
 
 def _ctx_la_estimate_hme_dev(self, depth, dPlanes, stride, wcu, hcu, hme, triples, dMvPool, dMvCostPool, dIntraCostPtrs, dInvQPtrs,
-                             dLowresCosts, dRowSatds, dSums, lam, lookaheadSlices=0):
+                             dLowresCosts, dRowSatds, dSums, lam, lookaheadSlices=0, dWeights=None):
     triples = np.ascontiguousarray(triples, dtype=LA_TRIPLE)
     self._chk(self.L.x265b200_la_estimate_hme_dev(self.h, depth, _vp(dPlanes), _i64(stride), int(wcu), int(hcu), ctypes.byref(hme), _vp(triples),
                                                   len(triples), _vp(dMvPool), _vp(dMvCostPool), _vp(dIntraCostPtrs), _vp(dInvQPtrs),
-                                                  _vp(dLowresCosts), _vp(dRowSatds), _vp(dSums), ctypes.c_double(lam), int(lookaheadSlices)))
+                                                  _vp(dLowresCosts), _vp(dRowSatds), _vp(dSums), ctypes.c_double(lam), int(lookaheadSlices), _vp(dWeights)))
 
 
 Ctx.la_estimate_hme_dev = _ctx_la_estimate_hme_dev

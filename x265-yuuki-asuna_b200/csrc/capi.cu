@@ -168,7 +168,9 @@ int la_intra_dev(Ctx*, int depth, const void* plane0, int64_t stride, int widthI
 int la_estimate_dev(Ctx*, int depth, const void* const* planes, int64_t stride, int widthInCU, int heightInCU,
                     const x265b200_la_triple* triplesHost, int numTriples, int32_t* mvPool, int32_t* mvCostPool,
                     const int32_t* const* intraCost, const int32_t* const* invQscale, uint16_t* lowresCosts, int32_t* rowSatds, int32_t* sums,
-                    double lambda, int maxSlices, int lookaheadSlices, const x265b200_la_hme* hme);
+                    double lambda, int maxSlices, int lookaheadSlices, const x265b200_la_hme* hme, const x265b200_la_weight* weights);
+int la_weights_analyse_dev(Ctx*, int depth, const x265b200_la_weight_job* jobsHost, int numJobs, int64_t stride, int paddedLines, int64_t padOffset,
+                           int width, int lines, x265b200_la_weight* out);
 int sub_ps_plane_dev(Ctx*, int depth, const void* a, int64_t strideA, const void* b, int64_t strideB, int16_t* dst, int64_t dstStride, int w, int h);
 int add_ps_plane_dev(Ctx*, int depth, void* dst, int64_t dstStride, const void* pred, int64_t predStride, const int16_t* resi, int64_t resiStride, int w, int h);
 
@@ -708,21 +710,27 @@ int x265b200_la_intra_dev(x265b200_ctx* ctx, int depth, const void* plane0, int6
 int x265b200_la_estimate_dev(x265b200_ctx* ctx, int depth, const void* const* planes, int64_t stride, int widthInCU, int heightInCU,
                              const x265b200_la_triple* triplesHost, int numTriples, int32_t* mvPool, int32_t* mvCostPool,
                              const int32_t* const* intraCost, const int32_t* const* invQscale, uint16_t* lowresCosts,
-                             int32_t* rowSatds, int32_t* sums, double lambda, int lookaheadSlices)
+                             int32_t* rowSatds, int32_t* sums, double lambda, int lookaheadSlices, const x265b200_la_weight* weights)
 {
     REQUIRE_CTX(ctx);
     return la_estimate_dev(CTX(ctx), depth, planes, stride, widthInCU, heightInCU, triplesHost, numTriples, mvPool, mvCostPool,
-                           intraCost, invQscale, lowresCosts, rowSatds, sums, lambda, 1, lookaheadSlices, nullptr);
+                           intraCost, invQscale, lowresCosts, rowSatds, sums, lambda, 1, lookaheadSlices, nullptr, weights);
+}
+int x265b200_la_weights_analyse_dev(x265b200_ctx* ctx, int depth, const x265b200_la_weight_job* jobsHost, int numJobs,
+                                    int64_t stride, int paddedLines, int64_t padOffset, int width, int lines, x265b200_la_weight* out)
+{
+    REQUIRE_CTX(ctx);
+    return la_weights_analyse_dev(CTX(ctx), depth, jobsHost, numJobs, stride, paddedLines, padOffset, width, lines, out);
 }
 int x265b200_la_estimate_hme_dev(x265b200_ctx* ctx, int depth, const void* const* planes, int64_t stride, int widthInCU, int heightInCU,
                                  const x265b200_la_hme* hme, const x265b200_la_triple* triplesHost, int numTriples, int32_t* mvPool, int32_t* mvCostPool,
                                  const int32_t* const* intraCost, const int32_t* const* invQscale, uint16_t* lowresCosts,
-                                 int32_t* rowSatds, int32_t* sums, double lambda, int lookaheadSlices)
+                                 int32_t* rowSatds, int32_t* sums, double lambda, int lookaheadSlices, const x265b200_la_weight* weights)
 {
     REQUIRE_CTX(ctx);
     if (!hme) { set_error("la_estimate_hme: hme descriptor is NULL"); return -1; }
     return la_estimate_dev(CTX(ctx), depth, planes, stride, widthInCU, heightInCU, triplesHost, numTriples, mvPool, mvCostPool,
-                           intraCost, invQscale, lowresCosts, rowSatds, sums, lambda, 1, lookaheadSlices, hme);
+                           intraCost, invQscale, lowresCosts, rowSatds, sums, lambda, 1, lookaheadSlices, hme, weights);
 }
 
 } // extern "C"

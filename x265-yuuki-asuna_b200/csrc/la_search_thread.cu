@@ -55,7 +55,8 @@ la_search_thread_kernel(LASearchArgs p)
         int32_t* mvs = p.mvPool + (int64_t)ch.mvSlot * ncu * 2;
         int32_t* mvcosts = p.mvCostPool + (int64_t)ch.mvSlot * ncu;
         const pixel* const* fencPlanes = (const pixel* const*)p.planes + ch.b * 4;
-        const pixel* const* refPlanes = (const pixel* const*)p.planes + ch.ref * 4;
+        const bool useW = p.weights && ch.wIdx >= 0 && p.weights[ch.wIdx].isWeighted;                   // wfref0, slicetype.cpp:3222
+        const pixel* const* refPlanes = (const pixel* const*)p.planes + (useW ? ch.wref : ch.ref) * 4;
         // the row above this lane belongs to another warp when this is the band's top lane and the slice goes on above it
         const bool publishes = rowValid && cuY > firstY && (lane == 31);
 

@@ -2,10 +2,11 @@
 // (lookahead_kernels.cu: one warp per CU; la_search_thread.cu: one lane per CU)
 #pragma once
 #include "common.cuh"
+#include "x265b200.h"
 
 namespace x265b200 {
 
-struct LAChain { int32_t b, ref, bBidir, mvSlot; };   // frame indices; MV/cost pool slot
+struct LAChain { int32_t b, ref, bBidir, mvSlot; int32_t wref, wIdx; };   // frame indices; MV/cost pool slot; weighted planes of list 0 (wIdx < 0: none)
 
 struct LASearchArgs
 {
@@ -29,6 +30,8 @@ struct LASearchArgs
     // (the last slice runs to the bottom row); the bottom row of every slice is searched with lastRow = true, i.e. without the
     // MV candidates of the row below, so the slices are independent wavefronts.  numSlices = 1: the whole field is one slice.
     int rowsPerSlice, numSlices;
+    // weightp (slicetype.cpp:3222): a list-0 chain searches planes[wref] when weights[wIdx].isWeighted (written by la_weights_analyse)
+    const x265b200_la_weight* weights;
 };
 
 int la_search_thread_launch(Ctx* ctx, int depth, const LASearchArgs& a);

@@ -412,7 +412,8 @@ la_finish_kernel(LAFinishArgs p)
 int la_estimate_dev(Ctx* ctx, int depth, const void* const* planes, int64_t stride, int widthInCU, int heightInCU,
                     const x265b200_la_triple* triplesHost, int numTriples,
                     int32_t* mvPool, int32_t* mvCostPool, const int32_t* const* intraCost, const int32_t* const* invQscale,
-                    uint16_t* lowresCosts, int32_t* rowSatds, int32_t* sums, double lambda, int maxSlices, int lookaheadSlices, const x265b200_la_hme* hme)
+                    uint16_t* lowresCosts, int32_t* rowSatds, int32_t* sums, double lambda, int maxSlices, int lookaheadSlices, const x265b200_la_hme* hme,
+                    const x265b200_la_weight* weights)
 {
     if (numTriples <= 0) return 0;
     if (hme)
@@ -443,8 +444,13 @@ int la_estimate_dev(Ctx* ctx, int depth, const void* const* planes, int64_t stri
     {
         const x265b200_la_triple& tr = triplesHost[t];
         int bBidir = tr.b < tr.p1;
-        if (tr.doSearch[0]) { LAChain c; c.b = tr.b; c.ref = tr.p0; c.bBidir = bBidir; c.mvSlot = tr.mvSlot[0]; chains.push_back(c); }
-        if (bBidir && tr.doSearch[1]) { LAChain c; c.b = tr.b; c.ref = tr.p1; c.bBidir = bBidir; c.mvSlot = tr.mvSlot[1]; chains.push_back(c); }
+        if (tr.doSearch[0])
+        {
+            LAChain c; c.b = tr.b; c.ref = tr.p0; c.bBidir = bBidir; c.mvSlot = tr.mvSlot[0];
+            c.wIdx = weights && tr.weightIdx0 > 0 ? tr.weightIdx0 - 1 : -1; c.wref = tr.weightPlanes0;
+            chains.push_back(c);
+        }
+        if (bBidir && tr.doSearch[1]) { LAChain c; c.b = tr.b; c.ref = tr.p1; c.bBidir = bBidir; c.mvSlot = tr.mvSlot[1]; c.wIdx = -1; c.wref = 0; chains.push_back(c); }
     }
     const int numChains = (int)chains.size();
     void* scratch = nullptr;
@@ -461,7 +467,7 @@ int la_estimate_dev(Ctx* ctx, int depth, const void* const* planes, int64_t stri
         a.widthInCU = widthInCU; a.heightInCU = heightInCU; a.depth = depth; a.merange = 16; a.maxSlices = maxSlices;   // s_merange, slicetype.h:259
         a.mvPool = mvPool; a.mvCostPool = mvCostPool; a.progress = dProg; a.workCounter = dProg + (size_t)numChains * heightInCU; a.cost = ctx->dMvCost;
         a.hme = 0; a.searchMethod = ME_HEX; a.hmeMvPool = nullptr; a.hmeMvCostPool = nullptr; a.hmeNcu = 0;
-        a.rowsPerSlice = rowsPerSlice; a.numSlices = numSlices;
+        a.rowsPerSlice = rowsPerSlice; a.numSlices = numSlices; a.weights = weights;
         if (hme)
         {
             // level 0 (slicetype.cpp:3177-3188): the same chains over the quarter-resolution planes, hmeSearchMethod[0] / hmeRange[0];
@@ -470,7 +476,7 @@ int la_estimate_dev(Ctx* ctx, int depth, const void* const* planes, int64_t stri
             LASearchArgs h = a;
             h.planes = hme->lowerPlanes; h.stride = hme->lowerStride; h.widthInCU = hme->width4; h.heightInCU = hme->height4;
             h.merange = hme->range[0]; h.searchMethod = hme->searchMethod[0]; h.hme = 1;
-            h.mvPool = hme->lowerMvPool; h.mvCostPool = hme->lowerMvCostPool;
+            h.mvPool = hme->lowerMvPool; h.mvCostPool = hme->lowerMvCostPool; h.weights = nullptr;        // wfref0 only without hme (:3222)
             h.progress = dProg + (size_t)numChains * heightInCU + 64; h.workCounter = h.progress + (size_t)numChains * hme->height4;
             if (numSlices > 1)
             {
@@ -498,6 +504,182 @@ int la_estimate_dev(Ctx* ctx, int depth, const void* const* planes, int64_t stri
     else           la_finish_kernel<uint8_t><<<grid, 64, 0, ctx->stream>>>(f);
     ctx->launches++;
     return check(cudaGetLastError(), "la_finish launch");
+}
+
+// ---------------------------------------------------------------------------------------------
+// weightp in the lookahead: LookaheadTLD::weightsAnalyse (slicetype.cpp:860-961) for a batch of (fenc, ref) pairs.
+// Host: the float scale / offset guess (:886-923), evaluated with the reference's own operation order.  Device: the two
+// weightCostLuma passes (:805-841) in one kernel, then the accept test (:935) folded into the kernel that weights the 4 planes.
+// ---------------------------------------------------------------------------------------------
+struct LAWeightDev
+{
+    const void* fenc; const int32_t* intraCost; const void* refBuf[4]; void* wbuf[4];
+    int32_t measure;                          // 0: early termination (:895-897), nothing is measured or weighted
+    int32_t identity;                         // the candidate reduces to weight 1, offset 0 (:935): measured, never applied
+    int32_t curScale, curDenom, curOffset;    // the candidate the second weightCostLuma pass measures (:923)
+    int32_t finScale, finDenom;               // the same weight over the smaller denominator (:926-933)
+};
+
+template<typename pixel>
+__global__ void __launch_bounds__(128)
+la_weight_cost_kernel(const LAWeightDev* jobs, x265b200_la_weight* out, int64_t stride, int64_t padOffset, int widthInCU, int heightInCU, int depth)
+{
+    const LAWeightDev j = jobs[blockIdx.y];
+    if (!j.measure) return;
+    const int mb = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned c0 = 0, c1 = 0;
+    if (mb < widthInCU * heightInCU)
+    {
+        const int cuX = mb % widthInCU, cuY = mb / widthInCU;
+        const int64_t pixoff = (int64_t)8 * cuY * stride + 8 * cuX;
+        const pixel* f = (const pixel*)j.fenc + pixoff;
+        const pixel* r = (const pixel*)j.refBuf[0] + padOffset + pixoff;
+        const int corr = 14 - depth, maxVal = (1 << depth) - 1;
+        const int offset = j.curOffset * (1 << (depth - 8)), shift = j.curDenom + corr;
+        const int round = (j.curDenom ? 1 << (j.curDenom - 1) : 0) << corr;
+        int fe[64], a[64];
+        constexpr int NW = 8 * (int)sizeof(pixel) / 4;
+        for (int y = 0; y < 8; y++)
+        {
+            uint32_t wf[NW], wr[NW];
+            ld_words<pixel, NW>(f + y * stride, wf);
+            ld_words<pixel, NW>(r + y * stride, wr);
+#pragma unroll
+            for (int x = 0; x < 8; x++)
+            {
+                constexpr int PER = 4 / (int)sizeof(pixel), BITS = 8 * (int)sizeof(pixel);
+                fe[y * 8 + x] = (wf[x / PER] >> ((x % PER) * BITS)) & ((1u << BITS) - 1);
+                a[y * 8 + x] = (wr[x / PER] >> ((x % PER) * BITS)) & ((1u << BITS) - 1);
+            }
+        }
+        const int ic = j.intraCost[mb];
+        c0 = (unsigned)min(satd8x8_arr(fe, a), ic);                                      // wtPresent = 0: the unweighted reference
+        for (int e = 0; e < 64; e++)
+        {
+            const int v = ((j.curScale * (int)(int16_t)(a[e] << corr) + round) >> shift) + offset;     // weight_pp_c, pixel.cpp:518-543
+            a[e] = v < 0 ? 0 : (v > maxVal ? maxVal : v);
+        }
+        c1 = (unsigned)min(satd8x8_arr(fe, a), ic);
+    }
+    for (int o = 16; o; o >>= 1) { c0 += __shfl_xor_sync(0xffffffffu, c0, o); c1 += __shfl_xor_sync(0xffffffffu, c1, o); }
+    if ((threadIdx.x & 31) == 0)
+    {
+        if (c0) atomicAdd(&out[blockIdx.y].origscore, c0);
+        if (c1) atomicAdd(&out[blockIdx.y].score, c1);
+    }
+}
+
+// the accept test of weightsAnalyse (:935) on the two sums; every thread evaluates it, one records it
+__device__ __forceinline__ bool la_weight_accept(const LAWeightDev& j, unsigned origscore, unsigned score)
+{
+    if (!j.measure || j.identity || !origscore || !(score < origscore)) return false;             // !minscore (:907), !found, identity
+    return !(__fdiv_rn(__uint2float_rn(score), __uint2float_rn(origscore)) > 0.998f);
+}
+
+template<typename pixel, int V>
+__global__ void __launch_bounds__(256)
+la_weight_planes_kernel(const LAWeightDev* jobs, x265b200_la_weight* out, int64_t count /* stride * paddedLines */, int depth)
+{
+    const int job = blockIdx.y >> 2, plane = blockIdx.y & 3;
+    const LAWeightDev j = jobs[job];
+    const bool on = la_weight_accept(j, out[job].origscore, out[job].score);
+    if (plane == 0 && blockIdx.x == 0 && threadIdx.x == 0)
+    {
+        out[job].isWeighted = on;
+        out[job].inputWeight = on ? j.finScale : 0; out[job].log2WeightDenom = on ? j.finDenom : 0; out[job].inputOffset = on ? j.curOffset : 0;
+    }
+    if (!on) return;
+    const int corr = 14 - depth, maxVal = (1 << depth) - 1;
+    const int offset = j.curOffset * (1 << (depth - 8)), shift = j.finDenom + corr, scale = j.finScale;
+    const int round = (j.finDenom ? 1 << (j.finDenom - 1) : 0) << corr;
+    const pixel* src = (const pixel*)j.refBuf[plane];
+    pixel* dst = (pixel*)j.wbuf[plane];
+    const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V;
+    if (i0 >= count) return;
+    pixel v[V];
+    if (V > 1 && i0 + V <= count) *(uint4*)v = *(const uint4*)(src + i0);
+    else for (int e = 0; e < V && i0 + e < count; e++) v[e] = src[i0 + e];
+#pragma unroll
+    for (int e = 0; e < V; e++)
+    {
+        const int w = ((scale * (int)(int16_t)((int)v[e] << corr) + round) >> shift) + offset;
+        v[e] = (pixel)(w < 0 ? 0 : (w > maxVal ? maxVal : w));
+    }
+    if (V > 1 && i0 + V <= count) *(uint4*)(dst + i0) = *(const uint4*)v;
+    else for (int e = 0; e < V && i0 + e < count; e++) dst[i0 + e] = v[e];
+}
+
+int la_weights_analyse_dev(Ctx* ctx, int depth, const x265b200_la_weight_job* jobsHost, int numJobs, int64_t stride, int paddedLines, int64_t padOffset,
+                           int width, int lines, x265b200_la_weight* out)
+{
+    if (numJobs <= 0) return 0;
+    if (!jobsHost || !out || width <= 0 || lines <= 0 || stride <= 0 || paddedLines <= 0) { set_error("la_weights_analyse: bad arguments"); return -1; }
+    std::vector<LAWeightDev> jobs(numJobs);
+    bool vec = true, any = false;
+    for (int n = 0; n < numJobs; n++)
+    {
+        const x265b200_la_weight_job& J = jobsHost[n];
+        LAWeightDev& d = jobs[n];
+        memset(&d, 0, sizeof(d));
+        d.fenc = J.fencPlane0; d.intraCost = J.intraCost;
+        for (int k = 0; k < 4; k++)
+        {
+            d.refBuf[k] = J.refBuffer[k]; d.wbuf[k] = J.weighted[k];
+            if (!J.refBuffer[k] || !J.weighted[k]) { set_error("la_weights_analyse: job %d plane %d is NULL", n, k); return -1; }
+            vec = vec && !(((uintptr_t)J.refBuffer[k] | (uintptr_t)J.weighted[k]) & 15);
+        }
+        if (!J.fencPlane0 || !J.intraCost) { set_error("la_weights_analyse: job %d source is NULL", n); return -1; }
+        // slicetype.cpp:886-897, float arithmetic in the reference's order (no contraction: -ffp-contract=off in the Makefile)
+        const float epsilon = 1.f / 128.f;
+        float guessScale, fencMean, refMean;
+        if (J.fencSsd && J.refSsd) guessScale = sqrtf((float)J.fencSsd / J.refSsd);
+        else guessScale = 1.0f;
+        fencMean = (float)J.fencSum / (lines * width) / (1 << (depth - 8));
+        refMean = (float)J.refSum / (lines * width) / (1 << (depth - 8));
+        if (fabsf(refMean - fencMean) < 0.5f && fabsf(1.f - guessScale) < epsilon) continue;           // early termination: measure = 0
+        d.measure = 1; any = true;
+        // WeightParam::setFromWeightAndOffset(w, 0, 7, true) (slice.h:304-316)
+        int minscale = (int)(guessScale * 128 + 0.5f), mindenom = 7;
+        while (mindenom > 0 && minscale > 127) { mindenom--; minscale >>= 1; }
+        minscale = minscale < 127 ? minscale : 127;
+        int curScale = minscale;
+        int curOffset = (int)(fencMean - refMean * curScale / (1 << mindenom) + 0.5f);
+        if (curOffset < -128 || curOffset > 127)
+        {
+            curOffset = curOffset < -128 ? -128 : 127;
+            curScale = (int)((1 << mindenom) * (fencMean - curOffset) / refMean + 0.5f);
+            curScale = curScale < 0 ? 0 : (curScale > 127 ? 127 : curScale);
+        }
+        d.curScale = curScale; d.curDenom = mindenom; d.curOffset = curOffset;
+        // the candidate only survives when it beat the unweighted cost (found), so the denominator reduction (:926-933) applies to it
+        int fs = curScale, fd = mindenom;
+        if (fd > 0 && !(fs & 1))
+        {
+            int idx = 0;
+            if (fs) while (!((fs >> idx) & 1)) idx++; else idx = 32;
+            int sh = idx < fd ? idx : fd;
+            fd -= sh; fs >>= sh;
+        }
+        d.finScale = fs; d.finDenom = fd;
+        d.identity = (fs == 1 << fd && curOffset == 0);
+    }
+    void* dJobsV = nullptr;
+    if (scratch_dev(ctx, 5, sizeof(LAWeightDev) * numJobs, &dJobsV)) return -1;
+    if (stage_small(ctx, dJobsV, jobs.data(), sizeof(LAWeightDev) * numJobs)) return -1;
+    const LAWeightDev* dJobs = (const LAWeightDev*)dJobsV;
+    X265B200_CHECK(cudaMemsetAsync(out, 0, sizeof(x265b200_la_weight) * numJobs, ctx->stream));
+    if (!any) return 0;                                                                        // every pair terminated early
+    const int widthInCU = (width + 7) >> 3, heightInCU = (lines + 7) >> 3;
+    dim3 gc((widthInCU * heightInCU + 127) / 128, numJobs);
+    if (depth > 8) la_weight_cost_kernel<uint16_t><<<gc, 128, 0, ctx->stream>>>(dJobs, out, stride, padOffset, widthInCU, heightInCU, depth);
+    else           la_weight_cost_kernel<uint8_t><<<gc, 128, 0, ctx->stream>>>(dJobs, out, stride, padOffset, widthInCU, heightInCU, depth);
+    const int64_t count = stride * paddedLines;
+    const int V = vec ? 16 / (depth > 8 ? 2 : 1) : 1;
+    dim3 gw((unsigned)((count + 256 * V - 1) / (256 * V)), numJobs * 4);
+    if (depth > 8) { if (vec) la_weight_planes_kernel<uint16_t, 8><<<gw, 256, 0, ctx->stream>>>(dJobs, out, count, depth); else la_weight_planes_kernel<uint16_t, 1><<<gw, 256, 0, ctx->stream>>>(dJobs, out, count, depth); }
+    else           { if (vec) la_weight_planes_kernel<uint8_t, 16><<<gw, 256, 0, ctx->stream>>>(dJobs, out, count, depth); else la_weight_planes_kernel<uint8_t, 1><<<gw, 256, 0, ctx->stream>>>(dJobs, out, count, depth); }
+    ctx->launches += 2;
+    return check(cudaGetLastError(), "la_weights_analyse launch");
 }
 
 } // namespace x265b200
