@@ -49,6 +49,7 @@ CTU_COLS, CTU_ROWS = W // CTU, (H + CTU - 1) // CTU
 NREF, MERANGE, SUBME, QP = 3, 57, 2, 30
 LEVELS = [64, 32, 16, 8]
 METRIC = "2160p preset-medium fps at 1/2/4/8 B200; ME SAD achieved HBM GB/s vs peak"
+LA_SMS = 0                                    # SMs set aside for the lookahead stream (0: none), see --la-sms
 LA_BATCH, LA_BFRAMES, LA_SLICES = 8, 4, 8      # frames per estimateFrameCost launch; bframes; --lookahead-slices (param.cpp:173)
 
 ME_DIA, ME_HEX, ME_UMH, ME_STAR = 0, 1, 2, 3
@@ -572,7 +573,7 @@ class MixWorkload(Workload):
         torch, pkg, dev = self.torch, self.pkg, self.dev
         # same priority as the main stream: measured 4.25 ms/step; giving the lookahead priority makes its CTAs displace frame-search
         # CTAs on every SM and costs more than it hides (5.2 ms/step), see DESIGN.md 7
-        self.la_stream = torch.cuda.Stream(device=dev)
+        self.la_stream = self.args.la_stream if self.args.la_stream is not None else torch.cuda.Stream(device=dev)
         self.la_ctx = pkg.Ctx(dev.index, stream=self.la_stream.cuda_stream)
         Wc, Hc = W, CTU_ROWS * CTU
         mx, my = PAD, 80
@@ -712,6 +713,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--config", type=int, default=3, choices=sorted(CONFIGS))
     ap.add_argument("--shard", default="frames", choices=["frames", "ctu-rows"])
+    ap.add_argument("--la-sms", type=int, default=LA_SMS, help="config 3: SMs set aside for the lookahead stream (x265b200_sm_partition); 0 = no partition")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
@@ -723,7 +725,15 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    stream = torch.cuda.Stream(device=local)               # a real (non-NULL) stream shared by torch and the C ABI
+    args.la_stream = None
+    if args.config == 3 and args.la_sms > 0:
+        # the lookahead keeps a few latency-bound warps per SM alive for milliseconds while the frame search fills every register
+        # file it runs on: give each its own SMs (green contexts) so that they run side by side instead of in turn
+        s_la, s_main, args.sm_split = pkg.sm_partition(local, args.la_sms)
+        stream = torch.cuda.ExternalStream(s_main, device=local)
+        args.la_stream = torch.cuda.ExternalStream(s_la, device=local)
+    else:
+        stream = torch.cuda.Stream(device=local)           # a real (non-NULL) stream shared by torch and the C ABI
     torch.cuda.set_stream(stream)
     ctx = pkg.Ctx(local, stream=stream.cuda_stream)       # fails loudly without the CUDA library
     assert stream.cuda_stream != 0 and ctx.stream == stream.cuda_stream
@@ -825,14 +835,21 @@ def main():
     for gi in range(groups):
         grp[gi]["cur"] = gi * (wl.nref + 1)
         grp[gi]["ref"][:wl.nref] = [gi * (wl.nref + 1) + 1 + r for r in range(wl.nref)]
+    # the roofline legs time a kernel ALONE on the whole device: with an SM partition they get a plain stream / context of their own
+    rf_stream, rf_ctx, step_ctx = stream, ctx, ctx
+    if args.la_stream is not None:
+        rf_stream = torch.cuda.Stream(device=local)
+        rf_ctx = pkg.Ctx(local, stream=rf_stream.cuda_stream)
+        wl.ctx = rf_ctx
+        torch.cuda.set_stream(rf_stream)
     wl.sad_stream(grp); torch.cuda.synchronize()
     sad_graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(sad_graph, stream=stream):
+    with torch.cuda.graph(sad_graph, stream=rf_stream):
         wl.sad_stream(grp)
     sad_loop_ms = []
     for rep in range(max(K, 5) + 1):
         r0 = torch.cuda.Event(enable_timing=True); r1 = torch.cuda.Event(enable_timing=True)
-        r0.record(stream); sad_graph.replay(); r1.record(stream)
+        r0.record(rf_stream); sad_graph.replay(); r1.record(rf_stream)
         torch.cuda.synchronize()
         if rep:                                  # first repetition is the warm-up
             sad_loop_ms.append(r0.elapsed_time(r1))
@@ -846,19 +863,21 @@ def main():
 
         def dct_loop():
             for kk in range(8):
-                ctx.dct_plane_dev(3, 8, resid_ring[kk].data_ptr(), W, W // 32, (CTU_ROWS * CTU) // 32, coef_ring[kk].data_ptr())
+                rf_ctx.dct_plane_dev(3, 8, resid_ring[kk].data_ptr(), W, W // 32, (CTU_ROWS * CTU) // 32, coef_ring[kk].data_ptr())
         dct_loop(); torch.cuda.synchronize()
         dct_graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(dct_graph, stream=stream):
+        with torch.cuda.graph(dct_graph, stream=rf_stream):
             dct_loop()
         dct_ms = []
         for rep in range(4):
             r0 = torch.cuda.Event(enable_timing=True); r1 = torch.cuda.Event(enable_timing=True)
-            r0.record(stream); dct_graph.replay(); r1.record(stream); torch.cuda.synchronize()
+            r0.record(rf_stream); dct_graph.replay(); r1.record(rf_stream); torch.cuda.synchronize()
             if rep:
                 dct_ms.append(r0.elapsed_time(r1) / 8)
         del dct_graph, resid_ring, coef_ring
         dct_line = dct_ms
+    wl.ctx = step_ctx
+    torch.cuda.set_stream(stream)
 
     # ---- end-to-end timing (host buffers in, results out, through the host-buffer C-ABI entry) ---------------------------
     def e2e_run(first, count):
@@ -900,6 +919,7 @@ def main():
                 "dtype": "u8" if cfg["depth"] == 8 else "u16", "data": "synthetic",
                 "config": {"workload": wl.workload, "baseline_config": args.config, "units_per_step": wl.units,
                            "l2": "frames come from a ring of %d frames (%.0f MB) larger than L2; no flush" % (wl.NF, wl.NF * wl.plane_bytes / 1e6),
+                           "sm_partition": ({"lookahead_sms": args.sm_split[0], "main_sms": args.sm_split[1], "how": "x265b200_sm_partition (CUDA green contexts): the lookahead stream and the main stream own disjoint SMs"} if args.la_stream is not None else None),
                            "parallelism": ("frame-parallel x%d (all_gather of the new plane + gather of results on a comm stream)" % world) if args.shard == "frames"
                                           else ("CTU-row bands of one frame x%d (all_gather of the bands' rows + gather of results)" % world)},
                 "clocks": sampler.summary(), "gpu_launches": int(launches),
@@ -926,7 +946,7 @@ def main():
                                           "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": me_bytes / me_t / 1e9 / pk["hbm_gbs"], "ms_per_step": me_t * 1e3,
                                           "note": "instruction-issue bound pattern search over smem-staged windows (DESIGN.md 5); HBM figure shown for scale only"}
         if world == 1:
-            line["cpu_baseline"] = cpu_baseline(args.config)
+            line["cpu_baseline"] = cpu_baseline(args.config) if not os.environ.get("BENCH_NO_CPU") else {"skipped": "BENCH_NO_CPU (diagnosis run)"}
         print(json.dumps(line))
     if hasattr(wl, "la_ctx"):
         wl.la_ctx.close()

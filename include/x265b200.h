@@ -37,6 +37,13 @@ int         x265b200_device_count(void);
 /* stream == NULL: the context creates its own non-blocking stream. */
 int         x265b200_create(int device, void* cudaStream, x265b200_ctx** out);
 void        x265b200_destroy(x265b200_ctx* ctx);
+/* SM partitioning (CUDA green contexts): splits the SMs of `device` into two disjoint groups and returns one stream per group --
+ * streamFirst runs on at least smsFirst SMs (rounded up to the hardware's granularity, 8 on sm_100), streamRest on all the others;
+ * smsGot[2] = the two group sizes.  Contexts created on these streams (x265b200_create) size their persistent grids for their
+ * group.  Used to run the latency-bound lookahead (a few warps per SM, x265b200_la_*) BESIDE the frame search, which otherwise
+ * fills every SM's register file and serialises with it.  The streams live until x265b200_sm_partition_release(). */
+int         x265b200_sm_partition(int device, int smsFirst, void** streamFirst, void** streamRest, int smsGot[2]);
+void        x265b200_sm_partition_release(void);
 int         x265b200_sync(x265b200_ctx* ctx);
 void*       x265b200_stream(x265b200_ctx* ctx);                 /* cudaStream_t the kernels run on */
 uint64_t    x265b200_launch_count(x265b200_ctx* ctx);           /* kernels launched so far        */

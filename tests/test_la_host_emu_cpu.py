@@ -1,7 +1,8 @@
 """CPU: the lookahead list search (csrc/la_search_thread.cu = estimateCUCost phase 1) with the DEVICE source of the search
 (csrc/me_device.cuh, lowres thread-only build) compiled for the host (tests/host_emu/) and compared with the per-CU MVs and MV
 costs the reference's own CostEstimateGroup / Lowres objects produce (oracle/_ref, unmodified slicetype.cpp) -- P and B
-frame-triples, both lists, 8- and 10-bit; the shipped build (packed-word SATD) and the scalar-SATD form."""
+frame-triples, both lists, 8- and 10-bit; the shipped build (two lanes per CU, packed-word SATD), the scalar-SATD form and the
+one-lane-per-CU form."""
 import ctypes
 import importlib
 import os
@@ -16,7 +17,7 @@ from test_lookahead_gpu import _arr, _bind, _frames
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pkg = importlib.import_module("x265-yuuki-asuna_b200")
 needs_ref = pytest.mark.skipif(not oracle.have_ref(8), reason="oracle/_ref not built (no /root/reference here)")
-VARIANTS = {"default": [], "scalar_satd": ["-DEMU_LA_PACKED_SATD_OFF=1"]}
+VARIANTS = {"default": [], "scalar_satd": ["-DEMU_LA_PACKED_SATD_OFF=1"], "one_lane_per_cu": ["-DEMU_LA_LANES=1"]}
 
 
 @pytest.fixture(scope="module", params=sorted(VARIANTS))

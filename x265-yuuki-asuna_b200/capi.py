@@ -99,6 +99,16 @@ class DevBuf:
             self.ptr = 0
 
 
+def sm_partition(device, sms_first):
+    """x265b200_sm_partition: (streamFirst, streamRest, (smsFirst, smsRest)) -- raw cudaStream_t values"""
+    L = load()
+    a, b = ctypes.c_void_p(), ctypes.c_void_p()
+    got = (ctypes.c_int * 2)()
+    if L.x265b200_sm_partition(int(device), int(sms_first), ctypes.byref(a), ctypes.byref(b), got) != 0:
+        raise X265B200Error(L.x265b200_last_error().decode())
+    return a.value, b.value, (got[0], got[1])
+
+
 class Ctx:
     """One backend context == one GPU + one stream (x265b200_create)."""
 

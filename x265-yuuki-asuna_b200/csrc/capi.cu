@@ -9,6 +9,8 @@
 #include <cstring>
 #include <mutex>
 #include <cmath>
+#include <vector>
+#include <cuda.h>          // types of the green-context driver API only: entry points are fetched at run time (no link against libcuda)
 
 namespace x265b200 {
 
@@ -184,6 +186,35 @@ struct x265b200_ctx { Ctx c; };
 #define REQUIRE_CTX(ctx) do { if (!(ctx)) { set_error("null x265b200 context (CUDA backend not initialised; there is no CPU fallback)"); return -1; } \
                               if (check(cudaSetDevice((ctx)->c.device), "cudaSetDevice")) return -1; } while (0)
 
+// ---- SM partitioning through green contexts (driver API >= 12.4, fetched with cudaGetDriverEntryPoint) ----------------------------
+namespace {
+template<typename F> bool drv_entry(const char* name, F& fn)
+{
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) { cudaGetLastError(); return false; }
+    fn = (F)p;
+    return true;
+}
+struct GreenPartition { CUgreenCtx ctx[2]; CUstream stream[2]; };
+std::mutex g_partMutex;
+std::vector<GreenPartition> g_partitions;
+
+// number of SMs the stream's kernels may run on: its green context's share, else the whole device
+int stream_sm_count(cudaStream_t stream, int deviceSms)
+{
+    CUresult (*getGreen)(CUstream, CUgreenCtx*) = nullptr;
+    CUresult (*getRes)(CUgreenCtx, CUdevResource*, CUdevResourceType) = nullptr;
+    if (!stream || !drv_entry("cuStreamGetGreenCtx", getGreen) || !drv_entry("cuGreenCtxGetDevResource", getRes)) return deviceSms;
+    CUgreenCtx g = nullptr;
+    if (getGreen((CUstream)stream, &g) != CUDA_SUCCESS || !g) return deviceSms;
+    CUdevResource r;
+    if (getRes(g, &r, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS || !r.sm.smCount) return deviceSms;
+    return (int)r.sm.smCount;
+}
+}
+
+
 extern "C" {
 
 int x265b200_version(void) { return 100; }
@@ -194,6 +225,64 @@ int x265b200_device_count(void)
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
     return n;
+}
+
+int x265b200_sm_partition(int device, int smsFirst, void** streamFirst, void** streamRest, int smsGot[2])
+{
+    if (!streamFirst || !streamRest || smsFirst <= 0) { set_error("x265b200_sm_partition: bad arguments"); return -1; }
+    int n = x265b200_device_count();
+    if (device < 0 || device >= n) { set_error("x265b200_sm_partition: device %d out of range [0,%d)", device, n); return -1; }
+    X265B200_CHECK(cudaSetDevice(device));
+    X265B200_CHECK(cudaFree(0));                                            // the primary context the green contexts derive from
+    CUresult (*devGet)(CUdevice*, int) = nullptr;
+    CUresult (*getRes)(CUdevice, CUdevResource*, CUdevResourceType) = nullptr;
+    CUresult (*split)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int, unsigned int) = nullptr;
+    CUresult (*genDesc)(CUdevResourceDesc*, CUdevResource*, unsigned int) = nullptr;
+    CUresult (*gcreate)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int) = nullptr;
+    CUresult (*gdestroy)(CUgreenCtx) = nullptr;
+    CUresult (*gstream)(CUstream*, CUgreenCtx, unsigned int, int) = nullptr;
+    if (!drv_entry("cuDeviceGet", devGet) || !drv_entry("cuDeviceGetDevResource", getRes) || !drv_entry("cuDevSmResourceSplitByCount", split) ||
+        !drv_entry("cuDevResourceGenerateDesc", genDesc) || !drv_entry("cuGreenCtxCreate", gcreate) || !drv_entry("cuGreenCtxDestroy", gdestroy) ||
+        !drv_entry("cuGreenCtxStreamCreate", gstream))
+    { set_error("x265b200_sm_partition: this driver has no green-context API"); return -1; }
+    CUdevice dev;
+    CUdevResource all, first, rest;
+    unsigned int groups = 1;
+    CUresult r;
+#define DRV(call, what) if ((r = (call)) != CUDA_SUCCESS) { set_error("x265b200_sm_partition: %s failed (CUresult %d)", what, (int)r); return -1; }
+    DRV(devGet(&dev, device), "cuDeviceGet");
+    DRV(getRes(dev, &all, CU_DEV_RESOURCE_TYPE_SM), "cuDeviceGetDevResource");
+    if ((unsigned)smsFirst >= all.sm.smCount) { set_error("x265b200_sm_partition: %d SMs asked of %u", smsFirst, all.sm.smCount); return -1; }
+    DRV(split(&first, &groups, &all, &rest, 0, (unsigned)smsFirst), "cuDevSmResourceSplitByCount");
+    if (groups != 1 || !rest.sm.smCount) { set_error("x265b200_sm_partition: the split left no second group"); return -1; }
+    GreenPartition P; memset(&P, 0, sizeof(P));
+    CUdevResource* parts[2] = { &first, &rest };
+    for (int k = 0; k < 2; k++)
+    {
+        CUdevResourceDesc desc;
+        DRV(genDesc(&desc, parts[k], 1), "cuDevResourceGenerateDesc");
+        DRV(gcreate(&P.ctx[k], desc, dev, CU_GREEN_CTX_DEFAULT_STREAM), "cuGreenCtxCreate");
+        DRV(gstream(&P.stream[k], P.ctx[k], CU_STREAM_NON_BLOCKING, 0), "cuGreenCtxStreamCreate");
+    }
+#undef DRV
+    { std::lock_guard<std::mutex> lk(g_partMutex); g_partitions.push_back(P); }
+    *streamFirst = (void*)P.stream[0]; *streamRest = (void*)P.stream[1];
+    if (smsGot) { smsGot[0] = (int)first.sm.smCount; smsGot[1] = (int)rest.sm.smCount; }
+    return 0;
+}
+
+void x265b200_sm_partition_release(void)
+{
+    CUresult (*gdestroy)(CUgreenCtx) = nullptr;
+    std::lock_guard<std::mutex> lk(g_partMutex);
+    if (!drv_entry("cuGreenCtxDestroy", gdestroy)) { g_partitions.clear(); return; }
+    for (auto& P : g_partitions)
+        for (int k = 0; k < 2; k++)
+        {
+            if (P.stream[k]) { cudaStreamSynchronize((cudaStream_t)P.stream[k]); cudaStreamDestroy((cudaStream_t)P.stream[k]); }
+            if (P.ctx[k]) gdestroy(P.ctx[k]);
+        }
+    g_partitions.clear();
 }
 
 int x265b200_create(int device, void* stream, x265b200_ctx** out)
@@ -215,7 +304,7 @@ int x265b200_create(int device, void* stream, x265b200_ctx** out)
     }
     cudaDeviceProp prop;
     if (check(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties")) { delete ctx; return -1; }
-    ctx->c.smCount = prop.multiProcessorCount;
+    ctx->c.smCount = stream_sm_count(ctx->c.stream, prop.multiProcessorCount);      // a stream of an SM partition: its share
     *out = ctx;
     return 0;
 }

@@ -21,6 +21,15 @@
 namespace x265b200 {
 
 constexpr int LAT_WARPS = 2;
+// Lanes per CU.  The search of a field is a wavefront whose length is fixed by the reference's candidate order (a slice of R rows
+// and W columns needs W + 2R dependent steps), so what a launch costs is the latency of ONE CU's search; with 2 lanes per CU each
+// lane owns four of the CU's eight rows (SAD and SATD are sums over 4x4 cells: the two halves meet in one shuffle per cost, and
+// both lanes take the same decisions), a warp covers 16 rows and twice as many warps are resident.
+#ifndef LA_LANES
+#define LA_LANES 2
+#endif
+constexpr int LAT_ROWS = 32 / LA_LANES;        // CU rows per warp
+constexpr int LAT_HR = 8 / LA_LANES;           // rows of the CU a lane owns
 
 // HME = false: the plain lookahead (search method and range are compile-time constants of the hot kernel);
 // HME = true: either level of --hme (runtime method / range, optional quarter-resolution candidate)
@@ -32,11 +41,12 @@ la_search_thread_kernel(LASearchArgs p)
     __shared__ __align__(16) pixel sFenc[LAT_WARPS][4][8 * 64];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int W = p.widthInCU, Hc = p.heightInCU, ncu = W * Hc;
-    // work items: (chain, 32-row band of a slice), bands counted bottom-up inside their slice; item ids are ordered band-major
+    const int row = lane / LA_LANES, half = lane % LA_LANES;          // CU row of the band this lane works on; which rows of the CU
+    // work items: (chain, LAT_ROWS-row band of a slice), bands counted bottom-up inside their slice; item ids are ordered band-major
     // inside a chain, so the band an item waits for (the one below it in the same slice) always has a smaller id
     const int nSl = p.numSlices, R = p.rowsPerSlice;
     const int maxRows = Hc - (nSl - 1) * R;                          // the last slice is the tallest (>= R rows)
-    const int bands = (max(maxRows, R) + 31) >> 5, perChain = bands * nSl;
+    const int bands = (max(maxRows, R) + LAT_ROWS - 1) / LAT_ROWS, perChain = bands * nSl;
 
     for (;;)
     {
@@ -48,7 +58,7 @@ la_search_thread_kernel(LASearchArgs p)
         const int band = rem / nSl, slice = rem - band * nSl;
         const LAChain ch = p.chains[chain];
         const int firstY = slice * R, lastY = slice == nSl - 1 ? Hc - 1 : (slice + 1) * R - 1;
-        const int cuY = lastY - band * 32 - lane;                   // this lane's row (bottom-up inside the slice)
+        const int cuY = lastY - band * LAT_ROWS - row;              // this lane's row (bottom-up inside the slice)
         const bool rowValid = cuY >= firstY;
         const bool lastRow = cuY == lastY;                          // estimateCUCost's lastRow: bottom row of the slice
         volatile int* below = p.progress + chain * Hc + cuY + 1;
@@ -58,25 +68,25 @@ la_search_thread_kernel(LASearchArgs p)
         const bool useW = p.weights && ch.wIdx >= 0 && p.weights[ch.wIdx].isWeighted;                   // wfref0, slicetype.cpp:3222
         const pixel* const* refPlanes = (const pixel* const*)p.planes + (useW ? ch.wref : ch.ref) * 4;
         // the row above this lane belongs to another warp when this is the band's top lane and the slice goes on above it
-        const bool publishes = rowValid && cuY > firstY && (lane == 31);
+        const bool publishes = rowValid && cuY > firstY && (lane == 32 - LA_LANES);
 
         MEState<pixel> s;
-        s.fenc = &sFenc[warp][lane >> 3][(lane & 7) * 8];
+        s.fenc = &sFenc[warp][row >> 3][(row & 7) * 8] + half * LAT_HR * 64;
         s.pred = nullptr; s.immed = nullptr;
-        s.stride = p.stride; s.isLowres = true; s.perThread = true; s.chromaSatd = false; s.groupSize = 1; s.groupMask = 1u << lane;
-        s.w = 8; s.h = 8; s.lane = 0; s.depth = p.depth; s.partSizeScale = 4; s.cost = p.cost + 2 * 32768;
+        s.stride = p.stride; s.isLowres = true; s.perThread = true; s.chromaSatd = false; s.groupSize = LA_LANES; s.groupMask = ((1u << LA_LANES) - 1u) << (lane - half);
+        s.w = 8; s.h = LAT_HR; s.lane = 0; s.depth = p.depth; s.partSizeScale = 4; s.cost = p.cost + 2 * 32768;
 
         int rightX = 0, rightY = 0;                                  // fencMV of the CU to the right (previous step of this lane)
-        const int steps = W + 2 * 31;
+        const int steps = W + 2 * (LAT_ROWS - 1);
 #pragma unroll 1
         for (int t = 0; t < steps; t++)
         {
-            const int cuX = W - 1 - (t - 2 * lane);
+            const int cuX = W - 1 - (t - 2 * row);
             if (rowValid && cuX >= 0 && cuX < W)
             {
                 const int cuXY = cuX + cuY * W;
                 const int64_t pelOffset = 8 * cuX + (int64_t)8 * cuY * p.stride;
-                if (lane == 0 && !lastRow)
+                if (row == 0 && !lastRow)
                 {
                     const int need = min(W, W - cuX + 1);
                     while (*below < need) __nanosleep(64);
@@ -85,9 +95,9 @@ la_search_thread_kernel(LASearchArgs p)
                 // setSourcePU: cache the 8x8 source block (motion.cpp:188-189)
                 {
                     constexpr int NW = 8 * (int)sizeof(pixel) / 4;
-                    const pixel* fp = fencPlanes[0] + pelOffset;
+                    const pixel* fp = fencPlanes[0] + pelOffset + (int64_t)half * LAT_HR * p.stride;     // this lane's rows of the CU
 #pragma unroll
-                    for (int y = 0; y < 8; y++)
+                    for (int y = 0; y < LAT_HR; y++)
                     {
                         uint32_t wv[NW];
                         ld_words<pixel, NW>(fp + (int64_t)y * p.stride, wv);
@@ -96,7 +106,7 @@ la_search_thread_kernel(LASearchArgs p)
                         for (int i = 0; i < NW; i++) d[i] = wv[i];
                     }
                 }
-                for (int k = 0; k < 4; k++) s.lowres[k] = refPlanes[k] + pelOffset;
+                for (int k = 0; k < 4; k++) s.lowres[k] = refPlanes[k] + pelOffset + (int64_t)half * LAT_HR * p.stride;
                 s.fref = s.lowres[0]; s.gfref = s.lowres[0]; s.gstride = p.stride;
 
                 // reverse-order MV prediction candidates (slicetype.cpp:3269-3280)
@@ -134,7 +144,7 @@ la_search_thread_kernel(LASearchArgs p)
                 int fencCost = motion_estimate<pixel>(s, mvmin, mvmax, mv2(mvpx, mvpy), 0, nullptr, p.merange, HME ? p.searchMethod : (int)ME_HEX, 1, p.maxSlices, 0, ox, oy);
                 if (skipCost < 64 && skipCost < fencCost && ch.bBidir) { fencCost = skipCost; ox = 0; oy = 0; }
                 rightX = ox; rightY = oy;
-                mvs[cuXY * 2] = ox; mvs[cuXY * 2 + 1] = oy; mvcosts[cuXY] = fencCost;
+                if (half == 0) { mvs[cuXY * 2] = ox; mvs[cuXY * 2 + 1] = oy; mvcosts[cuXY] = fencCost; }
                 if (publishes)
                 {
                     __threadfence();
@@ -149,7 +159,7 @@ la_search_thread_kernel(LASearchArgs p)
 int la_search_thread_launch(Ctx* ctx, int depth, const LASearchArgs& a)
 {
     const int maxRows = a.heightInCU - (a.numSlices - 1) * a.rowsPerSlice;
-    const int bands = ((maxRows > a.rowsPerSlice ? maxRows : a.rowsPerSlice) + 31) >> 5;
+    const int bands = ((maxRows > a.rowsPerSlice ? maxRows : a.rowsPerSlice) + LAT_ROWS - 1) / LAT_ROWS;
     const int64_t items = (int64_t)a.numChains * bands * a.numSlices;
     int64_t blocksWanted = (items + LAT_WARPS - 1) / LAT_WARPS;
     int64_t cap = (int64_t)ctx->smCount * 8;
