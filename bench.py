@@ -50,7 +50,7 @@ NREF, MERANGE, SUBME, QP = 3, 57, 2, 30
 LEVELS = [64, 32, 16, 8]
 METRIC = "2160p preset-medium fps at 1/2/4/8 B200; ME SAD achieved HBM GB/s vs peak"
 LA_SMS = 0                                    # SMs set aside for the lookahead stream (0: none), see --la-sms
-LA_BATCH, LA_BFRAMES, LA_SLICES = 8, 4, 8      # frames per estimateFrameCost launch; bframes; --lookahead-slices (param.cpp:173)
+LA_BATCH, LA_BFRAMES, LA_SLICES = int(os.environ.get("BENCH_LA_BATCH", "8")), 4, 8      # frames per estimateFrameCost launch; bframes; --lookahead-slices (param.cpp:173)
 
 ME_DIA, ME_HEX, ME_UMH, ME_STAR = 0, 1, 2, 3
 CONFIGS = {

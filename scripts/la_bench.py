@@ -48,7 +48,8 @@ allt = [(b - dd, b + dd, b) for dd in range(1, BF + 2) for b in range(NF) if b -
 import sys
 SLICES = int(sys.argv[1]) if len(sys.argv) > 1 else 0          # --lookahead-slices (0 = non-cooperative path)
 print("lookahead slices:", SLICES)
-for k in (1, 4, 8, 16, 24, 32, len(allt)):
+ONLY_FULL = len(sys.argv) > 2 and sys.argv[2] == "full"     # one size only (for an ncu capture)
+for k in ((len(allt),) if ONLY_FULL else (1, 4, 8, 16, 24, 32, len(allt))):
     wave = allt[:k]
     tr = np.zeros(len(wave), dtype=pkg.LA_TRIPLE)
     for t, (p0, p1, b) in enumerate(wave):

@@ -26,7 +26,7 @@ constexpr int LAT_WARPS = 2;
 // lane owns four of the CU's eight rows (SAD and SATD are sums over 4x4 cells: the two halves meet in one shuffle per cost, and
 // both lanes take the same decisions), a warp covers 16 rows and twice as many warps are resident.
 #ifndef LA_LANES
-#define LA_LANES 2
+#define LA_LANES 1
 #endif
 constexpr int LAT_ROWS = 32 / LA_LANES;        // CU rows per warp
 constexpr int LAT_HR = 8 / LA_LANES;           // rows of the CU a lane owns

@@ -228,6 +228,69 @@ __device__ __noinline__ int la_intra_cell_cost(const int* nb /* 33 neighbours, s
     return t >> 1;
 }
 
+// One angular mode on one 4x4 cell, with the mode as DATA: the lanes of a warp belong to eight CUs whose refinement candidates
+// (best +-2, +-1) differ, and the per-pixel form above then runs its direction / angle-sign / fraction branches once per distinct
+// mode.  Here the four lanes of a CU first write the mode's projected reference line (intrapred.cpp:146-172: ref[-8 .. 16], the
+// side neighbours projected through the inverse angle for negative angles) to shared memory, then every pixel is one two-tap
+// interpolation along that line -- the same instructions whatever the mode; only the pure horizontal / vertical modes (edge
+// filter on the first column, :176-189) take a short branch.
+__device__ __noinline__ int la_intra_ang_cell_cost(const int* smp, const int* flt, int* line /* [25], shared by the CU's lanes */, const int* tabs /* angle[17] | invAngle[8] */,
+                                                   int mode, int depth, int cell, int x0, int y0, const int* fenc /* [16] */)
+{
+    const bool hor = mode < 18;
+    const int angleOffset = hor ? 10 - mode : mode - 26;
+    const int angle = tabs[8 + angleOffset];
+    const int inv = angle < 0 ? tabs[17 - angleOffset - 1] : 0;
+    const int* src = min(abs(mode - 26), abs(mode - 10)) > 7 ? flt : smp;            // g_intraFilterFlags[mode] & 8
+    for (int L = cell; L < 25; L += 4)
+    {
+        const int idx = L - 8;
+        int i = (angle >= 0 || idx >= -1) ? idx + 1 : 16 + ((128 + (-1 - idx) * inv) >> 8);
+        i = max(0, min(i, 32));                                                      // entries a mode never reads
+        const int j = (!hor || i == 0) ? i : (i <= 16 ? 16 + i : i - 16);            // the flipped neighbour view of the horizontal modes
+        line[L] = src[j];
+    }
+    __syncwarp();
+    const int yyB = hor ? x0 : y0, xxB = hor ? y0 : x0;
+    int pv[4][4];
+#pragma unroll
+    for (int t = 0; t < 4; t++)
+    {
+        const int angleSum = (yyB + t + 1) * angle, off = angleSum >> 5, f = angleSum & 31;
+        const int* a = line + off + xxB + 8;
+#pragma unroll
+        for (int u = 0; u < 4; u++) pv[t][u] = ((32 - f) * a[u] + f * a[u + 1] + 16) >> 5;
+    }
+    if (!angle && xxB == 0)
+    {
+        // first column (row for mode 10) of the pure vertical / horizontal modes: nb(1) + ((nb(N2 + 1 + yy) - nb(0)) >> 1), clipped
+        const int n1 = hor ? smp[17] : smp[1], n0 = smp[0];
+#pragma unroll
+        for (int t = 0; t < 4; t++)
+        {
+            const int side = hor ? smp[1 + yyB + t] : smp[17 + yyB + t];
+            pv[t][0] = clip3i(0, (1 << depth) - 1, (int)(int16_t)(n1 + ((side - n0) >> 1)));
+        }
+    }
+    __syncwarp();                                                                    // the line is rewritten by the next mode
+    int d[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+    {
+#pragma unroll
+        for (int k = 0; k < 4; k++) d[i][k] = fenc[i * 4 + k] - (hor ? pv[k][i] : pv[i][k]);
+        me_hadamard4(d[i][0], d[i][1], d[i][2], d[i][3]);
+    }
+    int t = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+    {
+        me_hadamard4(d[0][k], d[1][k], d[2][k], d[3][k]);
+        t += abs(d[0][k]) + abs(d[1][k]) + abs(d[2][k]) + abs(d[3][k]);
+    }
+    return t >> 1;
+}
+
 // FOUR LANES PER CU: a lane owns one 4x4 cell of the 8x8 CU (pu[LUMA_8x8].satd is the sum of its four 4x4 Hadamard costs,
 // pixel.cpp:210-261), predicts only that cell for every mode tried and the four partial costs meet in two shuffles, so the
 // lanes of a CU hold identical costs and walk the mode decision together.  The raw and the 1:2:1-filtered neighbour arrays of
@@ -238,8 +301,15 @@ template<typename pixel>
 __global__ void __launch_bounds__(64)
 la_intra_kernel(LAIntraArgs p)
 {
-    __shared__ int sSmp[LAI_CUS][34], sFlt[LAI_CUS][34];
+    __shared__ int sSmp[LAI_CUS][34], sFlt[LAI_CUS][34], sLine[LAI_CUS][26], sTabs[25];
     const int slot = threadIdx.x >> 2, cell = threadIdx.x & 3;
+    if (threadIdx.x < 25)
+    {
+        const int8_t angleTable[17] = { -32, -26, -21, -17, -13, -9, -5, -2, 0, 2, 5, 9, 13, 17, 21, 26, 32 };
+        const int16_t invAngleTable[8] = { 4096, 1638, 910, 630, 482, 390, 315, 256 };
+        sTabs[threadIdx.x] = threadIdx.x < 17 ? (int)angleTable[threadIdx.x] : (int)invAngleTable[threadIdx.x - 17];
+    }
+    __syncthreads();
     const int ncu = p.widthInCU * p.heightInCU;
     const int cuXY = min(blockIdx.x * LAI_CUS + slot, ncu - 1);     // surplus lanes shadow the last CU (they take part in the shuffles)
     const bool live = blockIdx.x * LAI_CUS + slot < ncu;
@@ -284,8 +354,7 @@ la_intra_kernel(LAIntraArgs p)
         if (cost < icost) { icost = cost; ilowmode = 0; }
     }
     auto angCost = [&](int mode) -> int {
-        const int dist = min(abs(mode - 26), abs(mode - 10));
-        return cuSum(la_intra_cell_cost(dist > 7 ? flt : smp, mode, 1, 0, p.depth, x0, y0, fenc));            // g_intraFilterFlags[mode] & 8
+        return cuSum(la_intra_ang_cell_cost(smp, flt, sLine[slot], sTabs, mode, p.depth, cell, x0, y0, fenc));
     };
     int acost = ME_COST_MAX, alowmode = 4;
 #pragma unroll 1
