@@ -50,7 +50,7 @@ NREF, MERANGE, SUBME, QP = 3, 57, 2, 30
 LEVELS = [64, 32, 16, 8]
 METRIC = "2160p preset-medium fps at 1/2/4/8 B200; ME SAD achieved HBM GB/s vs peak"
 LA_SMS = 0                                    # SMs set aside for the lookahead stream (0: none), see --la-sms
-LA_BATCH, LA_BFRAMES, LA_SLICES = int(os.environ.get("BENCH_LA_BATCH", "8")), 4, 8      # frames per estimateFrameCost launch; bframes; --lookahead-slices (param.cpp:173)
+LA_BATCH, LA_BFRAMES, LA_SLICES = int(os.environ.get("BENCH_LA_BATCH", "16")), 4, 8      # frames per estimateFrameCost launch; bframes; --lookahead-slices (param.cpp:173)
 
 ME_DIA, ME_HEX, ME_UMH, ME_STAR = 0, 1, 2, 3
 CONFIGS = {
@@ -65,7 +65,8 @@ CONFIGS = {
 WORKLOAD3 = ("2160p-8bit-medium primitive mix (SURVEY.md 8d config 3): SAD at the predictor + HEX subme2 merange57 search of every 2Nx2N PU 64..8 x 3 refs; "
              "one 8-tap MC interpolation per PU and level (all 15 fractions); residual -> DCT/quant/dequant/IDCT on every 32/16/8/4 TU -> recon; "
              "intra neighbour smoothing + all 35 modes on every 8/16/32 block (fused); lookahead (lowres init + intra estimate + 10 estimateFrameCost list "
-             "searches per frame, --lookahead-slices 8) on a second stream, inside the timed region")
+             "searches per frame, --lookahead-slices 8; the searches of %d queued frames go in one launch, within medium's rc-lookahead of 20) on a second stream, "
+             "inside the timed region" % LA_BATCH)
 
 
 def peaks():
