@@ -58,6 +58,21 @@ extend_border_kernel(pixel* __restrict__ pic, int64_t stride, int width, int hei
     pic[(int64_t)yy * stride + xx] = pic[(int64_t)sy * stride + sx];
 }
 
+// the four hpel planes of a Lowres in one launch (blockIdx.y = plane)
+template<typename pixel>
+__global__ void __launch_bounds__(256)
+extend_border4_kernel(pixel* __restrict__ p0, pixel* __restrict__ p1, pixel* __restrict__ p2, pixel* __restrict__ p3, int64_t stride, int width, int height, int marginX, int marginY)
+{
+    pixel* pic = blockIdx.y == 0 ? p0 : (blockIdx.y == 1 ? p1 : (blockIdx.y == 2 ? p2 : p3));
+    const int fullW = width + 2 * marginX, fullH = height + 2 * marginY;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)fullW * fullH) return;
+    int yy = (int)(i / fullW) - marginY, xx = (int)(i % fullW) - marginX;
+    if (xx >= 0 && xx < width && yy >= 0 && yy < height) return;
+    int sx = min(max(xx, 0), width - 1), sy = min(max(yy, 0), height - 1);
+    pic[(int64_t)yy * stride + xx] = pic[(int64_t)sy * stride + sx];
+}
+
 int lowres_init_dev(Ctx* ctx, int depth, const void* src, int64_t srcStride, void* const planes[4], int64_t dstStride,
                     int width, int height, int marginX, int marginY)
 {
@@ -74,12 +89,10 @@ int lowres_init_dev(Ctx* ctx, int depth, const void* src, int64_t srcStride, voi
     {
         int64_t total = (int64_t)(width + 2 * marginX) * (height + 2 * marginY);
         unsigned blocks = (unsigned)((total + 255) / 256);
-        for (int k = 0; k < 4; k++)
-        {
-            if (depth > 8) extend_border_kernel<uint16_t><<<blocks, 256, 0, ctx->stream>>>((uint16_t*)planes[k], dstStride, width, height, marginX, marginY);
-            else           extend_border_kernel<uint8_t><<<blocks, 256, 0, ctx->stream>>>((uint8_t*)planes[k], dstStride, width, height, marginX, marginY);
-            ctx->launches++;
-        }
+        dim3 g4(blocks, 4);
+        if (depth > 8) extend_border4_kernel<uint16_t><<<g4, 256, 0, ctx->stream>>>((uint16_t*)planes[0], (uint16_t*)planes[1], (uint16_t*)planes[2], (uint16_t*)planes[3], dstStride, width, height, marginX, marginY);
+        else           extend_border4_kernel<uint8_t><<<g4, 256, 0, ctx->stream>>>((uint8_t*)planes[0], (uint8_t*)planes[1], (uint8_t*)planes[2], (uint8_t*)planes[3], dstStride, width, height, marginX, marginY);
+        ctx->launches++;
         if (check(cudaGetLastError(), "extend_border launch")) return -1;
     }
     return 0;
