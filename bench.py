@@ -517,11 +517,14 @@ class MEWorkload(Workload):
         if self.csp:
             kw.update(hostC=(self.hostC[0][f].data_ptr(), self.hostC[1][f].data_ptr()), devCBase=(self.poolC[0][f].data_ptr(), self.poolC[1][f].data_ptr()),
                       bytesC=self.planeC_bytes)
-        self.ctx.me_frame_ex_host(self.params, self.yptr(f) + self.shY, self.g["stride"], [self.yptr(r) + self.shY for r in refs], self.g["stride"],
-                                  self.host_y[f].data_ptr(), self.yptr(f, base=True), self.plane_bytes, self.me_out[k].data_ptr(), self.res_h[k].data_ptr(),
-                                  self.nout * 12, **kw)
+        # _begin queues H2D (copy stream) -> search -> D2H (copy stream); the rest of the step is queued behind the search and
+        # _end blocks until the {mv, cost} records are in host memory
+        self.ctx.me_frame_ex_host_begin(self.params, self.yptr(f) + self.shY, self.g["stride"], [self.yptr(r) + self.shY for r in refs], self.g["stride"],
+                                        self.host_y[f].data_ptr(), self.yptr(f, base=True), self.plane_bytes, self.me_out[k].data_ptr(), self.res_h[k].data_ptr(),
+                                        self.nout * 12, **kw)
         if self.row0 == 0:
             self.sad_stream(self.one_group(t))
+        self.ctx.me_frame_host_end()
 
     def h2d_bytes(self):
         return self.plane_bytes + (2 * self.planeC_bytes if self.csp else 0)
@@ -689,12 +692,13 @@ class MixWorkload(Workload):
     def e2e_step(self, t, k=0):
         torch = self.torch
         f, refs = self.frame(t), self.refs_of(t)
-        self.ctx.me_frame_host(8, self.host_y[f].data_ptr(), self.plane_bytes, self.yptr(f, base=True), STRIDE, [self.yptr(r) for r in refs], STRIDE, PAD, PAD, ROWS,
-                               CTU_COLS, CTU_ROWS, 15, None, ME_HEX, SUBME, MERANGE, self.lam, self.P(self.me_out[k]), self.res_h[k].data_ptr(), self.njobs * 12)
+        self.ctx.me_frame_host_begin(8, self.host_y[f].data_ptr(), self.plane_bytes, self.yptr(f, base=True), STRIDE, [self.yptr(r) for r in refs], STRIDE, PAD, PAD, ROWS,
+                                     CTU_COLS, CTU_ROWS, 15, None, ME_HEX, SUBME, MERANGE, self.lam, self.P(self.me_out[k]), self.res_h[k].data_ptr(), self.njobs * 12)
         ev = torch.cuda.Event(); ev.record(self.stream)
         self.lookahead_step(t, ev)
         self.sad_stream(self.one_group(t))
         self.stages_after_search(t)
+        self.ctx.me_frame_host_end()           # the step's result ({mv, cost} of every PU) is in pinned host memory from here on
 
     def h2d_bytes(self):
         return self.plane_bytes
@@ -925,7 +929,7 @@ def main():
                                           else ("CTU-row bands of one frame x%d (all_gather of the bands' rows + gather of results)" % world)},
                 "clocks": sampler.summary(), "gpu_launches": int(launches),
                 "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": wl.h2d_bytes(), "d2h_bytes_per_step": wl.d2h_bytes(),
-                        "how": "x265b200_me_frame%s_host: the frame is copied from pinned host memory, searched, and the {mv,cost} records are copied back, per step" % ("" if args.config == 3 else "_ex")},
+                        "how": "x265b200_me_frame%s_host_begin / _host_end: per step the frame is copied from pinned host memory (copy stream), searched, and the {mv,cost} records are copied back to pinned host memory; the step's other stages are queued in between" % ("" if args.config == 3 else "_ex")},
                 "roofline": {"kernel": "sad_stream_kernel (streaming ME SAD at the predictor: all 4 PU levels x %d references, %d frame groups in one launch, TMA ring)" % (wl.nref, groups),
                              "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": traffic,
                              "traffic_src": "profiles/r02_sad_stream.txt (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum of the same launch)" if traffic else None,

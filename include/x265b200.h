@@ -456,6 +456,17 @@ int x265b200_me_frame_host(x265b200_ctx* ctx, int depth, const void* hostCurBase
                            int marginX, int marginY, int rowsTotal, int ctuCols, int ctuRows, int puMask,
                            const int32_t* mvpCtu, int searchMethod, int subpelRefine, int merange, double lambda,
                            int32_t* devOut, int32_t* hostOut, size_t outBytes);
+/* The same in two halves, for callers that have more device work to queue behind the search (the stages that consume the MVs):
+ * _begin returns once the transfers and the search are queued -- the source picture travels on the context's own copy stream, so it
+ * overlaps whatever is still running on the compute stream, the search waits for it, and the results travel back on the copy stream
+ * while the compute stream goes on; x265b200_me_frame_host_end blocks until hostOut is complete.  One call may be pending per context;
+ * the destination plane must not be read by work queued before _begin (a picture buffer that left the reference list). */
+int x265b200_me_frame_host_begin(x265b200_ctx* ctx, int depth, const void* hostCurBase, size_t planeBytes, void* devCurBase, int64_t curStride,
+                                 const void* const* refOriginsHost, int numRefs, int64_t refStride,
+                                 int marginX, int marginY, int rowsTotal, int ctuCols, int ctuRows, int puMask,
+                                 const int32_t* mvpCtu, int searchMethod, int subpelRefine, int merange, double lambda,
+                                 int32_t* devOut, int32_t* hostOut, size_t outBytes);
+int x265b200_me_frame_host_end(x265b200_ctx* ctx);
 /* planes->curY / curCb / curCr are the device ORIGINS as in x265b200_me_frame_ex_dev; hostCur*Base / devCur*Base the padded
  * planes' first bytes (Cb / Cr may be NULL when params->csp == 0 or subpelRefine <= 2). */
 int x265b200_me_frame_ex_host(x265b200_ctx* ctx, const x265b200_me_frame_params* params, const x265b200_me_frame_planes* planes,
@@ -463,6 +474,11 @@ int x265b200_me_frame_ex_host(x265b200_ctx* ctx, const x265b200_me_frame_params*
                               const void* hostCurCbBase, void* devCurCbBase, const void* hostCurCrBase, void* devCurCrBase, size_t bytesC,
                               const int32_t* mvpCtu, const int32_t* mvpPu, const uint8_t* numCandPu, const int32_t* mvcPu,
                               int32_t* devOut, int32_t* hostOut, size_t outBytes);
+int x265b200_me_frame_ex_host_begin(x265b200_ctx* ctx, const x265b200_me_frame_params* params, const x265b200_me_frame_planes* planes,
+                              const void* hostCurYBase, void* devCurYBase, size_t bytesY,
+                              const void* hostCurCbBase, void* devCurCbBase, const void* hostCurCrBase, void* devCurCrBase, size_t bytesC,
+                              const int32_t* mvpCtu, const int32_t* mvpPu, const uint8_t* numCandPu, const int32_t* mvcPu,
+                              int32_t* devOut, int32_t* hostOut, size_t outBytes);      /* ended by x265b200_me_frame_host_end */
 /* The PUs of one CTU in the order x265b200_me_frame_ex_dev uses: {x, y, w, h} inside the CTU, CU sizes from ctuSize down to
  * minCuSize, CUs in raster order, per CU the part modes in PartSize order (2Nx2N, 2NxN, Nx2N, 2NxnU, 2NxnD, nLx2N, nRx2N;
  * common/cudata.h).  Writes at most cap entries; returns the number of PUs (host side, no GPU needed), -1 on bad arguments. */

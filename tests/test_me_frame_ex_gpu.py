@@ -182,6 +182,55 @@ def test_equals_the_2Nx2N_frame_entry(ctx):
     dMvp.free(); dOut.free(); F.free()
 
 
+def test_host_buffer_entries_equal_the_device_entry(ctx):
+    """x265b200_me_frame_ex_host and its _begin / _end halves (source picture from host memory over the copy stream, results to
+    host memory) return what x265b200_me_frame_ex_dev returns; work queued between _begin and _end does not disturb them; so does
+    x265b200_me_frame_host against x265b200_me_frame_dev."""
+    import ctypes
+    C, cols, rows, nref, merange = 64, 3, 2, 2, 24
+    F = Frames(ctx, cols * C, rows * C, 160, 160, 8, nref, 1, seed=7300)
+    r = run_frame(ctx, F, C, 8, True, False, pkg.ME_HEX, 3, merange, nref, np.random.default_rng(3))
+    want = r["out"]
+    n, nctu = len(r["layout"]), cols * rows
+    params = dict(depth=8, ctuSize=C, minCuSize=8, rect=1, amp=0, picWidth=F.W, picHeight=F.H, firstCtuRow=0, ctuCols=cols, ctuRows=rows, marginX=F.padX,
+                  marginY=F.padY, rowsTotal=F.R, searchMethod=int(pkg.ME_HEX), subpelRefine=3, merange=merange, csp=1, maxCand=0, maxSlices=1,
+                  chromaMarginX=F.cpadX, chromaMarginY=F.cpadY)
+    params["lambda"] = pkg.lambda_for_qp(30, 8)
+    dMvp = ctx.to_device(r["mvpCtu"])
+    o, oc = F.origin, F.originC
+    # fresh device planes for the source picture: the host entries must fill them
+    dY, dCb, dCr = ctx.to_device(np.zeros_like(F.y[0])), ctx.to_device(np.zeros_like(F.cb[0])), ctx.to_device(np.zeros_like(F.cr[0]))
+    kw = dict(curC=(dCb.ptr + oc, dCr.ptr + oc), curStrideC=F.Sc, refCb=[b.ptr + oc for b in F.dCb[1:]], refCr=[b.ptr + oc for b in F.dCr[1:]], refStrideC=F.Sc,
+              hostC=(F.cb[0].ctypes.data, F.cr[0].ctypes.data), devCBase=(dCb.ptr, dCr.ptr), bytesC=F.cb[0].nbytes)
+    dOut = ctx.empty(nref * nctu * n * 12)
+    for mode in ("sync", "begin_end"):
+        host = np.full((nref, nctu, n, 3), -7, dtype=np.int32)
+        args = (params, dY.ptr + o, F.S, [b.ptr + o for b in F.dY[1:]], F.S, F.y[0].ctypes.data, dY.ptr, F.y[0].nbytes, dOut, host.ctypes.data, host.nbytes)
+        if mode == "sync":
+            ctx.me_frame_ex_host(*args, dMvpCtu=dMvp, **kw)
+        else:
+            ctx.me_frame_ex_host_begin(*args, dMvpCtu=dMvp, **kw)
+            scratch = ctx.to_device(np.arange(1 << 16, dtype=np.int32))        # unrelated work on the compute stream in between
+            ctx.me_frame_host_end()
+            scratch.free()
+        assert np.array_equal(host, want), mode
+        assert np.array_equal(dY.download(F.y[0].dtype), F.y[0])
+        dY.upload(np.zeros_like(F.y[0]))
+    # the 2Nx2N entry
+    per_level = [nctu * (1 << l) ** 2 for l in range(4)]
+    dOld = ctx.empty(nref * sum(per_level) * 12)
+    ctx.me_frame_dev(8, F.dY[0].ptr + o, F.S, [b.ptr + o for b in F.dY[1:]], F.S, F.padX, F.padY, F.R, cols, rows, 15, dMvp, pkg.ME_HEX, 2, merange,
+                     params["lambda"], dOld)
+    old = dOld.download(np.int32)
+    host = np.zeros_like(old)
+    ctx.me_frame_host(8, F.y[0].ctypes.data, F.y[0].nbytes, dY.ptr, F.S, [b.ptr + o for b in F.dY[1:]], F.S, F.padX, F.padY, F.R, cols, rows, 15, dMvp,
+                      pkg.ME_HEX, 2, merange, params["lambda"], dOld, host.ctypes.data, host.nbytes)
+    assert np.array_equal(host, old)
+    for b in (dY, dCb, dCr, dOut, dOld, dMvp):
+        b.free()
+    F.free()
+
+
 def _sample_ctus(cols, rows, k, rng):
     pts = {(0, 0), (cols - 1, 0), (0, rows - 1), (cols - 1, rows - 1), (cols // 2, rows // 2)}
     while len(pts) < k:

@@ -498,6 +498,35 @@ def _ctx_me_frame_ex_host(self, params, curY, curStride, refY, refStride, hostY,
 Ctx.me_frame_ex_host = _ctx_me_frame_ex_host
 
 
+def _ctx_me_frame_ex_host_begin(self, params, curY, curStride, refY, refStride, hostY, devYBase, bytesY, devOut, hostOut, outBytes,
+                                dMvpCtu=None, dMvpPu=None, dNumCand=None, dMvc=None, curC=None, curStrideC=0, refCb=None, refCr=None, refStrideC=0,
+                                hostC=None, devCBase=None, bytesC=0):
+    """x265b200_me_frame_ex_host_begin (same arguments as me_frame_ex_host); finish with me_frame_host_end()"""
+    P, pl, _keep = _me_frame_structs(params, curY, curStride, refY, refStride, curC, curStrideC, refCb, refCr, refStrideC)
+    hc = hostC if hostC is not None else (None, None)
+    dc = devCBase if devCBase is not None else (None, None)
+    self._chk(self.L.x265b200_me_frame_ex_host_begin(self.h, ctypes.byref(P), ctypes.byref(pl), _vp(hostY), _vp(devYBase), ctypes.c_size_t(bytesY),
+                                                     _vp(hc[0]), _vp(dc[0]), _vp(hc[1]), _vp(dc[1]), ctypes.c_size_t(bytesC),
+                                                     _vp(dMvpCtu), _vp(dMvpPu), _vp(dNumCand), _vp(dMvc), _vp(devOut), _vp(hostOut), ctypes.c_size_t(outBytes)))
+
+
+def _ctx_me_frame_host_begin(self, depth, hostCurBase, planeBytes, devCurBase, curStride, refOrigins, refStride, marginX, marginY, rowsTotal, ctuCols, ctuRows,
+                             puMask, dMvpCtu, searchMethod, subpelRefine, merange, lam, devOut, hostOut, outBytes):
+    arr = (ctypes.c_void_p * len(refOrigins))(*[int(p) for p in refOrigins])
+    self._chk(self.L.x265b200_me_frame_host_begin(self.h, depth, _vp(hostCurBase), ctypes.c_size_t(planeBytes), _vp(devCurBase), _i64(curStride), arr, len(refOrigins),
+                                                  _i64(refStride), int(marginX), int(marginY), int(rowsTotal), int(ctuCols), int(ctuRows), int(puMask), _vp(dMvpCtu),
+                                                  int(searchMethod), int(subpelRefine), int(merange), ctypes.c_double(lam), _vp(devOut), _vp(hostOut), ctypes.c_size_t(outBytes)))
+
+
+def _ctx_me_frame_host_end(self):
+    self._chk(self.L.x265b200_me_frame_host_end(self.h))
+
+
+Ctx.me_frame_ex_host_begin = _ctx_me_frame_ex_host_begin
+Ctx.me_frame_host_begin = _ctx_me_frame_host_begin
+Ctx.me_frame_host_end = _ctx_me_frame_host_end
+
+
 def _ctx_me_frame_host(self, depth, hostCurBase, planeBytes, devCurBase, curStride, refOrigins, refStride, marginX, marginY, rowsTotal, ctuCols, ctuRows,
                        puMask, dMvpCtu, searchMethod, subpelRefine, merange, lam, devOut, hostOut, outBytes):
     arr = (ctypes.c_void_p * len(refOrigins))(*[int(p) for p in refOrigins])

@@ -325,6 +325,11 @@ void x265b200_destroy(x265b200_ctx* ctx)
         if (ctx->c.hStage[i]) cudaFreeHost(ctx->c.hStage[i]);
         if (ctx->c.hStageEv[i]) cudaEventDestroy(ctx->c.hStageEv[i]);
     }
+    if (ctx->c.copyStream)
+    {
+        cudaStreamSynchronize(ctx->c.copyStream); cudaStreamDestroy(ctx->c.copyStream);
+        cudaEventDestroy(ctx->c.evH2D); cudaEventDestroy(ctx->c.evSearch); cudaEventDestroy(ctx->c.evD2H);
+    }
     me_ctu_release(&ctx->c);
     if (ctx->c.ownsStream) cudaStreamDestroy(ctx->c.stream);
     delete ctx;
@@ -708,22 +713,83 @@ int x265b200_sad_stream_dev(x265b200_ctx* ctx, int depth, const void* poolOrigin
     return sad_stream_dev(CTX(ctx), depth, poolOrigin, framePitch, stride, marginX, marginY, rowsTotal, numFrames, ctuCols, ctuRows,
                           groupsHost, numGroups, numRefs, out8, out16, out32, out64);
 }
+// host-buffer forms: H2D and D2H run on the context's copy stream, ordered against the search on the compute stream by events, so the
+// copies of one call overlap whatever else the caller has queued on the compute stream (the stages that follow the previous search)
+static int host_copy_setup(x265b200_ctx* ctx)
+{
+    Ctx& c = ctx->c;
+    if (c.copyStream) return 0;
+    X265B200_CHECK(cudaStreamCreateWithFlags(&c.copyStream, cudaStreamNonBlocking));
+    X265B200_CHECK(cudaEventCreateWithFlags(&c.evH2D, cudaEventDisableTiming));
+    X265B200_CHECK(cudaEventCreateWithFlags(&c.evSearch, cudaEventDisableTiming));
+    X265B200_CHECK(cudaEventCreateWithFlags(&c.evD2H, cudaEventDisableTiming));
+    return 0;
+}
+static int host_results_back(x265b200_ctx* ctx, int32_t* devOut, int32_t* hostOut, size_t outBytes)
+{
+    Ctx& c = ctx->c;
+    X265B200_CHECK(cudaEventRecord(c.evSearch, c.stream));
+    X265B200_CHECK(cudaStreamWaitEvent(c.copyStream, c.evSearch, 0));
+    X265B200_CHECK(cudaMemcpyAsync(hostOut, devOut, outBytes, cudaMemcpyDeviceToHost, c.copyStream));
+    X265B200_CHECK(cudaEventRecord(c.evD2H, c.copyStream));
+    c.hostPending = true;
+    return 0;
+}
+int x265b200_me_frame_host_begin(x265b200_ctx* ctx, int depth, const void* hostCurBase, size_t planeBytes, void* devCurBase, int64_t curStride,
+                                 const void* const* refOriginsHost, int numRefs, int64_t refStride,
+                                 int marginX, int marginY, int rowsTotal, int ctuCols, int ctuRows, int puMask,
+                                 const int32_t* mvpCtu, int searchMethod, int subpelRefine, int merange, double lambda,
+                                 int32_t* devOut, int32_t* hostOut, size_t outBytes)
+{
+    REQUIRE_CTX(ctx);
+    if (!hostCurBase || !devCurBase || !devOut || !hostOut) { set_error("me_frame_host: null buffer"); return -1; }
+    if (ctx->c.hostPending) { set_error("me_frame_host_begin: the previous call has not been ended (x265b200_me_frame_host_end)"); return -1; }
+    if (host_copy_setup(ctx)) return -1;
+    const int px = depth > 8 ? 2 : 1;
+    X265B200_CHECK(cudaMemcpyAsync(devCurBase, hostCurBase, planeBytes, cudaMemcpyHostToDevice, ctx->c.copyStream));
+    X265B200_CHECK(cudaEventRecord(ctx->c.evH2D, ctx->c.copyStream));
+    X265B200_CHECK(cudaStreamWaitEvent(ctx->c.stream, ctx->c.evH2D, 0));
+    const char* origin = (const char*)devCurBase + ((int64_t)marginY * curStride + marginX) * px;
+    if (me_frame_dev(CTX(ctx), depth, origin, curStride, refOriginsHost, numRefs, refStride, marginX, marginY, rowsTotal, ctuCols, ctuRows, puMask,
+                     mvpCtu, searchMethod, subpelRefine, merange, lambda, devOut)) return -1;
+    return host_results_back(ctx, devOut, hostOut, outBytes);
+}
+int x265b200_me_frame_ex_host_begin(x265b200_ctx* ctx, const x265b200_me_frame_params* params, const x265b200_me_frame_planes* planes,
+                                    const void* hostCurYBase, void* devCurYBase, size_t bytesY,
+                                    const void* hostCurCbBase, void* devCurCbBase, const void* hostCurCrBase, void* devCurCrBase, size_t bytesC,
+                                    const int32_t* mvpCtu, const int32_t* mvpPu, const uint8_t* numCandPu, const int32_t* mvcPu,
+                                    int32_t* devOut, int32_t* hostOut, size_t outBytes)
+{
+    REQUIRE_CTX(ctx);
+    if (!hostCurYBase || !devCurYBase || !devOut || !hostOut) { set_error("me_frame_ex_host: null buffer"); return -1; }
+    if (ctx->c.hostPending) { set_error("me_frame_ex_host_begin: the previous call has not been ended (x265b200_me_frame_host_end)"); return -1; }
+    if (host_copy_setup(ctx)) return -1;
+    cudaStream_t cs = ctx->c.copyStream;
+    X265B200_CHECK(cudaMemcpyAsync(devCurYBase, hostCurYBase, bytesY, cudaMemcpyHostToDevice, cs));
+    if (hostCurCbBase && devCurCbBase) X265B200_CHECK(cudaMemcpyAsync(devCurCbBase, hostCurCbBase, bytesC, cudaMemcpyHostToDevice, cs));
+    if (hostCurCrBase && devCurCrBase) X265B200_CHECK(cudaMemcpyAsync(devCurCrBase, hostCurCrBase, bytesC, cudaMemcpyHostToDevice, cs));
+    X265B200_CHECK(cudaEventRecord(ctx->c.evH2D, cs));
+    X265B200_CHECK(cudaStreamWaitEvent(ctx->c.stream, ctx->c.evH2D, 0));
+    if (me_frame_ex_dev(CTX(ctx), params, planes, mvpCtu, mvpPu, numCandPu, mvcPu, devOut)) return -1;
+    return host_results_back(ctx, devOut, hostOut, outBytes);
+}
+int x265b200_me_frame_host_end(x265b200_ctx* ctx)
+{
+    REQUIRE_CTX(ctx);
+    if (!ctx->c.hostPending) return 0;
+    ctx->c.hostPending = false;
+    X265B200_CHECK(cudaEventSynchronize(ctx->c.evD2H));
+    return 0;
+}
 int x265b200_me_frame_host(x265b200_ctx* ctx, int depth, const void* hostCurBase, size_t planeBytes, void* devCurBase, int64_t curStride,
                            const void* const* refOriginsHost, int numRefs, int64_t refStride,
                            int marginX, int marginY, int rowsTotal, int ctuCols, int ctuRows, int puMask,
                            const int32_t* mvpCtu, int searchMethod, int subpelRefine, int merange, double lambda,
                            int32_t* devOut, int32_t* hostOut, size_t outBytes)
 {
-    REQUIRE_CTX(ctx);
-    if (!hostCurBase || !devCurBase || !devOut || !hostOut) { set_error("me_frame_host: null buffer"); return -1; }
-    const int px = depth > 8 ? 2 : 1;
-    X265B200_CHECK(cudaMemcpyAsync(devCurBase, hostCurBase, planeBytes, cudaMemcpyHostToDevice, ctx->c.stream));
-    const char* origin = (const char*)devCurBase + ((int64_t)marginY * curStride + marginX) * px;
-    if (me_frame_dev(CTX(ctx), depth, origin, curStride, refOriginsHost, numRefs, refStride, marginX, marginY, rowsTotal, ctuCols, ctuRows, puMask,
-                     mvpCtu, searchMethod, subpelRefine, merange, lambda, devOut)) return -1;
-    X265B200_CHECK(cudaMemcpyAsync(hostOut, devOut, outBytes, cudaMemcpyDeviceToHost, ctx->c.stream));
-    X265B200_CHECK(cudaStreamSynchronize(ctx->c.stream));
-    return 0;
+    if (x265b200_me_frame_host_begin(ctx, depth, hostCurBase, planeBytes, devCurBase, curStride, refOriginsHost, numRefs, refStride, marginX, marginY, rowsTotal,
+                                     ctuCols, ctuRows, puMask, mvpCtu, searchMethod, subpelRefine, merange, lambda, devOut, hostOut, outBytes)) return -1;
+    return x265b200_me_frame_host_end(ctx);
 }
 int x265b200_me_frame_ex_host(x265b200_ctx* ctx, const x265b200_me_frame_params* params, const x265b200_me_frame_planes* planes,
                               const void* hostCurYBase, void* devCurYBase, size_t bytesY,
@@ -731,16 +797,11 @@ int x265b200_me_frame_ex_host(x265b200_ctx* ctx, const x265b200_me_frame_params*
                               const int32_t* mvpCtu, const int32_t* mvpPu, const uint8_t* numCandPu, const int32_t* mvcPu,
                               int32_t* devOut, int32_t* hostOut, size_t outBytes)
 {
-    REQUIRE_CTX(ctx);
-    if (!hostCurYBase || !devCurYBase || !devOut || !hostOut) { set_error("me_frame_ex_host: null buffer"); return -1; }
-    X265B200_CHECK(cudaMemcpyAsync(devCurYBase, hostCurYBase, bytesY, cudaMemcpyHostToDevice, ctx->c.stream));
-    if (hostCurCbBase && devCurCbBase) X265B200_CHECK(cudaMemcpyAsync(devCurCbBase, hostCurCbBase, bytesC, cudaMemcpyHostToDevice, ctx->c.stream));
-    if (hostCurCrBase && devCurCrBase) X265B200_CHECK(cudaMemcpyAsync(devCurCrBase, hostCurCrBase, bytesC, cudaMemcpyHostToDevice, ctx->c.stream));
-    if (me_frame_ex_dev(CTX(ctx), params, planes, mvpCtu, mvpPu, numCandPu, mvcPu, devOut)) return -1;
-    X265B200_CHECK(cudaMemcpyAsync(hostOut, devOut, outBytes, cudaMemcpyDeviceToHost, ctx->c.stream));
-    X265B200_CHECK(cudaStreamSynchronize(ctx->c.stream));
-    return 0;
+    if (x265b200_me_frame_ex_host_begin(ctx, params, planes, hostCurYBase, devCurYBase, bytesY, hostCurCbBase, devCurCbBase, hostCurCrBase, devCurCrBase, bytesC,
+                                        mvpCtu, mvpPu, numCandPu, mvcPu, devOut, hostOut, outBytes)) return -1;
+    return x265b200_me_frame_host_end(ctx);
 }
+
 int x265b200_cutree_propagate_dev(x265b200_ctx* ctx, int widthInCU, int heightInCU, const uint16_t* propagateCostB, const int32_t* intraCost,
                                   const uint16_t* lowresCosts, const int32_t* invQscale, const int32_t* mvs0, const int32_t* mvs1,
                                   uint16_t* refCost0, uint16_t* refCost1, int bipredWeight, double fpsFactor)

@@ -37,6 +37,11 @@ struct Ctx
     size_t       hStageBytes[4];
     cudaEvent_t  hStageEv[4];
     int          hStageNext;
+    // host-buffer frame searches (x265b200_me_frame*_host_begin / _host_end): a copy stream next to the compute stream, and the
+    // events that order H2D -> search -> D2H across them
+    cudaStream_t copyStream;
+    cudaEvent_t  evH2D, evSearch, evD2H;
+    bool         hostPending;
 };
 
 void set_error(const char* fmt, ...);
