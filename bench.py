@@ -446,6 +446,14 @@ class Workload:
     def frame(self, t):
         return t % self.NF
 
+    def e2e_retire(self, drain=False):
+        """a step's {mv, cost} records are read (x265b200_me_frame_host_end) once the NEXT step has been queued, so the host stays one step
+        ahead of the device; every step's H2D and D2H still happen inside the timed region"""
+        self.e2e_pending = getattr(self, "e2e_pending", 0) + (0 if drain else 1)
+        while self.e2e_pending > (0 if drain else 1):
+            self.ctx.me_frame_host_end()
+            self.e2e_pending -= 1
+
     def refs_of(self, t):
         return [(t - 1 - r) % self.NF for r in range(self.nref)]
 
@@ -524,7 +532,7 @@ class MEWorkload(Workload):
                                         self.nout * 12, **kw)
         if self.row0 == 0:
             self.sad_stream(self.one_group(t))
-        self.ctx.me_frame_host_end()
+        self.e2e_retire()
 
     def h2d_bytes(self):
         return self.plane_bytes + (2 * self.planeC_bytes if self.csp else 0)
@@ -698,7 +706,7 @@ class MixWorkload(Workload):
         self.lookahead_step(t, ev)
         self.sad_stream(self.one_group(t))
         self.stages_after_search(t)
-        self.ctx.me_frame_host_end()           # the step's result ({mv, cost} of every PU) is in pinned host memory from here on
+        self.e2e_retire()
 
     def h2d_bytes(self):
         return self.plane_bytes
@@ -892,6 +900,7 @@ def main():
                 stream.wait_event(comm_events[k])
             wl.e2e_step(first + i, k)
             exchange(first + i, k, wl.me_out[k])
+        wl.e2e_retire(drain=True)
         wl.join()
         if comm is not None:
             stream.wait_stream(comm)

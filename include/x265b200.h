@@ -459,7 +459,8 @@ int x265b200_me_frame_host(x265b200_ctx* ctx, int depth, const void* hostCurBase
 /* The same in two halves, for callers that have more device work to queue behind the search (the stages that consume the MVs):
  * _begin returns once the transfers and the search are queued -- the source picture travels on the context's own copy stream, so it
  * overlaps whatever is still running on the compute stream, the search waits for it, and the results travel back on the copy stream
- * while the compute stream goes on; x265b200_me_frame_host_end blocks until hostOut is complete.  One call may be pending per context;
+ * while the compute stream goes on; x265b200_me_frame_host_end blocks until the hostOut of the OLDEST pending call is complete.  Two calls
+ * may be pending per context (queue frame t+1, then read frame t: the host never idles the device);
  * the destination plane must not be read by work queued before _begin (a picture buffer that left the reference list). */
 int x265b200_me_frame_host_begin(x265b200_ctx* ctx, int depth, const void* hostCurBase, size_t planeBytes, void* devCurBase, int64_t curStride,
                                  const void* const* refOriginsHost, int numRefs, int64_t refStride,

@@ -216,6 +216,20 @@ def test_host_buffer_entries_equal_the_device_entry(ctx):
         assert np.array_equal(host, want), mode
         assert np.array_equal(dY.download(F.y[0].dtype), F.y[0])
         dY.upload(np.zeros_like(F.y[0]))
+    # two calls pending: the second is queued before the first is read
+    dY.upload(np.zeros_like(F.y[0]))
+    hostA, hostB = np.full((nref, nctu, n, 3), -7, dtype=np.int32), np.full((nref, nctu, n, 3), -7, dtype=np.int32)
+    dOutB = ctx.empty(nref * nctu * n * 12)
+    base = (params, dY.ptr + o, F.S, [b.ptr + o for b in F.dY[1:]], F.S, F.y[0].ctypes.data, dY.ptr, F.y[0].nbytes)
+    ctx.me_frame_ex_host_begin(*base, dOut, hostA.ctypes.data, hostA.nbytes, dMvpCtu=dMvp, **kw)
+    ctx.me_frame_ex_host_begin(*base, dOutB, hostB.ctypes.data, hostB.nbytes, dMvpCtu=dMvp, **kw)
+    with pytest.raises(pkg.X265B200Error):
+        ctx.me_frame_ex_host_begin(*base, dOutB, hostB.ctypes.data, hostB.nbytes, dMvpCtu=dMvp, **kw)        # a third one is refused
+    ctx.me_frame_host_end()
+    assert np.array_equal(hostA, want)
+    ctx.me_frame_host_end()
+    assert np.array_equal(hostB, want)
+    dOutB.free()
     # the 2Nx2N entry
     per_level = [nctu * (1 << l) ** 2 for l in range(4)]
     dOld = ctx.empty(nref * sum(per_level) * 12)

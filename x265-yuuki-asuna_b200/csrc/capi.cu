@@ -328,7 +328,7 @@ void x265b200_destroy(x265b200_ctx* ctx)
     if (ctx->c.copyStream)
     {
         cudaStreamSynchronize(ctx->c.copyStream); cudaStreamDestroy(ctx->c.copyStream);
-        cudaEventDestroy(ctx->c.evH2D); cudaEventDestroy(ctx->c.evSearch); cudaEventDestroy(ctx->c.evD2H);
+        cudaEventDestroy(ctx->c.evH2D); cudaEventDestroy(ctx->c.evSearch); cudaEventDestroy(ctx->c.evD2H[0]); cudaEventDestroy(ctx->c.evD2H[1]);
     }
     me_ctu_release(&ctx->c);
     if (ctx->c.ownsStream) cudaStreamDestroy(ctx->c.stream);
@@ -722,7 +722,8 @@ static int host_copy_setup(x265b200_ctx* ctx)
     X265B200_CHECK(cudaStreamCreateWithFlags(&c.copyStream, cudaStreamNonBlocking));
     X265B200_CHECK(cudaEventCreateWithFlags(&c.evH2D, cudaEventDisableTiming));
     X265B200_CHECK(cudaEventCreateWithFlags(&c.evSearch, cudaEventDisableTiming));
-    X265B200_CHECK(cudaEventCreateWithFlags(&c.evD2H, cudaEventDisableTiming));
+    X265B200_CHECK(cudaEventCreateWithFlags(&c.evD2H[0], cudaEventDisableTiming));
+    X265B200_CHECK(cudaEventCreateWithFlags(&c.evD2H[1], cudaEventDisableTiming));
     return 0;
 }
 static int host_results_back(x265b200_ctx* ctx, int32_t* devOut, int32_t* hostOut, size_t outBytes)
@@ -731,8 +732,8 @@ static int host_results_back(x265b200_ctx* ctx, int32_t* devOut, int32_t* hostOu
     X265B200_CHECK(cudaEventRecord(c.evSearch, c.stream));
     X265B200_CHECK(cudaStreamWaitEvent(c.copyStream, c.evSearch, 0));
     X265B200_CHECK(cudaMemcpyAsync(hostOut, devOut, outBytes, cudaMemcpyDeviceToHost, c.copyStream));
-    X265B200_CHECK(cudaEventRecord(c.evD2H, c.copyStream));
-    c.hostPending = true;
+    X265B200_CHECK(cudaEventRecord(c.evD2H[(c.hostHead + c.hostCount) & 1], c.copyStream));
+    c.hostCount++;
     return 0;
 }
 int x265b200_me_frame_host_begin(x265b200_ctx* ctx, int depth, const void* hostCurBase, size_t planeBytes, void* devCurBase, int64_t curStride,
@@ -743,7 +744,7 @@ int x265b200_me_frame_host_begin(x265b200_ctx* ctx, int depth, const void* hostC
 {
     REQUIRE_CTX(ctx);
     if (!hostCurBase || !devCurBase || !devOut || !hostOut) { set_error("me_frame_host: null buffer"); return -1; }
-    if (ctx->c.hostPending) { set_error("me_frame_host_begin: the previous call has not been ended (x265b200_me_frame_host_end)"); return -1; }
+    if (ctx->c.hostCount >= 2) { set_error("me_frame_host_begin: two calls are pending already (x265b200_me_frame_host_end)"); return -1; }
     if (host_copy_setup(ctx)) return -1;
     const int px = depth > 8 ? 2 : 1;
     X265B200_CHECK(cudaMemcpyAsync(devCurBase, hostCurBase, planeBytes, cudaMemcpyHostToDevice, ctx->c.copyStream));
@@ -762,7 +763,7 @@ int x265b200_me_frame_ex_host_begin(x265b200_ctx* ctx, const x265b200_me_frame_p
 {
     REQUIRE_CTX(ctx);
     if (!hostCurYBase || !devCurYBase || !devOut || !hostOut) { set_error("me_frame_ex_host: null buffer"); return -1; }
-    if (ctx->c.hostPending) { set_error("me_frame_ex_host_begin: the previous call has not been ended (x265b200_me_frame_host_end)"); return -1; }
+    if (ctx->c.hostCount >= 2) { set_error("me_frame_ex_host_begin: two calls are pending already (x265b200_me_frame_host_end)"); return -1; }
     if (host_copy_setup(ctx)) return -1;
     cudaStream_t cs = ctx->c.copyStream;
     X265B200_CHECK(cudaMemcpyAsync(devCurYBase, hostCurYBase, bytesY, cudaMemcpyHostToDevice, cs));
@@ -776,9 +777,10 @@ int x265b200_me_frame_ex_host_begin(x265b200_ctx* ctx, const x265b200_me_frame_p
 int x265b200_me_frame_host_end(x265b200_ctx* ctx)
 {
     REQUIRE_CTX(ctx);
-    if (!ctx->c.hostPending) return 0;
-    ctx->c.hostPending = false;
-    X265B200_CHECK(cudaEventSynchronize(ctx->c.evD2H));
+    if (!ctx->c.hostCount) return 0;
+    const int slot = ctx->c.hostHead;
+    ctx->c.hostHead ^= 1; ctx->c.hostCount--;
+    X265B200_CHECK(cudaEventSynchronize(ctx->c.evD2H[slot]));                 // the OLDEST pending call
     return 0;
 }
 int x265b200_me_frame_host(x265b200_ctx* ctx, int depth, const void* hostCurBase, size_t planeBytes, void* devCurBase, int64_t curStride,

@@ -40,8 +40,8 @@ struct Ctx
     // host-buffer frame searches (x265b200_me_frame*_host_begin / _host_end): a copy stream next to the compute stream, and the
     // events that order H2D -> search -> D2H across them
     cudaStream_t copyStream;
-    cudaEvent_t  evH2D, evSearch, evD2H;
-    bool         hostPending;
+    cudaEvent_t  evH2D, evSearch, evD2H[2];
+    int          hostHead, hostCount;      // ring of pending host calls (at most two: the caller may queue the next frame before it reads this one)
 };
 
 void set_error(const char* fmt, ...);
