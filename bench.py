@@ -718,6 +718,99 @@ class MixWorkload(Workload):
         pass
 
 
+class LookaheadWorkload(MixWorkload):
+    """--shard triples (config 3): ONE stream of frames goes through the lookahead half of the path on N GPUs.  The rank
+    that owns a frame (t % N) runs Lowres::init + lowresIntraEstimate and broadcasts the four hpel planes and the intra costs; the
+    frame-triples of every batch are dealt round-robin (they are independent, slicetype.cpp:1942-1968); rank 0 gathers lowresCosts,
+    rowSatds and the frame sums.  Strong scaling: the work is fixed as N grows."""
+
+    def __init__(self, args, cfg, pkg, torch, ctx, dev, stream, rank, world, band=None):
+        Workload.__init__(self, args, cfg, pkg, torch, ctx, dev, stream, rank, world, band)
+        import torch.distributed as dist
+        self.dist = dist
+        self.P = lambda t: t.data_ptr()
+        self.njobs = 0
+        self.me_out = [torch.empty((1, 3), dtype=torch.int32, device=dev) for _ in range(2)]
+        self.units = {"lookahead_list_searches_per_frame": 2 * (LA_BFRAMES + 1), "frames_per_launch": LA_BATCH}
+        self.workload = ("2160p-8bit-medium LOOKAHEAD half only (SURVEY.md 8e row 2): Lowres::init + lowresIntraEstimate per frame on the owning rank, broadcast of the "
+                         "4 hpel planes + intra costs, the %d frame-triples of every %d-frame batch dealt round-robin over the ranks (--lookahead-slices 8), "
+                         "gather of lowresCosts / rowSatds / sums on rank 0" % (LA_BATCH * (LA_BFRAMES + 1), LA_BATCH))
+        self.n32 = (W // 32) * (CTU_ROWS * 2)
+        self.init_lookahead()
+        ntr = LA_BATCH * (LA_BFRAMES + 1)
+        self.per_rank = pkg.triples_per_rank_max(ntr, world)
+        n = self.per_rank
+        self.res_send = torch.zeros(n * (self.ncu * 2 + self.hcu * 4 + 16), dtype=torch.uint8, device=dev)
+        self.res_all = [torch.empty_like(self.res_send) for _ in range(world)] if rank == 0 and world > 1 else None
+        self.res_host = torch.empty((world, self.res_send.numel()), dtype=torch.uint8).pin_memory() if rank == 0 else None
+        self.e2e = False
+
+    def la_estimate(self, frames):
+        torch, dist = self.torch, self.dist
+        NL = self.NF
+        centre = lambda b: min(max(b, LA_BFRAMES + 1), NL - LA_BFRAMES - 2)
+        wave = [(centre(b) - d, centre(b) + d, centre(b)) for b in frames for d in range(1, LA_BFRAMES + 2)]
+        mine = self.pkg.triples_of_rank(len(wave), self.rank, self.world)
+        tr = np.zeros(len(mine), dtype=self.pkg.LA_TRIPLE)
+        for j, t in enumerate(mine):
+            p0, p1, b = wave[t]
+            d = t % (LA_BFRAMES + 1) + 1
+            tr[j]["b"], tr[j]["p0"], tr[j]["p1"] = b, p0, p1
+            for lst in (0, 1):
+                tr[j]["mvSlot"][lst] = (b * 2 + lst) * (LA_BFRAMES + 2) + d
+                tr[j]["doSearch"][lst] = 1
+        P = self.P
+        if len(mine):
+            self.la_ctx.la_estimate_dev(8, P(self.la_plane_ptrs_d), self.ls, self.wcu, self.hcu, tr, P(self.la_mv), P(self.la_mvc), P(self.la_intra_ptrs_d), None,
+                                        P(self.la_lc), P(self.la_rs), P(self.la_sm), self.la_lam, lookaheadSlices=LA_SLICES)
+        with torch.cuda.stream(self.la_stream):
+            n, ncu, hcu = len(mine), self.ncu, self.hcu
+            o1, o2 = self.per_rank * ncu * 2, self.per_rank * (ncu * 2 + hcu * 4)
+            self.res_send[:n * ncu * 2].copy_(self.la_lc[:n * ncu].view(torch.uint8))
+            self.res_send[o1:o1 + n * hcu * 4].copy_(self.la_rs[:n * hcu].view(torch.uint8))
+            self.res_send[o2:o2 + n * 16].copy_(self.la_sm[:n * 4].view(torch.uint8))
+            if self.world > 1:
+                dist.gather(self.res_send, self.res_all, dst=0)
+            if self.e2e and self.rank == 0:
+                src = self.res_all if self.world > 1 else [self.res_send]
+                for r in range(self.world):
+                    self.res_host[r].copy_(src[r], non_blocking=True)
+
+    def step(self, t, k=0, events=None):
+        self.e2e = False
+        return self.one_frame(t, k)
+
+    def one_frame(self, t, k):
+        torch, dist = self.torch, self.dist
+        f, owner = self.frame(t), t % self.world
+        with torch.cuda.stream(self.la_stream):
+            if owner == self.rank:
+                if self.e2e:
+                    self.pool[f].copy_(self.host_y[f], non_blocking=True)        # the new frame arrives from pinned host memory
+                self.la_frame(f)
+            if self.world > 1:
+                dist.broadcast(self.la_planes[f], src=owner)
+                dist.broadcast(self.la_intra_cost[f], src=owner)
+        self.la_pending.append(f)
+        if len(self.la_pending) == LA_BATCH:
+            self.la_estimate(self.la_pending)
+            self.la_pending = []
+        return self.me_out[k]
+
+    def e2e_step(self, t, k=0):
+        self.e2e = True
+        self.one_frame(t, k)
+
+    def e2e_retire(self, drain=False):
+        pass
+
+    def h2d_bytes(self):
+        return self.plane_bytes
+
+    def d2h_bytes(self):
+        return (LA_BFRAMES + 1) * (self.ncu * 2 + self.hcu * 4 + 16)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -725,7 +818,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--config", type=int, default=3, choices=sorted(CONFIGS))
-    ap.add_argument("--shard", default="frames", choices=["frames", "ctu-rows"])
+    ap.add_argument("--shard", default="frames", choices=["frames", "ctu-rows", "triples"])
     ap.add_argument("--la-sms", type=int, default=LA_SMS, help="config 3: SMs set aside for the lookahead stream (x265b200_sm_partition); 0 = no partition")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -760,12 +853,14 @@ def main():
         band = pkg.band_rows(geometry(cfg)["rows"], rank, world)
     if args.config == 3 and args.shard == "ctu-rows":
         raise SystemExit("--shard ctu-rows applies to the frame-search configs (2, 4, 5)")
-    wl = (MixWorkload if args.config == 3 else MEWorkload)(args, cfg, pkg, torch, ctx, dev, stream, rank, world, band)
+    if args.shard == "triples" and args.config != 3:
+        raise SystemExit("--shard triples applies to the lookahead of config 3")
+    wl = (LookaheadWorkload if args.shard == "triples" else (MixWorkload if args.config == 3 else MEWorkload))(args, cfg, pkg, torch, ctx, dev, stream, rank, world, band)
 
     # ---- N > 1: the path's exchange on a comm stream, overlapped with the next step ----------------------------
     comm = torch.cuda.Stream(device=local) if world > 1 else None
     g = wl.g
-    if world > 1:
+    if world > 1 and args.shard != "triples":
         if args.shard == "frames":
             # every rank needs the reference pixels the others produced: all_gather of the new luma plane; rank 0 collects the {mv,cost} records
             gathered = [torch.empty((world, wl.pool[0].shape[0], wl.pool[0].shape[1] * wl.item), dtype=torch.uint8, device=dev) for _ in range(2)]   # bytes: NCCL has no int16
@@ -781,7 +876,7 @@ def main():
     comm_events = [None, None]
 
     def exchange(t, k, out):
-        if world == 1:
+        if world == 1 or args.shard == "triples":          # the lookahead workload runs its own broadcast / gather
             return
         done = torch.cuda.Event(); done.record(stream)
         with torch.cuda.stream(comm):
@@ -834,7 +929,7 @@ def main():
 
     # ---- per-kernel times of the two ME kernels (a separate short pass: events inside the step) ---------------------------
     stage_events = []
-    if isinstance(wl, MixWorkload):
+    if isinstance(wl, MixWorkload) and not isinstance(wl, LookaheadWorkload):
         run_steps(t_first, 4, stage_events)
         torch.cuda.synchronize()
     sad_ms = [e[0].elapsed_time(e[1]) for e in stage_events]
@@ -935,10 +1030,11 @@ def main():
                            "l2": "frames come from a ring of %d frames (%.0f MB) larger than L2; no flush" % (wl.NF, wl.NF * wl.plane_bytes / 1e6),
                            "sm_partition": ({"lookahead_sms": args.sm_split[0], "main_sms": args.sm_split[1], "how": "x265b200_sm_partition (CUDA green contexts): the lookahead stream and the main stream own disjoint SMs"} if args.la_stream is not None else None),
                            "parallelism": ("frame-parallel x%d (all_gather of the new plane + gather of results on a comm stream)" % world) if args.shard == "frames"
-                                          else ("CTU-row bands of one frame x%d (all_gather of the bands' rows + gather of results)" % world)},
+                                          else ("CTU-row bands of one frame x%d (all_gather of the bands' rows + gather of results)" % world) if args.shard == "ctu-rows"
+                                          else ("lookahead frame-triples round-robin x%d (broadcast of the new frame's lowres planes + intra costs, gather of the cost records)" % world)},
                 "clocks": sampler.summary(), "gpu_launches": int(launches),
                 "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": wl.h2d_bytes(), "d2h_bytes_per_step": wl.d2h_bytes(),
-                        "how": "x265b200_me_frame%s_host_begin / _host_end: per step the frame is copied from pinned host memory (copy stream), searched, and the {mv,cost} records are copied back to pinned host memory; the step's other stages are queued in between" % ("" if args.config == 3 else "_ex")},
+                        "how": "the owning rank copies the new frame from pinned host memory, rank 0 copies the gathered cost records back to pinned host memory" if args.shard == "triples" else "x265b200_me_frame%s_host_begin / _host_end: per step the frame is copied from pinned host memory (copy stream), searched, and the {mv,cost} records are copied back to pinned host memory; the step's other stages are queued in between" % ("" if args.config == 3 else "_ex")},
                 "roofline": {"kernel": "sad_stream_kernel (streaming ME SAD at the predictor: all 4 PU levels x %d references, %d frame groups in one launch, TMA ring)" % (wl.nref, groups),
                              "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": traffic,
                              "traffic_src": "profiles/r02_sad_stream.txt (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum of the same launch)" if traffic else None,

@@ -147,3 +147,59 @@ def test_band_partition_arithmetic():
             assert all(bands[i][0] + bands[i][1] == bands[i + 1][0] for i in range(world - 1))
             assert max(n for _, n in bands) - min(n for _, n in bands) <= 1
             assert pkg.plane_chunk(rows * 64, world) * world >= rows * 64
+
+
+def _triple_worker(rank, world, port, q):
+    """--shard triples: the frame-triples of a batch dealt round-robin; each rank's records (here: a function of the triple) are padded
+    to the largest share and gathered; rank 0 puts them back in batch order"""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    import importlib
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pkg = importlib.import_module("x265-yuuki-asuna_b200")
+    ntr, reclen = 25, 7                                                    # 5 frames x (bframes 4 + 1) triples
+    wave = [(b - d, b + d, b) for b in range(10, 15) for d in range(1, 6)]
+    rec = lambda t: np.array([wave[t][0], wave[t][1], wave[t][2], t, t * t, 1, 2], dtype=np.int32)
+    mine = pkg.triples_of_rank(ntr, rank, world)
+    n = pkg.triples_per_rank_max(ntr, world)
+    send = torch.zeros((n, reclen), dtype=torch.int32)
+    for j, t in enumerate(mine):
+        send[j] = torch.from_numpy(rec(t))
+    parts = [torch.empty_like(send) for _ in range(world)] if rank == 0 else None
+    dist.gather(send, parts, dst=0)
+    # the owning rank's new lowres planes reach every rank
+    plane = torch.full((4, 64), rank, dtype=torch.uint8)
+    for owner in range(world):
+        buf = plane.clone() if owner == rank else torch.empty_like(plane)
+        dist.broadcast(buf, src=owner)
+        assert int(buf[0, 0]) == owner
+    if rank == 0:
+        got = pkg.assemble_triples([p.numpy() for p in parts], ntr, world)
+        q.put(bool(np.array_equal(got, np.stack([rec(t) for t in range(ntr)]))))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_lookahead_triples_round_robin_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_triple_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    ok = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert ok
+
+
+def test_triple_partition_arithmetic():
+    import importlib
+    pkg = importlib.import_module("x265-yuuki-asuna_b200")
+    for n in (0, 1, 5, 80, 81):
+        for world in (1, 2, 3, 8):
+            shares = [pkg.triples_of_rank(n, r, world) for r in range(world)]
+            assert sorted(t for s in shares for t in s) == list(range(n))
+            assert max(len(s) for s in shares) == pkg.triples_per_rank_max(n, world) or n == 0

@@ -34,3 +34,23 @@ def assemble_bands(parts, ctu_rows, ctu_cols, pus_per_ctu, num_refs, world):
             rows.append(parts[r][ref * n:(ref + 1) * n])
         out.append(np.concatenate(rows, axis=0))
     return np.stack(out)
+
+
+def triples_of_rank(num_triples, rank, world):
+    """lookahead-triple sharding: the (p0, p1, b) cost estimates of a batch are independent
+    (slicetype.cpp:1942-1968), so triple i goes to rank i % world; returns this rank's indices in batch order"""
+    return list(range(rank, num_triples, world))
+
+
+def triples_per_rank_max(num_triples, world):
+    return (num_triples + world - 1) // world
+
+
+def assemble_triples(parts, num_triples, world):
+    """parts[r]: rank r's gathered numpy array [triples_per_rank_max][...] (padded).  Returns [num_triples][...] in batch order."""
+    import numpy as np
+    out = np.empty((num_triples,) + tuple(parts[0].shape[1:]), dtype=parts[0].dtype)
+    for r in range(world):
+        idx = triples_of_rank(num_triples, r, world)
+        out[idx] = parts[r][:len(idx)]
+    return out
