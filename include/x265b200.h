@@ -87,7 +87,7 @@ int x265b200_pixelcmp_host(x265b200_ctx* ctx, int kind, int depth, int w, int h,
  * (pixel.cpp:40-55) of every 2Nx2N PU of every 64x64 CTU, i.e. the cost-at-predictor step of
  * motionEstimate (motion.cpp:771-784) for all PU levels at once, against numRefs references in ONE launch.
  * refsDev: DEVICE array of numRefs plane pointers.  mvCtu: optional full-pel {x,y} per [ref][CTU] applied to the
- * reference.  outN holds numRefs consecutive raster grids of NxN blocks (ctuCols*64/N per row).  8-bit. */
+ * reference.  outN holds numRefs consecutive raster grids of NxN blocks (ctuCols*64/N per row).  8- and 16-bit samples. */
 int x265b200_sad_pyramid_dev(x265b200_ctx* ctx, int depth, const void* cur, int64_t strideCur, const void* const* refsDev, int numRefs, int64_t strideRef,
                              int ctuCols, int ctuRows, const int16_t* mvCtu,
                              int32_t* out8, int32_t* out16, int32_t* out32, int32_t* out64);

@@ -131,24 +131,26 @@ def test_grid_mode_with_mv_field(ctx):
             b.free()
 
 
-@pytest.mark.parametrize("with_mv", [False, True])
-def test_sad_pyramid_matches_per_level_sad(ctx, with_mv):
-    """one streaming pass = sad<8,8>..sad<64,64> of every 2Nx2N PU (incl. an odd CTU count and unaligned MVs)."""
+@pytest.mark.parametrize("with_mv,depth", [(False, 8), (True, 8), (False, 10), (True, 10), (True, 12)])
+def test_sad_pyramid_matches_per_level_sad(ctx, with_mv, depth):
+    """one streaming pass = sad<8,8>..sad<64,64> of every 2Nx2N PU (incl. an odd CTU count and unaligned MVs), 8- and 16-bit samples."""
+    from util import pdtype
     rng = np.random.default_rng(11)
     ctuCols, ctuRows, pad = 5, 2, 48
     W, H = ctuCols * 64, ctuRows * 64
     S = W + 2 * pad + 16 - (W + 2 * pad) % 16
-    cur = rng.integers(0, 256, (H + 2 * pad) * S, dtype=np.int64).astype(np.uint8)
+    px = 2 if depth > 8 else 1
+    cur = rng.integers(0, 1 << depth, (H + 2 * pad) * S, dtype=np.int64).astype(pdtype(depth))
     NREF = 2
-    refs = [rng.integers(0, 256, (H + 2 * pad) * S, dtype=np.int64).astype(np.uint8) for _ in range(NREF)]
+    refs = [rng.integers(0, 1 << depth, (H + 2 * pad) * S, dtype=np.int64).astype(pdtype(depth)) for _ in range(NREF)]
     base = pad * S + 48
     mv = rng.integers(-20, 21, (NREF, ctuRows * ctuCols, 2), dtype=np.int64).astype(np.int16) if with_mv else None
     dC = ctx.to_device(cur)
     dR = [ctx.to_device(r) for r in refs]
-    dPtrs = ctx.to_device(np.array([d.ptr + base for d in dR], dtype=np.int64))
+    dPtrs = ctx.to_device(np.array([d.ptr + base * px for d in dR], dtype=np.int64))
     dMv = ctx.to_device(mv) if with_mv else None
     outs = {s: ctx.empty(NREF * (W // s) * (H // s) * 4) for s in (8, 16, 32, 64)}
-    ctx.sad_pyramid_dev(8, dC.ptr + base, S, dPtrs, NREF, S, ctuCols, ctuRows, dMv, outs[8], outs[16], outs[32], outs[64])
+    ctx.sad_pyramid_dev(depth, dC.ptr + base * px, S, dPtrs, NREF, S, ctuCols, ctuRows, dMv, outs[8], outs[16], outs[32], outs[64])
     for s in (8, 16, 32, 64):
         got = outs[s].download(np.int32).reshape(NREF, -1)
         cols = W // s
@@ -160,8 +162,8 @@ def test_sad_pyramid_matches_per_level_sad(ctx, with_mv):
                 mx, my = (int(mv[r][ctu][0]), int(mv[r][ctu][1])) if with_mv else (0, 0)
                 offA.append(base + by * s * S + bx * s)
                 offB.append(base + (by * s + my) * S + bx * s + mx)
-            exp = orc_cmp("sad", 8, s, s, cur, S, refs[r], S, np.array(offA), np.array(offB))
-            assert list(map(int, got[r])) == exp, (s, with_mv, r)
+            exp = orc_cmp("sad", depth, s, s, cur, S, refs[r], S, np.array(offA), np.array(offB))
+            assert list(map(int, got[r])) == exp, (s, with_mv, depth, r)
 
 
 @pytest.mark.parametrize("depth,ctuCols,ctuRows,nref,ngroups", [(8, 5, 2, 2, 3), (8, 9, 3, 3, 4), (10, 5, 2, 2, 3), (10, 3, 3, 1, 2)])

@@ -425,14 +425,15 @@ __device__ __forceinline__ uint4 ld16_any(const uint8_t* p)
 // CTA = 4 warps = one CTU row (64 rows) x 512 px (8 CTUs): warp w owns the 16-row band w, lane l the 16-px column l, so
 // every row is read as one contiguous 512-byte run per warp (DRAM-friendly); 32x32 / 64x64 sums combine lanes by
 // shuffle and the 4 row bands through shared memory.
+template<typename pixel>
 __global__ void __launch_bounds__(128, 8)
-sad_pyramid_kernel(const uint8_t* __restrict__ cur, int64_t strideC, const uint8_t* const* __restrict__ refs, int64_t strideR,
+sad_pyramid_kernel(const pixel* __restrict__ cur, int64_t strideC, const pixel* const* __restrict__ refs, int64_t strideR,
                    int ctuCols, int ctuRows, const int16_t* __restrict__ mvCtu,
                    int32_t* __restrict__ out8, int32_t* __restrict__ out16, int32_t* __restrict__ out32, int32_t* __restrict__ out64)
 {
     __shared__ int sBand[4][32];
     // blockIdx.y = reference index: all references of a frame in ONE launch (the source CTU rows are shared in L2)
-    const uint8_t* __restrict__ ref = refs[blockIdx.y];
+    const pixel* __restrict__ ref = refs[blockIdx.y];
     {
         const int64_t nctu = (int64_t)ctuCols * ctuRows;
         out8 += blockIdx.y * nctu * 64; out16 += blockIdx.y * nctu * 16; out32 += blockIdx.y * nctu * 4; out64 += blockIdx.y * nctu;
@@ -446,23 +447,44 @@ sad_pyramid_kernel(const uint8_t* __restrict__ cur, int64_t strideC, const uint8
     const int x0 = chunk * 512 + lane * 16, y0 = ctuY * 64 + rsub * 16;
     int mvx = 0, mvy = 0;
     if (mvCtu && valid) { mvx = mvCtu[2 * (ctuY * ctuCols + ctuX)]; mvy = mvCtu[2 * (ctuY * ctuCols + ctuX) + 1]; }
-    const uint8_t* c = cur + (int64_t)y0 * strideC + x0;
-    const uint8_t* r = ref + (int64_t)(y0 + mvy) * strideR + x0 + mvx;
+    const pixel* c = cur + (int64_t)y0 * strideC + x0;
+    const pixel* r = ref + (int64_t)(y0 + mvy) * strideR + x0 + mvx;
     uint32_t s8[4] = { 0, 0, 0, 0 };        // [row group 0/1][left/right 8x8]
     if (valid)
     {
-        // 4 batches of 4 rows: 8 independent 128-bit loads in flight per lane
+        // 4 batches of 4 rows: 8 (16-bit: 16) independent 128-bit loads in flight per lane
 #pragma unroll
         for (int g = 0; g < 4; g++)
         {
-            uint4 a[4], b[4];
-#pragma unroll
-            for (int i = 0; i < 4; i++) { a[i] = __ldg((const uint4*)(c + (int64_t)(g * 4 + i) * strideC)); b[i] = ld16_any(r + (int64_t)(g * 4 + i) * strideR); }
-#pragma unroll
-            for (int i = 0; i < 4; i++)
+            if constexpr (sizeof(pixel) == 1)
             {
-                s8[(g >> 1) * 2 + 0] += __vsadu4(a[i].x, b[i].x) + __vsadu4(a[i].y, b[i].y);
-                s8[(g >> 1) * 2 + 1] += __vsadu4(a[i].z, b[i].z) + __vsadu4(a[i].w, b[i].w);
+                uint4 a[4], b[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) { a[i] = __ldg((const uint4*)(c + (int64_t)(g * 4 + i) * strideC)); b[i] = ld16_any(r + (int64_t)(g * 4 + i) * strideR); }
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                {
+                    s8[(g >> 1) * 2 + 0] += __vsadu4(a[i].x, b[i].x) + __vsadu4(a[i].y, b[i].y);
+                    s8[(g >> 1) * 2 + 1] += __vsadu4(a[i].z, b[i].z) + __vsadu4(a[i].w, b[i].w);
+                }
+            }
+            else
+            {
+                // 16-bit samples: a row of the lane's 16 pixels is two vectors, one per 8x8 half
+                uint4 a[4][2], b[4][2];
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+#pragma unroll
+                    for (int h = 0; h < 2; h++)
+                    {
+                        a[i][h] = __ldg((const uint4*)(c + (int64_t)(g * 4 + i) * strideC + 8 * h));
+                        b[i][h] = ld16_any((const uint8_t*)(r + (int64_t)(g * 4 + i) * strideR + 8 * h));
+                    }
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+#pragma unroll
+                    for (int h = 0; h < 2; h++)
+                        s8[(g >> 1) * 2 + h] += sad_u16x2(a[i][h].x, b[i][h].x) + sad_u16x2(a[i][h].y, b[i][h].y) + sad_u16x2(a[i][h].z, b[i][h].z) + sad_u16x2(a[i][h].w, b[i][h].w);
             }
         }
     }
@@ -492,13 +514,14 @@ sad_pyramid_kernel(const uint8_t* __restrict__ cur, int64_t strideC, const uint8
 int sad_pyramid_dev(Ctx* ctx, int depth, const void* cur, int64_t strideC, const void* const* refs, int numRefs, int64_t strideR, int ctuCols, int ctuRows,
                     const int16_t* mvCtu, int32_t* out8, int32_t* out16, int32_t* out32, int32_t* out64)
 {
-    if (depth != 8) { set_error("sad_pyramid: 8-bit planes only (use pixelcmp grid mode for high bit depth)"); return -1; }
-    if (((uintptr_t)cur & 15) || (strideC & 15)) { set_error("sad_pyramid: cur plane and stride must be 16-byte aligned"); return -1; }
+    const int px = depth > 8 ? 2 : 1;
+    if (((uintptr_t)cur & 15) || ((strideC * px) & 15)) { set_error("sad_pyramid: cur plane and row pitch must be 16-byte aligned"); return -1; }
     if (((uintptr_t)out8 & 7)) { set_error("sad_pyramid: out8 must be 8-byte aligned"); return -1; }
     int64_t ctas = (int64_t)((ctuCols + 7) / 8) * ctuRows;
     if (ctas <= 0 || numRefs <= 0) return 0;
     dim3 grid((unsigned)ctas, (unsigned)numRefs);
-    sad_pyramid_kernel<<<grid, 128, 0, ctx->stream>>>((const uint8_t*)cur, strideC, (const uint8_t* const*)refs, strideR, ctuCols, ctuRows, mvCtu, out8, out16, out32, out64);
+    if (depth > 8) sad_pyramid_kernel<uint16_t><<<grid, 128, 0, ctx->stream>>>((const uint16_t*)cur, strideC, (const uint16_t* const*)refs, strideR, ctuCols, ctuRows, mvCtu, out8, out16, out32, out64);
+    else           sad_pyramid_kernel<uint8_t><<<grid, 128, 0, ctx->stream>>>((const uint8_t*)cur, strideC, (const uint8_t* const*)refs, strideR, ctuCols, ctuRows, mvCtu, out8, out16, out32, out64);
     ctx->launches++;
     return check(cudaGetLastError(), "sad_pyramid launch");
 }
