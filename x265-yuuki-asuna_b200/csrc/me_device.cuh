@@ -470,6 +470,32 @@ __device__ __forceinline__ int thread_satd(const MEState<pixel>& s, const pixel*
         }
     return acc;
 #else
+#if defined(ME_PACKED_SATD) && defined(ME_LOWRES_ONLY) && !defined(ME_LA_SATD8_OFF)
+    // the lookahead's 8x8 CU at 8 bits: one pass over the eight rows (each row loaded once for its two 4x4 cells), fully unrolled
+    if constexpr (sizeof(pixel) == 1)
+    {
+        if (ME_PU_W(s) == 8 && s.h == 8)
+        {
+            uint32_t rw[8][2];
+            uint2 fw[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+            {
+                ld_words<pixel, 2>(r + (int64_t)i * rs, rw[i]);
+                fw[i] = *smem_hint((const uint2*)(s.fenc + i * 64));
+            }
+#pragma unroll
+            for (int q = 0; q < 2; q++)
+            {
+                uint32_t fl[4], fr[4], ol[4], orr[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) { fl[i] = fw[4 * q + i].x; fr[i] = fw[4 * q + i].y; ol[i] = rw[4 * q + i][0]; orr[i] = rw[4 * q + i][1]; }
+                acc += satd4x4_packed_u8(fl, ol) + satd4x4_packed_u8(fr, orr);
+            }
+            return acc;
+        }
+    }
+#endif
 #ifdef ME_PACKED_SATD
     // the lookahead kernel: the packed-word SATD on rows from any address space (-2 % per launch, profiles/r02_staged_ab.txt)
     if constexpr (sizeof(pixel) == 1)
