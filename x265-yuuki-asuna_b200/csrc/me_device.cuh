@@ -1626,6 +1626,33 @@ __device__ __forceinline__ int thread_lowres_avg_cost(const MEState<pixel>& s, c
     // lowres CUs are 8 pixels wide: both 4x4 cells of a row group come from one batch of (A, B) row loads
     constexpr int NW8 = 8 * (int)sizeof(pixel) / 4, NW4 = NW8 / 2;
     int acc = 0;
+#if defined(ME_PACKED_SATD) && !defined(ME_LA_SATD8_OFF)
+    // 8-bit SATD (the quarter-pel candidates and the neighbour-MV candidates of the lookahead): the averaged rows ARE the packed words
+    // the packed-word SATD takes -- no unpacking into cells, no out-of-line cell cost; four rows (two cells) per batch
+    if constexpr (sizeof(pixel) == 1)
+    {
+        if (useSatd)
+        {
+#pragma unroll 1
+            for (int y0 = 0; y0 < s.h; y0 += 4)
+            {
+                uint32_t wl[4], wr[4], fl[4], fr[4];
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+                {
+                    uint32_t wa[2], wb[2];
+                    ld_words<pixel, 2>(A + (int64_t)(y0 + r) * s.stride, wa);
+                    ld_words<pixel, 2>(B + (int64_t)(y0 + r) * s.stride, wb);
+                    wl[r] = __vavgu4(wa[0], wb[0]); wr[r] = __vavgu4(wa[1], wb[1]);
+                    const uint2 f = *smem_hint((const uint2*)(s.fenc + (y0 + r) * 64));
+                    fl[r] = f.x; fr[r] = f.y;
+                }
+                acc += satd4x4_packed_u8(fl, wl) + satd4x4_packed_u8(fr, wr);
+            }
+            return acc;
+        }
+    }
+#endif
 #pragma unroll 1
     for (int y0 = 0; y0 < s.h; y0 += 4)
     {
