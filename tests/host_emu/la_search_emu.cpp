@@ -5,6 +5,7 @@
 #define ME_HOST_EMU 1
 #define ME_FORCE_THREAD 1
 #define ME_LOWRES_ONLY 1
+#define ME_BATCH_GROUPSUM 1          /* the candidate SADs of a search step through the register-only call (me_device.cuh thread_cand_sads) */
 #ifndef EMU_LA_PACKED_SATD_OFF
 #define ME_PACKED_SATD 1
 #endif

@@ -12,6 +12,7 @@
 // one-warp-per-CU kernel in lookahead_kernels.cu tops out at 0.85 ms per 32 640-CU field; profiles/r01_lookahead.txt).
 #define ME_FORCE_THREAD 1
 #define ME_LOWRES_ONLY 1
+#define ME_BATCH_GROUPSUM 1          /* the candidate SADs of a search step through the register-only call (me_device.cuh thread_cand_sads) */
 #ifndef LA_PACKED_SATD_OFF            /* packed-word 4x4 SATD (satd_packed.cuh) in the lowres search: -2 % (profiles/r02_staged_ab.txt) */
 #define ME_PACKED_SATD 1
 #endif

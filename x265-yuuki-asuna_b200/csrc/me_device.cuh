@@ -542,6 +542,7 @@ __device__ __forceinline__ int thread_satd(const MEState<pixel>& s, const pixel*
 #endif
 }
 
+__device__ __forceinline__ uint32_t pack_cand(int x, int y) { return ((uint32_t)x & 0xffffu) | ((uint32_t)y << 16); }
 #ifdef ME_WINDOW_CHECK
 // Frame-search form (me_ctu_kernels.cu): ONE out-of-line function costs the K (1..4) full-pel candidates of a search step.
 // The candidate offsets arrive packed in registers ((x & 0xffff) | (y << 16); as ox[] / oy[] arrays of a __noinline__ function
@@ -551,7 +552,6 @@ __device__ __forceinline__ int thread_satd(const MEState<pixel>& s, const pixel*
 // SAD + mvcost, and the callers (hexSearch, squareRefine, starPattern ...) stay small enough for the instruction caches
 // (inlined, this code made them 5-13 KB each and stall_no_instruction rose from 0.23 to 1.75 per issue,
 // profiles/r02_me_ctu_v1.txt).
-__device__ __forceinline__ uint32_t pack_cand(int x, int y) { return ((uint32_t)x & 0xffffu) | ((uint32_t)y << 16); }
 template<typename pixel>
 __device__ __noinline__ int4 thread_cand_costs(const MEState<pixel>& s, int K, uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3, bool addMvCost)
 {
@@ -591,6 +591,40 @@ __device__ __forceinline__ void warp_sad_k(const MEState<pixel>& s, int K, const
 {
     const int4 c = thread_cand_costs<pixel>(s, K, pack_cand(ox[0], oy[0]), K > 1 ? pack_cand(ox[1], oy[1]) : 0u, K > 2 ? pack_cand(ox[2], oy[2]) : 0u,
                                             K > 3 ? pack_cand(ox[3], oy[3]) : 0u, addMvCost);
+    costs[0] = c.x;
+    if (K > 1) costs[1] = c.y;
+    if (K > 2) costs[2] = c.z;
+    if (K > 3) costs[3] = c.w;
+}
+#elif defined(ME_FORCE_THREAD) && defined(ME_BATCH_GROUPSUM) && !defined(ME_SADK_ARRAYS)
+// Thread-only builds without the window test (the 2Nx2N frame search, the lookahead search): the same register-only calling form --
+// the K candidate offsets arrive packed in registers and the K sums return in an int4 (as arrays of an out-of-line function they
+// lived in local memory: every candidate began with two dependent LDL, 7 % of the stall samples of profiles/r02_me_frame_v11.txt).
+template<typename pixel>
+__device__ __noinline__ int4 thread_cand_sads(const MEState<pixel>& s, int K, uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3)
+{
+    int part[4] = { 0, 0, 0, 0 };
+#pragma unroll 1
+    for (int k = 0; k < K; k++)
+    {
+        const uint32_t pk = k == 0 ? p0 : (k == 1 ? p1 : (k == 2 ? p2 : p3));
+        const int mx = (int)(int16_t)(pk & 0xffffu), my = (int)pk >> 16;
+        const int v = thread_sad_any<pixel>(s, s.fref + mx + (int64_t)my * s.stride, s.stride);
+#pragma unroll
+        for (int j = 0; j < 4; j++) part[j] = j == k ? v : part[j];
+    }
+    for (int o = 1; o < s.groupSize; o <<= 1)
+    {
+#pragma unroll
+        for (int k = 0; k < 4; k++) part[k] += __shfl_xor_sync(s.groupMask, part[k], o);
+    }
+    return make_int4(part[0], part[1], part[2], part[3]);
+}
+template<typename pixel>
+__device__ __forceinline__ void warp_sad_k(const MEState<pixel>& s, int K, const int ox[4], const int oy[4], int costs[4])
+{
+    const int4 c = thread_cand_sads<pixel>(s, K, pack_cand(ox[0], oy[0]), K > 1 ? pack_cand(ox[1], oy[1]) : 0u, K > 2 ? pack_cand(ox[2], oy[2]) : 0u,
+                                           K > 3 ? pack_cand(ox[3], oy[3]) : 0u);
     costs[0] = c.x;
     if (K > 1) costs[1] = c.y;
     if (K > 2) costs[2] = c.z;
