@@ -1597,8 +1597,15 @@ __device__ __noinline__ int thread_chroma_cost(const MEState<pixel>& s, int qx, 
 #endif
 
 // MotionEstimate::subpelCompare (motion.cpp:1571-1599); useSatd selects cmp
+// In a thread-only build without the window test this is a trampoline (pick the full-pel cost or the sub-pel one, then add the lanes'
+// partials): inlined into its callers it saves a call level whose only memory traffic was re-loading the state.
+#if defined(ME_FORCE_THREAD) && !defined(ME_WINDOW_CHECK) && !defined(ME_SUBPEL_CALL)
+#define ME_SUBPEL_INLINE __forceinline__
+#else
+#define ME_SUBPEL_INLINE __noinline__
+#endif
 template<typename pixel>
-__device__ __noinline__ int subpel_compare(const MEState<pixel>& s, int qx, int qy, bool useSatd)
+__device__ ME_SUBPEL_INLINE int subpel_compare(const MEState<pixel>& s, int qx, int qy, bool useSatd)
 {
     const pixel* fref = s.fref + (qx >> 2) + (int64_t)(qy >> 2) * s.stride;
     const int xFrac = qx & 3, yFrac = qy & 3;
