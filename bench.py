@@ -665,9 +665,8 @@ class MixWorkload(Workload):
         f, refs = self.frame(t), self.refs_of(t)
         cptr, r0 = self.yptr(f), self.yptr(refs[0])
         HH = CTU_ROWS * CTU
-        for sz in LEVELS:
-            for kind, jd in self.ip_jobs_d[sz].items():
-                ctx.interp_dev(kind, 8, 8, sz, sz, r0, STRIDE, P(self.pred[sz]), W, P(jd), len(self.ip_jobs_h[sz][kind]), 0)
+        ctx.interp_multi_dev(8, 8, [(kind, sz, sz, r0, STRIDE, P(self.pred[sz]), W, P(jd), len(self.ip_jobs_h[sz][kind]))
+                                    for sz in LEVELS for kind, jd in self.ip_jobs_d[sz].items()])          # every level and filter kind in one launch
         for idx, N in TU_SIZES:
             qbits, add = quant_params(N)
             ctx.tu_pipeline_dev(idx, 8, 0, cptr, STRIDE, P(self.pred[16]), W, P(self.recon), W, W // N, HH // N, P(self.qtab), qbits, add, None, 40 << 5, 9,

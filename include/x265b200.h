@@ -215,6 +215,12 @@ typedef struct { int64_t srcOff, dstOff; int32_t idxX, idxY; } x265b200_interp_j
 int x265b200_interp_dev(x265b200_ctx* ctx, int kind, int taps, int depth, int w, int h,
                         const void* src, int64_t srcStride, void* dst, int64_t dstStride,
                         const x265b200_interp_job* jobs, int64_t n, int isRowExt);
+/* The same for several (kind, block size) segments at once -- e.g. the luma predictions of every PU level of a frame: segments the
+ * packed-word kernel takes (8-bit, 8 taps, HPP / VPP / HVPP, sizes and strides multiples of 4) share launches (up to 16 per launch),
+ * anything else is forwarded to x265b200_interp_dev segment by segment.  segsHost is a HOST array. */
+typedef struct { int32_t kind, w, h, isRowExt; const void* src; int64_t srcStride; void* dst; int64_t dstStride;
+                 const x265b200_interp_job* jobs; int64_t n; } x265b200_interp_seg;
+int x265b200_interp_multi_dev(x265b200_ctx* ctx, int taps, int depth, const x265b200_interp_seg* segsHost, int numSegs);
 
 /* ---- motion compensation driver: Predict::motionCompensation (common/predict.cpp:77-257) for n PUs.
  * Per job: CUData::clipMv on both MVs (cudata.cpp:1915-1928, from cuX/cuY and the descriptor's picture size / maxCUSize),

@@ -33,6 +33,7 @@ int main(void)
     S(x265b200_me_chroma); F(x265b200_me_chroma, fencCb); F(x265b200_me_chroma, fencStrideC); F(x265b200_me_chroma, refCbPlanes); F(x265b200_me_chroma, refStrideC);
     S(x265b200_la_hme); F(x265b200_la_hme, lowerStride); F(x265b200_la_hme, width4); F(x265b200_la_hme, lowerMvPool); F(x265b200_la_hme, searchMethod); F(x265b200_la_hme, range);
     S(x265b200_sad_group); F(x265b200_sad_group, ref);
+    S(x265b200_interp_seg); F(x265b200_interp_seg, isRowExt); F(x265b200_interp_seg, src); F(x265b200_interp_seg, dstStride); F(x265b200_interp_seg, jobs); F(x265b200_interp_seg, n);
     S(x265b200_me_frame_params); F(x265b200_me_frame_params, minCuSize); F(x265b200_me_frame_params, picWidth); F(x265b200_me_frame_params, chromaMarginX); F(x265b200_me_frame_params, numRefs);
     F(x265b200_me_frame_params, merange); F(x265b200_me_frame_params, maxCand); F(x265b200_me_frame_params, sliceTotalRows); F(x265b200_me_frame_params, refLagPixels);
     S(x265b200_me_frame_planes); F(x265b200_me_frame_planes, curCr); F(x265b200_me_frame_planes, curStrideC); F(x265b200_me_frame_planes, refY); F(x265b200_me_frame_planes, refStrideC);
@@ -67,7 +68,7 @@ def test_record_layouts_match_the_header():
         for (n, f), off in c.items():
             if n == name and f != "size":
                 assert dt.fields[f][1] == off, (name, f, dt.fields[f][1], off)
-    structs = {"x265b200_mc_desc": pkg.MC_DESC, "x265b200_me_chroma": pkg.ME_CHROMA, "x265b200_la_hme": pkg.LA_HME,
+    structs = {"x265b200_mc_desc": pkg.MC_DESC, "x265b200_me_chroma": pkg.ME_CHROMA, "x265b200_la_hme": pkg.LA_HME, "x265b200_interp_seg": pkg.INTERP_SEG,
                "x265b200_me_frame_params": pkg.ME_FRAME_PARAMS, "x265b200_me_frame_planes": pkg.ME_FRAME_PLANES}
     for name, st in structs.items():
         assert ctypes.sizeof(st) == c[(name, "size")], (name, ctypes.sizeof(st), c[(name, "size")])

@@ -118,6 +118,37 @@ def test_interp_batch_many_jobs(ctx):
         b.free()
 
 
+def test_interp_multi_segments_equal_single_launches(ctx):
+    """x265b200_interp_multi_dev: segments of different kinds / block sizes in shared launches (and one the packed-word kernel does not
+    take, forwarded) give what one x265b200_interp_dev call per segment gives."""
+    rng = np.random.default_rng(17)
+    W, H, S = 256, 128, 288
+    plane = rng.integers(0, 256, (H + 32) * S, dtype=np.int64).astype(np.uint8)
+    dP = ctx.to_device(plane)
+    specs = [(pkg.IP_HPP, 8, 8, 150), (pkg.IP_VPP, 16, 16, 90), (pkg.IP_HVPP, 32, 32, 40), (pkg.IP_HVPP, 8, 8, 0), (pkg.IP_HPP, 64, 64, 7),
+             (pkg.IP_HVPP, 12, 16, 33), (pkg.IP_HPS, 16, 16, 20), (pkg.IP_VPP, 8, 32, 25)] + [(pkg.IP_HPP, 16, 8, 11)] * 12
+    segs, singles, keep = [], [], []
+    for kind, w, h, n in specs:
+        job = np.zeros(max(n, 1), dtype=pkg.INTERP_JOB)[:n]
+        job["srcOff"] = (16 + rng.integers(0, H - h, n)) * S + 16 + rng.integers(0, W - w - 16, n)
+        job["dstOff"] = np.arange(n) * w * h
+        job["idxX"] = rng.integers(1, 4, n)
+        job["idxY"] = rng.integers(1, 4, n)
+        px = 2 if kind == pkg.IP_HPS else 1
+        dJ = ctx.to_device(job) if n else None
+        dA, dB = ctx.empty(max(n, 1) * w * h * px), ctx.empty(max(n, 1) * w * h * px)
+        segs.append((kind, w, h, dP, S, dA, w, dJ, n))
+        singles.append((kind, w, h, dB, dJ, n, px))
+        keep += [dA, dB] + ([dJ] if n else [])
+    ctx.interp_multi_dev(8, 8, segs)
+    for (kind, w, h, dB, dJ, n, px), sg in zip(singles, segs):
+        if n:
+            ctx.interp_dev(kind, 8, 8, w, h, dP, S, dB, w, dJ, n)
+            assert np.array_equal(sg[5].download(np.uint8), dB.download(np.uint8)), (kind, w, h, n)
+    for b in keep + [dP]:
+        b.free()
+
+
 @pytest.mark.parametrize("depth", [8, 10])
 def test_intra_pred_all_modes(ctx, depth):
     R = _ref(depth)

@@ -222,6 +222,24 @@ def _ctx_interp_dev(self, kind, taps, depth, w, h, dSrc, srcStride, dDst, dstStr
                                          _vp(dJobs), _i64(n), int(isRowExt)))
 
 
+class INTERP_SEG(ctypes.Structure):
+    """x265b200_interp_seg (include/x265b200.h)"""
+    _fields_ = [("kind", ctypes.c_int32), ("w", ctypes.c_int32), ("h", ctypes.c_int32), ("isRowExt", ctypes.c_int32),
+                ("src", ctypes.c_void_p), ("srcStride", ctypes.c_int64), ("dst", ctypes.c_void_p), ("dstStride", ctypes.c_int64),
+                ("jobs", ctypes.c_void_p), ("n", ctypes.c_int64)]
+
+
+def _ctx_interp_multi_dev(self, taps, depth, segs):
+    """segs: list of (kind, w, h, dSrc, srcStride, dDst, dstStride, dJobs, n[, isRowExt])"""
+    arr = (INTERP_SEG * len(segs))()
+    for i, sg in enumerate(segs):
+        kind, w, h, dSrc, srcStride, dDst, dstStride, dJobs, n = sg[:9]
+        arr[i].kind, arr[i].w, arr[i].h, arr[i].isRowExt = int(kind), int(w), int(h), int(sg[9]) if len(sg) > 9 else 0
+        arr[i].src, arr[i].srcStride, arr[i].dst, arr[i].dstStride = _vp(dSrc).value, int(srcStride), _vp(dDst).value, int(dstStride)
+        arr[i].jobs, arr[i].n = _vp(dJobs).value, int(n)
+    self._chk(self.L.x265b200_interp_multi_dev(self.h, int(taps), int(depth), arr, len(segs)))
+
+
 def _ctx_intra_pred_dev(self, depth, log2N, dNbr, dDst, dstStride, dJobs, n):
     self._chk(self.L.x265b200_intra_pred_dev(self.h, depth, log2N, _vp(dNbr), _vp(dDst), _i64(dstStride), _vp(dJobs), _i64(n)))
 
@@ -240,6 +258,7 @@ Ctx.quant_dev = _ctx_quant_dev
 Ctx.dequant_normal_dev = _ctx_dequant_normal_dev
 Ctx.dequant_scaling_dev = _ctx_dequant_scaling_dev
 Ctx.count_nonzero_dev = _ctx_count_nonzero_dev
+Ctx.interp_multi_dev = _ctx_interp_multi_dev
 Ctx.interp_dev = _ctx_interp_dev
 Ctx.intra_pred_dev = _ctx_intra_pred_dev
 Ctx.intra_filter_dev = _ctx_intra_filter_dev

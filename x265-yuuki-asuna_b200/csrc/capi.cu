@@ -108,6 +108,7 @@ int tu_pipeline_dev(Ctx*, int sizeIdx, int depth, int useDST, const void* fenc, 
 void host_dct_table(int N, int16_t* out);
 int interp_dev(Ctx*, int kind, int taps, int depth, int w, int h, const void* src, int64_t srcStride,
                void* dst, int64_t dstStride, const x265b200_interp_job* jobs, int64_t n, int isRowExt);
+int interp_multi_dev(Ctx*, int taps, int depth, const x265b200_interp_seg* segs, int numSegs);
 int intra_modes_dev(Ctx*, int depth, int log2N, const void* neighbours, void* dest, int bLuma, int64_t n);
 int mc_dev(Ctx*, int depth, const x265b200_mc_desc* d, const x265b200_mc_job* jobs, int64_t n, int bLuma, int bChroma);
 int sao_apply_dev(Ctx*, int kind, int depth, void* rec, int64_t stride, const x265b200_sao_job* jobs, int64_t n, int8_t* signBuf, const int8_t* offsets, int maxWidth);
@@ -494,6 +495,11 @@ int x265b200_dct_table(int N, int16_t* out)
 }
 
 // ---- interpolation / intra ----------------------------------------------------------------------
+int x265b200_interp_multi_dev(x265b200_ctx* ctx, int taps, int depth, const x265b200_interp_seg* segsHost, int numSegs)
+{
+    REQUIRE_CTX(ctx);
+    return interp_multi_dev(CTX(ctx), taps, depth, segsHost, numSegs);
+}
 int x265b200_interp_dev(x265b200_ctx* ctx, int kind, int taps, int depth, int w, int h, const void* src, int64_t srcStride,
                         void* dst, int64_t dstStride, const x265b200_interp_job* jobs, int64_t n, int isRowExt)
 {

@@ -163,6 +163,69 @@ interp_pp8_cell_kernel(InterpArgs p)
     interp_pp8_cell_thread(p, (int64_t)blockIdx.x * 128 + threadIdx.x, c_lumaFilter);
 }
 
+// Several (kind, block size) segments in ONE launch: the bench's MC stage is 12 short launches of this kernel (one per PU level and
+// filter kind, 8 us each, mostly ramp and tail); here a CTA finds its segment from the prefix sums of the segments' CTA counts.
+constexpr int IP_MAX_SEGS = 16;
+struct InterpMultiArgs { InterpArgs seg[IP_MAX_SEGS]; uint32_t firstCta[IP_MAX_SEGS + 1]; int numSegs; };
+__global__ void __launch_bounds__(128)
+interp_pp8_cell_multi_kernel(const __grid_constant__ InterpMultiArgs m)
+{
+    int k = 0;
+#pragma unroll 1
+    while (k + 1 < m.numSegs && blockIdx.x >= m.firstCta[k + 1]) k++;
+    interp_pp8_cell_thread(m.seg[k], (int64_t)(blockIdx.x - m.firstCta[k]) * 128 + threadIdx.x, c_lumaFilter);
+}
+
+static bool interp_cell_ok(int kind, int taps, int depth, int w, int h, int64_t srcStride)
+{
+    return depth == 8 && taps == 8 && !(w & 3) && !(h & 3) && !(srcStride & 3) &&
+           (kind == X265B200_IP_HPP || kind == X265B200_IP_VPP || kind == X265B200_IP_HVPP);
+}
+
+int interp_dev(Ctx* ctx, int kind, int taps, int depth, int w, int h, const void* src, int64_t srcStride,
+               void* dst, int64_t dstStride, const x265b200_interp_job* jobs, int64_t n, int isRowExt);
+
+int interp_multi_dev(Ctx* ctx, int taps, int depth, const x265b200_interp_seg* segs, int numSegs)
+{
+    if (numSegs <= 0) return 0;
+    if (!segs) { set_error("interp_multi: segs == NULL"); return -1; }
+    int done = 0;
+    while (done < numSegs)
+    {
+        // greedily pack consecutive segments the cell kernel takes into one launch; anything else goes through interp_dev
+        InterpMultiArgs m; m.numSegs = 0; m.firstCta[0] = 0;
+        int k = done;
+        for (; k < numSegs && m.numSegs < IP_MAX_SEGS; k++)
+        {
+            const x265b200_interp_seg& g = segs[k];
+            if (g.n <= 0) continue;
+            if (!interp_cell_ok(g.kind, taps, depth, g.w, g.h, g.srcStride)) break;
+            const int64_t ctas = (g.n * (g.w >> 2) * (g.h >> 2) + 127) / 128;
+            if ((int64_t)m.firstCta[m.numSegs] + ctas >= 0x7fffffffLL) break;
+            InterpArgs& a = m.seg[m.numSegs];
+            a.src = g.src; a.srcStride = g.srcStride; a.dst = g.dst; a.dstStride = g.dstStride; a.jobs = g.jobs; a.n = g.n;
+            a.kind = g.kind; a.taps = taps; a.depth = depth; a.w = g.w; a.h = g.h; a.isRowExt = g.isRowExt;
+            m.firstCta[m.numSegs + 1] = m.firstCta[m.numSegs] + (uint32_t)ctas;
+            m.numSegs++;
+        }
+        if (m.numSegs)
+        {
+            if (upload_filters(ctx)) return -1;
+            interp_pp8_cell_multi_kernel<<<m.firstCta[m.numSegs], 128, 0, ctx->stream>>>(m);
+            ctx->launches++;
+            if (check(cudaGetLastError(), "interp multi kernel launch")) return -1;
+        }
+        if (k < numSegs && k == done + 0 && !m.numSegs)
+        {
+            const x265b200_interp_seg& g = segs[k];
+            if (g.n > 0 && interp_dev(ctx, g.kind, taps, depth, g.w, g.h, g.src, g.srcStride, g.dst, g.dstStride, g.jobs, g.n, g.isRowExt)) return -1;
+            k++;
+        }
+        done = k;
+    }
+    return 0;
+}
+
 int interp_dev(Ctx* ctx, int kind, int taps, int depth, int w, int h, const void* src, int64_t srcStride,
                void* dst, int64_t dstStride, const x265b200_interp_job* jobs, int64_t n, int isRowExt)
 {
