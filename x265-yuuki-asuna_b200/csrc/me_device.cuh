@@ -1974,6 +1974,7 @@ struct MESearch
     }
 
     // me_hex2 (motion.cpp:845-944)
+#if defined(ME_WINDOW_CHECK) || defined(ME_HEX_MEMBERS) || defined(ME_LOWRES_ONLY)      /* the lookahead build measured 1 % slower with the register form */
     __device__ __noinline__ void hexSearch(int merange)
     {
         int costs[4];
@@ -2017,6 +2018,71 @@ struct MESearch
         bcost >>= 3;
         squareRefine();
     }
+#else
+    // The same walk with the search state in registers: as members of this object (which lives in local memory, like the MEState it
+    // points to) the best cost / MV, the range and the MV-cost operands were re-loaded after every out-of-line candidate call --
+    // three dependent loads (this -> s -> cost table) on the critical path of each of the ~8 steps (hexSearch: 27 M instructions but
+    // 9 % of the stall samples in profiles/r02_me_frame_v12.txt).
+    __device__ __noinline__ void hexSearch(int merange)
+    {
+        const MEState<pixel>& st = s;
+        const uint16_t* const costT = st.cost;
+        const int px = st.mvpx, py = st.mvpy;
+        const MV2 mn = mvmin, mx = mvmax;
+        MV2 b = bmv; int bc = bcost;
+        auto yok = [&](int y) { return (y >= mn.y) & (y <= mx.y); };
+        auto inr = [&](int x, int y) { return x >= mn.x && x <= mx.x && y >= mn.y && y <= mx.y; };
+        auto dir3 = [&](int dx0, int dy0, int dx1, int dy1, int dx2, int dy2, int costs[4]) {
+            int ox[4] = { b.x + dx0, b.x + dx1, b.x + dx2, 0 }, oy[4] = { b.y + dy0, b.y + dy1, b.y + dy2, 0 };
+            warp_sad_k<pixel>(st, 3, ox, oy, costs);
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+            {
+                const int ix = clip3i(-kMvTableHalf, kMvTableHalf, (ox[k] << 2) - px), iy = clip3i(-kMvTableHalf, kMvTableHalf, (oy[k] << 2) - py);
+                costs[k] += ((int)costT[ix] + (int)costT[iy]) & 0xffff;                    // mvcost(), bitcost.h:45
+            }
+        };
+        int costs[4];
+        dir3(-2, 0, -1, 2, 1, 2, costs);
+        bc <<= 3;
+        if (yok(b.y) && (costs[0] << 3) + 2 < bc) bc = (costs[0] << 3) + 2;
+        if (yok(b.y + 2))
+        {
+            if ((costs[1] << 3) + 3 < bc) bc = (costs[1] << 3) + 3;
+            if ((costs[2] << 3) + 4 < bc) bc = (costs[2] << 3) + 4;
+        }
+        dir3(2, 0, 1, -2, -1, -2, costs);
+        if (yok(b.y) && (costs[0] << 3) + 5 < bc) bc = (costs[0] << 3) + 5;
+        if (yok(b.y - 2))
+        {
+            if ((costs[1] << 3) + 6 < bc) bc = (costs[1] << 3) + 6;
+            if ((costs[2] << 3) + 7 < bc) bc = (costs[2] << 3) + 7;
+        }
+        if (bc & 7)
+        {
+            int dir = (bc & 7) - 2;
+            if (yok(b.y + c_hex2[dir + 1][1]))
+            {
+                b.x += c_hex2[dir + 1][0]; b.y += c_hex2[dir + 1][1];
+                for (int i = (merange >> 1) - 1; i > 0 && inr(b.x, b.y); i--)
+                {
+                    const int dy0 = c_hex2[dir][1], dy1 = c_hex2[dir + 1][1], dy2 = c_hex2[dir + 2][1];
+                    dir3(c_hex2[dir][0], dy0, c_hex2[dir + 1][0], dy1, c_hex2[dir + 2][0], dy2, costs);
+                    bc &= ~7;
+                    if (yok(b.y + dy0) && (costs[0] << 3) + 1 < bc) bc = (costs[0] << 3) + 1;
+                    if (yok(b.y + dy1) && (costs[1] << 3) + 2 < bc) bc = (costs[1] << 3) + 2;
+                    if (yok(b.y + dy2) && (costs[2] << 3) + 3 < bc) bc = (costs[2] << 3) + 3;
+                    if (!(bc & 7)) break;
+                    dir += (bc & 7) - 2;
+                    dir = c_mod6m1[dir + 1];
+                    b.x += c_hex2[dir + 1][0]; b.y += c_hex2[dir + 1][1];
+                }
+            }
+        }
+        bmv = b; bcost = bc >> 3;
+        squareRefine();
+    }
+#endif
 
     // two-point refinement after a distance-1 star result (motion.cpp:1151-1166, :1225-1235)
     __device__ __forceinline__ void twoPoint(int bPointNr)
