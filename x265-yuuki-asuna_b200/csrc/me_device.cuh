@@ -2542,7 +2542,7 @@ __device__ int motion_estimate(const MEState<pixel>& s, MV2 mvmin, MV2 mvmax, MV
     {
         bool hpelSatd = wl.hpel_satd != 0;
         if (hpelSatd)
-            bcost = subpel_compare<pixel>(s, bmv.x, bmv.y, true) + mvcost(s, bmv.x, bmv.y);
+            { const int mc = mvcost(s, bmv.x, bmv.y); bcost = subpel_compare<pixel>(s, bmv.x, bmv.y, true) + mc; }
         for (int iter = 0; iter < wl.hpel_iters; iter++)
         {
             int bdir = 0;
@@ -2550,14 +2550,15 @@ __device__ int motion_estimate(const MEState<pixel>& s, MV2 mvmin, MV2 mvmax, MV
             {
                 int qx = bmv.x + c_square1[i][0] * 2, qy = bmv.y + c_square1[i][1] * 2;
                 if ((qy < qmvmin.y) | (qy > qmvmax.y)) continue;
-                int cost = subpel_compare<pixel>(s, qx, qy, hpelSatd) + mvcost(s, qx, qy);
+                int cost = mvcost(s, qx, qy);                           // first: its table loads are in flight under the interpolation
+                cost += subpel_compare<pixel>(s, qx, qy, hpelSatd);
                 if (cost < bcost) { bcost = cost; bdir = i; }
             }
             if (bdir) { bmv.x += c_square1[bdir][0] * 2; bmv.y += c_square1[bdir][1] * 2; }
             else break;
         }
         if (!hpelSatd)
-            bcost = subpel_compare<pixel>(s, bmv.x, bmv.y, true) + mvcost(s, bmv.x, bmv.y);
+            { const int mc = mvcost(s, bmv.x, bmv.y); bcost = subpel_compare<pixel>(s, bmv.x, bmv.y, true) + mc; }
         for (int iter = 0; iter < wl.qpel_iters; iter++)
         {
             int bdir = 0;
@@ -2565,7 +2566,8 @@ __device__ int motion_estimate(const MEState<pixel>& s, MV2 mvmin, MV2 mvmax, MV
             {
                 int qx = bmv.x + c_square1[i][0], qy = bmv.y + c_square1[i][1];
                 if ((qy < qmvmin.y) | (qy > qmvmax.y)) continue;
-                int cost = subpel_compare<pixel>(s, qx, qy, true) + mvcost(s, qx, qy);
+                int cost = mvcost(s, qx, qy);                           // first: its table loads are in flight under the interpolation
+                cost += subpel_compare<pixel>(s, qx, qy, true);
                 if (cost < bcost) { bcost = cost; bdir = i; }
             }
             if (bdir) { bmv.x += c_square1[bdir][0]; bmv.y += c_square1[bdir][1]; }
