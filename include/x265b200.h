@@ -254,7 +254,9 @@ int x265b200_mc_dev(x265b200_ctx* ctx, int depth, const x265b200_mc_desc* desc, 
  *     E2       processSaoCUE2(rec, bufft = buf0, buff1 = buf1, offsetEo, width, stride)
  *     E3       processSaoCUE3(rec, upBuff1 = buf0, offsetEo, stride, startX, endX = width)
  *     B0       processSaoCUB0(rec, offsetBo[32], ctuWidth = width, ctuHeight = height, stride)
- *     maxWidth = largest job.width (<= 256) of the launch.
+ *     maxWidth = largest job.width (<= 256) of the launch; it sizes the CTAs (one thread per column), so the edge-offset kinds do NOT
+ *     process columns at or beyond it -- a job wider than maxWidth is the caller's error (the jobs live in device memory, the host cannot
+ *     check them; CTUs are at most 64 wide, the adapter passes the slot's own width).
  *   statistics (x265b200_sao_stats_dev), replaces primitives.saoCuStats* (primitives.h:351-355; sao.cpp:1762-1926):
  *     BO / E0 / E1 (upBuff1 = buf0) / E2 (upBuff1 = buf0, upBufft = buf1) / E3 (upBuff1 = buf0), endX = width, endY = height;
  *     the sign buffers end in the state the row-by-row C loops leave them in. */
