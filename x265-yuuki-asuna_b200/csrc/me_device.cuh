@@ -1633,7 +1633,10 @@ __device__ ME_SUBPEL_INLINE int subpel_compare(const MEState<pixel>& s, int qx, 
 #else
         if (!(xFrac | yFrac))
             return useSatd ? warp_satd<pixel>(s, fref, s.stride) : warp_sad_block<pixel>(s, fref, s.stride);
-        return group_sum<pixel>(s, thread_subpel_cost<pixel>(s, fref, xFrac, yFrac, useSatd));
+        const int gs = s.groupSize; const unsigned gm = s.groupMask;          // read before the call: not re-loaded on its critical path
+        int v = thread_subpel_cost<pixel>(s, fref, xFrac, yFrac, useSatd);
+        for (int o = 1; o < gs; o <<= 1) v += __shfl_xor_sync(gm, v, o);
+        return v;
 #endif
     }
 #ifndef ME_FORCE_THREAD
@@ -2079,8 +2082,31 @@ struct MESearch
                 }
             }
         }
-        bmv = b; bcost = bc >> 3;
-        squareRefine();
+        bc >>= 3;
+        // square refine (motion.cpp:933-943), same registers
+        auto dir4 = [&](int dx0, int dy0, int dx1, int dy1, int dx2, int dy2, int dx3, int dy3, int costs[4]) {
+            int ox[4] = { b.x + dx0, b.x + dx1, b.x + dx2, b.x + dx3 }, oy[4] = { b.y + dy0, b.y + dy1, b.y + dy2, b.y + dy3 };
+            warp_sad_k<pixel>(st, 4, ox, oy, costs);
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+            {
+                const int ix = clip3i(-kMvTableHalf, kMvTableHalf, (ox[k] << 2) - px), iy = clip3i(-kMvTableHalf, kMvTableHalf, (oy[k] << 2) - py);
+                costs[k] += ((int)costT[ix] + (int)costT[iy]) & 0xffff;
+            }
+        };
+        int sq = 0;
+        dir4(0, -1, 0, 1, -1, 0, 1, 0, costs);
+        if (yok(b.y - 1) && costs[0] < bc) { bc = costs[0]; sq = 1; }
+        if (yok(b.y + 1) && costs[1] < bc) { bc = costs[1]; sq = 2; }
+        if (costs[2] < bc) { bc = costs[2]; sq = 3; }
+        if (costs[3] < bc) { bc = costs[3]; sq = 4; }
+        dir4(-1, -1, -1, 1, 1, -1, 1, 1, costs);
+        if (yok(b.y - 1) && costs[0] < bc) { bc = costs[0]; sq = 5; }
+        if (yok(b.y + 1) && costs[1] < bc) { bc = costs[1]; sq = 6; }
+        if (yok(b.y - 1) && costs[2] < bc) { bc = costs[2]; sq = 7; }
+        if (yok(b.y + 1) && costs[3] < bc) { bc = costs[3]; sq = 8; }
+        b.x += c_square1[sq][0]; b.y += c_square1[sq][1];
+        bmv = b; bcost = bc;
     }
 #endif
 
