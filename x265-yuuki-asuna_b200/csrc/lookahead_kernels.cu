@@ -169,6 +169,7 @@ __device__ __forceinline__ void lowres_mc_arr(const pixel* const planes[4], int6
 // ---------------------------------------------------------------------------------------------
 // lowresIntraEstimate (slicetype.cpp:696-805), four lanes per 8x8 CU
 // ---------------------------------------------------------------------------------------------
+// [host-testable: tests/test_la_intra_cell_cpu.py compiles the functions between these markers for the CPU]
 __device__ __forceinline__ int la_intra_pixel(const int* s /* 33 neighbours */, int mode, int bFilter, int y, int x, int dcVal, int depth)
 {
     // N = 8 specialisation of intrapred.cpp:69-204 (see intra_kernels.cu for the general form)
@@ -304,6 +305,7 @@ __device__ __noinline__ int la_intra_ang_cell_cost(const int* smp, const int* fl
     return t >> 1;
 }
 
+// [host-testable end]
 // FOUR LANES PER CU: a lane owns one 4x4 cell of the 8x8 CU (pu[LUMA_8x8].satd is the sum of its four 4x4 Hadamard costs,
 // pixel.cpp:210-261), predicts only that cell for every mode tried and the four partial costs meet in two shuffles, so the
 // lanes of a CU hold identical costs and walk the mode decision together.  The raw and the 1:2:1-filtered neighbour arrays of
