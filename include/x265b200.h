@@ -535,6 +535,10 @@ typedef struct {
     uint64_t fencSum, fencSsd, refSum, refSsd;
 } x265b200_la_weight_job;
 typedef struct { int32_t isWeighted, inputWeight, log2WeightDenom, inputOffset; uint32_t origscore, score; } x265b200_la_weight;
+/* The host half of the above on its own (no GPU needed, like x265b200_bitcost_table): out = { measure, curScale, curDenom, curOffset, finScale,
+ * finDenom, identity } -- measure 0 = the early termination of slicetype.cpp:895-897; (curScale, curDenom, curOffset) = the candidate the
+ * second weightCostLuma pass measures; (finScale, finDenom, curOffset) = the weight applied when the candidate is accepted. */
+int x265b200_la_weight_guess(int depth, int width, int lines, uint64_t fencSum, uint64_t fencSsd, uint64_t refSum, uint64_t refSsd, int32_t out[7]);
 int x265b200_la_weights_analyse_dev(x265b200_ctx* ctx, int depth, const x265b200_la_weight_job* jobsHost, int numJobs,
                                     int64_t stride, int paddedLines, int64_t padOffset, int width, int lines, x265b200_la_weight* out);
 int x265b200_lowres_init_dev(x265b200_ctx* ctx, int depth, const void* src, int64_t srcStride,

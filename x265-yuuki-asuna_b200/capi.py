@@ -405,6 +405,16 @@ def _ctx_la_estimate_dev(self, depth, dPlanes, stride, wcu, hcu, triples, dMvPoo
                                               _vp(dRowSatds), _vp(dSums), ctypes.c_double(lam), int(lookaheadSlices), _vp(dWeights)))
 
 
+def la_weight_guess(depth, width, lines, fencSum, fencSsd, refSum, refSsd):
+    """x265b200_la_weight_guess (host only): dict(measure, curScale, curDenom, curOffset, finScale, finDenom, identity)"""
+    L = load()
+    out = (ctypes.c_int32 * 7)()
+    if L.x265b200_la_weight_guess(int(depth), int(width), int(lines), ctypes.c_uint64(fencSum), ctypes.c_uint64(fencSsd),
+                                  ctypes.c_uint64(refSum), ctypes.c_uint64(refSsd), out) != 0:
+        raise X265B200Error(L.x265b200_last_error().decode())
+    return dict(zip(("measure", "curScale", "curDenom", "curOffset", "finScale", "finDenom", "identity"), [int(v) for v in out]))
+
+
 def _ctx_la_weights_analyse_dev(self, depth, jobs, stride, paddedLines, padOffset, width, lines, dOut):
     """jobs: numpy array of LA_WEIGHT_JOB (host); dOut: device array of LA_WEIGHT records"""
     j = np.ascontiguousarray(jobs, dtype=LA_WEIGHT_JOB)

@@ -172,6 +172,7 @@ int la_estimate_dev(Ctx*, int depth, const void* const* planes, int64_t stride, 
                     const x265b200_la_triple* triplesHost, int numTriples, int32_t* mvPool, int32_t* mvCostPool,
                     const int32_t* const* intraCost, const int32_t* const* invQscale, uint16_t* lowresCosts, int32_t* rowSatds, int32_t* sums,
                     double lambda, int maxSlices, int lookaheadSlices, const x265b200_la_hme* hme, const x265b200_la_weight* weights);
+void la_weight_guess(int depth, int width, int lines, uint64_t fencSum, uint64_t fencSsd, uint64_t refSum, uint64_t refSsd, int out[7]);
 int la_weights_analyse_dev(Ctx*, int depth, const x265b200_la_weight_job* jobsHost, int numJobs, int64_t stride, int paddedLines, int64_t padOffset,
                            int width, int lines, x265b200_la_weight* out);
 int sub_ps_plane_dev(Ctx*, int depth, const void* a, int64_t strideA, const void* b, int64_t strideB, int16_t* dst, int64_t dstStride, int w, int h);
@@ -873,6 +874,12 @@ int x265b200_la_estimate_dev(x265b200_ctx* ctx, int depth, const void* const* pl
     REQUIRE_CTX(ctx);
     return la_estimate_dev(CTX(ctx), depth, planes, stride, widthInCU, heightInCU, triplesHost, numTriples, mvPool, mvCostPool,
                            intraCost, invQscale, lowresCosts, rowSatds, sums, lambda, 1, lookaheadSlices, nullptr, weights);
+}
+int x265b200_la_weight_guess(int depth, int width, int lines, uint64_t fencSum, uint64_t fencSsd, uint64_t refSum, uint64_t refSsd, int32_t out[7])
+{
+    if (!out || width <= 0 || lines <= 0 || depth < 8) { set_error("la_weight_guess: bad arguments"); return -1; }
+    la_weight_guess(depth, width, lines, fencSum, fencSsd, refSum, refSsd, out);
+    return 0;
 }
 int x265b200_la_weights_analyse_dev(x265b200_ctx* ctx, int depth, const x265b200_la_weight_job* jobsHost, int numJobs,
                                     int64_t stride, int paddedLines, int64_t padOffset, int width, int lines, x265b200_la_weight* out)

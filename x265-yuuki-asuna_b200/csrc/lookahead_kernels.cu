@@ -693,6 +693,46 @@ la_weight_planes_kernel(const LAWeightDev* jobs, x265b200_la_weight* out, int64_
     else for (int e = 0; e < V && i0 + e < count; e++) dst[i0 + e] = v[e];
 }
 
+// The host half of weightsAnalyse (slicetype.cpp:886-933): the float scale / offset guess in the reference's operation order (no
+// contraction: -ffp-contract=off in the Makefile).  out = { measure (0: early termination :895-897), curScale, curDenom, curOffset (the
+// candidate the second weightCostLuma pass measures, :923), finScale, finDenom (the same weight over the smaller denominator, :926-933;
+// the candidate only survives when it beat the unweighted cost, so the reduction applies to it), identity (weight 1, offset 0: :935) }.
+void la_weight_guess(int depth, int width, int lines, uint64_t fencSum, uint64_t fencSsd, uint64_t refSum, uint64_t refSsd, int out[7])
+{
+    for (int i = 0; i < 7; i++) out[i] = 0;
+    const float epsilon = 1.f / 128.f;
+    float guessScale, fencMean, refMean;
+    if (fencSsd && refSsd) guessScale = sqrtf((float)fencSsd / refSsd);
+    else guessScale = 1.0f;
+    fencMean = (float)fencSum / (lines * width) / (1 << (depth - 8));
+    refMean = (float)refSum / (lines * width) / (1 << (depth - 8));
+    if (fabsf(refMean - fencMean) < 0.5f && fabsf(1.f - guessScale) < epsilon) return;
+    out[0] = 1;
+    // WeightParam::setFromWeightAndOffset(w, 0, 7, true) (slice.h:304-316)
+    int minscale = (int)(guessScale * 128 + 0.5f), mindenom = 7;
+    while (mindenom > 0 && minscale > 127) { mindenom--; minscale >>= 1; }
+    minscale = minscale < 127 ? minscale : 127;
+    int curScale = minscale;
+    int curOffset = (int)(fencMean - refMean * curScale / (1 << mindenom) + 0.5f);
+    if (curOffset < -128 || curOffset > 127)
+    {
+        curOffset = curOffset < -128 ? -128 : 127;
+        curScale = (int)((1 << mindenom) * (fencMean - curOffset) / refMean + 0.5f);
+        curScale = curScale < 0 ? 0 : (curScale > 127 ? 127 : curScale);
+    }
+    out[1] = curScale; out[2] = mindenom; out[3] = curOffset;
+    int fs = curScale, fd = mindenom;
+    if (fd > 0 && !(fs & 1))
+    {
+        int idx = 0;
+        if (fs) while (!((fs >> idx) & 1)) idx++; else idx = 32;
+        int sh = idx < fd ? idx : fd;
+        fd -= sh; fs >>= sh;
+    }
+    out[4] = fs; out[5] = fd;
+    out[6] = (fs == 1 << fd && curOffset == 0);
+}
+
 int la_weights_analyse_dev(Ctx* ctx, int depth, const x265b200_la_weight_job* jobsHost, int numJobs, int64_t stride, int paddedLines, int64_t padOffset,
                            int width, int lines, x265b200_la_weight* out)
 {
@@ -713,39 +753,11 @@ int la_weights_analyse_dev(Ctx* ctx, int depth, const x265b200_la_weight_job* jo
             vec = vec && !(((uintptr_t)J.refBuffer[k] | (uintptr_t)J.weighted[k]) & 15);
         }
         if (!J.fencPlane0 || !J.intraCost) { set_error("la_weights_analyse: job %d source is NULL", n); return -1; }
-        // slicetype.cpp:886-897, float arithmetic in the reference's order (no contraction: -ffp-contract=off in the Makefile)
-        const float epsilon = 1.f / 128.f;
-        float guessScale, fencMean, refMean;
-        if (J.fencSsd && J.refSsd) guessScale = sqrtf((float)J.fencSsd / J.refSsd);
-        else guessScale = 1.0f;
-        fencMean = (float)J.fencSum / (lines * width) / (1 << (depth - 8));
-        refMean = (float)J.refSum / (lines * width) / (1 << (depth - 8));
-        if (fabsf(refMean - fencMean) < 0.5f && fabsf(1.f - guessScale) < epsilon) continue;           // early termination: measure = 0
+        int g[7];
+        la_weight_guess(depth, width, lines, J.fencSum, J.fencSsd, J.refSum, J.refSsd, g);
+        if (!g[0]) continue;                                                                           // early termination: measure = 0
         d.measure = 1; any = true;
-        // WeightParam::setFromWeightAndOffset(w, 0, 7, true) (slice.h:304-316)
-        int minscale = (int)(guessScale * 128 + 0.5f), mindenom = 7;
-        while (mindenom > 0 && minscale > 127) { mindenom--; minscale >>= 1; }
-        minscale = minscale < 127 ? minscale : 127;
-        int curScale = minscale;
-        int curOffset = (int)(fencMean - refMean * curScale / (1 << mindenom) + 0.5f);
-        if (curOffset < -128 || curOffset > 127)
-        {
-            curOffset = curOffset < -128 ? -128 : 127;
-            curScale = (int)((1 << mindenom) * (fencMean - curOffset) / refMean + 0.5f);
-            curScale = curScale < 0 ? 0 : (curScale > 127 ? 127 : curScale);
-        }
-        d.curScale = curScale; d.curDenom = mindenom; d.curOffset = curOffset;
-        // the candidate only survives when it beat the unweighted cost (found), so the denominator reduction (:926-933) applies to it
-        int fs = curScale, fd = mindenom;
-        if (fd > 0 && !(fs & 1))
-        {
-            int idx = 0;
-            if (fs) while (!((fs >> idx) & 1)) idx++; else idx = 32;
-            int sh = idx < fd ? idx : fd;
-            fd -= sh; fs >>= sh;
-        }
-        d.finScale = fs; d.finDenom = fd;
-        d.identity = (fs == 1 << fd && curOffset == 0);
+        d.curScale = g[1]; d.curDenom = g[2]; d.curOffset = g[3]; d.finScale = g[4]; d.finDenom = g[5]; d.identity = g[6];
     }
     void* dJobsV = nullptr;
     if (scratch_dev(ctx, 5, sizeof(LAWeightDev) * numJobs, &dJobsV)) return -1;
